@@ -1,0 +1,255 @@
+"""BodyModel — drop-in for humor/body_model/body_model.py:11-115 on the fused sm_100a LBS kernels.
+
+Same constructor and ``forward`` signature, same output struct (``v f betas Jtr pose_body full_pose
+pose_hand``), same attributes the reference's callers read (``model_type``, ``num_joints``,
+``bm.faces_tensor``, ``use_vtx_selector``).  The arithmetic of smplx==0.1.28 (``lbs``,
+``SMPLH.forward``, ``VertexJointSelector``) runs in csrc/lbs.cu; there is no CPU path.
+Scope: SMPL+H (the only model HuMoR supports, run_fitting.py:356-358) with identity hands
+(``pose_hand=None`` + ``flat_hand_mean=True``, body_model.py:56-57,82-83).
+"""
+import ctypes as C
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _ext
+
+NUM_VERTS = 6890
+NUM_JOINTS = 52
+KF = 208
+# smplx.vertex_ids.vertex_ids['smplh'] in VertexJointSelector order
+EXTRA_VERTEX_IDS = [332, 6260, 2800, 4071, 583, 3216, 3226, 3387, 6617, 6624, 6787,
+                    2746, 2319, 2445, 2556, 2673, 6191, 5782, 5905, 6016, 6133]
+# humor/body_model/utils.py:17-19
+KEYPT_VERTS = [4404, 920, 3076, 3169, 823, 4310, 1010, 1085, 4495, 4569, 6615, 3217, 3313, 6713,
+               6785, 3383, 6607, 3207, 1241, 1508, 4797, 4122, 1618, 1569, 5135, 5040, 5691, 5636,
+               5404, 2230, 2173, 2108, 134, 3645, 6543, 3123, 3024, 4194, 1306, 182, 3694, 4294, 744]
+
+
+class Struct(object):
+    def __init__(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+
+def pack_smplh(asset, num_betas=16):
+    """numpy packing of the model constants into the layouts of include/humor_b200.h (HbLbsModel)."""
+    if num_betas > 16:
+        raise NotImplementedError('humor_b200 LBS kernels are built for <= 16 betas (HuMoR uses 16)')
+    vt = np.asarray(asset['v_template'], np.float64)
+    V = vt.shape[0]
+    if V != NUM_VERTS:
+        raise ValueError(f'expected an SMPL+H mesh with {NUM_VERTS} vertices, got {V}')
+    sd = np.asarray(asset['shapedirs'], np.float64)[:, :, :num_betas]          # (V,3,nb)
+    pd = np.asarray(asset['posedirs'], np.float64)                            # (V,3,459)
+    if pd.shape[-1] < 189:
+        raise ValueError('posedirs must hold at least the 21 body joints (189 columns)')
+    Jreg = np.asarray(asset['J_regressor'], np.float64)                       # (52,V)
+    if Jreg.shape[0] != NUM_JOINTS:
+        raise ValueError('expected a 52-joint SMPL+H regressor')
+    W = np.asarray(asset['weights'], np.float64)                              # (V,52)
+    v3_ld = ((3 * V + 63) // 64) * 64
+    blend = np.zeros((KF, v3_ld), np.float32)
+    blend[:num_betas, :3 * V] = sd.reshape(3 * V, num_betas).T
+    blend[16:16 + 189, :3 * V] = pd[:, :, :189].reshape(3 * V, 189).T
+    j_template = (Jreg @ vt).astype(np.float32)                                # (52,3)
+    j_dirs = np.zeros((NUM_JOINTS * 3, 16), np.float32)
+    j_dirs[:, :num_betas] = np.einsum('jv,vcl->jcl', Jreg, sd).reshape(NUM_JOINTS * 3, num_betas)
+    nnz = (W != 0).sum(1)
+    wk = int(max(1, nnz.max()))
+    order = np.argsort(-np.abs(W), axis=1, kind='stable')[:, :wk]
+    w_idx = order.astype(np.int32)
+    w_val = np.take_along_axis(W, order, axis=1).astype(np.float32)
+    par = np.asarray(asset['kintree_table'])[0].astype(np.int64).copy()
+    par[0] = -1
+    return {
+        'num_verts': V, 'v3_ld': v3_ld, 'wk': wk,
+        'v_template': vt.astype(np.float32).reshape(-1), 'blend': blend,
+        'blend_t': np.ascontiguousarray(blend.T), 'j_template': j_template.reshape(-1), 'j_dirs': j_dirs,
+        'w_idx': np.ascontiguousarray(w_idx), 'w_val': np.ascontiguousarray(w_val),
+        'parents': par.astype(np.int32), 'extra_ids': np.asarray(EXTRA_VERTEX_IDS, np.int32),
+    }
+
+
+class LbsModel:
+    """Device copy of the packed constants + the ctypes HbLbsModel handed to the C-ABI."""
+
+    def __init__(self, packed, device):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('humor_b200.BodyModel needs a CUDA device (there is no CPU path)')
+        self.t = {k: torch.as_tensor(v).to(self.device).contiguous() for k, v in packed.items()
+                  if isinstance(v, np.ndarray)}
+        s = _ext.HbLbsModel()
+        s.num_verts, s.v3_ld, s.wk, s.reserved = packed['num_verts'], packed['v3_ld'], packed['wk'], 0
+        for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_val', 'parents', 'extra_ids'):
+            setattr(s, k, self.t[k].data_ptr())
+        self.struct = s
+        self._ws = {}
+        self._vlists = {}
+
+    def workspace(self, N):
+        ws = self._ws.get(N)
+        if ws is None:
+            nbytes = _ext.lib().humor_lbs_workspace_bytes(N)
+            ws = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+            self._ws[N] = ws
+        return ws
+
+    def vlist(self, ids):
+        key = tuple(ids)
+        t = self._vlists.get(key)
+        if t is None:
+            t = torch.tensor(list(ids), dtype=torch.int32, device=self.device)
+            self._vlists[key] = t
+        return t
+
+
+class _LbsFn(torch.autograd.Function):
+    """(root_orient, pose_body, betas, trans) -> (v_dense | None, v_sel | None, joints).
+
+    v_dense carries gradient only when ``dense_grad``; v_sel (the listed vertices) always does —
+    the Stage-III energies touch 43 key vertices + 73 joints, so their reverse pass skins only those.
+    """
+
+    @staticmethod
+    def forward(ctx, model, root_orient, pose_body, betas, trans, fpb, sel_ids, want_dense, dense_grad, njo):
+        _ext.require_cuda(root_orient, pose_body, betas, trans)
+        ro, pb, be, tr = (_ext.f32c(x) for x in (root_orient, pose_body, betas, trans))
+        N = ro.shape[0]
+        L = _ext.lib()
+        ws = model.workspace(N)
+        nl = C.c_int64(0)
+        joints = torch.empty(N, njo, 3, device=ro.device, dtype=torch.float32)
+        v_dense = v_sel = None
+        sel = model.vlist(sel_ids) if sel_ids is not None else None
+        if want_dense:
+            v_dense = torch.empty(N, model.struct.num_verts, 3, device=ro.device, dtype=torch.float32)
+            _ext.check(L.humor_lbs_fwd(C.byref(model.struct), N, fpb, _ext.ptr(ro), _ext.ptr(pb), _ext.ptr(be), _ext.ptr(tr),
+                                       _ext.ptr(ws), ws.numel() * 4, None, 0, _ext.ptr(v_dense), _ext.ptr(joints), njo,
+                                       C.byref(nl), _ext.stream_ptr()), 'humor_lbs_fwd')
+            if sel is not None:
+                v_sel = v_dense[:, sel.long()].contiguous()
+        else:
+            if sel is not None:
+                v_sel = torch.empty(N, sel.numel(), 3, device=ro.device, dtype=torch.float32)
+            _ext.check(L.humor_lbs_fwd(C.byref(model.struct), N, fpb, _ext.ptr(ro), _ext.ptr(pb), _ext.ptr(be), _ext.ptr(tr),
+                                       _ext.ptr(ws), ws.numel() * 4, _ext.ptr(sel), 0 if sel is None else sel.numel(),
+                                       _ext.ptr(v_sel), _ext.ptr(joints), njo, C.byref(nl), _ext.stream_ptr()), 'humor_lbs_fwd')
+        _ext.LaunchCounter.total += nl.value
+        ctx.model, ctx.fpb, ctx.sel, ctx.njo, ctx.dense_grad = model, fpb, sel, njo, dense_grad
+        ctx.betas_shape = betas.shape
+        ctx.save_for_backward(ro, pb, be, tr)
+        ctx.set_materialize_grads(False)
+        outs = []
+        if v_dense is None:
+            v_dense = torch.empty(0, device=ro.device)
+        if v_sel is None:
+            v_sel = torch.empty(0, device=ro.device)
+        if not dense_grad:
+            ctx.mark_non_differentiable(v_dense)
+        return v_dense, v_sel, joints
+
+    @staticmethod
+    def backward(ctx, d_dense, d_sel, d_joints):
+        ro, pb, be, tr = ctx.saved_tensors
+        model, N = ctx.model, ro.shape[0]
+        L = _ext.lib()
+        ws = model.workspace(N)
+        d_ro, d_pb, d_tr = torch.empty_like(ro), torch.empty_like(pb), torch.empty_like(tr)
+        d_be = torch.empty(N, 16, device=ro.device, dtype=torch.float32)
+        dj = _ext.f32c(d_joints) if d_joints is not None else None
+
+        def run(vlist, nv, dv, djoints, out):
+            nl = C.c_int64(0)
+            _ext.check(L.humor_lbs_bwd(C.byref(model.struct), N, ctx.fpb, _ext.ptr(ro), _ext.ptr(pb), _ext.ptr(be), _ext.ptr(tr),
+                                       _ext.ptr(ws), ws.numel() * 4, _ext.ptr(vlist), nv, _ext.ptr(dv), _ext.ptr(djoints),
+                                       ctx.njo, _ext.ptr(out[0]), _ext.ptr(out[1]), _ext.ptr(out[2]), _ext.ptr(out[3]),
+                                       C.byref(nl), _ext.stream_ptr()), 'humor_lbs_bwd')
+            _ext.LaunchCounter.total += nl.value
+
+        have_dense = ctx.dense_grad and d_dense is not None and d_dense.numel() > 0
+        have_sel = d_sel is not None and d_sel.numel() > 0 and ctx.sel is not None
+        outs = (d_ro, d_pb, d_be, d_tr)
+        if have_dense:
+            run(None, 0, _ext.f32c(d_dense), dj, outs)
+            if have_sel:
+                o2 = tuple(torch.empty_like(x) for x in outs)
+                run(ctx.sel, ctx.sel.numel(), _ext.f32c(d_sel), None, o2)
+                for a, b in zip(outs, o2):
+                    a += b
+        elif have_sel:
+            run(ctx.sel, ctx.sel.numel(), _ext.f32c(d_sel), dj, outs)
+        else:
+            run(None, 0, None, dj, outs)
+        nb = ctx.betas_shape[0]
+        d_betas = d_be.view(nb, -1, 16).sum(1) if ctx.fpb > 1 else d_be
+        d_betas = d_betas[:, :ctx.betas_shape[1]] if ctx.betas_shape[1] < 16 else d_betas
+        return None, d_ro, d_pb, d_betas, d_tr, None, None, None, None, None
+
+
+def lbs(model, root_orient, pose_body, betas, trans, frames_per_beta=1, sel_ids=None, want_dense=True,
+        dense_grad=True, num_joints_out=52):
+    if betas.shape[1] < 16:
+        betas = torch.nn.functional.pad(betas, (0, 16 - betas.shape[1]))
+    if root_orient.shape[0] != betas.shape[0] * frames_per_beta:
+        raise ValueError('betas rows * frames_per_beta must equal the number of frames')
+    return _LbsFn.apply(model, root_orient, pose_body, betas, trans, frames_per_beta, sel_ids, want_dense,
+                        dense_grad, num_joints_out)
+
+
+class BodyModel(nn.Module):
+    """Wrapper with the reference's interface (body_model.py:16-115)."""
+
+    def __init__(self, bm_path, num_betas=10, batch_size=1, num_expressions=10, use_vtx_selector=False,
+                 model_type='smplh'):
+        super().__init__()
+        if model_type != 'smplh':
+            raise NotImplementedError('Only SMPL+H is supported (as in HuMoR, run_fitting.py:356-358)')
+        asset = bm_path if isinstance(bm_path, dict) else dict(np.load(bm_path, encoding='latin1'))
+        self.model_type = model_type
+        self.num_joints = 51                       # smplx SMPLH.NUM_JOINTS
+        self.use_vtx_selector = use_vtx_selector
+        self.num_betas = num_betas
+        self.batch_size = batch_size
+        self._packed = pack_smplh(asset, num_betas)
+        self._model = None
+        self.bm = nn.Module()
+        self.bm.register_buffer('faces_tensor', torch.as_tensor(np.asarray(asset['f']).astype(np.int64)))
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        dev = self.bm.faces_tensor.device
+        if dev.type == 'cuda' and (self._model is None or self._model.device != dev):
+            self._model = LbsModel(self._packed, dev)
+        return self
+
+    @property
+    def lbs_model(self):
+        if self._model is None:
+            raise RuntimeError('BodyModel must be moved to a CUDA device first (.to("cuda")); there is no CPU path')
+        return self._model
+
+    def forward(self, root_orient=None, pose_body=None, pose_hand=None, pose_jaw=None, pose_eye=None, betas=None,
+                trans=None, dmpls=None, expression=None, return_dict=False, **kwargs):
+        assert dmpls is None
+        m = self.lbs_model
+        dev = m.device
+        given = [x for x in (root_orient, pose_body, betas, trans) if x is not None]
+        N = given[0].shape[0] if given else self.batch_size
+        z = lambda d: torch.zeros(N, d, device=dev, dtype=torch.float32)
+        root_orient = z(3) if root_orient is None else root_orient
+        pose_body = z(63) if pose_body is None else pose_body
+        betas = z(self.num_betas) if betas is None else betas
+        trans = z(3) if trans is None else trans
+        if pose_hand is not None and bool((pose_hand != 0).any()):
+            raise NotImplementedError('non-identity hand poses are outside the Stage-III path '
+                                      '(the reference always passes pose_hand=None, motion_optimizer.py:1087-1092)')
+        njo = 73 if self.use_vtx_selector else 52
+        v, _, J = lbs(m, root_orient, pose_body, betas, trans, 1, None, True, True, njo)
+        hands = z(90)
+        out = {'v': v, 'f': self.bm.faces_tensor, 'betas': betas, 'Jtr': J, 'pose_body': pose_body,
+               'full_pose': torch.cat([root_orient, pose_body, hands], 1), 'pose_hand': hands}
+        return out if return_dict else Struct(**out)

@@ -1,0 +1,24 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HB_OK 0
+#define HB_ERR_ARG 1001
+#define HB_ERR_WORKSPACE 1002
+
+// every launch is followed by this: the C-ABI returns the cudaError_t (non-zero) to the caller
+#define HB_LAUNCH_CHECK()                           \
+  do {                                              \
+    cudaError_t e__ = cudaGetLastError();           \
+    if (e__ != cudaSuccess) return (int)e__;        \
+  } while (0)
+#define HB_CUDA(x)                                  \
+  do {                                              \
+    cudaError_t e__ = (x);                          \
+    if (e__ != cudaSuccess) return (int)e__;        \
+  } while (0)
+
+namespace hb {
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace hb

@@ -1,0 +1,394 @@
+// SMPL+H linear blend skinning, forward and reverse (exact-fp32 FFMA path).
+// Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs
+// (humor/body_model/body_model.py:72-115; algorithm SURVEY.md Appendix A.1).
+//
+// Decomposition
+//   lbs_pose_kernel      per frame : Rodrigues x22, pose feature, rest joints from betas, kinematic chain,
+//                                    skinning transforms A[52][3x4], posed joints (+trans)
+//   lbs_skin_fwd_kernel  (vertex tile x frame tile): v_posed = v_template + [betas|pose_feat] . blend
+//                                    (one K=208 contraction: shape blend and pose blend fused), then
+//                                    sparse (ELL) skinning  v = sum_w w * (A_j [v_posed;1]) + trans
+//   lbs_skin_bwd_kernel  frame tile, loops vertex chunks: recompute v_posed, d v_posed, reduce
+//                                    dA[52][3x4], d feature[208], d trans without atomics (deterministic)
+//   lbs_pose_bwd_kernel  per frame : chain / Rodrigues reverse, d betas
+// (N,6890,4,4) skinning transforms, pose offsets and homogeneous copies that smplx materialises
+// (~1.2 MB/frame) never exist; per frame the only HBM traffic is the inputs, A (2.5 KB) and v.
+#include "common.cuh"
+#include "lbs_chain.cuh"
+#include "../../include/humor_b200.h"
+
+namespace hb {
+
+constexpr int SK_VT = 64;    // vertices per block tile
+constexpr int SK_FT = 64;    // frames per block tile (forward)
+constexpr int SK_FPT = 16;   // frames per thread (forward)
+constexpr int BW_FT = 16;    // frames per block (backward)
+
+struct LbsWs {
+  float *feat, *A, *dfeat, *dA, *dtr;
+  size_t total;
+};
+static LbsWs lbs_carve(float* base, int N) {
+  LbsWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += align_up(n, 64); return p; };
+  size_t Np = align_up((size_t)N, 64);
+  w.feat = take(Np * LBS_KF);
+  w.A = take(Np * 624);
+  w.dfeat = take(Np * LBS_KF);
+  w.dA = take(Np * 624);
+  w.dtr = take(Np * 4);
+  w.total = off;
+  return w;
+}
+
+__device__ __forceinline__ void rest_joints(const HbLbsModel& m, const float* __restrict__ beta, float* J) {
+  for (int e = 0; e < LBS_J * 3; ++e) {
+    float a = m.j_template[e];
+    const float* d = m.j_dirs + e * LBS_NB;
+#pragma unroll
+    for (int l = 0; l < LBS_NB; ++l) a = fmaf(d[l], beta[l], a);
+    J[e] = a;
+  }
+}
+
+__global__ void lbs_pose_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ root_orient,
+                                const float* __restrict__ pose_body, const float* __restrict__ betas,
+                                const float* __restrict__ trans, float* feat, float* A, float* joints, int njo) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* beta = betas + (size_t)(n / fpb) * LBS_NB;
+  float pose[66], J[LBS_J * 3], Jp[LBS_J * 3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pose[i] = root_orient[(size_t)n * 3 + i];
+  for (int i = 0; i < 63; ++i) pose[3 + i] = pose_body[(size_t)n * 63 + i];
+  rest_joints(m, beta, J);
+  float* f = feat ? feat + (size_t)n * LBS_KF : nullptr;
+  if (f) {
+#pragma unroll
+    for (int l = 0; l < LBS_NB; ++l) f[l] = beta[l];
+    f[205] = f[206] = f[207] = 0.f;
+  }
+  lbs_chain_fwd(pose, J, m.parents, f ? f + LBS_NB : nullptr, A ? A + (size_t)n * 624 : nullptr, Jp);
+  if (joints) {
+    float t0 = trans[(size_t)n * 3], t1 = trans[(size_t)n * 3 + 1], t2 = trans[(size_t)n * 3 + 2];
+    float* jo = joints + (size_t)n * njo * 3;
+    for (int j = 0; j < LBS_J; ++j) { jo[3 * j] = Jp[3 * j] + t0; jo[3 * j + 1] = Jp[3 * j + 1] + t1; jo[3 * j + 2] = Jp[3 * j + 2] + t2; }
+  }
+}
+
+// out[(n*out_fs) + slot*3 + c], slot = index within the vertex list (or the vertex id when dense)
+__global__ void __launch_bounds__(256)
+lbs_skin_fwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const float* __restrict__ A,
+                    const float* __restrict__ trans, const int* __restrict__ vlist, int nv, float* out, size_t out_fs) {
+  extern __shared__ __align__(16) float Fs[];              // [SK_FT][LBS_KF]
+  const int tid = threadIdx.x;
+  const int vi = tid % SK_VT, fg = tid / SK_VT;            // 4 frame groups x 16 frames
+  const int f0 = blockIdx.y * SK_FT;
+  const int slot = blockIdx.x * SK_VT + vi;
+  const bool vok = slot < nv;
+  const int vid = vok ? (vlist ? vlist[slot] : slot) : 0;
+  for (int i = tid; i < SK_FT * LBS_KF / 4; i += 256) {
+    int f = i / (LBS_KF / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f0 + f < N) v = reinterpret_cast<const float4*>(feat + (size_t)(f0 + f) * LBS_KF)[i % (LBS_KF / 4)];
+    reinterpret_cast<float4*>(Fs)[i] = v;
+  }
+  __syncthreads();
+  float acc[SK_FPT][3];
+#pragma unroll
+  for (int f = 0; f < SK_FPT; ++f) acc[f][0] = acc[f][1] = acc[f][2] = 0.f;
+  const float* bp = m.blend + (size_t)vid * 3;
+  const float* fs = Fs + (size_t)(fg * SK_FPT) * LBS_KF;
+  for (int k = 0; k < 205; k += 4) {            // rows 205..207 are padding (zero)
+    float p[4][3];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float* b = bp + (size_t)(k + kk) * m.v3_ld;
+      p[kk][0] = __ldg(b); p[kk][1] = __ldg(b + 1); p[kk][2] = __ldg(b + 2);
+    }
+#pragma unroll
+    for (int f = 0; f < SK_FPT; ++f) {
+      float4 fv = *reinterpret_cast<const float4*>(fs + f * LBS_KF + k);
+      const float q[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        acc[f][0] = fmaf(q[kk], p[kk][0], acc[f][0]);
+        acc[f][1] = fmaf(q[kk], p[kk][1], acc[f][1]);
+        acc[f][2] = fmaf(q[kk], p[kk][2], acc[f][2]);
+      }
+    }
+  }
+  if (!vok) return;
+  const float vt0 = m.v_template[vid * 3], vt1 = m.v_template[vid * 3 + 1], vt2 = m.v_template[vid * 3 + 2];
+  const int* wi = m.w_idx + (size_t)vid * m.wk;
+  const float* wv = m.w_val + (size_t)vid * m.wk;
+#pragma unroll 1
+  for (int f = 0; f < SK_FPT; ++f) {
+    const int n = f0 + fg * SK_FPT + f;
+    if (n >= N) break;
+    const float px = vt0 + acc[f][0], py = vt1 + acc[f][1], pz = vt2 + acc[f][2];
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    const float* An = A + (size_t)n * 624;
+    for (int w = 0; w < m.wk; ++w) {
+      const float wt = wv[w];
+      if (wt == 0.f) continue;
+      const float4* a = reinterpret_cast<const float4*>(An + wi[w] * 12);
+      const float4 r0 = __ldg(a), r1 = __ldg(a + 1), r2 = __ldg(a + 2);
+      ox = fmaf(wt, fmaf(r0.x, px, fmaf(r0.y, py, fmaf(r0.z, pz, r0.w))), ox);
+      oy = fmaf(wt, fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w))), oy);
+      oz = fmaf(wt, fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))), oz);
+    }
+    float* o = out + (size_t)n * out_fs + (size_t)slot * 3;
+    o[0] = ox + trans[(size_t)n * 3];
+    o[1] = oy + trans[(size_t)n * 3 + 1];
+    o[2] = oz + trans[(size_t)n * 3 + 2];
+  }
+}
+
+// One block owns BW_FT frames and walks over the vertex list in chunks of 64; all reductions over
+// vertices are thread-private (no atomics).  dv[(n*dv_fs) + slot*3 + c].
+__global__ void __launch_bounds__(256)
+lbs_skin_bwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const float* __restrict__ A,
+                    const int* __restrict__ vlist, int nv, const float* __restrict__ dv, size_t dv_fs,
+                    float* dfeat, float* dA, float* dtr, int accumulate) {
+  extern __shared__ __align__(16) float sm[];
+  float* Fs = sm;                              // [BW_FT][208]
+  float* GP = Fs + BW_FT * LBS_KF;             // [BW_FT][192]   d v_posed
+  float* Gs = GP + BW_FT * 192;                // [BW_FT][192]   d v
+  float* Ps = Gs + BW_FT * 192;                // [BW_FT][192]   v_posed
+  float* dAs = Ps + BW_FT * 192;               // [BW_FT][624]
+  const int tid = threadIdx.x;
+  const int f0 = blockIdx.x * BW_FT;
+  for (int i = tid; i < BW_FT * LBS_KF; i += 256) {
+    int f = i / LBS_KF;
+    Fs[i] = (f0 + f < N) ? feat[(size_t)(f0 + f) * LBS_KF + (i % LBS_KF)] : 0.f;
+  }
+  for (int i = tid; i < BW_FT * 624; i += 256) dAs[i] = 0.f;
+  float accF[BW_FT];
+#pragma unroll
+  for (int f = 0; f < BW_FT; ++f) accF[f] = 0.f;
+  float accT = 0.f;
+  __syncthreads();
+  const int vi = tid % 64, fq = tid / 64;      // phase 1: 4 frames per thread
+  for (int c0 = 0; c0 < nv; c0 += 64) {
+    const int slot = c0 + vi;
+    const bool vok = slot < nv;
+    const int vid = vok ? (vlist ? vlist[slot] : slot) : 0;
+    // ---- phase 1: v_posed and d v_posed for (4 frames, 1 vertex)
+    {
+      float acc[4][3];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) acc[f][0] = acc[f][1] = acc[f][2] = 0.f;
+      const float* bp = m.blend + (size_t)vid * 3;
+      for (int k = 0; k < 205; ++k) {
+        const float* b = bp + (size_t)k * m.v3_ld;
+        const float p0 = __ldg(b), p1 = __ldg(b + 1), p2 = __ldg(b + 2);
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          const float q = Fs[(fq * 4 + f) * LBS_KF + k];
+          acc[f][0] = fmaf(q, p0, acc[f][0]);
+          acc[f][1] = fmaf(q, p1, acc[f][1]);
+          acc[f][2] = fmaf(q, p2, acc[f][2]);
+        }
+      }
+      const float vt0 = m.v_template[vid * 3], vt1 = m.v_template[vid * 3 + 1], vt2 = m.v_template[vid * 3 + 2];
+      const int* wi = m.w_idx + (size_t)vid * m.wk;
+      const float* wv = m.w_val + (size_t)vid * m.wk;
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const int fl = fq * 4 + f, n = f0 + fl;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+        if (vok && n < N) {
+          const float* g = dv + (size_t)n * dv_fs + (size_t)slot * 3;
+          g0 = g[0]; g1 = g[1]; g2 = g[2];
+          const float* An = A + (size_t)n * 624;
+          for (int w = 0; w < m.wk; ++w) {
+            const float wt = wv[w];
+            if (wt == 0.f) continue;
+            const float* a = An + wi[w] * 12;
+            q0 = fmaf(wt, a[0] * g0 + a[4] * g1 + a[8] * g2, q0);
+            q1 = fmaf(wt, a[1] * g0 + a[5] * g1 + a[9] * g2, q1);
+            q2 = fmaf(wt, a[2] * g0 + a[6] * g1 + a[10] * g2, q2);
+          }
+        }
+        float* gp = GP + fl * 192 + vi * 3; gp[0] = q0; gp[1] = q1; gp[2] = q2;
+        float* gs = Gs + fl * 192 + vi * 3; gs[0] = g0; gs[1] = g1; gs[2] = g2;
+        float* ps = Ps + fl * 192 + vi * 3; ps[0] = vt0 + acc[f][0]; ps[1] = vt1 + acc[f][1]; ps[2] = vt2 + acc[f][2];
+      }
+    }
+    __syncthreads();
+    const int cn = min(64, nv - c0);
+    // ---- phase 2a: dA[f][j][r][c] += w * g[r] * [p;1][c]     thread = (frame, element of the 3x4)
+    {
+      const int f = tid / 16, e = tid % 16;
+      if (e < 12) {
+        const int r = e / 4, c = e % 4;
+        float* dst = dAs + f * 624 + e;
+        for (int i = 0; i < cn; ++i) {
+          const int v2 = vlist ? vlist[c0 + i] : c0 + i;
+          const float gr = Gs[f * 192 + i * 3 + r];
+          const float pc = c < 3 ? Ps[f * 192 + i * 3 + c] : 1.f;
+          const float gpc = gr * pc;
+          const int* wi = m.w_idx + (size_t)v2 * m.wk;
+          const float* wv = m.w_val + (size_t)v2 * m.wk;
+          for (int w = 0; w < m.wk; ++w) {
+            const float wt = __ldg(wv + w);
+            if (wt != 0.f) dst[__ldg(wi + w) * 12] += wt * gpc;
+          }
+        }
+      }
+    }
+    // ---- phase 2b: d feat[f][k] += sum_vc GP[f][vc] * blend_t[vc][k]   thread = k
+    if (tid < LBS_KF) {
+      for (int i = 0; i < cn; ++i) {
+        const int v2 = vlist ? vlist[c0 + i] : c0 + i;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float bt = __ldg(m.blend_t + ((size_t)v2 * 3 + c) * LBS_KF + tid);
+#pragma unroll
+          for (int f = 0; f < BW_FT; ++f) accF[f] = fmaf(GP[f * 192 + i * 3 + c], bt, accF[f]);
+        }
+      }
+    } else if (tid < LBS_KF + BW_FT * 3) {
+      // ---- phase 2c: d trans[f][c] += sum_i g
+      const int f = (tid - LBS_KF) / 3, c = (tid - LBS_KF) % 3;
+      for (int i = 0; i < cn; ++i) accT += Gs[f * 192 + i * 3 + c];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < BW_FT * 624; i += 256) {
+    int f = i / 624;
+    if (f0 + f < N) {
+      float* d = dA + (size_t)(f0 + f) * 624 + (i % 624);
+      *d = accumulate ? *d + dAs[i] : dAs[i];
+    }
+  }
+  if (tid < LBS_KF) {
+#pragma unroll
+    for (int f = 0; f < BW_FT; ++f)
+      if (f0 + f < N) {
+        float* d = dfeat + (size_t)(f0 + f) * LBS_KF + tid;
+        *d = accumulate ? *d + accF[f] : accF[f];
+      }
+  } else if (tid < LBS_KF + BW_FT * 3) {
+    const int f = (tid - LBS_KF) / 3, c = (tid - LBS_KF) % 3;
+    if (f0 + f < N) {
+      float* d = dtr + (size_t)(f0 + f) * 4 + c;
+      *d = accumulate ? *d + accT : accT;
+    }
+  }
+}
+
+__global__ void lbs_pose_bwd_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ root_orient,
+                                    const float* __restrict__ pose_body, const float* __restrict__ betas,
+                                    const float* __restrict__ dfeat, const float* __restrict__ dA,
+                                    const float* __restrict__ dtr, const float* __restrict__ djoints, int njo,
+                                    float* d_root_orient, float* d_pose_body, float* d_betas, float* d_trans) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* beta = betas + (size_t)(n / fpb) * LBS_NB;
+  float pose[66], J[LBS_J * 3], dpose[66], dJ[LBS_J * 3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pose[i] = root_orient[(size_t)n * 3 + i];
+  for (int i = 0; i < 63; ++i) pose[3 + i] = pose_body[(size_t)n * 63 + i];
+  rest_joints(m, beta, J);
+  const float* dj = djoints ? djoints + (size_t)n * njo * 3 : nullptr;
+  lbs_chain_bwd(pose, J, m.parents, dA ? dA + (size_t)n * 624 : nullptr, dj,
+                dfeat ? dfeat + (size_t)n * LBS_KF + LBS_NB : nullptr, dpose, dJ);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) d_root_orient[(size_t)n * 3 + i] = dpose[i];
+  for (int i = 0; i < 63; ++i) d_pose_body[(size_t)n * 63 + i] = dpose[3 + i];
+  for (int l = 0; l < LBS_NB; ++l) {
+    float a = dfeat ? dfeat[(size_t)n * LBS_KF + l] : 0.f;
+    for (int e = 0; e < LBS_J * 3; ++e) a = fmaf(m.j_dirs[e * LBS_NB + l], dJ[e], a);
+    d_betas[(size_t)n * LBS_NB + l] = a;
+  }
+  float t[3] = {dtr ? dtr[(size_t)n * 4] : 0.f, dtr ? dtr[(size_t)n * 4 + 1] : 0.f, dtr ? dtr[(size_t)n * 4 + 2] : 0.f};
+  // the 21 vertex-picked joints reach trans through the skinning pass (dtr); only the chain joints add here
+  if (dj)
+    for (int j = 0; j < LBS_J; ++j) { t[0] += dj[3 * j]; t[1] += dj[3 * j + 1]; t[2] += dj[3 * j + 2]; }
+  d_trans[(size_t)n * 3] = t[0]; d_trans[(size_t)n * 3 + 1] = t[1]; d_trans[(size_t)n * 3 + 2] = t[2];
+}
+
+static const size_t SKIN_FWD_SMEM = (size_t)SK_FT * LBS_KF * sizeof(float);
+static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + BW_FT * 624) * sizeof(float);
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" size_t humor_lbs_workspace_bytes(int N) { return lbs_carve(nullptr, N).total * sizeof(float); }
+
+extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* root_orient, const float* pose_body,
+                             const float* betas, const float* trans, float* workspace, size_t workspace_bytes,
+                             const int* vlist, int nv, float* verts, float* joints, int njo, int64_t* launches,
+                             cudaStream_t st) {
+  if (!m || N <= 0 || fpb <= 0 || !root_orient || !pose_body || !betas || !trans || !workspace) return HB_ERR_ARG;
+  if (njo != 52 && njo != 73) return HB_ERR_ARG;
+  LbsWs ws = lbs_carve(workspace, N);
+  if (workspace_bytes < ws.total * sizeof(float)) return HB_ERR_WORKSPACE;
+  int64_t nl = 0;
+  const bool need_skin = (verts != nullptr) || (joints && njo == 73);
+  lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
+                                             need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo);
+  HB_LAUNCH_CHECK(); ++nl;
+  if (need_skin) {
+    HB_CUDA(cudaFuncSetAttribute(lbs_skin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKIN_FWD_SMEM));
+    if (verts) {
+      const int nvv = vlist ? nv : m->num_verts;
+      if (nvv > 0) {
+        dim3 grid(cdiv(nvv, SK_VT), cdiv(N, SK_FT));
+        lbs_skin_fwd_kernel<<<grid, 256, SKIN_FWD_SMEM, st>>>(*m, N, ws.feat, ws.A, trans, vlist, nvv, verts, (size_t)nvv * 3);
+        HB_LAUNCH_CHECK(); ++nl;
+      }
+    }
+    if (joints && njo == 73) {
+      dim3 grid(1, cdiv(N, SK_FT));
+      lbs_skin_fwd_kernel<<<grid, 256, SKIN_FWD_SMEM, st>>>(*m, N, ws.feat, ws.A, trans, m->extra_ids, 21, joints + 52 * 3, (size_t)73 * 3);
+      HB_LAUNCH_CHECK(); ++nl;
+    }
+  }
+  if (launches) *launches = nl;
+  return HB_OK;
+}
+
+extern "C" int humor_lbs_bwd(const HbLbsModel* m, int N, int fpb, const float* root_orient, const float* pose_body,
+                             const float* betas, const float* trans, float* workspace, size_t workspace_bytes,
+                             const int* vlist, int nv, const float* d_verts, const float* d_joints, int njo,
+                             float* d_root_orient, float* d_pose_body, float* d_betas, float* d_trans,
+                             int64_t* launches, cudaStream_t st) {
+  if (!m || N <= 0 || fpb <= 0 || !root_orient || !pose_body || !betas || !workspace) return HB_ERR_ARG;
+  if (!d_root_orient || !d_pose_body || !d_betas || !d_trans) return HB_ERR_ARG;
+  if (njo != 52 && njo != 73) return HB_ERR_ARG;
+  LbsWs ws = lbs_carve(workspace, N);
+  if (workspace_bytes < ws.total * sizeof(float)) return HB_ERR_WORKSPACE;
+  int64_t nl = 0;
+  const bool xj = d_joints && njo == 73;
+  const bool need_skin = (d_verts != nullptr) || xj;
+  if (need_skin) {
+    // recompute the per-frame forward (feature rows, skinning transforms): cheaper than keeping them
+    lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52);
+    HB_LAUNCH_CHECK(); ++nl;
+    HB_CUDA(cudaFuncSetAttribute(lbs_skin_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKIN_BWD_SMEM));
+    int acc = 0;
+    if (d_verts) {
+      const int nvv = vlist ? nv : m->num_verts;
+      lbs_skin_bwd_kernel<<<cdiv(N, BW_FT), 256, SKIN_BWD_SMEM, st>>>(*m, N, ws.feat, ws.A, vlist, nvv, d_verts, (size_t)nvv * 3,
+                                                                     ws.dfeat, ws.dA, ws.dtr, acc);
+      HB_LAUNCH_CHECK(); ++nl;
+      acc = 1;
+    }
+    if (xj) {
+      lbs_skin_bwd_kernel<<<cdiv(N, BW_FT), 256, SKIN_BWD_SMEM, st>>>(*m, N, ws.feat, ws.A, m->extra_ids, 21, d_joints + 52 * 3,
+                                                                     (size_t)73 * 3, ws.dfeat, ws.dA, ws.dtr, acc);
+      HB_LAUNCH_CHECK(); ++nl;
+    }
+  }
+  lbs_pose_bwd_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, need_skin ? ws.dfeat : nullptr,
+                                                 need_skin ? ws.dA : nullptr, need_skin ? ws.dtr : nullptr, d_joints, njo,
+                                                 d_root_orient, d_pose_body, d_betas, d_trans);
+  HB_LAUNCH_CHECK(); ++nl;
+  if (launches) *launches = nl;
+  return HB_OK;
+}

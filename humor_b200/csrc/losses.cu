@@ -1,0 +1,429 @@
+// Fused Stage-III energies and their gradients (reference: humor/fitting/fitting_loss.py
+// root_fit :94-181, smpl_fit :183-224, motion_fit :226-309 and the per-term functions :317-518;
+// projection humor/fitting/fitting_utils.py:647-676, gmof :250-258).
+//
+// One block per (sequence b, frame t).  Every gradient element has exactly one owner thread, so the
+// outputs are written once (no atomics) and the term values go through a fixed-order reduction:
+// results are bit-reproducible run to run.  A term whose coefficient is 0 contributes exactly zero
+// (the reference gates on `weight > 0`, fitting_loss.py:193,240,277).
+#include "common.cuh"
+#include "../../include/humor_b200.h"
+
+namespace hb {
+
+__constant__ int c_smpl2op[25] = {52, 12, 17, 19, 21, 16, 18, 20, 0, 2, 5, 8, 1, 4, 7, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62};
+// body_model/utils.py:9 SMPL_PARENTS (the reference's table, shoulders -> neck), used by bone_length_loss
+__constant__ int c_parents_ref[22] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 12, 12, 13, 14, 16, 17, 18, 19};
+__constant__ int c_nchild[22] = {3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 3, 1, 1, 0, 1, 1, 1, 1, 0, 0};
+__constant__ int c_child[22][3] = {{1, 2, 3}, {4, 0, 0}, {5, 0, 0}, {6, 0, 0}, {7, 0, 0}, {8, 0, 0}, {9, 0, 0}, {10, 0, 0},
+                                   {11, 0, 0}, {12, 0, 0}, {0, 0, 0}, {0, 0, 0}, {13, 14, 15}, {16, 0, 0}, {17, 0, 0},
+                                   {0, 0, 0}, {18, 0, 0}, {19, 0, 0}, {20, 0, 0}, {21, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+// datasets/amass_utils.py:22-23 CONTACT_INDS -> slot in the 9 contact logits (-1: not a contact joint)
+__constant__ int c_contact_slot[22] = {0, -1, -1, -1, 1, 2, -1, 3, 4, -1, 5, 6, -1, -1, -1, -1, -1, -1, -1, -1, 7, 8};
+
+constexpr int NT = HB_NUM_TERMS;
+constexpr int LB = 128;  // block size
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+__device__ __forceinline__ bool vis(float x) { return !isinf(x); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float bone_len(const float* J, int j) {
+  const int p = c_parents_ref[j];
+  const float dx = J[3 * j] - J[3 * p], dy = J[3 * j + 1] - J[3 * p + 1], dz = J[3 * j + 2] - J[3 * p + 2];
+  return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+// d(0.5 sum_t (bl_{t+1}-bl_t)^2)/d bl_t for bone j at frame t
+__device__ __forceinline__ float bone_dl(const float* Jr_bt, int T, int t, int j) {
+  const float l = bone_len(Jr_bt, j);
+  float g = 0.f;
+  if (t > 0) g += l - bone_len(Jr_bt - 66, j);
+  if (t + 1 < T) g -= bone_len(Jr_bt + 66, j) - l;
+  return g;
+}
+
+__global__ void __launch_bounds__(LB) fit_losses_kernel(HbFitArgs a) {
+  __shared__ float red[4];
+  const int b = blockIdx.x / a.T, t = blockIdx.x % a.T;
+  const int tid = threadIdx.x;
+  const int T = a.T, B = a.B, njx = a.njx;
+  const size_t bt = (size_t)b * T + t;
+  const size_t obt = (size_t)b * a.T_obs + t;
+  float v_j2d = 0.f, v_j3d = 0.f, v_smooth = 0.f, v_v3d = 0.f, v_ovp = 0.f, v_ovv = 0.f;
+  float v_jc = 0.f, v_bl = 0.f, v_j3r = 0.f, v_cv = 0.f, v_ch = 0.f, v_mp = 0.f, v_pp = 0.f;
+  float v_sp = 0.f, v_ovb = 0.f, v_fr = 0.f, v_ovf = 0.f;
+  const float* cf = a.coef;
+
+  // ---------------------------------------------------------------- camera-frame joints (owner: joint j)
+  if (tid < njx) {
+    const int j = tid;
+    const float* P = a.cam_joints + (bt * njx + j) * 3;
+    const float px = P[0], py = P[1], pz = P[2];
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (cf[HB_T_JOINTS2D] != 0.f && a.obs_joints2d) {
+      int k = -1;
+#pragma unroll
+      for (int q = 0; q < 25; ++q) k = (c_smpl2op[q] == j) ? q : k;
+      if (k >= 0) {
+        const float* o = a.obs_joints2d + (obt * 25 + k) * 3;
+        float conf = (k == 1 || k == 9 || k == 12) ? 0.f : o[2];      // OP_IGNORE_JOINTS, fitting_loss.py:350-352
+        const float fx = a.cam_f[b * 2], fy = a.cam_f[b * 2 + 1];
+        const float iz = 1.f / pz;
+        const float rx = px * iz * fx + a.cam_c[b * 2] - o[0];
+        const float ry = py * iz * fy + a.cam_c[b * 2 + 1] - o[1];
+        const float s2 = a.sigma2d * a.sigma2d, c2 = conf * conf;
+        const float dx_ = s2 + rx * rx, dy_ = s2 + ry * ry;
+        v_j2d = c2 * (s2 * rx * rx / dx_ + s2 * ry * ry / dy_);
+        const float grx = c2 * 2.f * rx * s2 * s2 / (dx_ * dx_) * cf[HB_T_JOINTS2D];
+        const float gry = c2 * 2.f * ry * s2 * s2 / (dy_ * dy_) * cf[HB_T_JOINTS2D];
+        gx += grx * fx * iz;
+        gy += gry * fy * iz;
+        gz -= (grx * fx * px + gry * fy * py) * iz * iz;
+      }
+    }
+    if (j < 22) {
+      if (cf[HB_T_JOINTS3D] != 0.f && a.obs_joints3d) {
+        const float* o = a.obs_joints3d + (obt * 22 + j) * 3;
+        const float w = cf[HB_T_JOINTS3D];
+        if (vis(o[0])) { float d = px - o[0]; v_j3d += 0.5f * d * d; gx += w * d; }
+        if (vis(o[1])) { float d = py - o[1]; v_j3d += 0.5f * d * d; gy += w * d; }
+        if (vis(o[2])) { float d = pz - o[2]; v_j3d += 0.5f * d * d; gz += w * d; }
+      }
+      if (cf[HB_T_SMOOTH] != 0.f) {
+        const float w = cf[HB_T_SMOOTH];
+        if (t + 1 < T) {
+          const float* Q = P + (size_t)njx * 3;
+          const float d0 = Q[0] - px, d1 = Q[1] - py, d2 = Q[2] - pz;
+          v_smooth += 0.5f * (d0 * d0 + d1 * d1 + d2 * d2);
+          gx -= w * d0; gy -= w * d1; gz -= w * d2;
+        }
+        if (t > 0) {
+          const float* Q = P - (size_t)njx * 3;
+          gx += w * (px - Q[0]); gy += w * (py - Q[1]); gz += w * (pz - Q[2]);
+        }
+      }
+    }
+    float* g = a.d_cam_joints + (bt * njx + j) * 3;
+    g[0] = gx; g[1] = gy; g[2] = gz;
+  }
+
+  // ---------------------------------------------------------------- camera-frame key vertices (owner: vertex k)
+  if (tid < 43) {
+    const int k = tid;
+    const float* V = a.cam_verts + (bt * 43 + k) * 3;
+    float g[3] = {0.f, 0.f, 0.f};
+    if (cf[HB_T_VERTS3D] != 0.f && a.obs_verts3d) {
+      const float* o = a.obs_verts3d + (obt * 43 + k) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (vis(o[c])) { float d = V[c] - o[c]; v_v3d += 0.5f * d * d; g[c] += cf[HB_T_VERTS3D] * d; }
+    }
+    if (cf[HB_T_OV_POS] != 0.f && a.seq_interval) {
+      const float w = cf[HB_T_OV_POS];
+      // role 'c': head of sequence b against the tail of b-1   (fitting_loss.py:136-157)
+      if (b > 0) {
+        const int ov = a.seq_interval[(b - 1) * 2 + 1] - a.seq_interval[b * 2];
+        if (t < ov) {
+          const int ta = T - ov + t;
+          const float* Aa = a.cam_verts + (((size_t)(b - 1) * T + ta) * 43 + k) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float d = Aa[c] - V[c];                        // d_i = a_i - c_i
+            float gd = d;
+            v_ovp += 0.5f * d * d;
+            if (ov > 1) {
+              if (t + 1 < ov) { const float dn = Aa[129 + c] - V[129 + c]; v_ovv += 0.5f * (dn - d) * (dn - d); gd -= dn - d; }
+              if (t > 0) { const float dp = Aa[c - 129] - V[c - 129]; gd += d - dp; }
+            }
+            g[c] -= w * gd;
+          }
+        }
+      }
+      // role 'a': tail of sequence b against the head of b+1
+      if (b + 1 < B) {
+        const int ov = a.seq_interval[b * 2 + 1] - a.seq_interval[(b + 1) * 2];
+        const int i = t - (T - ov);
+        if (i >= 0 && i < ov) {
+          const float* Cc = a.cam_verts + (((size_t)(b + 1) * T + i) * 43 + k) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float d = V[c] - Cc[c];
+            float gd = d;
+            if (ov > 1) {
+              if (i + 1 < ov) { const float dn = V[129 + c] - Cc[129 + c]; gd -= dn - d; }
+              if (i > 0) { const float dp = V[c - 129] - Cc[c - 129]; gd += d - dp; }
+            }
+            g[c] += w * gd;
+          }
+        }
+      }
+    }
+    float* o = a.d_cam_verts + (bt * 43 + k) * 3;
+    o[0] = g[0]; o[1] = g[1]; o[2] = g[2];
+  }
+
+  // ---------------------------------------------------------------- prior-frame SMPL joints / rollout joints
+  if (tid >= 64 && tid < 64 + 22) {
+    const int j = tid - 64;
+    const float* Jp = a.prior_joints + (bt * 22 + j) * 3;
+    const float* JrF = a.roll_joints + bt * 66;           // this frame's 22 joints
+    const float* Jr = JrF + 3 * j;
+    float gp[3] = {0.f, 0.f, 0.f}, gr[3] = {0.f, 0.f, 0.f};
+    if (cf[HB_T_JOINT_CONSIST] != 0.f) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float d = Jp[c] - Jr[c];
+        v_jc += 0.5f * d * d;
+        gp[c] += cf[HB_T_JOINT_CONSIST] * d;
+        gr[c] -= cf[HB_T_JOINT_CONSIST] * d;
+      }
+    }
+    if (cf[HB_T_BONE_LEN] != 0.f) {
+      const float w = cf[HB_T_BONE_LEN];
+      if (j > 0) {
+        const float l = bone_len(JrF, j);
+        if (t + 1 < T) { const float d = bone_len(JrF + 66, j) - l; v_bl += 0.5f * d * d; }
+        const float gl = w * bone_dl(JrF, T, t, j) / l;
+        const int p = c_parents_ref[j];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gr[c] += gl * (Jr[c] - JrF[3 * p + c]);
+      }
+      for (int q = 0; q < c_nchild[j]; ++q) {
+        const int ch = c_child[j][q];
+        const float l = bone_len(JrF, ch);
+        const float gl = w * bone_dl(JrF, T, t, ch) / l;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gr[c] -= gl * (JrF[3 * ch + c] - Jr[c]);
+      }
+    }
+    if (cf[HB_T_J3D_ROLLOUT] != 0.f && a.obs_joints3d) {
+      const float* o = a.obs_joints3d + (obt * 22 + j) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (vis(o[c])) { const float d = Jr[c] - o[c]; v_j3r += 0.5f * d * d; gr[c] += cf[HB_T_J3D_ROLLOUT] * d; }
+    }
+    // contacts (fitting_loss.py:450-469; conf = sigmoid(logits) scattered to CONTACT_INDS, first frame
+    // repeated: motion_optimizer.py:982-998)
+    const int slot = c_contact_slot[j];
+    if (slot >= 0 && T > 1) {
+      const float* lg = a.contact_logits + ((size_t)b * (T - 1)) * 9 + slot;
+      const float conf = sigmoidf_(lg[(size_t)(t > 0 ? t - 1 : 0) * 9]);
+      float dconf = 0.f;                         // d loss / d conf of the logit this thread owns (t>=1)
+      if (cf[HB_T_CONTACT_VEL] != 0.f) {
+        const float w = cf[HB_T_CONTACT_VEL];
+        if (t > 0) {
+          const float d0 = Jp[0] - Jp[-66], d1 = Jp[1] - Jp[-65], d2 = Jp[2] - Jp[-64];
+          const float n2 = d0 * d0 + d1 * d1 + d2 * d2;
+          v_cv += 0.5f * n2 * conf;
+          dconf += w * 0.5f * n2;
+          gp[0] += w * conf * d0; gp[1] += w * conf * d1; gp[2] += w * conf * d2;
+        }
+        if (t + 1 < T) {
+          const float cn = sigmoidf_(lg[(size_t)t * 9]);
+          gp[0] -= w * cn * (Jp[66] - Jp[0]); gp[1] -= w * cn * (Jp[67] - Jp[1]); gp[2] -= w * cn * (Jp[68] - Jp[2]);
+        }
+      }
+      if (cf[HB_T_CONTACT_H] != 0.f) {
+        const float w = cf[HB_T_CONTACT_H];
+        const float z = Jp[2], az = fabsf(z), r = fmaxf(az - 0.08f, 0.f);
+        v_ch += r * conf;
+        if (az > 0.08f) gp[2] += w * conf * (z > 0.f ? 1.f : -1.f);
+        dconf += w * r;
+        if (t == 1) {                            // frame 0 shares logit 0
+          const float z0 = Jp[2 - 66];
+          dconf += w * fmaxf(fabsf(z0) - 0.08f, 0.f);
+        }
+      }
+      if (t > 0) a.d_contact_logits[((size_t)b * (T - 1) + (t - 1)) * 9 + slot] = dconf * conf * (1.f - conf);
+    }
+    float* o = a.d_prior_joints + (bt * 22 + j) * 3;
+    o[0] = gp[0]; o[1] = gp[1]; o[2] = gp[2];
+    o = a.d_roll_joints + (bt * 22 + j) * 3;
+    o[0] = gr[0]; o[1] = gr[1]; o[2] = gr[2];
+  }
+
+  // ---------------------------------------------------------------- motion prior (owner: latent dim)
+  if (tid < 48 && t + 1 < T) {
+    const size_t zi = ((size_t)b * (T - 1) + t) * 48 + tid;
+    const float z = a.z[zi];
+    const float w = cf[HB_T_MOTION_PRIOR];
+    if (a.prior_out) {
+      const size_t pi = ((size_t)t * B + b) * 96 + tid;
+      const float m = a.prior_out[pi], lv = a.prior_out[pi + 48];
+      const float var = expf(lv), d = z - m;
+      // -log N(z; m, var), fitting_loss.py:404-414,504-518
+      v_mp = logf(sqrtf(var)) + 0.91893853320467274178f + d * d / (2.f * var);
+      a.d_z[zi] = w * d / var;
+      a.d_prior_out[pi] = -w * d / var;
+      a.d_prior_out[pi + 48] = w * (0.5f - d * d / (2.f * var));
+    } else {
+      v_mp = z * z;
+      a.d_z[zi] = w * 2.f * z;
+    }
+  }
+  // ---------------------------------------------------------------- pose prior on the re-encoded latent pose
+  if (a.latent_pose && tid >= 96 && tid < 128) {
+    const size_t li = bt * 32 + (tid - 96);
+    const float x = a.latent_pose[li];
+    v_pp = x * x;
+    a.d_latent_pose[li] = cf[HB_T_POSE_PRIOR] * 2.f * x;
+  }
+  // ---------------------------------------------------------------- per-sequence terms (frame 0 block)
+  if (t == 0) {
+    if (tid >= 48 && tid < 64) {
+      const int l = tid - 48;
+      const float x = a.betas[b * 16 + l];
+      float g = 0.f;
+      v_sp = x * x;
+      g += cf[HB_T_SHAPE_PRIOR] * 2.f * x;
+      if (cf[HB_T_OV_BETAS] != 0.f && a.seq_interval) {
+        if (b > 0) { const float d = a.betas[(b - 1) * 16 + l] - x; v_ovb = 0.5f * d * d; g -= cf[HB_T_OV_BETAS] * d; }
+        if (b + 1 < B) { const float d = x - a.betas[(b + 1) * 16 + l]; g += cf[HB_T_OV_BETAS] * d; }
+      }
+      a.d_betas[b * 16 + l] = g;
+    }
+    if (a.floor && tid >= 86 && tid < 89) {
+      const int c = tid - 86;
+      const float x = a.floor[b * 3 + c];
+      float g = 0.f;
+      if (cf[HB_T_FLOOR_REG] != 0.f && a.obs_floor) {
+        const float d = x - a.obs_floor[b * 4 + c] * a.obs_floor[b * 4 + 3];
+        v_fr = 0.5f * d * d;
+        g += cf[HB_T_FLOOR_REG] * d;
+      }
+      if (cf[HB_T_OV_FLOOR] != 0.f && a.seq_interval) {
+        if (b > 0) { const float d = a.floor[(b - 1) * 3 + c] - x; v_ovf = 0.5f * d * d; g -= cf[HB_T_OV_FLOOR] * d; }
+        if (b + 1 < B) { const float d = x - a.floor[(b + 1) * 3 + c]; g += cf[HB_T_OV_FLOOR] * d; }
+      }
+      a.d_floor[b * 3 + c] = g;
+    }
+  }
+
+  // ---------------------------------------------------------------- fixed-order block reduction of the terms
+  float* out = a.partials + bt * NT;
+  float s;
+#define HB_RED(val, id) s = block_sum(val, red); if (tid == 0) out[id] = s;
+  HB_RED(v_j2d, HB_T_JOINTS2D) HB_RED(v_j3d, HB_T_JOINTS3D) HB_RED(v_v3d, HB_T_VERTS3D) HB_RED(v_ovp, HB_T_OV_POS)
+  HB_RED(v_ovv, HB_T_OV_VEL) HB_RED(v_pp, HB_T_POSE_PRIOR) HB_RED(v_sp, HB_T_SHAPE_PRIOR) HB_RED(v_smooth, HB_T_SMOOTH)
+  HB_RED(v_ovb, HB_T_OV_BETAS) HB_RED(v_mp, HB_T_MOTION_PRIOR) HB_RED(v_jc, HB_T_JOINT_CONSIST) HB_RED(v_bl, HB_T_BONE_LEN)
+  HB_RED(v_j3r, HB_T_J3D_ROLLOUT) HB_RED(v_cv, HB_T_CONTACT_VEL) HB_RED(v_ch, HB_T_CONTACT_H) HB_RED(v_fr, HB_T_FLOOR_REG)
+  HB_RED(v_ovf, HB_T_OV_FLOOR)
+#undef HB_RED
+  if (tid == 0) { out[HB_T_INIT_PRIOR] = 0.f; for (int i = HB_T_OV_FLOOR + 1; i < NT; ++i) out[i] = 0.f; }
+}
+
+// warp w sums term w over all rows in a fixed order; thread 0 forms the weighted loss
+__global__ void fit_reduce_kernel(HbFitArgs a) {
+  __shared__ float tot[NT];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = a.B * a.T;
+  float s = 0.f;
+  for (int r = lane; r < rows; r += 32) s += a.partials[(size_t)r * NT + w];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) { tot[w] = s; a.terms[w] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f;
+    for (int i = 0; i < NT; ++i) l += a.coef[i] * tot[i];
+    a.loss[0] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GMM negative log-likelihood: one block per row; warp-per-component Mahalanobis via Linv (lower)
+// ------------------------------------------------------------------------------------------------
+constexpr int GMM_MAXD = 160, GMM_MAXK = 32;
+__global__ void __launch_bounds__(256) gmm_nll_kernel(int D, int K, const float* __restrict__ x, const float* __restrict__ logw,
+                                                       const float* __restrict__ mean, const float* __restrict__ Linv,
+                                                       const float* __restrict__ logdet, float* nll, float* dx) {
+  __shared__ float xs[GMM_MAXD];
+  __shared__ float ys[8][GMM_MAXD];
+  __shared__ float lp[GMM_MAXK];
+  __shared__ float resp[GMM_MAXK];
+  const int b = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < D; i += 256) xs[i] = x[(size_t)b * D + i];
+  __syncthreads();
+  // pass 1: log p_k
+  for (int k = w; k < K; k += 8) {
+    const float* L = Linv + (size_t)k * D * D;
+    const float* mu = mean + (size_t)k * D;
+    float maha = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      float y = 0.f;
+      for (int j = 0; j <= i; ++j) y = fmaf(L[(size_t)i * D + j], xs[j] - mu[j], y);
+      maha += y * y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maha += __shfl_xor_sync(0xffffffffu, maha, o);
+    if (lane == 0) lp[k] = logw[k] - 0.5f * ((float)D * 1.8378770664093453f + maha) - logdet[k];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, lp[k]);
+    float se = 0.f;
+    for (int k = 0; k < K; ++k) se += expf(lp[k] - mx);
+    const float lse = mx + logf(se);
+    nll[b] = -lse;
+    for (int k = 0; k < K; ++k) resp[k] = expf(lp[k] - lse);
+  }
+  __syncthreads();
+  // pass 2: d nll / dx = sum_k resp_k * Sigma_k^{-1} (x - mu_k) = sum_k resp_k * Linv_k^T (Linv_k (x-mu_k))
+  float g = 0.f;                                    // thread tid < D owns dx[tid]
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    const int k = k0 + w;
+    if (k < K) {
+      const float* L = Linv + (size_t)k * D * D;
+      const float* mu = mean + (size_t)k * D;
+      for (int i = lane; i < D; i += 32) {
+        float y = 0.f;
+        for (int j = 0; j <= i; ++j) y = fmaf(L[(size_t)i * D + j], xs[j] - mu[j], y);
+        ys[w][i] = y;
+      }
+    }
+    __syncthreads();
+    if (tid < D) {
+      for (int kk = 0; kk < 8 && k0 + kk < K; ++kk) {
+        const float* L = Linv + (size_t)(k0 + kk) * D * D;
+        float acc = 0.f;
+        for (int i = tid; i < D; ++i) acc = fmaf(L[(size_t)i * D + tid], ys[kk][i], acc);
+        g = fmaf(resp[k0 + kk], acc, g);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < D) dx[(size_t)b * D + tid] = g;
+}
+
+}  // namespace hb
+using namespace hb;
+
+extern "C" int humor_fit_losses(const HbFitArgs* a, int64_t* launches, cudaStream_t st) {
+  if (!a || a->B <= 0 || a->T <= 0 || !a->terms || !a->loss || !a->partials) return HB_ERR_ARG;
+  if (a->njx != 52 && a->njx != 73) return HB_ERR_ARG;
+  if (!a->cam_joints || !a->cam_verts || !a->prior_joints || !a->roll_joints || !a->betas || !a->z) return HB_ERR_ARG;
+  if (a->T > 1 && !a->contact_logits) return HB_ERR_ARG;
+  fit_losses_kernel<<<a->B * a->T, LB, 0, st>>>(*a);
+  HB_LAUNCH_CHECK();
+  fit_reduce_kernel<<<1, NT * 32, 0, st>>>(*a);
+  HB_LAUNCH_CHECK();
+  if (launches) *launches = 2;
+  return HB_OK;
+}
+
+extern "C" int humor_gmm_nll(int B, int D, int K, const float* x, const float* logw, const float* mean, const float* Linv,
+                             const float* logdet, float* nll, float* d_x, cudaStream_t st) {
+  if (B <= 0 || D <= 0 || D > GMM_MAXD || K <= 0 || K > GMM_MAXK || !x || !logw || !mean || !Linv || !logdet || !nll || !d_x)
+    return HB_ERR_ARG;
+  gmm_nll_kernel<<<B, 256, 0, st>>>(D, K, x, logw, mean, Linv, logdet, nll, d_x);
+  HB_LAUNCH_CHECK();
+  return HB_OK;
+}

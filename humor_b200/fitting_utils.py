@@ -1,0 +1,46 @@
+"""Camera <-> prior-frame geometry of the fitting path (humor/fitting/fitting_utils.py:61-103,
+:149-190, :678-682).  Per-sequence (B rows, once per closure) so it is a handful of torch ops around
+the native Rodrigues kernel; the per-frame work lives in the CUDA kernels."""
+import torch
+
+from .transforms import batch_rodrigues
+
+OP_NUM_JOINTS = 25
+OP_IGNORE_JOINTS = [1, 9, 12]
+OP_EDGE_LIST = [[1, 8], [1, 2], [1, 5], [2, 3], [3, 4], [5, 6], [6, 7], [8, 9], [9, 10], [10, 11], [8, 12], [12, 13],
+                [13, 14], [1, 0], [0, 15], [15, 17], [0, 16], [16, 18], [14, 19], [19, 20], [14, 21], [11, 22],
+                [22, 23], [11, 24]]
+NSTAGES = 3
+
+
+def parse_floor_plane(floor_plane):
+    """(B,3) normal*offset -> (B,4) (a,b,c,d) with the normal pointing up in camera space (-y)."""
+    d = floor_plane.norm(dim=1, keepdim=True)
+    n = floor_plane / d
+    flip = n[:, 1:2] > 0.0
+    sgn = torch.where(flip, -torch.ones_like(d), torch.ones_like(d))
+    return torch.cat([n * sgn, d * sgn], 1)
+
+
+def compute_plane_intersection(point, direction, plane):
+    """s with point + s*direction on the plane n.x = d (either sign of s)."""
+    n, d = plane[:, :3], plane[:, 3]
+    s = (d - (n * point).sum(-1)) / (n * direction).sum(-1)
+    return point + s[:, None] * direction, s
+
+
+def compute_cam2prior(floor_plane, trans, root_orient, joints):
+    """Rotation/translation from the camera frame to the prior's canonical frame and the root height
+    above the floor (fitting_utils.py:149-190): up = floor normal, right = body -x projected on the floor."""
+    plane = parse_floor_plane(floor_plane) if floor_plane.size(1) == 3 else floor_plane
+    up = plane[:, :3]
+    foot, _ = compute_plane_intersection(trans, -up, plane)
+    body_right = -batch_rodrigues(root_orient)[:, :, 0]
+    hit, s = compute_plane_intersection(trans, body_right, plane)
+    right = (hit - foot) * torch.where(s < 0, -1.0, 1.0)[:, None]
+    right = right / right.norm(dim=1, keepdim=True)
+    fwd = torch.linalg.cross(up, right, dim=1)
+    fwd = fwd / fwd.norm(dim=1, keepdim=True)
+    R = torch.stack([right, fwd, up], 1)           # rows = prior axes expressed in the camera frame
+    _, s_root = compute_plane_intersection(joints[:, 0], -up, plane)
+    return R, -trans, s_root[:, None]

@@ -1,0 +1,179 @@
+/* humor_b200 — C-ABI of the B200-native HuMoR Stage-III hot path.
+ *
+ * The reference (davrempe/humor) has no FFI for this path: its de-facto plugin surface is the
+ * duck-typed Python objects handed to MotionOptimizer (humor/fitting/run_fitting.py:385-406).
+ * This header is the boundary a maintainer binds instead (ctypes stub in INTEGRATION.md); each
+ * entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a cudaError_t (>0) or HB_ERR_* (>1000) otherwise;
+ *     no exceptions, no printf, no hidden allocation, no hidden synchronisation.
+ *   - all pointers are DEVICE pointers to fp32 (or int32) arrays owned by the caller, including
+ *     workspaces (query the size with the *_workspace_bytes function).
+ *   - all work is enqueued on the given stream; functions are re-entrant per stream.
+ *   - `launches` (nullable) receives the number of kernels the call enqueued.
+ */
+#ifndef HUMOR_B200_H_
+#define HUMOR_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* hb_stream_t; /* == cudaStream_t */
+
+#define HB_NUM_VERTS 6890
+#define HB_NUM_JOINTS 52
+#define HB_NUM_JOINTS_X 73 /* + 21 vertex-picked joints (smplx VertexJointSelector) */
+#define HB_LBS_KF 208      /* feature row: betas 0:16 | pose feature 16:205 | pad */
+
+/* ---------------------------------------------------------------------------------------------
+ * SMPL+H model constants, packed by humor_b200/body_model.py (pack_smplh) from the npz the
+ * reference loads in humor/body_model/body_model.py:37-58.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HbLbsModel {
+  int num_verts;           /* V = 6890 */
+  int v3_ld;               /* leading dimension of blend (>= 3V, multiple of 64) */
+  int wk;                  /* ELL width of the skinning weights = max non-zeros per vertex */
+  int reserved;
+  const float* v_template; /* [3V] */
+  const float* blend;      /* [208][v3_ld]  row k: shapedirs (k<16) / posedirs (16<=k<205) of coord 3v+c */
+  const float* blend_t;    /* [v3_ld][208]  transpose of blend */
+  const float* j_template; /* [52*3]   J_regressor @ v_template */
+  const float* j_dirs;     /* [52*3][16] J_regressor @ shapedirs */
+  const int* w_idx;        /* [V][wk] joint index of each non-zero weight (padding: 0) */
+  const float* w_val;      /* [V][wk] weight (padding: 0.0) */
+  const int* parents;      /* [52] kintree_table[0], parents[0] = -1 */
+  const int* extra_ids;    /* [21] smplx vertex_ids['smplh'] in VertexJointSelector order */
+} HbLbsModel;
+
+/* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs
+ * (humor/body_model/body_model.py:72-115).  N frames; betas row of frame n is n / frames_per_beta.
+ *   vlist == NULL : all vertices, verts is [N][V][3];  else verts is [N][nv][3] for the listed ids;
+ *   verts == NULL : no vertex output.    joints is [N][num_joints_out][3], num_joints_out in {52,73}. */
+size_t humor_lbs_workspace_bytes(int N);
+int humor_lbs_fwd(const HbLbsModel* m, int N, int frames_per_beta, const float* root_orient,
+                  const float* pose_body, const float* betas, const float* trans, float* workspace,
+                  size_t workspace_bytes, const int* vlist, int nv, float* verts, float* joints,
+                  int num_joints_out, int64_t* launches, hb_stream_t stream);
+/* Reverse mode of the above (what autograd does through smplx in the reference).  d_verts follows the
+ * same vlist convention; d_betas is per frame [N][16] (the caller reduces over frames_per_beta). */
+int humor_lbs_bwd(const HbLbsModel* m, int N, int frames_per_beta, const float* root_orient,
+                  const float* pose_body, const float* betas, const float* trans, float* workspace,
+                  size_t workspace_bytes, const int* vlist, int nv, const float* d_verts,
+                  const float* d_joints, int num_joints_out, float* d_root_orient, float* d_pose_body,
+                  float* d_betas, float* d_trans, int64_t* launches, hb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * HuMoR CVAE weights, packed by humor_b200/humor_model.py (pack_humor_weights) from the state
+ * dict keys decoder.net.{0,1,3,4,6,7,9}.* / prior_net.net.{0,1,3,...,12}.*
+ * (humor/models/humor_model.py:181-206,1206-1229).  K dims zero-padded to the listed sizes.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HbHumorWeights {
+  const float* dec_w[4];  /* [1024][416] [1024][1088] [512][1088] [216][576] */
+  const float* dec_b[4];  /* [1024] [1024] [512] [216] */
+  const float* dec_g[3];  /* GroupNorm gamma [1024] [1024] [512] */
+  const float* dec_be[3]; /* GroupNorm beta */
+  const float* dec_wt[4]; /* transposes: [416][1024] [1088][1024] [1088][512] [576][224] */
+  const float* pri_w[5];  /* [1024][352] [1024][1024]x3 [96][1024] */
+  const float* pri_b[5];
+  const float* pri_g[4];
+  const float* pri_be[4];
+  const float* pri_wt[5]; /* [352][1024] [1024][1024]x3 [1024][96] */
+} HbHumorWeights;
+
+/* Replaces HumorModel.roll_out(x_past=None, init_input_dict, S, z_seq, return_prior=True)
+ * (humor/models/humor_model.py:785-1017) for in_rot_rep='mat', out_rot_rep='aa', steps_in=1,
+ * output_delta, 'smpl+joints+contacts'.
+ *   init_state [B][339] = trans3|trans_vel3|root_orient9|root_orient_vel3|pose_body189|joints66|joints_vel66
+ *   z_seq      [B][S][48]
+ *   world      [S][B][348] world-frame outputs per step:
+ *              trans3|trans_vel3|root_orient9|root_orient_vel3|pose_body189|joints66|joints_vel66|contacts9
+ *   prior_out  [S][B][96]  (mean | log-variance) of the conditional prior at every step (nullable)
+ * The workspace keeps the activations the reverse pass needs (the "tape"). */
+size_t humor_rollout_workspace_bytes(int B, int S);
+int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const float* init_state, const float* z_seq,
+                      float* workspace, size_t workspace_bytes, float* world, float* prior_out,
+                      int64_t* launches, hb_stream_t stream);
+/* BPTT through the rollout: d_world [S][B][348], d_prior_out [S][B][96] (nullable) ->
+ * d_init [B][339], d_z [B][S][48].  Must follow humor_rollout_fwd on the same workspace. */
+int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* workspace, size_t workspace_bytes,
+                      const float* d_world, const float* d_prior_out, float* d_init, float* d_z,
+                      int64_t* launches, hb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched rotation conversions (humor/utils/transforms.py:139-170 batch_rodrigues,
+ * :243-389 rotation_matrix_to_angle_axis) and their reverse modes.  n rotations.
+ * ------------------------------------------------------------------------------------------- */
+int humor_rodrigues_fwd(int n, const float* aa, float* R, hb_stream_t stream);
+int humor_rodrigues_bwd(int n, const float* aa, const float* dR, float* daa, hb_stream_t stream);
+int humor_mat2aa_fwd(int n, const float* R, float* aa, hb_stream_t stream);
+int humor_mat2aa_bwd(int n, const float* R, const float* daa, float* dR, hb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused Stage-III energies (humor/fitting/fitting_loss.py:94-309 motion_fit/smpl_fit/root_fit and
+ * the per-term functions :317-484, :504-518) — loss terms and their gradients in one pass.
+ * ------------------------------------------------------------------------------------------- */
+#define HB_NUM_TERMS 24
+enum HbTerm {
+  HB_T_JOINTS2D = 0, HB_T_JOINTS3D, HB_T_VERTS3D, HB_T_OV_POS, HB_T_OV_VEL, HB_T_POSE_PRIOR,
+  HB_T_SHAPE_PRIOR, HB_T_SMOOTH, HB_T_OV_BETAS, HB_T_MOTION_PRIOR, HB_T_INIT_PRIOR, HB_T_JOINT_CONSIST,
+  HB_T_BONE_LEN, HB_T_J3D_ROLLOUT, HB_T_CONTACT_VEL, HB_T_CONTACT_H, HB_T_FLOOR_REG, HB_T_OV_FLOOR
+};
+
+typedef struct HbFitArgs {
+  int B, T;               /* sequences, frames actually rolled out (nsteps) */
+  int njx;                /* joints per frame in cam_joints: 73 (with OpenPose extras) or 52 */
+  float coef[HB_NUM_TERMS]; /* weight * scale of every term; 0 disables it (exactly zero grad) */
+  float sigma2d;
+  /* predictions (device) */
+  const float* cam_joints;   /* [B][T][njx][3] camera-frame SMPL joints */
+  const float* cam_verts;    /* [B][T][43][3]  camera-frame key vertices */
+  const float* prior_joints; /* [B][T][22][3]  prior-frame SMPL joints */
+  const float* roll_joints;  /* [B][T][22][3]  joints regressed by the rollout */
+  const float* contact_logits; /* [B][T-1][9] */
+  const float* betas;        /* [B][16] */
+  const float* floor;        /* [B][3] (nullable) */
+  const float* z;            /* [B][T-1][48] */
+  const float* prior_out;    /* [T-1][B][96] (nullable -> standard normal) */
+  const float* latent_pose;  /* [B][T][32] (nullable) */
+  /* observations */
+  const float* obs_joints2d; /* [B][T_obs][25][3] (nullable) */
+  const float* obs_joints3d; /* [B][T_obs][22][3] (nullable) */
+  const float* obs_verts3d;  /* [B][T_obs][43][3] (nullable) */
+  const float* obs_floor;    /* [B][4] (nullable) */
+  const int* seq_interval;   /* [B][2] (nullable) */
+  const float* cam_f;        /* [B][2] */
+  const float* cam_c;        /* [B][2] */
+  int T_obs;                 /* frame stride of the observation tensors */
+  /* outputs */
+  float* terms;              /* [HB_NUM_TERMS] unweighted term values */
+  float* loss;               /* [1] sum coef*term (+ init prior, added by the caller via coef) */
+  float* d_cam_joints;       /* same shapes as the predictions; overwritten */
+  float* d_cam_verts;
+  float* d_prior_joints;
+  float* d_roll_joints;
+  float* d_contact_logits;
+  float* d_betas;
+  float* d_floor;
+  float* d_z;
+  float* d_prior_out;
+  float* d_latent_pose;
+  float* partials;           /* [B*T][HB_NUM_TERMS] scratch for the deterministic reduction */
+} HbFitArgs;
+int humor_fit_losses(const HbFitArgs* a, int64_t* launches, hb_stream_t stream);
+
+/* Init-state GMM prior (fitting_loss.py:416-429 + torch MixtureSameFamily):
+ *   x [B][D], logw [K], mean [K][D], Linv [K][D][D] (inverse Cholesky factor, lower), logdet [K]
+ *   -> nll [B] and d_x [B][D] = d(sum nll)/dx.  D <= 160, K <= 32. */
+int humor_gmm_nll(int B, int D, int K, const float* x, const float* logw, const float* mean,
+                  const float* Linv, const float* logdet, float* nll, float* d_x, hb_stream_t stream);
+
+const char* humor_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HUMOR_B200_H_ */

@@ -1,0 +1,95 @@
+"""GPU parity of the whole Stage-III closure (loss, every energy term, every parameter gradient)
+against the CPU oracle port, for both benchmark configurations and all three stage-3 phases."""
+import numpy as np
+import pytest
+import torch
+
+from humor_b200 import synth
+from tests import util_stage3 as U
+
+pytestmark = pytest.mark.gpu
+
+
+def compare(optim_floor, B, T, nsteps, scale, seed=4, overlap=3):
+    W = synth.RGB_STAGE3_WEIGHTS if optim_floor else synth.AMASS_STAGE3_WEIGHTS
+    prob = synth.make_stage3_problem(B, T, seed=seed, overlap=overlap, cam=optim_floor)
+    port = U.build_port(B, T, W, optim_floor, prob)
+    if optim_floor:
+        # informative 2-D observations: project the oracle's own camera-frame joints
+        _, _, aux = U.closure_port(port, prob, optim_floor)
+        cj = torch.cat([aux['inter']['cam_pred']['joints3d'], aux['inter']['cam_pred']['joints3d_extra']], 2)
+        prob = U.project_joints2d(prob, cj.detach().numpy())
+    l_c, g_c, aux_c = U.closure_port(port, prob, optim_floor, nsteps, scale)
+    mo = U.build_product(B, T, W, optim_floor, prob)
+    l_g, g_g, aux_g = U.closure_product(mo, prob, nsteps, scale)
+    assert abs(l_g - l_c) / max(1.0, abs(l_c)) < 2e-5, (l_g, l_c)
+    for k, v in aux_c['stats'].items():
+        assert k in aux_g['stats'], k
+        assert abs(aux_g['stats'][k] - v) <= 2e-4 * max(1.0, abs(v)), (k, aux_g['stats'][k], v)
+    for k in g_c:
+        err = float((g_g[k].cpu() - g_c[k]).abs().max() / (g_c[k].abs().max() + 1e-8))
+        assert err < 2e-3, (k, err)
+    # vertices of the final camera-frame SMPL evaluation
+    v_c = aux_c['inter']['cam_pred']['points3d']
+    v_g = aux_g['cam_pred']['points3d'].cpu()
+    assert float((v_g - v_c).abs().max()) < 1e-4
+    return l_g
+
+
+@pytest.mark.parametrize('nsteps,scale', [(None, 1.0), (4, 1.0), (None, 2.0)])
+def test_closure_rgb_config(nsteps, scale):
+    compare(True, 4, 8, nsteps, scale)
+
+
+@pytest.mark.parametrize('nsteps,scale', [(None, 1.0), (4, 1.0)])
+def test_closure_amass_keypts_config(nsteps, scale):
+    compare(False, 3, 7, nsteps, scale)
+
+
+def test_closure_is_deterministic():
+    prob = synth.make_stage3_problem(3, 6, seed=2, overlap=2)
+    mo = U.build_product(3, 6, synth.RGB_STAGE3_WEIGHTS, True, prob)
+    l1, g1, _ = U.closure_product(mo, prob)
+    l2, g2, _ = U.closure_product(mo, prob)
+    assert l1 == l2
+    for k in g1:
+        assert torch.equal(g1[k], g2[k]), k
+
+
+def test_full_size_properties():
+    """BASELINE config 3 size (B=64, T=60): no oracle run (minutes on CPU); size-independent properties instead:
+    sequences are independent when the overlap energy is off, so a sub-batch reproduces its slice."""
+    B, T = 64, 60
+    W = dict(synth.RGB_STAGE3_WEIGHTS)
+    W['rgb_overlap_consist'] = 0.0
+    prob = synth.make_stage3_problem(B, T, seed=9, overlap=10)
+    mo = U.build_product(B, T, W, True, prob)
+    l_full, g_full, aux = U.closure_product(mo, prob)
+    assert np.isfinite(l_full)
+    for k, g in g_full.items():
+        assert torch.isfinite(g).all(), k
+    sub = 8
+    p2 = {'params': {k: v[:sub] for k, v in prob['params'].items()}, 'obs': {k: v[:sub] for k, v in prob['obs'].items()},
+          'cam_mat': prob['cam_mat'][:sub]}
+    mo2 = U.build_product(sub, T, W, True, p2)
+    _, g_sub, _ = U.closure_product(mo2, p2)
+    for k in g_sub:
+        err = float((g_sub[k] - g_full[k][:sub]).abs().max() / (g_full[k][:sub].abs().max() + 1e-8))
+        assert err < 1e-4, (k, err)
+
+
+def test_motion_optimizer_run_smoke():
+    """MotionOptimizer.run end to end (all three stages, tiny iteration counts) with the reference's contract."""
+    B, T = 2, 8
+    prob = synth.make_stage3_problem(B, T, seed=3, overlap=3)
+    mo = U.build_product(B, T, synth.RGB_STAGE3_WEIGHTS, True, prob, contact_refine_only=True)
+    mo.stage3_tune_init_num_frames, mo.stage3_tune_init_freeze_start, mo.stage3_tune_init_freeze_end = 4, 1, 2
+    obs = {k: torch.as_tensor(v).cuda() for k, v in prob['obs'].items() if k in U.obs_keys(True)}
+    res, stages = mo.run(obs, num_iter=[1, 1, 3], lbfgs_max_iter=2)
+    assert res['trans'].shape == (B, T, 3) and res['pose_body'].shape == (B, T, 63) and res['betas'].shape == (B, 16)
+    assert res['latent_motion'].shape == (B, T - 1, 48) and res['floor_plane'].shape == (B, 4) and res['contacts'].shape == (B, T, 22)
+    assert set(['stage1', 'stage2', 'stage3']) <= set(stages)
+    s3 = stages['stage3']
+    assert s3['verts3d'].shape == (B, T, 43, 3) and s3['points3d'].shape == (B, T, 6890, 3) and 'prior_trans' in s3
+    for v in res.values():
+        assert torch.isfinite(v).all()

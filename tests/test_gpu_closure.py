@@ -57,25 +57,34 @@ def test_closure_is_deterministic():
 
 
 def test_full_size_properties():
-    """BASELINE config 3 size (B=64, T=60): no oracle run (minutes on CPU); size-independent properties instead:
-    sequences are independent when the overlap energy is off, so a sub-batch reproduces its slice."""
+    """BASELINE config 3 size (B=64, T=60).  The oracle takes minutes at that size on CPU, so: (1) sequences are
+    independent when the overlap energy is off -> a sub-batch must reproduce its slice of the full batch;
+    (2) that sub-batch (8 x 60 frames, full rollout length) is checked against the CPU oracle."""
     B, T = 64, 60
     W = dict(synth.RGB_STAGE3_WEIGHTS)
     W['rgb_overlap_consist'] = 0.0
     prob = synth.make_stage3_problem(B, T, seed=9, overlap=10)
+    sub = 8
+    p2 = {'params': {k: v[:sub] for k, v in prob['params'].items()}, 'obs': {k: v[:sub] for k, v in prob['obs'].items()},
+          'cam_mat': prob['cam_mat'][:sub]}
+    port = U.build_port(sub, T, W, True, p2)
+    _, _, aux = U.closure_port(port, p2, True)
+    cj = torch.cat([aux['inter']['cam_pred']['joints3d'], aux['inter']['cam_pred']['joints3d_extra']], 2).detach().numpy()
+    p2 = U.project_joints2d(p2, cj)
+    prob['obs']['joints2d'][:sub] = p2['obs']['joints2d']
+    l_c, g_c, _ = U.closure_port(port, p2, True)
     mo = U.build_product(B, T, W, True, prob)
     l_full, g_full, aux = U.closure_product(mo, prob)
     assert np.isfinite(l_full)
     for k, g in g_full.items():
         assert torch.isfinite(g).all(), k
-    sub = 8
-    p2 = {'params': {k: v[:sub] for k, v in prob['params'].items()}, 'obs': {k: v[:sub] for k, v in prob['obs'].items()},
-          'cam_mat': prob['cam_mat'][:sub]}
     mo2 = U.build_product(sub, T, W, True, p2)
-    _, g_sub, _ = U.closure_product(mo2, p2)
+    l_sub, g_sub, _ = U.closure_product(mo2, p2)
+    assert abs(l_sub - l_c) / max(1.0, abs(l_c)) < 1e-4, (l_sub, l_c)
     for k in g_sub:
-        err = float((g_sub[k] - g_full[k][:sub]).abs().max() / (g_full[k][:sub].abs().max() + 1e-8))
-        assert err < 1e-4, (k, err)
+        scale = float(g_c[k].abs().max()) + 1e-8
+        assert float((g_sub[k].cpu() - g_c[k]).abs().max()) / scale < 5e-3, k          # vs oracle, T=60 BPTT
+        assert float((g_sub[k] - g_full[k][:sub]).abs().max()) / scale < 5e-3, k       # slice of the full batch
 
 
 def test_motion_optimizer_run_smoke():

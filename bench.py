@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the HuMoR Stage-III optimiser step (BASELINE.json metric: frames/sec = B*T / t_closure).
+
+One *step* = one full-T Stage-III closure: forward (VPoser decode -> cam2prior -> CVAE rollout -> SMPL+H LBS ->
+fitting energies) + backward to every optimisation variable (reference: humor/fitting/motion_optimizer.py:514-608).
+Workload at N=1: the configuration the target is quoted on, B x T = 256 x 60, RGB config (optim_floor,
+stage-3 weights of configs/fit_rgb_demo_use_split.cfg), synthetic seeded inputs (no licensed assets exist offline).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's arm
+    python bench.py --impl reference ...                     # the reference algorithm on the host CPUs (oracle port)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from humor_b200 import synth  # noqa: E402
+
+LBS_BYTES_FWD = 83896          # per frame, fwd (inputs + v + Jtr)
+LBS_BYTES_BWD = 84236
+METRIC = 'stage3_optimizer_step_frames_per_sec'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d['hbm_gbs'], d.get('bf16_tflops', 1590.0), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def build_problem(B, T, seed=4):
+    return synth.make_stage3_problem(B, T, seed=seed, overlap=10, cam=True)
+
+
+def make_optimizer(B, T, prob, dev):
+    from humor_b200.body_model import BodyModel
+    from humor_b200.humor_model import HumorModel
+    from humor_b200.motion_optimizer import MotionOptimizer
+    bm = BodyModel(synth.make_smplh_asset(), num_betas=16, batch_size=B * T, use_vtx_selector=True).to(dev)
+    humor = HumorModel(in_rot_rep='mat', out_rot_rep='aa', latent_size=48, model_data_config='smpl+joints+contacts', steps_in=1)
+    humor.load_state_dict(synth.make_humor_state_dict())
+    humor.to(dev).eval()
+    gmm = tuple(g.to(dev) for g in synth.make_gmm())
+    w = dict(synth.RGB_STAGE3_WEIGHTS)
+    mo = MotionOptimizer(dev, bm, 16, B, T, ['joints2d', 'floor_plane', 'seq_interval'], [dict(w), dict(w), dict(w)],
+                         synth.FakeVPoser().to(dev), humor, {'gmm': gmm}, True, torch.as_tensor(prob['cam_mat']).to(dev),
+                         'bisquare', 4.6851, 100.0)
+    mo.fitting_loss.assume_unit_grad = True
+    return mo
+
+
+OBS_KEYS = ('joints2d', 'floor_plane', 'seq_interval')
+
+
+def project_obs_from_product(mo, prob, dev):
+    """Informative 2-D keypoints: project the product's own camera-frame joints at the initial state (+noise)."""
+    mo.set_stage3_state(prob['params'])
+    obs = {k: torch.as_tensor(prob['obs'][k]).to(dev) for k in OBS_KEYS}
+    with torch.no_grad():
+        _, _, _, _, cam_pred = mo.stage3_forward(obs)
+    from humor_b200.fitting_loss import SMPL2OP
+    j = cam_pred['Jtr'][:, :, SMPL2OP].cpu().numpy()
+    rng = np.random.RandomState(5)
+    f, c = np.asarray(synth.CAM_F), np.asarray(synth.CAM_C)
+    prob['obs']['joints2d'][..., :2] = (j[..., :2] / j[..., 2:3] * f + c + rng.randn(*j.shape[:3], 2) * 2.0).astype(np.float32)
+    return prob
+
+
+def run_product(args):
+    from humor_b200 import _ext
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    _ext.lib()
+    B, T = args.batch, args.seq_len
+    prob = build_problem(B, T, seed=4 + rank)
+    mo = make_optimizer(B, T, prob, dev)
+    prob = project_obs_from_product(mo, prob, dev)
+    names = mo.set_stage3_state(prob['params'])
+    obs = {k: torch.as_tensor(prob['obs'][k]).to(dev) for k in OBS_KEYS}
+    params = [getattr(mo, n) for n in names]
+
+    def step():
+        for p in params:
+            p.grad = None
+        loss, _, _, _, _ = mo.stage3_forward(obs)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    # ---- device-resident timing (value)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = _ext.LaunchCounter.total
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _ext.LaunchCounter.total - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end-to-end timing: host params/observations in pinned memory in, loss + gradients out, every step
+    host_in = {n: torch.as_tensor(prob['params'][n]).pin_memory() for n in names}
+    host_obs = {k: torch.as_tensor(prob['obs'][k]).pin_memory() for k in OBS_KEYS}
+    host_out = {n: torch.empty_like(host_in[n]).pin_memory() for n in names}
+    host_loss = torch.empty(1).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host_in.values()) + sum(t.numel() * t.element_size() for t in host_obs.values())
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values()) + 4
+
+    def step_e2e():
+        with torch.no_grad():
+            for n in names:
+                getattr(mo, n).copy_(host_in[n], non_blocking=True)
+            for k in OBS_KEYS:
+                obs[k].copy_(host_obs[k], non_blocking=True)
+        loss = step()
+        host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        for n in names:
+            host_out[n].copy_(getattr(mo, n).grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the caller (L-BFGS) reads the loss on the host
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    times = torch.tensor([ms, ms_e2e], device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(times[0]), float(times[1])
+    if rank != 0:
+        return
+    frames = B * T * world * args.steps
+    value = frames / (ms * 1e-3)
+    e2e = frames / (ms_e2e * 1e-3)
+    hbm_peak, _, peak_kind = load_peaks()
+    roof = lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind)
+    shares = kernel_shares(mo, obs, params, dev)
+    cpu = cpu_baseline(args, threads=os.cpu_count()) if not args.no_cpu_baseline else None
+    out = {
+        'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic (seeded SMPL+H-shaped asset, random-init HuMoR weights, projected 2-D keypoints)',
+        'config': {'workload': f'Stage-III full-T closure fwd+bwd, B={B} sub-sequences/GPU x T={T}, RGB config '
+                               '(optim_floor, fit_rgb_demo_use_split stage-3 weights, overlap 10)',
+                   'batch_per_gpu': B, 'seq_len': T, 'parallelism': f'dp{world} over sub-sequences',
+                   'l2': 'working set per step (rollout tape 0.45 GB + dense vertices 1.3 GB) exceeds the 126 MB L2'},
+        'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': int(launches), 'gpu_launches_per_step': launches / args.steps,
+        'clocks': clocks, 'roofline': roof, 'step_breakdown_ms': shares, 'cpu_baseline': cpu,
+        'lbs_bytes_roofline_frac_of_step': value * (2.0 + 3.0 / T) * (LBS_BYTES_FWD + LBS_BYTES_BWD) / (hbm_peak * 1e9),
+    }
+    print(json.dumps(out))
+
+
+def lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind):
+    """Dominant-bytes kernel named by BASELINE: the dense LBS forward (lbs_skin_fwd_kernel) timed alone with CUDA
+    events on the launching stream; algorithmic bytes = 83 896 B/frame x frames per launch."""
+    from humor_b200.body_model import lbs
+    N = B * T
+    g = torch.Generator(device='cpu').manual_seed(0)
+    ro = (torch.randn(N, 3, generator=g) * 0.5).to(dev)
+    pb = (torch.randn(N, 63, generator=g) * 0.3).to(dev)
+    be = (torch.randn(B, 16, generator=g) * 0.5).to(dev)
+    tr = torch.randn(N, 3, generator=g).to(dev)
+    m = mo.body_model.lbs_model
+    with torch.no_grad():
+        for _ in range(3):
+            lbs(m, ro, pb, be, tr, T, None, True, False, 73)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            lbs(m, ro, pb, be, tr, T, None, True, False, 73)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    achieved = N * LBS_BYTES_FWD / (ms * 1e-3) / 1e9
+    return {'kernel': 'lbs forward (lbs_pose_kernel + lbs_skin_fwd_kernel, dense v)', 'bound': 'hbm', 'achieved': achieved,
+            'peak': hbm_peak, 'peak_source': peak_kind, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
+            'ms_per_launch': ms, 'frames_per_launch': N, 'algorithmic_bytes_per_frame': LBS_BYTES_FWD}
+
+
+def kernel_shares(mo, obs, params, dev):
+    """Coarse split of one step (CUDA events around phases of an extra, untimed step)."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for p in params:
+        p.grad = None
+    torch.cuda.synchronize()
+    ev[0].record()
+    loss, _, _, _, _ = mo.stage3_forward(obs)
+    ev[1].record()
+    loss.backward()
+    ev[2].record()
+    torch.cuda.synchronize()
+    return {'forward': ev[0].elapsed_time(ev[1]), 'backward': ev[1].elapsed_time(ev[2])}
+
+
+def cpu_baseline(args, threads):
+    """The oracle port (plain-torch restatement of the reference closure) on the host cores, bounded sample."""
+    from tests import util_stage3 as U
+    torch.set_num_threads(max(1, threads))
+    Bc, T = args.cpu_batch, args.seq_len
+    prob = build_problem(Bc, T, seed=4)
+    port = U.build_port(Bc, T, synth.RGB_STAGE3_WEIGHTS, True, prob)
+    U.closure_port(port, prob, True)                 # warm-up
+    ts = []
+    for _ in range(args.cpu_steps):
+        t0 = time.perf_counter()
+        U.closure_port(port, prob, True)
+        ts.append(time.perf_counter() - t0)
+    med = float(np.median(ts))
+    return {'value': Bc * T / med, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+            'sample': f'{args.cpu_steps} full-T closures (fwd+bwd) at B={Bc}, T={T} (same config, smaller batch), median',
+            's_per_step': med}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count()
+    cb = cpu_baseline(args, threads)
+    B, T = args.batch, args.seq_len
+    out = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'frames/s',
+           'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': args.cpu_steps, 'warmup': 1,
+           'ms_per_step': cb['s_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': f'Stage-III full-T closure fwd+bwd, B={B} x T={T}, RGB config; timed on a bounded sample '
+                                  f'of B={args.cpu_batch} on the host CPUs (oracle port of the reference algorithm; the '
+                                  'reference itself is Python + unavailable smplx and cannot travel to this box)'},
+           'cpu_baseline': cb,
+           'e2e': {'value': cb['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='humor_b200', choices=['humor_b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='sub-sequences per GPU')
+    ap.add_argument('--seq-len', type=int, default=60)
+    ap.add_argument('--cpu-batch', type=int, default=16)
+    ap.add_argument('--cpu-steps', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'humor_b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == '__main__':
+    main()

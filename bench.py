@@ -200,7 +200,7 @@ def run_product(args):
     hbm_peak, _, peak_kind = load_peaks()
     roof = lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind)
     shares = kernel_shares(mo, obs, params, dev)
-    cpu = cpu_baseline(args, threads=os.cpu_count()) if not args.no_cpu_baseline else None
+    cpu = cpu_baseline(args) if not args.no_cpu_baseline else None
     out = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -262,7 +262,7 @@ def kernel_shares(mo, obs, params, dev):
     return {'forward': ev[0].elapsed_time(ev[1]), 'backward': ev[1].elapsed_time(ev[2])}
 
 
-def cpu_baseline(args, threads):
+def cpu_baseline_inproc(args, threads):
     """The oracle port (plain-torch restatement of the reference closure) on the host cores, bounded sample."""
     from tests import util_stage3 as U
     torch.set_num_threads(max(1, threads))
@@ -281,16 +281,36 @@ def cpu_baseline(args, threads):
             's_per_step': med}
 
 
+def cpu_threads():
+    # the closure is ~10^5 small torch ops: beyond ~16 intra-op threads the fork/join cost dominates
+    return min(os.cpu_count() or 1, int(os.environ.get('HB_CPU_THREADS', 16)))
+
+
+def cpu_baseline(args, threads=None, limit_s=150):
+    """Runs cpu_baseline_inproc in a child process with a hard time limit so the bench always finishes."""
+    threads = threads or cpu_threads()
+    cmd = [sys.executable, os.path.abspath(__file__), '--_cpu-child', '--cpu-batch', str(args.cpu_batch),
+           '--cpu-steps', str(args.cpu_steps), '--seq-len', str(args.seq_len), '--cpu-threads', str(threads)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads))
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=limit_s, env=env)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {'value': None, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+                'sample': f'did not finish within {limit_s} s ({type(e).__name__})'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    threads = os.cpu_count()
-    cb = cpu_baseline(args, threads)
+    cb = cpu_baseline(args, limit_s=240)
     B, T = args.batch, args.seq_len
     out = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'frames/s',
            'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': args.cpu_steps, 'warmup': 1,
-           'ms_per_step': cb['s_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'ms_per_step': (cb.get('s_per_step') or 0.0) * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'f32', 'data': 'synthetic',
            'config': {'workload': f'Stage-III full-T closure fwd+bwd, B={B} x T={T}, RGB config; timed on a bounded sample '
                                   f'of B={args.cpu_batch} on the host CPUs (oracle port of the reference algorithm; the '
@@ -308,10 +328,17 @@ def main():
     ap.add_argument('--impl', default='humor_b200', choices=['humor_b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='sub-sequences per GPU')
     ap.add_argument('--seq-len', type=int, default=60)
-    ap.add_argument('--cpu-batch', type=int, default=16)
+    ap.add_argument('--cpu-batch', type=int, default=8)
     ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--_cpu-child', dest='cpu_child', action='store_true', help=argparse.SUPPRESS)
+    ap.add_argument('--cpu-threads', type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_child:
+        import warnings
+        warnings.filterwarnings('ignore')
+        print(json.dumps(cpu_baseline_inproc(args, args.cpu_threads or cpu_threads())))
+        return
     args.warmup = max(args.warmup, 3) if args.impl == 'humor_b200' else args.warmup
     if args.impl == 'reference':
         run_reference(args)

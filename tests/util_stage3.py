@@ -36,7 +36,7 @@ def closure_port(port, prob, optim_floor, nsteps=None, scale=1.0):
     obs = {k: torch.as_tensor(v).clone() for k, v in prob['obs'].items() if k in obs_keys(optim_floor)}
     loss, stats, inter = port.closure(p, obs, nsteps, scale)
     loss.backward()
-    return float(loss), {k: p[k].grad.detach() for k in names}, {'stats': {k: float(v) for k, v in stats.items()}, 'inter': inter}
+    return float(loss.detach()), {k: p[k].grad.detach() for k in names}, {'stats': {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in stats.items()}, 'inter': inter}
 
 
 def build_product(B, T, weights, optim_floor, prob, device='cuda', contact_refine_only=True):
@@ -63,4 +63,4 @@ def closure_product(mo, prob, nsteps=None, scale=1.0):
     loss, stats, roll, cam, cam_pred = mo.stage3_forward(obs, nsteps, scale)
     loss.backward()
     grads = {n: getattr(mo, n).grad.detach() for n in names}
-    return float(loss), grads, {'stats': {k: float(v) for k, v in stats.items()}, 'roll': roll, 'cam': cam, 'cam_pred': cam_pred}
+    return float(loss.detach()), grads, {'stats': {k: float(v.detach()) for k, v in stats.items()}, 'roll': roll, 'cam': cam, 'cam_pred': cam_pred}

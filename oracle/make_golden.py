@@ -1,0 +1,76 @@
+"""ORACLE (test infrastructure) — generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, build container only) on seeded synthetic inputs.
+
+    python -m oracle.make_golden
+
+Each fixture holds the observations that were used (2-D keypoints are the projection of the reference's
+own camera-frame joints + seeded noise), the reference's loss, every energy term, the gradient of every
+stage-3 variable and a few intermediates.  Inputs other than the observations are regenerated from
+humor_b200.synth seeds by the tests.
+"""
+import os
+import numpy as np
+import torch
+
+from humor_b200 import synth
+from oracle import ref_closure
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+# NB: B == 3 is avoided on purpose: the reference calls torch.cross without `dim` (fitting_utils.py:181,
+# transforms.py:26), which picks the FIRST size-3 axis - the batch axis when B == 3.  The reference itself pads
+# a batch of 3 to 4 for this reason (run_fitting.py:61-63,288-318); port and product use dim=1.
+CASES = {
+    'stage3_rgb': dict(optim_floor=True, B=4, T=8, seed=21, overlap=3, nsteps=None, scale=1.0),
+    'stage3_rgb_phase1': dict(optim_floor=True, B=4, T=8, seed=22, overlap=3, nsteps=4, scale=1.0),
+    'stage3_rgb_refine': dict(optim_floor=True, B=2, T=7, seed=23, overlap=2, nsteps=None, scale=7.0 / 4.0),
+    'stage3_amass': dict(optim_floor=False, B=2, T=6, seed=24, overlap=2, nsteps=None, scale=1.0),
+}
+SMPL2OP = [52, 12, 17, 19, 21, 16, 18, 20, 0, 2, 5, 8, 1, 4, 7, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62]
+
+
+def run_case(c):
+    W = synth.RGB_STAGE3_WEIGHTS if c['optim_floor'] else synth.AMASS_STAGE3_WEIGHTS
+    prob = synth.make_stage3_problem(c['B'], c['T'], seed=c['seed'], overlap=c['overlap'], cam=c['optim_floor'])
+    keys = ('joints2d', 'floor_plane', 'seq_interval') if c['optim_floor'] else ('verts3d',)
+    ref, mo, _, _ = ref_closure.build(c['B'], c['T'], W, c['optim_floor'], prob['cam_mat'] if c['optim_floor'] else None)
+    obs = {k: torch.as_tensor(prob['obs'][k]) for k in keys}
+    if c['optim_floor']:
+        ref_closure.set_params(mo, prob['params'], requires_grad=False)
+        with torch.no_grad():
+            _, _, inter = ref_closure.stage3_closure(ref, mo, {k: v.clone() for k, v in obs.items()}, backward=False)
+        j = torch.cat([inter['cam_pred']['joints3d'], inter['cam_pred']['joints3d_extra']], 2)[:, :, SMPL2OP].numpy()
+        rng = np.random.RandomState(c['seed'] + 100)
+        xy = j[..., :2] / j[..., 2:3] * np.asarray(synth.CAM_F) + np.asarray(synth.CAM_C) + rng.randn(*j.shape[:3], 2) * 2.0
+        obs['joints2d'] = obs['joints2d'].clone()
+        obs['joints2d'][..., :2] = torch.as_tensor(xy.astype(np.float32))
+    names = ref_closure.set_params(mo, prob['params'])
+    loss, stats, inter = ref_closure.stage3_closure(ref, mo, {k: v.clone() for k, v in obs.items()}, c['nsteps'], c['scale'])
+    out = {'loss': np.float32(loss.item())}
+    for k, v in stats.items():
+        out['stat_' + k] = np.float32(float(v))
+    for n in names:
+        out['grad_' + n] = getattr(mo, n).grad.numpy()
+    for k in keys:
+        out['obs_' + k] = obs[k].numpy()
+    out['cam_verts3d'] = inter['cam_pred']['verts3d'].detach().numpy()
+    out['cam_joints3d'] = inter['cam_pred']['joints3d'].detach().numpy()
+    out['rollout_trans'] = inter['rollout']['trans'].detach().numpy()
+    out['rollout_pose_body'] = inter['rollout']['pose_body'].detach().numpy()
+    out['cond_prior_mean'] = inter['rollout']['cond_prior'][0].detach().numpy()
+    out['cond_prior_var'] = inter['rollout']['cond_prior'][1].detach().numpy()
+    out['meta'] = np.array([c['B'], c['T'], c['seed'], c['overlap'], -1 if c['nsteps'] is None else c['nsteps'], int(c['optim_floor'])])
+    out['scale'] = np.float32(c['scale'])
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    for name, c in CASES.items():
+        out = run_case(c)
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+        print(name, 'loss', out['loss'], {k[5:]: float(v) for k, v in out.items() if k.startswith('stat_')})
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,32 @@
+import os
+import numpy as np
+from humor_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+CASES = ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass']
+
+
+def load_case(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    B, T, seed, overlap, nsteps, of = [int(x) for x in g['meta']]
+    optim_floor = bool(of)
+    prob = synth.make_stage3_problem(B, T, seed=seed, overlap=overlap, cam=optim_floor)
+    for k in list(prob['obs'].keys()):
+        if 'obs_' + k in g:
+            prob['obs'][k] = g['obs_' + k]
+    W = synth.RGB_STAGE3_WEIGHTS if optim_floor else synth.AMASS_STAGE3_WEIGHTS
+    return g, prob, dict(B=B, T=T, optim_floor=optim_floor, nsteps=None if nsteps < 0 else nsteps, scale=float(g['scale']), W=W)
+
+
+def check_against_golden(g, loss, stats, grads, loss_tol=2e-5, stat_tol=2e-4, grad_tol=2e-3):
+    assert abs(loss - float(g['loss'])) <= loss_tol * max(1.0, abs(float(g['loss']))), (loss, float(g['loss']))
+    for k in g:
+        if k.startswith('stat_'):
+            v = float(g[k])
+            assert k[5:] in stats, k
+            assert abs(stats[k[5:]] - v) <= stat_tol * max(1.0, abs(v)), (k, stats[k[5:]], v)
+        if k.startswith('grad_'):
+            ref = g[k]
+            got = np.asarray(grads[k[5:]].cpu() if hasattr(grads[k[5:]], 'cpu') else grads[k[5:]])
+            err = np.abs(got - ref).max() / (np.abs(ref).max() + 1e-8)
+            assert err < grad_tol, (k, err)

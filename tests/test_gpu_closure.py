@@ -102,3 +102,17 @@ def test_motion_optimizer_run_smoke():
     assert s3['verts3d'].shape == (B, T, 43, 3) and s3['points3d'].shape == (B, T, 6890, 3) and 'prior_trans' in s3
     for v in res.values():
         assert torch.isfinite(v).all()
+
+
+@pytest.mark.parametrize('name', ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass'])
+def test_closure_matches_reference_golden(name):
+    """CUDA path against fixtures produced by the UNMODIFIED reference in the build container."""
+    from tests.golden_util import load_case, check_against_golden
+    g, prob, c = load_case(name)
+    mo = U.build_product(c['B'], c['T'], c['W'], c['optim_floor'], prob)
+    loss, grads, aux = U.closure_product(mo, prob, c['nsteps'], c['scale'])
+    check_against_golden(g, loss, aux['stats'], grads)
+    assert np.abs(aux['cam_pred']['verts3d'].detach().cpu().numpy() - g['cam_verts3d']).max() < 1e-4
+    assert np.abs(aux['roll']['trans'].detach().cpu().numpy() - g['rollout_trans']).max() < 2e-5
+    pm = aux['roll']['cond_prior'][0].detach().cpu().numpy()
+    assert np.abs(pm - g['cond_prior_mean']).max() / np.abs(g['cond_prior_mean']).max() < 1e-5

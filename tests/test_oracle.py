@@ -87,7 +87,7 @@ def test_lbs_root_rotation_is_rigid_about_root_joint(smpl):
     v1, J1, _ = m.forward(beta, aa, z63, z3)
     R = rodrigues(aa)[0]
     root = J0[0, 0]
-    assert ((v0[0] - root) @ R.T + root - v1[0]).abs().max() < 1e-9
+    assert ((v0[0] - root) @ R.T + root - v1[0]).abs().max() < 1e-6    # weights sum to 1 to fp32 rounding
     assert ((J0[0] - root) @ R.T + root - J1[0]).abs().max() < 1e-9
 
 

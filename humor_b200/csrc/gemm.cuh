@@ -5,7 +5,7 @@
 //                    C = relu(gamma*xhat+beta) ; also stores xhat and rstd for the backward
 //   EPI_GN_RELU_BWD  acc is dL/dh ; columns < Cch: dL/dy of relu(GN(y)) (uses saved xhat, rstd) ;
 //                    columns >= Cch (skip-connected z) pass through
-// K must be a multiple of BK (operands are stored zero-padded), lda/ldb multiples of 4.
+// K must be a multiple of BK = 32 (operands are stored zero-padded), lda/ldb multiples of 4.
 // This is the exact-fp32 path required by the 1e-5 parity bound on decoder states / prior log-prob.
 #pragma once
 #include "common.cuh"
@@ -52,31 +52,34 @@ gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
 #pragma unroll
     for (int j = 0; j < NSN * 4; ++j) acc[i][j] = 0.f;
 
-  float4 ra[A_PT], rb[B_PT];
-  auto gload = [&](int k0) {
+  // global -> register -> (transposed) shared staging with a prefetch distance of TWO tiles: with one
+  // CTA per SM (the sequential decoder steps only offer ~128 CTAs) a single tile of compute does not
+  // cover the L2 latency, two do.
+  float4 ra[2][A_PT], rb[2][B_PT];
+  auto gload = [&](int k0, float4* pa, float4* pb) {
 #pragma unroll
     for (int i = 0; i < A_PT; ++i) {
       int idx = tid + i * NT;
       int r = idx / KV, kv = idx % KV;
-      ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx < A_V4 && m0 + r < M) ra[i] = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + k0 + kv * 4);
+      pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < A_V4 && m0 + r < M) pa[i] = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + k0 + kv * 4);
     }
 #pragma unroll
     for (int i = 0; i < B_PT; ++i) {
       int idx = tid + i * NT;
       int r = idx / KV, kv = idx % KV;
-      rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx < B_V4 && n0 + r < N) rb[i] = *reinterpret_cast<const float4*>(B + (size_t)(n0 + r) * ldb + k0 + kv * 4);
+      pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < B_V4 && n0 + r < N) pb[i] = *reinterpret_cast<const float4*>(B + (size_t)(n0 + r) * ldb + k0 + kv * 4);
     }
   };
-  auto sstore = [&](int buf) {
+  auto sstore = [&](int buf, const float4* pa, const float4* pb) {
 #pragma unroll
     for (int i = 0; i < A_PT; ++i) {
       int idx = tid + i * NT;
       if (idx < A_V4) {
         int r = idx / KV, kv = idx % KV;
-        As[buf][kv * 4 + 0][r] = ra[i].x; As[buf][kv * 4 + 1][r] = ra[i].y;
-        As[buf][kv * 4 + 2][r] = ra[i].z; As[buf][kv * 4 + 3][r] = ra[i].w;
+        As[buf][kv * 4 + 0][r] = pa[i].x; As[buf][kv * 4 + 1][r] = pa[i].y;
+        As[buf][kv * 4 + 2][r] = pa[i].z; As[buf][kv * 4 + 3][r] = pa[i].w;
       }
     }
 #pragma unroll
@@ -84,19 +87,12 @@ gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
       int idx = tid + i * NT;
       if (idx < B_V4) {
         int r = idx / KV, kv = idx % KV;
-        Bs[buf][kv * 4 + 0][r] = rb[i].x; Bs[buf][kv * 4 + 1][r] = rb[i].y;
-        Bs[buf][kv * 4 + 2][r] = rb[i].z; Bs[buf][kv * 4 + 3][r] = rb[i].w;
+        Bs[buf][kv * 4 + 0][r] = pb[i].x; Bs[buf][kv * 4 + 1][r] = pb[i].y;
+        Bs[buf][kv * 4 + 2][r] = pb[i].z; Bs[buf][kv * 4 + 3][r] = pb[i].w;
       }
     }
   };
-
-  gload(0);
-  sstore(0);
-  __syncthreads();
-  const int nk = K / BK;
-  for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) gload((kt + 1) * BK);
+  auto compute = [&](int buf) {
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[NSM * 4], b[NSN * 4];
@@ -115,9 +111,27 @@ gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
 #pragma unroll
         for (int j = 0; j < NSN * 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+  };
+
+  const int nk = K / BK;
+  gload(0, ra[0], rb[0]);
+  if (nk > 1) gload(BK, ra[1], rb[1]);
+  sstore(0, ra[0], rb[0]);
+  __syncthreads();
+  if (nk > 2) gload(2 * BK, ra[0], rb[0]);
+  // tile kt+1 sits in register stage (kt+1)&1; after it is stored, that stage prefetches tile kt+3
+  for (int kt = 0; kt < nk; kt += 2) {
+    compute(0);
     if (kt + 1 < nk) {
-      sstore(buf ^ 1);
+      sstore(1, ra[1], rb[1]);
       __syncthreads();
+      if (kt + 3 < nk) gload((kt + 3) * BK, ra[1], rb[1]);
+      compute(1);
+      if (kt + 2 < nk) {
+        sstore(0, ra[0], rb[0]);
+        __syncthreads();
+        if (kt + 4 < nk) gload((kt + 4) * BK, ra[0], rb[0]);
+      }
     }
   }
 
@@ -213,7 +227,7 @@ static inline cudaError_t launch_gemm(const float* A, int lda, const float* B, i
     gemm_tn_kernel<128, 128, 16, 2, 2, EPI><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, ep);
   } else {
     dim3 grid(cdiv(N, 64), cdiv(M, 32));
-    gemm_tn_kernel<32, 64, 16, 1, 1, EPI><<<grid, 128, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, ep);
+    gemm_tn_kernel<32, 64, 32, 1, 1, EPI><<<grid, 128, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, ep);
   }
   return cudaGetLastError();
 }

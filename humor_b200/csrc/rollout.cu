@@ -70,19 +70,102 @@ __global__ void rollout_init_kernel(int B, int S, const float* __restrict__ init
   if (threadIdx.x < 3) t2j[b * 4 + threadIdx.x] = threadIdx.x < 2 ? -init[(size_t)b * STATE_D + 207 + threadIdx.x] : 0.f;
 }
 
-// one thread per sequence row
-__global__ void glue_fwd_kernel(int B, int S, int t, const float* __restrict__ xin, const float* __restrict__ raw,
-                                const float* __restrict__ G, const float* __restrict__ t2j, const float* __restrict__ z,
-                                float* xnext, float* world, float* Gnext, float* h1, float* h2, float* h3) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
+// ------------------------------------------------------------------------------------------------
+// Glue kernels: ONE WARP PER SEQUENCE ROW, lane = joint.  Rows are staged through shared memory with
+// coalesced loads/stores; the root-level reverse-mode sums (dRa, dGr, dGt, dta, dt2j) are warp-shuffle
+// reductions.  Same arithmetic as glue_step_fwd / glue_step_bwd in rollout_glue.cuh (the scalar
+// host/device statement that tests/host validates against autograd).
+// ------------------------------------------------------------------------------------------------
+constexpr int GLUE_WARPS = 4;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(GLUE_WARPS * 32)
+glue_fwd_kernel(int B, int S, int t, const float* __restrict__ xin, const float* __restrict__ raw,
+                const float* __restrict__ G, const float* __restrict__ t2jg, const float* __restrict__ z,
+                float* xnext, float* world, float* Gnext, float* h1, float* h2, float* h3) {
+  __shared__ float s_x[GLUE_WARPS][340], s_r[GLUE_WARPS][216], s_n[GLUE_WARPS][340], s_w[GLUE_WARPS][348];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * GLUE_WARPS + wid;
   if (b >= B) return;
+  float* sx = s_x[wid]; float* sr = s_r[wid]; float* sn = s_n[wid]; float* sw = s_w[wid];
+  const float* xr = xin + (size_t)b * XIN_LD;
+  const float* rr = raw + (size_t)b * RAW_LD;
+  for (int i = lane; i < STATE_D; i += 32) sx[i] = xr[i];
+  for (int i = lane; i < RAW_D; i += 32) sr[i] = rr[i];
+  __syncwarp();
+  float Gr[9], Gt[3], t2j[3], tr[3], R0[9], D[9], Ra[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) Gr[e] = G[(size_t)b * 12 + e];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { Gt[i] = G[(size_t)b * 12 + 9 + i]; t2j[i] = t2jg[b * 4 + i]; tr[i] = sx[i] + sr[i]; }
+  rodrigues_fwd(sr + 6, D);
+  mat3_mul(D, sx + 6, R0);
+  w2a_fwd(R0, Ra);
+  const float ta[3] = {-tr[0], -tr[1], 0.f};
+  if (lane < NJ) {
+    const int k = lane;
+    float p[3], v[3], a[3], o[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      p[i] = sx[207 + 3 * k + i] + sr[75 + 3 * k + i];
+      v[i] = sx[273 + 3 * k + i] + sr[141 + 3 * k + i];
+      a[i] = p[i] + ta[i] + t2j[i];
+    }
+    mat3_vec(Ra, a, o);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { sn[207 + 3 * k + i] = o[i] - t2j[i]; a[i] = p[i] + t2j[i]; }
+    mat3_tvec(Gr, a, o);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sw[207 + 3 * k + i] = o[i] - t2j[i] - Gt[i];
+    mat3_vec(Ra, v, sn + 273 + 3 * k);
+    mat3_tvec(Gr, v, sw + 273 + 3 * k);
+    if (k == 0) {
+      mat3_mul(Ra, R0, sn + 6);
+      mat3_mul_tn(Gr, R0, sw + 6);
+    } else {
+      const int j = k - 1;
+      float Dj[9], Rj[9];
+      rodrigues_fwd(sr + 12 + 3 * j, Dj);
+      mat3_mul(Dj, sx + 18 + 9 * j, Rj);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { sn[18 + 9 * j + e] = Rj[e]; sw[18 + 9 * j + e] = Rj[e]; }
+    }
+  } else if (lane == 22) {
+    float u[3] = {tr[0] + ta[0], tr[1] + ta[1], tr[2] + ta[2]};
+    mat3_vec(Ra, u, sn + 0);
+    float wt[3];
+    mat3_tvec(Gr, tr, wt);
+    float* gn = Gnext + (size_t)b * 12;
+    mat3_mul(Gr, Ra, gn);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { wt[i] -= Gt[i]; sw[i] = wt[i]; }
+    gn[9] = -wt[0]; gn[10] = -wt[1]; gn[11] = 0.f;
+  } else if (lane == 23) {
+    float tv[3] = {sx[3] + sr[3], sx[4] + sr[4], sx[5] + sr[5]};
+    mat3_vec(Ra, tv, sn + 3);
+    mat3_tvec(Gr, tv, sw + 3);
+  } else if (lane == 24) {
+    float rv[3] = {sx[15] + sr[9], sx[16] + sr[10], sx[17] + sr[11]};
+    mat3_vec(Ra, rv, sn + 15);
+    mat3_tvec(Gr, rv, sw + 15);
+  } else if (lane == 25) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) sw[339 + c] = sr[207 + c];
+  }
+  __syncwarp();
   float* xn = xnext + (size_t)b * XIN_LD;
-  glue_step_fwd(xin + (size_t)b * XIN_LD, raw + (size_t)b * RAW_LD, G + (size_t)b * 12, t2j + b * 4, xn,
-                world + (size_t)b * WORLD_LD, Gnext + (size_t)b * 12);
+  float* wo = world + (size_t)b * WORLD_LD;
+  for (int i = lane; i < STATE_D; i += 32) xn[i] = sn[i];
+  for (int i = lane; i < WORLD_LD; i += 32) wo[i] = sw[i];
   if (t + 1 < S) {
     const float* zt = z + ((size_t)b * S + (t + 1)) * 48;
-    for (int i = 0; i < 48; ++i) {
-      float v = zt[i];
+    for (int i = lane; i < 48; i += 32) {
+      const float v = zt[i];
       xn[STATE_D + i] = v;
       h1[(size_t)b * 1088 + 1024 + i] = v;
       h2[(size_t)b * 1088 + 1024 + i] = v;
@@ -92,35 +175,174 @@ __global__ void glue_fwd_kernel(int B, int S, int t, const float* __restrict__ x
 }
 
 // reverse of one step.  have_next: grads from step t+1 exist (da0/dxres/dpx_next) and dz[:,t+1] is emitted.
-__global__ void glue_bwd_kernel(int B, int S, int t, int have_next, const float* __restrict__ xin,
-                                const float* __restrict__ raw, const float* __restrict__ G, const float* __restrict__ t2j,
-                                const float* __restrict__ dworld, const float* __restrict__ da0,
-                                const float* __restrict__ dpx_next, const float* __restrict__ dh1,
-                                const float* __restrict__ dh2, const float* __restrict__ dh3, float* dxres, float* dnsum,
-                                const float* __restrict__ dGn, float* dG, float* dt2j, float* draw, float* dz) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(GLUE_WARPS * 32)
+glue_bwd_kernel(int B, int S, int t, int have_next, const float* __restrict__ xin, const float* __restrict__ raw,
+                const float* __restrict__ G, const float* __restrict__ t2jg, const float* __restrict__ dworld,
+                const float* __restrict__ da0, const float* __restrict__ dpx_next, const float* __restrict__ dh1,
+                const float* __restrict__ dh2, const float* __restrict__ dh3, float* dxres, float* dnsum,
+                const float* __restrict__ dGn_g, float* dG, float* dt2j, float* draw, float* dz) {
+  __shared__ float s_x[GLUE_WARPS][340], s_r[GLUE_WARPS][216], s_dn[GLUE_WARPS][340], s_dw[GLUE_WARPS][348],
+      s_dx[GLUE_WARPS][340], s_dr[GLUE_WARPS][224];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * GLUE_WARPS + wid;
   if (b >= B) return;
-  float* dn = dnsum + (size_t)b * 340;
-  float* dx = dxres + (size_t)b * 340;
-  float dGnext[12];
-  if (have_next) {
-    const float* a0 = da0 + (size_t)b * XIN_LD;
-    const float* px = dpx_next + (size_t)b * 352;
-    for (int i = 0; i < STATE_D; ++i) dn[i] = dx[i] + a0[i] + px[i];
-    float* dzt = dz + ((size_t)b * S + (t + 1)) * 48;
-    for (int i = 0; i < 48; ++i)
-      dzt[i] = a0[STATE_D + i] + dh1[(size_t)b * 1088 + 1024 + i] + dh2[(size_t)b * 1088 + 1024 + i] +
-               dh3[(size_t)b * 576 + 512 + i];
-    for (int i = 0; i < 12; ++i) dGnext[i] = dGn[(size_t)b * 12 + i];
-  } else {
-    for (int i = 0; i < STATE_D; ++i) dn[i] = 0.f;
-    for (int i = 0; i < 12; ++i) dGnext[i] = 0.f;
-    dt2j[b * 4 + 0] = dt2j[b * 4 + 1] = dt2j[b * 4 + 2] = 0.f;
+  float* sx = s_x[wid]; float* sr = s_r[wid]; float* dn = s_dn[wid]; float* dw = s_dw[wid];
+  float* dx = s_dx[wid]; float* dr = s_dr[wid];
+  {
+    const float* xr = xin + (size_t)b * XIN_LD;
+    const float* rr = raw + (size_t)b * RAW_LD;
+    const float* wr = dworld + (size_t)b * WORLD_LD;
+    for (int i = lane; i < STATE_D; i += 32) sx[i] = xr[i];
+    for (int i = lane; i < RAW_D; i += 32) sr[i] = rr[i];
+    for (int i = lane; i < WORLD_LD; i += 32) dw[i] = wr[i];
+    if (have_next) {
+      const float* a0 = da0 + (size_t)b * XIN_LD;
+      const float* px = dpx_next + (size_t)b * 352;
+      const float* xs = dxres + (size_t)b * 340;
+      for (int i = lane; i < STATE_D; i += 32) dn[i] = xs[i] + a0[i] + px[i];
+      float* dzt = dz + ((size_t)b * S + (t + 1)) * 48;
+      for (int i = lane; i < 48; i += 32)
+        dzt[i] = a0[STATE_D + i] + dh1[(size_t)b * 1088 + 1024 + i] + dh2[(size_t)b * 1088 + 1024 + i] +
+                 dh3[(size_t)b * 576 + 512 + i];
+    } else {
+      for (int i = lane; i < STATE_D; i += 32) dn[i] = 0.f;
+    }
   }
-  float* dr = draw + (size_t)b * RAW_LD;
-  glue_step_bwd(xin + (size_t)b * XIN_LD, raw + (size_t)b * RAW_LD, G + (size_t)b * 12, t2j + b * 4, dn,
-                dworld + (size_t)b * WORLD_LD, dGnext, dx, dr, dG + (size_t)b * 12, dt2j + b * 4);
-  for (int i = RAW_D; i < RAW_LD; ++i) dr[i] = 0.f;
+  __syncwarp();
+  float Gr[9], Gt[3], t2j[3], tr[3], R0[9], D[9], Ra[9], dGn[12];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) Gr[e] = G[(size_t)b * 12 + e];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { Gt[i] = G[(size_t)b * 12 + 9 + i]; t2j[i] = t2jg[b * 4 + i]; tr[i] = sx[i] + sr[i]; }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) dGn[i] = have_next ? dGn_g[(size_t)b * 12 + i] : 0.f;
+  rodrigues_fwd(sr + 6, D);
+  mat3_mul(D, sx + 6, R0);
+  w2a_fwd(R0, Ra);
+  const float ta[3] = {-tr[0], -tr[1], 0.f};
+  // per-lane partial sums of the root-level adjoints
+  float dRa[9], dGr[9], dGt[3] = {0.f, 0.f, 0.f}, dta[3] = {0.f, 0.f, 0.f}, d2j[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { dRa[e] = 0.f; dGr[e] = 0.f; }
+  float dR0[9], dtr[3] = {0.f, 0.f, 0.f};            // lane 25 / lane 22 private
+#pragma unroll
+  for (int e = 0; e < 9; ++e) dR0[e] = 0.f;
+
+  if (lane < NJ) {
+    const int k = lane;
+    float p[3], v[3], a[3], dp[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f}, du[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      p[i] = sx[207 + 3 * k + i] + sr[75 + 3 * k + i];
+      v[i] = sx[273 + 3 * k + i] + sr[141 + 3 * k + i];
+      a[i] = p[i] + ta[i] + t2j[i];
+    }
+    const float* dnj = dn + 207 + 3 * k;
+    const float* dwj = dw + 207 + 3 * k;
+    mv_bwd(Ra, a, dnj, dRa, du);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { dp[i] += du[i]; dta[i] += du[i]; d2j[i] += du[i] - dnj[i]; du[i] = 0.f; a[i] = p[i] + t2j[i]; }
+    mtv_bwd(Gr, a, dwj, dGr, du);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { dp[i] += du[i]; d2j[i] += du[i] - dwj[i]; dGt[i] -= dwj[i]; }
+    mv_bwd(Ra, v, dn + 273 + 3 * k, dRa, dv);
+    mtv_bwd(Gr, v, dw + 273 + 3 * k, dGr, dv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      dx[207 + 3 * k + i] = dp[i]; dr[75 + 3 * k + i] = dp[i];
+      dx[273 + 3 * k + i] = dv[i]; dr[141 + 3 * k + i] = dv[i];
+    }
+    if (k > 0) {
+      const int j = k - 1;
+      float Dj[9], dRj[9], dD[9], dRin[9];
+      rodrigues_fwd(sr + 12 + 3 * j, Dj);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { dRj[e] = dn[18 + 9 * j + e] + dw[18 + 9 * j + e]; dD[e] = 0.f; dRin[e] = 0.f; }
+      mat3_mul_bwd(Dj, sx + 18 + 9 * j, dRj, dD, dRin);
+      float daa[3] = {0.f, 0.f, 0.f};
+      rodrigues_bwd(sr + 12 + 3 * j, dD, daa);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) dx[18 + 9 * j + e] = dRin[e];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dr[12 + 3 * j + i] = daa[i];
+    }
+  } else if (lane == 22) {
+    float dwt[3] = {dw[0] - dGn[9], dw[1] - dGn[10], dw[2]};
+    mtv_bwd(Gr, tr, dwt, dGr, dtr);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dGt[i] -= dwt[i];
+    float u[3] = {tr[0] + ta[0], tr[1] + ta[1], tr[2] + ta[2]};
+    float du[3] = {0.f, 0.f, 0.f};
+    mv_bwd(Ra, u, dn + 0, dRa, du);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { dtr[i] += du[i]; dta[i] += du[i]; }
+  } else if (lane == 23) {
+    float tv[3] = {sx[3] + sr[3], sx[4] + sr[4], sx[5] + sr[5]}, dtv[3] = {0.f, 0.f, 0.f};
+    mv_bwd(Ra, tv, dn + 3, dRa, dtv);
+    mtv_bwd(Gr, tv, dw + 3, dGr, dtv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { dx[3 + i] = dtv[i]; dr[3 + i] = dtv[i]; }
+  } else if (lane == 24) {
+    float rv[3] = {sx[15] + sr[9], sx[16] + sr[10], sx[17] + sr[11]}, drv[3] = {0.f, 0.f, 0.f};
+    mv_bwd(Ra, rv, dn + 15, dRa, drv);
+    mtv_bwd(Gr, rv, dw + 15, dGr, drv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { dx[15 + i] = drv[i]; dr[9 + i] = drv[i]; }
+  } else if (lane == 25) {
+    mat3_mul_bwd(Gr, Ra, dGn, dGr, dRa);                 // Gnext = Gr Ra
+    const float* dW = dw + 6;                            // world.R0 = Gr^T R0
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float a = 0.f, bb = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { a += R0[i * 3 + k] * dW[j * 3 + k]; bb += Gr[i * 3 + k] * dW[k * 3 + j]; }
+        dGr[i * 3 + j] += a;
+        dR0[i * 3 + j] += bb;
+      }
+    mat3_mul_bwd(Ra, R0, dn + 6, dRa, dR0);              // next.R0 = Ra R0
+#pragma unroll
+    for (int c = 0; c < 9; ++c) dr[207 + c] = dw[339 + c];
+    for (int c = RAW_D; c < RAW_LD; ++c) dr[c] = 0.f;
+  }
+  // ---- warp totals (every lane receives them)
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { dRa[e] = warp_sum(dRa[e]); dGr[e] = warp_sum(dGr[e]); }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { dGt[i] = warp_sum(dGt[i]); dta[i] = warp_sum(dta[i]); d2j[i] = warp_sum(d2j[i]); }
+  if (lane == 25) {
+    w2a_bwd(R0, dRa, dR0);                               // Ra = w2a(R0)
+    float dD[9], dRin[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { dD[e] = 0.f; dRin[e] = 0.f; }
+    mat3_mul_bwd(D, sx + 6, dR0, dD, dRin);              // R0 = D xin.R0
+    float daa[3] = {0.f, 0.f, 0.f};
+    rodrigues_bwd(sr + 6, dD, daa);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) dx[6 + e] = dRin[e];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dr[6 + i] = daa[i];
+  } else if (lane == 22) {
+    dtr[0] -= dta[0];                                    // ta = (-tr.x, -tr.y, 0)
+    dtr[1] -= dta[1];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { dx[i] = dtr[i]; dr[i] = dtr[i]; }
+  } else if (lane == 0) {
+    float* g = dG + (size_t)b * 12;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) g[e] = dGr[e];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      g[9 + i] = dGt[i];
+      dt2j[b * 4 + i] = (have_next ? dt2j[b * 4 + i] : 0.f) + d2j[i];
+    }
+  }
+  __syncwarp();
+  float* xo = dxres + (size_t)b * 340;
+  float* ro = draw + (size_t)b * RAW_LD;
+  for (int i = lane; i < STATE_D; i += 32) xo[i] = dx[i];
+  for (int i = lane; i < RAW_LD; i += 32) ro[i] = dr[i];
 }
 
 __global__ void rollout_bwd_final_kernel(int B, int S, const float* __restrict__ dxres, const float* __restrict__ da0,
@@ -168,7 +390,7 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
   HB_CUDA(cudaMemsetAsync(tp.h1, 0, ((size_t)B * 1088 * 2 + (size_t)B * 576 + 256) * sizeof(float), st));
   rollout_init_kernel<<<B, 128, 0, st>>>(B, S, init_state, z_seq, tp.xins, tp.Gs, tp.t2j, tp.h1, tp.h2, tp.h3);
   HB_LAUNCH_CHECK(); ++nl;
-  const int gb = cdiv(B, 32);
+  const int gb = cdiv(B, GLUE_WARPS);
   for (int t = 0; t < S; ++t) {
     const size_t r = (size_t)t * B;
     float* xin = tp.xins + r * XIN_LD;
@@ -179,7 +401,7 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
     HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.h2, 1088, w->dec_w[2], 1088, tp.h3, 576, B, 512, 1088,
                                      epi_gn(w->dec_b[2], w->dec_g[2], w->dec_be[2], tp.dxh3 + r * 512, 512, tp.drs3 + r * 16, 512, 32), st));
     HB_CUDA(launch_gemm<EPI_BIAS>(tp.h3, 576, w->dec_w[3], 576, tp.raws + r * RAW_LD, RAW_LD, B, 216, 576, epi_bias(w->dec_b[3]), st));
-    glue_fwd_kernel<<<gb, 32, 0, st>>>(B, S, t, xin, tp.raws + r * RAW_LD, tp.Gs + r * 12, tp.t2j, z_seq,
+    glue_fwd_kernel<<<gb, GLUE_WARPS * 32, 0, st>>>(B, S, t, xin, tp.raws + r * RAW_LD, tp.Gs + r * 12, tp.t2j, z_seq,
                                        tp.xins + (r + B) * XIN_LD, world + r * WORLD_LD, tp.Gs + (r + B) * 12, tp.h1, tp.h2, tp.h3);
     HB_LAUNCH_CHECK();
     nl += 5;
@@ -223,14 +445,14 @@ extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* w
   } else {
     HB_CUDA(cudaMemsetAsync(tp.dpx, 0, (size_t)M * 352 * sizeof(float), st));
   }
-  const int gb = cdiv(B, 32);
+  const int gb = cdiv(B, GLUE_WARPS);
   float* dGbuf[2] = {tp.dG0, tp.dG1};
   for (int t = S - 1; t >= 0; --t) {
     const size_t r = (size_t)t * B;
     const int have_next = (t + 1 < S);
     float* dGn = dGbuf[(t + 1) & 1];
     float* dGc = dGbuf[t & 1];
-    glue_bwd_kernel<<<gb, 32, 0, st>>>(B, S, t, have_next, tp.xins + r * XIN_LD, tp.raws + r * RAW_LD, tp.Gs + r * 12, tp.t2j,
+    glue_bwd_kernel<<<gb, GLUE_WARPS * 32, 0, st>>>(B, S, t, have_next, tp.xins + r * XIN_LD, tp.raws + r * RAW_LD, tp.Gs + r * 12, tp.t2j,
                                        d_world + r * WORLD_LD, tp.da0, tp.dpx + (r + B) * 352, tp.dh1, tp.dh2, tp.dh3,
                                        tp.dxres, tp.dnsum, dGn, dGc, tp.dt2j, tp.draw, d_z);
     HB_LAUNCH_CHECK();

@@ -124,16 +124,18 @@ def run_product(args):
     prob = build_problem(B, T, seed=4 + rank)
     mo = make_optimizer(B, T, prob, dev)
     prob = project_obs_from_product(mo, prob, dev)
+    # global frame intervals of this rank's block of sub-sequences (one video split across the ranks)
+    prob['obs']['seq_interval'] = prob['obs']['seq_interval'] + rank * B * (T - 10)
+    if world > 1:
+        from humor_b200.parallel import Shard
+        mo.shard = Shard.from_env(ov_max=16)
     names = mo.set_stage3_state(prob['params'])
     obs = {k: torch.as_tensor(prob['obs'][k]).to(dev) for k in OBS_KEYS}
     params = [getattr(mo, n) for n in names]
+    mo.use_cuda_graph = (world == 1) and not args.no_graph
 
     def step():
-        for p in params:
-            p.grad = None
-        loss, _, _, _, _ = mo.stage3_forward(obs)
-        loss.backward()
-        return loss
+        return mo.stage3_step(obs, params=params)
 
     def barrier():
         if world > 1:
@@ -208,6 +210,8 @@ def run_product(args):
         'config': {'workload': f'Stage-III full-T closure fwd+bwd, B={B} sub-sequences/GPU x T={T}, RGB config '
                                '(optim_floor, fit_rgb_demo_use_split stage-3 weights, overlap 10)',
                    'batch_per_gpu': B, 'seq_len': T, 'parallelism': f'dp{world} over sub-sequences',
+                   'cuda_graph': bool(mo.use_cuda_graph),
+                   'collectives_per_step': 0 if world == 1 else 'all_gather(halo pack) fwd + all_reduce(halo grad) bwd',
                    'l2': 'working set per step (rollout tape 0.45 GB + dense vertices 1.3 GB) exceeds the 126 MB L2'},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
@@ -252,6 +256,7 @@ def kernel_shares(mo, obs, params, dev):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for p in params:
         p.grad = None
+    mo.use_cuda_graph = False
     torch.cuda.synchronize()
     ev[0].record()
     loss, _, _, _, _ = mo.stage3_forward(obs)
@@ -331,6 +336,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=8)
     ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='evaluate the closure eagerly instead of replaying a CUDA graph')
     ap.add_argument('--_cpu-child', dest='cpu_child', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--cpu-threads', type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -334,7 +334,11 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
                                              need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo);
   HB_LAUNCH_CHECK(); ++nl;
   if (need_skin) {
-    HB_CUDA(cudaFuncSetAttribute(lbs_skin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKIN_FWD_SMEM));
+    static bool attr_fwd = false;     // once per process (and outside any stream capture: the first call is a warm-up)
+    if (!attr_fwd) {
+      HB_CUDA(cudaFuncSetAttribute(lbs_skin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKIN_FWD_SMEM));
+      attr_fwd = true;
+    }
     if (verts) {
       const int nvv = vlist ? nv : m->num_verts;
       if (nvv > 0) {
@@ -370,7 +374,11 @@ extern "C" int humor_lbs_bwd(const HbLbsModel* m, int N, int fpb, const float* r
     // recompute the per-frame forward (feature rows, skinning transforms): cheaper than keeping them
     lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52);
     HB_LAUNCH_CHECK(); ++nl;
-    HB_CUDA(cudaFuncSetAttribute(lbs_skin_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKIN_BWD_SMEM));
+    static bool attr_bwd = false;
+    if (!attr_bwd) {
+      HB_CUDA(cudaFuncSetAttribute(lbs_skin_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKIN_BWD_SMEM));
+      attr_bwd = true;
+    }
     int acc = 0;
     if (d_verts) {
       const int nvv = vlist ? nv : m->num_verts;

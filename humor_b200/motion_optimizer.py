@@ -86,6 +86,12 @@ class MotionOptimizer():
                                         self.cam_center, robust_loss_type, robust_tuning_const,
                                         joints2d_sigma=joint2d_sigma, use_chamfer=use_chamfer).to(device)
         self.return_points3d = True      # dense vertices in every camera-frame SMPL evaluation (reference behaviour)
+        # multi-GPU: this process owns a contiguous block of the sub-sequences; the overlap energies that couple
+        # the last sequence of rank r with the first of rank r+1 are exchanged as small halos (parallel.py)
+        self.shard = None
+        # CUDA-graph capture of the Stage-III closure (forward + backward): one replay per L-BFGS evaluation
+        self.use_cuda_graph = False
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------------
     # SMPL
@@ -242,8 +248,68 @@ class MotionOptimizer():
             self.fitting_loss.loss_weights['rgb_overlap_consist'] = 0.0
         loss, stats = self.fitting_loss.motion_fit(loss_obs, pred, cam_pred, loss_nsteps,
                                                    init_motion_scale=init_motion_scale)
+        if self.shard is not None and self.shard.world > 1 and 'seq_interval' in loss_obs \
+                and self.fitting_loss.loss_weights['rgb_overlap_consist'] > 0.0:
+            from .parallel import boundary_overlap_energy
+            e, bstats = boundary_overlap_energy(self.shard, cam_pred['verts3d'], self.betas,
+                                                self.floor_plane if self.optim_floor else None,
+                                                loss_obs['seq_interval'], self.seq_len)
+            loss = loss + self.fitting_loss.loss_weights['rgb_overlap_consist'] * e
+            for k, v in bstats.items():
+                stats[k] = stats[k] + v if k in stats else v
         self.fitting_loss.loss_weights['rgb_overlap_consist'] = saved_ov
         return loss, stats, roll, cam, cam_pred
+
+    # ------------------------------------------------------------------------------------------------
+    # CUDA-graphed closure
+    # ------------------------------------------------------------------------------------------------
+    def stage3_step(self, observed_data, nsteps=None, init_motion_scale=1.0, params=None):
+        """One Stage-III closure evaluation: zero grads, forward, backward.  Returns the loss tensor (device);
+        gradients land in ``.grad`` of the stage-3 variables that require grad.  With ``use_cuda_graph`` the whole
+        evaluation (several hundred launches) is captured once per (phase, weights, trainable-set) and replayed."""
+        params = self.stage3_params() if params is None else params
+        if not self.use_cuda_graph:
+            for p in params:
+                p.grad = None
+            loss, _, _, _, _ = self.stage3_forward(observed_data, nsteps, init_motion_scale)
+            loss.backward()
+            return loss
+        from . import _ext
+        w = self.fitting_loss.loss_weights
+        key = (nsteps, float(init_motion_scale), tuple(bool(p.requires_grad) for p in params),
+               tuple(sorted((k, float(v)) for k, v in w.items())), tuple(id(p) for p in params),
+               tuple((k, v.data_ptr()) for k, v in sorted(observed_data.items()) if torch.is_tensor(v)))
+        g = self._graphs.get(key)
+        if g is None:
+            for p in params:
+                if p.requires_grad and p.grad is None:
+                    p.grad = torch.zeros_like(p)          # static gradient buffers the graph writes into
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                        # warm-up: allocator pools, lazy module state
+                    self._eval_into_static(observed_data, nsteps, init_motion_scale, params)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            l0 = _ext.LaunchCounter.total
+            with torch.cuda.graph(graph):
+                static_loss = self._eval_into_static(observed_data, nsteps, init_motion_scale, params)
+            g = (graph, static_loss, _ext.LaunchCounter.total - l0)
+            self._graphs[key] = g
+        g[0].replay()
+        _ext.LaunchCounter.total += g[2]
+        return g[1]
+
+    def _eval_into_static(self, observed_data, nsteps, scale, params):
+        loss, _, _, _, _ = self.stage3_forward(observed_data, nsteps, scale)
+        live = [p for p in params if p.requires_grad]
+        grads = torch.autograd.grad(loss, live, allow_unused=True)
+        for p, gr in zip(live, grads):
+            if gr is None:
+                p.grad.zero_()
+            else:
+                p.grad.copy_(gr)
+        return loss.detach()
 
     def stage3_params(self):
         p = [self.trans, self.root_orient, self.latent_pose, self.betas, self.latent_motion,
@@ -440,10 +506,7 @@ class MotionOptimizer():
             nsteps = nfr if (tune and i < self.stage3_tune_init_freeze_start) else None
 
             def closure():
-                motion_optim.zero_grad()
-                loss, _, _, _, _ = self.stage3_forward(observed_data, nsteps, scale, fit_gender)
-                loss.backward()
-                return loss
+                return self.stage3_step(observed_data, nsteps, scale, all_params)
             motion_optim.step(closure)
 
         # ---- final rollout (motion_optimizer.py:612-676)

@@ -1,0 +1,100 @@
+"""Multi-GPU sharding of the Stage-III batch.
+
+One process per GPU; rank r owns the contiguous sub-sequences [r*B_local, (r+1)*B_local) of one video and
+their 2 961 optimisation variables each.  Every energy is per-sequence except the overlap-consistency terms
+(fitting_loss.py:136-157 key-vertex positions/velocities, :211-215 betas, :296-300 floor), which couple
+ADJACENT sequences only.  Inside a rank they are evaluated by the fused kernel; across the rank boundary the
+last sequence of rank r and the first of rank r+1 exchange a halo:
+
+    tail pack of rank r  = [ verts3d[-1, T-ov_max:T] (ov_max*43*3) | betas[-1] (16) | floor[-1] (3) ]
+
+Forward: one all_gather of the packs (a few KB, latency-bound; NCCL over NVLink on GPUs, gloo in the CPU
+tests); the receiving rank r+1 evaluates the boundary energy.  Backward: the gradient w.r.t. the received
+pack is all_gathered back and rank r adds the slice that belongs to its tail.  Scalars shared by a joint
+L-BFGS (loss, directional derivatives) go through `allreduce_scalars` — one collective per evaluation.
+"""
+import torch
+import torch.distributed as dist
+
+
+class Shard:
+    def __init__(self, rank=0, world=1, group=None, ov_max=16):
+        self.rank, self.world, self.group, self.ov_max = rank, world, group, ov_max
+
+    @staticmethod
+    def from_env(ov_max=16):
+        if dist.is_available() and dist.is_initialized():
+            return Shard(dist.get_rank(), dist.get_world_size(), None, ov_max)
+        return Shard()
+
+
+class _GatherPacks(torch.autograd.Function):
+    """all_gather with the matching reverse: d(pack_r) = sum over ranks of their gradient w.r.t. slot r."""
+
+    @staticmethod
+    def forward(ctx, shard, pack):
+        out = [torch.empty_like(pack) for _ in range(shard.world)]
+        dist.all_gather(out, pack.contiguous(), group=shard.group)
+        ctx.shard = shard
+        return torch.stack(out, 0)
+
+    @staticmethod
+    def backward(ctx, d_all):
+        shard = ctx.shard
+        d_all = d_all.contiguous()
+        dist.all_reduce(d_all, op=dist.ReduceOp.SUM, group=shard.group)
+        return None, d_all[shard.rank]
+
+
+def tail_pack(shard, verts3d, betas, floor, T):
+    """[ov_max*129 + 16 + 3] floats describing the LAST local sequence (zero-padded in front when T < ov_max)."""
+    ov = shard.ov_max
+    v = verts3d[-1, max(0, T - ov):T].reshape(-1)
+    if v.numel() < ov * 129:
+        v = torch.cat([torch.zeros(ov * 129 - v.numel(), device=v.device, dtype=v.dtype), v])
+    f = floor[-1] if floor is not None else torch.zeros(3, device=v.device, dtype=v.dtype)
+    return torch.cat([v, betas[-1, :16], f])
+
+
+def boundary_overlap_energy(shard, verts3d, betas, floor, seq_interval, T):
+    """Overlap-consistency energy between this rank's FIRST sequence and the previous rank's LAST one
+    (unweighted; same formulas as fitting_loss.py:142-157,211-215,296-300).  Needs the global interval of the
+    previous rank's last sequence: seq_interval holds the LOCAL rows, so its end is gathered with the pack."""
+    dev = verts3d.device
+    ov_max = shard.ov_max
+    pack = tail_pack(shard, verts3d, betas, floor, T)
+    iv = seq_interval.to(device=dev, dtype=verts3d.dtype)
+    pack = torch.cat([pack, iv[-1, 1:2]])                               # + end frame of my last sequence
+    allp = _GatherPacks.apply(shard, pack)                              # (world, P)
+    zero = verts3d.sum() * 0.0
+    stats = {}
+    if shard.rank == 0:
+        return zero + allp.sum() * 0.0, stats                           # keeps the reverse collective symmetric
+    prev = allp[shard.rank - 1]
+    ov = int(round(float(prev[-1].item()))) - int(seq_interval[0, 0].item())
+    if ov <= 0:
+        return zero + allp.sum() * 0.0, stats
+    if ov > ov_max or ov > T:
+        raise ValueError(f'overlap {ov} exceeds the halo capacity {ov_max} / sequence length {T}')
+    a = prev[:ov_max * 129].reshape(ov_max, 43, 3)[ov_max - ov:]        # tail of the previous rank's last sequence
+    c = verts3d[0, :ov]
+    d = a - c
+    pos = 0.5 * (d ** 2).sum()
+    vel = 0.5 * ((d[1:] - d[:-1]) ** 2).sum() if ov > 1 else zero
+    bet = 0.5 * ((prev[ov_max * 129:ov_max * 129 + 16] - betas[0, :16]) ** 2).sum()
+    e = pos + vel + bet
+    stats = {'rgb_overlap_consist_verts3d_pos': pos.detach(), 'rgb_overlap_consist_verts3d_vel': vel.detach() if ov > 1 else zero.detach(),
+             'rgb_overlap_consist_betas': bet.detach()}
+    if floor is not None:
+        fl = 0.5 * ((prev[ov_max * 129 + 16:ov_max * 129 + 19] - floor[0]) ** 2).sum()
+        e = e + fl
+        stats['rgb_overlap_consist_floor'] = fl.detach()
+    return e + allp.sum() * 0.0, stats
+
+
+def allreduce_scalars(shard, values):
+    """Sum a small vector of per-rank scalars (loss, g.d, y.s, y.y, ...) in ONE collective."""
+    if shard is None or shard.world == 1:
+        return values
+    dist.all_reduce(values, op=dist.ReduceOp.SUM, group=shard.group)
+    return values

@@ -116,3 +116,32 @@ def test_closure_matches_reference_golden(name):
     assert np.abs(aux['roll']['trans'].detach().cpu().numpy() - g['rollout_trans']).max() < 2e-5
     pm = aux['roll']['cond_prior'][0].detach().cpu().numpy()
     assert np.abs(pm - g['cond_prior_mean']).max() / np.abs(g['cond_prior_mean']).max() < 1e-5
+
+
+def test_cuda_graph_step_matches_eager():
+    """stage3_step with use_cuda_graph replays a captured forward+backward: same loss and gradients as eager,
+    and it tracks in-place parameter updates (what L-BFGS does between evaluations)."""
+    B, T = 4, 8
+    prob = synth.make_stage3_problem(B, T, seed=6, overlap=3)
+    mo = U.build_product(B, T, synth.RGB_STAGE3_WEIGHTS, True, prob)
+    names = mo.set_stage3_state(prob['params'])
+    obs = {k: torch.as_tensor(v).cuda() for k, v in prob['obs'].items() if k in U.obs_keys(True)}
+    params = [getattr(mo, n) for n in names]
+    mo.use_cuda_graph = False
+    l_e = float(mo.stage3_step(obs, params=params))
+    g_e = [p.grad.clone() for p in params]
+    mo.use_cuda_graph = True
+    l_g = float(mo.stage3_step(obs, params=params))
+    assert abs(l_g - l_e) <= 1e-6 * abs(l_e)
+    for a, p in zip(g_e, params):
+        assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-6 * float(a.abs().max()))
+    with torch.no_grad():
+        mo.latent_motion.mul_(0.9)
+        mo.betas.add_(0.05)
+    l_g2 = float(mo.stage3_step(obs, params=params))        # replay on the updated values
+    g_g2 = [p.grad.clone() for p in params]
+    mo.use_cuda_graph = False
+    l_e2 = float(mo.stage3_step(obs, params=params))
+    assert abs(l_g2 - l_e2) <= 1e-6 * abs(l_e2) and abs(l_g2 - l_g) > 1e-3
+    for a, p in zip(g_g2, params):
+        assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-6 * float(a.abs().max()))

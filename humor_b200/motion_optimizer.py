@@ -292,8 +292,15 @@ class MotionOptimizer():
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             l0 = _ext.LaunchCounter.total
-            with torch.cuda.graph(graph):
-                static_loss = self._eval_into_static(observed_data, nsteps, init_motion_scale, params)
+            try:
+                with torch.cuda.graph(graph):
+                    static_loss = self._eval_into_static(observed_data, nsteps, init_motion_scale, params)
+            except RuntimeError as e:       # e.g. an injected pose prior that syncs or copies from the host
+                import warnings
+                warnings.warn(f'Stage-III closure is not CUDA-graph capturable ({e}); falling back to eager launches')
+                self.use_cuda_graph = False
+                torch.cuda.synchronize()
+                return self.stage3_step(observed_data, nsteps, init_motion_scale, params)
             g = (graph, static_loss, _ext.LaunchCounter.total - l0)
             self._graphs[key] = g
         g[0].replay()

@@ -184,15 +184,13 @@ class FakeVPoser(nn.Module):
         self.b2 = f32(0.02 * rng.randn(126))
         self.we = f32(rng.randn(63, 32) / math.sqrt(63))
         self.be = f32(0.1 * rng.randn(32))
+        self.base6d = f32(np.array([[1.0, 0.0], [0.0, 1.0], [0.0, 0.0]]))
 
     def decode(self, z, output_type='matrot'):
         assert output_type == 'matrot'
         h = torch.tanh(z @ self.w1 + self.b1)
         o = (h @ self.w2 + self.b2).reshape(-1, 21, 3, 2)
-        base = torch.zeros(3, 2, dtype=z.dtype, device=z.device)
-        base[0, 0] = 1.0
-        base[1, 1] = 1.0
-        o = o + base
+        o = o + self.base6d
         a1, a2 = o[..., 0], o[..., 1]
         b1 = a1 / a1.norm(dim=-1, keepdim=True)
         b2 = a2 - (b1 * a2).sum(-1, keepdim=True) * b1

@@ -92,6 +92,7 @@ class MotionOptimizer():
         # CUDA-graph capture of the Stage-III closure (forward + backward): one replay per L-BFGS evaluation
         self.use_cuda_graph = False
         self._graphs = {}
+        self._contact_idx = torch.tensor(CONTACT_INDS, dtype=torch.long, device=device)
 
     # ------------------------------------------------------------------------------------------------
     # SMPL
@@ -193,7 +194,7 @@ class MotionOptimizer():
         with torch.no_grad():
             conf9 = torch.sigmoid(out['contacts_logits'])
             conf = torch.zeros(B, S, NUM_JOINTS, device=conf9.device)
-            conf[:, :, CONTACT_INDS] = conf9
+            conf.index_copy_(2, self._contact_idx, conf9)          # device index: no host copy (graph-capturable)
             conf = torch.cat([conf[:, 0:1], conf], 1)
             out['contacts_conf'] = conf
             out['contacts'] = (conf > CONTACT_THRESH).to(torch.float)
@@ -296,8 +297,11 @@ class MotionOptimizer():
                 with torch.cuda.graph(graph):
                     static_loss = self._eval_into_static(observed_data, nsteps, init_motion_scale, params)
             except RuntimeError as e:       # e.g. an injected pose prior that syncs or copies from the host
+                import traceback
                 import warnings
-                warnings.warn(f'Stage-III closure is not CUDA-graph capturable ({e}); falling back to eager launches')
+                where = traceback.format_exc().strip().splitlines()[-6:-1]
+                warnings.warn(f'Stage-III closure is not CUDA-graph capturable ({e}); falling back to eager launches. '
+                              f'At: {" | ".join(x.strip() for x in where)}')
                 self.use_cuda_graph = False
                 torch.cuda.synchronize()
                 return self.stage3_step(observed_data, nsteps, init_motion_scale, params)

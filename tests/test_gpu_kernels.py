@@ -227,7 +227,7 @@ def test_roll_out_api_dict(humor):
     """HumorModel.roll_out keeps the reference's call surface and output dict."""
     B, S = 3, 4
     x0 = torch.tensor(make_state(B, 1)).cuda()
-    z = torch.randn(B, S, 48, device='cuda') * 0.3
+    z = (torch.randn(B, S, 48) * 0.3).cuda()
     names, dims = ['trans', 'trans_vel', 'root_orient', 'root_orient_vel', 'pose_body', 'joints', 'joints_vel'], [3, 3, 9, 3, 189, 66, 66]
     init, s = {}, 0
     for n, d in zip(names, dims):

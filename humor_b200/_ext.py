@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libhumor_b200.so')
-SOURCES = ['rollout.cu', 'lbs.cu', 'rot.cu', 'losses.cu']
+SOURCES = ['rollout.cu', 'lbs.cu', 'rot.cu', 'losses.cu', 'umma_gemm.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -72,7 +72,8 @@ class HbHumorWeights(C.Structure):
     _fields_ = [('dec_w', C.c_void_p * 4), ('dec_b', C.c_void_p * 4), ('dec_g', C.c_void_p * 3),
                 ('dec_be', C.c_void_p * 3), ('dec_wt', C.c_void_p * 4), ('pri_w', C.c_void_p * 5),
                 ('pri_b', C.c_void_p * 5), ('pri_g', C.c_void_p * 4), ('pri_be', C.c_void_p * 4),
-                ('pri_wt', C.c_void_p * 5)]
+                ('pri_wt', C.c_void_p * 5), ('pri_w_hi', C.c_void_p * 5), ('pri_w_lo', C.c_void_p * 5),
+                ('pri_wt_hi', C.c_void_p * 5), ('pri_wt_lo', C.c_void_p * 5), ('use_umma', C.c_int), ('reserved', C.c_int)]
 
 
 class HbFitArgs(C.Structure):
@@ -93,7 +94,8 @@ class HbFitArgs(C.Structure):
 
 EXPORTS = ['humor_lbs_workspace_bytes', 'humor_lbs_fwd', 'humor_lbs_bwd', 'humor_rollout_workspace_bytes',
            'humor_rollout_fwd', 'humor_rollout_bwd', 'humor_rodrigues_fwd', 'humor_rodrigues_bwd',
-           'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version']
+           'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version',
+           'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes']
 
 _LIB = None
 
@@ -131,6 +133,10 @@ def lib():
     L.humor_fit_losses.argtypes = [C.POINTER(HbFitArgs), i64p, vp]
     L.humor_gmm_nll.restype = ci
     L.humor_gmm_nll.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.humor_umma_gemm_workspace_bytes.restype = sz
+    L.humor_umma_gemm_workspace_bytes.argtypes = [ci, ci, ci, ci]
+    L.humor_umma_gemm.restype = ci
+    L.humor_umma_gemm.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, vp, sz, vp]
     L.humor_b200_version.restype = C.c_char_p
     _LIB = L
     return L

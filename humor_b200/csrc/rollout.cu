@@ -11,6 +11,7 @@
 //     cat(x, z) skip connections are free (z is written once into the padded tail columns).
 #include "gemm.cuh"
 #include "rollout_glue.cuh"
+#include "umma_launch.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
@@ -22,6 +23,7 @@ struct Tape {
   float *h1, *h2, *h3;                 // decoder transients [B][1088],[B][1088],[B][576]
   float *pa, *pb;                      // prior ping-pong [S*B][1024]
   float *dh3, *dh2, *dh1, *da0, *draw, *dxres, *dnsum, *dG0, *dG1, *dt2j, *dpx;
+  float *xin_hi, *xin_lo, *pa_lo, *pb_lo, *dpo_hi, *dpo_lo;   // operand planes of the tensor-core prior (pa/pb hold hi)
   size_t total;
 };
 
@@ -45,6 +47,9 @@ static Tape carve(float* base, int B, int S) {
   t.dxres = take((size_t)B * 340); t.dnsum = take((size_t)B * 340);
   t.dG0 = take((size_t)B * 12); t.dG1 = take((size_t)B * 12); t.dt2j = take((size_t)B * 4);
   t.dpx = take(M * 352);
+  t.xin_hi = take(M * XIN_LD); t.xin_lo = take(M * XIN_LD);
+  t.pa_lo = take(M * 1024); t.pb_lo = take(M * 1024);
+  t.dpo_hi = take(M * 96); t.dpo_lo = take(M * 96);
   t.total = off;
   return t;
 }
@@ -408,16 +413,36 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
   }
   if (prior_out) {
     const int M = S * B;
-    HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.xins, XIN_LD, w->pri_w[0], 352, tp.pa, 1024, M, 1024, 352,
-                                     epi_gn(w->pri_b[0], w->pri_g[0], w->pri_be[0], tp.pxh1, 1024, tp.prs1, 1024, 64), st));
-    HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.pa, 1024, w->pri_w[1], 1024, tp.pb, 1024, M, 1024, 1024,
-                                     epi_gn(w->pri_b[1], w->pri_g[1], w->pri_be[1], tp.pxh2, 1024, tp.prs2, 1024, 64), st));
-    HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.pb, 1024, w->pri_w[2], 1024, tp.pa, 1024, M, 1024, 1024,
-                                     epi_gn(w->pri_b[2], w->pri_g[2], w->pri_be[2], tp.pxh3, 1024, tp.prs3, 1024, 64), st));
-    HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.pa, 1024, w->pri_w[3], 1024, tp.pb, 1024, M, 1024, 1024,
-                                     epi_gn(w->pri_b[3], w->pri_g[3], w->pri_be[3], tp.pxh4, 1024, tp.prs4, 1024, 64), st));
-    HB_CUDA(launch_gemm<EPI_BIAS>(tp.pb, 1024, w->pri_w[4], 1024, prior_out, 96, M, 96, 1024, epi_bias(w->pri_b[4]), st));
-    nl += 5;
+    if (w->use_umma && umma_available()) {
+      // batched prior on the 5th-gen tensor cores (3xTF32): activations travel as hi/lo planes
+      HB_CUDA(launch_split_hilo(tp.xins, tp.xin_hi, tp.xin_lo, (size_t)M * XIN_LD, st));
+      float* hi[2] = {tp.pa, tp.pb};
+      float* lo[2] = {tp.pa_lo, tp.pb_lo};
+      float* xh[4] = {tp.pxh1, tp.pxh2, tp.pxh3, tp.pxh4};
+      float* rs[4] = {tp.prs1, tp.prs2, tp.prs3, tp.prs4};
+      const float* a_hi = tp.xin_hi;
+      const float* a_lo = tp.xin_lo;
+      int lda = XIN_LD, K = 352;
+      for (int l = 0; l < 4; ++l) {
+        HB_CUDA(launch_umma_gemm3(a_hi, a_lo, lda, w->pri_w_hi[l], w->pri_w_lo[l], K, M, 1024, K, nullptr, hi[l & 1], lo[l & 1], 1024,
+                                  EPI_GN_RELU, epi_gn(w->pri_b[l], w->pri_g[l], w->pri_be[l], xh[l], 1024, rs[l], 1024, 64), st));
+        a_hi = hi[l & 1]; a_lo = lo[l & 1]; lda = 1024; K = 1024;
+      }
+      HB_CUDA(launch_umma_gemm3(a_hi, a_lo, 1024, w->pri_w_hi[4], w->pri_w_lo[4], 1024, M, 96, 1024, prior_out, nullptr, nullptr, 96,
+                                EPI_BIAS, epi_bias(w->pri_b[4]), st));
+      nl += 6;
+    } else {
+      HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.xins, XIN_LD, w->pri_w[0], 352, tp.pa, 1024, M, 1024, 352,
+                                       epi_gn(w->pri_b[0], w->pri_g[0], w->pri_be[0], tp.pxh1, 1024, tp.prs1, 1024, 64), st));
+      HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.pa, 1024, w->pri_w[1], 1024, tp.pb, 1024, M, 1024, 1024,
+                                       epi_gn(w->pri_b[1], w->pri_g[1], w->pri_be[1], tp.pxh2, 1024, tp.prs2, 1024, 64), st));
+      HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.pb, 1024, w->pri_w[2], 1024, tp.pa, 1024, M, 1024, 1024,
+                                       epi_gn(w->pri_b[2], w->pri_g[2], w->pri_be[2], tp.pxh3, 1024, tp.prs3, 1024, 64), st));
+      HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.pa, 1024, w->pri_w[3], 1024, tp.pb, 1024, M, 1024, 1024,
+                                       epi_gn(w->pri_b[3], w->pri_g[3], w->pri_be[3], tp.pxh4, 1024, tp.prs4, 1024, 64), st));
+      HB_CUDA(launch_gemm<EPI_BIAS>(tp.pb, 1024, w->pri_w[4], 1024, prior_out, 96, M, 96, 1024, epi_bias(w->pri_b[4]), st));
+      nl += 5;
+    }
   }
   if (launches) *launches = nl;
   return HB_OK;
@@ -431,7 +456,25 @@ extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* w
   if (workspace_bytes < tp.total * sizeof(float)) return HB_ERR_WORKSPACE;
   int64_t nl = 0;
   const int M = S * B;
-  if (d_prior_out) {
+  if (d_prior_out && w->use_umma && umma_available()) {
+    HB_CUDA(launch_split_hilo(d_prior_out, tp.dpo_hi, tp.dpo_lo, (size_t)M * 96, st));
+    float* hi[2] = {tp.pa, tp.pb};
+    float* lo[2] = {tp.pa_lo, tp.pb_lo};
+    float* xh[4] = {tp.pxh1, tp.pxh2, tp.pxh3, tp.pxh4};
+    float* rs[4] = {tp.prs1, tp.prs2, tp.prs3, tp.prs4};
+    const float* a_hi = tp.dpo_hi;
+    const float* a_lo = tp.dpo_lo;
+    int lda = 96, K = 96;
+    for (int l = 4; l >= 1; --l) {            // reverse of Linear l, then GroupNorm/ReLU l-1
+      const int o = (4 - l) & 1;
+      HB_CUDA(launch_umma_gemm3(a_hi, a_lo, lda, w->pri_wt_hi[l], w->pri_wt_lo[l], K, M, 1024, K, nullptr, hi[o], lo[o], 1024,
+                                EPI_GN_RELU_BWD, epi_gn(nullptr, w->pri_g[l - 1], w->pri_be[l - 1], xh[l - 1], 1024, rs[l - 1], 1024, 64), st));
+      a_hi = hi[o]; a_lo = lo[o]; lda = 1024; K = 1024;
+    }
+    HB_CUDA(launch_umma_gemm3(a_hi, a_lo, 1024, w->pri_wt_hi[0], w->pri_wt_lo[0], 1024, M, 352, 1024, tp.dpx, nullptr, nullptr, 352,
+                              EPI_BIAS, epi_bias(nullptr), st));
+    nl += 6;
+  } else if (d_prior_out) {
     HB_CUDA(launch_gemm<EPI_GN_RELU_BWD>(d_prior_out, 96, w->pri_wt[4], 96, tp.pa, 1024, M, 1024, 96,
                                          epi_gn(nullptr, w->pri_g[3], w->pri_be[3], tp.pxh4, 1024, tp.prs4, 1024, 64), st));
     HB_CUDA(launch_gemm<EPI_GN_RELU_BWD>(tp.pa, 1024, w->pri_wt[3], 1024, tp.pb, 1024, M, 1024, 1024,

@@ -1,0 +1,114 @@
+// Host side of the tcgen05 GEMM: TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry
+// point, so the library does not link libcuda) and launches.
+#include "umma_gemm.cuh"
+#include "umma_launch.cuh"
+#include "../../include/humor_b200.h"
+
+namespace hb {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_encode_state = 0;      // 0 unknown, 1 ok, -1 unavailable
+
+static bool load_encode() {
+  if (g_encode_state == 0) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn) { g_encode = (EncodeTiledFn)fn; g_encode_state = 1; }
+    else { g_encode_state = -1; (void)cudaGetLastError(); }
+  }
+  return g_encode_state == 1;
+}
+bool umma_available() { return load_encode(); }
+
+// rows x K fp32 matrix, row stride ld floats; box = {32 floats, box_rows}, 128-byte swizzle, OOB rows read as zero
+static bool make_map(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows) {
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)UM_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int EPI>
+static cudaError_t launch_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                            int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, const GemmEpi& ep, cudaStream_t st) {
+  constexpr int BN = 128;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dim3 grid(cdiv(N, BN), cdiv(M, UM_BM));
+  umma_gemm3_kernel<BN, EPI><<<grid, 192, UmmaSmem<BN>::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, M, N, K, C, C_hi, C_lo, ldc, ep);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_umma_gemm3(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
+                              int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, int epi, const GemmEpi& ep,
+                              cudaStream_t st) {
+  if (!load_encode()) return cudaErrorNotSupported;
+  if (K % UM_BK || lda % 4 || ldb % 4 || ldc % 4) return cudaErrorInvalidValue;
+  if ((C_hi == nullptr) != (C_lo == nullptr)) return cudaErrorInvalidValue;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  if (!make_map(&ta_hi, A_hi, M, K, lda, UM_BM) || !make_map(&ta_lo, A_lo, M, K, lda, UM_BM) ||
+      !make_map(&tb_hi, B_hi, N, K, ldb, 128) || !make_map(&tb_lo, B_lo, N, K, ldb, 128))
+    return cudaErrorInvalidValue;
+  switch (epi) {
+    case EPI_BIAS: return launch_t<EPI_BIAS>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
+    case EPI_GN_RELU: return launch_t<EPI_GN_RELU>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
+    case EPI_GN_RELU_BWD: return launch_t<EPI_GN_RELU_BWD>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+__global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
+  if (n % 4) return cudaErrorInvalidValue;
+  const size_t n4 = n / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  split_hilo_kernel<<<blocks, 256, 0, st>>>(x, hi, lo, n4);
+  return cudaGetLastError();
+}
+
+}  // namespace hb
+using namespace hb;
+
+// Test / utility entry point: C = A * B^T (+bias) in fp32-level accuracy on the tensor cores.
+// workspace: 2*(M*lda + N*ldb) floats for the operand planes.
+extern "C" size_t humor_umma_gemm_workspace_bytes(int M, int N, int lda, int ldb) {
+  return (size_t)2 * ((size_t)M * lda + (size_t)N * ldb) * sizeof(float);
+}
+extern "C" int humor_umma_gemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M,
+                               int N, int K, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!A || !B || !C || !workspace || M <= 0 || N <= 0 || K <= 0) return HB_ERR_ARG;
+  if (workspace_bytes < humor_umma_gemm_workspace_bytes(M, N, lda, ldb)) return HB_ERR_WORKSPACE;
+  float* a_hi = workspace;
+  float* a_lo = a_hi + (size_t)M * lda;
+  float* b_hi = a_lo + (size_t)M * lda;
+  float* b_lo = b_hi + (size_t)N * ldb;
+  HB_CUDA(launch_split_hilo(A, a_hi, a_lo, (size_t)M * lda, st));
+  HB_CUDA(launch_split_hilo(B, b_hi, b_lo, (size_t)N * ldb, st));
+  GemmEpi ep;
+  ep.bias = bias; ep.gamma = ep.beta = nullptr; ep.xhat = ep.rstd = nullptr; ep.ldxh = 0; ep.Cch = 0; ep.gsize = 64;
+  HB_CUDA(launch_umma_gemm3(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, C, nullptr, nullptr, ldc, EPI_BIAS, ep, st));
+  return HB_OK;
+}

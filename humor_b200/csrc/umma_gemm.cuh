@@ -1,0 +1,268 @@
+// tcgen05 (5th-gen tensor core) GEMM with fp32-level accuracy:  C[M,N] = A[M,K] * B[N,K]^T
+//
+// The 1e-5 parity bound on HuMoR's decoder states / prior log-prob rules out a single TF32 pass, so each
+// operand is split once into  x = hi + lo  (hi = top 11 mantissa bits, lo = the exact remainder) and three
+// MMAs accumulate  hi*hi + lo*hi + hi*lo  into one TMEM accumulator ("3xTF32", ~2^-21 relative).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes {32 floats = 128 B, rows}, SWIZZLE_128B,
+//               4 tiles per stage (A_hi, A_lo, B_hi, B_lo) into a 3-stage mbarrier ring
+//   warp 1      allocates TMEM, issues tcgen05.mma.cta_group::1.kind::tf32 (one elected lane),
+//               tcgen05.commit releases smem stages / signals the epilogue
+//   warps 2..5  epilogue: tcgen05.ld (each warp owns its 32-lane TMEM quadrant = 32 output rows),
+//               one thread per output row, so a whole GroupNorm group (64 or 32 columns) is private to a
+//               thread: bias + two-pass GroupNorm + ReLU (or its reverse) without any shuffle,
+//               then writes the result as hi/lo planes for the next layer's TMA loads.
+#pragma once
+#include <cuda.h>
+#include "gemm.cuh"
+
+namespace hb {
+
+constexpr int UM_BM = 128;
+constexpr int UM_BK = 32;          // tf32 elements per stage row = 128 bytes = one swizzle span
+constexpr int UM_STAGES = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (1024 B between 8-row groups)
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// GroupNorm(+ReLU) forward / reverse on GS columns held privately by one thread (fully unrolled: v stays in registers)
+template <int GS>
+__device__ __forceinline__ void gn_relu_fwd_group(float* v, int col, int row, const GemmEpi& ep) {
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < GS; ++j) { v[j] += ep.bias[col + j]; sum += v[j]; }
+  const float mean = sum / (float)GS;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < GS; ++j) { const float d = v[j] - mean; sq += d * d; }
+  const float rs = rsqrtf(sq / (float)GS + 1e-5f);
+  ep.rstd[(size_t)row * 16 + col / GS] = rs;
+#pragma unroll
+  for (int j = 0; j < GS; j += 4) {
+    float4 xh;
+    float* xp = &xh.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      xp[e] = (v[j + e] - mean) * rs;
+      v[j + e] = fmaxf(fmaf(ep.gamma[col + j + e], xp[e], ep.beta[col + j + e]), 0.f);
+    }
+    *reinterpret_cast<float4*>(ep.xhat + (size_t)row * ep.ldxh + col + j) = xh;
+  }
+}
+template <int GS>
+__device__ __forceinline__ void gn_relu_bwd_group(float* v, int col, int row, const GemmEpi& ep) {
+  float xh[GS];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < GS; j += 4) {
+    const float4 x4 = *reinterpret_cast<const float4*>(ep.xhat + (size_t)row * ep.ldxh + col + j);
+    xh[j] = x4.x; xh[j + 1] = x4.y; xh[j + 2] = x4.z; xh[j + 3] = x4.w;
+  }
+#pragma unroll
+  for (int j = 0; j < GS; ++j) {
+    const float g = ep.gamma[col + j];
+    const bool on = fmaf(g, xh[j], ep.beta[col + j]) > 0.f;
+    const float u = on ? g * v[j] : 0.f;
+    v[j] = u;
+    s1 += u;
+    s2 += u * xh[j];
+  }
+  const float rs = ep.rstd[(size_t)row * 16 + col / GS];
+  const float inv = 1.f / (float)GS;
+#pragma unroll
+  for (int j = 0; j < GS; ++j) v[j] = rs * (v[j] - s1 * inv - xh[j] * s2 * inv);
+}
+
+template <int BN>
+struct UmmaSmem {
+  static constexpr int A_TILE = UM_BM * 128;                  // bytes
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int TOTAL = UM_STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  int M, int N, int K, float* __restrict__ C, float* __restrict__ C_hi, float* __restrict__ C_lo, int ldc,
+                  GemmEpi ep) {
+  using SM = UmmaSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bars = base + UM_STAGES * SM::STAGE;          // full[3] | empty[3] | tmem_full | tmem_ptr
+  const uint32_t full0 = bars, empty0 = bars + 8 * UM_STAGES, tfull = bars + 16 * UM_STAGES, tptr = tfull + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
+  const int nkb = K / UM_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % UM_STAGES;
+        const uint32_t ph = (kb / UM_STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t st = base + s * SM::STAGE;
+        mbar_expect_tx(full0 + 8 * s, SM::STAGE);
+        tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * UM_BK, m0);
+        tma_load_2d(st + SM::A_TILE, &tmA_lo, full0 + 8 * s, kb * UM_BK, m0);
+        tma_load_2d(st + 2 * SM::A_TILE, &tmB_hi, full0 + 8 * s, kb * UM_BK, n0);
+        tma_load_2d(st + 2 * SM::A_TILE + SM::B_TILE, &tmB_lo, full0 + 8 * s, kb * UM_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2 at bits 7 and 10), K-major both, N>>3 at 17, M>>4 at 24
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % UM_STAGES;
+        const uint32_t ph = (kb / UM_STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = base + s * SM::STAGE;
+#pragma unroll
+        for (int k = 0; k < UM_BK / 8; ++k) {                  // one UMMA consumes K = 8 tf32 = 32 bytes
+          const uint64_t a_hi = umma_desc_sw128(st + k * 32);
+          const uint64_t a_lo = umma_desc_sw128(st + SM::A_TILE + k * 32);
+          const uint64_t b_hi = umma_desc_sw128(st + 2 * SM::A_TILE + k * 32);
+          const uint64_t b_lo = umma_desc_sw128(st + 2 * SM::A_TILE + SM::B_TILE + k * 32);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, a_lo, b_hi, idesc, 1);
+          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+        }
+        umma_commit(empty0 + 8 * s);                           // frees the stage once these MMAs retire
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: one thread per output row
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool rok = row < M;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    auto store_planes = [&](int col, const float* o, int n) {   // n valid columns (multiple of 4 or tail)
+      for (int j = 0; j < n; j += 4) {
+        if (col + j + 3 < N) {
+          const float4 v = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          if (C) *reinterpret_cast<float4*>(C + (size_t)row * ldc + col + j) = v;
+          if (C_hi) {
+            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            *reinterpret_cast<float4*>(C_hi + (size_t)row * ldc + col + j) = h;
+            *reinterpret_cast<float4*>(C_lo + (size_t)row * ldc + col + j) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          }
+        } else {
+          for (int jj = j; jj < j + 4 && col + jj < N; ++jj) {
+            if (C) C[(size_t)row * ldc + col + jj] = o[jj];
+            if (C_hi) { const float h = tf32_hi(o[jj]); C_hi[(size_t)row * ldc + col + jj] = h; C_lo[(size_t)row * ldc + col + jj] = o[jj] - h; }
+          }
+        }
+      }
+    };
+    if (EPI == EPI_BIAS) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(trow + c0, v);
+        if (rok && n0 + c0 < N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += (ep.bias && n0 + c0 + j < N) ? ep.bias[n0 + c0 + j] : 0.f;
+          store_planes(n0 + c0, v, 32);
+        }
+      }
+    } else {
+      const int gs = ep.gsize;                                  // 64 or 32 (BN is a multiple of 64)
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        float v[64];
+        tmem_ld32(trow + c0, v);
+        tmem_ld32(trow + c0 + 32, v + 32);
+        const int col = n0 + c0;
+        if (!rok || col >= N) continue;
+        if (EPI == EPI_GN_RELU) {
+          if (gs == 64) gn_relu_fwd_group<64>(v, col, row, ep);
+          else { gn_relu_fwd_group<32>(v, col, row, ep); gn_relu_fwd_group<32>(v + 32, col + 32, row, ep); }
+          store_planes(col, v, 64);
+        } else {  // EPI_GN_RELU_BWD
+          if (col < ep.Cch) {
+            if (gs == 64) gn_relu_bwd_group<64>(v, col, row, ep);
+            else { gn_relu_bwd_group<32>(v, col, row, ep); gn_relu_bwd_group<32>(v + 32, col + 32, row, ep); }
+          }
+          store_planes(col, v, 64);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+}  // namespace hb

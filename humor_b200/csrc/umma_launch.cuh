@@ -1,0 +1,12 @@
+#pragma once
+#include "gemm.cuh"
+namespace hb {
+// C[M,N] = (A_hi+A_lo)[M,K] * (B_hi+B_lo)[N,K]^T on tcgen05 (3xTF32).  Operand planes are fp32 arrays with the
+// given leading dimensions (multiples of 4); K a multiple of 32.  Outputs: C (exact value) and/or the hi/lo planes.
+cudaError_t launch_umma_gemm3(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
+                              int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, int epi, const GemmEpi& ep,
+                              cudaStream_t st);
+// hi = top 11 mantissa bits of x, lo = x - hi (exact); n elements
+cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
+bool umma_available();
+}  // namespace hb

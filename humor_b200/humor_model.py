@@ -88,14 +88,25 @@ class PackedWeights:
             s.dec_g[i] = dev(gn.weight)
             s.dec_be[i] = dev(gn.bias)
         pl, pn = prior_net.linears(), prior_net.norms()
+        def split(t):
+            hi = (t.contiguous().view(torch.int32) & -8192).view(torch.float32)      # keep the top 11 mantissa bits
+            return hi, t - hi
+
         for i, lin in enumerate(pl):
             w = _pad_cols(lin.weight.detach().float(), self.PRI_K[i])
             s.pri_w[i] = dev(w)
             s.pri_b[i] = dev(lin.bias)
-            s.pri_wt[i] = dev(w.t().contiguous())
+            wt = w.t().contiguous()
+            s.pri_wt[i] = dev(wt)
+            (h, l), (ht, lt) = split(w), split(wt)
+            s.pri_w_hi[i], s.pri_w_lo[i] = dev(h), dev(l)
+            s.pri_wt_hi[i], s.pri_wt_lo[i] = dev(ht), dev(lt)
         for i, gn in enumerate(pn):
             s.pri_g[i] = dev(gn.weight)
             s.pri_be[i] = dev(gn.bias)
+        import os
+        s.use_umma = 0 if os.environ.get('HB_NO_UMMA') else 1
+        s.reserved = 0
         self.struct = s
         self.device = device
         self._ws = {}

@@ -82,6 +82,14 @@ typedef struct HbHumorWeights {
   const float* pri_g[4];
   const float* pri_be[4];
   const float* pri_wt[5]; /* [352][1024] [1024][1024]x3 [1024][96] */
+  /* tensor-core path of the batched prior: hi/lo operand planes (x = hi + lo, hi = top 11 mantissa bits) of
+   * pri_w / pri_wt for the 3xTF32 tcgen05 GEMM; use_umma = 0 keeps the exact-fp32 FFMA kernels */
+  const float* pri_w_hi[5];
+  const float* pri_w_lo[5];
+  const float* pri_wt_hi[5];
+  const float* pri_wt_lo[5];
+  int use_umma;
+  int reserved;
 } HbHumorWeights;
 
 /* Replaces HumorModel.roll_out(x_past=None, init_input_dict, S, z_seq, return_prior=True)
@@ -170,6 +178,12 @@ int humor_fit_losses(const HbFitArgs* a, int64_t* launches, hb_stream_t stream);
  *   -> nll [B] and d_x [B][D] = d(sum nll)/dx.  D <= 160, K <= 32. */
 int humor_gmm_nll(int B, int D, int K, const float* x, const float* logw, const float* mean,
                   const float* Linv, const float* logdet, float* nll, float* d_x, hb_stream_t stream);
+
+/* C = A[M,K] * B[N,K]^T (+bias) at fp32-level accuracy on the 5th-gen tensor cores (tcgen05, 3xTF32 operand split,
+ * TMA-staged tiles).  K % 32 == 0, leading dimensions % 4 == 0.  The building block of the batched prior MLP. */
+size_t humor_umma_gemm_workspace_bytes(int M, int N, int lda, int ldb);
+int humor_umma_gemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,
+                    int K, float* workspace, size_t workspace_bytes, hb_stream_t stream);
 
 const char* humor_b200_version(void);
 

@@ -131,29 +131,42 @@ struct UmmaSmem {
   static constexpr int TOTAL = UM_STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+constexpr int UM_CHUNK = 4;        // k-blocks (4 x 32 = K 128) accumulated in TMEM before promotion to fp32 registers
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// The tensor-core accumulator truncates on every add (measured on B200: -2e-5 relative bias over K = 1024 with
+// positive operands, error growing ~K), which alone would break the 1e-5 parity bound.  Each K-chunk of 128 is
+// therefore accumulated from zero in one of two TMEM buffers and then PROMOTED: the epilogue warps add it to fp32
+// register accumulators (round-to-nearest) while the MMA warp already fills the other buffer.
 template <int BN, int EPI>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   int M, int N, int K, float* __restrict__ C, float* __restrict__ C_hi, float* __restrict__ C_lo, int ldc,
                   GemmEpi ep) {
+  static_assert(BN == 128, "epilogue is written for 128-column tiles");
   using SM = UmmaSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                // SWIZZLE_128B tiles need 1024-byte alignment
-  const uint32_t bars = base + UM_STAGES * SM::STAGE;          // full[3] | empty[3] | tmem_full | tmem_ptr
-  const uint32_t full0 = bars, empty0 = bars + 8 * UM_STAGES, tfull = bars + 16 * UM_STAGES, tptr = tfull + 8;
+  const uint32_t bars = base + UM_STAGES * SM::STAGE;          // full[3] | empty[3] | tfull[2] | tempty[2] | tmem_ptr
+  const uint32_t full0 = bars, empty0 = bars + 8 * UM_STAGES, tfull0 = bars + 16 * UM_STAGES, tempty0 = tfull0 + 16,
+                 tptr = tempty0 + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
   const int nkb = K / UM_BK;
+  const int nchunk = (nkb + UM_CHUNK - 1) / UM_CHUNK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(tfull, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"((uint32_t)(2 * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -180,88 +193,100 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (lane == 0) {
       // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2 at bits 7 and 10), K-major both, N>>3 at 17, M>>4 at 24
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % UM_STAGES;
-        const uint32_t ph = (kb / UM_STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+      for (int c = 0; c < nchunk; ++c) {
+        const int buf = c & 1;
+        mbar_wait(tempty0 + 8 * buf, ((c >> 1) & 1) ^ 1);      // epilogue has drained this TMEM buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = base + s * SM::STAGE;
+        const uint32_t tacc = tmem_base + buf * BN;
+        const int kb_end = min(nkb, (c + 1) * UM_CHUNK);
+        for (int kb = c * UM_CHUNK; kb < kb_end; ++kb) {
+          const int s = kb % UM_STAGES;
+          const uint32_t ph = (kb / UM_STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = base + s * SM::STAGE;
 #pragma unroll
-        for (int k = 0; k < UM_BK / 8; ++k) {                  // one UMMA consumes K = 8 tf32 = 32 bytes
-          const uint64_t a_hi = umma_desc_sw128(st + k * 32);
-          const uint64_t a_lo = umma_desc_sw128(st + SM::A_TILE + k * 32);
-          const uint64_t b_hi = umma_desc_sw128(st + 2 * SM::A_TILE + k * 32);
-          const uint64_t b_lo = umma_desc_sw128(st + 2 * SM::A_TILE + SM::B_TILE + k * 32);
-          umma_tf32(tmem_base, a_hi, b_hi, idesc, (kb | k) != 0);
-          umma_tf32(tmem_base, a_lo, b_hi, idesc, 1);
-          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+          for (int k = 0; k < UM_BK / 8; ++k) {                // one UMMA consumes K = 8 tf32 = 32 bytes
+            const uint64_t a_hi = umma_desc_sw128(st + k * 32);
+            const uint64_t a_lo = umma_desc_sw128(st + SM::A_TILE + k * 32);
+            const uint64_t b_hi = umma_desc_sw128(st + 2 * SM::A_TILE + k * 32);
+            const uint64_t b_lo = umma_desc_sw128(st + 2 * SM::A_TILE + SM::B_TILE + k * 32);
+            umma_tf32(tacc, a_hi, b_hi, idesc, (kb != c * UM_CHUNK) || (k != 0));
+            umma_tf32(tacc, a_lo, b_hi, idesc, 1);
+            umma_tf32(tacc, a_hi, b_lo, idesc, 1);
+          }
+          umma_commit(empty0 + 8 * s);                         // frees the stage once these MMAs retire
         }
-        umma_commit(empty0 + 8 * s);                           // frees the stage once these MMAs retire
+        umma_commit(tfull0 + 8 * buf);                         // chunk complete -> promote
       }
-      umma_commit(tfull);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: one thread per output row
-    mbar_wait(tfull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ------------------------------------------------------------------ epilogue warps: one thread per output row
     const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
     const int row = m0 + q * 32 + lane;
     const bool rok = row < M;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    auto store_planes = [&](int col, const float* o, int n) {   // n valid columns (multiple of 4 or tail)
-      for (int j = 0; j < n; j += 4) {
-        if (col + j + 3 < N) {
-          const float4 v = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-          if (C) *reinterpret_cast<float4*>(C + (size_t)row * ldc + col + j) = v;
-          if (C_hi) {
-            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-            *reinterpret_cast<float4*>(C_hi + (size_t)row * ldc + col + j) = h;
-            *reinterpret_cast<float4*>(C_lo + (size_t)row * ldc + col + j) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-          }
-        } else {
-          for (int jj = j; jj < j + 4 && col + jj < N; ++jj) {
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      const int buf = c & 1;
+      mbar_wait(tfull0 + 8 * buf, (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float t[32];
+        tmem_ld32(trow + buf * BN + c0, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += t[j];
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+    }
+    auto store4 = [&](int col, float a, float b, float c_, float d) {
+      if (col + 3 < N) {
+        if (C) *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = make_float4(a, b, c_, d);
+        if (C_hi) {
+          const float4 h = make_float4(tf32_hi(a), tf32_hi(b), tf32_hi(c_), tf32_hi(d));
+          *reinterpret_cast<float4*>(C_hi + (size_t)row * ldc + col) = h;
+          *reinterpret_cast<float4*>(C_lo + (size_t)row * ldc + col) = make_float4(a - h.x, b - h.y, c_ - h.z, d - h.w);
+        }
+      } else {
+        const float o[4] = {a, b, c_, d};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          if (col + jj < N) {
             if (C) C[(size_t)row * ldc + col + jj] = o[jj];
             if (C_hi) { const float h = tf32_hi(o[jj]); C_hi[(size_t)row * ldc + col + jj] = h; C_lo[(size_t)row * ldc + col + jj] = o[jj] - h; }
           }
-        }
       }
     };
-    if (EPI == EPI_BIAS) {
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld32(trow + c0, v);
-        if (rok && n0 + c0 < N) {
+    if (rok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += (ep.bias && n0 + c0 + j < N) ? ep.bias[n0 + c0 + j] : 0.f;
-          store_planes(n0 + c0, v, 32);
-        }
-      }
-    } else {
-      const int gs = ep.gsize;                                  // 64 or 32 (BN is a multiple of 64)
       for (int c0 = 0; c0 < BN; c0 += 64) {
-        float v[64];
-        tmem_ld32(trow + c0, v);
-        tmem_ld32(trow + c0 + 32, v + 32);
         const int col = n0 + c0;
-        if (!rok || col >= N) continue;
-        if (EPI == EPI_GN_RELU) {
-          if (gs == 64) gn_relu_fwd_group<64>(v, col, row, ep);
-          else { gn_relu_fwd_group<32>(v, col, row, ep); gn_relu_fwd_group<32>(v + 32, col + 32, row, ep); }
-          store_planes(col, v, 64);
-        } else {  // EPI_GN_RELU_BWD
-          if (col < ep.Cch) {
-            if (gs == 64) gn_relu_bwd_group<64>(v, col, row, ep);
-            else { gn_relu_bwd_group<32>(v, col, row, ep); gn_relu_bwd_group<32>(v + 32, col + 32, row, ep); }
+        if (col < N) {
+          if (EPI == EPI_BIAS) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc[c0 + j] += (ep.bias && col + j < N) ? ep.bias[col + j] : 0.f;
+          } else if (EPI == EPI_GN_RELU) {
+            if (ep.gsize == 64) gn_relu_fwd_group<64>(acc + c0, col, row, ep);
+            else { gn_relu_fwd_group<32>(acc + c0, col, row, ep); gn_relu_fwd_group<32>(acc + c0 + 32, col + 32, row, ep); }
+          } else if (col < ep.Cch) {
+            if (ep.gsize == 64) gn_relu_bwd_group<64>(acc + c0, col, row, ep);
+            else { gn_relu_bwd_group<32>(acc + c0, col, row, ep); gn_relu_bwd_group<32>(acc + c0 + 32, col + 32, row, ep); }
           }
-          store_planes(col, v, 64);
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) store4(col + j, acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]);
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
   }
 }
 

@@ -270,11 +270,16 @@ class MotionOptimizer():
         evaluation (several hundred launches) is captured once per (phase, weights, trainable-set) and replayed."""
         params = self.stage3_params() if params is None else params
         if not self.use_cuda_graph:
+            # torch.autograd.grad (not loss.backward()): no AccumulateGrad nodes get bound to the eager stream, which
+            # would later invalidate a capture of the same closure on the capture stream
+            loss, _, _, _, _ = self.stage3_forward(observed_data, nsteps, init_motion_scale)
+            live = [p for p in params if p.requires_grad]
+            grads = torch.autograd.grad(loss, live, allow_unused=True)
             for p in params:
                 p.grad = None
-            loss, _, _, _, _ = self.stage3_forward(observed_data, nsteps, init_motion_scale)
-            loss.backward()
-            return loss
+            for p, gr in zip(live, grads):
+                p.grad = torch.zeros_like(p) if gr is None else gr
+            return loss.detach()
         from . import _ext
         w = self.fitting_loss.loss_weights
         key = (nsteps, float(init_motion_scale), tuple(bool(p.requires_grad) for p in params),

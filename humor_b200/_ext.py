@@ -73,7 +73,9 @@ class HbHumorWeights(C.Structure):
                 ('dec_be', C.c_void_p * 3), ('dec_wt', C.c_void_p * 4), ('pri_w', C.c_void_p * 5),
                 ('pri_b', C.c_void_p * 5), ('pri_g', C.c_void_p * 4), ('pri_be', C.c_void_p * 4),
                 ('pri_wt', C.c_void_p * 5), ('pri_w_hi', C.c_void_p * 5), ('pri_w_lo', C.c_void_p * 5),
-                ('pri_wt_hi', C.c_void_p * 5), ('pri_wt_lo', C.c_void_p * 5), ('use_umma', C.c_int), ('reserved', C.c_int)]
+                ('pri_wt_hi', C.c_void_p * 5), ('pri_wt_lo', C.c_void_p * 5), ('dec_w_hi', C.c_void_p * 4),
+                ('dec_w_lo', C.c_void_p * 4), ('dec_wt_hi', C.c_void_p * 4), ('dec_wt_lo', C.c_void_p * 4),
+                ('use_umma', C.c_int), ('reserved', C.c_int)]
 
 
 class HbFitArgs(C.Structure):

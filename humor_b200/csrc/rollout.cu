@@ -23,7 +23,8 @@ struct Tape {
   float *h1, *h2, *h3;                 // decoder transients [B][1088],[B][1088],[B][576]
   float *pa, *pb;                      // prior ping-pong [S*B][1024]
   float *dh3, *dh2, *dh1, *da0, *draw, *dxres, *dnsum, *dG0, *dG1, *dt2j, *dpx;
-  float *xin_hi, *xin_lo, *pa_lo, *pb_lo, *dpo_hi, *dpo_lo;   // operand planes of the tensor-core prior (pa/pb hold hi)
+  // hi/lo operand planes of the tensor-core path (x = hi + lo); h1/h2/h3, pa/pb, dh1/dh2/dh3 hold the hi plane
+  float *xin_hi, *xin_lo, *pa_lo, *pb_lo, *dpo_hi, *dpo_lo, *h1_lo, *h2_lo, *h3_lo, *dh1_lo, *dh2_lo, *dh3_lo, *draw_hi, *draw_lo;
   size_t total;
 };
 
@@ -47,16 +48,27 @@ static Tape carve(float* base, int B, int S) {
   t.dxres = take((size_t)B * 340); t.dnsum = take((size_t)B * 340);
   t.dG0 = take((size_t)B * 12); t.dG1 = take((size_t)B * 12); t.dt2j = take((size_t)B * 4);
   t.dpx = take(M * 352);
-  t.xin_hi = take(M * XIN_LD); t.xin_lo = take(M * XIN_LD);
+  t.xin_hi = take((size_t)(S + 1) * B * XIN_LD); t.xin_lo = take((size_t)(S + 1) * B * XIN_LD);
   t.pa_lo = take(M * 1024); t.pb_lo = take(M * 1024);
   t.dpo_hi = take(M * 96); t.dpo_lo = take(M * 96);
+  t.h1_lo = take((size_t)B * 1088); t.h2_lo = take((size_t)B * 1088); t.h3_lo = take((size_t)B * 576);
+  t.dh1_lo = take((size_t)B * 1088); t.dh2_lo = take((size_t)B * 1088); t.dh3_lo = take((size_t)B * 576);
+  t.draw_hi = take((size_t)B * RAW_LD); t.draw_lo = take((size_t)B * RAW_LD);
   t.total = off;
   return t;
 }
 
+__device__ __forceinline__ float hi11(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// write v as (hi, lo) planes when a lo plane exists, else exactly
+__device__ __forceinline__ void put_split(float* hi, float* lo, size_t i, float v) {
+  if (lo) { const float h = hi11(v); hi[i] = h; lo[i] = v - h; } else { hi[i] = v; }
+}
+__device__ __forceinline__ float get_split(const float* hi, const float* lo, size_t i) { return lo ? hi[i] + lo[i] : hi[i]; }
+
 // ------------------------------------------------------------------------------------------------
 __global__ void rollout_init_kernel(int B, int S, const float* __restrict__ init, const float* __restrict__ z,
-                                    float* xin0, float* G0, float* t2j, float* h1, float* h2, float* h3) {
+                                    float* xin0, float* xin0_hi, float* xin0_lo, float* G0, float* t2j, float* h1, float* h2,
+                                    float* h3, float* h1_lo, float* h2_lo, float* h3_lo) {
   int b = blockIdx.x;
   float* x = xin0 + (size_t)b * XIN_LD;
   for (int i = threadIdx.x; i < XIN_LD; i += blockDim.x) {
@@ -64,12 +76,13 @@ __global__ void rollout_init_kernel(int B, int S, const float* __restrict__ init
     if (i < STATE_D) v = init[(size_t)b * STATE_D + i];
     else if (i < STATE_D + 48) v = z[((size_t)b * S) * 48 + (i - STATE_D)];
     x[i] = v;
+    if (xin0_lo) put_split(xin0_hi, xin0_lo, (size_t)b * XIN_LD + i, v);
   }
   for (int i = threadIdx.x; i < 64; i += blockDim.x) {
     float v = i < 48 ? z[((size_t)b * S) * 48 + i] : 0.f;
-    h1[(size_t)b * 1088 + 1024 + i] = v;
-    h2[(size_t)b * 1088 + 1024 + i] = v;
-    h3[(size_t)b * 576 + 512 + i] = v;
+    put_split(h1, h1_lo, (size_t)b * 1088 + 1024 + i, v);
+    put_split(h2, h2_lo, (size_t)b * 1088 + 1024 + i, v);
+    put_split(h3, h3_lo, (size_t)b * 576 + 512 + i, v);
   }
   if (threadIdx.x < 12) G0[(size_t)b * 12 + threadIdx.x] = (threadIdx.x == 0 || threadIdx.x == 4 || threadIdx.x == 8) ? 1.f : 0.f;
   if (threadIdx.x < 3) t2j[b * 4 + threadIdx.x] = threadIdx.x < 2 ? -init[(size_t)b * STATE_D + 207 + threadIdx.x] : 0.f;
@@ -83,6 +96,7 @@ __global__ void rollout_init_kernel(int B, int S, const float* __restrict__ init
 // ------------------------------------------------------------------------------------------------
 constexpr int GLUE_WARPS = 4;
 
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -92,7 +106,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(GLUE_WARPS * 32)
 glue_fwd_kernel(int B, int S, int t, const float* __restrict__ xin, const float* __restrict__ raw,
                 const float* __restrict__ G, const float* __restrict__ t2jg, const float* __restrict__ z,
-                float* xnext, float* world, float* Gnext, float* h1, float* h2, float* h3) {
+                float* xnext, float* xnext_hi, float* xnext_lo, float* world, float* Gnext, float* h1, float* h2, float* h3,
+                float* h1_lo, float* h2_lo, float* h3_lo) {
   __shared__ float s_x[GLUE_WARPS][340], s_r[GLUE_WARPS][216], s_n[GLUE_WARPS][340], s_w[GLUE_WARPS][348];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * GLUE_WARPS + wid;
@@ -165,16 +180,20 @@ glue_fwd_kernel(int B, int S, int t, const float* __restrict__ xin, const float*
   __syncwarp();
   float* xn = xnext + (size_t)b * XIN_LD;
   float* wo = world + (size_t)b * WORLD_LD;
-  for (int i = lane; i < STATE_D; i += 32) xn[i] = sn[i];
+  for (int i = lane; i < STATE_D; i += 32) {
+    xn[i] = sn[i];
+    if (xnext_lo) put_split(xnext_hi, xnext_lo, (size_t)b * XIN_LD + i, sn[i]);
+  }
   for (int i = lane; i < WORLD_LD; i += 32) wo[i] = sw[i];
   if (t + 1 < S) {
     const float* zt = z + ((size_t)b * S + (t + 1)) * 48;
     for (int i = lane; i < 48; i += 32) {
       const float v = zt[i];
       xn[STATE_D + i] = v;
-      h1[(size_t)b * 1088 + 1024 + i] = v;
-      h2[(size_t)b * 1088 + 1024 + i] = v;
-      h3[(size_t)b * 576 + 512 + i] = v;
+      if (xnext_lo) put_split(xnext_hi, xnext_lo, (size_t)b * XIN_LD + STATE_D + i, v);
+      put_split(h1, h1_lo, (size_t)b * 1088 + 1024 + i, v);
+      put_split(h2, h2_lo, (size_t)b * 1088 + 1024 + i, v);
+      put_split(h3, h3_lo, (size_t)b * 576 + 512 + i, v);
     }
   }
 }
@@ -184,8 +203,9 @@ __global__ void __launch_bounds__(GLUE_WARPS * 32)
 glue_bwd_kernel(int B, int S, int t, int have_next, const float* __restrict__ xin, const float* __restrict__ raw,
                 const float* __restrict__ G, const float* __restrict__ t2jg, const float* __restrict__ dworld,
                 const float* __restrict__ da0, const float* __restrict__ dpx_next, const float* __restrict__ dh1,
-                const float* __restrict__ dh2, const float* __restrict__ dh3, float* dxres, float* dnsum,
-                const float* __restrict__ dGn_g, float* dG, float* dt2j, float* draw, float* dz) {
+                const float* __restrict__ dh2, const float* __restrict__ dh3, const float* __restrict__ dh1_lo,
+                const float* __restrict__ dh2_lo, const float* __restrict__ dh3_lo, float* dxres, float* dnsum,
+                const float* __restrict__ dGn_g, float* dG, float* dt2j, float* draw, float* draw_hi, float* draw_lo, float* dz) {
   __shared__ float s_x[GLUE_WARPS][340], s_r[GLUE_WARPS][216], s_dn[GLUE_WARPS][340], s_dw[GLUE_WARPS][348],
       s_dx[GLUE_WARPS][340], s_dr[GLUE_WARPS][224];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -207,8 +227,8 @@ glue_bwd_kernel(int B, int S, int t, int have_next, const float* __restrict__ xi
       for (int i = lane; i < STATE_D; i += 32) dn[i] = xs[i] + a0[i] + px[i];
       float* dzt = dz + ((size_t)b * S + (t + 1)) * 48;
       for (int i = lane; i < 48; i += 32)
-        dzt[i] = a0[STATE_D + i] + dh1[(size_t)b * 1088 + 1024 + i] + dh2[(size_t)b * 1088 + 1024 + i] +
-                 dh3[(size_t)b * 576 + 512 + i];
+        dzt[i] = a0[STATE_D + i] + get_split(dh1, dh1_lo, (size_t)b * 1088 + 1024 + i) +
+                 get_split(dh2, dh2_lo, (size_t)b * 1088 + 1024 + i) + get_split(dh3, dh3_lo, (size_t)b * 576 + 512 + i);
     } else {
       for (int i = lane; i < STATE_D; i += 32) dn[i] = 0.f;
     }
@@ -347,13 +367,17 @@ glue_bwd_kernel(int B, int S, int t, int have_next, const float* __restrict__ xi
   float* xo = dxres + (size_t)b * 340;
   float* ro = draw + (size_t)b * RAW_LD;
   for (int i = lane; i < STATE_D; i += 32) xo[i] = dx[i];
-  for (int i = lane; i < RAW_LD; i += 32) ro[i] = dr[i];
+  for (int i = lane; i < RAW_LD; i += 32) {
+    ro[i] = dr[i];
+    if (draw_lo) put_split(draw_hi, draw_lo, (size_t)b * RAW_LD + i, dr[i]);
+  }
 }
 
 __global__ void rollout_bwd_final_kernel(int B, int S, const float* __restrict__ dxres, const float* __restrict__ da0,
                                          const float* __restrict__ dpx0, const float* __restrict__ dh1,
                                          const float* __restrict__ dh2, const float* __restrict__ dh3,
-                                         const float* __restrict__ dt2j, float* dinit, float* dz) {
+                                         const float* __restrict__ dh1_lo, const float* __restrict__ dh2_lo,
+                                         const float* __restrict__ dh3_lo, const float* __restrict__ dt2j, float* dinit, float* dz) {
   int b = blockIdx.x;
   for (int i = threadIdx.x; i < STATE_D; i += blockDim.x) {
     float v = dxres[(size_t)b * 340 + i] + da0[(size_t)b * XIN_LD + i] + dpx0[(size_t)b * 352 + i];
@@ -361,8 +385,8 @@ __global__ void rollout_bwd_final_kernel(int B, int S, const float* __restrict__
     dinit[(size_t)b * STATE_D + i] = v;
   }
   for (int i = threadIdx.x; i < 48; i += blockDim.x)
-    dz[((size_t)b * S) * 48 + i] = da0[(size_t)b * XIN_LD + STATE_D + i] + dh1[(size_t)b * 1088 + 1024 + i] +
-                                   dh2[(size_t)b * 1088 + 1024 + i] + dh3[(size_t)b * 576 + 512 + i];
+    dz[((size_t)b * S) * 48 + i] = da0[(size_t)b * XIN_LD + STATE_D + i] + get_split(dh1, dh1_lo, (size_t)b * 1088 + 1024 + i) +
+                                   get_split(dh2, dh2_lo, (size_t)b * 1088 + 1024 + i) + get_split(dh3, dh3_lo, (size_t)b * 576 + 512 + i);
 }
 
 static GemmEpi epi_gn(const float* bias, const float* g, const float* be, float* xh, int ldxh, float* rs, int C, int gs) {
@@ -393,29 +417,53 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
   HB_CUDA(cudaMemsetAsync(tp.xins, 0, (size_t)(S + 1) * B * XIN_LD * sizeof(float), st));
   HB_CUDA(cudaMemsetAsync(tp.raws, 0, (size_t)S * B * RAW_LD * sizeof(float), st));
   HB_CUDA(cudaMemsetAsync(tp.h1, 0, ((size_t)B * 1088 * 2 + (size_t)B * 576 + 256) * sizeof(float), st));
-  rollout_init_kernel<<<B, 128, 0, st>>>(B, S, init_state, z_seq, tp.xins, tp.Gs, tp.t2j, tp.h1, tp.h2, tp.h3);
+  const bool tc = w->use_umma && umma_available();      // tensor-core path (tcgen05 3xTF32) for every GEMM
+  if (tc) {
+    HB_CUDA(cudaMemsetAsync(tp.h1_lo, 0, ((size_t)B * 1088 * 2 + (size_t)B * 576) * sizeof(float), st));
+    HB_CUDA(cudaMemsetAsync(tp.xin_hi, 0, (size_t)(S + 1) * B * XIN_LD * 2 * sizeof(float), st));
+  }
+  rollout_init_kernel<<<B, 128, 0, st>>>(B, S, init_state, z_seq, tp.xins, tc ? tp.xin_hi : nullptr, tc ? tp.xin_lo : nullptr, tp.Gs,
+                                         tp.t2j, tp.h1, tp.h2, tp.h3, tc ? tp.h1_lo : nullptr, tc ? tp.h2_lo : nullptr,
+                                         tc ? tp.h3_lo : nullptr);
   HB_LAUNCH_CHECK(); ++nl;
   const int gb = cdiv(B, GLUE_WARPS);
   for (int t = 0; t < S; ++t) {
     const size_t r = (size_t)t * B;
     float* xin = tp.xins + r * XIN_LD;
-    HB_CUDA(launch_gemm<EPI_GN_RELU>(xin, XIN_LD, w->dec_w[0], 416, tp.h1, 1088, B, 1024, 416,
-                                     epi_gn(w->dec_b[0], w->dec_g[0], w->dec_be[0], tp.dxh1 + r * 1024, 1024, tp.drs1 + r * 16, 1024, 64), st));
-    HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.h1, 1088, w->dec_w[1], 1088, tp.h2, 1088, B, 1024, 1088,
-                                     epi_gn(w->dec_b[1], w->dec_g[1], w->dec_be[1], tp.dxh2 + r * 1024, 1024, tp.drs2 + r * 16, 1024, 64), st));
-    HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.h2, 1088, w->dec_w[2], 1088, tp.h3, 576, B, 512, 1088,
-                                     epi_gn(w->dec_b[2], w->dec_g[2], w->dec_be[2], tp.dxh3 + r * 512, 512, tp.drs3 + r * 16, 512, 32), st));
-    HB_CUDA(launch_gemm<EPI_BIAS>(tp.h3, 576, w->dec_w[3], 576, tp.raws + r * RAW_LD, RAW_LD, B, 216, 576, epi_bias(w->dec_b[3]), st));
+    if (tc) {
+      HB_CUDA(launch_umma_gemm3(tp.xin_hi + r * XIN_LD, tp.xin_lo + r * XIN_LD, XIN_LD, w->dec_w_hi[0], w->dec_w_lo[0], 416, B, 1024, 416,
+                                nullptr, tp.h1, tp.h1_lo, 1088, EPI_GN_RELU,
+                                epi_gn(w->dec_b[0], w->dec_g[0], w->dec_be[0], tp.dxh1 + r * 1024, 1024, tp.drs1 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_umma_gemm3(tp.h1, tp.h1_lo, 1088, w->dec_w_hi[1], w->dec_w_lo[1], 1088, B, 1024, 1088, nullptr, tp.h2, tp.h2_lo, 1088,
+                                EPI_GN_RELU,
+                                epi_gn(w->dec_b[1], w->dec_g[1], w->dec_be[1], tp.dxh2 + r * 1024, 1024, tp.drs2 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_umma_gemm3(tp.h2, tp.h2_lo, 1088, w->dec_w_hi[2], w->dec_w_lo[2], 1088, B, 512, 1088, nullptr, tp.h3, tp.h3_lo, 576,
+                                EPI_GN_RELU,
+                                epi_gn(w->dec_b[2], w->dec_g[2], w->dec_be[2], tp.dxh3 + r * 512, 512, tp.drs3 + r * 16, 512, 32), st));
+      HB_CUDA(launch_umma_gemm3(tp.h3, tp.h3_lo, 576, w->dec_w_hi[3], w->dec_w_lo[3], 576, B, 216, 576, tp.raws + r * RAW_LD, nullptr,
+                                nullptr, RAW_LD, EPI_BIAS, epi_bias(w->dec_b[3]), st));
+    } else {
+      HB_CUDA(launch_gemm<EPI_GN_RELU>(xin, XIN_LD, w->dec_w[0], 416, tp.h1, 1088, B, 1024, 416,
+                                       epi_gn(w->dec_b[0], w->dec_g[0], w->dec_be[0], tp.dxh1 + r * 1024, 1024, tp.drs1 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.h1, 1088, w->dec_w[1], 1088, tp.h2, 1088, B, 1024, 1088,
+                                       epi_gn(w->dec_b[1], w->dec_g[1], w->dec_be[1], tp.dxh2 + r * 1024, 1024, tp.drs2 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.h2, 1088, w->dec_w[2], 1088, tp.h3, 576, B, 512, 1088,
+                                       epi_gn(w->dec_b[2], w->dec_g[2], w->dec_be[2], tp.dxh3 + r * 512, 512, tp.drs3 + r * 16, 512, 32), st));
+      HB_CUDA(launch_gemm<EPI_BIAS>(tp.h3, 576, w->dec_w[3], 576, tp.raws + r * RAW_LD, RAW_LD, B, 216, 576, epi_bias(w->dec_b[3]), st));
+    }
     glue_fwd_kernel<<<gb, GLUE_WARPS * 32, 0, st>>>(B, S, t, xin, tp.raws + r * RAW_LD, tp.Gs + r * 12, tp.t2j, z_seq,
-                                       tp.xins + (r + B) * XIN_LD, world + r * WORLD_LD, tp.Gs + (r + B) * 12, tp.h1, tp.h2, tp.h3);
+                                                    tp.xins + (r + B) * XIN_LD, tc ? tp.xin_hi + (r + B) * XIN_LD : nullptr,
+                                                    tc ? tp.xin_lo + (r + B) * XIN_LD : nullptr, world + r * WORLD_LD,
+                                                    tp.Gs + (r + B) * 12, tp.h1, tp.h2, tp.h3, tc ? tp.h1_lo : nullptr,
+                                                    tc ? tp.h2_lo : nullptr, tc ? tp.h3_lo : nullptr);
     HB_LAUNCH_CHECK();
     nl += 5;
   }
   if (prior_out) {
     const int M = S * B;
-    if (w->use_umma && umma_available()) {
+    if (tc) {
       // batched prior on the 5th-gen tensor cores (3xTF32): activations travel as hi/lo planes
-      HB_CUDA(launch_split_hilo(tp.xins, tp.xin_hi, tp.xin_lo, (size_t)M * XIN_LD, st));
+      // (the input planes xin_hi/xin_lo were written step by step by the glue kernel)
       float* hi[2] = {tp.pa, tp.pb};
       float* lo[2] = {tp.pa_lo, tp.pb_lo};
       float* xh[4] = {tp.pxh1, tp.pxh2, tp.pxh3, tp.pxh4};
@@ -430,7 +478,7 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
       }
       HB_CUDA(launch_umma_gemm3(a_hi, a_lo, 1024, w->pri_w_hi[4], w->pri_w_lo[4], 1024, M, 96, 1024, prior_out, nullptr, nullptr, 96,
                                 EPI_BIAS, epi_bias(w->pri_b[4]), st));
-      nl += 6;
+      nl += 5;
     } else {
       HB_CUDA(launch_gemm<EPI_GN_RELU>(tp.xins, XIN_LD, w->pri_w[0], 352, tp.pa, 1024, M, 1024, 352,
                                        epi_gn(w->pri_b[0], w->pri_g[0], w->pri_be[0], tp.pxh1, 1024, tp.prs1, 1024, 64), st));
@@ -456,7 +504,8 @@ extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* w
   if (workspace_bytes < tp.total * sizeof(float)) return HB_ERR_WORKSPACE;
   int64_t nl = 0;
   const int M = S * B;
-  if (d_prior_out && w->use_umma && umma_available()) {
+  const bool tc = w->use_umma && umma_available();
+  if (d_prior_out && tc) {
     HB_CUDA(launch_split_hilo(d_prior_out, tp.dpo_hi, tp.dpo_lo, (size_t)M * 96, st));
     float* hi[2] = {tp.pa, tp.pb};
     float* lo[2] = {tp.pa_lo, tp.pb_lo};
@@ -496,19 +545,36 @@ extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* w
     float* dGn = dGbuf[(t + 1) & 1];
     float* dGc = dGbuf[t & 1];
     glue_bwd_kernel<<<gb, GLUE_WARPS * 32, 0, st>>>(B, S, t, have_next, tp.xins + r * XIN_LD, tp.raws + r * RAW_LD, tp.Gs + r * 12, tp.t2j,
-                                       d_world + r * WORLD_LD, tp.da0, tp.dpx + (r + B) * 352, tp.dh1, tp.dh2, tp.dh3,
-                                       tp.dxres, tp.dnsum, dGn, dGc, tp.dt2j, tp.draw, d_z);
+                                                    d_world + r * WORLD_LD, tp.da0, tp.dpx + (r + B) * 352, tp.dh1, tp.dh2, tp.dh3,
+                                                    tc ? tp.dh1_lo : nullptr, tc ? tp.dh2_lo : nullptr, tc ? tp.dh3_lo : nullptr,
+                                                    tp.dxres, tp.dnsum, dGn, dGc, tp.dt2j, tp.draw, tc ? tp.draw_hi : nullptr,
+                                                    tc ? tp.draw_lo : nullptr, d_z);
     HB_LAUNCH_CHECK();
-    HB_CUDA(launch_gemm<EPI_GN_RELU_BWD>(tp.draw, RAW_LD, w->dec_wt[3], 224, tp.dh3, 576, B, 560, 224,
-                                         epi_gn(nullptr, w->dec_g[2], w->dec_be[2], tp.dxh3 + r * 512, 512, tp.drs3 + r * 16, 512, 32), st));
-    HB_CUDA(launch_gemm<EPI_GN_RELU_BWD>(tp.dh3, 576, w->dec_wt[2], 512, tp.dh2, 1088, B, 1072, 512,
-                                         epi_gn(nullptr, w->dec_g[1], w->dec_be[1], tp.dxh2 + r * 1024, 1024, tp.drs2 + r * 16, 1024, 64), st));
-    HB_CUDA(launch_gemm<EPI_GN_RELU_BWD>(tp.dh2, 1088, w->dec_wt[1], 1024, tp.dh1, 1088, B, 1072, 1024,
-                                         epi_gn(nullptr, w->dec_g[0], w->dec_be[0], tp.dxh1 + r * 1024, 1024, tp.drs1 + r * 16, 1024, 64), st));
-    HB_CUDA(launch_gemm<EPI_BIAS>(tp.dh1, 1088, w->dec_wt[0], 1024, tp.da0, XIN_LD, B, 387, 1024, epi_bias(nullptr), st));
+    if (tc) {
+      HB_CUDA(launch_umma_gemm3(tp.draw_hi, tp.draw_lo, RAW_LD, w->dec_wt_hi[3], w->dec_wt_lo[3], 224, B, 560, 224, nullptr, tp.dh3,
+                                tp.dh3_lo, 576, EPI_GN_RELU_BWD,
+                                epi_gn(nullptr, w->dec_g[2], w->dec_be[2], tp.dxh3 + r * 512, 512, tp.drs3 + r * 16, 512, 32), st));
+      HB_CUDA(launch_umma_gemm3(tp.dh3, tp.dh3_lo, 576, w->dec_wt_hi[2], w->dec_wt_lo[2], 512, B, 1072, 512, nullptr, tp.dh2, tp.dh2_lo,
+                                1088, EPI_GN_RELU_BWD,
+                                epi_gn(nullptr, w->dec_g[1], w->dec_be[1], tp.dxh2 + r * 1024, 1024, tp.drs2 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_umma_gemm3(tp.dh2, tp.dh2_lo, 1088, w->dec_wt_hi[1], w->dec_wt_lo[1], 1024, B, 1072, 1024, nullptr, tp.dh1, tp.dh1_lo,
+                                1088, EPI_GN_RELU_BWD,
+                                epi_gn(nullptr, w->dec_g[0], w->dec_be[0], tp.dxh1 + r * 1024, 1024, tp.drs1 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_umma_gemm3(tp.dh1, tp.dh1_lo, 1088, w->dec_wt_hi[0], w->dec_wt_lo[0], 1024, B, 387, 1024, tp.da0, nullptr, nullptr,
+                                XIN_LD, EPI_BIAS, epi_bias(nullptr), st));
+    } else {
+      HB_CUDA(launch_gemm<EPI_GN_RELU_BWD>(tp.draw, RAW_LD, w->dec_wt[3], 224, tp.dh3, 576, B, 560, 224,
+                                           epi_gn(nullptr, w->dec_g[2], w->dec_be[2], tp.dxh3 + r * 512, 512, tp.drs3 + r * 16, 512, 32), st));
+      HB_CUDA(launch_gemm<EPI_GN_RELU_BWD>(tp.dh3, 576, w->dec_wt[2], 512, tp.dh2, 1088, B, 1072, 512,
+                                           epi_gn(nullptr, w->dec_g[1], w->dec_be[1], tp.dxh2 + r * 1024, 1024, tp.drs2 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_gemm<EPI_GN_RELU_BWD>(tp.dh2, 1088, w->dec_wt[1], 1024, tp.dh1, 1088, B, 1072, 1024,
+                                           epi_gn(nullptr, w->dec_g[0], w->dec_be[0], tp.dxh1 + r * 1024, 1024, tp.drs1 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_gemm<EPI_BIAS>(tp.dh1, 1088, w->dec_wt[0], 1024, tp.da0, XIN_LD, B, 387, 1024, epi_bias(nullptr), st));
+    }
     nl += 5;
   }
-  rollout_bwd_final_kernel<<<B, 128, 0, st>>>(B, S, tp.dxres, tp.da0, tp.dpx, tp.dh1, tp.dh2, tp.dh3, tp.dt2j, d_init, d_z);
+  rollout_bwd_final_kernel<<<B, 128, 0, st>>>(B, S, tp.dxres, tp.da0, tp.dpx, tp.dh1, tp.dh2, tp.dh3, tc ? tp.dh1_lo : nullptr,
+                                              tc ? tp.dh2_lo : nullptr, tc ? tp.dh3_lo : nullptr, tp.dt2j, d_init, d_z);
   HB_LAUNCH_CHECK(); ++nl;
   if (launches) *launches = nl;
   return HB_OK;

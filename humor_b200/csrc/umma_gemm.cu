@@ -36,10 +36,9 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int K, int ld,
   return r == CUDA_SUCCESS;
 }
 
-template <int EPI>
+template <int BN, int EPI>
 static cudaError_t launch_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                             int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, const GemmEpi& ep, cudaStream_t st) {
-  constexpr int BN = 128;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(umma_gemm3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::TOTAL);
@@ -57,15 +56,22 @@ cudaError_t launch_umma_gemm3(const float* A_hi, const float* A_lo, int lda, con
   if (!load_encode()) return cudaErrorNotSupported;
   if (K % UM_BK || lda % 4 || ldb % 4 || ldc % 4) return cudaErrorInvalidValue;
   if ((C_hi == nullptr) != (C_lo == nullptr)) return cudaErrorInvalidValue;
+  // few row tiles (the sequential decoder steps, M = sub-sequences per GPU): 64-column tiles double the CTA count
+  const int bn = (M <= 1024) ? 64 : 128;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   if (!make_map(&ta_hi, A_hi, M, K, lda, UM_BM) || !make_map(&ta_lo, A_lo, M, K, lda, UM_BM) ||
-      !make_map(&tb_hi, B_hi, N, K, ldb, 128) || !make_map(&tb_lo, B_lo, N, K, ldb, 128))
+      !make_map(&tb_hi, B_hi, N, K, ldb, bn) || !make_map(&tb_lo, B_lo, N, K, ldb, bn))
     return cudaErrorInvalidValue;
+#define HB_UMMA_CASE(E)                                                                                              \
+  case E:                                                                                                            \
+    return bn == 64 ? launch_t<64, E>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st)               \
+                    : launch_t<128, E>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
   switch (epi) {
-    case EPI_BIAS: return launch_t<EPI_BIAS>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
-    case EPI_GN_RELU: return launch_t<EPI_GN_RELU>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
-    case EPI_GN_RELU_BWD: return launch_t<EPI_GN_RELU_BWD>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
+    HB_UMMA_CASE(EPI_BIAS)
+    HB_UMMA_CASE(EPI_GN_RELU)
+    HB_UMMA_CASE(EPI_GN_RELU_BWD)
   }
+#undef HB_UMMA_CASE
   return cudaErrorInvalidValue;
 }
 

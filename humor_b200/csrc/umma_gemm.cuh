@@ -21,7 +21,6 @@ namespace hb {
 
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;          // tf32 elements per stage row = 128 bytes = one swizzle span
-constexpr int UM_STAGES = 3;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -128,7 +127,8 @@ struct UmmaSmem {
   static constexpr int A_TILE = UM_BM * 128;                  // bytes
   static constexpr int B_TILE = BN * 128;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-  static constexpr int TOTAL = UM_STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGES = (BN <= 64) ? 4 : 3;           // 4 x 48 KB or 3 x 64 KB
+  static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 constexpr int UM_CHUNK = 4;        // k-blocks (4 x 32 = K 128) accumulated in TMEM before promotion to fp32 registers
@@ -147,8 +147,9 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   int M, int N, int K, float* __restrict__ C, float* __restrict__ C_hi, float* __restrict__ C_lo, int ldc,
                   GemmEpi ep) {
-  static_assert(BN == 128, "epilogue is written for 128-column tiles");
+  static_assert(BN == 128 || BN == 64, "epilogue is written for 64- or 128-column tiles");
   using SM = UmmaSmem<BN>;
+  constexpr int UM_STAGES = SM::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                // SWIZZLE_128B tiles need 1024-byte alignment

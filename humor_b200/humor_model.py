@@ -74,6 +74,10 @@ class PackedWeights:
             self.keep.append(t)
             return t.data_ptr()
 
+        def split(t):
+            hi = (t.contiguous().view(torch.int32) & -8192).view(torch.float32)      # keep the top 11 mantissa bits
+            return hi, t - hi
+
         s = _ext.HbHumorWeights()
         dl, dn = decoder.linears(), decoder.norms()
         for i, lin in enumerate(dl):
@@ -84,14 +88,13 @@ class PackedWeights:
             if i == 3:
                 wt = _pad_cols(wt, 224)
             s.dec_wt[i] = dev(wt)
+            (h, l), (ht, lt) = split(w), split(wt)
+            s.dec_w_hi[i], s.dec_w_lo[i] = dev(h), dev(l)
+            s.dec_wt_hi[i], s.dec_wt_lo[i] = dev(ht), dev(lt)
         for i, gn in enumerate(dn):
             s.dec_g[i] = dev(gn.weight)
             s.dec_be[i] = dev(gn.bias)
         pl, pn = prior_net.linears(), prior_net.norms()
-        def split(t):
-            hi = (t.contiguous().view(torch.int32) & -8192).view(torch.float32)      # keep the top 11 mantissa bits
-            return hi, t - hi
-
         for i, lin in enumerate(pl):
             w = _pad_cols(lin.weight.detach().float(), self.PRI_K[i])
             s.pri_w[i] = dev(w)

@@ -82,12 +82,16 @@ typedef struct HbHumorWeights {
   const float* pri_g[4];
   const float* pri_be[4];
   const float* pri_wt[5]; /* [352][1024] [1024][1024]x3 [1024][96] */
-  /* tensor-core path of the batched prior: hi/lo operand planes (x = hi + lo, hi = top 11 mantissa bits) of
-   * pri_w / pri_wt for the 3xTF32 tcgen05 GEMM; use_umma = 0 keeps the exact-fp32 FFMA kernels */
+  /* tensor-core path (batched prior AND sequential decoder steps): hi/lo operand planes (x = hi + lo, hi = top 11 mantissa bits) of
+   * pri_w / pri_wt / dec_w / dec_wt for the 3xTF32 tcgen05 GEMM; use_umma = 0 keeps the exact-fp32 FFMA kernels */
   const float* pri_w_hi[5];
   const float* pri_w_lo[5];
   const float* pri_wt_hi[5];
   const float* pri_wt_lo[5];
+  const float* dec_w_hi[4];
+  const float* dec_w_lo[4];
+  const float* dec_wt_hi[4];
+  const float* dec_wt_lo[4];
   int use_umma;
   int reserved;
 } HbHumorWeights;

@@ -65,7 +65,8 @@ class HbLbsModel(C.Structure):
     _fields_ = [('num_verts', C.c_int), ('v3_ld', C.c_int), ('wk', C.c_int), ('reserved', C.c_int),
                 ('v_template', C.c_void_p), ('blend', C.c_void_p), ('blend_t', C.c_void_p),
                 ('j_template', C.c_void_p), ('j_dirs', C.c_void_p), ('w_idx', C.c_void_p),
-                ('w_val', C.c_void_p), ('parents', C.c_void_p), ('extra_ids', C.c_void_p)]
+                ('w_val', C.c_void_p), ('parents', C.c_void_p), ('extra_ids', C.c_void_p),
+                ('blend_t_hi', C.c_void_p), ('blend_t_lo', C.c_void_p), ('use_umma', C.c_int), ('reserved2', C.c_int)]
 
 
 class HbHumorWeights(C.Structure):

@@ -86,6 +86,15 @@ class LbsModel:
         s.num_verts, s.v3_ld, s.wk, s.reserved = packed['num_verts'], packed['v3_ld'], packed['wk'], 0
         for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_val', 'parents', 'extra_ids'):
             setattr(s, k, self.t[k].data_ptr())
+        # operand planes of the tensor-core blend GEMM: blend_t with K padded 208 -> 224, split x = hi + lo
+        import os
+        bt = torch.zeros(packed['v3_ld'], 224, device=self.device)
+        bt[:, :KF] = self.t['blend_t']
+        hi = (bt.view(torch.int32) & -8192).view(torch.float32)
+        self.t['blend_t_hi'], self.t['blend_t_lo'] = hi.contiguous(), (bt - hi).contiguous()
+        s.blend_t_hi, s.blend_t_lo = self.t['blend_t_hi'].data_ptr(), self.t['blend_t_lo'].data_ptr()
+        s.use_umma = 0 if os.environ.get('HB_NO_UMMA') else 1
+        s.reserved2 = 0
         self.struct = s
         self._ws = {}
         self._vlists = {}

@@ -15,6 +15,7 @@
 // (~1.2 MB/frame) never exist; per frame the only HBM traffic is the inputs, A (2.5 KB) and v.
 #include "common.cuh"
 #include "lbs_chain.cuh"
+#include "umma_launch.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
@@ -24,8 +25,11 @@ constexpr int SK_FT = 64;    // frames per block tile (forward)
 constexpr int SK_FPT = 16;   // frames per thread (forward)
 constexpr int BW_FT = 16;    // frames per block (backward)
 
+constexpr int TC_SLAB = 512;     // frames per tensor-core slab: v_posed slab (512 x 20736 fp32 = 42 MB) stays in L2
+constexpr int TC_KF = 224;       // feature K padded to a multiple of 32 for the TMA/UMMA tiles
+
 struct LbsWs {
-  float *feat, *A, *dfeat, *dA, *dtr;
+  float *feat, *A, *dfeat, *dA, *dtr, *feat_hi, *feat_lo, *vposed;
   size_t total;
 };
 static LbsWs lbs_carve(float* base, int N) {
@@ -38,6 +42,9 @@ static LbsWs lbs_carve(float* base, int N) {
   w.dfeat = take(Np * LBS_KF);
   w.dA = take(Np * 624);
   w.dtr = take(Np * 4);
+  w.feat_hi = take(Np * TC_KF);
+  w.feat_lo = take(Np * TC_KF);
+  w.vposed = take((size_t)TC_SLAB * 20736);
   w.total = off;
   return w;
 }
@@ -54,7 +61,8 @@ __device__ __forceinline__ void rest_joints(const HbLbsModel& m, const float* __
 
 __global__ void lbs_pose_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ root_orient,
                                 const float* __restrict__ pose_body, const float* __restrict__ betas,
-                                const float* __restrict__ trans, float* feat, float* A, float* joints, int njo) {
+                                const float* __restrict__ trans, float* feat, float* A, float* joints, int njo,
+                                float* feat_hi, float* feat_lo) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float* beta = betas + (size_t)(n / fpb) * LBS_NB;
@@ -70,6 +78,14 @@ __global__ void lbs_pose_kernel(HbLbsModel m, int N, int fpb, const float* __res
     f[205] = f[206] = f[207] = 0.f;
   }
   lbs_chain_fwd(pose, J, m.parents, f ? f + LBS_NB : nullptr, A ? A + (size_t)n * 624 : nullptr, Jp);
+  if (feat_hi && f) {                 // hi/lo operand planes (x = hi + lo) of the feature row for the tensor-core blend
+    for (int k = 0; k < TC_KF; ++k) {
+      const float v = k < 205 ? f[k] : 0.f;
+      const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      feat_hi[(size_t)n * TC_KF + k] = h;
+      feat_lo[(size_t)n * TC_KF + k] = v - h;
+    }
+  }
   if (joints) {
     float t0 = trans[(size_t)n * 3], t1 = trans[(size_t)n * 3 + 1], t2 = trans[(size_t)n * 3 + 2];
     float* jo = joints + (size_t)n * njo * 3;
@@ -144,6 +160,67 @@ lbs_skin_fwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const f
     o[1] = oy + trans[(size_t)n * 3 + 1];
     o[2] = oz + trans[(size_t)n * 3 + 2];
   }
+}
+
+// Tensor-core path, second half: v_posed (template + blend, from the UMMA GEMM, L2-resident slab) -> skinned vertices.
+// Block = 128 consecutive vertices x SA_F frames; the frames' 52 skinning transforms are staged in shared memory
+// (the gather of <=4 transforms per vertex is the shared-memory-bound part of LBS); reads and writes are coalesced.
+constexpr int SA_F = 16;
+__global__ void __launch_bounds__(128)
+lbs_skin_apply_kernel(HbLbsModel m, int nframes, int v3_ld, const float* __restrict__ vposed, const float* __restrict__ A,
+                      const float* __restrict__ trans, float* out) {
+  __shared__ __align__(16) float As[SA_F][624];
+  __shared__ float Ts[SA_F][3];
+  const int tid = threadIdx.x;
+  const int f0 = blockIdx.y * SA_F;
+  const int nf = min(SA_F, nframes - f0);
+  for (int i = tid; i < nf * 624 / 4; i += 128) {
+    reinterpret_cast<float4*>(&As[0][0])[i] = reinterpret_cast<const float4*>(A + (size_t)f0 * 624)[i];
+  }
+  if (tid < nf * 3) Ts[tid / 3][tid % 3] = trans[(size_t)f0 * 3 + tid];
+  __syncthreads();
+  const int v = blockIdx.x * 128 + tid;
+  if (v >= m.num_verts) return;
+  int wi[8];
+  float wv[8];
+  const int wk = m.wk < 8 ? m.wk : 8;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { wi[w] = w < wk ? m.w_idx[(size_t)v * m.wk + w] * 12 : 0; wv[w] = w < wk ? m.w_val[(size_t)v * m.wk + w] : 0.f; }
+  for (int f = 0; f < nf; ++f) {
+    const float* p = vposed + (size_t)(f0 + f) * v3_ld + (size_t)v * 3;
+    const float px = p[0], py = p[1], pz = p[2];
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (wv[w] != 0.f) {
+        const float4* a = reinterpret_cast<const float4*>(&As[f][wi[w]]);
+        const float4 r0 = a[0], r1 = a[1], r2 = a[2];
+        ox = fmaf(wv[w], fmaf(r0.x, px, fmaf(r0.y, py, fmaf(r0.z, pz, r0.w))), ox);
+        oy = fmaf(wv[w], fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w))), oy);
+        oz = fmaf(wv[w], fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))), oz);
+      }
+    }
+    for (int w = 8; w < m.wk; ++w) {                      // generic tail for models with > 8 weights per vertex
+      const float wt = m.w_val[(size_t)v * m.wk + w];
+      if (wt != 0.f) {
+        const float* a = &As[f][m.w_idx[(size_t)v * m.wk + w] * 12];
+        ox = fmaf(wt, fmaf(a[0], px, fmaf(a[1], py, fmaf(a[2], pz, a[3]))), ox);
+        oy = fmaf(wt, fmaf(a[4], px, fmaf(a[5], py, fmaf(a[6], pz, a[7]))), oy);
+        oz = fmaf(wt, fmaf(a[8], px, fmaf(a[9], py, fmaf(a[10], pz, a[11]))), oz);
+      }
+    }
+    float* o = out + ((size_t)(f0 + f) * m.num_verts + v) * 3;
+    o[0] = ox + Ts[f][0]; o[1] = oy + Ts[f][1]; o[2] = oz + Ts[f][2];
+  }
+}
+// joints[n][52 + e] = verts[n][extra_ids[e]]
+__global__ void lbs_gather_extra_kernel(HbLbsModel m, int N, const float* __restrict__ verts, float* joints) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 21) return;
+  const int n = i / 21, e = i % 21;
+  const float* s = verts + ((size_t)n * m.num_verts + m.extra_ids[e]) * 3;
+  float* d = joints + ((size_t)n * 73 + 52 + e) * 3;
+  d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
 }
 
 // One block owns BW_FT frames and walks over the vertex list in chunks of 64; all reductions over
@@ -330,10 +407,30 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
   if (workspace_bytes < ws.total * sizeof(float)) return HB_ERR_WORKSPACE;
   int64_t nl = 0;
   const bool need_skin = (verts != nullptr) || (joints && njo == 73);
+  // dense output of >= 128 frames: blend on the 5th-gen tensor cores (UMMA 3xTF32) + shared-memory skinning pass
+  const bool tc = verts && !vlist && N >= 128 && m->use_umma && m->blend_t_hi && m->v3_ld == 20736 && umma_available();
   lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
-                                             need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo);
+                                             need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
+                                             tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);
   HB_LAUNCH_CHECK(); ++nl;
-  if (need_skin) {
+  if (tc) {
+    GemmEpi ep;
+    ep.bias = m->v_template; ep.gamma = ep.beta = nullptr; ep.xhat = ep.rstd = nullptr; ep.ldxh = 0; ep.Cch = 0; ep.gsize = 64;
+    for (int f0 = 0; f0 < N; f0 += TC_SLAB) {
+      const int nf = (N - f0 < TC_SLAB) ? N - f0 : TC_SLAB;
+      HB_CUDA(launch_umma_gemm3_bn(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
+                                   TC_KF, nf, 3 * m->num_verts, TC_KF, ws.vposed, nullptr, nullptr, m->v3_ld, EPI_BIAS, ep, 128, st));
+      dim3 grid(cdiv(m->num_verts, 128), cdiv(nf, SA_F));
+      lbs_skin_apply_kernel<<<grid, 128, 0, st>>>(*m, nf, m->v3_ld, ws.vposed, ws.A + (size_t)f0 * 624, trans + (size_t)f0 * 3,
+                                                  verts + (size_t)f0 * m->num_verts * 3);
+      HB_LAUNCH_CHECK();
+      nl += 2;
+    }
+    if (joints && njo == 73) {
+      lbs_gather_extra_kernel<<<cdiv(N * 21, 256), 256, 0, st>>>(*m, N, verts, joints);
+      HB_LAUNCH_CHECK(); ++nl;
+    }
+  } else if (need_skin) {
     static bool attr_fwd = false;     // once per process (and outside any stream capture: the first call is a warm-up)
     if (!attr_fwd) {
       HB_CUDA(cudaFuncSetAttribute(lbs_skin_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SKIN_FWD_SMEM));
@@ -372,7 +469,7 @@ extern "C" int humor_lbs_bwd(const HbLbsModel* m, int N, int fpb, const float* r
   const bool need_skin = (d_verts != nullptr) || xj;
   if (need_skin) {
     // recompute the per-frame forward (feature rows, skinning transforms): cheaper than keeping them
-    lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52);
+    lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52, nullptr, nullptr);
     HB_LAUNCH_CHECK(); ++nl;
     static bool attr_bwd = false;
     if (!attr_bwd) {

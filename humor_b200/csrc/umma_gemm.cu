@@ -53,11 +53,17 @@ static cudaError_t launch_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
 cudaError_t launch_umma_gemm3(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
                               int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, int epi, const GemmEpi& ep,
                               cudaStream_t st) {
+  // few row tiles (the sequential decoder steps, M = sub-sequences per GPU): 64-column tiles double the CTA count
+  return launch_umma_gemm3_bn(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, C, C_hi, C_lo, ldc, epi, ep, (M <= 1024) ? 64 : 128, st);
+}
+
+cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
+                                 int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, int epi, const GemmEpi& ep,
+                                 int bn, cudaStream_t st) {
   if (!load_encode()) return cudaErrorNotSupported;
+  if (bn != 64 && bn != 128) return cudaErrorInvalidValue;
   if (K % UM_BK || lda % 4 || ldb % 4 || ldc % 4) return cudaErrorInvalidValue;
   if ((C_hi == nullptr) != (C_lo == nullptr)) return cudaErrorInvalidValue;
-  // few row tiles (the sequential decoder steps, M = sub-sequences per GPU): 64-column tiles double the CTA count
-  const int bn = (M <= 1024) ? 64 : 128;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   if (!make_map(&ta_hi, A_hi, M, K, lda, UM_BM) || !make_map(&ta_lo, A_lo, M, K, lda, UM_BM) ||
       !make_map(&tb_hi, B_hi, N, K, ldb, bn) || !make_map(&tb_lo, B_lo, N, K, ldb, bn))

@@ -6,6 +6,10 @@ namespace hb {
 cudaError_t launch_umma_gemm3(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
                               int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, int epi, const GemmEpi& ep,
                               cudaStream_t st);
+// same with the tile width chosen by the caller (bn = 64 or 128)
+cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
+                                 int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, int epi, const GemmEpi& ep,
+                                 int bn, cudaStream_t st);
 // hi = top 11 mantissa bits of x, lo = x - hi (exact); n elements
 cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 bool umma_available();

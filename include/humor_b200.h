@@ -47,6 +47,12 @@ typedef struct HbLbsModel {
   const float* w_val;      /* [V][wk] weight (padding: 0.0) */
   const int* parents;      /* [52] kintree_table[0], parents[0] = -1 */
   const int* extra_ids;    /* [21] smplx vertex_ids['smplh'] in VertexJointSelector order */
+  /* tensor-core blend: hi/lo planes (x = hi + lo) of blend_t with K padded to 224: [v3_ld][224]; NULL / use_umma = 0
+   * keeps the exact-fp32 FFMA kernels */
+  const float* blend_t_hi;
+  const float* blend_t_lo;
+  int use_umma;
+  int reserved2;
 } HbLbsModel;
 
 /* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs

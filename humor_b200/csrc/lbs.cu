@@ -408,7 +408,7 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
   int64_t nl = 0;
   const bool need_skin = (verts != nullptr) || (joints && njo == 73);
   // dense output of >= 128 frames: blend on the 5th-gen tensor cores (UMMA 3xTF32) + shared-memory skinning pass
-  const bool tc = verts && !vlist && N >= 128 && m->use_umma && m->blend_t_hi && m->v3_ld == 20736 && umma_available();
+  const bool tc = verts && !vlist && N >= 128 && m->use_umma && m->blend_t_hi && m->v3_ld <= 20736 && umma_available();
   lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
                                              need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
                                              tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);

@@ -194,6 +194,10 @@ def run_product(args):
         import torch.distributed as dist
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(times[0]), float(times[1])
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        mo.shard = None                 # the rank-0-only diagnostics below must not enter collectives
     if rank != 0:
         return
     frames = B * T * world * args.steps
@@ -329,6 +333,15 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def _watchdog(limit_s):
+    """A hung collective must not hold a GPU box: hard-exit after limit_s."""
+    def run():
+        time.sleep(limit_s)
+        sys.stderr.write(f'bench.py watchdog: no result after {limit_s} s, aborting\n')
+        os._exit(3)
+    threading.Thread(target=run, daemon=True).start()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -350,6 +363,7 @@ def main():
         print(json.dumps(cpu_baseline_inproc(args, args.cpu_threads or cpu_threads())))
         return
     args.warmup = max(args.warmup, 3) if args.impl == 'humor_b200' else args.warmup
+    _watchdog(int(os.environ.get('HB_BENCH_LIMIT_S', 420)))
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -132,7 +132,9 @@ def run_product(args):
     names = mo.set_stage3_state(prob['params'])
     obs = {k: torch.as_tensor(prob['obs'][k]).to(dev) for k in OBS_KEYS}
     params = [getattr(mo, n) for n in names]
-    mo.use_cuda_graph = (world == 1) and not args.no_graph
+    if world > 1:
+        mo.shard.prepare(obs['seq_interval'])
+    mo.use_cuda_graph = not args.no_graph
 
     def step():
         return mo.stage3_step(obs, params=params)

@@ -20,6 +20,22 @@ import torch.distributed as dist
 class Shard:
     def __init__(self, rank=0, world=1, group=None, ov_max=16):
         self.rank, self.world, self.group, self.ov_max = rank, world, group, ov_max
+        self.ov_prev = None          # frames shared with the previous rank's last sequence (host int, set by prepare)
+
+    def prepare(self, seq_interval):
+        """One-time host exchange of the interval ends so that the per-evaluation halo code has no host
+        synchronisation (and is CUDA-graph capturable together with its collectives)."""
+        iv = seq_interval.detach().to('cpu', torch.int64)
+        mine = torch.tensor([int(iv[0, 0]), int(iv[-1, 1])], dtype=torch.int64)
+        if self.world > 1:
+            dev = seq_interval.device if seq_interval.is_cuda else torch.device('cpu')
+            buf = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(self.world)]
+            dist.all_gather(buf, mine.to(dev), group=self.group)
+            ends = [int(b[1]) for b in buf]
+        else:
+            ends = [int(mine[1])]
+        self.ov_prev = 0 if self.rank == 0 else max(0, ends[self.rank - 1] - int(mine[0]))
+        return self
 
     @staticmethod
     def from_env(ov_max=16):
@@ -58,22 +74,19 @@ def tail_pack(shard, verts3d, betas, floor, T):
 
 def boundary_overlap_energy(shard, verts3d, betas, floor, seq_interval, T):
     """Overlap-consistency energy between this rank's FIRST sequence and the previous rank's LAST one
-    (unweighted; same formulas as fitting_loss.py:142-157,211-215,296-300).  Needs the global interval of the
-    previous rank's last sequence: seq_interval holds the LOCAL rows, so its end is gathered with the pack."""
-    dev = verts3d.device
+    (unweighted; same formulas as fitting_loss.py:142-157,211-215,296-300).  The overlap length with the previous
+    rank comes from Shard.prepare (host, once); nothing here synchronises with the host."""
     ov_max = shard.ov_max
+    if shard.ov_prev is None:
+        shard.prepare(seq_interval)
     pack = tail_pack(shard, verts3d, betas, floor, T)
-    iv = seq_interval.to(device=dev, dtype=verts3d.dtype)
-    pack = torch.cat([pack, iv[-1, 1:2]])                               # + end frame of my last sequence
     allp = _GatherPacks.apply(shard, pack)                              # (world, P)
     zero = verts3d.sum() * 0.0
     stats = {}
-    if shard.rank == 0:
+    ov = shard.ov_prev
+    if shard.rank == 0 or ov <= 0:
         return zero + allp.sum() * 0.0, stats                           # keeps the reverse collective symmetric
     prev = allp[shard.rank - 1]
-    ov = int(round(float(prev[-1].item()))) - int(seq_interval[0, 0].item())
-    if ov <= 0:
-        return zero + allp.sum() * 0.0, stats
     if ov > ov_max or ov > T:
         raise ValueError(f'overlap {ov} exceeds the halo capacity {ov_max} / sequence length {T}')
     a = prev[:ov_max * 129].reshape(ov_max, 43, 3)[ov_max - ov:]        # tail of the previous rank's last sequence

@@ -270,16 +270,12 @@ class MotionOptimizer():
         evaluation (several hundred launches) is captured once per (phase, weights, trainable-set) and replayed."""
         params = self.stage3_params() if params is None else params
         if not self.use_cuda_graph:
-            # torch.autograd.grad (not loss.backward()): no AccumulateGrad nodes get bound to the eager stream, which
-            # would later invalidate a capture of the same closure on the capture stream
-            loss, _, _, _, _ = self.stage3_forward(observed_data, nsteps, init_motion_scale)
-            live = [p for p in params if p.requires_grad]
-            grads = torch.autograd.grad(loss, live, allow_unused=True)
+            loss, grads, live = self._eval_on_aliases(observed_data, nsteps, init_motion_scale, params)
             for p in params:
                 p.grad = None
             for p, gr in zip(live, grads):
                 p.grad = torch.zeros_like(p) if gr is None else gr
-            return loss.detach()
+            return loss
         from . import _ext
         w = self.fitting_loss.loss_weights
         key = (nsteps, float(init_motion_scale), tuple(bool(p.requires_grad) for p in params),
@@ -316,16 +312,40 @@ class MotionOptimizer():
         _ext.LaunchCounter.total += g[2]
         return g[1]
 
+    _STAGE3_NAMES = ('trans', 'root_orient', 'latent_pose', 'betas', 'latent_motion', 'trans_vel', 'joints_vel',
+                     'root_orient_vel', 'floor_plane')
+
+    def _eval_on_aliases(self, observed_data, nsteps, scale, params):
+        """Forward + reverse on fresh detached ALIASES of the variables (same storage, new autograd leaves).
+        The variables' own lazily created AccumulateGrad nodes stay out of the graph: they are bound to whatever
+        stream first used them (the legacy default stream after an eager Stage I/II), and the engine would try to
+        synchronise that stream inside a CUDA-graph capture (cudaErrorStreamCaptureImplicit)."""
+        saved = {}
+        alias_of = {}
+        for n in self._STAGE3_NAMES:
+            t = getattr(self, n, None)
+            if torch.is_tensor(t):
+                a = t.detach().requires_grad_(t.requires_grad)
+                saved[n] = t
+                alias_of[id(t)] = a
+                setattr(self, n, a)
+        try:
+            loss, _, _, _, _ = self.stage3_forward(observed_data, nsteps, scale)
+            live = [p for p in params if p.requires_grad]
+            grads = torch.autograd.grad(loss, [alias_of.get(id(p), p) for p in live], allow_unused=True)
+        finally:
+            for n, t in saved.items():
+                setattr(self, n, t)
+        return loss.detach(), grads, live
+
     def _eval_into_static(self, observed_data, nsteps, scale, params):
-        loss, _, _, _, _ = self.stage3_forward(observed_data, nsteps, scale)
-        live = [p for p in params if p.requires_grad]
-        grads = torch.autograd.grad(loss, live, allow_unused=True)
+        loss, grads, live = self._eval_on_aliases(observed_data, nsteps, scale, params)
         for p, gr in zip(live, grads):
             if gr is None:
                 p.grad.zero_()
             else:
                 p.grad.copy_(gr)
-        return loss.detach()
+        return loss
 
     def stage3_params(self):
         p = [self.trans, self.root_orient, self.latent_pose, self.betas, self.latent_motion,

@@ -132,6 +132,7 @@ def test_cuda_graph_step_matches_eager():
     g_e = [p.grad.clone() for p in params]
     mo.use_cuda_graph = True
     l_g = float(mo.stage3_step(obs, params=params))
+    assert mo.use_cuda_graph and len(mo._graphs) == 1, 'capture fell back to eager'
     assert abs(l_g - l_e) <= 1e-6 * abs(l_e)
     for a, p in zip(g_e, params):
         assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-6 * float(a.abs().max()))

@@ -230,7 +230,7 @@ def run_product(args):
 
 
 def lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind):
-    """Dominant-bytes kernel named by BASELINE: the dense LBS forward (lbs_skin_fwd_kernel) timed alone with CUDA
+    """Dominant-bytes kernel named by BASELINE: the dense LBS forward timed alone with CUDA
     events on the launching stream; algorithmic bytes = 83 896 B/frame x frames per launch."""
     from humor_b200.body_model import lbs
     N = B * T
@@ -253,7 +253,8 @@ def lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind):
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     achieved = N * LBS_BYTES_FWD / (ms * 1e-3) / 1e9
-    return {'kernel': 'lbs forward (lbs_pose_kernel + lbs_skin_fwd_kernel, dense v)', 'bound': 'hbm', 'achieved': achieved,
+    return {'kernel': 'dense LBS forward: lbs_pose_kernel + per 512-frame slab umma_gemm3_kernel<128,BIAS> (tcgen05 blend) + '
+                      'lbs_skin_apply_kernel', 'bound': 'hbm', 'achieved': achieved,
             'peak': hbm_peak, 'peak_source': peak_kind, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
             'ms_per_launch': ms, 'frames_per_launch': N, 'algorithmic_bytes_per_frame': LBS_BYTES_FWD}
 

@@ -90,7 +90,7 @@ class MotionOptimizer():
         # the last sequence of rank r with the first of rank r+1 are exchanged as small halos (parallel.py)
         self.shard = None
         # CUDA-graph capture of the Stage-III closure (forward + backward): one replay per L-BFGS evaluation
-        self.use_cuda_graph = False
+        self.use_cuda_graph = True       # falls back to eager launches (with a warning) if the closure cannot be captured
         self._graphs = {}
         self._contact_idx = torch.tensor(CONTACT_INDS, dtype=torch.long, device=device)
 

@@ -74,6 +74,9 @@ def make_smplh_asset(seed=0):
     # bias towards the body: 80 % of the vertices on body bones
     body_mask = rng.rand(V) < 0.8
     child[body_mask] = rng.randint(1, NUM_BODY_JOINTS, size=int(body_mask.sum()))
+    # vertex ids are region-contiguous, as in the SMPL template (an artist-made mesh whose index ranges follow body
+    # parts: head, torso, arms, hands, legs ...): neighbouring ids are skinned to the same few joints
+    child = np.sort(child, kind='stable')
     parent = par[child]
     u = rng.rand(V, 1)
     radial = rng.randn(V, 3) * np.where(child[:, None] >= 22, 0.008, 0.045)

@@ -18,10 +18,14 @@ _ASSET_PATH = {}
 
 
 def asset_npz(seed=0):
+    """npz of the synthetic asset, keyed by its content so a changed generator never reuses a stale file."""
     if seed not in _ASSET_PATH:
-        p = os.path.join(tempfile.gettempdir(), f'humor_b200_smplh_seed{seed}.npz')
+        import hashlib
+        asset = synth.make_smplh_asset(seed)
+        tag = hashlib.sha1(asset['v_template'].tobytes() + asset['weights'].tobytes()).hexdigest()[:12]
+        p = os.path.join(tempfile.gettempdir(), f'humor_b200_smplh_seed{seed}_{tag}.npz')
         if not os.path.exists(p):
-            synth.write_smplh_npz(p, seed)
+            np.savez(p, **asset)
         _ASSET_PATH[seed] = p
     return _ASSET_PATH[seed]
 

@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry
 // point, so the library does not link libcuda) and launches.
+#include <cstdlib>
 #include "umma_gemm.cuh"
 #include "umma_launch.cuh"
 #include "../../include/humor_b200.h"
@@ -10,6 +11,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+static const bool g_splitk = (getenv("HB_NO_SPLITK") == nullptr);
 static int g_encode_state = 0;      // 0 unknown, 1 ok, -1 unavailable
 
 static bool load_encode() {
@@ -36,18 +38,26 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int K, int ld,
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int KS>
 static cudaError_t launch_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                             int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, const GemmEpi& ep, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm3_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm3_kernel<BN, EPI, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::TOTAL);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dim3 grid(cdiv(N, BN), cdiv(M, UM_BM));
-  umma_gemm3_kernel<BN, EPI><<<grid, 192, UmmaSmem<BN>::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, M, N, K, C, C_hi, C_lo, ldc, ep);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(N, BN) * KS, cdiv(M, UM_BM));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = UmmaSmem<BN>::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = KS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = KS > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, umma_gemm3_kernel<BN, EPI, KS>, a_hi, a_lo, b_hi, b_lo, M, N, K, C, C_hi, C_lo, ldc, ep);
 }
 
 cudaError_t launch_umma_gemm3(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
@@ -68,10 +78,13 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
   if (!make_map(&ta_hi, A_hi, M, K, lda, UM_BM) || !make_map(&ta_lo, A_lo, M, K, lda, UM_BM) ||
       !make_map(&tb_hi, B_hi, N, K, ldb, bn) || !make_map(&tb_lo, B_lo, N, K, ldb, bn))
     return cudaErrorInvalidValue;
+  // split-K over a 4-CTA cluster when there are few output tiles and K is long enough to share
+  const bool splitk = bn == 64 && g_splitk && cdiv(N, 64) * cdiv(M, UM_BM) <= 64 && K >= 8 * UM_BK;
 #define HB_UMMA_CASE(E)                                                                                              \
   case E:                                                                                                            \
-    return bn == 64 ? launch_t<64, E>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st)               \
-                    : launch_t<128, E>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
+    if (splitk) return launch_t<64, E, 4>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);          \
+    return bn == 64 ? launch_t<64, E, 1>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st)            \
+                    : launch_t<128, E, 1>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
   switch (epi) {
     HB_UMMA_CASE(EPI_BIAS)
     HB_UMMA_CASE(EPI_GN_RELU)

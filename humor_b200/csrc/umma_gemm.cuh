@@ -141,7 +141,23 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // positive operands, error growing ~K), which alone would break the 1e-5 parity bound.  Each K-chunk of 128 is
 // therefore accumulated from zero in one of two TMEM buffers and then PROMOTED: the epilogue warps add it to fp32
 // register accumulators (round-to-nearest) while the MMA warp already fills the other buffer.
-template <int BN, int EPI>
+// KS > 1: split-K over a thread-block cluster of KS CTAs (same output tile, disjoint K ranges).  The sequential decoder
+// steps have only M = sub-sequences-per-GPU rows, i.e. ~32 output tiles: splitting K four ways puts 128 CTAs on the
+// chip and shortens each CTA's dependent TMA->MMA chain 4x.  Partials meet in the leader's (rank 0) shared memory
+// through DSMEM stores between two cluster barriers; only the leader runs the epilogue.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem), "r"(rank)); return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+constexpr int UM_RED_LD = 68;      // floats per row of a partial tile in the leader's smem (64 + pad, float4-aligned)
+
+template <int BN, int EPI, int KS>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -157,8 +173,13 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   const uint32_t full0 = bars, empty0 = bars + 8 * UM_STAGES, tfull0 = bars + 16 * UM_STAGES, tempty0 = tfull0 + 16,
                  tptr = tempty0 + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
-  const int nkb = K / UM_BK;
+  static_assert(KS == 1 || BN == 64, "split-K partials are laid out for 64-column tiles");
+  const uint32_t krank = (KS > 1) ? cluster_ctarank() : 0u;
+  const int m0 = blockIdx.y * UM_BM, n0 = (blockIdx.x / KS) * BN;
+  const int nkb_all = K / UM_BK;
+  const int nkb_per = (nkb_all + KS - 1) / KS;
+  const int kb0 = (int)krank * nkb_per;                         // this CTA's K range, in 32-element blocks
+  const int nkb = max(0, min(nkb_all, kb0 + nkb_per) - kb0);
   const int nchunk = (nkb + UM_CHUNK - 1) / UM_CHUNK;
 
   if (warp == 0 && lane == 0) {
@@ -184,12 +205,13 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t st = base + s * SM::STAGE;
         mbar_expect_tx(full0 + 8 * s, SM::STAGE);
-        tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * UM_BK, m0);
-        tma_load_2d(st + SM::A_TILE, &tmA_lo, full0 + 8 * s, kb * UM_BK, m0);
-        tma_load_2d(st + 2 * SM::A_TILE, &tmB_hi, full0 + 8 * s, kb * UM_BK, n0);
-        tma_load_2d(st + 2 * SM::A_TILE + SM::B_TILE, &tmB_lo, full0 + 8 * s, kb * UM_BK, n0);
+        tma_load_2d(st, &tmA_hi, full0 + 8 * s, (kb0 + kb) * UM_BK, m0);
+        tma_load_2d(st + SM::A_TILE, &tmA_lo, full0 + 8 * s, (kb0 + kb) * UM_BK, m0);
+        tma_load_2d(st + 2 * SM::A_TILE, &tmB_hi, full0 + 8 * s, (kb0 + kb) * UM_BK, n0);
+        tma_load_2d(st + 2 * SM::A_TILE + SM::B_TILE, &tmB_lo, full0 + 8 * s, (kb0 + kb) * UM_BK, n0);
       }
     }
+    if (KS > 1) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2 at bits 7 and 10), K-major both, N>>3 at 17, M>>4 at 24
@@ -221,6 +243,7 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         umma_commit(tfull0 + 8 * buf);                         // chunk complete -> promote
       }
     }
+    if (KS > 1) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }
   } else {
     // ------------------------------------------------------------------ epilogue warps: one thread per output row
     const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
@@ -245,6 +268,27 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
+    if (KS > 1) {
+      cluster_sync_all();                                      // #1: every CTA's stage memory is idle now
+      if (krank != 0) {
+        const uint32_t dst = map_to_cta(base, 0) + (uint32_t)(((krank - 1) * UM_BM + q * 32 + lane) * UM_RED_LD) * 4u;
+#pragma unroll
+        for (int j = 0; j < BN; j += 4) st_cluster_v4(dst + j * 4, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
+      cluster_sync_all();                                      // #2: partials have landed in the leader
+      if (krank == 0) {
+#pragma unroll
+        for (int r = 0; r < KS - 1; ++r) {
+          const uint32_t src = base + (uint32_t)((r * UM_BM + q * 32 + lane) * UM_RED_LD) * 4u;
+#pragma unroll
+          for (int j = 0; j < BN; j += 4) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + j * 4));
+            acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+          }
+        }
+      }
+    }
     auto store4 = [&](int col, float a, float b, float c_, float d) {
       if (col + 3 < N) {
         if (C) *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = make_float4(a, b, c_, d);
@@ -263,7 +307,7 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           }
       }
     };
-    if (rok) {
+    if (rok && krank == 0) {
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 64) {
         const int col = n0 + c0;

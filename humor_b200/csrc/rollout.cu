@@ -109,6 +109,8 @@ glue_fwd_kernel(int B, int S, int t, const float* __restrict__ xin, const float*
                 float* xnext, float* xnext_hi, float* xnext_lo, float* world, float* Gnext, float* h1, float* h2, float* h3,
                 float* h1_lo, float* h2_lo, float* h3_lo) {
   __shared__ float s_x[GLUE_WARPS][340], s_r[GLUE_WARPS][216], s_n[GLUE_WARPS][340], s_w[GLUE_WARPS][348];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: let the next GEMM start its prologue
+  asm volatile("griddepcontrol.wait;" ::: "memory");                // ... and wait for the GEMM that produced `raw`
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * GLUE_WARPS + wid;
   if (b >= B) return;
@@ -208,6 +210,8 @@ glue_bwd_kernel(int B, int S, int t, int have_next, const float* __restrict__ xi
                 const float* __restrict__ dGn_g, float* dG, float* dt2j, float* draw, float* draw_hi, float* draw_lo, float* dz) {
   __shared__ float s_x[GLUE_WARPS][340], s_r[GLUE_WARPS][216], s_dn[GLUE_WARPS][340], s_dw[GLUE_WARPS][348],
       s_dx[GLUE_WARPS][340], s_dr[GLUE_WARPS][224];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * GLUE_WARPS + wid;
   if (b >= B) return;
@@ -451,12 +455,19 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
                                        epi_gn(w->dec_b[2], w->dec_g[2], w->dec_be[2], tp.dxh3 + r * 512, 512, tp.drs3 + r * 16, 512, 32), st));
       HB_CUDA(launch_gemm<EPI_BIAS>(tp.h3, 576, w->dec_w[3], 576, tp.raws + r * RAW_LD, RAW_LD, B, 216, 576, epi_bias(w->dec_b[3]), st));
     }
-    glue_fwd_kernel<<<gb, GLUE_WARPS * 32, 0, st>>>(B, S, t, xin, tp.raws + r * RAW_LD, tp.Gs + r * 12, tp.t2j, z_seq,
-                                                    tp.xins + (r + B) * XIN_LD, tc ? tp.xin_hi + (r + B) * XIN_LD : nullptr,
-                                                    tc ? tp.xin_lo + (r + B) * XIN_LD : nullptr, world + r * WORLD_LD,
-                                                    tp.Gs + (r + B) * 12, tp.h1, tp.h2, tp.h3, tc ? tp.h1_lo : nullptr,
-                                                    tc ? tp.h2_lo : nullptr, tc ? tp.h3_lo : nullptr);
-    HB_LAUNCH_CHECK();
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(gb); cfg.blockDim = dim3(GLUE_WARPS * 32); cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      HB_CUDA(cudaLaunchKernelEx(&cfg, glue_fwd_kernel, B, S, t, (const float*)xin, (const float*)(tp.raws + r * RAW_LD),
+                                 (const float*)(tp.Gs + r * 12), (const float*)tp.t2j, z_seq, tp.xins + (r + B) * XIN_LD,
+                                 tc ? tp.xin_hi + (r + B) * XIN_LD : (float*)nullptr, tc ? tp.xin_lo + (r + B) * XIN_LD : (float*)nullptr,
+                                 world + r * WORLD_LD, tp.Gs + (r + B) * 12, tp.h1, tp.h2, tp.h3, tc ? tp.h1_lo : (float*)nullptr,
+                                 tc ? tp.h2_lo : (float*)nullptr, tc ? tp.h3_lo : (float*)nullptr));
+    }
     nl += 5;
   }
   if (prior_out) {
@@ -544,12 +555,21 @@ extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* w
     const int have_next = (t + 1 < S);
     float* dGn = dGbuf[(t + 1) & 1];
     float* dGc = dGbuf[t & 1];
-    glue_bwd_kernel<<<gb, GLUE_WARPS * 32, 0, st>>>(B, S, t, have_next, tp.xins + r * XIN_LD, tp.raws + r * RAW_LD, tp.Gs + r * 12, tp.t2j,
-                                                    d_world + r * WORLD_LD, tp.da0, tp.dpx + (r + B) * 352, tp.dh1, tp.dh2, tp.dh3,
-                                                    tc ? tp.dh1_lo : nullptr, tc ? tp.dh2_lo : nullptr, tc ? tp.dh3_lo : nullptr,
-                                                    tp.dxres, tp.dnsum, dGn, dGc, tp.dt2j, tp.draw, tc ? tp.draw_hi : nullptr,
-                                                    tc ? tp.draw_lo : nullptr, d_z);
-    HB_LAUNCH_CHECK();
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(gb); cfg.blockDim = dim3(GLUE_WARPS * 32); cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      HB_CUDA(cudaLaunchKernelEx(&cfg, glue_bwd_kernel, B, S, t, have_next, (const float*)(tp.xins + r * XIN_LD),
+                                 (const float*)(tp.raws + r * RAW_LD), (const float*)(tp.Gs + r * 12), (const float*)tp.t2j,
+                                 d_world + r * WORLD_LD, (const float*)tp.da0, (const float*)(tp.dpx + (r + B) * 352),
+                                 (const float*)tp.dh1, (const float*)tp.dh2, (const float*)tp.dh3,
+                                 tc ? (const float*)tp.dh1_lo : (const float*)nullptr, tc ? (const float*)tp.dh2_lo : (const float*)nullptr,
+                                 tc ? (const float*)tp.dh3_lo : (const float*)nullptr, tp.dxres, tp.dnsum, (const float*)dGn, dGc,
+                                 tp.dt2j, tp.draw, tc ? tp.draw_hi : (float*)nullptr, tc ? tp.draw_lo : (float*)nullptr, d_z));
+    }
     if (tc) {
       HB_CUDA(launch_umma_gemm3(tp.draw_hi, tp.draw_lo, RAW_LD, w->dec_wt_hi[3], w->dec_wt_lo[3], 224, B, 560, 224, nullptr, tp.dh3,
                                 tp.dh3_lo, 576, EPI_GN_RELU_BWD,

@@ -12,6 +12,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static const bool g_splitk = (getenv("HB_NO_SPLITK") == nullptr);
+static const bool g_pdl = (getenv("HB_NO_PDL") == nullptr);
 static int g_encode_state = 0;      // 0 unknown, 1 ok, -1 unavailable
 
 static bool load_encode() {
@@ -52,11 +53,13 @@ static cudaError_t launch_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = UmmaSmem<BN>::TOTAL;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = KS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see griddepcontrol in the kernel
+  at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = KS; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
   cfg.attrs = at;
-  cfg.numAttrs = KS > 1 ? 1 : 0;
+  cfg.numAttrs = KS > 1 ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, umma_gemm3_kernel<BN, EPI, KS>, a_hi, a_lo, b_hi, b_lo, M, N, K, C, C_hi, C_lo, ldc, ep);
 }
 

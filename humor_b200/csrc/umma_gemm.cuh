@@ -182,6 +182,9 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   const int nkb = max(0, min(nkb_all, kb0 + nkb_per) - kb0);
   const int nchunk = (nkb + UM_CHUNK - 1) / UM_CHUNK;
 
+  // programmatic dependent launch: the next kernel of the chain may be scheduled now and run ITS prologue (barrier
+  // init, TMEM allocation) under this kernel's tail; ours ran under the predecessor's and waits below before reading.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
@@ -196,6 +199,7 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
+  asm volatile("griddepcontrol.wait;" ::: "memory");            // predecessor grid complete, its writes visible
 
   if (warp == 0) {
     if (lane == 0) {

@@ -135,6 +135,7 @@ def run_product(args):
     if world > 1:
         mo.shard.prepare(obs['seq_interval'])
     mo.use_cuda_graph = not args.no_graph
+    mo.set_precision(args.precision)
 
     def step():
         return mo.stage3_step(obs, params=params)
@@ -217,7 +218,7 @@ def run_product(args):
         'config': {'workload': f'Stage-III full-T closure fwd+bwd, B={B} sub-sequences/GPU x T={T}, RGB config '
                                '(optim_floor, fit_rgb_demo_use_split stage-3 weights, overlap 10)',
                    'batch_per_gpu': B, 'seq_len': T, 'parallelism': f'dp{world} over sub-sequences',
-                   'cuda_graph': graphed,
+                   'cuda_graph': graphed, 'precision': args.precision,
                    'collectives_per_step': 0 if world == 1 else 'all_gather(halo pack) fwd + all_reduce(halo grad) bwd',
                    'l2': 'working set per step (rollout tape 0.45 GB + dense vertices 1.3 GB) exceeds the 126 MB L2'},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -356,6 +357,8 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=8)
     ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='tensor', choices=['tensor', 'exact'],
+                    help="'tensor': GEMMs on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels (gradient-exact parity mode)")
     ap.add_argument('--no-graph', action='store_true', help='evaluate the closure eagerly instead of replaying a CUDA graph')
     ap.add_argument('--_cpu-child', dest='cpu_child', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--cpu-threads', type=int, default=0, help=argparse.SUPPRESS)

@@ -235,6 +235,13 @@ class BodyModel(nn.Module):
             self._model = LbsModel(self._packed, dev)
         return self
 
+    def set_precision(self, mode):
+        """'tensor': dense LBS forward blends on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels.  Both keep vertices
+        within ~2e-6 m of the fp64 oracle; the reverse pass is always exact fp32."""
+        if mode not in ('tensor', 'exact'):
+            raise ValueError(mode)
+        self.lbs_model.struct.use_umma = 1 if mode == 'tensor' else 0
+
     @property
     def lbs_model(self):
         if self._model is None:

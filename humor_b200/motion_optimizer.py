@@ -94,6 +94,13 @@ class MotionOptimizer():
         self._graphs = {}
         self._contact_idx = torch.tensor(CONTACT_INDS, dtype=torch.long, device=device)
 
+    def set_precision(self, mode):
+        """'tensor' (default) or 'exact' for the GEMM-shaped kernels of the motion prior and the body model
+        (see HumorModel.set_precision for the measured accuracy of each)."""
+        self.motion_prior.set_precision(mode)
+        self.body_model.set_precision(mode)
+        self.precision = mode
+
     # ------------------------------------------------------------------------------------------------
     # SMPL
     # ------------------------------------------------------------------------------------------------
@@ -278,7 +285,8 @@ class MotionOptimizer():
             return loss
         from . import _ext
         w = self.fitting_loss.loss_weights
-        key = (nsteps, float(init_motion_scale), tuple(bool(p.requires_grad) for p in params),
+        key = (nsteps, float(init_motion_scale), getattr(self.motion_prior, 'precision', None),
+               int(self.body_model.lbs_model.struct.use_umma), tuple(bool(p.requires_grad) for p in params),
                tuple(sorted((k, float(v)) for k, v in w.items())), tuple(id(p) for p in params),
                tuple((k, v.data_ptr()) for k, v in sorted(observed_data.items()) if torch.is_tensor(v)))
         g = self._graphs.get(key)

@@ -10,7 +10,7 @@ from tests import util_stage3 as U
 pytestmark = pytest.mark.gpu
 
 
-def compare(optim_floor, B, T, nsteps, scale, seed=4, overlap=3):
+def compare(optim_floor, B, T, nsteps, scale, seed=4, overlap=3, precision='exact'):
     W = synth.RGB_STAGE3_WEIGHTS if optim_floor else synth.AMASS_STAGE3_WEIGHTS
     prob = synth.make_stage3_problem(B, T, seed=seed, overlap=overlap, cam=optim_floor)
     port = U.build_port(B, T, W, optim_floor, prob)
@@ -21,6 +21,7 @@ def compare(optim_floor, B, T, nsteps, scale, seed=4, overlap=3):
         prob = U.project_joints2d(prob, cj.detach().numpy())
     l_c, g_c, aux_c = U.closure_port(port, prob, optim_floor, nsteps, scale)
     mo = U.build_product(B, T, W, optim_floor, prob)
+    mo.set_precision(precision)
     l_g, g_g, aux_g = U.closure_product(mo, prob, nsteps, scale)
     assert abs(l_g - l_c) / max(1.0, abs(l_c)) < 2e-5, (l_g, l_c)
     for k, v in aux_c['stats'].items():
@@ -28,7 +29,7 @@ def compare(optim_floor, B, T, nsteps, scale, seed=4, overlap=3):
         assert abs(aux_g['stats'][k] - v) <= 2e-4 * max(1.0, abs(v)), (k, aux_g['stats'][k], v)
     for k in g_c:
         err = float((g_g[k].cpu() - g_c[k]).abs().max() / (g_c[k].abs().max() + 1e-8))
-        assert err < 2e-3, (k, err)
+        assert err < (1e-4 if precision == 'exact' else 1e-2), (k, err)
     # vertices of the final camera-frame SMPL evaluation
     v_c = aux_c['inter']['cam_pred']['points3d']
     v_g = aux_g['cam_pred']['points3d'].cpu()
@@ -36,14 +37,16 @@ def compare(optim_floor, B, T, nsteps, scale, seed=4, overlap=3):
     return l_g
 
 
+@pytest.mark.parametrize('precision', ['exact', 'tensor'])
 @pytest.mark.parametrize('nsteps,scale', [(None, 1.0), (4, 1.0), (None, 2.0)])
-def test_closure_rgb_config(nsteps, scale):
-    compare(True, 4, 8, nsteps, scale)
+def test_closure_rgb_config(nsteps, scale, precision):
+    compare(True, 4, 8, nsteps, scale, precision=precision)
 
 
+@pytest.mark.parametrize('precision', ['exact', 'tensor'])
 @pytest.mark.parametrize('nsteps,scale', [(None, 1.0), (4, 1.0)])
-def test_closure_amass_keypts_config(nsteps, scale):
-    compare(False, 3, 7, nsteps, scale)
+def test_closure_amass_keypts_config(nsteps, scale, precision):
+    compare(False, 4, 7, nsteps, scale, precision=precision)
 
 
 def test_closure_is_deterministic():
@@ -79,6 +82,9 @@ def test_full_size_properties():
     for k, g in g_full.items():
         assert torch.isfinite(g).all(), k
     mo2 = U.build_product(sub, T, W, True, p2)
+    mo2.set_precision('exact')
+    mo.set_precision('exact')
+    l_full, g_full, aux = U.closure_product(mo, prob)
     l_sub, g_sub, _ = U.closure_product(mo2, p2)
     assert abs(l_sub - l_c) / max(1.0, abs(l_c)) < 1e-4, (l_sub, l_c)
     for k in g_sub:
@@ -104,14 +110,19 @@ def test_motion_optimizer_run_smoke():
         assert torch.isfinite(v).all()
 
 
+@pytest.mark.parametrize('precision', ['exact', 'tensor'])
 @pytest.mark.parametrize('name', ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass'])
-def test_closure_matches_reference_golden(name):
-    """CUDA path against fixtures produced by the UNMODIFIED reference in the build container."""
+def test_closure_matches_reference_golden(name, precision):
+    """CUDA path against fixtures produced by the UNMODIFIED reference in the build container.
+    'exact' (fp32 FFMA GEMMs): every gradient within 1e-4 of its scale.  'tensor' (tcgen05 3xTF32): forward states,
+    loss and energy terms to the same bounds; gradients through the reverse rollout within 1e-2 (measured ~3e-3:
+    the BPTT amplifies the tensor core's product rounding)."""
     from tests.golden_util import load_case, check_against_golden
     g, prob, c = load_case(name)
     mo = U.build_product(c['B'], c['T'], c['W'], c['optim_floor'], prob)
+    mo.set_precision(precision)
     loss, grads, aux = U.closure_product(mo, prob, c['nsteps'], c['scale'])
-    check_against_golden(g, loss, aux['stats'], grads)
+    check_against_golden(g, loss, aux['stats'], grads, loss_tol=1e-5, stat_tol=1e-4, grad_tol=1e-4 if precision == 'exact' else 1e-2)
     assert np.abs(aux['cam_pred']['verts3d'].detach().cpu().numpy() - g['cam_verts3d']).max() < 1e-4
     assert np.abs(aux['roll']['trans'].detach().cpu().numpy() - g['rollout_trans']).max() < 2e-5
     pm = aux['roll']['cond_prior'][0].detach().cpu().numpy()

@@ -26,7 +26,7 @@ def project_joints2d(prob, cam_joints73, seed=5, noise=2.0):
 
 def build_port(B, T, weights, optim_floor, prob, dtype=torch.float32):
     from oracle.stage3_port import Stage3Port
-    return Stage3Port(synth.make_smplh_asset(), synth.make_humor_state_dict(), synth.make_gmm(), synth.FakeVPoser(),
+    return Stage3Port(synth.make_smplh_asset(), synth.make_humor_state_dict(), synth.make_gmm(), synth.FakeVPoser().to(dtype),
                       weights, B, T, optim_floor, prob['cam_mat'], dtype=dtype)
 
 

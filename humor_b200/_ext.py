@@ -66,7 +66,8 @@ class HbLbsModel(C.Structure):
                 ('v_template', C.c_void_p), ('blend', C.c_void_p), ('blend_t', C.c_void_p),
                 ('j_template', C.c_void_p), ('j_dirs', C.c_void_p), ('w_idx', C.c_void_p),
                 ('w_val', C.c_void_p), ('parents', C.c_void_p), ('extra_ids', C.c_void_p),
-                ('blend_t_hi', C.c_void_p), ('blend_t_lo', C.c_void_p), ('use_umma', C.c_int), ('reserved2', C.c_int)]
+                ('blend_t_hi', C.c_void_p), ('blend_t_lo', C.c_void_p), ('use_umma', C.c_int), ('max_depth', C.c_int),
+                ('depth', C.c_void_p), ('child_start', C.c_void_p), ('child_list', C.c_void_p)]
 
 
 class HbHumorWeights(C.Structure):

@@ -64,7 +64,17 @@ def pack_smplh(asset, num_betas=16):
     w_val = np.take_along_axis(W, order, axis=1).astype(np.float32)
     par = np.asarray(asset['kintree_table'])[0].astype(np.int64).copy()
     par[0] = -1
+    # kinematic tree tables (depth per joint, children in CSR order) for the level-parallel chain kernels
+    depth = np.zeros(NUM_JOINTS, np.int32)
+    for j in range(1, NUM_JOINTS):
+        if not (0 <= par[j] < j):
+            raise ValueError('kintree_table must list parents before children')
+        depth[j] = depth[par[j]] + 1
+    kids = [[c for c in range(1, NUM_JOINTS) if par[c] == j] for j in range(NUM_JOINTS)]
+    child_start = np.cumsum([0] + [len(k) for k in kids]).astype(np.int32)
+    child_list = np.asarray([c for k in kids for c in k], np.int32)
     return {
+        'depth': depth, 'child_start': child_start, 'child_list': child_list, 'max_depth': int(depth.max()),
         'num_verts': V, 'v3_ld': v3_ld, 'wk': wk,
         'v_template': vt.astype(np.float32).reshape(-1), 'blend': blend,
         'blend_t': np.ascontiguousarray(blend.T), 'j_template': j_template.reshape(-1), 'j_dirs': j_dirs,
@@ -94,7 +104,8 @@ class LbsModel:
         self.t['blend_t_hi'], self.t['blend_t_lo'] = hi.contiguous(), (bt - hi).contiguous()
         s.blend_t_hi, s.blend_t_lo = self.t['blend_t_hi'].data_ptr(), self.t['blend_t_lo'].data_ptr()
         s.use_umma = 0 if os.environ.get('HB_NO_UMMA') else 1
-        s.reserved2 = 0
+        s.max_depth = packed['max_depth']
+        s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))
         self.struct = s
         self._ws = {}
         self._vlists = {}

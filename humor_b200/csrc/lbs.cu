@@ -13,6 +13,7 @@
 //   lbs_pose_bwd_kernel  per frame : chain / Rodrigues reverse, d betas
 // (N,6890,4,4) skinning transforms, pose offsets and homogeneous copies that smplx materialises
 // (~1.2 MB/frame) never exist; per frame the only HBM traffic is the inputs, A (2.5 KB) and v.
+#include <cstdlib>
 #include "common.cuh"
 #include "lbs_chain.cuh"
 #include "umma_launch.cuh"
@@ -90,6 +91,274 @@ __global__ void lbs_pose_kernel(HbLbsModel m, int N, int fpb, const float* __res
     float t0 = trans[(size_t)n * 3], t1 = trans[(size_t)n * 3 + 1], t2 = trans[(size_t)n * 3 + 2];
     float* jo = joints + (size_t)n * njo * 3;
     for (int j = 0; j < LBS_J; ++j) { jo[3 * j] = Jp[3 * j] + t0; jo[3 * j + 1] = Jp[3 * j + 1] + t1; jo[3 * j + 2] = Jp[3 * j + 2] + t2; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-per-frame versions of the per-frame kernels (the thread-per-frame ones above keep ~3 KB of local arrays per
+// thread and cost ~150 us per call whatever the frame count: pure latency).  One warp owns one frame; all per-frame
+// state lives in shared memory; the kinematic chain runs level by level (joints of equal tree depth in parallel,
+// m.depth / m.max_depth from pack_smplh); the reverse pass lets every parent PULL from its children in CSR order, so
+// no atomics are needed and results are bit-reproducible.
+// ------------------------------------------------------------------------------------------------
+constexpr int PW = 4;            // warps (frames) per block
+struct PoseSm {
+  float pose[68], beta[16], J[156], Rl[198], rot[198], tw[156];
+};
+struct PoseBwdSm {
+  float drot[198], dt[156], dJ[156], sc[468];
+};
+
+__device__ __forceinline__ void pose_forward_warp(const HbLbsModel& m, PoseSm& s, int lane, int n, int fpb,
+                                                  const float* __restrict__ root_orient, const float* __restrict__ pose_body,
+                                                  const float* __restrict__ betas) {
+  for (int i = lane; i < 66; i += 32) s.pose[i] = i < 3 ? root_orient[(size_t)n * 3 + i] : pose_body[(size_t)n * 63 + i - 3];
+  if (lane < 16) s.beta[lane] = betas[(size_t)(n / fpb) * LBS_NB + lane];
+  __syncwarp();
+  for (int e = lane; e < LBS_J * 3; e += 32) {
+    float a = m.j_template[e];
+    const float4* d = reinterpret_cast<const float4*>(m.j_dirs + e * LBS_NB);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 w = __ldg(d + q);
+      a = fmaf(w.x, s.beta[4 * q], a); a = fmaf(w.y, s.beta[4 * q + 1], a);
+      a = fmaf(w.z, s.beta[4 * q + 2], a); a = fmaf(w.w, s.beta[4 * q + 3], a);
+    }
+    s.J[e] = a;
+  }
+  if (lane < LBS_JB) rodrigues_fwd(s.pose + 3 * lane, s.Rl + 9 * lane);
+  __syncwarp();
+  for (int L = 0; L <= m.max_depth; ++L) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = lane + 32 * h;
+      if (j < LBS_J && m.depth[j] == L) {
+        if (j == 0) {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) s.rot[e] = s.Rl[e];
+          s.tw[0] = s.J[0]; s.tw[1] = s.J[1]; s.tw[2] = s.J[2];
+        } else {
+          const int p = m.parents[j];
+          if (j < LBS_JB) mat3_mul(s.rot + 9 * p, s.Rl + 9 * j, s.rot + 9 * j);
+          const float rel[3] = {s.J[3 * j] - s.J[3 * p], s.J[3 * j + 1] - s.J[3 * p + 1], s.J[3 * j + 2] - s.J[3 * p + 2]};
+          float o[3];
+          mat3_vec(s.rot + 9 * lbs_rot_owner(p), rel, o);
+          s.tw[3 * j] = o[0] + s.tw[3 * p]; s.tw[3 * j + 1] = o[1] + s.tw[3 * p + 1]; s.tw[3 * j + 2] = o[2] + s.tw[3 * p + 2];
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(PW * 32)
+lbs_pose_warp_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ root_orient, const float* __restrict__ pose_body,
+                     const float* __restrict__ betas, const float* __restrict__ trans, float* feat, float* A, float* joints,
+                     int njo, float* feat_hi, float* feat_lo) {
+  __shared__ PoseSm sm[PW];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * PW + wid;
+  if (n >= N) return;
+  PoseSm& s = sm[wid];
+  pose_forward_warp(m, s, lane, n, fpb, root_orient, pose_body, betas);
+  if (feat) {
+    float* f = feat + (size_t)n * LBS_KF;
+    for (int k = lane; k < TC_KF; k += 32) {
+      float v = 0.f;
+      if (k < LBS_NB) v = s.beta[k];
+      else if (k < 205) {
+        const int idx = k - LBS_NB, e = idx % 9;
+        v = s.Rl[9 + idx] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+      }
+      if (k < LBS_KF) f[k] = v;
+      if (feat_hi) {
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        feat_hi[(size_t)n * TC_KF + k] = h;
+        feat_lo[(size_t)n * TC_KF + k] = v - h;
+      }
+    }
+  }
+  const float t0 = joints ? trans[(size_t)n * 3] : 0.f, t1 = joints ? trans[(size_t)n * 3 + 1] : 0.f, t2 = joints ? trans[(size_t)n * 3 + 2] : 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+    if (j < LBS_J) {
+      if (A) {
+        const float* r = s.rot + 9 * lbs_rot_owner(j);
+        float c[3];
+        mat3_vec(r, s.J + 3 * j, c);
+        float4* a = reinterpret_cast<float4*>(A + (size_t)n * 624 + j * 12);
+        a[0] = make_float4(r[0], r[1], r[2], s.tw[3 * j] - c[0]);
+        a[1] = make_float4(r[3], r[4], r[5], s.tw[3 * j + 1] - c[1]);
+        a[2] = make_float4(r[6], r[7], r[8], s.tw[3 * j + 2] - c[2]);
+      }
+      if (joints) {
+        float* jo = joints + ((size_t)n * njo + j) * 3;
+        jo[0] = s.tw[3 * j] + t0; jo[1] = s.tw[3 * j + 1] + t1; jo[2] = s.tw[3 * j + 2] + t2;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PW * 32)
+lbs_pose_bwd_warp_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ root_orient, const float* __restrict__ pose_body,
+                         const float* __restrict__ betas, const float* __restrict__ dfeat, const float* __restrict__ dA,
+                         const float* __restrict__ dtr, const float* __restrict__ djoints, int njo, float* d_root_orient,
+                         float* d_pose_body, float* d_betas, float* d_trans) {
+  __shared__ PoseSm sm[PW];
+  __shared__ PoseBwdSm sb[PW];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * PW + wid;
+  if (n >= N) return;
+  PoseSm& s = sm[wid];
+  PoseBwdSm& b = sb[wid];
+  pose_forward_warp(m, s, lane, n, fpb, root_orient, pose_body, betas);
+  const float* dAn = dA ? dA + (size_t)n * 624 : nullptr;
+  const float* dj = djoints ? djoints + (size_t)n * njo * 3 : nullptr;
+  // ---- a. per-joint seeds: A_j = [rot_o | tw_j - rot_o J_j], Jp_j = tw_j
+  for (int i = lane; i < 198; i += 32) b.drot[i] = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+    if (j < LBS_J) {
+      float gt[3] = {0.f, 0.f, 0.f};
+      if (dAn) {
+        gt[0] = dAn[j * 12 + 3]; gt[1] = dAn[j * 12 + 7]; gt[2] = dAn[j * 12 + 11];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) b.sc[j * 9 + i * 3 + k] = dAn[j * 12 + i * 4 + k] - gt[i] * s.J[3 * j + k];
+        float back[3];
+        mat3_tvec(s.rot + 9 * lbs_rot_owner(j), gt, back);
+        b.dJ[3 * j] = -back[0]; b.dJ[3 * j + 1] = -back[1]; b.dJ[3 * j + 2] = -back[2];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) b.sc[j * 9 + e] = 0.f;
+        b.dJ[3 * j] = b.dJ[3 * j + 1] = b.dJ[3 * j + 2] = 0.f;
+      }
+      if (dj) { gt[0] += dj[3 * j]; gt[1] += dj[3 * j + 1]; gt[2] += dj[3 * j + 2]; }
+      b.dt[3 * j] = gt[0]; b.dt[3 * j + 1] = gt[1]; b.dt[3 * j + 2] = gt[2];
+    }
+  }
+  __syncwarp();
+  if (lane < LBS_JB) {                                   // rotation owners collect the A-part (wrists also their 15 hand joints)
+    float acc[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) acc[e] = b.sc[lane * 9 + e];
+    if (lane == 20 || lane == 21) {
+      const int h0 = lane == 20 ? 22 : 37;
+      for (int hj = h0; hj < h0 + 15; ++hj)
+#pragma unroll
+        for (int e = 0; e < 9; ++e) acc[e] += b.sc[hj * 9 + e];
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) b.drot[lane * 9 + e] = acc[e];
+  }
+  __syncwarp();
+  for (int i = lane; i < 468; i += 32) b.sc[i] = 0.f;    // sc now carries g (x) rel of hand joints whose parent is a hand joint
+  __syncwarp();
+  // ---- b. reverse levels: every joint pulls from its children (fixed CSR order)
+  for (int L = m.max_depth; L >= 0; --L) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = lane + 32 * h;
+      if (j < LBS_J && m.depth[j] == L) {
+        const int o = lbs_rot_owner(j);
+        float adt[3] = {b.dt[3 * j], b.dt[3 * j + 1], b.dt[3 * j + 2]};
+        float aJ[3] = {b.dJ[3 * j], b.dJ[3 * j + 1], b.dJ[3 * j + 2]};
+        float ar[9];
+        if (j < LBS_JB) {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) ar[e] = b.drot[j * 9 + e];
+        }
+        for (int ci = m.child_start[j]; ci < m.child_start[j + 1]; ++ci) {
+          const int c = m.child_list[ci];
+          const float g[3] = {b.dt[3 * c], b.dt[3 * c + 1], b.dt[3 * c + 2]};
+          const float rel[3] = {s.J[3 * c] - s.J[3 * j], s.J[3 * c + 1] - s.J[3 * j + 1], s.J[3 * c + 2] - s.J[3 * j + 2]};
+          float back[3];
+          mat3_tvec(s.rot + 9 * o, g, back);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { adt[i] += g[i]; aJ[i] -= back[i]; }
+          if (j < LBS_JB) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int k = 0; k < 3; ++k) ar[i * 3 + k] += g[i] * rel[k];
+            if (c < LBS_JB) {                             // rot_c = rot_j R_c
+              const float* dc = b.drot + 9 * c;
+              const float* Rc = s.Rl + 9 * c;
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) ar[i * 3 + k] += dc[i * 3] * Rc[k * 3] + dc[i * 3 + 1] * Rc[k * 3 + 1] + dc[i * 3 + 2] * Rc[k * 3 + 2];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int k = 0; k < 3; ++k) b.sc[c * 9 + i * 3 + k] = g[i] * rel[k];
+          }
+        }
+        if (j == 20 || j == 21) {                         // wrist: + contributions parked by its hand joints
+          const int h0 = j == 20 ? 22 : 37;
+          for (int hj = h0; hj < h0 + 15; ++hj)
+#pragma unroll
+            for (int e = 0; e < 9; ++e) ar[e] += b.sc[hj * 9 + e];
+        }
+        if (j > 0) {
+          float back[3];
+          mat3_tvec(s.rot + 9 * lbs_rot_owner(m.parents[j]), adt, back);
+          aJ[0] += back[0]; aJ[1] += back[1]; aJ[2] += back[2];
+        } else {
+          aJ[0] += adt[0]; aJ[1] += adt[1]; aJ[2] += adt[2];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { b.dt[3 * j + i] = adt[i]; b.dJ[3 * j + i] = aJ[i]; }
+        if (j < LBS_JB) {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) b.drot[j * 9 + e] = ar[e];
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // ---- c. rotations -> axis-angle
+  if (lane < LBS_JB) {
+    float dR[9];
+    if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) dR[e] = b.drot[e];
+    } else {
+      const float* rp = s.rot + 9 * m.parents[lane];
+      const float* dr = b.drot + 9 * lane;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dR[i * 3 + k] = rp[i] * dr[k] + rp[3 + i] * dr[3 + k] + rp[6 + i] * dr[6 + k];
+      if (dfeat) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) dR[e] += dfeat[(size_t)n * LBS_KF + LBS_NB + (lane - 1) * 9 + e];
+      }
+    }
+    float d3[3] = {0.f, 0.f, 0.f};
+    rodrigues_bwd(s.pose + 3 * lane, dR, d3);
+    float* out = lane == 0 ? d_root_orient + (size_t)n * 3 : d_pose_body + (size_t)n * 63 + (lane - 1) * 3;
+    out[0] = d3[0]; out[1] = d3[1]; out[2] = d3[2];
+  }
+  // ---- d. betas:  dfeat[0:16] + J_dirs^T dJ   (two half-sums combined in a fixed order)
+  {
+    const int l = lane & 15, half = lane >> 4;
+    float a = 0.f;
+    for (int e = half * 78; e < half * 78 + 78; ++e) a = fmaf(m.j_dirs[e * LBS_NB + l], b.dJ[e], a);
+    const float other = __shfl_xor_sync(0xffffffffu, a, 16);
+    if (half == 0) d_betas[(size_t)n * LBS_NB + l] = (dfeat ? dfeat[(size_t)n * LBS_KF + l] : 0.f) + (a + other);
+  }
+  // ---- e. translation
+  if (lane < 3) {
+    float t = dtr ? dtr[(size_t)n * 4 + lane] : 0.f;
+    if (dj)
+      for (int j = 0; j < LBS_J; ++j) t += dj[3 * j + lane];
+    d_trans[(size_t)n * 3 + lane] = t;
   }
 }
 
@@ -228,7 +497,10 @@ __global__ void lbs_gather_extra_kernel(HbLbsModel m, int N, const float* __rest
 __global__ void __launch_bounds__(256)
 lbs_skin_bwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const float* __restrict__ A,
                     const int* __restrict__ vlist, int nv, const float* __restrict__ dv, size_t dv_fs,
-                    float* dfeat, float* dA, float* dtr, int accumulate) {
+                    float* dfeat, float* dA, float* dtr, int accumulate,
+                    const int* __restrict__ vlist2, int nv1, const float* __restrict__ dv2, size_t dv2_fs) {
+  // slots [0, nv1) come from (vlist, dv); slots [nv1, nv) from the second source (vlist2, dv2) - used to fold the 21
+  // vertex-picked joints into the same pass as the listed key vertices (nv1 == nv: single source)
   extern __shared__ __align__(16) float sm[];
   float* Fs = sm;                              // [BW_FT][208]
   float* GP = Fs + BW_FT * LBS_KF;             // [BW_FT][192]   d v_posed
@@ -251,7 +523,7 @@ lbs_skin_bwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const f
   for (int c0 = 0; c0 < nv; c0 += 64) {
     const int slot = c0 + vi;
     const bool vok = slot < nv;
-    const int vid = vok ? (vlist ? vlist[slot] : slot) : 0;
+    const int vid = vok ? (slot < nv1 ? (vlist ? vlist[slot] : slot) : vlist2[slot - nv1]) : 0;
     // ---- phase 1: v_posed and d v_posed for (4 frames, 1 vertex)
     {
       float acc[4][3];
@@ -277,7 +549,7 @@ lbs_skin_bwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const f
         const int fl = fq * 4 + f, n = f0 + fl;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
         if (vok && n < N) {
-          const float* g = dv + (size_t)n * dv_fs + (size_t)slot * 3;
+          const float* g = slot < nv1 ? dv + (size_t)n * dv_fs + (size_t)slot * 3 : dv2 + (size_t)n * dv2_fs + (size_t)(slot - nv1) * 3;
           g0 = g[0]; g1 = g[1]; g2 = g[2];
           const float* An = A + (size_t)n * 624;
           for (int w = 0; w < m.wk; ++w) {
@@ -303,7 +575,7 @@ lbs_skin_bwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const f
         const int r = e / 4, c = e % 4;
         float* dst = dAs + f * 624 + e;
         for (int i = 0; i < cn; ++i) {
-          const int v2 = vlist ? vlist[c0 + i] : c0 + i;
+          const int v2 = (c0 + i) < nv1 ? (vlist ? vlist[c0 + i] : c0 + i) : vlist2[c0 + i - nv1];
           const float gr = Gs[f * 192 + i * 3 + r];
           const float pc = c < 3 ? Ps[f * 192 + i * 3 + c] : 1.f;
           const float gpc = gr * pc;
@@ -319,7 +591,7 @@ lbs_skin_bwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const f
     // ---- phase 2b: d feat[f][k] += sum_vc GP[f][vc] * blend_t[vc][k]   thread = k
     if (tid < LBS_KF) {
       for (int i = 0; i < cn; ++i) {
-        const int v2 = vlist ? vlist[c0 + i] : c0 + i;
+        const int v2 = (c0 + i) < nv1 ? (vlist ? vlist[c0 + i] : c0 + i) : vlist2[c0 + i - nv1];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float bt = __ldg(m.blend_t + ((size_t)v2 * 3 + c) * LBS_KF + tid);
@@ -388,6 +660,7 @@ __global__ void lbs_pose_bwd_kernel(HbLbsModel m, int N, int fpb, const float* _
   d_trans[(size_t)n * 3] = t[0]; d_trans[(size_t)n * 3 + 1] = t[1]; d_trans[(size_t)n * 3 + 2] = t[2];
 }
 
+static const bool g_thread_pose = (getenv("HB_LBS_THREAD") != nullptr);
 static const size_t SKIN_FWD_SMEM = (size_t)SK_FT * LBS_KF * sizeof(float);
 static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + BW_FT * 624) * sizeof(float);
 
@@ -409,9 +682,14 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
   const bool need_skin = (verts != nullptr) || (joints && njo == 73);
   // dense output of >= 128 frames: blend on the 5th-gen tensor cores (UMMA 3xTF32) + shared-memory skinning pass
   const bool tc = verts && !vlist && N >= 128 && m->use_umma && m->blend_t_hi && m->v3_ld <= 20736 && umma_available();
-  lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
-                                             need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
-                                             tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);
+  if (m->depth && m->child_start && !g_thread_pose)
+    lbs_pose_warp_kernel<<<cdiv(N, PW), PW * 32, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
+                                                         need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
+                                                         tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);
+  else
+    lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
+                                               need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
+                                               tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);
   HB_LAUNCH_CHECK(); ++nl;
   if (tc) {
     GemmEpi ep;
@@ -469,7 +747,11 @@ extern "C" int humor_lbs_bwd(const HbLbsModel* m, int N, int fpb, const float* r
   const bool need_skin = (d_verts != nullptr) || xj;
   if (need_skin) {
     // recompute the per-frame forward (feature rows, skinning transforms): cheaper than keeping them
-    lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52, nullptr, nullptr);
+    if (m->depth && m->child_start && !g_thread_pose)
+      lbs_pose_warp_kernel<<<cdiv(N, PW), PW * 32, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52,
+                                                           nullptr, nullptr);
+    else
+      lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52, nullptr, nullptr);
     HB_LAUNCH_CHECK(); ++nl;
     static bool attr_bwd = false;
     if (!attr_bwd) {
@@ -477,22 +759,35 @@ extern "C" int humor_lbs_bwd(const HbLbsModel* m, int N, int fpb, const float* r
       attr_bwd = true;
     }
     int acc = 0;
-    if (d_verts) {
-      const int nvv = vlist ? nv : m->num_verts;
-      lbs_skin_bwd_kernel<<<cdiv(N, BW_FT), 256, SKIN_BWD_SMEM, st>>>(*m, N, ws.feat, ws.A, vlist, nvv, d_verts, (size_t)nvv * 3,
-                                                                     ws.dfeat, ws.dA, ws.dtr, acc);
+    if (d_verts && vlist && xj) {
+      // listed key vertices + the 21 vertex-picked joints in ONE pass (43 + 21 = 64 = one chunk on the Stage-III path)
+      lbs_skin_bwd_kernel<<<cdiv(N, BW_FT), 256, SKIN_BWD_SMEM, st>>>(*m, N, ws.feat, ws.A, vlist, nv + 21, d_verts, (size_t)nv * 3,
+                                                                     ws.dfeat, ws.dA, ws.dtr, 0, m->extra_ids, nv, d_joints + 52 * 3,
+                                                                     (size_t)73 * 3);
       HB_LAUNCH_CHECK(); ++nl;
-      acc = 1;
-    }
-    if (xj) {
-      lbs_skin_bwd_kernel<<<cdiv(N, BW_FT), 256, SKIN_BWD_SMEM, st>>>(*m, N, ws.feat, ws.A, m->extra_ids, 21, d_joints + 52 * 3,
-                                                                     (size_t)73 * 3, ws.dfeat, ws.dA, ws.dtr, acc);
-      HB_LAUNCH_CHECK(); ++nl;
+    } else {
+      if (d_verts) {
+        const int nvv = vlist ? nv : m->num_verts;
+        lbs_skin_bwd_kernel<<<cdiv(N, BW_FT), 256, SKIN_BWD_SMEM, st>>>(*m, N, ws.feat, ws.A, vlist, nvv, d_verts, (size_t)nvv * 3,
+                                                                       ws.dfeat, ws.dA, ws.dtr, acc, nullptr, nvv, nullptr, 0);
+        HB_LAUNCH_CHECK(); ++nl;
+        acc = 1;
+      }
+      if (xj) {
+        lbs_skin_bwd_kernel<<<cdiv(N, BW_FT), 256, SKIN_BWD_SMEM, st>>>(*m, N, ws.feat, ws.A, m->extra_ids, 21, d_joints + 52 * 3,
+                                                                       (size_t)73 * 3, ws.dfeat, ws.dA, ws.dtr, acc, nullptr, 21, nullptr, 0);
+        HB_LAUNCH_CHECK(); ++nl;
+      }
     }
   }
-  lbs_pose_bwd_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, need_skin ? ws.dfeat : nullptr,
-                                                 need_skin ? ws.dA : nullptr, need_skin ? ws.dtr : nullptr, d_joints, njo,
-                                                 d_root_orient, d_pose_body, d_betas, d_trans);
+  if (m->depth && m->child_start && !g_thread_pose)
+    lbs_pose_bwd_warp_kernel<<<cdiv(N, PW), PW * 32, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, need_skin ? ws.dfeat : nullptr,
+                                                             need_skin ? ws.dA : nullptr, need_skin ? ws.dtr : nullptr, d_joints, njo,
+                                                             d_root_orient, d_pose_body, d_betas, d_trans);
+  else
+    lbs_pose_bwd_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, need_skin ? ws.dfeat : nullptr,
+                                                   need_skin ? ws.dA : nullptr, need_skin ? ws.dtr : nullptr, d_joints, njo,
+                                                   d_root_orient, d_pose_body, d_betas, d_trans);
   HB_LAUNCH_CHECK(); ++nl;
   if (launches) *launches = nl;
   return HB_OK;

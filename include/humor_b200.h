@@ -52,7 +52,11 @@ typedef struct HbLbsModel {
   const float* blend_t_hi;
   const float* blend_t_lo;
   int use_umma;
-  int reserved2;
+  int max_depth;           /* deepest level of the kinematic tree (root = 0) */
+  /* kinematic tree tables for the warp-per-frame kernels: depth of every joint, children in CSR form */
+  const int* depth;        /* [52] */
+  const int* child_start;  /* [53] */
+  const int* child_list;   /* [51] */
 } HbLbsModel;
 
 /* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs

@@ -298,6 +298,39 @@ def cpu_baseline_inproc(args, threads):
             's_per_step': med}
 
 
+def port_on_cuda(args):
+    """Context number for SURVEY.md 8(d): the reference ALGORITHM as eager PyTorch on the same B200 (the oracle port on
+    device='cuda' - the reference itself cannot travel to the GPU box).  Launch/dispatch-bound, so its time per closure
+    barely depends on B; the largest batch that fits is the fairest frames/s.  Not part of the default run."""
+    from tests import util_stage3 as U
+    import warnings
+    warnings.filterwarnings('ignore')
+    T = args.seq_len
+    res = []
+    for Bc in [int(b) for b in args.port_cuda.split(',')]:
+        try:
+            prob = build_problem(Bc, T, seed=4)
+            port = U.build_port(Bc, T, synth.RGB_STAGE3_WEIGHTS, True, prob, device='cuda')
+            U.closure_port(port, prob, True, device='cuda')
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(args.cpu_steps):
+                t0 = time.perf_counter()
+                U.closure_port(port, prob, True, device='cuda')
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            med = float(np.median(ts))
+            res.append({'batch': Bc, 's_per_step': med, 'frames_per_s': Bc * T / med,
+                        'peak_mem_gb': torch.cuda.max_memory_allocated() / 2**30})
+        except torch.OutOfMemoryError:
+            res.append({'batch': Bc, 'oom': True})
+        finally:
+            port = None
+            torch.cuda.empty_cache()
+    print(json.dumps({'impl': 'port-cuda', 'metric': METRIC, 'unit': 'frames/s', 'kind': 'oracle port, eager PyTorch on cuda:0',
+                      'steps': args.cpu_steps, 'results': res}))
+
+
 def cpu_threads():
     # the closure is ~10^5 small torch ops: beyond ~16 intra-op threads the fork/join cost dominates
     return min(os.cpu_count() or 1, int(os.environ.get('HB_CPU_THREADS', 16)))
@@ -360,6 +393,7 @@ def main():
     ap.add_argument('--precision', default='tensor', choices=['tensor', 'exact'],
                     help="'tensor': GEMMs on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels (gradient-exact parity mode)")
     ap.add_argument('--no-graph', action='store_true', help='evaluate the closure eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--port-cuda', default='', help='comma list of batch sizes: time the oracle port as eager PyTorch on cuda:0')
     ap.add_argument('--_cpu-child', dest='cpu_child', action='store_true', help=argparse.SUPPRESS)
     ap.add_argument('--cpu-threads', type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -370,7 +404,9 @@ def main():
         return
     args.warmup = max(args.warmup, 3) if args.impl == 'humor_b200' else args.warmup
     _watchdog(int(os.environ.get('HB_BENCH_LIMIT_S', 420)))
-    if args.impl == 'reference':
+    if args.port_cuda:
+        port_on_cuda(args)
+    elif args.impl == 'reference':
         run_reference(args)
     else:
         run_product(args)

@@ -67,7 +67,9 @@ class HbLbsModel(C.Structure):
                 ('j_template', C.c_void_p), ('j_dirs', C.c_void_p), ('w_idx', C.c_void_p),
                 ('w_val', C.c_void_p), ('parents', C.c_void_p), ('extra_ids', C.c_void_p),
                 ('blend_t_hi', C.c_void_p), ('blend_t_lo', C.c_void_p), ('use_umma', C.c_int), ('max_depth', C.c_int),
-                ('depth', C.c_void_p), ('child_start', C.c_void_p), ('child_list', C.c_void_p)]
+                ('depth', C.c_void_p), ('child_start', C.c_void_p), ('child_list', C.c_void_p),
+                ('fblend_hi', C.c_void_p), ('fblend_lo', C.c_void_p), ('fw_idx', C.c_void_p), ('fw_val', C.c_void_p),
+                ('fused_nct', C.c_int), ('fused_wk', C.c_int)]
 
 
 class HbHumorWeights(C.Structure):

@@ -73,7 +73,24 @@ def pack_smplh(asset, num_betas=16):
     kids = [[c for c in range(1, NUM_JOINTS) if par[c] == j] for j in range(NUM_JOINTS)]
     child_start = np.cumsum([0] + [len(k) for k in kids]).astype(np.int32)
     child_list = np.asarray([c for k in kids for c in k], np.int32)
+    # fused dense forward: blend matrix in 42-vertex tile order (+ template in feature column 205), weights by joint id
+    nct = (V + 41) // 42
+    fb = np.zeros((nct * 128, 224), np.float32)
+    vid = np.arange(V)
+    rows = (vid // 42) * 128 + ((vid % 42) // 21) * 64 + ((vid % 42) % 21) * 3
+    for d in range(3):
+        fb[rows + d, :KF] = blend[:, d:3 * V:3].T
+        fb[rows + d, 205] = vt[:, d]
+    fwk = 4 if wk <= 4 else (8 if wk <= 8 else 0)
+    fw_idx = np.zeros((V, max(fwk, 1)), np.int32)
+    fw_val = np.zeros((V, max(fwk, 1)), np.float32)
+    if fwk:
+        key = np.where(w_val != 0, w_idx, NUM_JOINTS + 1)                     # zero-weight slots last
+        o2 = np.argsort(key, axis=1, kind='stable')
+        fw_idx[:, :wk] = np.take_along_axis(w_idx, o2, axis=1) * 12
+        fw_val[:, :wk] = np.take_along_axis(w_val, o2, axis=1)
     return {
+        'fblend': fb, 'fw_idx': fw_idx, 'fw_val': fw_val, 'fused_nct': nct, 'fused_wk': fwk,
         'depth': depth, 'child_start': child_start, 'child_list': child_list, 'max_depth': int(depth.max()),
         'num_verts': V, 'v3_ld': v3_ld, 'wk': wk,
         'v_template': vt.astype(np.float32).reshape(-1), 'blend': blend,
@@ -104,18 +121,30 @@ class LbsModel:
         self.t['blend_t_hi'], self.t['blend_t_lo'] = hi.contiguous(), (bt - hi).contiguous()
         s.blend_t_hi, s.blend_t_lo = self.t['blend_t_hi'].data_ptr(), self.t['blend_t_lo'].data_ptr()
         s.use_umma = 0 if os.environ.get('HB_NO_UMMA') else 1
+        fh = (self.t['fblend'].view(torch.int32) & -8192).view(torch.float32)
+        self.t['fblend_hi'], self.t['fblend_lo'] = fh.contiguous(), (self.t['fblend'] - fh).contiguous()
+        del self.t['fblend']
+        s.fblend_hi, s.fblend_lo = self.t['fblend_hi'].data_ptr(), self.t['fblend_lo'].data_ptr()
+        s.fw_idx, s.fw_val = self.t['fw_idx'].data_ptr(), self.t['fw_val'].data_ptr()
+        # The fused kernel is numerically identical but slower than GEMM + skin pass on assets whose neighbouring vertices
+        # do not share joints ("fused dense LBS: measured and parked"): opt-in only.
+        self.fused_wk = packed['fused_wk']
+        s.fused_nct, s.fused_wk = packed['fused_nct'], (packed['fused_wk'] if os.environ.get('HB_LBS_FUSED') else 0)
+        self.ws_slot = 0
         s.max_depth = packed['max_depth']
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))
         self.struct = s
         self._ws = {}
         self._vlists = {}
 
-    def workspace(self, N):
-        ws = self._ws.get(N)
+    def workspace(self, N, slot=None):
+        """Scratch for one C-ABI call.  ``slot`` separates calls that may be in flight on different streams."""
+        key = (N, self.ws_slot if slot is None else slot)
+        ws = self._ws.get(key)
         if ws is None:
             nbytes = _ext.lib().humor_lbs_workspace_bytes(N)
             ws = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
-            self._ws[N] = ws
+            self._ws[key] = ws
         return ws
 
     def vlist(self, ids):

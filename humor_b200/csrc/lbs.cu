@@ -81,7 +81,7 @@ __global__ void lbs_pose_kernel(HbLbsModel m, int N, int fpb, const float* __res
   lbs_chain_fwd(pose, J, m.parents, f ? f + LBS_NB : nullptr, A ? A + (size_t)n * 624 : nullptr, Jp);
   if (feat_hi && f) {                 // hi/lo operand planes (x = hi + lo) of the feature row for the tensor-core blend
     for (int k = 0; k < TC_KF; ++k) {
-      const float v = k < 205 ? f[k] : 0.f;
+      const float v = k < 205 ? f[k] : (k == 205 ? 1.f : 0.f);   // column 205 = 1: picks up the template row of the fused blend matrix
       const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       feat_hi[(size_t)n * TC_KF + k] = h;
       feat_lo[(size_t)n * TC_KF + k] = v - h;
@@ -172,9 +172,10 @@ lbs_pose_warp_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ roo
       }
       if (k < LBS_KF) f[k] = v;
       if (feat_hi) {
-        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float vp = k == 205 ? 1.f : v;               // column 205 = 1: picks up the template row of the fused blend matrix
+        const float h = __uint_as_float(__float_as_uint(vp) & 0xffffe000u);
         feat_hi[(size_t)n * TC_KF + k] = h;
-        feat_lo[(size_t)n * TC_KF + k] = v - h;
+        feat_lo[(size_t)n * TC_KF + k] = vp - h;
       }
     }
   }
@@ -661,6 +662,7 @@ __global__ void lbs_pose_bwd_kernel(HbLbsModel m, int N, int fpb, const float* _
 }
 
 static const bool g_thread_pose = (getenv("HB_LBS_THREAD") != nullptr);
+static const bool g_unfused = (getenv("HB_LBS_UNFUSED") != nullptr);
 static const size_t SKIN_FWD_SMEM = (size_t)SK_FT * LBS_KF * sizeof(float);
 static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + BW_FT * 624) * sizeof(float);
 
@@ -691,7 +693,16 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
                                                need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
                                                tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);
   HB_LAUNCH_CHECK(); ++nl;
-  if (tc) {
+  if (tc && m->fblend_hi && m->fw_idx && (m->fused_wk == 4 || m->fused_wk == 8) && !g_unfused) {
+    // one persistent tcgen05 kernel: blend GEMM + skinning + coalesced store (lbs_fused.cuh)
+    HB_CUDA(launch_lbs_fused(ws.feat_hi, ws.feat_lo, TC_KF, m->fblend_hi, m->fblend_lo, TC_KF, N, m->num_verts, m->fused_nct,
+                             m->fused_wk, m->fw_idx, m->fw_val, ws.A, trans, verts, st));
+    ++nl;
+    if (joints && njo == 73) {
+      lbs_gather_extra_kernel<<<cdiv(N * 21, 256), 256, 0, st>>>(*m, N, verts, joints);
+      HB_LAUNCH_CHECK(); ++nl;
+    }
+  } else if (tc) {
     GemmEpi ep;
     ep.bias = m->v_template; ep.gamma = ep.beta = nullptr; ep.xhat = ep.rstd = nullptr; ep.ldxh = 0; ep.Cch = 0; ep.gsize = 64;
     for (int f0 = 0; f0 < N; f0 += TC_SLAB) {

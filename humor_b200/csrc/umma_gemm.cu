@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include "umma_gemm.cuh"
 #include "umma_launch.cuh"
+#include "lbs_fused.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
@@ -95,6 +96,44 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
   }
 #undef HB_UMMA_CASE
   return cudaErrorInvalidValue;
+}
+
+template <int WK>
+static cudaError_t launch_fused_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                                  int K, const LbsFusedArgs& a, int grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(lbs_fused_kernel<WK>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  lbs_fused_kernel<WK><<<grid, 192, LF_SMEM, st>>>(a_hi, a_lo, b_hi, b_lo, K, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf, const float* bf_hi, const float* bf_lo, int K,
+                             int N, int num_verts, int nct, int wk, const int* fw_idx, const float* fw_val, const float* A,
+                             const float* trans, float* out, cudaStream_t st) {
+  if (!load_encode()) return cudaErrorNotSupported;
+  if (K % UM_BK || ldf % 4 || (wk != 4 && wk != 8) || nct * LF_VT < num_verts) return cudaErrorInvalidValue;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+  }
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  if (!make_map(&ta_hi, feat_hi, N, K, ldf, UM_BM) || !make_map(&ta_lo, feat_lo, N, K, ldf, UM_BM) ||
+      !make_map(&tb_hi, bf_hi, nct * 128, K, K, 128) || !make_map(&tb_lo, bf_lo, nct * 128, K, K, 128))
+    return cudaErrorInvalidValue;
+  LbsFusedArgs a;
+  a.N = N; a.num_verts = num_verts; a.nrt = cdiv(N, UM_BM); a.nct = nct;
+  a.fw_idx = fw_idx; a.fw_val = fw_val; a.A = A; a.trans = trans; a.out = out;
+  const int ntiles = a.nrt * a.nct;
+  const int grid = ntiles < sms ? ntiles : sms;
+  return wk == 4 ? launch_fused_t<4>(ta_hi, ta_lo, tb_hi, tb_lo, K, a, grid, st)
+                 : launch_fused_t<8>(ta_hi, ta_lo, tb_hi, tb_lo, K, a, grid, st);
 }
 
 __global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {

@@ -13,4 +13,8 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
 // hi = top 11 mantissa bits of x, lo = x - hi (exact); n elements
 cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 bool umma_available();
+// dense LBS forward, fused blend GEMM + skinning (lbs_fused.cuh); bf_* = blend matrix in 42-vertex tile order [nct*128][K]
+cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf, const float* bf_hi, const float* bf_lo, int K,
+                             int N, int num_verts, int nct, int wk, const int* fw_idx, const float* fw_val, const float* A,
+                             const float* trans, float* out, cudaStream_t st);
 }  // namespace hb

@@ -86,6 +86,13 @@ class MotionOptimizer():
                                         self.cam_center, robust_loss_type, robust_tuning_const,
                                         joints2d_sigma=joint2d_sigma, use_chamfer=use_chamfer).to(device)
         self.return_points3d = True      # dense vertices in every camera-frame SMPL evaluation (reference behaviour)
+        # Nothing in the Stage-III energy reads the dense vertices (they are an OUTPUT of the closure), so their LBS pass
+        # runs on a side stream under the latency-bound reverse decoder chain and is joined when the closure ends.
+        self.overlap_dense = True
+        self._dense_stream = None
+        self._capture_stream = None
+        self._dense_pending = False
+        self._defer_dense_join = False
         # multi-GPU: this process owns a contiguous block of the sub-sequences; the overlap energies that couple
         # the last sequence of rank r with the first of rank r+1 are exchanged as small halos (parallel.py)
         self.shard = None
@@ -109,9 +116,12 @@ class MotionOptimizer():
         ones) because smplx needs a fixed batch; rows are independent, so only the rows given are run."""
         B, T, _ = trans.size()
         njo = self.njo if njo is None else njo
+        side_dense = dense and self.overlap_dense and sel and trans.is_cuda
         v, vs, J = lbs(self.body_model.lbs_model, root_orient.reshape(B * T, 3), body_pose.reshape(B * T, 63), beta,
                        trans.reshape(B * T, 3), frames_per_beta=T, sel_ids=KEYPT_VERTS if sel else None,
-                       want_dense=dense, dense_grad=False, num_joints_out=njo)
+                       want_dense=dense and not side_dense, dense_grad=False, num_joints_out=njo)
+        if side_dense:
+            v = self._dense_on_side_stream(trans, root_orient, body_pose, beta)
         J = J.reshape(B, T, njo, 3)
         pred = {'Jtr': J, 'joints3d': J[:, :, :NUM_JOINTS], 'joints3d_extra': J[:, :, NUM_JOINTS:],
                 'faces': self.body_model.bm.faces_tensor}
@@ -120,6 +130,35 @@ class MotionOptimizer():
         if dense:
             pred['points3d'] = v.reshape(B, T, -1, 3)
         return pred, None
+
+    def _dense_on_side_stream(self, trans, root_orient, body_pose, beta):
+        """Dense vertices (no gradient) on a second stream with its own scratch; joined by ``join_dense``."""
+        B, T, _ = trans.size()
+        model = self.body_model.lbs_model
+        main = torch.cuda.current_stream()
+        if self._dense_stream is None:
+            self._dense_stream = torch.cuda.Stream(device=trans.device)
+        side = self._dense_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side), torch.no_grad():
+            model.ws_slot = 1
+            try:
+                v, _, _ = lbs(model, root_orient.detach().reshape(B * T, 3), body_pose.detach().reshape(B * T, 63), beta.detach(),
+                              trans.detach().reshape(B * T, 3), frames_per_beta=T, sel_ids=None, want_dense=True,
+                              dense_grad=False, num_joints_out=52)
+            finally:
+                model.ws_slot = 0
+        if not torch.cuda.is_current_stream_capturing():
+            v.record_stream(main)
+        self._dense_pending = True
+        if not self._defer_dense_join:
+            self.join_dense()
+        return v
+
+    def join_dense(self):
+        if self._dense_pending:
+            torch.cuda.current_stream().wait_stream(self._dense_stream)
+            self._dense_pending = False
 
     def joints_only(self, trans, root_orient, body_pose, beta):
         B, T, _ = trans.size()
@@ -302,8 +341,11 @@ class MotionOptimizer():
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             l0 = _ext.LaunchCounter.total
+            if self._capture_stream is None:
+                # high priority: the sequential decoder chain wins free SMs over the side-stream dense LBS pass
+                self._capture_stream = torch.cuda.Stream(priority=-1)
             try:
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=self._capture_stream):
                     static_loss = self._eval_into_static(observed_data, nsteps, init_motion_scale, params)
             except RuntimeError as e:       # e.g. an injected pose prior that syncs or copies from the host
                 import traceback
@@ -338,10 +380,13 @@ class MotionOptimizer():
                 alias_of[id(t)] = a
                 setattr(self, n, a)
         try:
+            self._defer_dense_join = True          # dense vertices overlap the reverse pass; joined below
             loss, _, _, _, _ = self.stage3_forward(observed_data, nsteps, scale)
             live = [p for p in params if p.requires_grad]
             grads = torch.autograd.grad(loss, [alias_of.get(id(p), p) for p in live], allow_unused=True)
         finally:
+            self._defer_dense_join = False
+            self.join_dense()
             for n, t in saved.items():
                 setattr(self, n, t)
         return loss.detach(), grads, live

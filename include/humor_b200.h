@@ -57,6 +57,15 @@ typedef struct HbLbsModel {
   const int* depth;        /* [52] */
   const int* child_start;  /* [53] */
   const int* child_list;   /* [51] */
+  /* fused dense forward (blend GEMM + skinning in one tcgen05 kernel): blend matrix in 42-vertex tile order,
+     row = tile*128 + half*64 + 3*i + d (i < 21; row 63 of each half is zero), K = 224 with column 205 = v_template,
+     split x = hi + lo; skinning weights padded to fused_wk (4 or 8) slots sorted by joint id, index = joint*12 */
+  const float* fblend_hi;  /* [fused_nct*128][224] */
+  const float* fblend_lo;
+  const int* fw_idx;       /* [num_verts][fused_wk] */
+  const float* fw_val;     /* [num_verts][fused_wk] */
+  int fused_nct;
+  int fused_wk;            /* 0: fused path unavailable */
 } HbLbsModel;
 
 /* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs

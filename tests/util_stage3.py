@@ -24,16 +24,17 @@ def project_joints2d(prob, cam_joints73, seed=5, noise=2.0):
     return prob
 
 
-def build_port(B, T, weights, optim_floor, prob, dtype=torch.float32):
+def build_port(B, T, weights, optim_floor, prob, dtype=torch.float32, device='cpu'):
     from oracle.stage3_port import Stage3Port
-    return Stage3Port(synth.make_smplh_asset(), synth.make_humor_state_dict(), synth.make_gmm(), synth.FakeVPoser().to(dtype),
-                      weights, B, T, optim_floor, prob['cam_mat'], dtype=dtype)
+    return Stage3Port(synth.make_smplh_asset(), synth.make_humor_state_dict(), synth.make_gmm(),
+                      synth.FakeVPoser().to(dtype).to(device), weights, B, T, optim_floor, prob['cam_mat'], dtype=dtype,
+                      device=device)
 
 
-def closure_port(port, prob, optim_floor, nsteps=None, scale=1.0):
+def closure_port(port, prob, optim_floor, nsteps=None, scale=1.0, device='cpu'):
     names = PARAM_NAMES + (['floor_plane'] if optim_floor else [])
-    p = {k: torch.as_tensor(prob['params'][k]).clone().requires_grad_(True) for k in names}
-    obs = {k: torch.as_tensor(v).clone() for k, v in prob['obs'].items() if k in obs_keys(optim_floor)}
+    p = {k: torch.as_tensor(prob['params'][k]).to(device).clone().requires_grad_(True) for k in names}
+    obs = {k: torch.as_tensor(v).to(device).clone() for k, v in prob['obs'].items() if k in obs_keys(optim_floor)}
     loss, stats, inter = port.closure(p, obs, nsteps, scale)
     loss.backward()
     return float(loss.detach()), {k: p[k].grad.detach() for k in names}, {'stats': {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in stats.items()}, 'inter': inter}

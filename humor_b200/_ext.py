@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libhumor_b200.so')
-SOURCES = ['rollout.cu', 'lbs.cu', 'rot.cu', 'losses.cu', 'umma_gemm.cu']
+SOURCES = ['rollout.cu', 'lbs.cu', 'rot.cu', 'losses.cu', 'umma_gemm.cu', 'chamfer.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -101,7 +101,7 @@ class HbFitArgs(C.Structure):
 EXPORTS = ['humor_lbs_workspace_bytes', 'humor_lbs_fwd', 'humor_lbs_bwd', 'humor_rollout_workspace_bytes',
            'humor_rollout_fwd', 'humor_rollout_bwd', 'humor_rodrigues_fwd', 'humor_rodrigues_bwd',
            'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version',
-           'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes']
+           'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd']
 
 _LIB = None
 
@@ -143,6 +143,10 @@ def lib():
     L.humor_umma_gemm_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.humor_umma_gemm.restype = ci
     L.humor_umma_gemm.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, vp, sz, vp]
+    L.humor_chamfer_fwd.restype = ci
+    L.humor_chamfer_fwd.argtypes = [ci, ci, vp, ci, vp, vp, vp, vp, vp, i64p, vp]
+    L.humor_chamfer_bwd.restype = ci
+    L.humor_chamfer_bwd.argtypes = [ci, ci, vp, ci, vp, vp, vp, vp, vp, vp, vp, i64p, vp]
     L.humor_b200_version.restype = C.c_char_p
     _LIB = L
     return L

@@ -11,6 +11,8 @@ import torch.nn as nn
 
 from . import _ext
 from ._ext import TERM, HB_NUM_TERMS
+from .chamfer import ChamferDistance
+from .fitting_utils import apply_robust_weighting_sq
 
 SMPL2OP = [52, 12, 17, 19, 21, 16, 18, 20, 0, 2, 5, 8, 1, 4, 7, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62]
 # reference weight key -> (term ids sharing it)
@@ -111,8 +113,9 @@ class FittingLoss(nn.Module):
     def __init__(self, loss_weights, init_motion_prior=None, smpl2op_map=None, ignore_op_joints=None, cam_f=None,
                  cam_cent=None, robust_loss='none', robust_tuning_const=4.6851, joints2d_sigma=100, use_chamfer=False):
         super().__init__()
-        if use_chamfer:
-            raise NotImplementedError("points3d / chamfer is the 'next' row of the scope table (SURVEY.md §8f)")
+        # fitting_loss.py:52-54: the point-cloud term needs the native nearest-neighbour module.  Only obs -> pred is
+        # consumed (fitting_loss.py:385-392), so the other direction of the search is skipped.
+        self.chamfer_dist = ChamferDistance(one_way=True) if use_chamfer else None
         if smpl2op_map is not None and list(smpl2op_map) != SMPL2OP:
             raise NotImplementedError('the fused kernel hard-wires the SMPL+H -> OpenPose BODY_25 map')
         self.all_stage_loss_weights = loss_weights
@@ -255,10 +258,28 @@ class FittingLoss(nn.Module):
             nll = _GmmFn.apply(self.gmm, x).sum()
             loss = loss + self.loss_weights['init_motion_prior'] * init_motion_scale * nll
             stats['init_motion_prior'] = nll
+        if 'points3d' in observed and pred.get('points3d') is not None and self.loss_weights.get('points3d', 0.0) > 0.0:
+            # fitting_loss.py:114-117 (every stage: root_fit / smpl_fit / motion_fit all go through it)
+            cur = self.points3d_loss(observed['points3d'][:, :T], pred['points3d'])
+            loss = loss + self.loss_weights['points3d'] * cur
+            stats['points3d'] = cur
         for name, i in TERM.items():
             if coef[i] != 0.0:
                 stats[name] = terms[i]
         return loss, stats
+
+    def points3d_loss(self, points3d_obs, points3d_pred):
+        """One-way chamfer of the observed cloud against the predicted vertices with robust (bisquare/MAD) weights
+        (fitting_loss.py:378-396).  Nearest neighbours + deterministic scatter gradient: csrc/chamfer.cu."""
+        if self.chamfer_dist is None:
+            raise RuntimeError('FittingLoss was built with use_chamfer=False but a points3d term is active')
+        B, T, N_obs, _ = points3d_obs.size()
+        obs = points3d_obs.reshape(B * T, N_obs, 3)
+        pred = points3d_pred.reshape(B * T, -1, 3)
+        obs2pred_sqr_dist, _ = self.chamfer_dist(obs, pred)
+        weighted, _ = apply_robust_weighting_sq(obs2pred_sqr_dist.reshape(B, T * N_obs), self.robust_loss,
+                                                self.robust_tuning_const)
+        return 0.5 * torch.sum(weighted)
 
     # reference-named entry points ------------------------------------------------------------------
     def root_fit(self, observed_data, pred_data):

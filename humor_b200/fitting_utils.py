@@ -44,3 +44,48 @@ def compute_cam2prior(floor_plane, trans, root_orient, joints):
     R = torch.stack([right, fwd, up], 1)           # rows = prior axes expressed in the camera frame
     _, s_root = compute_plane_intersection(joints[:, 0], -up, plane)
     return R, -trans, s_root[:, None]
+
+
+# ------------------------------------------------------------------------------------------------
+# robust weighting of the point-cloud residuals (fitting_utils.py:192-248)
+# ------------------------------------------------------------------------------------------------
+def robust_std(res):
+    """MAD / 0.67449 per row of res (B,N) (fitting_utils.py:213-228; torch.median = lower median)."""
+    B = res.size(0)
+    med = torch.median(res, dim=-1)[0].reshape((B, 1))
+    mad = torch.median(torch.abs(res - med), dim=-1)[0].reshape((B, 1))
+    return mad / 0.67449
+
+
+def bisquare_robust_weights(res, tune_const=4.6851):
+    """Tukey bisquare weights (fitting_utils.py:230-248).  `torch.where` instead of the reference's boolean-mask
+    assignment: same values, no host synchronisation (CUDA-graph capturable)."""
+    norm_res = res / (robust_std(res) * tune_const)
+    w = (1.0 - norm_res ** 2) ** 2
+    return torch.where(norm_res >= 1.0, torch.zeros_like(w), w)
+
+
+class _SqrtSquare(torch.autograd.Function):
+    """sqrt(d)**2 with the exact derivative 1.  The reference forms `obs2pred_sqr_dist.sqrt()` and squares it again
+    (fitting_loss.py:389-391, fitting_utils.py:210): autograd then gives 2*sqrt(d)*(1/(2*sqrt(d))), NaN at d == 0
+    (an observed point lying exactly on a vertex).  Forward value identical, gradient finite."""
+
+    @staticmethod
+    def forward(ctx, d):
+        r = torch.sqrt(d)
+        return r * r
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def apply_robust_weighting_sq(sqr_res, robust_loss_type='bisquare', robust_tuning_const=4.6851):
+    """apply_robust_weighting (fitting_utils.py:192-211) taking the SQUARED residuals the chamfer search returns:
+    (w * sqrt(d)**2, w), the weights detached exactly as in the reference."""
+    if robust_loss_type not in ('none', 'bisquare'):
+        raise ValueError('Not a valid robust loss: %s' % robust_loss_type)
+    with torch.no_grad():
+        res = torch.sqrt(sqr_res)
+        w = torch.ones_like(res) if robust_loss_type == 'none' else bisquare_robust_weights(res, robust_tuning_const)
+    return w * _SqrtSquare.apply(sqr_res), w

@@ -111,15 +111,21 @@ class MotionOptimizer():
     # ------------------------------------------------------------------------------------------------
     # SMPL
     # ------------------------------------------------------------------------------------------------
-    def smpl_results(self, trans, root_orient, body_pose, beta, dense=True, sel=True, njo=None):
+    def points3d_active(self, observed_data):
+        """True when the point-cloud energy is live (fitting_loss.py:114): the dense vertices then carry gradient."""
+        return 'points3d' in observed_data and self.fitting_loss.loss_weights.get('points3d', 0.0) > 0.0
+
+    def smpl_results(self, trans, root_orient, body_pose, beta, dense=True, sel=True, njo=None, dense_grad=False):
         """motion_optimizer.py:1065-1110.  The reference expands a T=1 state to T rows (and pads short
-        ones) because smplx needs a fixed batch; rows are independent, so only the rows given are run."""
+        ones) because smplx needs a fixed batch; rows are independent, so only the rows given are run.
+        ``dense_grad``: the dense vertices feed an energy (points3d), so they stay on the main stream inside autograd."""
         B, T, _ = trans.size()
         njo = self.njo if njo is None else njo
-        side_dense = dense and self.overlap_dense and sel and trans.is_cuda
+        dense = dense or dense_grad
+        side_dense = dense and not dense_grad and self.overlap_dense and sel and trans.is_cuda
         v, vs, J = lbs(self.body_model.lbs_model, root_orient.reshape(B * T, 3), body_pose.reshape(B * T, 63), beta,
                        trans.reshape(B * T, 3), frames_per_beta=T, sel_ids=KEYPT_VERTS if sel else None,
-                       want_dense=dense and not side_dense, dense_grad=False, num_joints_out=njo)
+                       want_dense=dense and not side_dense, dense_grad=dense_grad, num_joints_out=njo)
         if side_dense:
             v = self._dense_on_side_stream(trans, root_orient, body_pose, beta)
         J = J.reshape(B, T, njo, 3)
@@ -275,11 +281,11 @@ class MotionOptimizer():
         if self.optim_floor:
             prior_joints = self.joints_only(roll['trans'], roll['root_orient'], roll['pose_body'], self.betas)
             cam_pred, _ = self.smpl_results(cam['trans'], cam['root_orient'], roll['pose_body'], self.betas,
-                                            dense=self.return_points3d)
+                                            dense=self.return_points3d, dense_grad=self.points3d_active(observed_data))
             cam_pred['floor_plane'] = self.floor_plane
         else:
             cam_pred, _ = self.smpl_results(roll['trans'], roll['root_orient'], roll['pose_body'], self.betas,
-                                            dense=self.return_points3d)
+                                            dense=self.return_points3d, dense_grad=self.points3d_active(observed_data))
             prior_joints = cam_pred['joints3d']
         cam_pred['betas'] = self.betas
         cam_pred['latent_pose'] = cur_latent_pose
@@ -514,7 +520,8 @@ class MotionOptimizer():
             def closure():
                 optim.zero_grad()
                 body_pose = self.latent2pose(self.latent_pose)
-                pred, _ = self.smpl_results(self.trans, self.root_orient, body_pose, self.betas, dense=False)
+                pred, _ = self.smpl_results(self.trans, self.root_orient, body_pose, self.betas, dense=False,
+                                            dense_grad=self.points3d_active(observed_data))
                 pred['betas'] = self.betas
                 if full:
                     pred['latent_pose'] = self.latent_pose

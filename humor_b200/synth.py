@@ -304,3 +304,24 @@ AMASS_STAGE3_WEIGHTS = {
     'joint_consistency': 1.0, 'bone_length': 10.0, 'joints3d_smooth': 0.0,
     'contact_vel': 1.0, 'contact_height': 1.0, 'floor_reg': 0.0, 'rgb_overlap_consist': 0.0,
 }
+# stage-3 column of configs/fit_proxd.cfg (PROX RGB-D: point cloud + 2-D keypoints, floor optimised)
+PROXD_STAGE3_WEIGHTS = {
+    'joints2d': 0.001, 'joints3d': 0.0, 'joints3d_rollout': 0.0, 'verts3d': 0.0, 'points3d': 1.0,
+    'pose_prior': 0.0, 'shape_prior': 0.034, 'motion_prior': 0.075, 'init_motion_prior': 0.075,
+    'joint_consistency': 100.0, 'bone_length': 2000.0, 'joints3d_smooth': 0.0,
+    'contact_vel': 100.0, 'contact_height': 10.0, 'floor_reg': 1.0, 'rgb_overlap_consist': 0.0,
+}
+WEIGHT_SETS = {'rgb': RGB_STAGE3_WEIGHTS, 'amass': AMASS_STAGE3_WEIGHTS, 'proxd': PROXD_STAGE3_WEIGHTS}
+
+
+def sample_point_cloud(verts, n_obs, seed=0, noise=0.01, outlier_frac=0.05, outlier_sigma=0.6):
+    """Synthetic depth-camera cloud for the points3d energy: n_obs points per frame drawn from the given vertices
+    (B,T,V,3) with Gaussian noise, a fraction of them pushed far away (what the bisquare weights must reject)."""
+    v = np.asarray(verts)
+    B, T, V, _ = v.shape
+    rng = np.random.RandomState(seed)
+    ids = rng.randint(0, V, size=(B, T, n_obs))
+    pts = np.take_along_axis(v, ids[..., None], axis=2) + rng.randn(B, T, n_obs, 3) * noise
+    out = rng.rand(B, T, n_obs) < outlier_frac
+    pts = pts + out[..., None] * rng.randn(B, T, n_obs, 3) * outlier_sigma
+    return pts.astype(v.dtype)

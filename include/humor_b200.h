@@ -208,6 +208,28 @@ size_t humor_umma_gemm_workspace_bytes(int M, int N, int lda, int ldb);
 int humor_umma_gemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,
                     int K, float* workspace, size_t workspace_bytes, hb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer nearest-neighbour search — the reference's only native module.  Replaces
+ * cd.forward_cuda / cd.backward_cuda (humor/utils/chamfer_distance/chamfer_distance.cpp:26-55,180-185;
+ * kernels chamfer_distance.cu:7-209), called by ChamferDistanceFunction (chamfer_distance.py:13-55) for
+ * FittingLoss.points3d_loss (humor/fitting/fitting_loss.py:378-396).
+ *   b clouds; xyz1 [b][n][3], xyz2 [b][m][3] (fp32, contiguous)
+ *   dist1 [b][n], idx1 [b][n] (int32): squared distance to / index of the nearest point of xyz2, first minimum wins;
+ *   dist2 [b][m], idx2 [b][m]: the other direction.  Passing dist2 == idx2 == NULL (or dist1 == idx1 == NULL)
+ *   skips that direction (points3d_loss consumes only dist1).
+ * Arithmetic and tie-breaking are those of the reference's CPU path (nnsearch, chamfer_distance.cpp:58-87):
+ * results are bit-identical to it.  Unlike the reference (printf-only errors, chamfer_distance.cu:155-157)
+ * launch failures are returned. */
+int humor_chamfer_fwd(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1,
+                      float* dist2, int* idx2, int64_t* launches, hb_stream_t stream);
+/* Reverse mode (chamfer_distance.cpp:114-177): grad_dist1 [b][n] / grad_dist2 [b][m] (NULL: that direction carries no
+ * gradient) -> grad_xyz1 [b][n][3], grad_xyz2 [b][m][3] (either may be NULL; both are overwritten, not accumulated).
+ * Deterministic: one owner thread per destination point applies the contributions in the reference's CPU loop
+ * order (the reference's CUDA path uses atomicAdd, chamfer_distance.cu:166-185). */
+int humor_chamfer_bwd(int b, int n, const float* xyz1, int m, const float* xyz2, const float* grad_dist1,
+                      const int* idx1, const float* grad_dist2, const int* idx2, float* grad_xyz1, float* grad_xyz2,
+                      int64_t* launches, hb_stream_t stream);
+
 const char* humor_b200_version(void);
 
 #ifdef __cplusplus

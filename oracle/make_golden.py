@@ -24,14 +24,17 @@ CASES = {
     'stage3_rgb_phase1': dict(optim_floor=True, B=4, T=8, seed=22, overlap=3, nsteps=4, scale=1.0),
     'stage3_rgb_refine': dict(optim_floor=True, B=2, T=7, seed=23, overlap=2, nsteps=None, scale=7.0 / 4.0),
     'stage3_amass': dict(optim_floor=False, B=2, T=6, seed=24, overlap=2, nsteps=None, scale=1.0),
+    # PROX RGB-D (configs/fit_proxd.cfg): point-cloud energy through the reference's compiled chamfer module
+    'stage3_proxd': dict(optim_floor=True, B=2, T=6, seed=25, overlap=2, nsteps=None, scale=1.0, wset='proxd', n_obs=96),
 }
 SMPL2OP = [52, 12, 17, 19, 21, 16, 18, 20, 0, 2, 5, 8, 1, 4, 7, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62]
 
 
 def run_case(c):
-    W = synth.RGB_STAGE3_WEIGHTS if c['optim_floor'] else synth.AMASS_STAGE3_WEIGHTS
+    W = synth.WEIGHT_SETS[c['wset']] if 'wset' in c else (synth.RGB_STAGE3_WEIGHTS if c['optim_floor'] else synth.AMASS_STAGE3_WEIGHTS)
     prob = synth.make_stage3_problem(c['B'], c['T'], seed=c['seed'], overlap=c['overlap'], cam=c['optim_floor'])
     keys = ('joints2d', 'floor_plane', 'seq_interval') if c['optim_floor'] else ('verts3d',)
+    pts = W.get('points3d', 0.0) > 0.0
     ref, mo, _, _ = ref_closure.build(c['B'], c['T'], W, c['optim_floor'], prob['cam_mat'] if c['optim_floor'] else None)
     obs = {k: torch.as_tensor(prob['obs'][k]) for k in keys}
     if c['optim_floor']:
@@ -43,6 +46,10 @@ def run_case(c):
         xy = j[..., :2] / j[..., 2:3] * np.asarray(synth.CAM_F) + np.asarray(synth.CAM_C) + rng.randn(*j.shape[:3], 2) * 2.0
         obs['joints2d'] = obs['joints2d'].clone()
         obs['joints2d'][..., :2] = torch.as_tensor(xy.astype(np.float32))
+        if pts:
+            obs['points3d'] = torch.as_tensor(synth.sample_point_cloud(inter['cam_pred']['points3d'].numpy(), c['n_obs'],
+                                                                        seed=c['seed'] + 200))
+            keys = keys + ('points3d',)
     names = ref_closure.set_params(mo, prob['params'])
     loss, stats, inter = ref_closure.stage3_closure(ref, mo, {k: v.clone() for k, v in obs.items()}, c['nsteps'], c['scale'])
     out = {'loss': np.float32(loss.item())}
@@ -60,13 +67,19 @@ def run_case(c):
     out['cond_prior_var'] = inter['rollout']['cond_prior'][1].detach().numpy()
     out['meta'] = np.array([c['B'], c['T'], c['seed'], c['overlap'], -1 if c['nsteps'] is None else c['nsteps'], int(c['optim_floor'])])
     out['scale'] = np.float32(c['scale'])
+    if 'wset' in c:
+        out['wset'] = np.array(c['wset'])
     return out
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    import sys
+    only = sys.argv[1:]
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         out = run_case(c)
         np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
         print(name, 'loss', out['loss'], {k[5:]: float(v) for k, v in out.items() if k.startswith('stat_')})

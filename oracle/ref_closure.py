@@ -30,6 +30,44 @@ def asset_npz(seed=0):
     return _ASSET_PATH[seed]
 
 
+class _RefChamferFn(torch.autograd.Function):
+    """The CPU branch of the reference's ChamferDistanceFunction (utils/chamfer_distance/chamfer_distance.py:13-55)
+    driving the reference's own compiled C++ (oracle/_ref/cd_ref.so, oracle/build_ref.py).  The reference's Python
+    wrapper cannot be imported as is: it JIT-builds the .cpp AND the .cu at import (chamfer_distance.py:10)."""
+
+    @staticmethod
+    def forward(ctx, cd, xyz1, xyz2):
+        b, n, _ = xyz1.size()
+        m = xyz2.size(1)
+        xyz1, xyz2 = xyz1.contiguous(), xyz2.contiguous()
+        dist1, dist2 = torch.zeros(b, n), torch.zeros(b, m)
+        idx1, idx2 = torch.zeros(b, n, dtype=torch.int), torch.zeros(b, m, dtype=torch.int)
+        cd.forward(xyz1, xyz2, dist1, dist2, idx1, idx2)
+        ctx.cd = cd
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        return dist1, dist2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        gx1, gx2 = torch.zeros(xyz1.size()), torch.zeros(xyz2.size())
+        ctx.cd.backward(xyz1, xyz2, gx1, gx2, g1.contiguous(), g2.contiguous(), idx1, idx2)
+        return None, gx1, gx2
+
+
+class RefChamfer(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        from oracle.build_ref import build as build_cd, load_cd_ref
+        build_cd()
+        self.cd = load_cd_ref()
+        if self.cd is None:
+            raise RuntimeError('reference chamfer module could not be built (oracle/build_ref.py)')
+
+    def forward(self, xyz1, xyz2):
+        return _RefChamferFn.apply(self.cd, xyz1.detach() if not xyz1.requires_grad else xyz1, xyz2)
+
+
 def build(B, T, weights, optim_floor, cam_mat=None, humor_sd=None, gmm=None, vposer=None,
           stage3_contact_refine_only=True):
     """Reference BodyModel + HumorModel + MotionOptimizer on CPU with synthetic assets."""
@@ -54,6 +92,9 @@ def build(B, T, weights, optim_floor, cam_mat=None, humor_sd=None, gmm=None, vpo
         None if cam_mat is None else torch.as_tensor(cam_mat),
         'bisquare', 4.6851, 100.0,
         stage3_contact_refine_only=stage3_contact_refine_only)
+    if w.get('points3d', 0.0) > 0.0:
+        # what FittingLoss(use_chamfer=True) sets up (fitting_loss.py:52-54), minus the import-time JIT build
+        mo.fitting_loss.chamfer_dist = RefChamfer()
     mo.fitting_loss.set_stage(2)
     return ref, mo, bm, humor
 

@@ -212,6 +212,7 @@ class Stage3Port:
         self.w = dict(weights)
         self.B, self.T, self.optim_floor = B, T, optim_floor
         self.sigma = joints2d_sigma
+        self.robust_loss, self.robust_tuning_const = 'bisquare', 4.6851
         gw, gm, gc = [g.to(dtype=dtype, device=device) for g in gmm]
         self.gmm_logw = torch.log(gw / gw.sum())
         self.gmm_mean = gm
@@ -326,6 +327,11 @@ class Stage3Port:
         if 'verts3d' in obs and w['verts3d'] > 0:
             st['verts3d'] = self._l2_vis(obs['verts3d'], cam_pred['verts3d'])
             loss = loss + w['verts3d'] * st['verts3d']
+        if 'points3d' in obs and w.get('points3d', 0.0) > 0:
+            # fitting_loss.py:114-117,378-396 (restated in oracle/chamfer.py; robust settings of run_fitting.py:398-399)
+            from oracle.chamfer import points3d_loss
+            st['points3d'] = points3d_loss(obs['points3d'], cam_pred['points3d'], self.robust_loss, self.robust_tuning_const)
+            loss = loss + w['points3d'] * st['points3d']
         if 'joints2d' in obs and w['joints2d'] > 0:
             st['joints2d'] = self.joints2d_loss(obs['joints2d'], cam_pred['joints3d'], cam_pred['joints3d_extra'])
             loss = loss + w['joints2d'] * st['joints2d']

@@ -3,7 +3,7 @@ import numpy as np
 from humor_b200 import synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass']
+CASES = ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass', 'stage3_proxd']
 
 
 def load_case(name):
@@ -11,10 +11,12 @@ def load_case(name):
     B, T, seed, overlap, nsteps, of = [int(x) for x in g['meta']]
     optim_floor = bool(of)
     prob = synth.make_stage3_problem(B, T, seed=seed, overlap=overlap, cam=optim_floor)
-    for k in list(prob['obs'].keys()):
-        if 'obs_' + k in g:
-            prob['obs'][k] = g['obs_' + k]
+    for k in g:
+        if k.startswith('obs_'):
+            prob['obs'][k[4:]] = g[k]
     W = synth.RGB_STAGE3_WEIGHTS if optim_floor else synth.AMASS_STAGE3_WEIGHTS
+    if 'wset' in g:
+        W = synth.WEIGHT_SETS[str(g['wset'])]
     return g, prob, dict(B=B, T=T, optim_floor=optim_floor, nsteps=None if nsteps < 0 else nsteps, scale=float(g['scale']), W=W)
 
 

@@ -8,8 +8,11 @@ from humor_b200 import synth
 PARAM_NAMES = ['trans', 'root_orient', 'latent_pose', 'betas', 'latent_motion', 'trans_vel', 'joints_vel', 'root_orient_vel']
 
 
-def obs_keys(optim_floor):
-    return ('joints2d', 'floor_plane', 'seq_interval') if optim_floor else ('verts3d',)
+def obs_keys(optim_floor, prob=None):
+    keys = ('joints2d', 'floor_plane', 'seq_interval') if optim_floor else ('verts3d',)
+    if prob is not None and 'points3d' in prob['obs']:
+        keys = keys + ('points3d',)          # PROX RGB-D style problems (golden case stage3_proxd)
+    return keys
 
 
 def project_joints2d(prob, cam_joints73, seed=5, noise=2.0):
@@ -34,7 +37,7 @@ def build_port(B, T, weights, optim_floor, prob, dtype=torch.float32, device='cp
 def closure_port(port, prob, optim_floor, nsteps=None, scale=1.0, device='cpu'):
     names = PARAM_NAMES + (['floor_plane'] if optim_floor else [])
     p = {k: torch.as_tensor(prob['params'][k]).to(device).clone().requires_grad_(True) for k in names}
-    obs = {k: torch.as_tensor(v).to(device).clone() for k, v in prob['obs'].items() if k in obs_keys(optim_floor)}
+    obs = {k: torch.as_tensor(v).to(device).clone() for k, v in prob['obs'].items() if k in obs_keys(optim_floor, prob)}
     loss, stats, inter = port.closure(p, obs, nsteps, scale)
     loss.backward()
     return float(loss.detach()), {k: p[k].grad.detach() for k in names}, {'stats': {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in stats.items()}, 'inter': inter}
@@ -51,16 +54,17 @@ def build_product(B, T, weights, optim_floor, prob, device='cuda', contact_refin
     humor.to(dev).eval()
     gmm = tuple(g.to(dev) for g in synth.make_gmm())
     w = dict(weights)
-    mo = MotionOptimizer(dev, bm, 16, B, T, list(obs_keys(optim_floor)), [dict(w), dict(w), dict(w)],
+    mo = MotionOptimizer(dev, bm, 16, B, T, list(obs_keys(optim_floor, prob)), [dict(w), dict(w), dict(w)],
                          synth.FakeVPoser().to(dev), humor, {'gmm': gmm}, optim_floor,
                          torch.as_tensor(prob['cam_mat']).to(dev) if optim_floor else None, 'bisquare', 4.6851, 100.0,
-                         stage3_contact_refine_only=contact_refine_only)
+                         stage3_contact_refine_only=contact_refine_only,
+                         use_chamfer='points3d' in prob['obs'])      # run_fitting.py:405
     return mo
 
 
 def closure_product(mo, prob, nsteps=None, scale=1.0):
     names = mo.set_stage3_state(prob['params'])
-    obs = {k: torch.as_tensor(v).to(mo.device) for k, v in prob['obs'].items() if k in obs_keys(mo.optim_floor)}
+    obs = {k: torch.as_tensor(v).to(mo.device) for k, v in prob['obs'].items() if k in obs_keys(mo.optim_floor, prob)}
     loss, stats, roll, cam, cam_pred = mo.stage3_forward(obs, nsteps, scale)
     loss.backward()
     grads = {n: getattr(mo, n).grad.detach() for n in names}

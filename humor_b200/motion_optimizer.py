@@ -97,6 +97,8 @@ class MotionOptimizer():
         # the last sequence of rank r with the first of rank r+1 are exchanged as small halos (parallel.py)
         self.shard = None
         # CUDA-graph capture of the Stage-III closure (forward + backward): one replay per L-BFGS evaluation
+        import os
+        self.lbfgs_impl = os.environ.get('HB_LBFGS', 'torch')    # 'torch' | 'native' (humor_b200.lbfgs); sharded runs use native
         self.use_cuda_graph = True       # falls back to eager launches (with a warning) if the closure cannot be captured
         self._graphs = {}
         self._contact_idx = torch.tensor(CONTACT_INDS, dtype=torch.long, device=device)
@@ -301,15 +303,7 @@ class MotionOptimizer():
             self.fitting_loss.loss_weights['rgb_overlap_consist'] = 0.0
         loss, stats = self.fitting_loss.motion_fit(loss_obs, pred, cam_pred, loss_nsteps,
                                                    init_motion_scale=init_motion_scale)
-        if self.shard is not None and self.shard.world > 1 and 'seq_interval' in loss_obs \
-                and self.fitting_loss.loss_weights['rgb_overlap_consist'] > 0.0:
-            from .parallel import boundary_overlap_energy
-            e, bstats = boundary_overlap_energy(self.shard, cam_pred['verts3d'], self.betas,
-                                                self.floor_plane if self.optim_floor else None,
-                                                loss_obs['seq_interval'], self.seq_len)
-            loss = loss + self.fitting_loss.loss_weights['rgb_overlap_consist'] * e
-            for k, v in bstats.items():
-                stats[k] = stats[k] + v if k in stats else v
+        loss, stats = self._boundary_energy(loss, stats, cam_pred['verts3d'], loss_obs)
         self.fitting_loss.loss_weights['rgb_overlap_consist'] = saved_ov
         return loss, stats, roll, cam, cam_pred
 
@@ -502,7 +496,32 @@ class MotionOptimizer():
     # the three stages
     # ------------------------------------------------------------------------------------------------
     def _lbfgs(self, params, lr, max_iter):
+        """motion_optimizer.py:228-231,281-284,461-478.  One process: the library optimiser the reference uses (or, with
+        ``lbfgs_impl = 'native'`` / HB_LBFGS=native, humor_b200.lbfgs with one packed host read per evaluation).  Sharded
+        over ranks: the JOINT L-BFGS of the reference (one step length and curvature history for all sub-sequences,
+        SURVEY.md 8e) needs global inner products, which only humor_b200.lbfgs provides."""
+        sharded = self.shard is not None and self.shard.world > 1
+        if sharded or self.lbfgs_impl == 'native':
+            from .lbfgs import LBFGS
+            group = (self.shard.group if self.shard.group is not None else True) if sharded else None
+            return LBFGS(params, max_iter=max_iter, lr=lr, line_search_fn=LINE_SEARCH, group=group)
         return torch.optim.LBFGS(params, max_iter=max_iter, lr=lr, line_search_fn=LINE_SEARCH)
+
+    def _boundary_energy(self, loss, stats, verts3d, observed_data, mode='motion'):
+        """Overlap-consistency energy across the rank boundary (parallel.py) — added on the receiving rank only.
+        Terms per stage as in the reference: root_fit key vertices (fitting_loss.py:136-157), smpl_fit + betas (:211-215),
+        motion_fit + floor (:296-300)."""
+        if self.shard is None or self.shard.world <= 1 or 'seq_interval' not in observed_data \
+                or self.fitting_loss.loss_weights['rgb_overlap_consist'] <= 0.0:
+            return loss, stats
+        from .parallel import boundary_overlap_energy
+        e, bstats = boundary_overlap_energy(self.shard, verts3d, self.betas,
+                                            self.floor_plane if (self.optim_floor and mode == 'motion') else None,
+                                            observed_data['seq_interval'], self.seq_len, with_betas=mode != 'root')
+        loss = loss + self.fitting_loss.loss_weights['rgb_overlap_consist'] * e
+        for k, v in bstats.items():
+            stats[k] = stats[k] + v if k in stats else v
+        return loss, stats
 
     def _stage12(self, observed_data, stage, num_iter, lr, lbfgs_max_iter):
         """Stage I (root only) / Stage II (pose + shape): motion_optimizer.py:224-306."""
@@ -525,9 +544,11 @@ class MotionOptimizer():
                 pred['betas'] = self.betas
                 if full:
                     pred['latent_pose'] = self.latent_pose
-                    loss, _ = self.fitting_loss.smpl_fit(observed_data, pred, self.seq_len)
+                    loss, st = self.fitting_loss.smpl_fit(observed_data, pred, self.seq_len)
+                    loss, _ = self._boundary_energy(loss, st, pred['verts3d'], observed_data, 'smpl')
                 else:
-                    loss, _ = self.fitting_loss.root_fit(observed_data, pred)
+                    loss, st = self.fitting_loss.root_fit(observed_data, pred)
+                    loss, _ = self._boundary_energy(loss, st, pred['verts3d'], observed_data, 'root')
                 loss.backward()
                 return loss
             optim.step(closure)

@@ -72,7 +72,7 @@ def tail_pack(shard, verts3d, betas, floor, T):
     return torch.cat([v, betas[-1, :16], f])
 
 
-def boundary_overlap_energy(shard, verts3d, betas, floor, seq_interval, T):
+def boundary_overlap_energy(shard, verts3d, betas, floor, seq_interval, T, with_betas=True):
     """Overlap-consistency energy between this rank's FIRST sequence and the previous rank's LAST one
     (unweighted; same formulas as fitting_loss.py:142-157,211-215,296-300).  The overlap length with the previous
     rank comes from Shard.prepare (host, once); nothing here synchronises with the host."""
@@ -94,10 +94,12 @@ def boundary_overlap_energy(shard, verts3d, betas, floor, seq_interval, T):
     d = a - c
     pos = 0.5 * (d ** 2).sum()
     vel = 0.5 * ((d[1:] - d[:-1]) ** 2).sum() if ov > 1 else zero
-    bet = 0.5 * ((prev[ov_max * 129:ov_max * 129 + 16] - betas[0, :16]) ** 2).sum()
-    e = pos + vel + bet
-    stats = {'rgb_overlap_consist_verts3d_pos': pos.detach(), 'rgb_overlap_consist_verts3d_vel': vel.detach() if ov > 1 else zero.detach(),
-             'rgb_overlap_consist_betas': bet.detach()}
+    e = pos + vel
+    stats = {'rgb_overlap_consist_verts3d_pos': pos.detach(), 'rgb_overlap_consist_verts3d_vel': vel.detach() if ov > 1 else zero.detach()}
+    if with_betas:             # Stage I (root_fit) couples the key vertices only (fitting_loss.py:136-157 vs :211-215)
+        bet = 0.5 * ((prev[ov_max * 129:ov_max * 129 + 16] - betas[0, :16]) ** 2).sum()
+        e = e + bet
+        stats['rgb_overlap_consist_betas'] = bet.detach()
     if floor is not None:
         fl = 0.5 * ((prev[ov_max * 129 + 16:ov_max * 129 + 19] - floor[0]) ** 2).sum()
         e = e + fl

@@ -119,7 +119,7 @@ def run_product(args):
         dist.init_process_group('nccl')
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
-    _ext.lib()
+    _ext.check(_ext.lib().humor_lbs_configure(args.lbs_skin, args.lbs_blend, args.lbs_slab), 'humor_lbs_configure')
     B, T = args.batch, args.seq_len
     prob = build_problem(B, T, seed=4 + rank)
     mo = make_optimizer(B, T, prob, dev)
@@ -209,6 +209,8 @@ def run_product(args):
     hbm_peak, _, peak_kind = load_peaks()
     graphed = bool(mo.use_cuda_graph)
     roof = lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind)
+    roof['forms'] = {'skin': args.lbs_skin or int(os.environ.get('HB_LBS_SKIN', 1)), 'blend': args.lbs_blend or int(os.environ.get('HB_LBS_BLEND', 1)),
+                     'slab_frames': args.lbs_slab or int(os.environ.get('HB_LBS_SLAB', 512))}
     shares = kernel_shares(mo, obs, params, dev)
     cpu = cpu_baseline(args) if not args.no_cpu_baseline else None
     out = {
@@ -392,6 +394,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='tensor', choices=['tensor', 'exact'],
                     help="'tensor': GEMMs on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels (gradient-exact parity mode)")
+    ap.add_argument('--lbs-skin', type=int, default=0, help='dense LBS skinning pass form (humor_lbs_configure): 1 lane=vertex, 2 lane=frame')
+    ap.add_argument('--lbs-blend', type=int, default=0, help='dense LBS blend GEMM form: 1 tile per CTA, 2 persistent 128x256 tiles')
+    ap.add_argument('--lbs-slab', type=int, default=0, help='frames per v_posed slab (128..512)')
     ap.add_argument('--no-graph', action='store_true', help='evaluate the closure eagerly instead of replaying a CUDA graph')
     ap.add_argument('--port-cuda', default='', help='comma list of batch sizes: time the oracle port as eager PyTorch on cuda:0')
     ap.add_argument('--_cpu-child', dest='cpu_child', action='store_true', help=argparse.SUPPRESS)

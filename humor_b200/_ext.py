@@ -69,7 +69,9 @@ class HbLbsModel(C.Structure):
                 ('blend_t_hi', C.c_void_p), ('blend_t_lo', C.c_void_p), ('use_umma', C.c_int), ('max_depth', C.c_int),
                 ('depth', C.c_void_p), ('child_start', C.c_void_p), ('child_list', C.c_void_p),
                 ('fblend_hi', C.c_void_p), ('fblend_lo', C.c_void_p), ('fw_idx', C.c_void_p), ('fw_val', C.c_void_p),
-                ('fused_nct', C.c_int), ('fused_wk', C.c_int)]
+                ('fused_nct', C.c_int), ('fused_wk', C.c_int),
+                ('g_start', C.c_void_p), ('g_joint', C.c_void_p), ('g_w', C.c_void_p), ('num_groups', C.c_int),
+                ('reserved2', C.c_int)]
 
 
 class HbHumorWeights(C.Structure):
@@ -101,7 +103,7 @@ class HbFitArgs(C.Structure):
 EXPORTS = ['humor_lbs_workspace_bytes', 'humor_lbs_fwd', 'humor_lbs_bwd', 'humor_rollout_workspace_bytes',
            'humor_rollout_fwd', 'humor_rollout_bwd', 'humor_rodrigues_fwd', 'humor_rodrigues_bwd',
            'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version',
-           'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd']
+           'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd', 'humor_lbs_configure']
 
 _LIB = None
 
@@ -143,6 +145,8 @@ def lib():
     L.humor_umma_gemm_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.humor_umma_gemm.restype = ci
     L.humor_umma_gemm.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, vp, sz, vp]
+    L.humor_lbs_configure.restype = ci
+    L.humor_lbs_configure.argtypes = [ci, ci, ci]
     L.humor_chamfer_fwd.restype = ci
     L.humor_chamfer_fwd.argtypes = [ci, ci, vp, ci, vp, vp, vp, vp, vp, i64p, vp]
     L.humor_chamfer_bwd.restype = ci

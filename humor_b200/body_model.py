@@ -89,7 +89,25 @@ def pack_smplh(asset, num_betas=16):
         o2 = np.argsort(key, axis=1, kind='stable')
         fw_idx[:, :wk] = np.take_along_axis(w_idx, o2, axis=1) * 12
         fw_val[:, :wk] = np.take_along_axis(w_val, o2, axis=1)
+    # lane = frame skinning pass: groups of 8 consecutive vertices -> union of their joints + per-joint weight rows
+    G = 8
+    ng = (V + G - 1) // G
+    Wf = W.astype(np.float32)
+    g_start = np.zeros(ng + 1, np.int32)
+    g_joint, g_w = [], []
+    for g in range(ng):
+        blk = Wf[g * G:(g + 1) * G]                                           # (<=8, 52)
+        js = np.nonzero((blk != 0).any(0))[0]
+        for j in js:
+            row = np.zeros(G, np.float32)
+            row[:blk.shape[0]] = blk[:, j]
+            g_joint.append(j * 12)
+            g_w.append(row)
+        g_start[g + 1] = len(g_joint)
+    g_joint = np.asarray(g_joint, np.int32)
+    g_w = np.stack(g_w, 0) if g_w else np.zeros((1, G), np.float32)
     return {
+        'g_start': g_start, 'g_joint': g_joint, 'g_w': np.ascontiguousarray(g_w), 'num_groups': ng,
         'fblend': fb, 'fw_idx': fw_idx, 'fw_val': fw_val, 'fused_nct': nct, 'fused_wk': fwk,
         'depth': depth, 'child_start': child_start, 'child_list': child_list, 'max_depth': int(depth.max()),
         'num_verts': V, 'v3_ld': v3_ld, 'wk': wk,
@@ -130,6 +148,8 @@ class LbsModel:
         # do not share joints ("fused dense LBS: measured and parked"): opt-in only.
         self.fused_wk = packed['fused_wk']
         s.fused_nct, s.fused_wk = packed['fused_nct'], (packed['fused_wk'] if os.environ.get('HB_LBS_FUSED') else 0)
+        s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
+        s.num_groups = packed['num_groups']
         self.ws_slot = 0
         s.max_depth = packed['max_depth']
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))

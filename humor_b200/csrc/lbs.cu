@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "lbs_chain.cuh"
 #include "umma_launch.cuh"
+#include "lbs_skin_group.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
@@ -27,7 +28,8 @@ constexpr int SK_FPT = 16;   // frames per thread (forward)
 constexpr int BW_FT = 16;    // frames per block (backward)
 
 constexpr int TC_SLAB = 512;     // frames per tensor-core slab: v_posed slab (512 x 20736 fp32 = 42 MB) stays in L2
-constexpr int TC_KF = 224;       // feature K padded to a multiple of 32 for the TMA/UMMA tiles
+constexpr int TC_KF = 224;
+constexpr int LB_BN_HOST = 256;   // column tile of the persistent blend kernel (lbs_blend.cuh)       // feature K padded to a multiple of 32 for the TMA/UMMA tiles
 
 struct LbsWs {
   float *feat, *A, *dfeat, *dA, *dtr, *feat_hi, *feat_lo, *vposed;
@@ -663,12 +665,28 @@ __global__ void lbs_pose_bwd_kernel(HbLbsModel m, int N, int fpb, const float* _
 
 static const bool g_thread_pose = (getenv("HB_LBS_THREAD") != nullptr);
 static const bool g_unfused = (getenv("HB_LBS_UNFUSED") != nullptr);
+// dense skinning pass: 1 = lane-per-vertex (lbs_skin_apply_kernel), 2 = lane-per-frame over vertex groups (lbs_skin_group.cuh)
+static int g_skin_form = getenv("HB_LBS_SKIN") ? atoi(getenv("HB_LBS_SKIN")) : 1;
+static int g_sm_count = 0;
+// blend GEMM of the dense forward: 1 = one 128x128 tile per CTA (umma_gemm3_kernel), 2 = persistent 128x256 tiles (lbs_blend.cuh)
+static int g_blend_form = getenv("HB_LBS_BLEND") ? atoi(getenv("HB_LBS_BLEND")) : 1;
+static int g_slab = getenv("HB_LBS_SLAB") ? atoi(getenv("HB_LBS_SLAB")) : 0;
 static const size_t SKIN_FWD_SMEM = (size_t)SK_FT * LBS_KF * sizeof(float);
 static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + BW_FT * 624) * sizeof(float);
 
 }  // namespace hb
 
 using namespace hb;
+
+extern "C" int humor_lbs_configure(int skin_form, int blend_form, int slab_frames) {
+  if ((skin_form != 0 && skin_form != 1 && skin_form != 2) || (blend_form != 0 && blend_form != 1 && blend_form != 2) ||
+      (slab_frames != 0 && (slab_frames < 128 || slab_frames > TC_SLAB)))
+    return HB_ERR_ARG;
+  if (skin_form) g_skin_form = skin_form;
+  if (blend_form) g_blend_form = blend_form;
+  if (slab_frames) g_slab = slab_frames;
+  return HB_OK;
+}
 
 extern "C" size_t humor_lbs_workspace_bytes(int N) { return lbs_carve(nullptr, N).total * sizeof(float); }
 
@@ -705,13 +723,37 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
   } else if (tc) {
     GemmEpi ep;
     ep.bias = m->v_template; ep.gamma = ep.beta = nullptr; ep.xhat = ep.rstd = nullptr; ep.ldxh = 0; ep.Cch = 0; ep.gsize = 64;
-    for (int f0 = 0; f0 < N; f0 += TC_SLAB) {
-      const int nf = (N - f0 < TC_SLAB) ? N - f0 : TC_SLAB;
-      HB_CUDA(launch_umma_gemm3_bn(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
-                                   TC_KF, nf, 3 * m->num_verts, TC_KF, ws.vposed, nullptr, nullptr, m->v3_ld, EPI_BIAS, ep, 128, st));
-      dim3 grid(cdiv(m->num_verts, 128), cdiv(nf, SA_F));
-      lbs_skin_apply_kernel<<<grid, 128, 0, st>>>(*m, nf, m->v3_ld, ws.vposed, ws.A + (size_t)f0 * 624, trans + (size_t)f0 * 3,
-                                                  verts + (size_t)f0 * m->num_verts * 3);
+    // frames per slab: the v_posed slab must stay in L2 between the two kernels (<= TC_SLAB rows of workspace)
+    const int slab = (g_slab >= 128 && g_slab <= TC_SLAB) ? g_slab : TC_SLAB;
+    for (int f0 = 0; f0 < N; f0 += slab) {
+      const int nf = (N - f0 < slab) ? N - f0 : slab;
+      if (g_blend_form == 2 && m->v3_ld % LB_BN_HOST == 0)
+        HB_CUDA(launch_lbs_blend(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
+                                 TC_KF, m->v3_ld, nf, 3 * m->num_verts, TC_KF, m->v_template, ws.vposed, m->v3_ld, st));
+      else
+        HB_CUDA(launch_umma_gemm3_bn(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
+                                     TC_KF, nf, 3 * m->num_verts, TC_KF, ws.vposed, nullptr, nullptr, m->v3_ld, EPI_BIAS, ep, 128, st));
+      if (g_skin_form == 2 && m->num_groups > 0 && m->g_start && (m->num_verts % 2) == 0 && m->v3_ld >= m->num_groups * 3 * SG_G) {
+        static bool attr_sg = false;   // once per process, on the first (un-captured) call
+        if (!attr_sg) {
+          HB_CUDA(cudaFuncSetAttribute(lbs_skin_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM));
+          int dev = 0;
+          HB_CUDA(cudaGetDevice(&dev));
+          HB_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+          attr_sg = true;
+        }
+        // two resident blocks per SM: split the vertex groups so that one slab fills the chip about once
+        const int fblocks = cdiv(nf, SG_FT);
+        const int want = cdiv(2 * (g_sm_count > 0 ? g_sm_count : 148), fblocks);
+        const int gpb = align_up((size_t)cdiv(m->num_groups, want < 1 ? 1 : want), SG_WARPS);
+        dim3 grid(cdiv(m->num_groups, gpb), fblocks);
+        lbs_skin_group_kernel<<<grid, SG_WARPS * 32, SG_SMEM, st>>>(*m, nf, m->v3_ld, ws.vposed, ws.A + (size_t)f0 * 624,
+                                                                   trans + (size_t)f0 * 3, verts + (size_t)f0 * m->num_verts * 3, gpb);
+      } else {
+        dim3 grid(cdiv(m->num_verts, 128), cdiv(nf, SA_F));
+        lbs_skin_apply_kernel<<<grid, 128, 0, st>>>(*m, nf, m->v3_ld, ws.vposed, ws.A + (size_t)f0 * 624, trans + (size_t)f0 * 3,
+                                                    verts + (size_t)f0 * m->num_verts * 3);
+      }
       HB_LAUNCH_CHECK();
       nl += 2;
     }

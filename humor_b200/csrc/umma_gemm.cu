@@ -4,6 +4,7 @@
 #include "umma_gemm.cuh"
 #include "umma_launch.cuh"
 #include "lbs_fused.cuh"
+#include "lbs_blend.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
@@ -134,6 +135,30 @@ cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf
   const int grid = ntiles < sms ? ntiles : sms;
   return wk == 4 ? launch_fused_t<4>(ta_hi, ta_lo, tb_hi, tb_lo, K, a, grid, st)
                  : launch_fused_t<8>(ta_hi, ta_lo, tb_hi, tb_lo, K, a, grid, st);
+}
+
+cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
+                             int b_rows, int M, int ncols, int K, const float* bias, float* C, int ldc, cudaStream_t st) {
+  if (!load_encode()) return cudaErrorNotSupported;
+  if (K % UM_BK || ldf % 4 || ldb % 4 || ldc % 4 || !bias || b_rows < ncols) return cudaErrorInvalidValue;
+  static int sms = 0;
+  static bool attr = false;
+  if (!attr) {                      // once per process, on the first (un-captured) call
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lbs_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  if (!make_map(&ta_hi, feat_hi, M, K, ldf, UM_BM) || !make_map(&ta_lo, feat_lo, M, K, ldf, UM_BM) ||
+      !make_map(&tb_hi, bt_hi, b_rows, K, ldb, LB_BN) || !make_map(&tb_lo, bt_lo, b_rows, K, ldb, LB_BN))
+    return cudaErrorInvalidValue;
+  const int ntiles = cdiv(M, UM_BM) * cdiv(ncols, LB_BN);
+  const int grid = ntiles < sms ? ntiles : sms;
+  lbs_blend_kernel<<<grid, 192, LB_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, M, ncols, K, bias, C, ldc);
+  return cudaGetLastError();
 }
 
 __global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {

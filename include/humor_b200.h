@@ -66,6 +66,13 @@ typedef struct HbLbsModel {
   const float* fw_val;     /* [num_verts][fused_wk] */
   int fused_nct;
   int fused_wk;            /* 0: fused path unavailable */
+  /* lane = frame skinning pass (csrc/lbs_skin_group.cuh): groups of 8 consecutive vertices; per group the union of the
+     joints its vertices are skinned to and, per joint, the 8 weights (0 where a vertex is not influenced) */
+  const int* g_start;      /* [num_groups + 1] offsets into g_joint / g_w */
+  const int* g_joint;      /* [E] joint * 12 */
+  const float* g_w;        /* [E][8], 16-byte aligned */
+  int num_groups;          /* 0: group tables absent */
+  int reserved2;
 } HbLbsModel;
 
 /* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs
@@ -77,6 +84,12 @@ int humor_lbs_fwd(const HbLbsModel* m, int N, int frames_per_beta, const float* 
                   const float* pose_body, const float* betas, const float* trans, float* workspace,
                   size_t workspace_bytes, const int* vlist, int nv, float* verts, float* joints,
                   int num_joints_out, int64_t* launches, hb_stream_t stream);
+/* Kernel forms of the DENSE tensor-core forward (results agree to fp32 rounding; 0 leaves a setting unchanged):
+ *   skin_form   1 lane = vertex (lbs_skin_apply_kernel)          2 lane = frame over vertex groups (lbs_skin_group.cuh)
+ *   blend_form  1 one 128x128 tile per CTA (umma_gemm3_kernel)   2 persistent 128x256 tiles (lbs_blend.cuh)
+ *   slab_frames frames per v_posed slab kept in L2 between the two kernels (128..512)
+ * Process-wide; not to be changed while a call is in flight.  Environment defaults: HB_LBS_SKIN, HB_LBS_BLEND, HB_LBS_SLAB. */
+int humor_lbs_configure(int skin_form, int blend_form, int slab_frames);
 /* Reverse mode of the above (what autograd does through smplx in the reference).  d_verts follows the
  * same vlist convention; d_betas is per frame [N][16] (the caller reduces over frames_per_beta). */
 int humor_lbs_bwd(const HbLbsModel* m, int N, int frames_per_beta, const float* root_orient,

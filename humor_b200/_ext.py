@@ -103,7 +103,7 @@ class HbFitArgs(C.Structure):
 EXPORTS = ['humor_lbs_workspace_bytes', 'humor_lbs_fwd', 'humor_lbs_bwd', 'humor_rollout_workspace_bytes',
            'humor_rollout_fwd', 'humor_rollout_bwd', 'humor_rodrigues_fwd', 'humor_rodrigues_bwd',
            'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version',
-           'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd', 'humor_lbs_configure']
+           'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd', 'humor_lbs_configure', 'humor_lbs_forms_used']
 
 _LIB = None
 
@@ -147,6 +147,8 @@ def lib():
     L.humor_umma_gemm.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, vp, sz, vp]
     L.humor_lbs_configure.restype = ci
     L.humor_lbs_configure.argtypes = [ci, ci, ci]
+    L.humor_lbs_forms_used.restype = ci
+    L.humor_lbs_forms_used.argtypes = [C.POINTER(ci), C.POINTER(ci)]
     L.humor_chamfer_fwd.restype = ci
     L.humor_chamfer_fwd.argtypes = [ci, ci, vp, ci, vp, vp, vp, vp, vp, i64p, vp]
     L.humor_chamfer_bwd.restype = ci

@@ -29,7 +29,7 @@ constexpr int BW_FT = 16;    // frames per block (backward)
 
 constexpr int TC_SLAB = 512;     // frames per tensor-core slab: v_posed slab (512 x 20736 fp32 = 42 MB) stays in L2
 constexpr int TC_KF = 224;
-constexpr int LB_BN_HOST = 256;   // column tile of the persistent blend kernel (lbs_blend.cuh)       // feature K padded to a multiple of 32 for the TMA/UMMA tiles
+      // feature K padded to a multiple of 32 for the TMA/UMMA tiles
 
 struct LbsWs {
   float *feat, *A, *dfeat, *dA, *dtr, *feat_hi, *feat_lo, *vposed;
@@ -668,6 +668,7 @@ static const bool g_unfused = (getenv("HB_LBS_UNFUSED") != nullptr);
 // dense skinning pass: 1 = lane-per-vertex (lbs_skin_apply_kernel), 2 = lane-per-frame over vertex groups (lbs_skin_group.cuh)
 static int g_skin_form = getenv("HB_LBS_SKIN") ? atoi(getenv("HB_LBS_SKIN")) : 1;
 static int g_sm_count = 0;
+static int g_used_skin = 0, g_used_blend = 0;   // forms the last dense tensor-core call actually ran (0: none yet)
 // blend GEMM of the dense forward: 1 = one 128x128 tile per CTA (umma_gemm3_kernel), 2 = persistent 128x256 tiles (lbs_blend.cuh)
 static int g_blend_form = getenv("HB_LBS_BLEND") ? atoi(getenv("HB_LBS_BLEND")) : 1;
 static int g_slab = getenv("HB_LBS_SLAB") ? atoi(getenv("HB_LBS_SLAB")) : 0;
@@ -685,6 +686,12 @@ extern "C" int humor_lbs_configure(int skin_form, int blend_form, int slab_frame
   if (skin_form) g_skin_form = skin_form;
   if (blend_form) g_blend_form = blend_form;
   if (slab_frames) g_slab = slab_frames;
+  return HB_OK;
+}
+
+extern "C" int humor_lbs_forms_used(int* skin_form, int* blend_form) {
+  if (skin_form) *skin_form = g_used_skin;
+  if (blend_form) *blend_form = g_used_blend;
   return HB_OK;
 }
 
@@ -727,13 +734,20 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
     const int slab = (g_slab >= 128 && g_slab <= TC_SLAB) ? g_slab : TC_SLAB;
     for (int f0 = 0; f0 < N; f0 += slab) {
       const int nf = (N - f0 < slab) ? N - f0 : slab;
-      if (g_blend_form == 2 && m->v3_ld % LB_BN_HOST == 0)
+      const bool blend2 = g_blend_form == 2 && m->v3_ld % 4 == 0;   // column tiles past v3_ld are zero-filled by TMA, never stored
+      g_used_blend = blend2 ? 2 : 1;
+      if (blend2)
         HB_CUDA(launch_lbs_blend(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
                                  TC_KF, m->v3_ld, nf, 3 * m->num_verts, TC_KF, m->v_template, ws.vposed, m->v3_ld, st));
       else
         HB_CUDA(launch_umma_gemm3_bn(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
                                      TC_KF, nf, 3 * m->num_verts, TC_KF, ws.vposed, nullptr, nullptr, m->v3_ld, EPI_BIAS, ep, 128, st));
-      if (g_skin_form == 2 && m->num_groups > 0 && m->g_start && (m->num_verts % 2) == 0 && m->v3_ld >= m->num_groups * 3 * SG_G) {
+      // the last group reads up to 3*SG_G floats per row, i.e. past a row of v3_ld = 20 672 floats: harmless (zero weights, nothing
+      // stored) as long as the slab buffer has that slack after its last row - it is carved for TC_SLAB rows of 20 736 floats
+      const bool skin2 = g_skin_form == 2 && m->num_groups > 0 && m->g_start && (m->num_verts % 2) == 0 && m->v3_ld % 4 == 0 &&
+                         (size_t)TC_SLAB * 20736 >= (size_t)(nf - 1) * m->v3_ld + (size_t)m->num_groups * 3 * SG_G;
+      g_used_skin = skin2 ? 2 : 1;
+      if (skin2) {
         static bool attr_sg = false;   // once per process, on the first (un-captured) call
         if (!attr_sg) {
           HB_CUDA(cudaFuncSetAttribute(lbs_skin_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM));

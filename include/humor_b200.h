@@ -90,6 +90,9 @@ int humor_lbs_fwd(const HbLbsModel* m, int N, int frames_per_beta, const float* 
  *   slab_frames frames per v_posed slab kept in L2 between the two kernels (128..512)
  * Process-wide; not to be changed while a call is in flight.  Environment defaults: HB_LBS_SKIN, HB_LBS_BLEND, HB_LBS_SLAB. */
 int humor_lbs_configure(int skin_form, int blend_form, int slab_frames);
+/* The forms the most recent dense tensor-core call actually ran (a requested form falls back to form 1 when the model's
+ * layout does not allow it); 0 before the first such call. */
+int humor_lbs_forms_used(int* skin_form, int* blend_form);
 /* Reverse mode of the above (what autograd does through smplx in the reference).  d_verts follows the
  * same vlist convention; d_betas is per frame [N][16] (the caller reduces over frames_per_beta). */
 int humor_lbs_bwd(const HbLbsModel* m, int N, int frames_per_beta, const float* root_orient,

@@ -8,7 +8,22 @@ import torch
 
 from humor_b200 import synth, _ext
 
-pytestmark = pytest.mark.gpu
+import os
+
+# Round-1 status: both forms are correct on the CPU side (the skin kernel runs through the SIMT shim, the host dispatch
+# through tests/test_host_dispatch.py) but have NOT executed on a B200 yet - the GPU budget of the round ended before the
+# run that would have exercised them (an earlier run fell back to form 1 because of a layout guard and proved nothing).
+# They stay opt-in, and so do these tests: HB_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_zz_lbs_forms.py
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get('HB_TEST_UNVERIFIED'),
+                                 reason='opt-in kernel forms not yet verified on hardware (set HB_TEST_UNVERIFIED=1)')]
+
+
+def forms_used():
+    import ctypes as C
+    a, b = C.c_int(0), C.c_int(0)
+    _ext.lib().humor_lbs_forms_used(C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 @pytest.fixture(scope='module')
@@ -37,9 +52,11 @@ def test_forms_agree_with_default(bm, skin, blend, slab, n):
         configure(skin, blend, slab)
         got = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
         torch.cuda.synchronize()
+        assert forms_used() == (skin, blend)             # the requested kernels really ran (no silent fall-back)
     finally:
         configure(1, 1)
     assert torch.isfinite(got.v).all()
+    assert not torch.equal(got.v, ref.v)                 # a different summation order must show in the last bits
     assert float((got.v - ref.v).abs().max()) < 5e-6
     assert float((got.Jtr - ref.Jtr).abs().max()) < 5e-6
 
@@ -54,6 +71,7 @@ def test_forms_match_oracle(bm):
         configure(2, 2)
         g = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
         torch.cuda.synchronize()
+        assert forms_used() == (2, 2)
     finally:
         configure(1, 1)
     assert float((g.v.cpu() - o.v).abs().max()) < 2e-5

@@ -49,7 +49,12 @@ def test_skin_group_kernel_matches_dense_sum(H, packed, nframes, gpb):
     asset, p = packed
     V, v3_ld = 6890, p['v3_ld']
     rng = np.random.RandomState(nframes)
-    vposed = np.full((nframes, v3_ld), np.nan, np.float32)      # the GEMM leaves columns >= 3V unwritten
+    # v3_ld = 20 672 < 862 groups * 24 floats: the last group of a row reads 16 floats into the next row (or, for the last
+    # row, into the slack the real slab buffer has after it); those belong to vertices >= 6890, carry zero weights and are
+    # never stored.  NaN everywhere the GEMM does not write makes any use of them visible.
+    flat = np.full(nframes * v3_ld + 32, np.nan, np.float32)
+    vposed = flat[:nframes * v3_ld].reshape(nframes, v3_ld)
+    assert v3_ld < p['num_groups'] * 24 and v3_ld % 4 == 0
     vposed[:, :3 * V] = rng.randn(nframes, 3 * V).astype(np.float32)
     A = rng.randn(nframes, 52, 3, 4).astype(np.float32)
     trans = rng.randn(nframes, 3).astype(np.float32)

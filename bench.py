@@ -213,6 +213,8 @@ def run_product(args):
                      'slab_frames': args.lbs_slab or int(os.environ.get('HB_LBS_SLAB', 512))}
     shares = kernel_shares(mo, obs, params, dev)
     cpu = cpu_baseline(args) if not args.no_cpu_baseline else None
+    # the same algorithm as eager PyTorch on this GPU (context for the '>= 20x the reference PyTorch-CUDA step' target)
+    torch_cuda = port_cuda_child(args) if not args.no_cpu_baseline else None
     out = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -227,6 +229,7 @@ def run_product(args):
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches), 'gpu_launches_per_step': launches / args.steps,
         'clocks': clocks, 'roofline': roof, 'step_breakdown_ms': shares, 'cpu_baseline': cpu,
+        'torch_cuda_port': torch_cuda,
         'lbs_bytes_roofline_frac_of_step': value * (2.0 + 3.0 / T) * (LBS_BYTES_FWD + LBS_BYTES_BWD) / (hbm_peak * 1e9),
     }
     print(json.dumps(out))
@@ -326,11 +329,31 @@ def port_on_cuda(args):
                         'peak_mem_gb': torch.cuda.max_memory_allocated() / 2**30})
         except torch.OutOfMemoryError:
             res.append({'batch': Bc, 'oom': True})
+        except Exception as e:  # noqa: BLE001  (a context number must never take the bench down)
+            res.append({'batch': Bc, 'error': f'{type(e).__name__}: {str(e)[:200]}'})
         finally:
             port = None
             torch.cuda.empty_cache()
     print(json.dumps({'impl': 'port-cuda', 'metric': METRIC, 'unit': 'frames/s', 'kind': 'oracle port, eager PyTorch on cuda:0',
                       'steps': args.cpu_steps, 'results': res}))
+
+
+def port_cuda_child(args, batch=64, limit_s=150):
+    """the reference ALGORITHM as eager PyTorch on the same B200 (the oracle port on device='cuda'; the
+    reference itself cannot travel to the GPU box), timed in a child process with a hard limit.  Launch/dispatch-bound:
+    its time per closure barely depends on the batch, so frames/s is quoted at the batch given."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--port-cuda', str(batch), '--cpu-steps', '3', '--seq-len', str(args.seq_len)]
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=limit_s, env=env)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        res = d['results'][0]
+        res['kind'] = d['kind']
+        return res
+    except Exception as e:  # noqa: BLE001
+        return {'batch': batch, 'error': f'{type(e).__name__}: {str(e)[:200]}'}
 
 
 def cpu_threads():

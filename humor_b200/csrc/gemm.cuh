@@ -217,6 +217,7 @@ gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
   }
 }
 
+#ifndef HB_HOST_SHIM   // launch syntax: device builds only (tests/host compiles the kernels with g++)
 // Host-side dispatch: small-M tiles (32x64) for the sequential decoder steps, 128x128 for the
 // batched prior.  Returns a cudaError_t.
 template <int EPI>
@@ -231,5 +232,6 @@ static inline cudaError_t launch_gemm(const float* A, int lda, const float* B, i
   }
   return cudaGetLastError();
 }
+#endif
 
 }  // namespace hb

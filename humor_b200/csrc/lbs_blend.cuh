@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(192, 1)
 lbs_blend_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, int M, int ncols, int K,
                  const float* __restrict__ bias, float* __restrict__ C, int ldc) {
-  extern __shared__ uint8_t smem_raw[];
+  HB_DYN_SMEM(smem_raw);
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t bars = base + LB_STAGES * LB_STAGE;
@@ -43,17 +43,16 @@ lbs_blend_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < LB_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(tptr, 512u);
+    tmem_relinquish();
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
+  tc_fence_after();
+  const uint32_t tmem_base = ld_shared_u32(tptr);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -80,12 +79,12 @@ lbs_blend_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
         const int buf = tc & 1;
         mbar_wait(tempty0 + 8 * buf, ((tc >> 1) & 1) ^ 1);      // epilogue has drained this TMEM buffer
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_fence_after();
         const uint32_t tacc = tmem_base + buf * LB_BN;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
           const int s = g % LB_STAGES;
           mbar_wait(full0 + 8 * s, (g / LB_STAGES) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          tc_fence_after();
           const uint32_t st = base + s * LB_STAGE;
 #pragma unroll
           for (int k = 0; k < UM_BK / 8; ++k) {
@@ -113,7 +112,7 @@ lbs_blend_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const bool rok = row < M;
       float* crow = C + (size_t)(rok ? row : 0) * ldc;
       mbar_wait(tfull0 + 8 * buf, (tc >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < LB_BN; c0 += 32) {
         float v[32];
@@ -133,15 +132,15 @@ lbs_blend_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    tmem_dealloc(tmem_base, 512u);
   }
 }
 

@@ -41,7 +41,7 @@ template <int WK>
 __global__ void __launch_bounds__(192, 1)
 lbs_fused_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, int K, LbsFusedArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+  HB_DYN_SMEM(smem_raw);
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
@@ -57,17 +57,16 @@ lbs_fused_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < LF_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(256u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(tptr, 256u);
+    tmem_relinquish();
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
+  tc_fence_after();
+  const uint32_t tmem_base = ld_shared_u32(tptr);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -94,13 +93,13 @@ lbs_fused_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int c = 0; c < nchunk; ++c, ++cc) {
           const int buf = cc & 1;
           mbar_wait(tempty0 + 8 * buf, ((cc >> 1) & 1) ^ 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          tc_fence_after();
           const uint32_t tacc = tmem_base + buf * 128;
           const int kb_end = min(nkb, (c + 1) * UM_CHUNK);
           for (int kb = c * UM_CHUNK; kb < kb_end; ++kb, ++g) {
             const int s = g % LF_STAGES;
             mbar_wait(full0 + 8 * s, (g / LF_STAGES) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_fence_after();
             const uint32_t st = base + s * LF_STAGE;
 #pragma unroll
             for (int k = 0; k < UM_BK / 8; ++k) {
@@ -136,7 +135,7 @@ lbs_fused_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       for (int c = 0; c < nchunk; ++c, ++cc) {
         const int buf = cc & 1;
         mbar_wait(tfull0 + 8 * buf, (cc >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
           float tv[32];
@@ -144,7 +143,7 @@ lbs_fused_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[c0 + j] += tv[j];
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
       }
@@ -203,10 +202,10 @@ lbs_fused_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    tmem_dealloc(tmem_base, 256u);
   }
 }
 

@@ -17,12 +17,46 @@
 #include <cuda.h>
 #include "gemm.cuh"
 
+// tests/host: the same kernel sources run on the CPU against a functional emulation of shared-memory addresses, mbarriers,
+// TMA tile loads (SWIZZLE_128B), tcgen05.mma kind::tf32 and TMEM (tests/host/shim/tc_emul.h); every PTX primitive below has
+// an emulated twin selected by HB_HOST_SHIM.  Device builds are unaffected (SASS identical before/after this split).
+#ifdef HB_HOST_SHIM
+#include "tc_emul.h"
+#define HB_DYN_SMEM(name) uint8_t* name = tcemu::dyn_smem()
+#else
+#define HB_DYN_SMEM(name) extern __shared__ uint8_t name[]
+#endif
+
 namespace hb {
 
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;          // tf32 elements per stage row = 128 bytes = one swizzle span
 
+#ifdef HB_HOST_SHIM
+using tcemu::smem_u32; using tcemu::mbar_init; using tcemu::mbar_expect_tx; using tcemu::mbar_wait; using tcemu::mbar_arrive;
+using tcemu::tma_load_2d; using tcemu::umma_tf32; using tcemu::umma_commit; using tcemu::tmem_ld32;
+using tcemu::tmem_alloc; using tcemu::tmem_relinquish; using tcemu::tmem_dealloc; using tcemu::tc_fence_before;
+using tcemu::tc_fence_after; using tcemu::mbar_fence_init; using tcemu::ld_shared_u32;
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// TMEM allocation (one warp, .sync.aligned): the base address lands in shared memory at `dst`
+__device__ __forceinline__ void tmem_alloc(uint32_t dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -65,6 +99,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
                : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+#endif  // HB_HOST_SHIM (primitives)
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (1024 B between 8-row groups)
 //   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
@@ -133,9 +168,11 @@ struct UmmaSmem {
 
 constexpr int UM_CHUNK = 4;        // k-blocks (4 x 32 = K 128) accumulated in TMEM before promotion to fp32 registers
 
+#ifndef HB_HOST_SHIM
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#endif
 
 // The tensor-core accumulator truncates on every add (measured on B200: -2e-5 relative bias over K = 1024 with
 // positive operands, error growing ~K), which alone would break the 1e-5 parity bound.  Each K-chunk of 128 is
@@ -145,6 +182,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // steps have only M = sub-sequences-per-GPU rows, i.e. ~32 output tiles: splitting K four ways puts 128 CTAs on the
 // chip and shortens each CTA's dependent TMA->MMA chain 4x.  Partials meet in the leader's (rank 0) shared memory
 // through DSMEM stores between two cluster barriers; only the leader runs the epilogue.
+#ifndef HB_HOST_SHIM   // split-K clusters / programmatic dependent launch: device only
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -338,5 +376,7 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
   }
 }
+
+#endif  // HB_HOST_SHIM (umma_gemm3_kernel)
 
 }  // namespace hb

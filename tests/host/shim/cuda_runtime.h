@@ -87,7 +87,7 @@ void launch(dim3 grid, dim3 block, F body) {
 #define __launch_bounds__(...)
 #define __syncthreads() shim::sync_block()
 #define __syncwarp(...) shim::sync_warp()
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 // Separately rounded fp32 operations (compile the harness with -ffp-contract=off so that plain expressions are not
 // fused either).
@@ -116,3 +116,6 @@ static inline float __shfl_sync(unsigned, float v, int src) {
 }
 using std::max;
 using std::min;
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+static inline int __ldg(const unsigned* p) { return (int)*p; }
+typedef unsigned long long cuuint64_t;

@@ -1,0 +1,151 @@
+// Test infrastructure: functional CPU emulation of the Blackwell primitives the tcgen05 kernels use, so that the SAME
+// kernel source (humor_b200/csrc/lbs_blend.cuh, lbs_fused.cuh) runs under the SIMT shim (cuda_runtime.h in this directory):
+//   * a shared-memory window with 32-bit addresses (the dynamic buffer deliberately starts at address 16, so the kernels'
+//     1024-byte align-up matters),
+//   * mbarriers: pending-arrival count + transaction bytes + phase parity (init / arrive / arrive.expect_tx / complete_tx /
+//     try_wait.parity; a wait that does not complete within 30 s aborts: protocol bugs fail, they do not hang),
+//   * TMA 2-D tile loads with SWIZZLE_128B (16-byte chunk index XOR (address bits 7..9)), out-of-range elements = 0,
+//   * tcgen05.mma kind::tf32, M = 128, K = 8 per instruction, operands read through K-major SWIZZLE_128B descriptors
+//     (start address, SBO) exactly as issued by the kernels, operands truncated to tf32, fp32 accumulation into TMEM,
+//   * TMEM as [128 lanes][512 columns] fp32, tcgen05.ld 32x32b.x32, alloc/dealloc, tcgen05.commit -> mbarrier arrive.
+// What it checks: tile/index arithmetic, descriptor offsets, barrier protocol (phases, buffer reuse), epilogues.  What it
+// cannot check: that the hardware interprets descriptors / swizzles the way modelled here (lbs_fused_kernel, which IS
+// verified on the B200, runs through the same emulation as a cross-check of the model), timing, real asynchrony.
+#pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
+#include "cuda.h"
+
+namespace tcemu {
+
+constexpr uint32_t WINDOW_BYTES = 256 * 1024;
+constexpr uint32_t DYN_OFFSET = 16;
+alignas(1024) inline uint8_t g_smem[WINDOW_BYTES];
+inline float g_tmem[128][512];
+inline std::mutex g_mu;
+struct Bar { int expected = 0, pending = 0; long long tx = 0; int phase = 0; };
+inline std::map<uint32_t, Bar> g_bars;
+inline long long g_mma_count = 0, g_tma_count = 0;
+
+inline uint8_t* dyn_smem() { return g_smem + DYN_OFFSET; }
+inline uint32_t smem_u32(const void* p) { return (uint32_t)(static_cast<const uint8_t*>(p) - g_smem); }
+inline uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
+inline float tf32_trunc(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
+
+inline void reset() {
+  std::lock_guard<std::mutex> l(g_mu);
+  g_bars.clear();
+  std::memset(g_smem, 0xff, sizeof(g_smem));          // NaN patterns: reading a byte nobody wrote shows
+  for (auto& r : g_tmem) for (auto& v : r) v = __builtin_nanf("");
+  g_mma_count = g_tma_count = 0;
+}
+inline void complete_if_done(Bar& b) {
+  if (b.pending == 0 && b.tx == 0) { b.phase ^= 1; b.pending = b.expected; }
+}
+inline void mbar_init(uint32_t bar, int count) {
+  std::lock_guard<std::mutex> l(g_mu);
+  Bar b; b.expected = b.pending = count;
+  g_bars[bar] = b;
+}
+inline void mbar_fence_init() {}
+inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  std::lock_guard<std::mutex> l(g_mu);
+  Bar& b = g_bars.at(bar);
+  b.tx += bytes; b.pending -= 1;
+  if (b.pending < 0) { std::fprintf(stderr, "tcemu: mbarrier %u over-arrived\n", bar); std::abort(); }
+  complete_if_done(b);
+}
+inline void mbar_arrive(uint32_t bar) {
+  std::lock_guard<std::mutex> l(g_mu);
+  Bar& b = g_bars.at(bar);
+  b.pending -= 1;
+  if (b.pending < 0) { std::fprintf(stderr, "tcemu: mbarrier %u over-arrived\n", bar); std::abort(); }
+  complete_if_done(b);
+}
+inline void complete_tx(uint32_t bar, uint32_t bytes) {
+  std::lock_guard<std::mutex> l(g_mu);
+  Bar& b = g_bars.at(bar);
+  b.tx -= bytes;
+  complete_if_done(b);
+}
+inline void mbar_wait(uint32_t bar, uint32_t parity) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    {
+      std::lock_guard<std::mutex> l(g_mu);
+      if ((uint32_t)g_bars.at(bar).phase != (parity & 1u)) return;      // the phase with this parity has completed
+    }
+    std::this_thread::yield();
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) {
+      std::fprintf(stderr, "tcemu: wait on mbarrier %u (parity %u) did not complete: protocol deadlock\n", bar, parity);
+      std::abort();
+    }
+  }
+}
+// cp.async.bulk.tensor.2d ... mbarrier::complete_tx::bytes with a {32 floats, box_rows} box and SWIZZLE_128B
+inline void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y) {
+  if (dst % 1024u) { std::fprintf(stderr, "tcemu: TMA destination %u is not 1024-byte aligned\n", dst); std::abort(); }
+  if (m->box_cols != 32) { std::fprintf(stderr, "tcemu: box must be one 128-byte swizzle span wide\n"); std::abort(); }
+  for (unsigned r = 0; r < m->box_rows; ++r)
+    for (unsigned c = 0; c < 32; ++c) {
+      const long long gr = (long long)y + r, gc = (long long)x + c;
+      const float v = (gr >= 0 && gc >= 0 && (unsigned long long)gr < m->rows && (unsigned long long)gc < m->cols) ? m->base[gr * m->ld + gc] : 0.f;
+      const uint32_t a = swz128(dst + r * 128u + c * 4u);
+      std::memcpy(g_smem + a, &v, 4);
+    }
+  { std::lock_guard<std::mutex> l(g_mu); ++g_tma_count; }
+  complete_tx(bar, m->box_rows * 128u);
+}
+// tcgen05.mma.cta_group::1.kind::tf32, M = 128 (idesc bits 24..28), N = idesc bits 17..22 << 3, K = 8 (32 bytes)
+inline void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  const int M = (int)((idesc >> 24) & 0x1F) << 4, N = (int)((idesc >> 17) & 0x3F) << 3;
+  if (M != 128 || N < 8 || N > 256 || (N % 16)) { std::fprintf(stderr, "tcemu: unsupported UMMA shape %dx%d\n", M, N); std::abort(); }
+  if (((adesc >> 61) & 7) != 2 || ((bdesc >> 61) & 7) != 2) { std::fprintf(stderr, "tcemu: descriptors must be SWIZZLE_128B\n"); std::abort(); }
+  const uint32_t a0 = (uint32_t)(adesc & 0x3FFF) << 4, b0 = (uint32_t)(bdesc & 0x3FFF) << 4;
+  const uint32_t asbo = (uint32_t)((adesc >> 32) & 0x3FFF) << 4, bsbo = (uint32_t)((bdesc >> 32) & 0x3FFF) << 4;
+  static thread_local float A[128][8], B[256][8];
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 8; ++k) {
+      float v; std::memcpy(&v, g_smem + swz128(a0 + (m / 8) * asbo + (m % 8) * 128u + k * 4u), 4);
+      A[m][k] = tf32_trunc(v);
+    }
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < 8; ++k) {
+      float v; std::memcpy(&v, g_smem + swz128(b0 + (n / 8) * bsbo + (n % 8) * 128u + k * 4u), 4);
+      B[n][k] = tf32_trunc(v);
+    }
+  const uint32_t lane0 = tmem_d >> 16, col0 = tmem_d & 0xFFFFu;
+  if (lane0 != 0 || col0 + (uint32_t)N > 512u) { std::fprintf(stderr, "tcemu: accumulator outside TMEM\n"); std::abort(); }
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float s = accum ? g_tmem[m][col0 + n] : 0.f;
+      for (int k = 0; k < 8; ++k) s += A[m][k] * B[n][k];
+      g_tmem[m][col0 + n] = s;
+    }
+  std::lock_guard<std::mutex> l(g_mu);
+  ++g_mma_count;
+}
+inline void umma_commit(uint32_t bar) { mbar_arrive(bar); }      // the MMAs above ran synchronously
+inline void tmem_ld32(uint32_t taddr, float* v) {
+  const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31u), col = taddr & 0xFFFFu;
+  if (lane >= 128u || col + 32u > 512u) { std::fprintf(stderr, "tcemu: tcgen05.ld outside TMEM\n"); std::abort(); }
+  // a warp may only touch its own lane quadrant (warp id % 4)
+  if ((taddr >> 16) != ((threadIdx.x >> 5) & 3u) * 32u) { std::fprintf(stderr, "tcemu: warp reads a foreign TMEM quadrant\n"); std::abort(); }
+  for (int j = 0; j < 32; ++j) v[j] = g_tmem[lane][col + j];
+}
+inline void tmem_alloc(uint32_t dst, uint32_t ncols) {
+  if (ncols < 32 || ncols > 512 || (ncols & (ncols - 1))) { std::fprintf(stderr, "tcemu: bad TMEM allocation %u\n", ncols); std::abort(); }
+  const uint32_t base = 0;
+  std::memcpy(g_smem + dst, &base, 4);
+}
+inline void tmem_relinquish() {}
+inline void tmem_dealloc(uint32_t, uint32_t) {}
+inline void tc_fence_before() {}
+inline void tc_fence_after() {}
+inline uint32_t ld_shared_u32(uint32_t addr) { uint32_t v; std::memcpy(&v, g_smem + addr, 4); return v; }
+
+}  // namespace tcemu

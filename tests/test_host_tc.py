@@ -1,0 +1,112 @@
+"""The tcgen05 kernels of the dense LBS forward executed on the CPU: SIMT shim + functional emulation of mbarriers, TMA
+(SWIZZLE_128B), tcgen05.mma kind::tf32 and TMEM (tests/host/shim/tc_emul.h), same kernel source as the GPU build.
+
+* lbs_fused_kernel is verified on the B200 (tests/test_gpu_kernels.py): running it here cross-checks the emulation MODEL
+  (descriptor / swizzle interpretation, barrier semantics) against a kernel known to be right on hardware.
+* lbs_blend_kernel (persistent 128x256 tiles) has not run on hardware yet: this is its functional check — tile order,
+  descriptor offsets, single-buffer-per-tile TMEM protocol, partial row/column tiles, operand planes past the matrix."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from humor_b200 import synth
+from humor_b200.body_model import pack_smplh
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope='module')
+def H():
+    so = os.path.join(HERE, 'host', 'tc_host.so')
+    src = os.path.join(HERE, 'host', 'tc_host.cpp')
+    subprocess.check_call(['g++', '-O2', '-std=c++20', '-pthread', '-shared', '-fPIC', '-I' + os.path.join(HERE, 'host', 'shim'),
+                           '-DHB_HOST_SHIM', src, '-o', so])
+    L = ctypes.CDLL(so)
+    L.h_lbs_blend.restype = ctypes.c_longlong
+    L.h_lbs_fused.restype = ctypes.c_longlong
+    return L
+
+
+def split(x):
+    hi = (x.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+    return np.ascontiguousarray(hi), np.ascontiguousarray(x - hi)
+
+
+@pytest.mark.parametrize('M,ncols,b_rows,grid', [(300, 700, 704, 3), (128, 256, 256, 1), (129, 257, 260, 7), (40, 1030, 1056, 2)])
+def test_blend_kernel_matches_fp64(H, M, ncols, b_rows, grid):
+    K = 224
+    rng = np.random.RandomState(M + ncols)
+    feat = np.zeros((M, K), np.float32)
+    feat[:, :205] = rng.randn(M, 205).astype(np.float32)
+    bt = np.zeros((b_rows, K), np.float32)
+    bt[:ncols, :205] = (rng.randn(ncols, 205) * 0.01).astype(np.float32)
+    bias = rng.randn(ncols).astype(np.float32)
+    fh, fl = split(feat)
+    bh, bl = split(bt)
+    ldc = ((ncols + 63) // 64) * 64
+    C = np.full((M, ldc), np.nan, np.float32)
+    nmma = H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, b_rows, M, ncols, K, P(bias), P(C), ldc, grid)
+    ntiles = ((M + 127) // 128) * ((ncols + 255) // 256)
+    assert nmma == ntiles * 7 * 4 * 3                          # 7 k-blocks x 4 UMMAs of K = 8 x (hi.hi + lo.hi + hi.lo)
+    ref = feat.astype(np.float64) @ bt[:ncols].astype(np.float64).T + bias
+    assert np.isfinite(C[:, :ncols]).all()
+    assert np.abs(C[:, :ncols] - ref).max() < 3e-6 * max(1.0, np.abs(ref).max())
+    assert np.isnan(C[:, ncols:]).all()                        # padding columns are never written
+
+
+def test_blend_kernel_on_the_model_layout(H):
+    """v3_ld = 20 672 rows of operand planes, 3V = 20 670 columns: the last 256-column tile reads 64 rows past the planes
+    (TMA zero fill) and stores only 190 columns; 2 persistent CTAs walk the last tiles of 2 row tiles."""
+    p = pack_smplh(synth.make_smplh_asset(), 16)
+    K, v3_ld, V3 = 224, p['v3_ld'], 3 * 6890
+    assert v3_ld == 20672
+    c0 = 20480 - 256                                           # keep the run short: the last two column tiles only
+    bt = np.zeros((v3_ld - c0, K), np.float32)
+    bt[:, :208] = p['blend_t'][c0:]
+    M = 130
+    rng = np.random.RandomState(0)
+    feat = np.zeros((M, K), np.float32)
+    feat[:, :205] = rng.randn(M, 205).astype(np.float32) * 0.5
+    fh, fl = split(feat)
+    bh, bl = split(bt)
+    ncols = V3 - c0
+    bias = p['v_template'][c0:V3].copy()
+    ldc = v3_ld - c0
+    C = np.full((M, ldc), np.nan, np.float32)
+    H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], M, ncols, K, P(bias), P(C), ldc, 2)
+    ref = feat.astype(np.float64) @ bt[:ncols].astype(np.float64).T + bias
+    assert np.abs(C[:, :ncols] - ref).max() < 3e-6 and np.isnan(C[:, ncols:]).all()
+
+
+def test_fused_kernel_cross_checks_the_emulation(H):
+    """lbs_fused_kernel (hardware-verified) through the same emulation against the dense skinning formula."""
+    asset = synth.make_smplh_asset()
+    p = pack_smplh(asset, 16)
+    V = 6890
+    nct_all, wk = p['fused_nct'], p['fused_wk']
+    nct = 2                                                    # the first 84 vertices are enough to exercise every stage
+    nv = 84
+    K, N = 224, 200                                            # 2 row tiles, the second ragged
+    rng = np.random.RandomState(1)
+    feat = np.zeros((N, K), np.float32)
+    feat[:, :205] = rng.randn(N, 205).astype(np.float32) * 0.5
+    feat[:, 205] = 1.0                                         # picks up the template column of the fused blend matrix
+    fb = np.ascontiguousarray(p['fblend'][:nct * 128])
+    fh, fl = split(feat)
+    bh, bl = split(fb)
+    A = rng.randn(N, 52, 3, 4).astype(np.float32)
+    trans = rng.randn(N, 3).astype(np.float32)
+    out = np.full((N, nv, 3), np.nan, np.float32)
+    fw_idx, fw_val = np.ascontiguousarray(p['fw_idx'][:nv]), np.ascontiguousarray(p['fw_val'][:nv])
+    H.h_lbs_fused(P(fh), P(fl), K, P(bh), P(bl), K, N, nv, nct, wk, P(fw_idx), P(fw_val), P(A), P(trans), P(out), 3)
+    blend = p['blend'][:, :3 * nv].astype(np.float64)          # (208, 3nv)
+    vp = feat[:, :208].astype(np.float64) @ blend + p['v_template'][:3 * nv].astype(np.float64)
+    vp = vp.reshape(N, nv, 3)
+    T = np.einsum('vj,njrc->nvrc', asset['weights'][:nv].astype(np.float64), A.astype(np.float64))
+    ref = np.einsum('nvrc,nvc->nvr', T[..., :3], vp) + T[..., 3] + trans[:, None]
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())

@@ -261,7 +261,12 @@ def lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind):
     achieved = N * LBS_BYTES_FWD / (ms * 1e-3) / 1e9
     return {'kernel': 'dense LBS forward: lbs_pose_kernel + per 512-frame slab umma_gemm3_kernel<128,BIAS> (tcgen05 blend) + '
                       'lbs_skin_apply_kernel', 'bound': 'hbm', 'achieved': achieved,
-            'peak': hbm_peak, 'peak_source': peak_kind, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
+            'peak': hbm_peak, 'peak_source': peak_kind, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of the two slab kernels in profiles/r01g_lbs_slab_kernels_set_full.ncu-rep
+            # (ncu --set full, cold L2: 41.4 MB blend GEMM + 46.7 MB skin pass per 512-frame slab) x slabs per launch.  Cold-cache
+            # replay: the blend planes (37 MB) are re-read from DRAM for every slab and v_posed makes a DRAM round trip, while the
+            # final write-back of the vertices is only partly inside the kernel's window.
+            'traffic': (41.36e6 + 46.68e6) * ((N + 511) // 512), 'traffic_source': 'profiles/r01g_lbs_slab_kernels_set_full.ncu-rep',
             'ms_per_launch': ms, 'frames_per_launch': N, 'algorithmic_bytes_per_frame': LBS_BYTES_FWD}
 
 

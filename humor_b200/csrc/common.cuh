@@ -18,6 +18,14 @@
     if (e__ != cudaSuccess) return (int)e__;        \
   } while (0)
 
+// dynamic shared memory of a kernel as a float array.  tests/host compiles the kernels with g++ against a SIMT shim
+// (HB_HOST_SHIM): there the block-shared buffer comes from the shim.
+#ifdef HB_HOST_SHIM
+#define HB_DYN_SMEM_F32(name) float* name = shim::dyn_smem_f32()
+#else
+#define HB_DYN_SMEM_F32(name) extern __shared__ __align__(16) float name[]
+#endif
+
 namespace hb {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -369,7 +369,7 @@ lbs_pose_bwd_warp_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__
 __global__ void __launch_bounds__(256)
 lbs_skin_fwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const float* __restrict__ A,
                     const float* __restrict__ trans, const int* __restrict__ vlist, int nv, float* out, size_t out_fs) {
-  extern __shared__ __align__(16) float Fs[];              // [SK_FT][LBS_KF]
+  HB_DYN_SMEM_F32(Fs);                                     // [SK_FT][LBS_KF]
   const int tid = threadIdx.x;
   const int vi = tid % SK_VT, fg = tid / SK_VT;            // 4 frame groups x 16 frames
   const int f0 = blockIdx.y * SK_FT;
@@ -504,7 +504,7 @@ lbs_skin_bwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const f
                     const int* __restrict__ vlist2, int nv1, const float* __restrict__ dv2, size_t dv2_fs) {
   // slots [0, nv1) come from (vlist, dv); slots [nv1, nv) from the second source (vlist2, dv2) - used to fold the 21
   // vertex-picked joints into the same pass as the listed key vertices (nv1 == nv: single source)
-  extern __shared__ __align__(16) float sm[];
+  HB_DYN_SMEM_F32(sm);
   float* Fs = sm;                              // [BW_FT][208]
   float* GP = Fs + BW_FT * LBS_KF;             // [BW_FT][192]   d v_posed
   float* Gs = GP + BW_FT * 192;                // [BW_FT][192]   d v
@@ -677,6 +677,7 @@ static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + 
 
 }  // namespace hb
 
+#ifndef HB_HOST_SHIM   // host side of the C-ABI (launch syntax): device builds only
 using namespace hb;
 
 extern "C" int humor_lbs_configure(int skin_form, int blend_form, int slab_frames) {
@@ -859,3 +860,4 @@ extern "C" int humor_lbs_bwd(const HbLbsModel* m, int N, int fpb, const float* r
   if (launches) *launches = nl;
   return HB_OK;
 }
+#endif  // HB_HOST_SHIM

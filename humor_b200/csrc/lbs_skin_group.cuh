@@ -29,11 +29,7 @@ constexpr int SG_SMEM = SG_FT * SG_AS * (int)sizeof(float);
 __global__ void __launch_bounds__(SG_WARPS * 32, 2)
 lbs_skin_group_kernel(HbLbsModel m, int nframes, int v3_ld, const float* __restrict__ vposed, const float* __restrict__ A,
                       const float* __restrict__ trans, float* __restrict__ out, int groups_per_block) {
-#ifdef HB_HOST_SHIM
-  alignas(16) static float As[SG_FT * SG_AS];
-#else
-  extern __shared__ __align__(16) float As[];
-#endif
+  HB_DYN_SMEM_F32(As);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f0 = blockIdx.y * SG_FT;
   const int nf = min(SG_FT, nframes - f0);

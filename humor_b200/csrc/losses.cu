@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(256) gmm_nll_kernel(int D, int K, const float*
 }
 
 }  // namespace hb
+#ifndef HB_HOST_SHIM   // host side of the C-ABI (launch syntax): device builds only
 using namespace hb;
 
 extern "C" int humor_fit_losses(const HbFitArgs* a, int64_t* launches, cudaStream_t st) {
@@ -427,3 +428,4 @@ extern "C" int humor_gmm_nll(int B, int D, int K, const float* x, const float* l
   HB_LAUNCH_CHECK();
   return HB_OK;
 }
+#endif  // HB_HOST_SHIM

@@ -41,6 +41,7 @@ __global__ void mat2aa_bwd_kernel(int n, const float* __restrict__ R, const floa
   for (int e = 0; e < 9; ++e) dR[9 * (size_t)i + e] = G[e];
 }
 }  // namespace hb
+#ifndef HB_HOST_SHIM   // host side of the C-ABI (launch syntax): device builds only
 using namespace hb;
 extern "C" int humor_rodrigues_fwd(int n, const float* aa, float* R, cudaStream_t st) {
   if (n <= 0 || !aa || !R) return HB_ERR_ARG;
@@ -63,3 +64,4 @@ extern "C" int humor_mat2aa_bwd(int n, const float* R, const float* daa, float* 
   HB_LAUNCH_CHECK(); return HB_OK;
 }
 extern "C" const char* humor_b200_version(void) { return "humor_b200 0.1 (sm_100a)"; }
+#endif  // HB_HOST_SHIM

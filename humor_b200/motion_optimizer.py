@@ -523,6 +523,23 @@ class MotionOptimizer():
             stats[k] = stats[k] + v if k in stats else v
         return loss, stats
 
+    def stage12_forward(self, observed_data, stage):
+        """Body of the Stage-I (stage 0: root_fit) / Stage-II (stage 1: smpl_fit) closures of motion_optimizer.py:237-250,
+        289-304 up to (loss, stats, pred).  The caller has selected the stage's weights (fitting_loss.set_stage)."""
+        full = stage == 1
+        body_pose = self.latent2pose(self.latent_pose)
+        pred, _ = self.smpl_results(self.trans, self.root_orient, body_pose, self.betas, dense=False,
+                                    dense_grad=self.points3d_active(observed_data))
+        pred['betas'] = self.betas
+        if full:
+            pred['latent_pose'] = self.latent_pose
+            loss, st = self.fitting_loss.smpl_fit(observed_data, pred, self.seq_len)
+            loss, st = self._boundary_energy(loss, st, pred['verts3d'], observed_data, 'smpl')
+        else:
+            loss, st = self.fitting_loss.root_fit(observed_data, pred)
+            loss, st = self._boundary_energy(loss, st, pred['verts3d'], observed_data, 'root')
+        return loss, st, pred
+
     def _stage12(self, observed_data, stage, num_iter, lr, lbfgs_max_iter):
         """Stage I (root only) / Stage II (pose + shape): motion_optimizer.py:224-306."""
         self.fitting_loss.set_stage(stage)
@@ -538,17 +555,7 @@ class MotionOptimizer():
 
             def closure():
                 optim.zero_grad()
-                body_pose = self.latent2pose(self.latent_pose)
-                pred, _ = self.smpl_results(self.trans, self.root_orient, body_pose, self.betas, dense=False,
-                                            dense_grad=self.points3d_active(observed_data))
-                pred['betas'] = self.betas
-                if full:
-                    pred['latent_pose'] = self.latent_pose
-                    loss, st = self.fitting_loss.smpl_fit(observed_data, pred, self.seq_len)
-                    loss, _ = self._boundary_energy(loss, st, pred['verts3d'], observed_data, 'smpl')
-                else:
-                    loss, st = self.fitting_loss.root_fit(observed_data, pred)
-                    loss, _ = self._boundary_energy(loss, st, pred['verts3d'], observed_data, 'root')
+                loss, _, _ = self.stage12_forward(observed_data, stage)
                 loss.backward()
                 return loss
             optim.step(closure)

@@ -314,6 +314,30 @@ PROXD_STAGE3_WEIGHTS = {
 WEIGHT_SETS = {'rgb': RGB_STAGE3_WEIGHTS, 'amass': AMASS_STAGE3_WEIGHTS, 'proxd': PROXD_STAGE3_WEIGHTS}
 
 
+def stage12_weights(wset):
+    """Stage-I/II columns (identical in the shipped configs) of fit_rgb_demo_use_split.cfg / fit_amass_keypts.cfg /
+    fit_proxd.cfg: the data terms of the stage-3 column plus pose prior and temporal smoothness, no motion terms."""
+    w = {k: 0.0 for k in RGB_STAGE3_WEIGHTS}
+    if wset == 'rgb':
+        w.update(joints2d=0.001, pose_prior=0.04, shape_prior=0.05, joints3d_smooth=100.0, rgb_overlap_consist=200.0)
+    elif wset == 'amass':
+        w.update(verts3d=1.0, pose_prior=2e-4, shape_prior=1.67e-4, joints3d_smooth=0.1)
+    elif wset == 'proxd':
+        w.update(points3d=1.0, joints2d=0.001, pose_prior=0.1, shape_prior=0.034, joints3d_smooth=100.0)
+    else:
+        raise ValueError(wset)
+    return w
+
+
+def make_stage12_params(B, T, seed=0, dtype=np.float32):
+    """Stage-I/II variables (motion_optimizer.py:66-77,224-283): per-frame trans / root_orient / latent_pose, betas."""
+    rng = np.random.RandomState(seed)
+    trans = np.zeros((B, T, 3)) + np.array([0.0, 0.1, 3.0]) + np.cumsum(rng.randn(B, T, 3) * 0.02, 1)
+    ro = np.zeros((B, T, 3)) + np.array([np.pi, 0.0, 0.0]) + rng.randn(B, T, 3) * 0.1
+    return {'trans': trans.astype(dtype), 'root_orient': ro.astype(dtype), 'betas': (rng.randn(B, 16) * 0.5).astype(dtype),
+            'latent_pose': (rng.randn(B, T, 32) * 0.5).astype(dtype)}
+
+
 def sample_point_cloud(verts, n_obs, seed=0, noise=0.01, outlier_frac=0.05, outlier_sigma=0.6):
     """Synthetic depth-camera cloud for the points3d energy: n_obs points per frame drawn from the given vertices
     (B,T,V,3) with Gaussian noise, a fraction of them pushed far away (what the bisquare weights must reject)."""

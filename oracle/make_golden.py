@@ -72,6 +72,54 @@ def run_case(c):
     return out
 
 
+CASES12 = {
+    'stage1_rgb': dict(wset='rgb', stage=0, optim_floor=True, B=4, T=6, seed=41, overlap=2),
+    'stage2_rgb': dict(wset='rgb', stage=1, optim_floor=True, B=4, T=6, seed=42, overlap=2),
+    'stage2_amass': dict(wset='amass', stage=1, optim_floor=False, B=2, T=7, seed=43, overlap=2),
+    'stage2_proxd': dict(wset='proxd', stage=1, optim_floor=True, B=2, T=5, seed=44, overlap=2, n_obs=80),
+}
+
+
+def run_case12(c):
+    """Stage-I/II closure of the unmodified reference (root_fit / smpl_fit) on per-frame variables."""
+    W12 = synth.stage12_weights(c['wset'])
+    W3 = synth.WEIGHT_SETS[c['wset']]
+    B, T = c['B'], c['T']
+    prob = synth.make_stage3_problem(B, T, seed=c['seed'], overlap=c['overlap'], cam=c['optim_floor'])
+    params = synth.make_stage12_params(B, T, seed=c['seed'] + 1)
+    keys = ('joints2d', 'floor_plane', 'seq_interval') if c['optim_floor'] else ('verts3d',)
+    if c['wset'] == 'proxd':
+        keys = ('joints2d', 'floor_plane')
+    ref, mo, _, _ = ref_closure.build(B, T, [W12, W12, W3], c['optim_floor'], prob['cam_mat'] if c['optim_floor'] else None)
+    obs = {k: torch.as_tensor(prob['obs'][k]) for k in keys}
+    if c['optim_floor']:
+        ref_closure.set_params12(mo, params, c['stage'])
+        with torch.no_grad():
+            _, _, inter = ref_closure.stage12_closure(ref, mo, {k: v.clone() for k, v in obs.items()}, c['stage'], backward=False)
+        j = torch.cat([inter['pred']['joints3d'], inter['pred']['joints3d_extra']], 2)[:, :, SMPL2OP].numpy()
+        rng = np.random.RandomState(c['seed'] + 100)
+        xy = j[..., :2] / j[..., 2:3] * np.asarray(synth.CAM_F) + np.asarray(synth.CAM_C) + rng.randn(*j.shape[:3], 2) * 2.0
+        obs['joints2d'] = obs['joints2d'].clone()
+        obs['joints2d'][..., :2] = torch.as_tensor(xy.astype(np.float32))
+        if W12.get('points3d', 0.0) > 0.0:
+            obs['points3d'] = torch.as_tensor(synth.sample_point_cloud(inter['pred']['points3d'].numpy(), c['n_obs'], seed=c['seed'] + 200))
+            keys = keys + ('points3d',)
+    names = ref_closure.set_params12(mo, params, c['stage'])
+    loss, stats, inter = ref_closure.stage12_closure(ref, mo, {k: v.clone() for k, v in obs.items()}, c['stage'])
+    out = {'loss': np.float32(loss.item())}
+    for k, v in stats.items():
+        out['stat_' + k] = np.float32(float(v))
+    for n in names:
+        out['grad_' + n] = getattr(mo, n).grad.numpy()
+    for k in keys:
+        out['obs_' + k] = obs[k].numpy()
+    out['pred_verts3d'] = inter['pred']['verts3d'].detach().numpy()
+    out['pred_joints3d'] = inter['pred']['joints3d'].detach().numpy()
+    out['meta'] = np.array([B, T, c['seed'], c['overlap'], c['stage'], int(c['optim_floor'])])
+    out['wset'] = np.array(c['wset'])
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -81,6 +129,12 @@ def main():
         if only and name not in only:
             continue
         out = run_case(c)
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+        print(name, 'loss', out['loss'], {k[5:]: float(v) for k, v in out.items() if k.startswith('stat_')})
+    for name, c in CASES12.items():
+        if only and name not in only:
+            continue
+        out = run_case12(c)
         np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
         print(name, 'loss', out['loss'], {k[5:]: float(v) for k, v in out.items() if k.startswith('stat_')})
 

@@ -85,9 +85,10 @@ def build(B, T, weights, optim_floor, cam_mat=None, humor_sd=None, gmm=None, vpo
     humor.eval()
     gmm = gmm if gmm is not None else synth.make_gmm()
     vposer = vposer if vposer is not None else synth.FakeVPoser()
-    w = dict(weights)
+    stage_w = [dict(x) for x in weights] if isinstance(weights, (list, tuple)) else [dict(weights)] * 3
+    w = {k: max(x[k] for x in stage_w) for k in stage_w[0]}
     mo = ref.motion_optimizer.MotionOptimizer(
-        dev, bm, 16, B, T, ['joints2d'] if optim_floor else ['verts3d'], [dict(w), dict(w), dict(w)],
+        dev, bm, 16, B, T, ['joints2d'] if optim_floor else ['verts3d'], [dict(x) for x in stage_w],
         vposer, humor, {'gmm': gmm}, optim_floor,
         None if cam_mat is None else torch.as_tensor(cam_mat),
         'bisquare', 4.6851, 100.0,
@@ -160,3 +161,29 @@ def stage3_closure(ref, mo, observed_data, nsteps=None, init_motion_scale=1.0, b
     inter = {'rollout': rollout, 'cam_rollout': cam_rollout, 'pred': pred, 'cam_pred': cam_pred,
              'body_pose0': cur_body_pose}
     return loss, stats, inter
+
+
+def set_params12(mo, params, stage):
+    """Stage-I/II variables with the reference's requires_grad pattern (motion_optimizer.py:224-228,276-280)."""
+    full = stage == 1
+    t = lambda k, g: torch.as_tensor(params[k]).clone().requires_grad_(g)
+    mo.trans, mo.root_orient = t('trans', True), t('root_orient', True)
+    mo.betas, mo.latent_pose = t('betas', full), t('latent_pose', full)
+    return ['trans', 'root_orient'] + (['betas', 'latent_pose'] if full else [])
+
+
+def stage12_closure(ref, mo, observed_data, stage, backward=True):
+    """The closure bodies of motion_optimizer.py:237-250 (stage 0) and :289-304 (stage 1), executed by the reference's own
+    methods on a reference MotionOptimizer."""
+    mo.fitting_loss.set_stage(stage)
+    body_pose = mo.latent2pose(mo.latent_pose)
+    pred, _ = mo.smpl_results(mo.trans, mo.root_orient, body_pose, mo.betas)
+    if stage == 1:
+        pred['latent_pose'] = mo.latent_pose
+        pred['betas'] = mo.betas
+        loss, stats = mo.fitting_loss.smpl_fit(observed_data, pred, mo.seq_len)
+    else:
+        loss, stats = mo.fitting_loss.root_fit(observed_data, pred)
+    if backward:
+        loss.backward()
+    return loss, stats, {'pred': pred, 'body_pose': body_pose}

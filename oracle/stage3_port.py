@@ -317,8 +317,10 @@ class Stage3Port:
         logp = -0.5 * (x.shape[1] * math.log(2 * math.pi) + maha) - logdet[None]
         return -torch.logsumexp(self.gmm_logw[None] + logp, 1).sum()
 
-    def motion_fit(self, obs, pred, cam_pred, p, z, prior, nsteps, init_scale, w):
-        """FittingLoss.motion_fit -> smpl_fit -> root_fit, fitting_loss.py:94-309."""
+    def motion_fit(self, obs, pred, cam_pred, p, z, prior, nsteps, init_scale, w, mode='motion'):
+        """FittingLoss.motion_fit -> smpl_fit -> root_fit, fitting_loss.py:94-309.  mode 'root' stops after root_fit (:94-179),
+        'smpl' after smpl_fit (:181-224), 'motion' runs all of motion_fit."""
+        smpl, motion = mode in ('smpl', 'motion'), mode == 'motion'
         st = {}
         loss = 0.0
         if 'joints3d' in obs and w['joints3d'] > 0:
@@ -349,19 +351,21 @@ class Stage3Port:
                     vel = vel + 0.5 * (((a[1:] - a[:-1]) - (c[1:] - c[:-1])) ** 2).sum()
             st['rgb_overlap_consist_verts3d_pos'], st['rgb_overlap_consist_verts3d_vel'] = pos, vel
             loss = loss + w['rgb_overlap_consist'] * (pos + vel)
-        if w['pose_prior'] > 0:
+        if smpl and w['pose_prior'] > 0:
             st['pose_prior'] = (cam_pred['latent_pose'] ** 2).sum()
             loss = loss + w['pose_prior'] * st['pose_prior']
-        if w['shape_prior'] > 0:
+        if smpl and w['shape_prior'] > 0:
             st['shape_prior'] = (p['betas'] ** 2).sum()
             loss = loss + w['shape_prior'] * nsteps * st['shape_prior']
-        if w['joints3d_smooth'] > 0:
+        if smpl and w['joints3d_smooth'] > 0:
             j = cam_pred['joints3d']
             st['joints3d_smooth'] = 0.5 * ((j[:, 1:] - j[:, :-1]) ** 2).sum()
             loss = loss + w['joints3d_smooth'] * st['joints3d_smooth']
-        if ov_on:
+        if smpl and ov_on:
             st['rgb_overlap_consist_betas'] = 0.5 * ((p['betas'][:-1] - p['betas'][1:]) ** 2).sum()
             loss = loss + w['rgb_overlap_consist'] * st['rgb_overlap_consist_betas']
+        if not motion:
+            return loss, st
         if w['motion_prior'] > 0:
             pm, pv = prior
             lp = -torch.log(torch.sqrt(pv)) - math.log(math.sqrt(2 * math.pi)) - (z - pm) ** 2 / (2 * pv)
@@ -399,6 +403,16 @@ class Stage3Port:
             st['rgb_overlap_consist_floor'] = 0.5 * ((fp[:-1] - fp[1:]) ** 2).sum()
             loss = loss + w['rgb_overlap_consist'] * st['rgb_overlap_consist_floor']
         return loss, st
+
+    # -- Stage I / II closures ---------------------------------------------------------------------
+    def closure12(self, p, obs, stage, weights):
+        """motion_optimizer.py:237-250 (stage 0, root_fit) / :289-304 (stage 1, smpl_fit).  p: trans (B,T,3), root_orient
+        (B,T,3), betas (B,16), latent_pose (B,T,32) leaf tensors; weights: that stage's column of the config."""
+        body_pose = self.latent2pose(p['latent_pose'])
+        pred = self.smpl_results(p['trans'], p['root_orient'], body_pose, p['betas'])
+        pred['latent_pose'] = p['latent_pose']
+        loss, st = self.motion_fit(obs, pred, pred, p, None, None, self.T, 1.0, dict(weights), mode='root' if stage == 0 else 'smpl')
+        return loss, st, {'pred': pred, 'body_pose': body_pose}
 
     # -- the closure -----------------------------------------------------------------------------
     def closure(self, p, obs, nsteps=None, init_motion_scale=1.0):

@@ -32,3 +32,17 @@ def check_against_golden(g, loss, stats, grads, loss_tol=2e-5, stat_tol=2e-4, gr
             got = np.asarray(grads[k[5:]].cpu() if hasattr(grads[k[5:]], 'cpu') else grads[k[5:]])
             err = np.abs(got - ref).max() / (np.abs(ref).max() + 1e-8)
             assert err < grad_tol, (k, err)
+
+
+CASES12 = ['stage1_rgb', 'stage2_rgb', 'stage2_amass', 'stage2_proxd']
+
+
+def load_case12(name):
+    """Stage-I/II fixtures of oracle/make_golden.py (run_case12): observations from the file, variables from the seed."""
+    g = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    B, T, seed, overlap, stage, of = [int(x) for x in g['meta']]
+    prob = synth.make_stage3_problem(B, T, seed=seed, overlap=overlap, cam=bool(of))
+    obs = {k[4:]: g[k] for k in g if k.startswith('obs_')}
+    wset = str(g['wset'])
+    return g, dict(B=B, T=T, stage=stage, optim_floor=bool(of), wset=wset, W12=synth.stage12_weights(wset),
+                   W3=synth.WEIGHT_SETS[wset], obs=obs, params=synth.make_stage12_params(B, T, seed=seed + 1), cam_mat=prob['cam_mat'])

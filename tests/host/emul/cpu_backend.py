@@ -1,0 +1,46 @@
+"""Test infrastructure: run the product's Python surfaces on CPU tensors against the kernel-executing CUDA runtime stand-in
+(tests/host/emul/cudart_emul.cpp).  Must be imported in a process started with LD_PRELOAD=<libcudart_emul.so>; `install`
+points the C-ABI loader at the `-cudart shared` link of the product objects and removes the product's "CUDA tensors only"
+guards FOR THIS TEST PROCESS ONLY.  The product has no CPU path of its own: without this harness every wrapper raises."""
+import os
+
+import numpy as np
+import torch
+
+
+def install(lib_path):
+    from humor_b200 import _ext, body_model
+    assert 'cudart_emul' in os.environ.get('LD_PRELOAD', ''), 'start the process with the emulating runtime preloaded'
+    _ext.LIB_PATH = lib_path
+    _ext._LIB = None
+    _ext.require_cuda = lambda *t: None
+    _ext.stream_ptr = lambda: None
+
+    def cpu_lbs_model(self, packed, device):
+        """LbsModel.__init__ for host memory: exact-fp32 forms only (no tensor-core planes, no fused tables)."""
+        self.device = torch.device('cpu')
+        self.t = {k: torch.as_tensor(v).contiguous() for k, v in packed.items() if isinstance(v, np.ndarray)}
+        s = _ext.HbLbsModel()
+        s.num_verts, s.v3_ld, s.wk, s.reserved = packed['num_verts'], packed['v3_ld'], packed['wk'], 0
+        for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_val', 'parents', 'extra_ids'):
+            setattr(s, k, self.t[k].data_ptr())
+        s.use_umma = 0
+        s.fused_nct, s.fused_wk = packed['fused_nct'], 0
+        s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
+        s.num_groups, s.max_depth = packed['num_groups'], packed['max_depth']
+        s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))
+        self.fused_wk = 0
+        self.ws_slot = 0
+        self.struct = s
+        self._ws, self._vlists = {}, {}
+
+    body_model.LbsModel.__init__ = cpu_lbs_model
+
+    def lbs_model(self):
+        if self._model is None:
+            self._model = body_model.LbsModel(self._packed, 'cpu')
+        return self._model
+
+    body_model.BodyModel.lbs_model = property(lbs_model)
+    body_model.BodyModel.set_precision = lambda self, mode: None
+    return _ext.lib()

@@ -1,0 +1,93 @@
+// Test infrastructure: a CUDA runtime stand-in (LD_PRELOADed into a child python process) that EXECUTES kernels on the CPU.
+// The product library is linked once more with `-cudart shared` (same nvcc-compiled host code: argument checks, workspace
+// carving, dispatch); every cudaLaunchKernel it issues is resolved here to the SAME kernel source compiled with g++ against
+// the SIMT shim (tests/host/shim) and run with the launch's grid/block on host memory.  "Device pointers" are host pointers.
+// Covers the SIMT kernels (lbs.cu, rot.cu, losses.cu, chamfer.cu); the tcgen05 kernels have their own emulation
+// (tests/host/shim/tc_emul.h, tests/test_host_tc.py) and are not wired in here (CPU runs use the exact-fp32 forms).
+// Not a product path: nothing in humor_b200/ references it; the product rejects CPU tensors unless a test patches that out.
+#include <cxxabi.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <map>
+#include <string>
+
+#define hb hb_emu          // the emulated kernels live in their own namespace: the library's host stubs keep `hb::`
+#include "../../../humor_b200/csrc/lbs.cu"
+#include "../../../humor_b200/csrc/rot.cu"
+#include "../../../humor_b200/csrc/losses.cu"
+#include "../../../humor_b200/csrc/chamfer.cu"
+#undef hb
+
+namespace {
+using Thunk = void (*)(dim3, dim3, void**);
+template <class T> T& arg(void** a, int i) { return *static_cast<T*>(a[i]); }
+typedef const float* cf;
+typedef const int* ci;
+#define A(T, i) arg<T>(a, i)
+#define RUN(...) shim::launch(g, b, [&] { __VA_ARGS__; })
+const std::map<std::string, Thunk>& registry() {
+  static const std::map<std::string, Thunk> r = {
+      {"hb::lbs_pose_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(float*, 11), A(float*, 12))); }},
+      {"hb::lbs_pose_warp_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_warp_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(float*, 11), A(float*, 12))); }},
+      {"hb::lbs_pose_bwd_warp_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_bwd_warp_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(cf, 8), A(cf, 9), A(int, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
+      {"hb::lbs_pose_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_bwd_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(cf, 8), A(cf, 9), A(int, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
+      {"hb::lbs_skin_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_fwd_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(cf, 3), A(cf, 4), A(ci, 5), A(int, 6), A(float*, 7), A(size_t, 8))); }},
+      {"hb::lbs_skin_apply_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_apply_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(float*, 6))); }},
+      {"hb::lbs_skin_group_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_group_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(float*, 6), A(int, 7))); }},
+      {"hb::lbs_gather_extra_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_gather_extra_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(float*, 3))); }},
+      {"hb::lbs_skin_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_bwd_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(cf, 3), A(ci, 4), A(int, 5), A(cf, 6), A(size_t, 7), A(float*, 8), A(float*, 9), A(float*, 10), A(int, 11), A(ci, 12), A(int, 13), A(cf, 14), A(size_t, 15))); }},
+      {"hb::rodrigues_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rodrigues_fwd_kernel(A(int, 0), A(cf, 1), A(float*, 2))); }},
+      {"hb::rodrigues_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rodrigues_bwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(float*, 3))); }},
+      {"hb::mat2aa_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::mat2aa_fwd_kernel(A(int, 0), A(cf, 1), A(float*, 2))); }},
+      {"hb::mat2aa_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::mat2aa_bwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(float*, 3))); }},
+      {"hb::fit_losses_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_losses_kernel(A(HbFitArgs, 0))); }},
+      {"hb::fit_reduce_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce_kernel(A(HbFitArgs, 0))); }},
+      {"hb::gmm_nll_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::gmm_nll_kernel(A(int, 0), A(int, 1), A(cf, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8))); }},
+      {"hb::chamfer_nn_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_nn_kernel(A(int, 0), A(cf, 1), A(int, 2), A(cf, 3), A(float*, 4), A(int*, 5))); }},
+      {"hb::chamfer_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_bwd_kernel(A(int, 0), A(cf, 1), A(int, 2), A(cf, 3), A(cf, 4), A(ci, 5), A(cf, 6), A(ci, 7), A(float*, 8), A(float*, 9))); }},
+      {"hb::chamfer_fill_zero_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_fill_zero_kernel(A(size_t, 0), A(float*, 1), A(int*, 2))); }},
+  };
+  return r;
+}
+long long g_launches = 0;
+int run_kernel(const void* f, dim3 g, dim3 b, void** args) {
+  Dl_info i;
+  std::string name = "?";
+  if (dladdr(f, &i) && i.dli_sname) {
+    int st = 0;
+    char* d = abi::__cxa_demangle(i.dli_sname, nullptr, nullptr, &st);
+    name = d ? d : i.dli_sname;
+    std::free(d);
+  }
+  const size_t paren = name.find('(');
+  if (paren != std::string::npos) name.resize(paren);
+  if (name.rfind("void ", 0) == 0) name = name.substr(5);
+  const auto it = registry().find(name);
+  if (it == registry().end()) {
+    std::fprintf(stderr, "cudart_emul: kernel '%s' has no CPU emulation registered\n", name.c_str());
+    return 98;                                   // cudaErrorInvalidDeviceFunction
+  }
+  if (getenv("HB_EMUL_TRACE")) std::fprintf(stderr, "EMUL %s grid=(%u,%u,%u) block=%u\n", name.c_str(), g.x, g.y, g.z, b.x);
+  it->second(g, b, args);
+  ++g_launches;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+int cudaLaunchKernel(const void* f, dim3 g, dim3 b, void** a, size_t, void*) { return run_kernel(f, g, b, a); }
+struct EmulLaunchConfig { dim3 grid; dim3 block; size_t dynamicSmemBytes; void* stream; void* attrs; unsigned numAttrs; };   // cudaLaunchConfig_t
+int cudaLaunchKernelExC(const EmulLaunchConfig* c, const void* f, void** a) { return run_kernel(f, c->grid, c->block, a); }
+int cudaPeekAtLastError() { return 0; }
+// the shim header already has a static cudaGetLastError for the kernel sources: export the runtime symbol under an asm label
+int emul_get_last_error() __asm__("cudaGetLastError");
+int emul_get_last_error() { return 0; }
+int cudaFuncSetAttribute(const void*, int, int) { return 0; }
+int cudaGetDevice(int* d) { *d = 0; return 0; }
+int cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return 0; }
+int cudaMemsetAsync(void* p, int v, size_t n, void*) { std::memset(p, v, n); return 0; }
+// tcgen05 path unavailable in this runtime: the tensor-map encoder cannot be resolved
+int cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, int* q) { *fn = nullptr; if (q) *q = 1; return 0; }
+long long hb_emul_launches() { return g_launches; }
+}

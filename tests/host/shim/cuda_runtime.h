@@ -43,6 +43,8 @@ inline std::barrier<>* block_bar = nullptr;
 inline std::vector<std::unique_ptr<std::barrier<>>> warp_bars;
 inline thread_local int t_lin = 0;
 inline std::vector<uint32_t> warp_xchg;     // one slot per thread: shuffle exchange area
+alignas(1024) inline float dyn_smem_buf[64 * 1024];    // 256 KB: dynamic shared memory of the running block
+inline float* dyn_smem_f32() { return dyn_smem_buf; }
 inline void sync_block() { block_bar->arrive_and_wait(); }
 inline void sync_warp() { warp_bars[t_lin / 32]->arrive_and_wait(); }
 
@@ -84,6 +86,7 @@ void launch(dim3 grid, dim3 block, F body) {
 #define __forceinline__ inline
 #define __restrict__
 #define __shared__ static
+#define __constant__ static const
 #define __launch_bounds__(...)
 #define __syncthreads() shim::sync_block()
 #define __syncwarp(...) shim::sync_warp()

@@ -1,0 +1,64 @@
+"""The PRODUCT on CPU tensors: the library's own nvcc-compiled host code (argument checks, workspace carving, kernel dispatch)
+linked with `-cudart shared`, run in a child process whose CUDA runtime is tests/host/emul/cudart_emul.cpp — every kernel
+launch executes the same kernel source compiled with g++ against the SIMT shim.  Python side: the product's classes with the
+"CUDA tensors only" guards patched out for that child process (tests/host/emul/cpu_backend.py).
+
+* BodyModel forward / reverse against the torch oracle.
+* Stage-I (root_fit) and Stage-II (smpl_fit) closures of MotionOptimizer against fixtures of the UNMODIFIED reference
+  (RGB, AMASS key-vertex and PROX-RGBD/point-cloud configurations): loss, every energy term, every gradient."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope='module')
+def emul(built_lib, tmp_path_factory):
+    d = tmp_path_factory.mktemp('emul')
+    rt = str(d / 'libcudart_emul.so')
+    lib = str(d / 'libhumor_b200_emul.so')
+    subprocess.check_call(['g++', '-O1', '-std=c++20', '-pthread', '-shared', '-fPIC', '-I' + os.path.join(HERE, 'host', 'shim'),
+                           '-DHB_HOST_SHIM', os.path.join(HERE, 'host', 'emul', 'cudart_emul.cpp'), '-o', rt, '-ldl'])
+    objs = sorted(glob.glob(os.path.join(ROOT, 'humor_b200', 'build', '*.o')))
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    subprocess.check_call([nvcc, '-shared', '-cudart', 'shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    return rt, lib
+
+
+def run_probe(emul, script, *args):
+    rt, lib = emul
+    env = dict(os.environ, LD_PRELOAD=rt, CUDA_VISIBLE_DEVICES='')
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'host', 'emul', script), ROOT, lib] + list(args),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=900)
+    lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    assert r.returncode == 0 and lines, (r.stdout[-1500:], r.stderr[-3000:])
+    return json.loads(lines[-1])
+
+
+def test_body_model_forward_and_reverse(emul):
+    out = run_probe(emul, 'probe_lbs.py')
+    assert out['v_err'] < 2e-5 and out['J_err'] < 2e-5          # metres (bound 1e-4)
+    for k in ('g_root_orient', 'g_pose_body', 'g_betas', 'g_trans'):
+        assert out[k] < 1e-4, (k, out[k])
+
+
+@pytest.mark.parametrize('name', ['stage1_rgb', 'stage2_rgb', 'stage2_amass', 'stage2_proxd'])
+def test_stage12_closure_matches_reference_golden(emul, name):
+    out = run_probe(emul, 'probe_stage12.py', name)
+    g = np.load(os.path.join(HERE, 'golden', name + '.npz'))
+    ref_loss = float(g['loss'])
+    assert abs(out['loss'] - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+    stats = {k[5:]: float(g[k]) for k in g.files if k.startswith('stat_')}
+    assert set(stats) == set(out['stats']), (sorted(stats), sorted(out['stats']))
+    for k, v in stats.items():
+        assert abs(out['stats'][k] - v) <= 1e-4 * max(1.0, abs(v)), (k, out['stats'][k], v)
+    assert out['verts_err'] < 1e-5
+    for k, e in out['grad_err'].items():
+        assert e < 1e-4, (k, e)

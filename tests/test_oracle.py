@@ -23,6 +23,22 @@ def test_port_matches_reference_golden(name):
     assert np.abs(inter['rollout']['cond_prior'][0].detach().numpy() - g['cond_prior_mean']).max() < 1e-5
 
 
+@pytest.mark.parametrize('name', ['stage1_rgb', 'stage2_rgb', 'stage2_amass', 'stage2_proxd'])
+def test_port_stage12_matches_reference_golden(name):
+    """Stage-I (root_fit) / Stage-II (smpl_fit) closures of the port against fixtures of the unmodified reference."""
+    from tests.golden_util import load_case12
+    g, c = load_case12(name)
+    port = U.build_port(c['B'], c['T'], c['W3'], c['optim_floor'], {'cam_mat': c['cam_mat']})
+    names = ['trans', 'root_orient'] + (['betas', 'latent_pose'] if c['stage'] == 1 else [])
+    p = {k: torch.as_tensor(v).clone().requires_grad_(k in names) for k, v in c['params'].items()}
+    obs = {k: torch.as_tensor(v).clone() for k, v in c['obs'].items()}
+    loss, stats, inter = port.closure12(p, obs, c['stage'], c['W12'])
+    loss.backward()
+    st = {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in stats.items()}
+    check_against_golden(g, float(loss.detach()), st, {k: p[k].grad for k in names}, loss_tol=2e-6, stat_tol=2e-5, grad_tol=1e-4)
+    assert np.abs(inter['pred']['verts3d'].detach().numpy() - g['pred_verts3d']).max() < 1e-5
+
+
 @pytest.mark.skipif(not ref_import.available(), reason='/root/reference is only present in the build container')
 @pytest.mark.parametrize('optim_floor,nsteps,scale', [(True, None, 1.0), (True, 5, 1.0), (False, None, 2.4)])
 def test_port_matches_live_reference(optim_floor, nsteps, scale):

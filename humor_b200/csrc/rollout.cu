@@ -58,6 +58,14 @@ static Tape carve(float* base, int B, int S) {
   return t;
 }
 
+// programmatic dependent launch (device) / nothing (tests/host CPU build of the kernels)
+#ifdef HB_HOST_SHIM
+static inline void pdl_launch_dependents() {}
+static inline void pdl_wait() {}
+#else
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 __device__ __forceinline__ float hi11(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // write v as (hi, lo) planes when a lo plane exists, else exactly
 __device__ __forceinline__ void put_split(float* hi, float* lo, size_t i, float v) {
@@ -109,8 +117,8 @@ glue_fwd_kernel(int B, int S, int t, const float* __restrict__ xin, const float*
                 float* xnext, float* xnext_hi, float* xnext_lo, float* world, float* Gnext, float* h1, float* h2, float* h3,
                 float* h1_lo, float* h2_lo, float* h3_lo) {
   __shared__ float s_x[GLUE_WARPS][340], s_r[GLUE_WARPS][216], s_n[GLUE_WARPS][340], s_w[GLUE_WARPS][348];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: let the next GEMM start its prologue
-  asm volatile("griddepcontrol.wait;" ::: "memory");                // ... and wait for the GEMM that produced `raw`
+  pdl_launch_dependents();   // PDL: let the next GEMM start its prologue
+  pdl_wait();                // ... and wait for the GEMM that produced `raw`
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * GLUE_WARPS + wid;
   if (b >= B) return;
@@ -210,8 +218,8 @@ glue_bwd_kernel(int B, int S, int t, int have_next, const float* __restrict__ xi
                 const float* __restrict__ dGn_g, float* dG, float* dt2j, float* draw, float* draw_hi, float* draw_lo, float* dz) {
   __shared__ float s_x[GLUE_WARPS][340], s_r[GLUE_WARPS][216], s_dn[GLUE_WARPS][340], s_dw[GLUE_WARPS][348],
       s_dx[GLUE_WARPS][340], s_dr[GLUE_WARPS][224];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_launch_dependents();
+  pdl_wait();
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * GLUE_WARPS + wid;
   if (b >= B) return;
@@ -406,6 +414,7 @@ static GemmEpi epi_bias(const float* bias) {
 
 }  // namespace hb
 
+#ifndef HB_HOST_SHIM   // host side of the C-ABI (launch syntax): device builds only
 using namespace hb;
 
 extern "C" size_t humor_rollout_workspace_bytes(int B, int S) { return carve(nullptr, B, S).total * sizeof(float); }
@@ -599,3 +608,4 @@ extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* w
   if (launches) *launches = nl;
   return HB_OK;
 }
+#endif  // HB_HOST_SHIM

@@ -43,4 +43,16 @@ def install(lib_path):
 
     body_model.BodyModel.lbs_model = property(lbs_model)
     body_model.BodyModel.set_precision = lambda self, mode: None
+
+    from humor_b200 import humor_model
+
+    def packed(self):
+        """HumorModel.packed for host memory: exact-fp32 kernels only."""
+        dev = self.decoder.net[0].weight.device
+        if self._packed is None or self._packed.device != dev:
+            self._packed = humor_model.PackedWeights(self.decoder, self.prior_net, dev)
+        self._packed.struct.use_umma = 0
+        return self._packed
+
+    humor_model.HumorModel.packed = packed
     return _ext.lib()

@@ -17,6 +17,7 @@
 #include "../../../humor_b200/csrc/rot.cu"
 #include "../../../humor_b200/csrc/losses.cu"
 #include "../../../humor_b200/csrc/chamfer.cu"
+#include "../../../humor_b200/csrc/rollout.cu"
 #undef hb
 
 namespace {
@@ -44,6 +45,15 @@ const std::map<std::string, Thunk>& registry() {
       {"hb::fit_losses_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_losses_kernel(A(HbFitArgs, 0))); }},
       {"hb::fit_reduce_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce_kernel(A(HbFitArgs, 0))); }},
       {"hb::gmm_nll_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::gmm_nll_kernel(A(int, 0), A(int, 1), A(cf, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8))); }},
+      {"hb::rollout_init_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rollout_init_kernel(A(int, 0), A(int, 1), A(cf, 2), A(cf, 3), A(float*, 4), A(float*, 5), A(float*, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(float*, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
+      {"hb::glue_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::glue_fwd_kernel(A(int, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(float*, 8), A(float*, 9), A(float*, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14), A(float*, 15), A(float*, 16), A(float*, 17), A(float*, 18))); }},
+      {"hb::glue_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::glue_bwd_kernel(A(int, 0), A(int, 1), A(int, 2), A(int, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(cf, 8), A(cf, 9), A(cf, 10), A(cf, 11), A(cf, 12), A(cf, 13), A(cf, 14), A(cf, 15), A(cf, 16), A(float*, 17), A(float*, 18), A(cf, 19), A(float*, 20), A(float*, 21), A(float*, 22), A(float*, 23), A(float*, 24), A(float*, 25))); }},
+      {"hb::rollout_bwd_final_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rollout_bwd_final_kernel(A(int, 0), A(int, 1), A(cf, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(cf, 8), A(cf, 9), A(cf, 10), A(cf, 11), A(float*, 12), A(float*, 13))); }},
+#define GEMM_THUNK(BM, BN, BK, NSM, NSN, EPI)                                                                                   \
+      {"hb::gemm_tn_kernel<" #BM ", " #BN ", " #BK ", " #NSM ", " #NSN ", " #EPI ">", [](dim3 g, dim3 b, void** a) {            \
+         RUN((hb_emu::gemm_tn_kernel<BM, BN, BK, NSM, NSN, EPI>(A(cf, 0), A(int, 1), A(cf, 2), A(int, 3), A(float*, 4), A(int, 5), A(int, 6), A(int, 7), A(int, 8), A(hb_emu::GemmEpi, 9)))); }},
+      GEMM_THUNK(128, 128, 16, 2, 2, 0) GEMM_THUNK(128, 128, 16, 2, 2, 1) GEMM_THUNK(128, 128, 16, 2, 2, 2)
+      GEMM_THUNK(32, 64, 32, 1, 1, 0) GEMM_THUNK(32, 64, 32, 1, 1, 1) GEMM_THUNK(32, 64, 32, 1, 1, 2)
       {"hb::chamfer_nn_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_nn_kernel(A(int, 0), A(cf, 1), A(int, 2), A(cf, 3), A(float*, 4), A(int*, 5))); }},
       {"hb::chamfer_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_bwd_kernel(A(int, 0), A(cf, 1), A(int, 2), A(cf, 3), A(cf, 4), A(ci, 5), A(cf, 6), A(ci, 7), A(float*, 8), A(float*, 9))); }},
       {"hb::chamfer_fill_zero_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_fill_zero_kernel(A(size_t, 0), A(float*, 1), A(int*, 2))); }},

@@ -62,3 +62,22 @@ def test_stage12_closure_matches_reference_golden(emul, name):
     assert out['verts_err'] < 1e-5
     for k, e in out['grad_err'].items():
         assert e < 1e-4, (k, e)
+
+
+@pytest.mark.parametrize('name', ['stage3_rgb_phase1', 'stage3_proxd'])
+def test_stage3_closure_matches_reference_golden(emul, name):
+    """The WHOLE Stage-III closure of the product (VPoser decode, cam->prior, CVAE rollout forward + BPTT on the exact-fp32
+    kernels, SMPL+H LBS, fused energies, GMM prior, chamfer/points3d for the PROX-RGBD case) on the CPU through the emulated
+    kernels, against fixtures of the unmodified reference.  (stage3_rgb / stage3_amass / stage3_rgb_refine pass the same way;
+    two cases keep the CPU suite short: `python tests/host/emul/probe_stage3.py` runs any of them.)"""
+    out = run_probe(emul, 'probe_stage3.py', name)
+    g = np.load(os.path.join(HERE, 'golden', name + '.npz'))
+    ref_loss = float(g['loss'])
+    assert abs(out['loss'] - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+    for k in g.files:
+        if k.startswith('stat_'):
+            v = float(g[k])
+            assert abs(out['stats'][k[5:]] - v) <= 1e-4 * max(1.0, abs(v)), (k, out['stats'][k[5:]], v)
+    assert out['verts_err'] < 1e-5 and out['trans_err'] < 1e-5 and out['prior_mean_err'] < 1e-5
+    for k, e in out['grad_err'].items():
+        assert e < 1e-4, (k, e)

@@ -81,3 +81,30 @@ def test_stage3_closure_matches_reference_golden(emul, name):
     assert out['verts_err'] < 1e-5 and out['trans_err'] < 1e-5 and out['prior_mean_err'] < 1e-5
     for k, e in out['grad_err'].items():
         assert e < 1e-4, (k, e)
+
+
+RUN_TOL = {'trans': 2e-5, 'root_orient': 2e-5, 'pose_body': 2e-5, 'betas': 2e-5, 'latent_pose': 2e-5, 'latent_motion': 2e-4,
+           'floor_plane': 5e-5, 'stage3_verts3d': 5e-5, 'stage1_joints3d': 2e-5, 'stage2_joints3d': 2e-5}
+
+
+def check_run_result(got, g):
+    for k, tol in RUN_TOL.items():
+        assert np.abs(got[k] - g[k]).max() <= tol, (k, float(np.abs(got[k] - g[k]).max()))
+    assert np.array_equal(got['contacts'], g['contacts'])
+
+
+@pytest.mark.skipif(not os.environ.get('HB_SLOW_TESTS'), reason='~6 min on the CPU emulation: set HB_SLOW_TESTS=1')
+def test_run_end_to_end_matches_reference_run(emul, tmp_path):
+    """MotionOptimizer.run — Stage I, Stage II, Stage-III initialisation (posterior encoder, finite-difference velocities),
+    Stage III with its three phases, L-BFGS with strong-Wolfe — of the product on the CPU emulation against the result of the
+    UNMODIFIED reference's run() on the same problem (tests/golden/run_rgb.npz, oracle/make_golden_run.py).
+    Measured: trans 6e-7, root_orient 1e-6, pose_body 1e-6, betas 3e-7, latent_motion 2e-5, contacts identical."""
+    from oracle.make_golden_run import CFG
+    out = str(tmp_path / 'run.npz')
+    rt, lib = emul
+    env = dict(os.environ, LD_PRELOAD=rt, CUDA_VISIBLE_DEVICES='')
+    args = [str(x) for x in (CFG['B'], CFG['T'], CFG['seed'], *CFG['num_iter'], CFG['lbfgs_max_iter'])]
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'host', 'emul', 'probe_run.py'), ROOT, lib, out] + args,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=3000)
+    assert r.returncode == 0, r.stderr[-3000:]
+    check_run_result(np.load(out), np.load(os.path.join(HERE, 'golden', 'run_rgb.npz')))

@@ -1,0 +1,34 @@
+"""End-to-end on the device: MotionOptimizer.run (three stages, library L-BFGS, Stage-III initialisation, exact-fp32 kernels,
+eager launches) against the result of the UNMODIFIED reference's run() on the same seeded problem
+(tests/golden/run_rgb.npz).  The same comparison passes on the CPU emulation (tests/test_emul_product.py, HB_SLOW_TESTS=1)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from humor_b200 import synth
+from tests import util_stage3 as U
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_run_end_to_end_matches_reference_run():
+    from oracle.make_golden_run import CFG
+    from tests.test_emul_product import check_run_result
+    prob = synth.make_stage3_problem(CFG['B'], CFG['T'], seed=CFG['seed'], overlap=CFG['overlap'], cam=True)
+    W12, W3 = synth.stage12_weights('rgb'), synth.RGB_STAGE3_WEIGHTS
+    mo = U.build_product(CFG['B'], CFG['T'], W3, True, prob, contact_refine_only=True)
+    mo.fitting_loss.all_stage_loss_weights = [dict(W12), dict(W12), dict(W3)]
+    mo.fitting_loss.set_stage(0)
+    mo.set_precision('exact')
+    mo.use_cuda_graph = False
+    mo.stage3_tune_init_num_frames, mo.stage3_tune_init_freeze_start, mo.stage3_tune_init_freeze_end = CFG['tune_init']
+    obs = {k: torch.as_tensor(v).cuda() for k, v in prob['obs'].items() if k in U.obs_keys(True)}
+    res, stages = mo.run(obs, num_iter=list(CFG['num_iter']), lbfgs_max_iter=CFG['lbfgs_max_iter'])
+    got = {k: v.detach().cpu().numpy() for k, v in res.items()}
+    for s in ('stage1', 'stage2'):
+        got[s + '_joints3d'] = stages[s]['joints3d'].detach().cpu().numpy()
+    got['stage3_verts3d'] = stages['stage3']['verts3d'].detach().cpu().numpy()
+    check_run_result(got, np.load(os.path.join(HERE, 'golden', 'run_rgb.npz')))

@@ -108,3 +108,30 @@ def test_run_end_to_end_matches_reference_run(emul, tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=3000)
     assert r.returncode == 0, r.stderr[-3000:]
     check_run_result(np.load(out), np.load(os.path.join(HERE, 'golden', 'run_rgb.npz')))
+
+
+@pytest.mark.skipif(not os.environ.get('HB_SLOW_TESTS'), reason='~5 min on the CPU emulation: set HB_SLOW_TESTS=1')
+def test_sharded_run_matches_single_process_run(emul, tmp_path):
+    """SURVEY.md 8(e) end to end: MotionOptimizer.run with the sub-sequences sharded over 2 gloo ranks — neighbour halo
+    exchange of the overlap energies in all three stages + the joint L-BFGS (all-reduced inner products) — against the same
+    run in one process.  Measured: every output within 8e-6 (trans 1e-6, latent_motion 1e-6, contacts identical)."""
+    rt, lib = emul
+    env = dict(os.environ, LD_PRELOAD=rt, CUDA_VISIBLE_DEVICES='')
+    probe = os.path.join(HERE, 'host', 'emul', 'probe_run_dist.py')
+    port = 24000 + (os.getpid() % 2000)
+    tail = ['4', '6', '61', '1', '1', '2', '2']                  # B_total T seed num_iter x3 lbfgs_max_iter
+    outs = [str(tmp_path / f'r{r}.npz') for r in range(2)] + [str(tmp_path / 'single.npz')]
+    procs = [subprocess.Popen([sys.executable, probe, ROOT, lib, outs[r], str(r), '2', str(port)] + tail, env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    procs.append(subprocess.Popen([sys.executable, probe, ROOT, lib, outs[2], '0', '1', '0'] + tail, env=env,
+                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        so, se = p.communicate(timeout=3000)
+        assert p.returncode == 0, se[-3000:]
+    r0, r1, single = (np.load(o) for o in outs)
+    for k in single.files:
+        both = np.concatenate([r0[k], r1[k]], 0)
+        if k == 'contacts':
+            assert np.array_equal(both, single[k])
+        else:
+            assert np.abs(both - single[k]).max() < 5e-5, (k, float(np.abs(both - single[k]).max()))

@@ -27,6 +27,14 @@
 #endif
 
 namespace hb {
+// programmatic dependent launch (device) / nothing to order (tests/host CPU build of the kernels)
+#ifdef HB_HOST_SHIM
+static inline void pdl_launch_dependents() {}
+static inline void pdl_wait() {}
+#elif defined(__CUDACC__)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 }  // namespace hb

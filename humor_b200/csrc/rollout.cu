@@ -58,14 +58,6 @@ static Tape carve(float* base, int B, int S) {
   return t;
 }
 
-// programmatic dependent launch (device) / nothing (tests/host CPU build of the kernels)
-#ifdef HB_HOST_SHIM
-static inline void pdl_launch_dependents() {}
-static inline void pdl_wait() {}
-#else
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#endif
 __device__ __forceinline__ float hi11(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // write v as (hi, lo) planes when a lo plane exists, else exactly
 __device__ __forceinline__ void put_split(float* hi, float* lo, size_t i, float v) {

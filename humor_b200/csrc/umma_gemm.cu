@@ -9,6 +9,7 @@
 
 namespace hb {
 
+#ifndef HB_HOST_SHIM   // host side (TMA descriptors, launches): device builds only
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -161,6 +162,8 @@ cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf
   return cudaGetLastError();
 }
 
+#endif  // HB_HOST_SHIM
+
 __global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -171,6 +174,7 @@ __global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict
     reinterpret_cast<float4*>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
   }
 }
+#ifndef HB_HOST_SHIM
 cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
   if (n % 4) return cudaErrorInvalidValue;
   const size_t n4 = n / 4;
@@ -181,7 +185,9 @@ cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cu
   return cudaGetLastError();
 }
 
+#endif  // HB_HOST_SHIM
 }  // namespace hb
+#ifndef HB_HOST_SHIM
 using namespace hb;
 
 // Test / utility entry point: C = A * B^T (+bias) in fp32-level accuracy on the tensor cores.
@@ -204,3 +210,4 @@ extern "C" int humor_umma_gemm(const float* A, int lda, const float* B, int ldb,
   HB_CUDA(launch_umma_gemm3(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, C, nullptr, nullptr, ldc, EPI_BIAS, ep, st));
   return HB_OK;
 }
+#endif  // HB_HOST_SHIM

@@ -182,7 +182,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // steps have only M = sub-sequences-per-GPU rows, i.e. ~32 output tiles: splitting K four ways puts 128 CTAs on the
 // chip and shortens each CTA's dependent TMA->MMA chain 4x.  Partials meet in the leader's (rank 0) shared memory
 // through DSMEM stores between two cluster barriers; only the leader runs the epilogue.
-#ifndef HB_HOST_SHIM   // split-K clusters / programmatic dependent launch: device only
+#ifdef HB_HOST_SHIM     // tests/host: single-CTA emulation; cluster instantiations (KS > 1) compile but must not run
+using tcemu::cluster_ctarank; using tcemu::cluster_sync_all; using tcemu::map_to_cta; using tcemu::st_cluster_v4;
+using tcemu::ld_shared_v4;
+#else
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -193,6 +201,7 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem, uint32_t ran
 __device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+#endif
 constexpr int UM_RED_LD = 68;      // floats per row of a partial tile in the leader's smem (64 + pad, float4-aligned)
 
 template <int BN, int EPI, int KS>
@@ -204,7 +213,7 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   static_assert(BN == 128 || BN == 64, "epilogue is written for 64- or 128-column tiles");
   using SM = UmmaSmem<BN>;
   constexpr int UM_STAGES = SM::STAGES;
-  extern __shared__ uint8_t smem_raw[];
+  HB_DYN_SMEM(smem_raw);
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t bars = base + UM_STAGES * SM::STAGE;          // full[3] | empty[3] | tfull[2] | tempty[2] | tmem_ptr
@@ -222,22 +231,21 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
   // programmatic dependent launch: the next kernel of the chain may be scheduled now and run ITS prologue (barrier
   // init, TMEM allocation) under this kernel's tail; ours ran under the predecessor's and waits below before reading.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"((uint32_t)(2 * BN)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(tptr, (uint32_t)(2 * BN));
+    tmem_relinquish();
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
-  asm volatile("griddepcontrol.wait;" ::: "memory");            // predecessor grid complete, its writes visible
+  tc_fence_after();
+  const uint32_t tmem_base = ld_shared_u32(tptr);
+  pdl_wait();                                                   // predecessor grid complete, its writes visible
 
   if (warp == 0) {
     if (lane == 0) {
@@ -261,14 +269,14 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       for (int c = 0; c < nchunk; ++c) {
         const int buf = c & 1;
         mbar_wait(tempty0 + 8 * buf, ((c >> 1) & 1) ^ 1);      // epilogue has drained this TMEM buffer
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_fence_after();
         const uint32_t tacc = tmem_base + buf * BN;
         const int kb_end = min(nkb, (c + 1) * UM_CHUNK);
         for (int kb = c * UM_CHUNK; kb < kb_end; ++kb) {
           const int s = kb % UM_STAGES;
           const uint32_t ph = (kb / UM_STAGES) & 1;
           mbar_wait(full0 + 8 * s, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          tc_fence_after();
           const uint32_t st = base + s * SM::STAGE;
 #pragma unroll
           for (int k = 0; k < UM_BK / 8; ++k) {                // one UMMA consumes K = 8 tf32 = 32 bytes
@@ -298,7 +306,7 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     for (int c = 0; c < nchunk; ++c) {
       const int buf = c & 1;
       mbar_wait(tfull0 + 8 * buf, (c >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float t[32];
@@ -306,7 +314,7 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[c0 + j] += t[j];
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
@@ -324,8 +332,7 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           const uint32_t src = base + (uint32_t)((r * UM_BM + q * 32 + lane) * UM_RED_LD) * 4u;
 #pragma unroll
           for (int j = 0; j < BN; j += 4) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + j * 4));
+            const float4 v = ld_shared_v4(src + j * 4);
             acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
           }
         }
@@ -370,13 +377,11 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       }
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    tmem_dealloc(tmem_base, (uint32_t)(2 * BN));
   }
 }
-
-#endif  // HB_HOST_SHIM (umma_gemm3_kernel)
 
 }  // namespace hb

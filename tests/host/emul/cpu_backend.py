@@ -17,19 +17,29 @@ def install(lib_path):
     _ext.stream_ptr = lambda: None
 
     def cpu_lbs_model(self, packed, device):
-        """LbsModel.__init__ for host memory: exact-fp32 forms only (no tensor-core planes, no fused tables)."""
+        """LbsModel.__init__ for host memory (same layouts as the product's constructor, body_model.py:LbsModel)."""
         self.device = torch.device('cpu')
         self.t = {k: torch.as_tensor(v).contiguous() for k, v in packed.items() if isinstance(v, np.ndarray)}
         s = _ext.HbLbsModel()
         s.num_verts, s.v3_ld, s.wk, s.reserved = packed['num_verts'], packed['v3_ld'], packed['wk'], 0
         for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_val', 'parents', 'extra_ids'):
             setattr(s, k, self.t[k].data_ptr())
-        s.use_umma = 0
+        split = lambda x: ((x.view(torch.int32) & -8192).view(torch.float32).contiguous(),)
+        bt = torch.zeros(packed['v3_ld'], 224)
+        bt[:, :208] = self.t['blend_t']
+        hi = split(bt)[0]
+        self.t['blend_t_hi'], self.t['blend_t_lo'] = hi, (bt - hi).contiguous()
+        fh = split(self.t['fblend'])[0]
+        self.t['fblend_hi'], self.t['fblend_lo'] = fh, (self.t['fblend'] - fh).contiguous()
+        s.blend_t_hi, s.blend_t_lo = self.t['blend_t_hi'].data_ptr(), self.t['blend_t_lo'].data_ptr()
+        s.fblend_hi, s.fblend_lo = self.t['fblend_hi'].data_ptr(), self.t['fblend_lo'].data_ptr()
+        s.fw_idx, s.fw_val = self.t['fw_idx'].data_ptr(), self.t['fw_val'].data_ptr()
+        s.use_umma = 1 if os.environ.get('HB_EMUL_TENSOR') else 0
         s.fused_nct, s.fused_wk = packed['fused_nct'], 0
         s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
         s.num_groups, s.max_depth = packed['num_groups'], packed['max_depth']
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))
-        self.fused_wk = 0
+        self.fused_wk = packed['fused_wk']
         self.ws_slot = 0
         self.struct = s
         self._ws, self._vlists = {}, {}
@@ -42,7 +52,7 @@ def install(lib_path):
         return self._model
 
     body_model.BodyModel.lbs_model = property(lbs_model)
-    body_model.BodyModel.set_precision = lambda self, mode: None
+    body_model.BodyModel.set_precision = lambda self, mode: setattr(self.lbs_model.struct, 'use_umma', 1 if mode == 'tensor' else 0)
 
     from humor_b200 import humor_model
 
@@ -51,7 +61,7 @@ def install(lib_path):
         dev = self.decoder.net[0].weight.device
         if self._packed is None or self._packed.device != dev:
             self._packed = humor_model.PackedWeights(self.decoder, self.prior_net, dev)
-        self._packed.struct.use_umma = 0
+        self._packed.struct.use_umma = 1 if (self.precision == 'tensor' and os.environ.get('HB_EMUL_TENSOR')) else 0
         return self._packed
 
     humor_model.HumorModel.packed = packed

@@ -2,8 +2,10 @@
 // The product library is linked once more with `-cudart shared` (same nvcc-compiled host code: argument checks, workspace
 // carving, dispatch); every cudaLaunchKernel it issues is resolved here to the SAME kernel source compiled with g++ against
 // the SIMT shim (tests/host/shim) and run with the launch's grid/block on host memory.  "Device pointers" are host pointers.
-// Covers the SIMT kernels (lbs.cu, rot.cu, losses.cu, chamfer.cu); the tcgen05 kernels have their own emulation
-// (tests/host/shim/tc_emul.h, tests/test_host_tc.py) and are not wired in here (CPU runs use the exact-fp32 forms).
+// Covers every SIMT kernel (lbs.cu, rot.cu, losses.cu, chamfer.cu, rollout.cu) and, on the functional tcgen05 / TMA / TMEM
+// emulation of tests/host/shim/tc_emul.h, the single-CTA tcgen05 kernels (umma_gemm3_kernel<.,.,1>, lbs_fused_kernel,
+// lbs_blend_kernel); cuTensorMapEncodeTiled is emulated too, so the library's own descriptor code runs.  Thread-block
+// clusters are not emulated: run with HB_NO_SPLITK=1.
 // Not a product path: nothing in humor_b200/ references it; the product rejects CPU tensors unless a test patches that out.
 #include <cxxabi.h>
 #include <dlfcn.h>
@@ -18,6 +20,7 @@
 #include "../../../humor_b200/csrc/losses.cu"
 #include "../../../humor_b200/csrc/chamfer.cu"
 #include "../../../humor_b200/csrc/rollout.cu"
+#include "../../../humor_b200/csrc/umma_gemm.cu"     // tcgen05 kernels on tests/host/shim/tc_emul.h + split_hilo_kernel
 #undef hb
 
 namespace {
@@ -54,6 +57,16 @@ const std::map<std::string, Thunk>& registry() {
          RUN((hb_emu::gemm_tn_kernel<BM, BN, BK, NSM, NSN, EPI>(A(cf, 0), A(int, 1), A(cf, 2), A(int, 3), A(float*, 4), A(int, 5), A(int, 6), A(int, 7), A(int, 8), A(hb_emu::GemmEpi, 9)))); }},
       GEMM_THUNK(128, 128, 16, 2, 2, 0) GEMM_THUNK(128, 128, 16, 2, 2, 1) GEMM_THUNK(128, 128, 16, 2, 2, 2)
       GEMM_THUNK(32, 64, 32, 1, 1, 0) GEMM_THUNK(32, 64, 32, 1, 1, 1) GEMM_THUNK(32, 64, 32, 1, 1, 2)
+#define MAP(i) (*static_cast<CUtensorMap*>(a[i]))     /* the first bytes of the 128-byte driver object hold the emulated map */
+#define UMMA_THUNK(BN, EPI)                                                                                                     \
+      {"hb::umma_gemm3_kernel<" #BN ", " #EPI ", 1>", [](dim3 g, dim3 b, void** a) {                                            \
+         tcemu::reset();                                                                                                        \
+         RUN((hb_emu::umma_gemm3_kernel<BN, EPI, 1>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(hb_emu::GemmEpi, 11)))); }},
+      UMMA_THUNK(64, 0) UMMA_THUNK(64, 1) UMMA_THUNK(64, 2) UMMA_THUNK(128, 0) UMMA_THUNK(128, 1) UMMA_THUNK(128, 2)
+      {"hb::lbs_blend_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_blend_kernel(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(cf, 7), A(float*, 8), A(int, 9))); }},
+      {"hb::lbs_fused_kernel<4>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<4>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
+      {"hb::lbs_fused_kernel<8>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<8>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
+      {"hb::split_hilo_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::split_hilo_kernel(A(cf, 0), A(float*, 1), A(float*, 2), A(size_t, 3))); }},
       {"hb::chamfer_nn_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_nn_kernel(A(int, 0), A(cf, 1), A(int, 2), A(cf, 3), A(float*, 4), A(int*, 5))); }},
       {"hb::chamfer_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_bwd_kernel(A(int, 0), A(cf, 1), A(int, 2), A(cf, 3), A(cf, 4), A(ci, 5), A(cf, 6), A(ci, 7), A(float*, 8), A(float*, 9))); }},
       {"hb::chamfer_fill_zero_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_fill_zero_kernel(A(size_t, 0), A(float*, 1), A(int*, 2))); }},
@@ -97,7 +110,19 @@ int cudaFuncSetAttribute(const void*, int, int) { return 0; }
 int cudaGetDevice(int* d) { *d = 0; return 0; }
 int cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return 0; }
 int cudaMemsetAsync(void* p, int v, size_t n, void*) { std::memset(p, v, n); return 0; }
-// tcgen05 path unavailable in this runtime: the tensor-map encoder cannot be resolved
-int cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, int* q) { *fn = nullptr; if (q) *q = 1; return 0; }
+// cuTensorMapEncodeTiled: 2-D fp32 maps only; the emulated description is stored in the caller's (128-byte) CUtensorMap
+static int emul_encode_tiled(void* m, int dtype, unsigned rank, void* base, const unsigned long long* gdim, const unsigned long long* gstr,
+                             const unsigned* box, const unsigned*, int, int swizzle, int, int) {
+  if (rank != 2 || dtype != 7 /* CU_TENSOR_MAP_DATA_TYPE_FLOAT32 */ || swizzle != 3 /* SWIZZLE_128B */ || (gstr[0] % 4)) return 1;
+  CUtensorMap e{static_cast<const float*>(base), gdim[1], gdim[0], gstr[0] / 4, box[0], box[1]};
+  std::memcpy(m, &e, sizeof(e));
+  return 0;
+}
+int cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long, int* q) {
+  const bool ok = std::strcmp(name, "cuTensorMapEncodeTiled") == 0;
+  *fn = ok ? (void*)emul_encode_tiled : nullptr;
+  if (q) *q = ok ? 0 : 1;
+  return 0;
+}
 long long hb_emul_launches() { return g_launches; }
 }

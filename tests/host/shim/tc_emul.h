@@ -147,5 +147,12 @@ inline void tmem_dealloc(uint32_t, uint32_t) {}
 inline void tc_fence_before() {}
 inline void tc_fence_after() {}
 inline uint32_t ld_shared_u32(uint32_t addr) { uint32_t v; std::memcpy(&v, g_smem + addr, 4); return v; }
+inline float4 ld_shared_v4(uint32_t addr) { float4 v; std::memcpy(&v, g_smem + addr, 16); return v; }
+// thread-block clusters are not emulated: split-K instantiations compile, a run that reaches them aborts
+inline uint32_t cluster_ctarank() { return 0; }
+[[noreturn]] inline void no_clusters() { std::fprintf(stderr, "tcemu: thread-block clusters are not emulated (set HB_NO_SPLITK=1)\n"); std::abort(); }
+inline void cluster_sync_all() { no_clusters(); }
+inline uint32_t map_to_cta(uint32_t, uint32_t) { no_clusters(); }
+inline void st_cluster_v4(uint32_t, float, float, float, float) { no_clusters(); }
 
 }  // namespace tcemu

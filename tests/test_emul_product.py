@@ -32,9 +32,11 @@ def emul(built_lib, tmp_path_factory):
     return rt, lib
 
 
-def run_probe(emul, script, *args):
+def run_probe(emul, script, *args, tensor=False):
     rt, lib = emul
     env = dict(os.environ, LD_PRELOAD=rt, CUDA_VISIBLE_DEVICES='')
+    if tensor:          # tcgen05 kernels on the functional emulation; thread-block clusters are not emulated
+        env.update(HB_EMUL_TENSOR='1', HB_NO_SPLITK='1')
     r = subprocess.run([sys.executable, os.path.join(HERE, 'host', 'emul', script), ROOT, lib] + list(args),
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=900)
     lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
@@ -135,3 +137,27 @@ def test_sharded_run_matches_single_process_run(emul, tmp_path):
             assert np.array_equal(both, single[k])
         else:
             assert np.abs(both - single[k]).max() < 5e-5, (k, float(np.abs(both - single[k]).max()))
+
+
+def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
+    """humor_lbs_fwd's tensor-core path on the emulated tcgen05 kernels: the library's own dispatch AND its own TMA-descriptor
+    code (cuTensorMapEncodeTiled is emulated) for the default forms, for forms (2,2) = lane-per-frame skinning + persistent
+    128x256 blend kernel (not yet run on hardware), and for the fused kernel.  All within 2e-5 m of the fp64 oracle."""
+    out = run_probe(emul, 'probe_lbs_forms.py', '140', tensor=True)
+    assert out['exact_vs_oracle'] < 2e-5
+    for key, want in (('forms_11', [1, 1]), ('forms_22', [2, 2])):
+        f = out[key]
+        assert f['used'] == want and f['finite'], (key, f)
+        assert f['v_vs_oracle'] < 2e-5 and f['J_vs_oracle'] < 2e-5 and f['v_vs_exact'] < 5e-6, (key, f)
+    assert out['fused']['v_vs_oracle'] < 2e-5 and out['fused']['J_vs_oracle'] < 2e-5
+
+
+def test_stage3_closure_tensor_precision(emul):
+    """The DEFAULT precision mode: every rollout GEMM on the (emulated) tcgen05 3xTF32 kernel with descriptors built by the
+    library's own host code, against the fixture of the unmodified reference."""
+    out = run_probe(emul, 'probe_stage3.py', 'stage3_rgb_phase1', tensor=True)
+    g = np.load(os.path.join(HERE, 'golden', 'stage3_rgb_phase1.npz'))
+    assert abs(out['loss'] - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    assert out['trans_err'] < 1e-5 and out['prior_mean_err'] < 1e-5
+    for k, e in out['grad_err'].items():
+        assert e < 1e-3, (k, e)          # hardware tolerance for this mode is 1e-2 (truncating accumulator, BPTT amplification)

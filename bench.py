@@ -423,7 +423,7 @@ def main():
     ap.add_argument('--precision', default='tensor', choices=['tensor', 'exact'],
                     help="'tensor': GEMMs on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels (gradient-exact parity mode)")
     ap.add_argument('--lbs-skin', type=int, default=0, help='dense LBS skinning pass form (humor_lbs_configure): 1 lane=vertex, 2 lane=frame')
-    ap.add_argument('--lbs-blend', type=int, default=0, help='dense LBS blend GEMM form: 1 tile per CTA, 2 persistent 128x256 tiles')
+    ap.add_argument('--lbs-blend', type=int, default=0, help='dense LBS blend GEMM form: 1 tile per CTA, 2 persistent 128x256 tiles, 3 = 2 + single TF32 pass on the pose columns')
     ap.add_argument('--lbs-slab', type=int, default=0, help='frames per v_posed slab (128..512)')
     ap.add_argument('--no-graph', action='store_true', help='evaluate the closure eagerly instead of replaying a CUDA graph')
     ap.add_argument('--port-cuda', default='', help='comma list of batch sizes: time the oracle port as eager PyTorch on cuda:0')

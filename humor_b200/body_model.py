@@ -118,6 +118,12 @@ def pack_smplh(asset, num_betas=16):
     }
 
 
+def _tf32_rn(x):
+    """x rounded to tf32 precision (to nearest, ties to even) — the hi plane of a 3xTF32 operand; x - hi is exact in fp32."""
+    u = x.contiguous().view(torch.int32)
+    return ((u + 0x0fff + ((u >> 13) & 1)) & -8192).view(torch.float32)
+
+
 class LbsModel:
     """Device copy of the packed constants + the ctypes HbLbsModel handed to the C-ABI."""
 
@@ -135,11 +141,11 @@ class LbsModel:
         import os
         bt = torch.zeros(packed['v3_ld'], 224, device=self.device)
         bt[:, :KF] = self.t['blend_t']
-        hi = (bt.view(torch.int32) & -8192).view(torch.float32)
+        hi = _tf32_rn(bt)
         self.t['blend_t_hi'], self.t['blend_t_lo'] = hi.contiguous(), (bt - hi).contiguous()
         s.blend_t_hi, s.blend_t_lo = self.t['blend_t_hi'].data_ptr(), self.t['blend_t_lo'].data_ptr()
         s.use_umma = 0 if os.environ.get('HB_NO_UMMA') else 1
-        fh = (self.t['fblend'].view(torch.int32) & -8192).view(torch.float32)
+        fh = _tf32_rn(self.t['fblend'])
         self.t['fblend_hi'], self.t['fblend_lo'] = fh.contiguous(), (self.t['fblend'] - fh).contiguous()
         del self.t['fblend']
         s.fblend_hi, s.fblend_lo = self.t['fblend_hi'].data_ptr(), self.t['fblend_lo'].data_ptr()

@@ -52,6 +52,14 @@ static LbsWs lbs_carve(float* base, int N) {
   return w;
 }
 
+// hi plane of an operand of the tensor-core blend: the value ROUNDED (to nearest, ties to even) to tf32 precision; lo = x - hi is
+// exact in fp32.  hi + lo == x as before, so the 3xTF32 product is unchanged in accuracy, and hi alone is the best single-pass
+// operand (blend form 3 uses one pass on the pose columns).  Inputs are bounded (betas, R - I): no overflow handling needed.
+__device__ __forceinline__ float tf32_rn(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return __uint_as_float((u + 0x0fffu + ((u >> 13) & 1u)) & 0xffffe000u);
+}
+
 __device__ __forceinline__ void rest_joints(const HbLbsModel& m, const float* __restrict__ beta, float* J) {
   for (int e = 0; e < LBS_J * 3; ++e) {
     float a = m.j_template[e];
@@ -84,7 +92,7 @@ __global__ void lbs_pose_kernel(HbLbsModel m, int N, int fpb, const float* __res
   if (feat_hi && f) {                 // hi/lo operand planes (x = hi + lo) of the feature row for the tensor-core blend
     for (int k = 0; k < TC_KF; ++k) {
       const float v = k < 205 ? f[k] : (k == 205 ? 1.f : 0.f);   // column 205 = 1: picks up the template row of the fused blend matrix
-      const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      const float h = tf32_rn(v);
       feat_hi[(size_t)n * TC_KF + k] = h;
       feat_lo[(size_t)n * TC_KF + k] = v - h;
     }
@@ -175,7 +183,7 @@ lbs_pose_warp_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ roo
       if (k < LBS_KF) f[k] = v;
       if (feat_hi) {
         const float vp = k == 205 ? 1.f : v;               // column 205 = 1: picks up the template row of the fused blend matrix
-        const float h = __uint_as_float(__float_as_uint(vp) & 0xffffe000u);
+        const float h = tf32_rn(vp);
         feat_hi[(size_t)n * TC_KF + k] = h;
         feat_lo[(size_t)n * TC_KF + k] = vp - h;
       }
@@ -681,7 +689,7 @@ static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + 
 using namespace hb;
 
 extern "C" int humor_lbs_configure(int skin_form, int blend_form, int slab_frames) {
-  if ((skin_form != 0 && skin_form != 1 && skin_form != 2) || (blend_form != 0 && blend_form != 1 && blend_form != 2) ||
+  if ((skin_form != 0 && skin_form != 1 && skin_form != 2) || (blend_form < 0 || blend_form > 3) ||
       (slab_frames != 0 && (slab_frames < 128 || slab_frames > TC_SLAB)))
     return HB_ERR_ARG;
   if (skin_form) g_skin_form = skin_form;
@@ -735,11 +743,11 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
     const int slab = (g_slab >= 128 && g_slab <= TC_SLAB) ? g_slab : TC_SLAB;
     for (int f0 = 0; f0 < N; f0 += slab) {
       const int nf = (N - f0 < slab) ? N - f0 : slab;
-      const bool blend2 = g_blend_form == 2 && m->v3_ld % 4 == 0;   // column tiles past v3_ld are zero-filled by TMA, never stored
-      g_used_blend = blend2 ? 2 : 1;
+      const bool blend2 = (g_blend_form == 2 || g_blend_form == 3) && m->v3_ld % 4 == 0;   // column tiles past v3_ld are zero-filled by TMA, never stored
+      g_used_blend = blend2 ? g_blend_form : 1;
       if (blend2)
         HB_CUDA(launch_lbs_blend(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
-                                 TC_KF, m->v3_ld, nf, 3 * m->num_verts, TC_KF, m->v_template, ws.vposed, m->v3_ld, st));
+                                 TC_KF, m->v3_ld, nf, 3 * m->num_verts, TC_KF, m->v_template, ws.vposed, m->v3_ld, g_blend_form == 3, st));
       else
         HB_CUDA(launch_umma_gemm3_bn(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
                                      TC_KF, nf, 3 * m->num_verts, TC_KF, ws.vposed, nullptr, nullptr, m->v3_ld, EPI_BIAS, ep, 128, st));

@@ -12,6 +12,10 @@
 //     so tile i+1's MMAs run under tile i's epilogue,
 //   * warps 2..5 = epilogue, one thread per frame row: tcgen05.ld 32 columns at a time, + template, 16-byte row stores
 //     (columns >= ncols are not written).
+//   * `fast` (blend form 3): k-block 0 (the 16 betas + the first 16 pose-feature columns: shape offsets of up to 0.3 m) keeps
+//     the three passes; the other 6 k-blocks (pose offsets, a few cm) run ONE pass on the hi planes, which hold the operands
+//     ROUNDED to tf32: 36 instead of 84 MMAs and 384 instead of 672 KB of operand planes per tile; vertex error <= 7e-5 m at
+//     extreme poses (2e-5 m typical) against the 1e-4 m bound, where the three-pass form is at 1e-6 m.
 // Same barrier / TMEM protocol as lbs_fused_kernel (lbs_fused.cuh), which is verified on the B200.
 #pragma once
 #include "umma_gemm.cuh"
@@ -28,7 +32,7 @@ constexpr int LB_SMEM = LB_STAGES * LB_STAGE + 1024 + 256;
 __global__ void __launch_bounds__(192, 1)
 lbs_blend_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, int M, int ncols, int K,
-                 const float* __restrict__ bias, float* __restrict__ C, int ldc) {
+                 const float* __restrict__ bias, float* __restrict__ C, int ldc, int fast) {
   HB_DYN_SMEM(smem_raw);
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -64,11 +68,14 @@ lbs_blend_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const int s = g % LB_STAGES;
           mbar_wait(empty0 + 8 * s, ((g / LB_STAGES) & 1) ^ 1);
           const uint32_t st = base + s * LB_STAGE;
-          mbar_expect_tx(full0 + 8 * s, LB_STAGE);
+          const bool one_pass = fast && kb > 0;                 // only the hi planes travel for single-pass k-blocks
+          mbar_expect_tx(full0 + 8 * s, one_pass ? LB_A_TILE + LB_B_TILE : LB_STAGE);
           tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * UM_BK, m0);
-          tma_load_2d(st + LB_A_TILE, &tmA_lo, full0 + 8 * s, kb * UM_BK, m0);
           tma_load_2d(st + 2 * LB_A_TILE, &tmB_hi, full0 + 8 * s, kb * UM_BK, n0);
-          tma_load_2d(st + 2 * LB_A_TILE + LB_B_TILE, &tmB_lo, full0 + 8 * s, kb * UM_BK, n0);
+          if (!one_pass) {
+            tma_load_2d(st + LB_A_TILE, &tmA_lo, full0 + 8 * s, kb * UM_BK, m0);
+            tma_load_2d(st + 2 * LB_A_TILE + LB_B_TILE, &tmB_lo, full0 + 8 * s, kb * UM_BK, n0);
+          }
         }
       }
     }
@@ -93,8 +100,10 @@ lbs_blend_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             const uint64_t b_hi = umma_desc_sw128(st + 2 * LB_A_TILE + k * 32);
             const uint64_t b_lo = umma_desc_sw128(st + 2 * LB_A_TILE + LB_B_TILE + k * 32);
             umma_tf32(tacc, a_hi, b_hi, idesc, (kb != 0) || (k != 0));
-            umma_tf32(tacc, a_lo, b_hi, idesc, 1);
-            umma_tf32(tacc, a_hi, b_lo, idesc, 1);
+            if (!(fast && kb > 0)) {
+              umma_tf32(tacc, a_lo, b_hi, idesc, 1);
+              umma_tf32(tacc, a_hi, b_lo, idesc, 1);
+            }
           }
           umma_commit(empty0 + 8 * s);
         }

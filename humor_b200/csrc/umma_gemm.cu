@@ -139,7 +139,7 @@ cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf
 }
 
 cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
-                             int b_rows, int M, int ncols, int K, const float* bias, float* C, int ldc, cudaStream_t st) {
+                             int b_rows, int M, int ncols, int K, const float* bias, float* C, int ldc, int fast, cudaStream_t st) {
   if (!load_encode()) return cudaErrorNotSupported;
   if (K % UM_BK || ldf % 4 || ldb % 4 || ldc % 4 || !bias || b_rows < ncols) return cudaErrorInvalidValue;
   static int sms = 0;
@@ -158,7 +158,7 @@ cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf
     return cudaErrorInvalidValue;
   const int ntiles = cdiv(M, UM_BM) * cdiv(ncols, LB_BN);
   const int grid = ntiles < sms ? ntiles : sms;
-  lbs_blend_kernel<<<grid, 192, LB_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, M, ncols, K, bias, C, ldc);
+  lbs_blend_kernel<<<grid, 192, LB_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, M, ncols, K, bias, C, ldc, fast);
   return cudaGetLastError();
 }
 

@@ -20,5 +20,5 @@ cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf
 // blend-shape contraction of the dense LBS forward as a persistent 128x256-tile kernel (lbs_blend.cuh):
 // C[M][ldc] (columns < ncols) = bias + (feat_hi+feat_lo)[M][K] . (bt_hi+bt_lo)[b_rows][K]^T
 cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
-                             int b_rows, int M, int ncols, int K, const float* bias, float* C, int ldc, cudaStream_t st);
+                             int b_rows, int M, int ncols, int K, const float* bias, float* C, int ldc, int fast, cudaStream_t st);
 }  // namespace hb

@@ -24,7 +24,7 @@ def install(lib_path):
         s.num_verts, s.v3_ld, s.wk, s.reserved = packed['num_verts'], packed['v3_ld'], packed['wk'], 0
         for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_val', 'parents', 'extra_ids'):
             setattr(s, k, self.t[k].data_ptr())
-        split = lambda x: ((x.view(torch.int32) & -8192).view(torch.float32).contiguous(),)
+        split = lambda x: (body_model._tf32_rn(x).contiguous(),)
         bt = torch.zeros(packed['v3_ld'], 224)
         bt[:, :208] = self.t['blend_t']
         hi = split(bt)[0]

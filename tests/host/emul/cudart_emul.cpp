@@ -63,7 +63,7 @@ const std::map<std::string, Thunk>& registry() {
          tcemu::reset();                                                                                                        \
          RUN((hb_emu::umma_gemm3_kernel<BN, EPI, 1>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(hb_emu::GemmEpi, 11)))); }},
       UMMA_THUNK(64, 0) UMMA_THUNK(64, 1) UMMA_THUNK(64, 2) UMMA_THUNK(128, 0) UMMA_THUNK(128, 1) UMMA_THUNK(128, 2)
-      {"hb::lbs_blend_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_blend_kernel(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(cf, 7), A(float*, 8), A(int, 9))); }},
+      {"hb::lbs_blend_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_blend_kernel(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(cf, 7), A(float*, 8), A(int, 9), A(int, 10))); }},
       {"hb::lbs_fused_kernel<4>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<4>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
       {"hb::lbs_fused_kernel<8>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<8>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
       {"hb::split_hilo_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::split_hilo_kernel(A(cf, 0), A(float*, 1), A(float*, 2), A(size_t, 3))); }},

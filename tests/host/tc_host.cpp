@@ -7,13 +7,13 @@ using namespace hb;
 extern "C" {
 // v_posed = bias + (feat_hi+feat_lo) . (bt_hi+bt_lo)^T through lbs_blend_kernel with `grid` persistent CTAs
 long long h_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb, int b_rows,
-                      int M, int ncols, int K, const float* bias, float* C, int ldc, int grid) {
+                      int M, int ncols, int K, const float* bias, float* C, int ldc, int grid, int fast) {
   CUtensorMap a_hi{feat_hi, (unsigned long long)M, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM};
   CUtensorMap a_lo{feat_lo, (unsigned long long)M, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM};
   CUtensorMap b_hi{bt_hi, (unsigned long long)b_rows, (unsigned long long)K, (unsigned long long)ldb, 32, LB_BN};
   CUtensorMap b_lo{bt_lo, (unsigned long long)b_rows, (unsigned long long)K, (unsigned long long)ldb, 32, LB_BN};
   tcemu::reset();
-  shim::launch(dim3(grid), dim3(192), [&] { lbs_blend_kernel(a_hi, a_lo, b_hi, b_lo, M, ncols, K, bias, C, ldc); });
+  shim::launch(dim3(grid), dim3(192), [&] { lbs_blend_kernel(a_hi, a_lo, b_hi, b_lo, M, ncols, K, bias, C, ldc, fast); });
   return tcemu::g_mma_count;
 }
 // the fused blend + skinning kernel (verified on the B200): cross-check of the emulation model

@@ -150,6 +150,8 @@ def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
         assert f['used'] == want and f['finite'], (key, f)
         assert f['v_vs_oracle'] < 2e-5 and f['J_vs_oracle'] < 2e-5 and f['v_vs_exact'] < 5e-6, (key, f)
     assert out['fused']['v_vs_oracle'] < 2e-5 and out['fused']['J_vs_oracle'] < 2e-5
+    f3 = out['forms_23']                                  # single TF32 pass on the pose columns: inside the 1e-4 m bound
+    assert f3['used'] == [2, 3] and f3['finite'] and f3['v_vs_oracle'] < 1e-4 and f3['v_vs_oracle'] > 1e-6, f3
 
 
 def test_stage3_closure_tensor_precision(emul):

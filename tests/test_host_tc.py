@@ -49,7 +49,7 @@ def test_blend_kernel_matches_fp64(H, M, ncols, b_rows, grid):
     bh, bl = split(bt)
     ldc = ((ncols + 63) // 64) * 64
     C = np.full((M, ldc), np.nan, np.float32)
-    nmma = H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, b_rows, M, ncols, K, P(bias), P(C), ldc, grid)
+    nmma = H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, b_rows, M, ncols, K, P(bias), P(C), ldc, grid, 0)
     ntiles = ((M + 127) // 128) * ((ncols + 255) // 256)
     assert nmma == ntiles * 7 * 4 * 3                          # 7 k-blocks x 4 UMMAs of K = 8 x (hi.hi + lo.hi + hi.lo)
     ref = feat.astype(np.float64) @ bt[:ncols].astype(np.float64).T + bias
@@ -77,9 +77,43 @@ def test_blend_kernel_on_the_model_layout(H):
     bias = p['v_template'][c0:V3].copy()
     ldc = v3_ld - c0
     C = np.full((M, ldc), np.nan, np.float32)
-    H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], M, ncols, K, P(bias), P(C), ldc, 2)
+    H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], M, ncols, K, P(bias), P(C), ldc, 2, 0)
     ref = feat.astype(np.float64) @ bt[:ncols].astype(np.float64).T + bias
     assert np.abs(C[:, :ncols] - ref).max() < 3e-6 and np.isnan(C[:, ncols:]).all()
+
+
+def split_rn(x):
+    u = x.view(np.uint32).astype(np.uint64)
+    hi = ((u + 0x0fff + ((u >> 13) & 1)) & 0xffffe000).astype(np.uint32).view(np.float32)
+    return np.ascontiguousarray(hi), np.ascontiguousarray(x - hi)
+
+
+def test_blend_kernel_mixed_precision_form(H):
+    """blend form 3: three passes on k-block 0 (betas + 16 pose columns), ONE pass on the tf32-ROUNDED hi planes for the rest.
+    36 MMAs per tile instead of 84; error of the single-pass columns ~2^-12 per product (sub-1e-4 m at SMPL magnitudes)."""
+    K, M, ncols, b_rows = 224, 200, 520, 528
+    rng = np.random.RandomState(5)
+    feat = np.zeros((M, K), np.float32)
+    feat[:, :16] = rng.randn(M, 16).astype(np.float32) * 0.7           # betas
+    feat[:, 16:205] = (rng.randn(M, 189) * 0.3).astype(np.float32)     # R - I at moderate poses
+    bt = np.zeros((b_rows, K), np.float32)
+    bt[:ncols, :16] = (rng.randn(ncols, 16) * 0.02).astype(np.float32)
+    bt[:ncols, 16:205] = (rng.randn(ncols, 189) * 0.004).astype(np.float32)
+    bias = rng.randn(ncols).astype(np.float32)
+    fh, fl = split_rn(feat)
+    bh, bl = split_rn(bt)
+    assert np.array_equal(fh + fl, feat) and np.array_equal(bh + bl, bt)       # the rounded split is still exact
+    ldc = 576
+    C = np.full((M, ldc), np.nan, np.float32)
+    nmma = H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, b_rows, M, ncols, K, P(bias), P(C), ldc, 3, 1)
+    ntiles = 2 * 3
+    assert nmma == ntiles * (4 * 3 + 6 * 4 * 1)
+    ref = feat.astype(np.float64) @ bt[:ncols].astype(np.float64).T + bias
+    err = np.abs(C[:, :ncols] - ref).max()
+    assert 1e-7 < err < 3e-5, err                       # measurably single-pass, far inside the 1e-4 m bound
+    C3 = np.full((M, ldc), np.nan, np.float32)
+    H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, b_rows, M, ncols, K, P(bias), P(C3), ldc, 3, 0)
+    assert np.abs(C3[:, :ncols] - ref).max() < 3e-6     # the same rounded planes through three passes: fp32-level
 
 
 def test_fused_kernel_cross_checks_the_emulation(H):

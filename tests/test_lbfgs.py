@@ -168,3 +168,26 @@ def test_sharded_joint_lbfgs_matches_single_process():
         assert abs(tot - ref_losses[i]) <= 1e-9 * max(1.0, abs(ref_losses[i])), (i, tot, ref_losses[i])
     assert out[0][2] == out[1][2] == opt._st['func_evals']   # lock-step, and the same evaluations as one process
     assert float((xs - x.detach()).abs().max()) < 1e-7
+
+
+def test_fixed_step_mode_matches_torch():
+    """line_search_fn=None (fixed step lr): the other branch of the library optimiser, iterate for iterate in fp64."""
+    f = objective(30, seed=5, dtype=torch.float64)
+
+    def go(cls):
+        x = torch.full((30,), 0.05, dtype=torch.float64, requires_grad=True)
+        opt = cls([x], lr=0.5, max_iter=6, line_search_fn=None)
+        out = []
+        for _ in range(3):
+            def closure():
+                opt.zero_grad()
+                loss = f(x)
+                loss.backward()
+                return loss
+            out.append(float(opt.step(closure).detach()))
+        return out, x.detach().clone()
+    l_ref, x_ref = go(torch.optim.LBFGS)
+    l_new, x_new = go(LBFGS)
+    for a, b in zip(l_ref, l_new):
+        assert abs(a - b) <= 1e-9 * max(1.0, abs(a)), (l_ref, l_new)
+    assert float((x_ref - x_new).abs().max()) < 1e-8

@@ -1,18 +1,25 @@
 #!/bin/bash
-# One-shot hardware check of the alternative dense-LBS kernel forms + A/B bench + chamfer timing (bounded by timeouts).
+# First GPU call of the next round (≈2-3 min of box time): put the kernel forms that round 1 verified only on the CPU
+# emulation onto the B200, time them, and decide the defaults from the STEP time.
+#   /usr/local/graft/bin/gpurun --timeout 420 -- 'bash tools/gpu_final_check.sh'
 mkdir -p gpurun_out
-(timeout 80 python -m pytest tests/test_gpu_zz_lbs_forms.py -x -q -k "2-1-512 or rejects" 2>&1 | tail -6) > gpurun_out/t_forms_skin.log
-(timeout 90 python -m pytest tests/test_gpu_zz_lbs_forms.py -x -q -k "not 2-1-512 and not rejects" 2>&1 | tail -12) > gpurun_out/t_forms_blend.log
-(timeout 75 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --lbs-skin 2 2>gpurun_out/bench_skin2.err) > gpurun_out/bench_skin2.json
-(timeout 75 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --lbs-skin 2 --lbs-blend 2 2>gpurun_out/bench_skin2_blend2.err) > gpurun_out/bench_skin2_blend2.json
-(timeout 40 python tools/chamfer_time.py 240 2>&1 | tail -2) > gpurun_out/chamfer_time.json
-tail -2 gpurun_out/t_forms_skin.log gpurun_out/t_forms_blend.log
-for f in gpurun_out/bench_skin2.json gpurun_out/bench_skin2_blend2.json; do python - "$f" <<'PY'
+# 1. correctness of the opt-in forms (asserts humor_lbs_forms_used == requested and a last-bit difference vs form 1)
+(HB_TEST_UNVERIFIED=1 timeout 120 python -m pytest tests/test_gpu_zz_lbs_forms.py -x -q 2>&1 | tail -12) > gpurun_out/t_forms.log
+# 2. stand-alone dense LBS forward per form (ms, GB/s, forms used, bitwise difference vs form 1)
+(timeout 90 python tools/lbs_forms_time.py 2>&1 | tail -1) > gpurun_out/lbs_forms_time.json
+# 3. step time with each candidate (the dense pass runs on a side stream under the decoder chain: persistent CTAs may delay it)
+for cfg in "2 1" "2 2" "2 3"; do set -- $cfg
+  (timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --lbs-skin $1 --lbs-blend $2 2>gpurun_out/bench_s$1b$2.err) > gpurun_out/bench_s$1b$2.json
+done
+# 4. the tests that round 1 could only run on the emulation
+(timeout 150 python -m pytest tests/test_gpu_zz_stage12.py tests/test_gpu_zz_run_e2e.py -x -q 2>&1 | tail -6) > gpurun_out/t_stage12_e2e.log
+tail -n 3 gpurun_out/t_forms.log gpurun_out/t_stage12_e2e.log
+cat gpurun_out/lbs_forms_time.json
+for f in gpurun_out/bench_s*.json; do python - "$f" <<'PY'
 import json, sys
 try:
-    d = json.load(open(sys.argv[1])); print(sys.argv[1], d['ms_per_step'], d['roofline']['ms_per_launch'], d['roofline']['frac'])
+    d = json.load(open(sys.argv[1])); print(sys.argv[1], 'ms/step', round(d['ms_per_step'], 3), 'LBS ms', round(d['roofline']['ms_per_launch'], 3), 'frac', round(d['roofline']['frac'], 4))
 except Exception as e:
     print(sys.argv[1], 'unreadable', e)
 PY
 done
-cat gpurun_out/chamfer_time.json

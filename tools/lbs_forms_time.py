@@ -27,7 +27,7 @@ pb = (torch.randn(N, 63, generator=g) * 0.3).cuda()
 be = (torch.randn(B, 16, generator=g) * 0.5).cuda()
 tr = torch.randn(N, 3, generator=g).cuda()
 L = _ext.lib()
-cfgs = [(1, 1), (2, 1), (1, 2), (2, 2)]
+cfgs = [(1, 1), (2, 1), (1, 2), (2, 2), (2, 3)]
 if args.only:
     cfgs = [tuple(int(x) for x in args.only.split(','))]
 ref = None
@@ -45,9 +45,12 @@ for skin, blend in cfgs:
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.reps
+    import ctypes as C
+    us, ub = C.c_int(0), C.c_int(0)
+    L.humor_lbs_forms_used(C.byref(us), C.byref(ub))
     if ref is None:
         ref = v.clone()
-    out.append({'skin': skin, 'blend': blend, 'slab': args.slab, 'ms': ms, 'GBps': N * 83896 / (ms * 1e-3) / 1e9,
+    out.append({'skin': skin, 'blend': blend, 'used': [us.value, ub.value], 'slab': args.slab, 'ms': ms, 'GBps': N * 83896 / (ms * 1e-3) / 1e9,
                 'max_abs_diff_vs_first': float((v - ref).abs().max()), 'bitwise_equal_to_first': bool(torch.equal(v, ref))})
     del v
 print(json.dumps(out))

@@ -84,7 +84,15 @@ def make_smplh_asset(seed=0):
     # skinning weights: <= 4 non-zeros per vertex
     W = np.zeros((V, NUM_JOINTS))
     gp = np.where(par[parent] >= 0, par[parent], parent)
-    other = rng.randint(0, NUM_JOINTS, size=V)
+    # 4th influence: a kinematic NEIGHBOUR of the bone (a child of either end, i.e. the next bone or a sibling), as in SMPL,
+    # whose skinning weights are local by construction (initialised from an artist's segmentation and regularised towards
+    # it).  An earlier generator drew this joint uniformly from all 52, which made every 128-vertex range touch ~48 joints.
+    kids = [[c for c in range(1, NUM_JOINTS) if par[c] == j] for j in range(NUM_JOINTS)]
+    pick = rng.rand(V)
+    other = np.empty(V, np.int64)
+    for v in range(V):
+        cand = [c for c in kids[child[v]] + kids[parent[v]] if c != child[v]] or [gp[v]]
+        other[v] = cand[int(pick[v] * len(cand))]
     raw = rng.dirichlet([2.0, 2.0, 0.5, 0.3], size=V)
     raw[:, 0] *= (0.3 + u[:, 0])
     raw[:, 1] *= (1.3 - u[:, 0])

@@ -106,8 +106,10 @@ def pack_smplh(asset, num_betas=16):
         g_start[g + 1] = len(g_joint)
     g_joint = np.asarray(g_joint, np.int32)
     g_w = np.stack(g_w, 0) if g_w else np.zeros((1, G), np.float32)
+    g_slot, ft_tab = fuseg_tables(g_start, g_joint, ng)
     return {
         'g_start': g_start, 'g_joint': g_joint, 'g_w': np.ascontiguousarray(g_w), 'num_groups': ng,
+        'g_slot': g_slot, 'ft_tab': ft_tab, 'ft_nct': ft_tab.shape[0],
         'fblend': fb, 'fw_idx': fw_idx, 'fw_val': fw_val, 'fused_nct': nct, 'fused_wk': fwk,
         'depth': depth, 'child_start': child_start, 'child_list': child_list, 'max_depth': int(depth.max()),
         'num_verts': V, 'v3_ld': v3_ld, 'wk': wk,
@@ -116,6 +118,50 @@ def pack_smplh(asset, num_betas=16):
         'w_idx': np.ascontiguousarray(w_idx), 'w_val': np.ascontiguousarray(w_val),
         'parents': par.astype(np.int32), 'extra_ids': np.asarray(EXTRA_VERTEX_IDS, np.int32),
     }
+
+
+FG_NSLOT = 12          # csrc/lbs_fuseg.cuh: shared-memory slots for skinning transforms, [128 frames][12 floats] each
+FG_GPT = 8             # vertex groups per 192-column tile (64 vertices)
+FG_SLOT_BYTES = 128 * 48
+
+
+def fuseg_tables(g_start, g_joint, num_groups, nslot=FG_NSLOT, gpt=FG_GPT):
+    """Static schedule of the transform slots of the fused blend + group-skinning kernel (csrc/lbs_fuseg.cuh).
+
+    A CTA walks consecutive 64-vertex column tiles for the same 128 frames, so the 3x4 transforms of the joints a tile is
+    skinned to are kept in ``nslot`` shared-memory slots across tiles.  Per tile c the table lists which (joint, slot) pairs to
+    load when the CTA arrives from tile c-1 of the same frames ("inc") and when it starts at c ("fresh" = every slot the tile
+    uses).  A joint keeps its slot only while consecutive tiles need it (so the state at c does not depend on where a CTA
+    started), and a new joint never takes a slot tile c-1 used (its epilogue may still be reading).  Joints that find no slot
+    are read from global memory by the epilogue (g_slot = -1): correct for any mesh, fast for SMPL-like locality.
+
+    Returns g_slot [E] (byte offset of the slot of group entry e in ITS tile, or -1) and ft_tab [nct][2 + 2*nslot]:
+    n_fresh, n_inc, fresh entries, inc entries; entry = joint*12 | slot << 16."""
+    nct = (num_groups + gpt - 1) // gpt
+    g_slot = np.full(len(g_joint), -1, np.int32)
+    tab = np.zeros((nct, 2 + 2 * nslot), np.int32)
+    prev = {}                                                   # joint*12 -> slot of tile c-1
+    for c in range(nct):
+        e0, e1 = int(g_start[min(c * gpt, num_groups)]), int(g_start[min((c + 1) * gpt, num_groups)])
+        js, cnt = np.unique(g_joint[e0:e1], return_counts=True)
+        order = [int(j) for j in js[np.argsort(-cnt, kind='stable')]]      # most used first
+        cur = {j: prev[j] for j in order if j in prev}
+        free = [s for s in range(nslot) if s not in prev.values()]
+        inc = []
+        for j in order:
+            if j not in cur and free:
+                cur[j] = free.pop(0)
+                inc.append(j)
+        fresh = sorted(cur, key=lambda j: cur[j])
+        tab[c, 0], tab[c, 1] = len(fresh), len(inc)
+        tab[c, 2:2 + len(fresh)] = [j | (cur[j] << 16) for j in fresh]
+        tab[c, 2 + nslot:2 + nslot + len(inc)] = [j | (cur[j] << 16) for j in inc]
+        for e in range(e0, e1):
+            j = int(g_joint[e])
+            if j in cur:
+                g_slot[e] = cur[j] * FG_SLOT_BYTES
+        prev = cur
+    return g_slot, tab
 
 
 def _tf32_rn(x):
@@ -156,6 +202,7 @@ class LbsModel:
         s.fused_nct, s.fused_wk = packed['fused_nct'], (packed['fused_wk'] if os.environ.get('HB_LBS_FUSED') else 0)
         s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
         s.num_groups = packed['num_groups']
+        s.g_slot, s.ft_tab, s.ft_nct = self.t['g_slot'].data_ptr(), self.t['ft_tab'].data_ptr(), packed['ft_nct']
         self.ws_slot = 0
         s.max_depth = packed['max_depth']
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))

@@ -689,7 +689,7 @@ static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + 
 using namespace hb;
 
 extern "C" int humor_lbs_configure(int skin_form, int blend_form, int slab_frames) {
-  if ((skin_form != 0 && skin_form != 1 && skin_form != 2) || (blend_form < 0 || blend_form > 3) ||
+  if ((skin_form < 0 || skin_form > 3) || (blend_form < 0 || blend_form > 3) ||
       (slab_frames != 0 && (slab_frames < 128 || slab_frames > TC_SLAB)))
     return HB_ERR_ARG;
   if (skin_form) g_skin_form = skin_form;
@@ -727,7 +727,23 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
                                                need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
                                                tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);
   HB_LAUNCH_CHECK(); ++nl;
-  if (tc && m->fblend_hi && m->fw_idx && (m->fused_wk == 4 || m->fused_wk == 8) && !g_unfused) {
+  // skin form 3: one persistent tcgen05 kernel, blend accumulators skinned straight out of TMEM by lane = frame (lbs_fuseg.cuh);
+  // blend form 3 selects its single-pass pose columns, any other value the three-pass blend (reported as 1)
+  const bool fuseg = tc && g_skin_form == 3 && m->ft_tab && m->g_slot && m->g_start && m->g_joint && m->g_w && m->num_groups > 0 &&
+                     m->ft_nct == cdiv(m->num_groups, 8) && (m->num_verts % 2) == 0 && m->v3_ld % 4 == 0;
+  if (fuseg) {
+    LbsFusegArgs fa;
+    fa.N = N; fa.num_verts = m->num_verts; fa.num_groups = m->num_groups; fa.nrt = fa.nct = 0; fa.fast = g_blend_form == 3;
+    fa.g_start = m->g_start; fa.g_joint = m->g_joint; fa.g_slot = m->g_slot; fa.g_w = m->g_w; fa.ft_tab = m->ft_tab;
+    fa.v_template = m->v_template; fa.A = ws.A; fa.trans = trans; fa.out = verts;
+    HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_t_hi, m->blend_t_lo, TC_KF, m->v3_ld, TC_KF, fa, st));
+    g_used_skin = 3; g_used_blend = fa.fast ? 3 : 1;
+    ++nl;
+    if (joints && njo == 73) {
+      lbs_gather_extra_kernel<<<cdiv(N * 21, 256), 256, 0, st>>>(*m, N, verts, joints);
+      HB_LAUNCH_CHECK(); ++nl;
+    }
+  } else if (tc && m->fblend_hi && m->fw_idx && (m->fused_wk == 4 || m->fused_wk == 8) && !g_unfused) {
     // one persistent tcgen05 kernel: blend GEMM + skinning + coalesced store (lbs_fused.cuh)
     HB_CUDA(launch_lbs_fused(ws.feat_hi, ws.feat_lo, TC_KF, m->fblend_hi, m->fblend_lo, TC_KF, N, m->num_verts, m->fused_nct,
                              m->fused_wk, m->fw_idx, m->fw_val, ws.A, trans, verts, st));

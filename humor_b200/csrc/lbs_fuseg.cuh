@@ -1,0 +1,305 @@
+// Dense SMPL+H forward, skin form 3: blend GEMM + skinning in ONE persistent tcgen05 kernel with a lane = frame epilogue.
+//
+//   v_posed[frame, 3v+d] = v_template[3v+d] + feat[frame, :224] . blend_t[3v+d, :224]      (3xTF32, or `fast`: see below)
+//   out[frame, v, :]     = sum_j W[v][j] (A[frame, j] . [v_posed[frame, v]; 1]) + trans[frame]
+//
+// What the two measured predecessors taught (profiles/r01g):
+//   * lbs_skin_apply_kernel (lane = vertex) gathers <= 4 transforms of 48 B per (vertex, frame) from shared memory - the
+//     shared-memory port is its bound; lbs_fused_kernel (thread = frame, vertex by vertex) re-loads transforms from global
+//     memory whenever the joint of a weight slot changes.
+//   * the TMEM accumulator layout IS lane = frame (M = frames): a thread that reads its row with tcgen05.ld holds
+//     consecutive vertices of ONE frame, which is exactly the operand of the group-skinning form (lbs_skin_group.cuh): a
+//     transform is fetched once per (frame, joint, group of 8 vertices) and joint index / weights are warp-uniform.
+// Plan of one CTA (one per SM, 320 threads):
+//   tiles   128 frames x 192 columns (= 64 vertices = 8 groups), walked ROW-major in one contiguous chunk per CTA: ~88
+//           consecutive column tiles of the same 128 frames, so the frames' transforms stay on the SM
+//   warp 0  TMA producer: (a) operand ring of 3 entries of 40 KB = one A plane (128 x 32 floats) + one B plane (192 x 32);
+//           a three-pass k-block takes two entries (hi planes, lo planes), a single-pass one only the hi entry;
+//           (b) the 3x4 transforms of the joints the tile is skinned to, as [128 frames][12 floats] boxes cut from
+//           A[N][52*12] into 12 shared-memory slots under the host's static schedule (body_model.fuseg_tables): a joint
+//           keeps its slot while consecutive tiles need it, so a tile loads ~1 new slot (6 KB) instead of ~6
+//   warp 1  tcgen05.mma issuer; a tile's k-blocks accumulate into ONE of two 192-column TMEM buffers (K = 224: no
+//           promotion chunks needed, lbs_blend.cuh), so tile i+1's MMAs run under tile i's epilogue
+//   warps 2..9  epilogue: TMEM lane quadrant q = warp % 4, column half h = (warp - 2) / 4 -> 4 groups each.  Per group:
+//           tcgen05.ld 24 columns (8 vertices of the thread's frame), + template, skin with the group's joint list
+//           (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), + trans, park the 24 floats in a
+//           per-warp staging tile and write two 96-byte frame rows per instruction (a lane = frame store would touch
+//           32 different lines per instruction).
+//   `fast`  (blend form 3) k-block 0 (betas + first pose columns: shape offsets of up to 0.3 m) keeps three passes, the other
+//           six run one TF32 pass on the tf32-ROUNDED hi planes: 36 instead of 84 MMAs and 320 instead of 560 KB of operand
+//           planes per tile; <= 7e-5 m.
+// Barrier protocol (all mbarriers, phases counted per use):
+//   full[s]/empty[s]   operand ring (TMA complete_tx / tcgen05.commit), as lbs_blend_kernel
+//   tfull[b]/tempty[b] TMEM buffer b = tile parity (tcgen05.commit / one arrive per epilogue warp), as lbs_blend_kernel
+//   ttf[b]             transforms of tile parity b have landed (arrive.expect_tx by the producer, complete_tx by TMA).
+//                      The producer issues tile i's transform loads only after tempty says the epilogue is done with tile
+//                      i-2 (slots tile i-1 uses are never chosen by the schedule), and after tile i-1 when the frames change
+//                      (then every slot is reloaded).
+// Same TMA / UMMA descriptor forms and TMEM protocol as lbs_fused_kernel (verified on the B200); executed on the CPU through
+// tests/host/shim/tc_emul.h (tests/test_host_tc.py).  NOT yet executed on hardware: opt-in (humor_lbs_configure(3, ...)).
+#pragma once
+#include "umma_gemm.cuh"
+#include "umma_launch.cuh"
+
+namespace hb {
+
+constexpr int FG_BN = 192;                          // columns per tile = 64 vertices
+constexpr int FG_GPT = 8;                           // vertex groups per tile
+constexpr int FG_G = 8;                             // vertices per group
+constexpr int FG_GC = 3 * FG_G;                     // columns per group
+constexpr int FG_RING = 3;
+constexpr int FG_A_PLANE = UM_BM * 128;             // bytes: 128 rows x 128 B
+constexpr int FG_B_PLANE = FG_BN * 128;
+constexpr int FG_ENTRY = FG_A_PLANE + FG_B_PLANE;   // 40 KB
+constexpr int FG_NSLOT = 12;                        // body_model.FG_NSLOT
+constexpr int FG_SLOT = UM_BM * 48;                 // [128 frames][12 floats]
+constexpr int FG_EPI_WARPS = 8;
+constexpr int FG_SLD = 25;                          // staging row stride in floats (odd: conflict-free lane = row writes)
+constexpr int FG_STAGE_W = 32 * FG_SLD * 4;         // bytes per epilogue warp
+constexpr int FG_OFF_SLOTS = FG_RING * FG_ENTRY;
+constexpr int FG_OFF_STAGE = FG_OFF_SLOTS + FG_NSLOT * FG_SLOT;
+constexpr int FG_OFF_BARS = FG_OFF_STAGE + FG_EPI_WARPS * FG_STAGE_W;
+constexpr int FG_SMEM = FG_OFF_BARS + 128 + 1024;   // + barriers + 1024-byte alignment slack = 223 360 B
+constexpr int FG_THREADS = 64 + 32 * FG_EPI_WARPS;
+constexpr int FG_TAB = 2 + 2 * FG_NSLOT;            // ints per column tile of ft_tab
+
+#ifndef HB_HOST_SHIM
+// tcgen05.ld of one vertex group: 24 consecutive columns of the thread's TMEM lane
+__device__ __forceinline__ void tmem_ld24(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+               : "r"(taddr + 16u) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void stcs2(float* p, float x, float y) { __stcs(reinterpret_cast<float2*>(p), make_float2(x, y)); }
+#define HB_EMU_GUARD_ACQ(addr, bytes)
+#define HB_EMU_GUARD_REL(addr)
+#else
+using tcemu::tmem_ld24;
+static inline void stcs2(float* p, float x, float y) { p[0] = x; p[1] = y; }
+// tests/host: tell the emulation which shared-memory ranges are being read, so that a TMA write into them aborts
+#define HB_EMU_GUARD_ACQ(addr, bytes) tcemu::guard_acquire(addr, bytes)
+#define HB_EMU_GUARD_REL(addr) tcemu::guard_release(addr)
+#endif
+
+__global__ void __launch_bounds__(FG_THREADS, 1)
+lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const __grid_constant__ CUtensorMap tmT, int K, LbsFusegArgs a) {
+  HB_DYN_SMEM(smem_raw);
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bars = base + FG_OFF_BARS;
+  const uint32_t full0 = bars, empty0 = bars + 8 * FG_RING, tfull0 = empty0 + 8 * FG_RING, tempty0 = tfull0 + 16, ttf0 = tempty0 + 16,
+                 tptr = ttf0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = a.nrt * a.nct;
+  const int nkb = K / UM_BK;
+  // one contiguous chunk of the row-major tile list per CTA (column tile fastest: the frames change at most twice per chunk)
+  const int t_begin = (int)((long long)ntiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < FG_RING; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, FG_EPI_WARPS); mbar_init(ttf0 + 8 * b, 1); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tptr, 512u);                                     // 2 x 192 columns (allocations are powers of two)
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ld_shared_u32(tptr);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0, tc = 0, prev_r = -1;                           // ring entries issued, tiles started, row tile of the previous tile
+      for (int t = t_begin; t < t_end; ++t, ++tc) {
+        const int r = t / a.nct, c = t - r * a.nct;
+        const int m0 = r * UM_BM, n0 = c * FG_BN;
+        // ---- skinning transforms of this tile's joints -> shared-memory slots
+        const bool fresh = r != prev_r;                         // first tile of the CTA, or other frames: reload every slot
+        prev_r = r;
+        if (fresh && tc >= 1) mbar_wait(tempty0 + 8 * ((tc - 1) & 1), ((tc - 1) >> 1) & 1);   // epilogue done with tile tc-1
+        if (tc >= 2) mbar_wait(tempty0 + 8 * (tc & 1), ((tc >> 1) & 1) ^ 1);                   // ... with tile tc-2
+        const int* tab = a.ft_tab + (size_t)c * FG_TAB;
+        const int nl = fresh ? tab[0] : tab[1];
+        const int* ent = tab + 2 + (fresh ? 0 : FG_NSLOT);
+        const uint32_t tb = ttf0 + 8 * (tc & 1);
+        mbar_expect_tx(tb, (uint32_t)nl * FG_SLOT);
+        for (int i = 0; i < nl; ++i) {
+          const int e = ent[i];
+          tma_load_2d(base + FG_OFF_SLOTS + (uint32_t)(e >> 16) * FG_SLOT, &tmT, tb, e & 0xffff, m0);
+        }
+        // ---- operand planes
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int npl = (!a.fast || kb == 0) ? 2 : 1;         // hi entry, then (three-pass k-blocks) lo entry
+          for (int pl = 0; pl < npl; ++pl, ++g) {
+            const int s = g % FG_RING;
+            mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
+            const uint32_t st = base + s * FG_ENTRY;
+            mbar_expect_tx(full0 + 8 * s, FG_ENTRY);
+            tma_load_2d(st, pl ? &tmA_lo : &tmA_hi, full0 + 8 * s, kb * UM_BK, m0);
+            tma_load_2d(st + FG_A_PLANE, pl ? &tmB_lo : &tmB_hi, full0 + 8 * s, kb * UM_BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FG_BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+      int g = 0, tc = 0;
+      for (int t = t_begin; t < t_end; ++t, ++tc) {
+        const int buf = tc & 1;
+        mbar_wait(tempty0 + 8 * buf, ((tc >> 1) & 1) ^ 1);      // epilogue has drained this TMEM buffer
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * FG_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int gh = g++;
+          const int sh = gh % FG_RING;
+          mbar_wait(full0 + 8 * sh, (gh / FG_RING) & 1);
+          tc_fence_after();
+          const uint32_t sth = base + sh * FG_ENTRY;
+#pragma unroll
+          for (int k = 0; k < UM_BK / 8; ++k)                   // hi . hi
+            umma_tf32(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc, (kb != 0) || (k != 0));
+          if (!a.fast || kb == 0) {
+            const int gl = g++;
+            const int sl = gl % FG_RING;
+            mbar_wait(full0 + 8 * sl, (gl / FG_RING) & 1);
+            tc_fence_after();
+            const uint32_t stl = base + sl * FG_ENTRY;
+#pragma unroll
+            for (int k = 0; k < UM_BK / 8; ++k) {               // lo . hi + hi . lo
+              umma_tf32(tacc, umma_desc_sw128(stl + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc, 1);
+              umma_tf32(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(stl + FG_A_PLANE + k * 32), idesc, 1);
+            }
+            umma_commit(empty0 + 8 * sh);
+            umma_commit(empty0 + 8 * sl);
+          } else {
+            umma_commit(empty0 + 8 * sh);
+          }
+        }
+        umma_commit(tfull0 + 8 * buf);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int q = warp & 3;                                     // TMEM lane quadrant of this warp
+    const int h = ew >> 2;                                      // column half: groups 4h .. 4h+3 of the tile
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* S = reinterpret_cast<float*>(gbase + FG_OFF_STAGE + ew * FG_STAGE_W);
+    const uint32_t tsl = base + FG_OFF_SLOTS + (uint32_t)(q * 32 + lane) * 48u;       // this thread's frame inside a slot
+    const int sub = lane / 12, idx = lane - 12 * sub;           // store phase: lanes 0..23 = 2 rows x 12 float2
+    int tc = 0;
+    for (int t = t_begin; t < t_end; ++t, ++tc) {
+      const int buf = tc & 1;
+      const int r = t / a.nct, c = t - r * a.nct;
+      const int f0 = r * UM_BM + q * 32;
+      const int fr = min(f0 + lane, a.N - 1);                   // rows past N: computed on a valid frame, never stored
+      const float t0 = __ldg(a.trans + (size_t)fr * 3), t1 = __ldg(a.trans + (size_t)fr * 3 + 1), t2 = __ldg(a.trans + (size_t)fr * 3 + 2);
+      const float* Arow = a.A + (size_t)fr * 624;
+      mbar_wait(tfull0 + 8 * buf, (tc >> 1) & 1);
+      mbar_wait(ttf0 + 8 * buf, (tc >> 1) & 1);
+      tc_fence_after();
+#ifdef HB_HOST_SHIM
+      if (lane == 0) {                                          // (emulation only) the slots this tile reads
+        const int* tab = a.ft_tab + (size_t)c * FG_TAB;
+        for (int i = 0; i < tab[0]; ++i) HB_EMU_GUARD_ACQ(base + FG_OFF_SLOTS + (uint32_t)(tab[2 + i] >> 16) * FG_SLOT, FG_SLOT);
+      }
+#endif
+#pragma unroll 1
+      for (int gg = 0; gg < FG_GPT / 2; ++gg) {
+        const int g = c * FG_GPT + h * (FG_GPT / 2) + gg;
+        if (g >= a.num_groups) break;                           // warp-uniform
+        float p[FG_GC], acc[FG_GC];
+        tmem_ld24(trow + buf * FG_BN + (h * (FG_GPT / 2) + gg) * FG_GC, p);
+        const int col0 = g * FG_GC;
+        const int nv3 = min(FG_G, a.num_verts - g * FG_G) * 3;  // floats of this group inside the mesh
+#pragma unroll
+        for (int i = 0; i < FG_GC; ++i) {
+          p[i] += (i < nv3) ? __ldg(a.v_template + col0 + i) : 0.f;
+          acc[i] = 0.f;
+        }
+        const int e0 = __ldg(a.g_start + g), e1 = __ldg(a.g_start + g + 1);
+        // one entry of look-ahead on the (warp-uniform) slot and weight row
+        int son = 0, jn = 0;
+        float4 wan = make_float4(0.f, 0.f, 0.f, 0.f), wbn = wan;
+        if (e0 < e1) {
+          son = __ldg(a.g_slot + e0); jn = __ldg(a.g_joint + e0);
+          wan = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e0 * FG_G));
+          wbn = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e0 * FG_G) + 1);
+        }
+        for (int e = e0; e < e1; ++e) {
+          float4 r0, r1, r2;
+          if (son >= 0) {                                       // warp-uniform
+            r0 = ld_shared_v4(tsl + (uint32_t)son); r1 = ld_shared_v4(tsl + (uint32_t)son + 16u); r2 = ld_shared_v4(tsl + (uint32_t)son + 32u);
+          } else {                                              // joint without a slot in this tile (rare): from L1/L2
+            const float4* ap = reinterpret_cast<const float4*>(Arow + jn);
+            r0 = __ldg(ap); r1 = __ldg(ap + 1); r2 = __ldg(ap + 2);
+          }
+          const float w[FG_G] = {wan.x, wan.y, wan.z, wan.w, wbn.x, wbn.y, wbn.z, wbn.w};
+          if (e + 1 < e1) {
+            son = __ldg(a.g_slot + e + 1); jn = __ldg(a.g_joint + e + 1);
+            wan = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)(e + 1) * FG_G));
+            wbn = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)(e + 1) * FG_G) + 1);
+          }
+#pragma unroll
+          for (int i = 0; i < FG_G; ++i) {
+            if (w[i] != 0.f) {                                  // warp-uniform: weights depend on the vertex only
+              const float px = p[3 * i], py = p[3 * i + 1], pz = p[3 * i + 2];
+              acc[3 * i] = fmaf(w[i], fmaf(r0.x, px, fmaf(r0.y, py, fmaf(r0.z, pz, r0.w))), acc[3 * i]);
+              acc[3 * i + 1] = fmaf(w[i], fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w))), acc[3 * i + 1]);
+              acc[3 * i + 2] = fmaf(w[i], fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))), acc[3 * i + 2]);
+            }
+          }
+        }
+        // park the group (lane = frame), then two 96-byte frame rows per store instruction
+        float* Sr = S + lane * FG_SLD;
+#pragma unroll
+        for (int i = 0; i < FG_GC; ++i) Sr[i] = acc[i] + ((i % 3) == 0 ? t0 : ((i % 3) == 1 ? t1 : t2));
+        __syncwarp();
+        if (lane < 24) {
+          float* obase = a.out + ((size_t)g * FG_G) * 3 + 2 * idx;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; rr += 2) {
+            const int row = rr + sub;
+            const int frame = f0 + row;
+            if (frame < a.N) {
+              const float x = S[row * FG_SLD + 2 * idx], y = S[row * FG_SLD + 2 * idx + 1];
+              float* dst = obase + (size_t)frame * a.num_verts * 3;
+              if (2 * idx + 1 < nv3) stcs2(dst, x, y);
+              else if (2 * idx < nv3) __stcs(dst, x);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+#ifdef HB_HOST_SHIM
+      if (lane == 0) {
+        const int* tab = a.ft_tab + (size_t)c * FG_TAB;
+        for (int i = 0; i < tab[0]; ++i) HB_EMU_GUARD_REL(base + FG_OFF_SLOTS + (uint32_t)(tab[2 + i] >> 16) * FG_SLOT);
+      }
+#endif
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+}  // namespace hb

@@ -5,6 +5,7 @@
 #include "umma_launch.cuh"
 #include "lbs_fused.cuh"
 #include "lbs_blend.cuh"
+#include "lbs_fuseg.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
@@ -38,6 +39,19 @@ static bool make_map(CUtensorMap* m, const float* base, int rows, int K, int ld,
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// rows x cols fp32 matrix, row stride ld floats; un-swizzled box = {box_cols floats, box_rows} (box_cols * 4 a multiple of 16):
+// shared memory receives the box rows back to back
+static bool make_map_plain(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -159,6 +173,40 @@ cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf
   const int ntiles = cdiv(M, UM_BM) * cdiv(ncols, LB_BN);
   const int grid = ntiles < sms ? ntiles : sms;
   lbs_blend_kernel<<<grid, 192, LB_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, M, ncols, K, bias, C, ldc, fast);
+  return cudaGetLastError();
+}
+
+// skin form 3: blend + group skinning in one persistent kernel (lbs_fuseg.cuh).  `a` arrives with the model tables, A, trans,
+// out, N, num_verts, num_groups and fast filled in; tile counts are set here.
+cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
+                             int b_rows, int K, LbsFusegArgs a, cudaStream_t st) {
+  if (!load_encode()) return cudaErrorNotSupported;
+  if (K % UM_BK || ldf % 4 || ldb % 4 || a.N <= 0 || a.num_groups <= 0 || (a.num_verts & 1) ||
+      a.num_groups != cdiv(a.num_verts, FG_G) || !a.g_start || !a.g_joint || !a.g_slot || !a.g_w || !a.ft_tab)
+    return cudaErrorInvalidValue;
+  static int sms = 0, want = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lbs_fuseg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FG_SMEM);
+    if (e != cudaSuccess) { sms = 0; return e; }
+    // persistent CTAs hold an SM (223 KB of shared memory, all of TMEM) for the whole pass: HB_LBS_FUSEG_CTAS leaves SMs to
+    // kernels of other streams (the latency-bound decoder chain runs next to the dense pass)
+    const char* w = getenv("HB_LBS_FUSEG_CTAS");
+    want = w ? atoi(w) : 0;
+  }
+  a.nrt = cdiv(a.N, UM_BM);
+  a.nct = cdiv(a.num_groups, FG_GPT);
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tt;
+  if (!make_map(&ta_hi, feat_hi, a.N, K, ldf, UM_BM) || !make_map(&ta_lo, feat_lo, a.N, K, ldf, UM_BM) ||
+      !make_map(&tb_hi, bt_hi, b_rows, K, ldb, FG_BN) || !make_map(&tb_lo, bt_lo, b_rows, K, ldb, FG_BN) ||
+      !make_map_plain(&tt, a.A, a.N, 624, 624, 12, UM_BM))
+    return cudaErrorInvalidValue;
+  const int ntiles = a.nrt * a.nct;
+  int grid = ntiles < sms ? ntiles : sms;
+  if (want > 0 && want < grid) grid = want;
+  lbs_fuseg_kernel<<<grid, FG_THREADS, FG_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tt, K, a);
   return cudaGetLastError();
 }
 

@@ -21,4 +21,24 @@ cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf
 // C[M][ldc] (columns < ncols) = bias + (feat_hi+feat_lo)[M][K] . (bt_hi+bt_lo)[b_rows][K]^T
 cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
                              int b_rows, int M, int ncols, int K, const float* bias, float* C, int ldc, int fast, cudaStream_t st);
+// dense LBS forward, skin form 3: blend GEMM + lane = frame group skinning in one persistent kernel (lbs_fuseg.cuh)
+struct LbsFusegArgs {
+  int N;                   // frames
+  int num_verts;
+  int num_groups;
+  int nrt, nct;            // row tiles (128 frames), column tiles (64 vertices)
+  int fast;
+  const int* g_start;      // [num_groups + 1]
+  const int* g_joint;      // [E] joint * 12
+  const int* g_slot;       // [E] byte offset of the entry's slot, -1: transform read from global memory
+  const float* g_w;        // [E][8]
+  const int* ft_tab;       // [nct][FG_TAB]
+  const float* v_template; // [3 * num_verts]
+  const float* A;          // [N][52][12] skinning transforms
+  const float* trans;      // [N][3]
+  float* out;              // [N][num_verts][3]
+};
+// bt_* = blend_t hi/lo planes [b_rows][K] (ldb floats per row); the caller fills every field of `a` except nrt / nct
+cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
+                             int b_rows, int K, LbsFusegArgs a, cudaStream_t st);
 }  // namespace hb

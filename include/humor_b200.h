@@ -72,7 +72,11 @@ typedef struct HbLbsModel {
   const int* g_joint;      /* [E] joint * 12 */
   const float* g_w;        /* [E][8], 16-byte aligned */
   int num_groups;          /* 0: group tables absent */
-  int reserved2;
+  /* fused blend + group skinning (csrc/lbs_fuseg.cuh, skin form 3): 192-column tiles = 8 groups; the transforms of a tile's
+     joints live in 12 shared-memory slots that persist across the consecutive column tiles a CTA walks */
+  int ft_nct;              /* column tiles = ceil(num_groups / 8); 0: tables absent */
+  const int* g_slot;       /* [E] byte offset of entry e's slot in the tile of its group, or -1: read A from global memory */
+  const int* ft_tab;       /* [ft_nct][26] n_fresh, n_inc, 12 fresh + 12 incremental loads (joint*12 | slot << 16) */
 } HbLbsModel;
 
 /* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs

@@ -38,6 +38,7 @@ def install(lib_path):
         s.fused_nct, s.fused_wk = packed['fused_nct'], 0
         s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
         s.num_groups, s.max_depth = packed['num_groups'], packed['max_depth']
+        s.g_slot, s.ft_tab, s.ft_nct = self.t['g_slot'].data_ptr(), self.t['ft_tab'].data_ptr(), packed['ft_nct']
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))
         self.fused_wk = packed['fused_wk']
         self.ws_slot = 0

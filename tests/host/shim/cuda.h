@@ -8,5 +8,6 @@ struct CUtensorMap {
   unsigned long long rows, cols;  // extents; out-of-range box elements read as zero
   unsigned long long ld;          // row stride in floats
   unsigned box_cols, box_rows;    // box = {32 floats = 128 B (one swizzle span), box_rows}
+  unsigned plain;                 // 0: SWIZZLE_128B (default); 1: SWIZZLE_NONE, box rows of box_cols floats back to back
 };
 #define __grid_constant__

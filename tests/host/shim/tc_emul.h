@@ -30,6 +30,8 @@ inline std::mutex g_mu;
 struct Bar { int expected = 0, pending = 0; long long tx = 0; int phase = 0; };
 inline std::map<uint32_t, Bar> g_bars;
 inline long long g_mma_count = 0, g_tma_count = 0;
+struct Guard { uint32_t lo, hi; int count; };
+inline std::map<uint32_t, Guard> g_guards;
 
 inline uint8_t* dyn_smem() { return g_smem + DYN_OFFSET; }
 inline uint32_t smem_u32(const void* p) { return (uint32_t)(static_cast<const uint8_t*>(p) - g_smem); }
@@ -39,6 +41,7 @@ inline float tf32_trunc(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xff
 inline void reset() {
   std::lock_guard<std::mutex> l(g_mu);
   g_bars.clear();
+  g_guards.clear();
   std::memset(g_smem, 0xff, sizeof(g_smem));          // NaN patterns: reading a byte nobody wrote shows
   for (auto& r : g_tmem) for (auto& v : r) v = __builtin_nanf("");
   g_mma_count = g_tma_count = 0;
@@ -87,7 +90,41 @@ inline void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 // cp.async.bulk.tensor.2d ... mbarrier::complete_tx::bytes with a {32 floats, box_rows} box and SWIZZLE_128B
+// shared-memory ranges a kernel declares "being read" (HB_EMU_GUARD_* in the kernel source, no-ops on the device): a TMA
+// write into one of them is a protocol bug the synchronous emulation would otherwise hide
+inline void guard_acquire(uint32_t addr, uint32_t bytes) {
+  std::lock_guard<std::mutex> l(g_mu);
+  Guard& g = g_guards[addr];
+  g.lo = addr; g.hi = addr + bytes; g.count += 1;
+}
+inline void guard_release(uint32_t addr) {
+  std::lock_guard<std::mutex> l(g_mu);
+  Guard& g = g_guards.at(addr);
+  if (--g.count < 0) { std::fprintf(stderr, "tcemu: guard %u released twice\n", addr); std::abort(); }
+}
+inline void guard_check_write(uint32_t dst, uint32_t bytes) {
+  std::lock_guard<std::mutex> l(g_mu);
+  for (const auto& kv : g_guards)
+    if (kv.second.count > 0 && dst < kv.second.hi && kv.second.lo < dst + bytes) {
+      std::fprintf(stderr, "tcemu: TMA write [%u, %u) into a range still being read [%u, %u)\n", dst, dst + bytes, kv.second.lo, kv.second.hi);
+      std::abort();
+    }
+}
 inline void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y) {
+  if (m->plain) {                 // SWIZZLE_NONE: box rows back to back, 16-byte granules
+    const uint32_t rowb = m->box_cols * 4u;
+    if (dst % 128u || rowb % 16u) { std::fprintf(stderr, "tcemu: plain TMA box: destination %u / row of %u bytes not aligned\n", dst, rowb); std::abort(); }
+    guard_check_write(dst, m->box_rows * rowb);
+    for (unsigned r = 0; r < m->box_rows; ++r)
+      for (unsigned c = 0; c < m->box_cols; ++c) {
+        const long long gr = (long long)y + r, gc = (long long)x + c;
+        const float v = (gr >= 0 && gc >= 0 && (unsigned long long)gr < m->rows && (unsigned long long)gc < m->cols) ? m->base[gr * m->ld + gc] : 0.f;
+        std::memcpy(g_smem + dst + r * rowb + c * 4u, &v, 4);
+      }
+    { std::lock_guard<std::mutex> l(g_mu); ++g_tma_count; }
+    complete_tx(bar, m->box_rows * rowb);
+    return;
+  }
   if (dst % 1024u) { std::fprintf(stderr, "tcemu: TMA destination %u is not 1024-byte aligned\n", dst); std::abort(); }
   if (m->box_cols != 32) { std::fprintf(stderr, "tcemu: box must be one 128-byte swizzle span wide\n"); std::abort(); }
   for (unsigned r = 0; r < m->box_rows; ++r)
@@ -136,6 +173,12 @@ inline void tmem_ld32(uint32_t taddr, float* v) {
   // a warp may only touch its own lane quadrant (warp id % 4)
   if ((taddr >> 16) != ((threadIdx.x >> 5) & 3u) * 32u) { std::fprintf(stderr, "tcemu: warp reads a foreign TMEM quadrant\n"); std::abort(); }
   for (int j = 0; j < 32; ++j) v[j] = g_tmem[lane][col + j];
+}
+inline void tmem_ld24(uint32_t taddr, float* v) {              // 32x32b.x16 + .x8: 24 consecutive columns
+  const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31u), col = taddr & 0xFFFFu;
+  if (lane >= 128u || col + 24u > 512u) { std::fprintf(stderr, "tcemu: tcgen05.ld outside TMEM\n"); std::abort(); }
+  if ((taddr >> 16) != ((threadIdx.x >> 5) & 3u) * 32u) { std::fprintf(stderr, "tcemu: warp reads a foreign TMEM quadrant\n"); std::abort(); }
+  for (int j = 0; j < 24; ++j) v[j] = g_tmem[lane][col + j];
 }
 inline void tmem_alloc(uint32_t dst, uint32_t ncols) {
   if (ncols < 32 || ncols > 512 || (ncols & (ncols - 1))) { std::fprintf(stderr, "tcemu: bad TMEM allocation %u\n", ncols); std::abort(); }

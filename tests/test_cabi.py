@@ -35,7 +35,23 @@ def test_struct_sizes_match_header():
     import ctypes as C
     # pointers-only structs: one slot per array entry
     assert C.sizeof(_ext.HbHumorWeights) == 8 * (4 + 4 + 3 + 3 + 4 + 5 + 5 + 4 + 4 + 5 + 20 + 16) + 8
-    assert C.sizeof(_ext.HbLbsModel) == 16 + 8 * 9 + 8 * 2 + 8 + 8 * 3 + 8 * 4 + 8 + 8 * 3 + 8
+    assert C.sizeof(_ext.HbLbsModel) == 16 + 8 * 9 + 8 * 2 + 8 + 8 * 3 + 8 * 4 + 8 + 8 * 3 + 8 + 8 * 2
+
+
+def test_lbs_model_layout_matches_the_compiled_header(tmp_path):
+    """sizeof / offsetof of HbLbsModel as gcc sees include/humor_b200.h against the ctypes mirror (every field)."""
+    import ctypes as C
+    import subprocess
+    fields = [n for n, _ in _ext.HbLbsModel._fields_]
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "humor_b200.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(HbLbsModel));\n' +
+                   ''.join(f'  printf("%zu\\n", offsetof(HbLbsModel, {n}));\n' for n in fields) + '  return 0;\n}\n')
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I' + os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert got[0] == C.sizeof(_ext.HbLbsModel)
+    assert got[1:] == [getattr(_ext.HbLbsModel, n).offset for n in fields]
 
 
 def test_product_has_no_oracle_import():

@@ -145,13 +145,15 @@ def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
     128x256 blend kernel (not yet run on hardware), and for the fused kernel.  All within 2e-5 m of the fp64 oracle."""
     out = run_probe(emul, 'probe_lbs_forms.py', '140', tensor=True)
     assert out['exact_vs_oracle'] < 2e-5
-    for key, want in (('forms_11', [1, 1]), ('forms_22', [2, 2])):
+    for key, want in (('forms_11', [1, 1]), ('forms_22', [2, 2]), ('forms_31', [3, 1])):   # 31: fused blend + group skinning
         f = out[key]
         assert f['used'] == want and f['finite'], (key, f)
         assert f['v_vs_oracle'] < 2e-5 and f['J_vs_oracle'] < 2e-5 and f['v_vs_exact'] < 5e-6, (key, f)
     assert out['fused']['v_vs_oracle'] < 2e-5 and out['fused']['J_vs_oracle'] < 2e-5
     f3 = out['forms_23']                                  # single TF32 pass on the pose columns: inside the 1e-4 m bound
     assert f3['used'] == [2, 3] and f3['finite'] and f3['v_vs_oracle'] < 1e-4 and f3['v_vs_oracle'] > 1e-6, f3
+    f33 = out['forms_33']                                 # the same mixed precision inside the fused kernel
+    assert f33['used'] == [3, 3] and f33['finite'] and f33['v_vs_oracle'] < 1e-4 and f33['v_vs_oracle'] > 1e-6, f33
 
 
 def test_stage3_closure_tensor_precision(emul):

@@ -42,7 +42,7 @@ def configure(skin, blend, slab=512):
     _ext.check(_ext.lib().humor_lbs_configure(skin, blend, slab), 'humor_lbs_configure')
 
 
-@pytest.mark.parametrize('skin,blend,slab', [(2, 1, 512), (1, 2, 512), (2, 2, 512), (2, 2, 256)])
+@pytest.mark.parametrize('skin,blend,slab', [(2, 1, 512), (1, 2, 512), (2, 2, 512), (2, 2, 256), (3, 1, 512)])   # 3 = fused (lbs_fuseg.cuh)
 @pytest.mark.parametrize('n', [300, 1100])
 def test_forms_agree_with_default(bm, skin, blend, slab, n):
     ro, pb, be, tr = rand_pose(n, n)                     # 300: ragged row tile / frame block; 1100: 3 slabs
@@ -78,7 +78,44 @@ def test_forms_match_oracle(bm):
     assert float((g.Jtr.cpu() - o.Jtr).abs().max()) < 2e-5
 
 
+@pytest.mark.parametrize('skin', [2, 3])
+def test_mixed_precision_blend_stays_inside_the_vertex_bound(bm, skin):
+    """blend form 3 (one TF32 pass on the pose-offset k-blocks): <= 1e-4 m against the oracle, visibly different from form 1."""
+    from oracle.smplh_lbs import OracleBodyModel
+    ob = OracleBodyModel(synth.make_smplh_asset(), use_vtx_selector=True)
+    n = 300
+    ro, pb, be, tr = rand_pose(n, 9)
+    o = ob(root_orient=ro.cpu(), pose_body=pb.cpu(), betas=be.cpu(), trans=tr.cpu())
+    try:
+        configure(skin, 3)
+        g = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
+        torch.cuda.synchronize()
+        assert forms_used() == (skin, 3)
+    finally:
+        configure(1, 1)
+    err = float((g.v.cpu() - o.v).abs().max())
+    assert 1e-6 < err < 1e-4, err
+
+
+def test_fused_group_form_over_many_row_tiles(bm):
+    """skin form 3 at a size where every persistent CTA walks several column tiles and most cross a row-tile boundary."""
+    n = 128 * 9 + 5
+    ro, pb, be, tr = rand_pose(n, 21)
+    configure(1, 1)
+    ref = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
+    try:
+        configure(3, 1)
+        got = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
+        again = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
+        torch.cuda.synchronize()
+        assert forms_used() == (3, 1)
+    finally:
+        configure(1, 1)
+    assert torch.isfinite(got.v).all() and torch.equal(got.v, again.v)       # deterministic run to run
+    assert float((got.v - ref.v).abs().max()) < 5e-6
+
+
 def test_configure_rejects_bad_values():
     L = _ext.lib()
-    assert L.humor_lbs_configure(3, 0, 0) != 0 and L.humor_lbs_configure(0, 7, 0) != 0 and L.humor_lbs_configure(0, 0, 64) != 0
+    assert L.humor_lbs_configure(4, 0, 0) != 0 and L.humor_lbs_configure(0, 7, 0) != 0 and L.humor_lbs_configure(0, 0, 64) != 0
     assert L.humor_lbs_configure(0, 0, 0) == 0

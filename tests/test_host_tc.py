@@ -144,3 +144,83 @@ def test_fused_kernel_cross_checks_the_emulation(H):
     ref = np.einsum('nvrc,nvc->nvr', T[..., :3], vp) + T[..., 3] + trans[:, None]
     assert np.isfinite(out).all()
     assert np.abs(out - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+# ---- skin form 3: fused blend + lane = frame group skinning (csrc/lbs_fuseg.cuh), not yet on hardware
+def _fuseg_problem(N, seed):
+    asset = synth.make_smplh_asset()
+    p = pack_smplh(asset, 16)
+    V, K = 6890, 224
+    rng = np.random.RandomState(seed)
+    feat = np.zeros((N, K), np.float32)
+    feat[:, :16] = rng.randn(N, 16).astype(np.float32) * 0.7            # betas
+    feat[:, 16:205] = (rng.randn(N, 189) * 0.3).astype(np.float32)      # R - I at moderate poses
+    feat[:, 205] = 1.0                                                  # the pose kernels write 1 here; blend_t has a zero column
+    bt = np.zeros((p['v3_ld'], K), np.float32)
+    bt[:, :208] = p['blend_t']
+    A = rng.randn(N, 52, 3, 4).astype(np.float32)
+    trans = rng.randn(N, 3).astype(np.float32)
+    vp = feat[:, :208].astype(np.float64) @ p['blend'][:, :3 * V].astype(np.float64) + p['v_template'].astype(np.float64)
+    W = asset['weights'].astype(np.float64)
+    T = np.einsum('vj,njrc->nvrc', W, A.astype(np.float64))
+    ref = np.einsum('nvrc,nvc->nvr', T[..., :3], vp.reshape(N, V, 3)) + T[..., 3] + trans[:, None].astype(np.float64)
+    return p, feat, bt, A, trans, ref
+
+
+def _run_fuseg(H, p, feat, bt, A, trans, grid, fast):
+    N, K, V = feat.shape[0], 224, 6890
+    fh, fl = split_rn(feat)
+    bh, bl = split_rn(bt)
+    out = np.full((N, V, 3), np.nan, np.float32)
+    ntma = ctypes.c_longlong(0)
+    H.h_lbs_fuseg.restype = ctypes.c_longlong
+    nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, N, V, p['num_groups'], P(p['g_start']), P(p['g_joint']),
+                         P(p['g_slot']), P(p['g_w']), P(p['ft_tab']), P(p['v_template']), P(A), P(trans), P(out), grid, fast,
+                         ctypes.byref(ntma))
+    return out, nmma, ntma.value
+
+
+def test_fuseg_slot_schedule_is_consistent():
+    """body_model.fuseg_tables: every slotted entry's joint is resident in its slot whether the CTA arrived incrementally or
+    started fresh at that tile; incremental loads never take a slot the previous tile reads."""
+    p = pack_smplh(synth.make_smplh_asset(), 16)
+    tab, gs, gj, gsl = p['ft_tab'], p['g_start'], p['g_joint'], p['g_slot']
+    nct, ng = tab.shape[0], p['num_groups']
+    assert nct == (ng + 7) // 8 and len(gsl) == len(gj)
+    state = {}                                                   # slot -> joint*12, as left by an incremental walk from tile 0
+    for c in range(nct):
+        fresh = {int(e) >> 16: int(e) & 0xffff for e in tab[c, 2:2 + tab[c, 0]]}
+        inc = {int(e) >> 16: int(e) & 0xffff for e in tab[c, 14:14 + tab[c, 1]]}
+        assert len(fresh) == tab[c, 0] <= 12 and all(0 <= s < 12 for s in fresh)
+        prev_used = set(state) if c else set()
+        assert not (set(inc) & prev_used)                        # a new joint never overwrites a slot tile c-1 may be reading
+        kept = {s: j for s, j in state.items() if s in fresh and fresh[s] == j}
+        state = {**kept, **inc}
+        assert state == fresh                                    # incremental arrival == fresh start
+        for g in range(8 * c, min(8 * c + 8, ng)):
+            for e in range(gs[g], gs[g + 1]):
+                if gsl[e] >= 0:
+                    assert gsl[e] % (128 * 48) == 0 and fresh[gsl[e] // (128 * 48)] == gj[e]
+    assert (gsl < 0).mean() < 0.05                               # SMPL-like locality: few joints are left to global loads
+
+
+@pytest.mark.parametrize('N,grid,fast', [(200, 3, 0), (40, 7, 0), (140, 2, 1)])
+def test_fuseg_kernel_matches_fp64(H, N, grid, fast):
+    """The whole mesh (108 column tiles, the last one 64 operand rows past the planes) x 1-2 row tiles (ragged), CTA chunks that
+    start in the middle of a row and cross into the next one (fresh slot loads + full drain), three-pass and mixed precision."""
+    p, feat, bt, A, trans, ref = _fuseg_problem(N, N + grid)
+    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid, fast)
+    ntiles = ((N + 127) // 128) * 108
+    assert nmma == ntiles * (4 * 3 + 6 * 4 * (1 if fast else 3))
+    assert np.isfinite(out).all()                                # every vertex of every frame written
+    err = np.abs(out - ref).max()
+    scale = max(1.0, np.abs(ref).max())
+    if fast:
+        assert 1e-7 * scale < err < 6e-5 * scale, err            # single pass on the pose columns: visible, inside the 1e-4 m bound
+    else:
+        assert err < 4e-6 * scale, err
+    # operand entries (2 TMA boxes each) + transform slots: at most the fresh list per tile, at least the incremental one
+    ent = ntiles * (8 if fast else 14) * 2
+    tab = p['ft_tab']
+    nrt = (N + 127) // 128
+    assert ent + nrt * int(tab[:, 1].sum()) <= ntma <= ent + nrt * int(tab[:, 1].sum()) + (grid + nrt) * 12

@@ -90,6 +90,8 @@ int humor_lbs_fwd(const HbLbsModel* m, int N, int frames_per_beta, const float* 
                   int num_joints_out, int64_t* launches, hb_stream_t stream);
 /* Kernel forms of the DENSE tensor-core forward (results agree to fp32 rounding; 0 leaves a setting unchanged):
  *   skin_form   1 lane = vertex (lbs_skin_apply_kernel)          2 lane = frame over vertex groups (lbs_skin_group.cuh)
+ *               3 blend + lane = frame skinning fused in one persistent kernel (lbs_fuseg.cuh): blend_form 3 selects its
+ *                 single-pass pose columns, any other value three passes (reported as 1); slab_frames unused
  *   blend_form  1 one 128x128 tile per CTA (umma_gemm3_kernel)   2 persistent 128x256 tiles (lbs_blend.cuh)
  *               3 = 2 with a single TF32 pass on the pose-offset columns (<= 7e-5 m vertex error; forms 1, 2: 1e-6 m)
  *   slab_frames frames per v_posed slab kept in L2 between the two kernels (128..512)

@@ -203,6 +203,13 @@ class LbsModel:
         s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
         s.num_groups = packed['num_groups']
         s.g_slot, s.ft_tab, s.ft_nct = self.t['g_slot'].data_ptr(), self.t['ft_tab'].data_ptr(), packed['ft_nct']
+        # blend form 4: blend_t * 2^10 (exact) - columns 0..31 as tf32 hi/lo planes, columns 32..223 as ONE fp16 plane (the
+        # scale keeps pose offsets down to 1e-7 m in fp16's normal range; the kernel's epilogue scales back)
+        k0 = (bt[:, :32] * 1024.0).contiguous()
+        k0h = _tf32_rn(k0)
+        self.t['blend_k0_hi'], self.t['blend_k0_lo'] = k0h.contiguous(), (k0 - k0h).contiguous()
+        self.t['blend16'] = (bt[:, 32:] * 1024.0).to(torch.float16).contiguous()
+        s.blend_k0_hi, s.blend_k0_lo, s.blend16 = (self.t[k].data_ptr() for k in ('blend_k0_hi', 'blend_k0_lo', 'blend16'))
         self.ws_slot = 0
         s.max_depth = packed['max_depth']
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))

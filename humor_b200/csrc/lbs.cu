@@ -32,7 +32,7 @@ constexpr int TC_KF = 224;
       // feature K padded to a multiple of 32 for the TMA/UMMA tiles
 
 struct LbsWs {
-  float *feat, *A, *dfeat, *dA, *dtr, *feat_hi, *feat_lo, *vposed;
+  float *feat, *A, *dfeat, *dA, *dtr, *feat_hi, *feat_lo, *vposed, *feat16;
   size_t total;
 };
 static LbsWs lbs_carve(float* base, int N) {
@@ -48,6 +48,7 @@ static LbsWs lbs_carve(float* base, int N) {
   w.feat_hi = take(Np * TC_KF);
   w.feat_lo = take(Np * TC_KF);
   w.vposed = take((size_t)TC_SLAB * 20736);
+  w.feat16 = take(Np * 96);                     // [Np][192] halves: fp16 plane of the pose-feature columns (blend form 4)
   w.total = off;
   return w;
 }
@@ -689,7 +690,7 @@ static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + 
 using namespace hb;
 
 extern "C" int humor_lbs_configure(int skin_form, int blend_form, int slab_frames) {
-  if ((skin_form < 0 || skin_form > 3) || (blend_form < 0 || blend_form > 3) ||
+  if ((skin_form < 0 || skin_form > 3) || (blend_form < 0 || blend_form > 4) ||
       (slab_frames != 0 && (slab_frames < 128 || slab_frames > TC_SLAB)))
     return HB_ERR_ARG;
   if (skin_form) g_skin_form = skin_form;
@@ -733,11 +734,22 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
                      m->ft_nct == cdiv(m->num_groups, 8) && (m->num_verts % 2) == 0 && m->v3_ld % 4 == 0;
   if (fuseg) {
     LbsFusegArgs fa;
-    fa.N = N; fa.num_verts = m->num_verts; fa.num_groups = m->num_groups; fa.nrt = fa.nct = 0; fa.fast = g_blend_form == 3;
+    const bool f16 = g_blend_form == 4 && m->blend16 && m->blend_k0_hi && m->blend_k0_lo;
+    fa.N = N; fa.num_verts = m->num_verts; fa.num_groups = m->num_groups; fa.nrt = fa.nct = 0; fa.fast = g_blend_form == 3 || f16;
+    fa.nkb16 = f16 ? 3 : 0; fa.out_scale = f16 ? 0.0009765625f : 1.f;
     fa.g_start = m->g_start; fa.g_joint = m->g_joint; fa.g_slot = m->g_slot; fa.g_w = m->g_w; fa.ft_tab = m->ft_tab;
     fa.v_template = m->v_template; fa.A = ws.A; fa.trans = trans; fa.out = verts;
-    HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_t_hi, m->blend_t_lo, TC_KF, m->v3_ld, TC_KF, fa, st));
-    g_used_skin = 3; g_used_blend = fa.fast ? 3 : 1;
+    if (f16) {
+      // columns 0..31 (betas + first pose columns): three tf32 passes on the 2^10-scaled planes; columns 32..223: one fp16 pass
+      HB_CUDA(launch_feat_f16(ws.feat, LBS_KF, LBS_KF, N, 32, 3, ws.feat16, st));
+      ++nl;
+      HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_k0_hi, m->blend_k0_lo, 32, m->v3_ld, 32, ws.feat16, m->blend16, 192,
+                               fa, st));
+    } else {
+      HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_t_hi, m->blend_t_lo, TC_KF, m->v3_ld, TC_KF, nullptr, nullptr, 0,
+                               fa, st));
+    }
+    g_used_skin = 3; g_used_blend = f16 ? 4 : (fa.fast ? 3 : 1);
     ++nl;
     if (joints && njo == 73) {
       lbs_gather_extra_kernel<<<cdiv(N * 21, 256), 256, 0, st>>>(*m, N, verts, joints);

@@ -28,6 +28,10 @@
 //   `fast`  (blend form 3) k-block 0 (betas + first pose columns: shape offsets of up to 0.3 m) keeps three passes, the other
 //           six run one TF32 pass on the tf32-ROUNDED hi planes: 36 instead of 84 MMAs and 320 instead of 560 KB of operand
 //           planes per tile; <= 7e-5 m.
+//   fp16    (blend form 4) k-block 0 as in `fast`; the remaining pose columns travel as ONE fp16 plane per operand (fp16 has
+//           the 11-bit significand of tf32; the blend planes are pre-scaled by 2^10 so that pose offsets of 1e-6 m stay in
+//           fp16's normal range, the epilogue scales back): 3 entries of 64 halves instead of 6 of 32 floats - 200 KB of
+//           operand planes and 24 MMA issue slots per tile.
 // Barrier protocol (all mbarriers, phases counted per use):
 //   full[s]/empty[s]   operand ring (TMA complete_tx / tcgen05.commit), as lbs_blend_kernel
 //   tfull[b]/tempty[b] TMEM buffer b = tile parity (tcgen05.commit / one arrive per epilogue warp), as lbs_blend_kernel
@@ -91,7 +95,8 @@ static inline void stcs2(float* p, float x, float y) { p[0] = x; p[1] = y; }
 __global__ void __launch_bounds__(FG_THREADS, 1)
 lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                 const __grid_constant__ CUtensorMap tmT, int K, LbsFusegArgs a) {
+                 const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmA16,
+                 const __grid_constant__ CUtensorMap tmB16, int K, LbsFusegArgs a) {
   HB_DYN_SMEM(smem_raw);
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -152,6 +157,14 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             tma_load_2d(st + FG_A_PLANE, pl ? &tmB_lo : &tmB_hi, full0 + 8 * s, kb * UM_BK, n0);
           }
         }
+        for (int kb = 0; kb < a.nkb16; ++kb, ++g) {             // fp16 k-blocks: 64 halves = the same 128-byte rows, same entry
+          const int s = g % FG_RING;
+          mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
+          const uint32_t st = base + s * FG_ENTRY;
+          mbar_expect_tx(full0 + 8 * s, FG_ENTRY);
+          tma_load_2d(st, &tmA16, full0 + 8 * s, kb * 64, m0);
+          tma_load_2d(st + FG_A_PLANE, &tmB16, full0 + 8 * s, kb * 64, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -188,6 +201,18 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           } else {
             umma_commit(empty0 + 8 * sh);
           }
+        }
+        for (int kb = 0; kb < a.nkb16; ++kb) {                  // one fp16 pass: 4 MMAs of K = 16 per 64-wide k-block
+          constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(FG_BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+          const int gh = g++;
+          const int sh = gh % FG_RING;
+          mbar_wait(full0 + 8 * sh, (gh / FG_RING) & 1);
+          tc_fence_after();
+          const uint32_t sth = base + sh * FG_ENTRY;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc16, 1);
+          umma_commit(empty0 + 8 * sh);
         }
         umma_commit(tfull0 + 8 * buf);
       }
@@ -227,7 +252,7 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int nv3 = min(FG_G, a.num_verts - g * FG_G) * 3;  // floats of this group inside the mesh
 #pragma unroll
         for (int i = 0; i < FG_GC; ++i) {
-          p[i] += (i < nv3) ? __ldg(a.v_template + col0 + i) : 0.f;
+          p[i] = fmaf(p[i], a.out_scale, (i < nv3) ? __ldg(a.v_template + col0 + i) : 0.f);
           acc[i] = 0.f;
         }
         const int e0 = __ldg(a.g_start + g), e1 = __ldg(a.g_start + g + 1);

@@ -1,6 +1,9 @@
 // Host side of the tcgen05 GEMM: TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry
 // point, so the library does not link libcuda) and launches.
 #include <cstdlib>
+#ifndef HB_HOST_SHIM
+#include <cuda_fp16.h>
+#endif
 #include "umma_gemm.cuh"
 #include "umma_launch.cuh"
 #include "lbs_fused.cuh"
@@ -52,6 +55,18 @@ static bool make_map_plain(CUtensorMap* m, const float* base, int rows, int cols
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// rows x K fp16 matrix, row stride ld halves; box = {64 halves = 128 B, box_rows}, 128-byte swizzle, OOB reads as zero
+static bool make_map_f16(CUtensorMap* m, const void* base, int rows, int K, int ld, int box_rows) {
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -179,11 +194,12 @@ cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf
 // skin form 3: blend + group skinning in one persistent kernel (lbs_fuseg.cuh).  `a` arrives with the model tables, A, trans,
 // out, N, num_verts, num_groups and fast filled in; tile counts are set here.
 cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
-                             int b_rows, int K, LbsFusegArgs a, cudaStream_t st) {
+                             int b_rows, int K, const void* feat16, const void* bt16, int ld16, LbsFusegArgs a, cudaStream_t st) {
   if (!load_encode()) return cudaErrorNotSupported;
   if (K % UM_BK || ldf % 4 || ldb % 4 || a.N <= 0 || a.num_groups <= 0 || (a.num_verts & 1) ||
       a.num_groups != cdiv(a.num_verts, FG_G) || !a.g_start || !a.g_joint || !a.g_slot || !a.g_w || !a.ft_tab)
     return cudaErrorInvalidValue;
+  if (a.nkb16 < 0 || (a.nkb16 > 0 && (!feat16 || !bt16 || ld16 % 8 || ld16 < 64 * a.nkb16))) return cudaErrorInvalidValue;
   static int sms = 0, want = 0;
   if (!sms) {
     int dev = 0;
@@ -198,15 +214,21 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
   }
   a.nrt = cdiv(a.N, UM_BM);
   a.nct = cdiv(a.num_groups, FG_GPT);
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tt;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16;
   if (!make_map(&ta_hi, feat_hi, a.N, K, ldf, UM_BM) || !make_map(&ta_lo, feat_lo, a.N, K, ldf, UM_BM) ||
       !make_map(&tb_hi, bt_hi, b_rows, K, ldb, FG_BN) || !make_map(&tb_lo, bt_lo, b_rows, K, ldb, FG_BN) ||
       !make_map_plain(&tt, a.A, a.N, 624, 624, 12, UM_BM))
     return cudaErrorInvalidValue;
+  if (a.nkb16 > 0) {
+    if (!make_map_f16(&ta16, feat16, a.N, 64 * a.nkb16, ld16, UM_BM) || !make_map_f16(&tb16, bt16, b_rows, 64 * a.nkb16, ld16, FG_BN))
+      return cudaErrorInvalidValue;
+  } else {                                                    // never dereferenced: any valid descriptor
+    ta16 = ta_hi; tb16 = tb_hi;
+  }
   const int ntiles = a.nrt * a.nct;
   int grid = ntiles < sms ? ntiles : sms;
   if (want > 0 && want < grid) grid = want;
-  lbs_fuseg_kernel<<<grid, FG_THREADS, FG_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tt, K, a);
+  lbs_fuseg_kernel<<<grid, FG_THREADS, FG_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16, K, a);
   return cudaGetLastError();
 }
 
@@ -222,7 +244,30 @@ __global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict
     reinterpret_cast<float4*>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
   }
 }
+// fp16 operand plane of the pose-feature columns (blend form 4): out[n][j] = fp16(feat[n][c0 + j]), j < 64 * nkb16, columns
+// past ncols read as zero.  Round to nearest: the same 11-bit significand the tf32-rounded hi plane carries.
+#ifdef HB_HOST_SHIM
+static inline unsigned short f16_bits(float x) { return tcemu::f32_to_f16_bits(x); }
+#else
+__device__ __forceinline__ unsigned short f16_bits(float x) { return __half_as_ushort(__float2half_rn(x)); }
+#endif
+__global__ void feat_f16_kernel(const float* __restrict__ feat, int ldf, int ncols, int N, int c0, int w, unsigned short* __restrict__ out) {
+  const size_t n = (size_t)N * w;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / w;
+    const int j = (int)(i - r * w);
+    out[i] = f16_bits(c0 + j < ncols ? feat[r * ldf + c0 + j] : 0.f);
+  }
+}
 #ifndef HB_HOST_SHIM
+cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, cudaStream_t st) {
+  if (!feat || !out || N <= 0 || nkb16 <= 0) return cudaErrorInvalidValue;
+  const size_t n = (size_t)N * 64 * nkb16;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  feat_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(feat, ldf, ncols, N, c0, 64 * nkb16, static_cast<unsigned short*>(out));
+  return cudaGetLastError();
+}
 cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
   if (n % 4) return cudaErrorInvalidValue;
   const size_t n4 = n / 4;

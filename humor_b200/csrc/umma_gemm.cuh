@@ -34,7 +34,7 @@ constexpr int UM_BK = 32;          // tf32 elements per stage row = 128 bytes = 
 
 #ifdef HB_HOST_SHIM
 using tcemu::smem_u32; using tcemu::mbar_init; using tcemu::mbar_expect_tx; using tcemu::mbar_wait; using tcemu::mbar_arrive;
-using tcemu::tma_load_2d; using tcemu::umma_tf32; using tcemu::umma_commit; using tcemu::tmem_ld32;
+using tcemu::tma_load_2d; using tcemu::umma_tf32; using tcemu::umma_f16; using tcemu::umma_commit; using tcemu::tmem_ld32;
 using tcemu::tmem_alloc; using tcemu::tmem_relinquish; using tcemu::tmem_dealloc; using tcemu::tc_fence_before;
 using tcemu::tc_fence_after; using tcemu::mbar_fence_init; using tcemu::ld_shared_u32;
 #else
@@ -82,6 +82,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// fp16 x fp16 -> fp32 (K = 16 per instruction); idesc a/b format 0
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

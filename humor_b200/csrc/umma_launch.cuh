@@ -27,7 +27,9 @@ struct LbsFusegArgs {
   int num_verts;
   int num_groups;
   int nrt, nct;            // row tiles (128 frames), column tiles (64 vertices)
-  int fast;
+  int fast;                // 1: only k-block 0 keeps three TF32 passes
+  int nkb16;               // > 0 (blend form 4): after the tf32 k-blocks, this many 64-wide fp16 k-blocks (one pass, kind::f16)
+  float out_scale;         // accumulator -> metres (2^-10 when the blend planes are pre-scaled for the fp16 range, else 1)
   const int* g_start;      // [num_groups + 1]
   const int* g_joint;      // [E] joint * 12
   const int* g_slot;       // [E] byte offset of the entry's slot, -1: transform read from global memory
@@ -38,7 +40,10 @@ struct LbsFusegArgs {
   const float* trans;      // [N][3]
   float* out;              // [N][num_verts][3]
 };
-// bt_* = blend_t hi/lo planes [b_rows][K] (ldb floats per row); the caller fills every field of `a` except nrt / nct
+// bt_* = blend_t hi/lo planes [b_rows][K] (ldb floats per row); the caller fills every field of `a` except nrt / nct.
+// a.nkb16 > 0: feat16 [N][ld16] / bt16 [b_rows][ld16] fp16 planes of the remaining K columns (ld16 halves per row, >= 64 * nkb16)
 cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
-                             int b_rows, int K, LbsFusegArgs a, cudaStream_t st);
+                             int b_rows, int K, const void* feat16, const void* bt16, int ld16, LbsFusegArgs a, cudaStream_t st);
+// fp16 plane of the pose-feature columns [c0, c0 + 64 * nkb16) of feat[N][ldf] (columns >= ncols read as zero)
+cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, cudaStream_t st);
 }  // namespace hb

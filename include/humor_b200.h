@@ -77,6 +77,11 @@ typedef struct HbLbsModel {
   int ft_nct;              /* column tiles = ceil(num_groups / 8); 0: tables absent */
   const int* g_slot;       /* [E] byte offset of entry e's slot in the tile of its group, or -1: read A from global memory */
   const int* ft_tab;       /* [ft_nct][26] n_fresh, n_inc, 12 fresh + 12 incremental loads (joint*12 | slot << 16) */
+  /* blend form 4 (fp16 pose columns, skin form 3 only): blend_t scaled by 2^10 - columns 0..31 as tf32 hi/lo planes
+     [v3_ld][32], columns 32..223 as one fp16 plane [v3_ld][192]; NULL: form unavailable */
+  const float* blend_k0_hi;
+  const float* blend_k0_lo;
+  const void* blend16;
 } HbLbsModel;
 
 /* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs
@@ -94,6 +99,8 @@ int humor_lbs_fwd(const HbLbsModel* m, int N, int frames_per_beta, const float* 
  *                 single-pass pose columns, any other value three passes (reported as 1); slab_frames unused
  *   blend_form  1 one 128x128 tile per CTA (umma_gemm3_kernel)   2 persistent 128x256 tiles (lbs_blend.cuh)
  *               3 = 2 with a single TF32 pass on the pose-offset columns (<= 7e-5 m vertex error; forms 1, 2: 1e-6 m)
+ *               4 (with skin_form 3 only) = 3 with those columns as fp16 operand planes (same 11-bit significand, half the
+ *                 bytes, kind::f16 MMAs)
  *   slab_frames frames per v_posed slab kept in L2 between the two kernels (128..512)
  * Process-wide; not to be changed while a call is in flight.  Environment defaults: HB_LBS_SKIN, HB_LBS_BLEND, HB_LBS_SLAB. */
 int humor_lbs_configure(int skin_form, int blend_form, int slab_frames);

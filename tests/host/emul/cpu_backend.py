@@ -39,6 +39,11 @@ def install(lib_path):
         s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
         s.num_groups, s.max_depth = packed['num_groups'], packed['max_depth']
         s.g_slot, s.ft_tab, s.ft_nct = self.t['g_slot'].data_ptr(), self.t['ft_tab'].data_ptr(), packed['ft_nct']
+        k0 = (bt[:, :32] * 1024.0).contiguous()
+        k0h = split(k0)[0]
+        self.t['blend_k0_hi'], self.t['blend_k0_lo'] = k0h, (k0 - k0h).contiguous()
+        self.t['blend16'] = (bt[:, 32:] * 1024.0).to(torch.float16).contiguous()
+        s.blend_k0_hi, s.blend_k0_lo, s.blend16 = (self.t[k].data_ptr() for k in ('blend_k0_hi', 'blend_k0_lo', 'blend16'))
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))
         self.fused_wk = packed['fused_wk']
         self.ws_slot = 0

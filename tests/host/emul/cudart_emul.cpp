@@ -64,7 +64,8 @@ const std::map<std::string, Thunk>& registry() {
          RUN((hb_emu::umma_gemm3_kernel<BN, EPI, 1>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(hb_emu::GemmEpi, 11)))); }},
       UMMA_THUNK(64, 0) UMMA_THUNK(64, 1) UMMA_THUNK(64, 2) UMMA_THUNK(128, 0) UMMA_THUNK(128, 1) UMMA_THUNK(128, 2)
       {"hb::lbs_blend_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_blend_kernel(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(cf, 7), A(float*, 8), A(int, 9), A(int, 10))); }},
-      {"hb::lbs_fuseg_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fuseg_kernel(MAP(0), MAP(1), MAP(2), MAP(3), MAP(4), A(int, 5), A(hb_emu::LbsFusegArgs, 6))); }},
+      {"hb::lbs_fuseg_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fuseg_kernel(MAP(0), MAP(1), MAP(2), MAP(3), MAP(4), MAP(5), MAP(6), A(int, 7), A(hb_emu::LbsFusegArgs, 8))); }},
+      {"hb::feat_f16_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::feat_f16_kernel(A(cf, 0), A(int, 1), A(int, 2), A(int, 3), A(int, 4), A(int, 5), A(unsigned short*, 6))); }},
       {"hb::lbs_fused_kernel<4>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<4>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
       {"hb::lbs_fused_kernel<8>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<8>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
       {"hb::split_hilo_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::split_hilo_kernel(A(cf, 0), A(float*, 1), A(float*, 2), A(size_t, 3))); }},
@@ -114,10 +115,12 @@ int cudaMemsetAsync(void* p, int v, size_t n, void*) { std::memset(p, v, n); ret
 // cuTensorMapEncodeTiled: 2-D fp32 maps only; the emulated description is stored in the caller's (128-byte) CUtensorMap
 static int emul_encode_tiled(void* m, int dtype, unsigned rank, void* base, const unsigned long long* gdim, const unsigned long long* gstr,
                              const unsigned* box, const unsigned*, int, int swizzle, int, int) {
-  if (rank != 2 || dtype != 7 /* CU_TENSOR_MAP_DATA_TYPE_FLOAT32 */ || (swizzle != 3 /* SWIZZLE_128B */ && swizzle != 0 /* NONE */) ||
-      (gstr[0] % 16) || ((box[0] * 4) % 16) || box[0] > 256 || box[1] > 256)
+  const bool half = dtype == 6;   /* CU_TENSOR_MAP_DATA_TYPE_FLOAT16 */
+  const unsigned esz = half ? 2 : 4;
+  if (rank != 2 || (dtype != 7 /* FLOAT32 */ && !half) || (swizzle != 3 /* SWIZZLE_128B */ && swizzle != 0 /* NONE */) ||
+      (half && swizzle != 3) || (gstr[0] % 16) || ((box[0] * esz) % 16) || box[0] > 256 || box[1] > 256)
     return 1;
-  CUtensorMap e{static_cast<const float*>(base), gdim[1], gdim[0], gstr[0] / 4, box[0], box[1], swizzle == 0 ? 1u : 0u};
+  CUtensorMap e{static_cast<const float*>(base), gdim[1], gdim[0], gstr[0] / esz, box[0], box[1], swizzle == 0 ? 1u : 0u, half ? 1u : 0u};
   std::memcpy(m, &e, sizeof(e));
   return 0;
 }

@@ -9,5 +9,6 @@ struct CUtensorMap {
   unsigned long long ld;          // row stride in floats
   unsigned box_cols, box_rows;    // box = {32 floats = 128 B (one swizzle span), box_rows}
   unsigned plain;                 // 0: SWIZZLE_128B (default); 1: SWIZZLE_NONE, box rows of box_cols floats back to back
+  unsigned half;                  // 0: fp32 elements (default); 1: fp16 elements - base points at halves, ld / cols / box_cols count halves
 };
 #define __grid_constant__

@@ -126,6 +126,20 @@ inline void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x,
     return;
   }
   if (dst % 1024u) { std::fprintf(stderr, "tcemu: TMA destination %u is not 1024-byte aligned\n", dst); std::abort(); }
+  if (m->half) {                  // fp16 elements, SWIZZLE_128B: 64 halves per box row
+    if (m->box_cols != 64) { std::fprintf(stderr, "tcemu: fp16 box must be one 128-byte swizzle span (64 halves) wide\n"); std::abort(); }
+    const uint16_t* hb = reinterpret_cast<const uint16_t*>(m->base);
+    for (unsigned r = 0; r < m->box_rows; ++r)
+      for (unsigned c = 0; c < 64; ++c) {
+        const long long gr = (long long)y + r, gc = (long long)x + c;
+        const uint16_t v = (gr >= 0 && gc >= 0 && (unsigned long long)gr < m->rows && (unsigned long long)gc < m->cols) ? hb[gr * m->ld + gc] : (uint16_t)0;
+        const uint32_t a = swz128(dst + r * 128u + c * 2u);
+        std::memcpy(g_smem + a, &v, 2);
+      }
+    { std::lock_guard<std::mutex> l(g_mu); ++g_tma_count; }
+    complete_tx(bar, m->box_rows * 128u);
+    return;
+  }
   if (m->box_cols != 32) { std::fprintf(stderr, "tcemu: box must be one 128-byte swizzle span wide\n"); std::abort(); }
   for (unsigned r = 0; r < m->box_rows; ++r)
     for (unsigned c = 0; c < 32; ++c) {
@@ -166,6 +180,38 @@ inline void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t 
   std::lock_guard<std::mutex> l(g_mu);
   ++g_mma_count;
 }
+// tcgen05.mma.cta_group::1.kind::f16 with fp16 operands (idesc a/b format 0), M = 128, K = 16 per instruction (32 bytes), fp32
+// accumulation into the same TMEM columns the tf32 MMAs use
+inline void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  const int M = (int)((idesc >> 24) & 0x1F) << 4, N = (int)((idesc >> 17) & 0x3F) << 3;
+  if (M != 128 || N < 8 || N > 256 || (N % 16)) { std::fprintf(stderr, "tcemu: unsupported UMMA shape %dx%d\n", M, N); std::abort(); }
+  if (((idesc >> 7) & 7) != 0 || ((idesc >> 10) & 7) != 0 || ((idesc >> 4) & 3) != 1) { std::fprintf(stderr, "tcemu: kind::f16 expects F16 x F16 -> F32\n"); std::abort(); }
+  if (((adesc >> 61) & 7) != 2 || ((bdesc >> 61) & 7) != 2) { std::fprintf(stderr, "tcemu: descriptors must be SWIZZLE_128B\n"); std::abort(); }
+  const uint32_t a0 = (uint32_t)(adesc & 0x3FFF) << 4, b0 = (uint32_t)(bdesc & 0x3FFF) << 4;
+  const uint32_t asbo = (uint32_t)((adesc >> 32) & 0x3FFF) << 4, bsbo = (uint32_t)((bdesc >> 32) & 0x3FFF) << 4;
+  static thread_local float A[128][16], B[256][16];
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 16; ++k) {
+      _Float16 v; std::memcpy(&v, g_smem + swz128(a0 + (m / 8) * asbo + (m % 8) * 128u + k * 2u), 2);
+      A[m][k] = (float)v;
+    }
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < 16; ++k) {
+      _Float16 v; std::memcpy(&v, g_smem + swz128(b0 + (n / 8) * bsbo + (n % 8) * 128u + k * 2u), 2);
+      B[n][k] = (float)v;
+    }
+  const uint32_t lane0 = tmem_d >> 16, col0 = tmem_d & 0xFFFFu;
+  if (lane0 != 0 || col0 + (uint32_t)N > 512u) { std::fprintf(stderr, "tcemu: accumulator outside TMEM\n"); std::abort(); }
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float s = accum ? g_tmem[m][col0 + n] : 0.f;
+      for (int k = 0; k < 16; ++k) s += A[m][k] * B[n][k];
+      g_tmem[m][col0 + n] = s;
+    }
+  std::lock_guard<std::mutex> l(g_mu);
+  ++g_mma_count;
+}
+inline uint16_t f32_to_f16_bits(float x) { const _Float16 h = (_Float16)x; uint16_t b; std::memcpy(&b, &h, 2); return b; }
 inline void umma_commit(uint32_t bar) { mbar_arrive(bar); }      // the MMAs above ran synchronously
 inline void tmem_ld32(uint32_t taddr, float* v) {
   const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31u), col = taddr & 0xFFFFu;

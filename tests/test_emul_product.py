@@ -85,7 +85,11 @@ def test_stage3_closure_matches_reference_golden(emul, name):
         assert e < 1e-4, (k, e)
 
 
-RUN_TOL = {'trans': 2e-5, 'root_orient': 2e-5, 'pose_body': 2e-5, 'betas': 2e-5, 'latent_pose': 2e-5, 'latent_motion': 2e-4,
+# Tolerances of the END-TO-END comparison = ~10x the rounding-noise floor of the optimisation itself, measured by rebuilding the
+# emulated kernels with FMA contraction (g++ -mfma -ffp-contract=fast, what nvcc does on the device): the same run then moves by
+# trans 3e-6, pose_body 3e-6, stage3_verts3d 5e-6 and latent_motion 2.3e-4 (the latent is weakly determined: 7 L-BFGS iterations
+# amplify last-bit differences).  Measured against the reference on the plain build: trans 6e-7 ... latent_motion 2e-5.
+RUN_TOL = {'trans': 3e-5, 'root_orient': 3e-5, 'pose_body': 3e-5, 'betas': 2e-5, 'latent_pose': 3e-5, 'latent_motion': 2e-3,
            'floor_plane': 5e-5, 'stage3_verts3d': 5e-5, 'stage1_joints3d': 2e-5, 'stage2_joints3d': 2e-5}
 
 
@@ -154,6 +158,8 @@ def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
     assert f3['used'] == [2, 3] and f3['finite'] and f3['v_vs_oracle'] < 1e-4 and f3['v_vs_oracle'] > 1e-6, f3
     f33 = out['forms_33']                                 # the same mixed precision inside the fused kernel
     assert f33['used'] == [3, 3] and f33['finite'] and f33['v_vs_oracle'] < 1e-4 and f33['v_vs_oracle'] > 1e-6, f33
+    f34 = out['forms_34']                                 # ... with the pose columns as fp16 planes (feat_f16_kernel + kind::f16)
+    assert f34['used'] == [3, 4] and f34['finite'] and f34['v_vs_oracle'] < 1e-4 and f34['v_vs_oracle'] > 1e-6, f34
 
 
 def test_stage3_closure_tensor_precision(emul):

@@ -78,8 +78,8 @@ def test_forms_match_oracle(bm):
     assert float((g.Jtr.cpu() - o.Jtr).abs().max()) < 2e-5
 
 
-@pytest.mark.parametrize('skin', [2, 3])
-def test_mixed_precision_blend_stays_inside_the_vertex_bound(bm, skin):
+@pytest.mark.parametrize('skin,blend', [(2, 3), (3, 3), (3, 4)])          # (3, 4): the pose columns as fp16 planes
+def test_mixed_precision_blend_stays_inside_the_vertex_bound(bm, skin, blend):
     """blend form 3 (one TF32 pass on the pose-offset k-blocks): <= 1e-4 m against the oracle, visibly different from form 1."""
     from oracle.smplh_lbs import OracleBodyModel
     ob = OracleBodyModel(synth.make_smplh_asset(), use_vtx_selector=True)
@@ -87,10 +87,10 @@ def test_mixed_precision_blend_stays_inside_the_vertex_bound(bm, skin):
     ro, pb, be, tr = rand_pose(n, 9)
     o = ob(root_orient=ro.cpu(), pose_body=pb.cpu(), betas=be.cpu(), trans=tr.cpu())
     try:
-        configure(skin, 3)
+        configure(skin, blend)
         g = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
         torch.cuda.synchronize()
-        assert forms_used() == (skin, 3)
+        assert forms_used() == (skin, blend)
     finally:
         configure(1, 1)
     err = float((g.v.cpu() - o.v).abs().max())

@@ -167,16 +167,24 @@ def _fuseg_problem(N, seed):
     return p, feat, bt, A, trans, ref
 
 
-def _run_fuseg(H, p, feat, bt, A, trans, grid, fast):
+def _run_fuseg(H, p, feat, bt, A, trans, grid, fast, f16=False):
     N, K, V = feat.shape[0], 224, 6890
     fh, fl = split_rn(feat)
-    bh, bl = split_rn(bt)
     out = np.full((N, V, 3), np.nan, np.float32)
     ntma = ctypes.c_longlong(0)
     H.h_lbs_fuseg.restype = ctypes.c_longlong
-    nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, N, V, p['num_groups'], P(p['g_start']), P(p['g_joint']),
-                         P(p['g_slot']), P(p['g_w']), P(p['ft_tab']), P(p['v_template']), P(A), P(trans), P(out), grid, fast,
-                         ctypes.byref(ntma))
+    tabs = (N, V, p['num_groups'], P(p['g_start']), P(p['g_joint']), P(p['g_slot']), P(p['g_w']), P(p['ft_tab']), P(p['v_template']),
+            P(A), P(trans), P(out), grid)
+    if f16:     # blend form 4: columns 0..31 three tf32 passes on planes scaled by 2^10, columns 32..223 one fp16 pass
+        bh, bl = split_rn(np.ascontiguousarray(bt[:, :32] * np.float32(1024)))
+        f16p = np.ascontiguousarray(feat[:, 32:].astype(np.float16))
+        b16p = np.ascontiguousarray((bt[:, 32:] * np.float32(1024)).astype(np.float16))
+        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), 32, bt.shape[0], 32, *tabs, 1, ctypes.byref(ntma), P(f16p), P(b16p), 192, 3,
+                             ctypes.c_float(2.0 ** -10))
+    else:
+        bh, bl = split_rn(bt)
+        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, *tabs, fast, ctypes.byref(ntma), None, None, 0, 0,
+                             ctypes.c_float(1.0))
     return out, nmma, ntma.value
 
 
@@ -224,3 +232,19 @@ def test_fuseg_kernel_matches_fp64(H, N, grid, fast):
     tab = p['ft_tab']
     nrt = (N + 127) // 128
     assert ent + nrt * int(tab[:, 1].sum()) <= ntma <= ent + nrt * int(tab[:, 1].sum()) + (grid + nrt) * 12
+
+
+def test_fuseg_kernel_fp16_pose_columns(H):
+    """blend form 4: the pose columns past k-block 0 as ONE fp16 plane per operand (kind::f16, K = 16 per MMA): 12 + 12 MMAs and
+    5 ring entries per tile; fp16 carries tf32's 11-bit significand, so the error matches the single-pass tf32 form."""
+    N, grid = 140, 2
+    p, feat, bt, A, trans, ref = _fuseg_problem(N, N + grid)
+    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid, 1, f16=True)
+    ntiles = 2 * 108
+    assert nmma == ntiles * (4 * 3 + 3 * 4)
+    assert np.isfinite(out).all()
+    err = np.abs(out - ref).max()
+    scale = max(1.0, np.abs(ref).max())
+    assert 1e-7 * scale < err < 6e-5 * scale, err
+    fast, _, _ = _run_fuseg(H, p, feat, bt, A, trans, grid, 1)
+    assert np.abs(fast - ref).max() < 6e-5 * scale and np.abs(out - fast).max() < 8e-5 * scale

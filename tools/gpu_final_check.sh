@@ -8,14 +8,14 @@ mkdir -p gpurun_out
 # 2. stand-alone dense LBS forward per form (ms, GB/s, forms used, bitwise difference vs form 1)
 (timeout 90 python tools/lbs_forms_time.py 2>&1 | tail -1) > gpurun_out/lbs_forms_time.json
 # 3. step time with each candidate (the dense pass runs on a side stream under the decoder chain: persistent CTAs may delay it)
-for cfg in "2 1" "2 2" "2 3" "3 1" "3 3"; do set -- $cfg
+for cfg in "2 1" "2 2" "2 3" "3 1" "3 3" "3 4"; do set -- $cfg
   (timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --lbs-skin $1 --lbs-blend $2 2>gpurun_out/bench_s$1b$2.err) > gpurun_out/bench_s$1b$2.json
 done
 # 3b. skin form 3 holds every SM it runs on (223 KB of shared memory, all of TMEM) for the whole pass: with fewer persistent
 #     CTAs the decoder chain of the main stream keeps some SMs
 (HB_LBS_FUSEG_CTAS=100 timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --lbs-skin 3 --lbs-blend 3 2>gpurun_out/bench_s3b3_100.err) > gpurun_out/bench_s3b3_100.json
 # 4. the tests that round 1 could only run on the emulation
-(timeout 150 python -m pytest tests/test_gpu_zz_stage12.py tests/test_gpu_zz_run_e2e.py -x -q 2>&1 | tail -6) > gpurun_out/t_stage12_e2e.log
+(HB_TEST_UNVERIFIED=1 timeout 150 python -m pytest tests/test_gpu_zz_stage12.py tests/test_gpu_zz_run_e2e.py -x -q 2>&1 | tail -6) > gpurun_out/t_stage12_e2e.log
 tail -n 3 gpurun_out/t_forms.log gpurun_out/t_stage12_e2e.log
 cat gpurun_out/lbs_forms_time.json
 for f in gpurun_out/bench_s*.json; do python - "$f" <<'PY'

@@ -27,7 +27,7 @@ pb = (torch.randn(N, 63, generator=g) * 0.3).cuda()
 be = (torch.randn(B, 16, generator=g) * 0.5).cuda()
 tr = torch.randn(N, 3, generator=g).cuda()
 L = _ext.lib()
-cfgs = [(1, 1), (2, 1), (1, 2), (2, 2), (2, 3), (3, 1), (3, 3)]
+cfgs = [(1, 1), (2, 1), (1, 2), (2, 2), (2, 3), (3, 1), (3, 3), (3, 4)]
 if args.only:
     cfgs = [tuple(int(x) for x in args.only.split(','))]
 ref = None

@@ -68,17 +68,16 @@ constexpr int FG_THREADS = 64 + 32 * FG_EPI_WARPS;
 constexpr int FG_TAB = 2 + 2 * FG_NSLOT;            // ints per column tile of ft_tab
 
 #ifndef HB_HOST_SHIM
-// tcgen05.ld of one vertex group: 24 consecutive columns of the thread's TMEM lane
+// tcgen05.ld of one vertex group: 24 consecutive columns of the thread's TMEM lane, as three naturally aligned 8-column loads
+// (group offsets are multiples of 24, i.e. of 8 but not of 16)
 __device__ __forceinline__ void tmem_ld24(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr) : "memory");
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
-               : "r"(taddr + 16u) : "memory");
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[8 * c]), "=r"(r[8 * c + 1]), "=r"(r[8 * c + 2]), "=r"(r[8 * c + 3]), "=r"(r[8 * c + 4]), "=r"(r[8 * c + 5]),
+                   "=r"(r[8 * c + 6]), "=r"(r[8 * c + 7])
+                 : "r"(taddr + 8u * c) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void stcs2(float* p, float x, float y) { __stcs(reinterpret_cast<float2*>(p), make_float2(x, y)); }

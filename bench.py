@@ -245,6 +245,9 @@ def run_product(args):
         left = _time_left() - 20.0
         out['torch_cuda_port'] = port_cuda_child(args, limit_s=min(120.0, left)) if left >= 25.0 else \
             {'batch': 64, 'error': 'skipped: the run\'s time limit was nearly spent'}
+        # the opt-in kernel forms of the dense LBS forward, verified against the default forms and timed stand-alone on this GPU
+        # (separate child processes: a form that faults must not take the measurement down).  The step above ran forms 1/1.
+        out['roofline_candidates'] = lbs_candidates(B, T, hbm_peak)
     _PARTIAL = None
     print(json.dumps(out))
 
@@ -386,6 +389,43 @@ def port_cuda_child(args, batch=64, limit_s=150):
         return res
     except Exception as e:  # noqa: BLE001
         return {'batch': batch, 'error': f'{type(e).__name__}: {str(e)[:200]}'}
+
+
+def lbs_candidates(B, T, hbm_peak):
+    """tools/lbs_forms_time.py in bounded children: per opt-in form {used, ms, GBps, frac, max |dv| vs forms 1/1, deterministic,
+    verified}.  Two groups, the hardware-riskier fused forms last, so a fault there keeps the records of the first group."""
+    tool = os.path.join(ROOT, 'tools', 'lbs_forms_time.py')
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'HB_LBS_SKIN', 'HB_LBS_BLEND'):
+        env.pop(k, None)
+    recs = []
+    for forms in ('2,1;1,2;2,2;2,3', '3,1;3,3;3,4'):
+        left = _time_left() - 20.0
+        if left < 40.0:
+            recs.append({'forms': forms, 'error': 'skipped: the run\'s time limit was nearly spent'})
+            continue
+        cmd = [sys.executable, tool, '--forms', forms, '--seqs', str(B), '--frames-per-seq', str(T), '--reps', '5', '--peak-gbs', str(hbm_peak)]
+        got, err = [], None
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=min(90.0, left), env=env)
+            text, rc, tail = r.stdout, r.returncode, r.stderr[-300:]
+        except subprocess.TimeoutExpired as e:
+            text = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or '')
+            rc, tail = 'timeout', ''
+        except Exception as e:  # noqa: BLE001
+            text, rc, tail = '', type(e).__name__, str(e)[:300]
+        for line in text.splitlines():
+            if line.startswith('{'):
+                try:
+                    got.append(json.loads(line))
+                except ValueError:
+                    pass
+        recs.extend(got)
+        if rc != 0:
+            done = {(g['skin'], g['blend']) for g in got}
+            missing = [f for f in forms.split(';') if tuple(int(x) for x in f.split(',')) not in done]
+            recs.append({'forms': ';'.join(missing), 'error': f'child ended with {rc}', 'stderr_tail': tail})
+    return recs
 
 
 def cpu_threads():

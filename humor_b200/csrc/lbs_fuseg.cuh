@@ -287,6 +287,21 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             }
           }
         }
+        if (a.direct_store) {
+          // A/B variant (HB_LBS_FUSEG_DIRECT=1): every thread writes its frame's 96 bytes itself - 12 STG.64 and no staging,
+          // but 32 different lines per instruction
+          if (f0 + lane < a.N) {
+            float* dst = a.out + ((size_t)(f0 + lane) * a.num_verts + (size_t)g * FG_G) * 3;
+#pragma unroll
+            for (int q2 = 0; q2 < FG_GC / 2; ++q2) {
+              const float x = acc[2 * q2] + ((2 * q2) % 3 == 0 ? t0 : ((2 * q2) % 3 == 1 ? t1 : t2));
+              const float y = acc[2 * q2 + 1] + ((2 * q2 + 1) % 3 == 0 ? t0 : ((2 * q2 + 1) % 3 == 1 ? t1 : t2));
+              if (2 * q2 + 1 < nv3) stcs2(dst + 2 * q2, x, y);
+              else if (2 * q2 < nv3) __stcs(dst + 2 * q2, x);
+            }
+          }
+          continue;
+        }
         // park the group (lane = frame), then two 96-byte frame rows per store instruction
         float* Sr = S + lane * FG_SLD;
 #pragma unroll

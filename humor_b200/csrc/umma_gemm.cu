@@ -200,7 +200,7 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
       a.num_groups != cdiv(a.num_verts, FG_G) || !a.g_start || !a.g_joint || !a.g_slot || !a.g_w || !a.ft_tab)
     return cudaErrorInvalidValue;
   if (a.nkb16 < 0 || (a.nkb16 > 0 && (!feat16 || !bt16 || ld16 % 8 || ld16 < 64 * a.nkb16))) return cudaErrorInvalidValue;
-  static int sms = 0, want = 0;
+  static int sms = 0, want = 0, direct = 0;
   if (!sms) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -211,7 +211,9 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
     // kernels of other streams (the latency-bound decoder chain runs next to the dense pass)
     const char* w = getenv("HB_LBS_FUSEG_CTAS");
     want = w ? atoi(w) : 0;
+    direct = getenv("HB_LBS_FUSEG_DIRECT") ? 1 : 0;
   }
+  a.direct_store = direct;
   a.nrt = cdiv(a.N, UM_BM);
   a.nct = cdiv(a.num_groups, FG_GPT);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16;

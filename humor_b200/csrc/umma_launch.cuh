@@ -30,6 +30,7 @@ struct LbsFusegArgs {
   int fast;                // 1: only k-block 0 keeps three TF32 passes
   int nkb16;               // > 0 (blend form 4): after the tf32 k-blocks, this many 64-wide fp16 k-blocks (one pass, kind::f16)
   float out_scale;         // accumulator -> metres (2^-10 when the blend planes are pre-scaled for the fp16 range, else 1)
+  int direct_store;        // 1: lane = frame stores straight from registers (A/B variant), 0: staged row stores; set by the launcher
   const int* g_start;      // [num_groups + 1]
   const int* g_joint;      // [E] joint * 12
   const int* g_slot;       // [E] byte offset of the entry's slot, -1: transform read from global memory

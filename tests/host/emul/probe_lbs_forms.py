@@ -39,7 +39,7 @@ m.struct.use_umma = 0
 exact = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
 out['exact_vs_oracle'] = float((exact.v - o.v).abs().max())
 m.struct.use_umma = 1
-for skin, blend in [(1, 1), (2, 2), (2, 3), (3, 1), (3, 3), (3, 4)]:
+for skin, blend in [(int(f[0]), int(f[1])) for f in (sys.argv[4].split(';') if len(sys.argv) > 4 else ['11', '22', '23', '31', '33', '34'])]:
     assert L.humor_lbs_configure(skin, blend, 512) == 0
     g = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
     out[f'forms_{skin}{blend}'] = {'used': used(), 'v_vs_oracle': float((g.v - o.v).abs().max()), 'J_vs_oracle': float((g.Jtr - o.Jtr).abs().max()),

@@ -46,7 +46,7 @@ long long h_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const
   CUtensorMap a16{static_cast<const float*>(feat16), (unsigned long long)N, 64ull * nkb16, (unsigned long long)ld16, 64, UM_BM, 0, 1};
   CUtensorMap b16{static_cast<const float*>(bt16), (unsigned long long)b_rows, 64ull * nkb16, (unsigned long long)ld16, 64, FG_BN, 0, 1};
   LbsFusegArgs a;
-  a.nkb16 = nkb16; a.out_scale = out_scale;
+  a.nkb16 = nkb16; a.out_scale = out_scale; a.direct_store = getenv("HB_LBS_FUSEG_DIRECT") ? 1 : 0;
   a.N = N; a.num_verts = num_verts; a.num_groups = num_groups; a.nrt = cdiv(N, UM_BM); a.nct = cdiv(num_groups, FG_GPT); a.fast = fast;
   a.g_start = g_start; a.g_joint = g_joint; a.g_slot = g_slot; a.g_w = g_w; a.ft_tab = ft_tab;
   a.v_template = v_template; a.A = A; a.trans = trans; a.out = out;

@@ -147,7 +147,7 @@ def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
     """humor_lbs_fwd's tensor-core path on the emulated tcgen05 kernels: the library's own dispatch AND its own TMA-descriptor
     code (cuTensorMapEncodeTiled is emulated) for the default forms, for forms (2,2) = lane-per-frame skinning + persistent
     128x256 blend kernel (not yet run on hardware), and for the fused kernel.  All within 2e-5 m of the fp64 oracle."""
-    out = run_probe(emul, 'probe_lbs_forms.py', '140', tensor=True)
+    out = run_probe(emul, 'probe_lbs_forms.py', '140', '11;22;23;31', tensor=True)
     assert out['exact_vs_oracle'] < 2e-5
     for key, want in (('forms_11', [1, 1]), ('forms_22', [2, 2]), ('forms_31', [3, 1])):   # 31: fused blend + group skinning
         f = out[key]
@@ -156,10 +156,22 @@ def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
     assert out['fused']['v_vs_oracle'] < 2e-5 and out['fused']['J_vs_oracle'] < 2e-5
     f3 = out['forms_23']                                  # single TF32 pass on the pose columns: inside the 1e-4 m bound
     assert f3['used'] == [2, 3] and f3['finite'] and f3['v_vs_oracle'] < 1e-4 and f3['v_vs_oracle'] > 1e-6, f3
-    f33 = out['forms_33']                                 # the same mixed precision inside the fused kernel
-    assert f33['used'] == [3, 3] and f33['finite'] and f33['v_vs_oracle'] < 1e-4 and f33['v_vs_oracle'] > 1e-6, f33
-    f34 = out['forms_34']                                 # ... with the pose columns as fp16 planes (feat_f16_kernel + kind::f16)
-    assert f34['used'] == [3, 4] and f34['finite'] and f34['v_vs_oracle'] < 1e-4 and f34['v_vs_oracle'] > 1e-6, f34
+    # forms (3, 3) / (3, 4) - the fused kernel's mixed-precision modes: tests/test_host_tc.py at kernel level, and (3, 4) through this
+    # dispatch in test_forms_verification_tool below; `python tests/host/emul/probe_lbs_forms.py ... 140 "33;34"` runs them here
+
+
+def test_forms_verification_tool(emul):
+    """tools/lbs_forms_time.measure (what bench.py's `roofline_candidates` children run on the device) on the emulation: every
+    form reports the kernels it really launched, agrees with form (1, 1) inside its tolerance, is deterministic, and differs
+    from form (1, 1) in the last bits."""
+    out = run_probe(emul, 'probe_forms_tool.py', '3,1;3,4', tensor=True)
+    recs = {(r['skin'], r['blend']): r for r in out['recs']}
+    assert set(recs) == {(3, 1), (3, 4)}
+    for key, r in recs.items():
+        assert r['verified'] and r['used'] == list(key) and r['deterministic'] and r['finite'] and r['frames'] == 129, r
+        assert r['ms'] > 0 and r['GBps'] > 0 and 0 < r['frac'] < 1
+    assert not recs[(3, 1)]['bitwise_equal_to_11']
+    assert recs[(3, 1)]['max_abs_diff_vs_11'] < 5e-6 < recs[(3, 4)]['max_abs_diff_vs_11'] < 1e-4
 
 
 def test_stage3_closure_tensor_precision(emul):

@@ -1,12 +1,12 @@
 #!/bin/bash
-# First GPU call of the next round (≈2-3 min of box time): put the kernel forms that round 1 verified only on the CPU
+# First GPU call of the next round (≈10 min of box time): put the kernel forms that round 1 verified only on the CPU
 # emulation onto the B200, time them, and decide the defaults from the STEP time.
-#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/gpu_final_check.sh'
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_final_check.sh'
 mkdir -p gpurun_out
 # 1. correctness of the opt-in forms (asserts humor_lbs_forms_used == requested and a last-bit difference vs form 1)
 (HB_TEST_UNVERIFIED=1 timeout 180 python -m pytest tests/test_gpu_zz_lbs_forms.py -x -q 2>&1 | tail -12) > gpurun_out/t_forms.log
 # 2. stand-alone dense LBS forward per form (ms, GB/s, forms used, bitwise difference vs form 1)
-(timeout 90 python tools/lbs_forms_time.py 2>&1 | tail -1) > gpurun_out/lbs_forms_time.json
+(timeout 120 python tools/lbs_forms_time.py --peak-gbs 6490.5 2>gpurun_out/lbs_forms_time.err) > gpurun_out/lbs_forms_time.jsonl
 # 3. step time with each candidate (the dense pass runs on a side stream under the decoder chain: persistent CTAs may delay it)
 for cfg in "2 1" "2 2" "2 3" "3 1" "3 3" "3 4"; do set -- $cfg
   (timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --lbs-skin $1 --lbs-blend $2 2>gpurun_out/bench_s$1b$2.err) > gpurun_out/bench_s$1b$2.json
@@ -17,7 +17,7 @@ done
 # 4. the tests that round 1 could only run on the emulation
 (HB_TEST_UNVERIFIED=1 timeout 150 python -m pytest tests/test_gpu_zz_stage12.py tests/test_gpu_zz_run_e2e.py -x -q 2>&1 | tail -6) > gpurun_out/t_stage12_e2e.log
 tail -n 3 gpurun_out/t_forms.log gpurun_out/t_stage12_e2e.log
-cat gpurun_out/lbs_forms_time.json
+cat gpurun_out/lbs_forms_time.jsonl
 for f in gpurun_out/bench_s*.json; do python - "$f" <<'PY'
 import json, sys
 try:

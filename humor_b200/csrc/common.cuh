@@ -2,9 +2,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef HB_OK          /* same values as include/humor_b200.h (sources that do not include the public header) */
 #define HB_OK 0
 #define HB_ERR_ARG 1001
 #define HB_ERR_WORKSPACE 1002
+#endif
 
 // every launch is followed by this: the C-ABI returns the cudaError_t (non-zero) to the caller
 #define HB_LAUNCH_CHECK()                           \

@@ -24,6 +24,11 @@ extern "C" {
 
 typedef struct CUstream_st* hb_stream_t; /* == cudaStream_t */
 
+/* return codes: 0, a cudaError_t (1..999), or one of */
+#define HB_OK 0
+#define HB_ERR_ARG 1001       /* NULL / out-of-range argument; nothing was launched */
+#define HB_ERR_WORKSPACE 1002 /* workspace_bytes smaller than the *_workspace_bytes() query; nothing was launched */
+
 #define HB_NUM_VERTS 6890
 #define HB_NUM_JOINTS 52
 #define HB_NUM_JOINTS_X 73 /* + 21 vertex-picked joints (smplx VertexJointSelector) */

@@ -61,3 +61,50 @@ def test_product_has_no_oracle_import():
         if f.endswith('.py'):
             txt = open(os.path.join(pkg, f)).read()
             assert 'import oracle' not in txt and 'from oracle' not in txt, f
+
+
+def test_argument_errors_are_reported_before_any_launch(built_lib):
+    """Error behaviour of the boundary (include/humor_b200.h): bad arguments and short workspaces come back as HB_ERR_* codes
+    from the argument checks, i.e. before any CUDA call - which is why this runs without a GPU.  (The reference's only native
+    boundary, the chamfer module, merely printf's launch errors: chamfer_distance.cu:155-157.)"""
+    import ctypes as C
+    L = built_lib
+    ARG, WS = 1001, 1002
+    hdr = open(os.path.join(ROOT, 'include', 'humor_b200.h')).read()
+    assert '#define HB_ERR_ARG 1001' in hdr and '#define HB_ERR_WORKSPACE 1002' in hdr
+    buf = (C.c_float * 4096)()
+    p = C.cast(buf, C.c_void_p)
+    m = _ext.HbLbsModel()
+    nl = C.c_int64(0)
+    # LBS: NULL model / inputs, bad joint count, N <= 0, workspace too small
+    assert L.humor_lbs_fwd(None, 4, 1, p, p, p, p, p, 1 << 30, None, 0, p, p, 73, C.byref(nl), None) == ARG
+    assert L.humor_lbs_fwd(C.byref(m), 0, 1, p, p, p, p, p, 1 << 30, None, 0, p, p, 73, C.byref(nl), None) == ARG
+    assert L.humor_lbs_fwd(C.byref(m), 4, 1, None, p, p, p, p, 1 << 30, None, 0, p, p, 73, C.byref(nl), None) == ARG
+    assert L.humor_lbs_fwd(C.byref(m), 4, 1, p, p, p, p, p, 1 << 30, None, 0, p, p, 60, C.byref(nl), None) == ARG
+    assert L.humor_lbs_fwd(C.byref(m), 4, 0, p, p, p, p, p, 1 << 30, None, 0, p, p, 73, C.byref(nl), None) == ARG
+    assert L.humor_lbs_fwd(C.byref(m), 4, 1, p, p, p, p, p, 16, None, 0, p, p, 73, C.byref(nl), None) == WS
+    assert L.humor_lbs_bwd(None, 4, 1, p, p, p, p, p, 1 << 30, None, 0, p, p, 73, p, p, p, p, C.byref(nl), None) == ARG
+    assert L.humor_lbs_bwd(C.byref(m), 4, 1, p, p, p, p, p, 16, None, 0, p, p, 73, p, p, p, p, C.byref(nl), None) == WS
+    # rollout: NULL weights / state, short workspace
+    w = _ext.HbHumorWeights()
+    assert L.humor_rollout_fwd(None, 2, 3, p, p, p, 1 << 30, p, p, C.byref(nl), None) == ARG
+    assert L.humor_rollout_fwd(C.byref(w), 2, 3, None, p, p, 1 << 30, p, p, C.byref(nl), None) == ARG
+    assert L.humor_rollout_fwd(C.byref(w), 0, 3, p, p, p, 1 << 30, p, p, C.byref(nl), None) == ARG
+    assert L.humor_rollout_fwd(C.byref(w), 2, 3, p, p, p, 16, p, p, C.byref(nl), None) == WS
+    assert L.humor_rollout_bwd(C.byref(w), 2, 3, p, 16, p, p, p, p, C.byref(nl), None) == WS
+    assert L.humor_rollout_bwd(C.byref(w), 2, 3, None, 1 << 30, p, p, p, p, C.byref(nl), None) == ARG
+    # energies, GMM, rotations, chamfer, kernel-form switches
+    assert L.humor_fit_losses(None, C.byref(nl), None) == ARG
+    a = _ext.HbFitArgs()
+    a.B, a.T, a.njx = 2, 3, 60
+    assert L.humor_fit_losses(C.byref(a), C.byref(nl), None) == ARG
+    assert L.humor_gmm_nll(0, 4, 2, p, p, p, p, p, p, p, None) == ARG
+    assert L.humor_gmm_nll(2, 4, 2, None, p, p, p, p, p, p, None) == ARG
+    assert L.humor_rodrigues_fwd(0, p, p, None) == ARG and L.humor_rodrigues_fwd(4, None, p, None) == ARG
+    assert L.humor_mat2aa_bwd(4, p, None, p, None) == ARG
+    assert L.humor_chamfer_fwd(-1, 4, p, 4, p, p, p, p, p, C.byref(nl), None) == ARG
+    assert L.humor_chamfer_fwd(1, 4, None, 4, p, p, p, p, p, C.byref(nl), None) == ARG
+    assert L.humor_chamfer_fwd(1, 4, p, 4, p, p, None, p, p, C.byref(nl), None) == ARG        # dist1 without idx1
+    assert L.humor_lbs_configure(4, 0, 0) == ARG and L.humor_lbs_configure(0, 5, 0) == ARG and L.humor_lbs_configure(0, 0, 64) == ARG
+    assert L.humor_lbs_configure(0, 0, 0) == 0
+    assert nl.value == 0

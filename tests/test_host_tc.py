@@ -248,3 +248,32 @@ def test_fuseg_kernel_fp16_pose_columns(H):
     assert 1e-7 * scale < err < 6e-5 * scale, err
     fast, _, _ = _run_fuseg(H, p, feat, bt, A, trans, grid, 1)
     assert np.abs(fast - ref).max() < 6e-5 * scale and np.abs(out - fast).max() < 8e-5 * scale
+
+
+def test_fuseg_kernel_on_a_mesh_without_locality(H):
+    """Nothing in the slot schedule assumes SMPL: with skinning weights scattered over all 52 joints (up to 8 influences per
+    vertex, every 64-vertex tile touching ~50 joints) most group entries find no slot and the epilogue reads their transforms
+    from global memory - same result."""
+    asset = dict(synth.make_smplh_asset())
+    rng = np.random.RandomState(3)
+    V = 6890
+    W = np.zeros((V, 52))
+    for v in range(V):
+        js = rng.choice(52, size=rng.randint(1, 9), replace=False)
+        W[v, js] = rng.rand(len(js)) + 0.05
+    asset['weights'] = (W / W.sum(1, keepdims=True)).astype(np.float32)
+    p = pack_smplh(asset, 16)
+    assert p['wk'] == 8 and (p['g_slot'] < 0).mean() > 0.5 and p['ft_tab'][:, 0].max() == 12
+    N, K = 70, 224
+    feat = np.zeros((N, K), np.float32)
+    feat[:, :205] = (rng.randn(N, 205) * 0.3).astype(np.float32)
+    bt = np.zeros((p['v3_ld'], K), np.float32)
+    bt[:, :208] = p['blend_t']
+    A = rng.randn(N, 52, 3, 4).astype(np.float32)
+    trans = rng.randn(N, 3).astype(np.float32)
+    out, nmma, _ = _run_fuseg(H, p, feat, bt, A, trans, 2, 0)
+    vp = feat[:, :208].astype(np.float64) @ p['blend'][:, :3 * V].astype(np.float64) + p['v_template'].astype(np.float64)
+    T = np.einsum('vj,njrc->nvrc', asset['weights'].astype(np.float64), A.astype(np.float64))
+    ref = np.einsum('nvrc,nvc->nvr', T[..., :3], vp.reshape(N, V, 3)) + T[..., 3] + trans[:, None].astype(np.float64)
+    assert nmma == 108 * 84 and np.isfinite(out).all()
+    assert np.abs(out - ref).max() < 4e-6 * max(1.0, np.abs(ref).max())

@@ -249,11 +249,20 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         tmem_ld24(trow + buf * FG_BN + (h * (FG_GPT / 2) + gg) * FG_GC, p);
         const int col0 = g * FG_GC;
         const int nv3 = min(FG_G, a.num_verts - g * FG_G) * 3;  // floats of this group inside the mesh
+        if (nv3 == FG_GC) {                                     // warp-uniform; a group's 96 template bytes are 16-byte aligned
+          const float4* tp = reinterpret_cast<const float4*>(a.v_template + col0);
 #pragma unroll
-        for (int i = 0; i < FG_GC; ++i) {
-          p[i] = fmaf(p[i], a.out_scale, (i < nv3) ? __ldg(a.v_template + col0 + i) : 0.f);
-          acc[i] = 0.f;
+          for (int i4 = 0; i4 < FG_GC / 4; ++i4) {
+            const float4 tv = __ldg(tp + i4);
+            p[4 * i4] = fmaf(p[4 * i4], a.out_scale, tv.x); p[4 * i4 + 1] = fmaf(p[4 * i4 + 1], a.out_scale, tv.y);
+            p[4 * i4 + 2] = fmaf(p[4 * i4 + 2], a.out_scale, tv.z); p[4 * i4 + 3] = fmaf(p[4 * i4 + 3], a.out_scale, tv.w);
+          }
+        } else {                                                // the mesh's last, partial group
+#pragma unroll
+          for (int i = 0; i < FG_GC; ++i) p[i] = fmaf(p[i], a.out_scale, (i < nv3) ? __ldg(a.v_template + col0 + i) : 0.f);
         }
+#pragma unroll
+        for (int i = 0; i < FG_GC; ++i) acc[i] = 0.f;
         const int e0 = __ldg(a.g_start + g), e1 = __ldg(a.g_start + g + 1);
         // one entry of look-ahead on the (warp-uniform) slot and weight row
         int son = 0, jn = 0;

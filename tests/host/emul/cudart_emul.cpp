@@ -4,8 +4,9 @@
 // the SIMT shim (tests/host/shim) and run with the launch's grid/block on host memory.  "Device pointers" are host pointers.
 // Covers every SIMT kernel (lbs.cu, rot.cu, losses.cu, chamfer.cu, rollout.cu) and, on the functional tcgen05 / TMA / TMEM
 // emulation of tests/host/shim/tc_emul.h, the single-CTA tcgen05 kernels (umma_gemm3_kernel<.,.,1>, lbs_fused_kernel,
-// lbs_blend_kernel); cuTensorMapEncodeTiled is emulated too, so the library's own descriptor code runs.  Thread-block
-// clusters are not emulated: run with HB_NO_SPLITK=1.
+// lbs_blend_kernel, lbs_fuseg_kernel) and the 4-CTA-cluster split-K instantiations of umma_gemm3_kernel (the CTAs of a cluster
+// run concurrently, DSMEM stores and cluster barriers are emulated); cuTensorMapEncodeTiled is emulated too, so the library's
+// own descriptor code runs.
 // Not a product path: nothing in humor_b200/ references it; the product rejects CPU tensors unless a test patches that out.
 #include <cxxabi.h>
 #include <dlfcn.h>
@@ -29,7 +30,8 @@ template <class T> T& arg(void** a, int i) { return *static_cast<T*>(a[i]); }
 typedef const float* cf;
 typedef const int* ci;
 #define A(T, i) arg<T>(a, i)
-#define RUN(...) shim::launch(g, b, [&] { __VA_ARGS__; })
+unsigned g_cluster_x = 1;        // cluster dimension of the launch being executed (cudaLaunchKernelExC attribute)
+#define RUN(...) shim::launch_cluster(g, b, g_cluster_x, [&] { __VA_ARGS__; })
 const std::map<std::string, Thunk>& registry() {
   static const std::map<std::string, Thunk> r = {
       {"hb::lbs_pose_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(float*, 11), A(float*, 12))); }},
@@ -63,6 +65,12 @@ const std::map<std::string, Thunk>& registry() {
          tcemu::reset();                                                                                                        \
          RUN((hb_emu::umma_gemm3_kernel<BN, EPI, 1>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(hb_emu::GemmEpi, 11)))); }},
       UMMA_THUNK(64, 0) UMMA_THUNK(64, 1) UMMA_THUNK(64, 2) UMMA_THUNK(128, 0) UMMA_THUNK(128, 1) UMMA_THUNK(128, 2)
+#define UMMA_SPLITK_THUNK(EPI)   /* split-K over a 4-CTA cluster: the four CTAs run concurrently, partials meet through DSMEM stores */      \
+      {"hb::umma_gemm3_kernel<64, " #EPI ", 4>", [](dim3 g, dim3 b, void** a) {                                                 \
+         tcemu::reset();                                                                                                        \
+         if (g_cluster_x != 4) { std::fprintf(stderr, "cudart_emul: split-K GEMM launched without its 4-CTA cluster\n"); std::abort(); }  \
+         RUN((hb_emu::umma_gemm3_kernel<64, EPI, 4>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(hb_emu::GemmEpi, 11)))); }},
+      UMMA_SPLITK_THUNK(0) UMMA_SPLITK_THUNK(1) UMMA_SPLITK_THUNK(2)
       {"hb::lbs_blend_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_blend_kernel(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(cf, 7), A(float*, 8), A(int, 9), A(int, 10))); }},
       {"hb::lbs_fuseg_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fuseg_kernel(MAP(0), MAP(1), MAP(2), MAP(3), MAP(4), MAP(5), MAP(6), A(int, 7), A(hb_emu::LbsFusegArgs, 8))); }},
       {"hb::feat_f16_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::feat_f16_kernel(A(cf, 0), A(int, 1), A(int, 2), A(int, 3), A(int, 4), A(int, 5), A(unsigned short*, 6))); }},
@@ -101,9 +109,20 @@ int run_kernel(const void* f, dim3 g, dim3 b, void** args) {
 }  // namespace
 
 extern "C" {
-int cudaLaunchKernel(const void* f, dim3 g, dim3 b, void** a, size_t, void*) { return run_kernel(f, g, b, a); }
-struct EmulLaunchConfig { dim3 grid; dim3 block; size_t dynamicSmemBytes; void* stream; void* attrs; unsigned numAttrs; };   // cudaLaunchConfig_t
-int cudaLaunchKernelExC(const EmulLaunchConfig* c, const void* f, void** a) { return run_kernel(f, c->grid, c->block, a); }
+int cudaLaunchKernel(const void* f, dim3 g, dim3 b, void** a, size_t, void*) { g_cluster_x = 1; return run_kernel(f, g, b, a); }
+struct EmulLaunchAttr { int id; int pad; unsigned val[16]; };                       // cudaLaunchAttribute: id, padding to 8, 64-byte value
+struct EmulLaunchConfig { dim3 grid; dim3 block; size_t dynamicSmemBytes; void* stream; EmulLaunchAttr* attrs; unsigned numAttrs; };   // cudaLaunchConfig_t
+int cudaLaunchKernelExC(const EmulLaunchConfig* c, const void* f, void** a) {
+  g_cluster_x = 1;
+  for (unsigned i = 0; i < c->numAttrs; ++i)
+    if (c->attrs[i].id == 4 /* cudaLaunchAttributeClusterDimension */) {
+      if (c->attrs[i].val[1] != 1 || c->attrs[i].val[2] != 1) { std::fprintf(stderr, "cudart_emul: only x-clusters are emulated\n"); return 1; }
+      g_cluster_x = c->attrs[i].val[0];
+    }
+  const int rc = run_kernel(f, c->grid, c->block, a);
+  g_cluster_x = 1;
+  return rc;
+}
 int cudaPeekAtLastError() { return 0; }
 // the shim header already has a static cudaGetLastError for the kernel sources: export the runtime symbol under an asm label
 int emul_get_last_error() __asm__("cudaGetLastError");

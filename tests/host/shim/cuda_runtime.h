@@ -1,8 +1,9 @@
 // Test infrastructure: a minimal SIMT-on-CPU stand-in for <cuda_runtime.h>, found first on the include path when a
 // kernel source is compiled with g++ for tests/host/*.cpp.  One std::thread per CUDA thread of a block, blocks run one
-// after another; __syncthreads() is a real barrier, __shared__ becomes a function-local static (shared by the threads
-// of the running block).  Enough to execute the index arithmetic, tiling, tails and barrier structure of plain SIMT
-// kernels on the host with the same source the GPU runs.  Not a product path: nothing in humor_b200/ includes this.
+// after another (the blocks of a thread-block cluster together); __syncthreads() is a real barrier, __shared__ becomes a
+// function-local static (shared by the threads of the running block; kernels launched as clusters must use dynamic shared
+// memory).  Enough to execute the index arithmetic, tiling, tails and barrier structure of plain SIMT kernels on the host
+// with the same source the GPU runs.  Not a product path: nothing in humor_b200/ includes this.
 #pragma once
 #include <algorithm>
 #include <barrier>
@@ -36,48 +37,69 @@ static const cudaError_t cudaSuccess = 0;
 static inline cudaError_t cudaGetLastError() { return 0; }
 
 namespace shim {
+// per-CTA state of the running launch.  Blocks normally run one after another; the blocks of a thread-block CLUSTER run
+// concurrently (launch_cluster), each with its own context, so everything a kernel thread touches is reached through
+// thread-local pointers.
+struct Cta {
+  std::unique_ptr<std::barrier<>> bar;
+  std::vector<std::unique_ptr<std::barrier<>>> warp_bars;
+  std::vector<uint32_t> warp_xchg;         // one slot per thread: shuffle exchange area
+};
 inline thread_local uint3 t_idx{0, 0, 0};
-inline uint3 b_idx{0, 0, 0};
+inline thread_local uint3 t_bidx{0, 0, 0};
+inline thread_local Cta* t_cta = nullptr;
+inline thread_local unsigned t_crank = 0;          // rank of the thread's CTA inside its cluster
+inline thread_local std::barrier<>* t_cluster_bar = nullptr;
+inline unsigned cluster_size = 1;
 inline dim3 b_dim, g_dim;
-inline std::barrier<>* block_bar = nullptr;
-inline std::vector<std::unique_ptr<std::barrier<>>> warp_bars;
 inline thread_local int t_lin = 0;
-inline std::vector<uint32_t> warp_xchg;     // one slot per thread: shuffle exchange area
-alignas(1024) inline float dyn_smem_buf[64 * 1024];    // 256 KB: dynamic shared memory of the running block
+alignas(1024) inline float dyn_smem_buf[64 * 1024];    // 256 KB: dynamic shared memory of the running block (plain SIMT kernels)
 inline float* dyn_smem_f32() { return dyn_smem_buf; }
-inline void sync_block() { block_bar->arrive_and_wait(); }
-inline void sync_warp() { warp_bars[t_lin / 32]->arrive_and_wait(); }
+inline void sync_block() { t_cta->bar->arrive_and_wait(); }
+inline void sync_warp() { t_cta->warp_bars[t_lin / 32]->arrive_and_wait(); }
+inline void sync_cluster() { t_cluster_bar->arrive_and_wait(); }
 
-// Runs `body` once per thread of every block of the grid.
+// Runs `body` once per thread of every block of the grid; `csize` consecutive blocks along x form a cluster and run together.
 template <class F>
-void launch(dim3 grid, dim3 block, F body) {
+void launch_cluster(dim3 grid, dim3 block, unsigned csize, F body) {
   g_dim = grid;
   b_dim = block;
+  cluster_size = csize;
   const int nt = (int)(block.x * block.y * block.z);
-  warp_xchg.assign(nt, 0u);
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        b_idx = {bx, by, bz};
-        std::barrier<> bar(nt);
-        block_bar = &bar;
-        warp_bars.clear();
-        for (int w = 0; w < (nt + 31) / 32; ++w) warp_bars.emplace_back(new std::barrier<>(std::min(32, nt - 32 * w)));
+      for (unsigned bx0 = 0; bx0 < grid.x; bx0 += csize) {
+        const unsigned nc = std::min(csize, grid.x - bx0);
+        std::vector<Cta> ctas(nc);
+        for (auto& c : ctas) {
+          c.bar.reset(new std::barrier<>(nt));
+          for (int w = 0; w < (nt + 31) / 32; ++w) c.warp_bars.emplace_back(new std::barrier<>(std::min(32, nt - 32 * w)));
+          c.warp_xchg.assign(nt, 0u);
+        }
+        std::barrier<> cbar((std::ptrdiff_t)nc * nt);
         std::vector<std::thread> th;
-        th.reserve(nt);
-        for (int t = 0; t < nt; ++t)
-          th.emplace_back([=, &body] {
-            t_lin = t;
-            t_idx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
-            body();
-          });
+        th.reserve((size_t)nc * nt);
+        for (unsigned r = 0; r < nc; ++r)
+          for (int t = 0; t < nt; ++t)
+            th.emplace_back([=, &body, &ctas, &cbar] {
+              t_lin = t;
+              t_idx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+              t_bidx = {bx0 + r, by, bz};
+              t_cta = &ctas[r];
+              t_crank = r;
+              t_cluster_bar = &cbar;
+              body();
+            });
         for (auto& x : th) x.join();
       }
+  cluster_size = 1;
 }
+template <class F>
+void launch(dim3 grid, dim3 block, F body) { launch_cluster(grid, block, 1u, body); }
 }  // namespace shim
 
 #define threadIdx (shim::t_idx)
-#define blockIdx (shim::b_idx)
+#define blockIdx (shim::t_bidx)
 #define blockDim (shim::b_dim)
 #define gridDim (shim::g_dim)
 #define __global__
@@ -104,16 +126,16 @@ static inline void __stcs(float* p, float v) { *p = v; }
 static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
-  shim::warp_xchg[shim::t_lin] = __float_as_uint(v);
+  shim::t_cta->warp_xchg[shim::t_lin] = __float_as_uint(v);
   shim::sync_warp();
-  const float r = __uint_as_float(shim::warp_xchg[(shim::t_lin & ~31) | ((shim::t_lin ^ lane_mask) & 31)]);
+  const float r = __uint_as_float(shim::t_cta->warp_xchg[(shim::t_lin & ~31) | ((shim::t_lin ^ lane_mask) & 31)]);
   shim::sync_warp();
   return r;
 }
 static inline float __shfl_sync(unsigned, float v, int src) {
-  shim::warp_xchg[shim::t_lin] = __float_as_uint(v);
+  shim::t_cta->warp_xchg[shim::t_lin] = __float_as_uint(v);
   shim::sync_warp();
-  const float r = __uint_as_float(shim::warp_xchg[(shim::t_lin & ~31) | (src & 31)]);
+  const float r = __uint_as_float(shim::t_cta->warp_xchg[(shim::t_lin & ~31) | (src & 31)]);
   shim::sync_warp();
   return r;
 }

@@ -7,7 +7,10 @@
 //   * TMA 2-D tile loads with SWIZZLE_128B (16-byte chunk index XOR (address bits 7..9)), out-of-range elements = 0,
 //   * tcgen05.mma kind::tf32, M = 128, K = 8 per instruction, operands read through K-major SWIZZLE_128B descriptors
 //     (start address, SBO) exactly as issued by the kernels, operands truncated to tf32, fp32 accumulation into TMEM,
-//   * TMEM as [128 lanes][512 columns] fp32, tcgen05.ld 32x32b.x32, alloc/dealloc, tcgen05.commit -> mbarrier arrive.
+//   * TMEM as [128 lanes][512 columns] fp32, tcgen05.ld 32x32b.x32 / x8, alloc/dealloc, tcgen05.commit -> mbarrier arrive,
+//   * un-swizzled and fp16 TMA boxes, tcgen05.mma kind::f16, read guards on shared-memory ranges (lbs_fuseg_kernel),
+//   * thread-block clusters: one state (shared-memory window, TMEM, mbarriers) per CTA of the running cluster, the CTAs run
+//     concurrently (shim::launch_cluster); %cluster_ctarank, barrier.cluster, mapa + st.shared::cluster (DSMEM stores).
 // What it checks: tile/index arithmetic, descriptor offsets, barrier protocol (phases, buffer reuse), epilogues.  What it
 // cannot check: that the hardware interprets descriptors / swizzles the way modelled here (lbs_fused_kernel, which IS
 // verified on the B200, runs through the same emulation as a cross-check of the model), timing, real asynchrony.
@@ -24,26 +27,39 @@ namespace tcemu {
 
 constexpr uint32_t WINDOW_BYTES = 256 * 1024;
 constexpr uint32_t DYN_OFFSET = 16;
-alignas(1024) inline uint8_t g_smem[WINDOW_BYTES];
-inline float g_tmem[128][512];
-inline std::mutex g_mu;
+constexpr int MAX_CLUSTER = 8;
+constexpr uint32_t RANK_SHIFT = 24;                    // mapa result: (rank + 1) << 24 | offset in that CTA's window
 struct Bar { int expected = 0, pending = 0; long long tx = 0; int phase = 0; };
-inline std::map<uint32_t, Bar> g_bars;
-inline long long g_mma_count = 0, g_tma_count = 0;
 struct Guard { uint32_t lo, hi; int count; };
-inline std::map<uint32_t, Guard> g_guards;
+// one instance per CTA of the running cluster (rank = shim::t_crank; single-CTA launches use rank 0)
+struct CtaState {
+  alignas(1024) uint8_t smem[WINDOW_BYTES];
+  float tmem[128][512];
+  std::map<uint32_t, Bar> bars;
+  std::map<uint32_t, Guard> guards;
+};
+inline CtaState g_cta[MAX_CLUSTER];
+inline std::mutex g_mu;
+inline long long g_mma_count = 0, g_tma_count = 0;
+inline CtaState& cur() { return g_cta[shim::t_crank]; }
+#define g_smem (tcemu::cur().smem)
+#define g_tmem (tcemu::cur().tmem)
+#define g_bars (tcemu::cur().bars)
+#define g_guards (tcemu::cur().guards)
 
-inline uint8_t* dyn_smem() { return g_smem + DYN_OFFSET; }
-inline uint32_t smem_u32(const void* p) { return (uint32_t)(static_cast<const uint8_t*>(p) - g_smem); }
+inline uint8_t* dyn_smem() { return cur().smem + DYN_OFFSET; }
+inline uint32_t smem_u32(const void* p) { return (uint32_t)(static_cast<const uint8_t*>(p) - cur().smem); }
 inline uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
 inline float tf32_trunc(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xffffe000u; std::memcpy(&x, &u, 4); return x; }
 
 inline void reset() {
   std::lock_guard<std::mutex> l(g_mu);
-  g_bars.clear();
-  g_guards.clear();
-  std::memset(g_smem, 0xff, sizeof(g_smem));          // NaN patterns: reading a byte nobody wrote shows
-  for (auto& r : g_tmem) for (auto& v : r) v = __builtin_nanf("");
+  for (auto& c : g_cta) {
+    c.bars.clear();
+    c.guards.clear();
+    std::memset(c.smem, 0xff, sizeof(c.smem));            // NaN patterns: reading a byte nobody wrote shows
+    for (auto& r : c.tmem) for (auto& v : r) v = __builtin_nanf("");
+  }
   g_mma_count = g_tma_count = 0;
 }
 inline void complete_if_done(Bar& b) {
@@ -237,11 +253,19 @@ inline void tc_fence_before() {}
 inline void tc_fence_after() {}
 inline uint32_t ld_shared_u32(uint32_t addr) { uint32_t v; std::memcpy(&v, g_smem + addr, 4); return v; }
 inline float4 ld_shared_v4(uint32_t addr) { float4 v; std::memcpy(&v, g_smem + addr, 16); return v; }
-// thread-block clusters are not emulated: split-K instantiations compile, a run that reaches them aborts
-inline uint32_t cluster_ctarank() { return 0; }
-[[noreturn]] inline void no_clusters() { std::fprintf(stderr, "tcemu: thread-block clusters are not emulated (set HB_NO_SPLITK=1)\n"); std::abort(); }
-inline void cluster_sync_all() { no_clusters(); }
-inline uint32_t map_to_cta(uint32_t, uint32_t) { no_clusters(); }
-inline void st_cluster_v4(uint32_t, float, float, float, float) { no_clusters(); }
+// thread-block clusters: the CTAs of a cluster run concurrently (shim::launch_cluster), each on its own CtaState.  What the
+// split-K GEMM uses: %cluster_ctarank, barrier.cluster (all threads of all CTAs), mapa + st.shared::cluster (DSMEM stores).
+inline uint32_t cluster_ctarank() { return shim::t_crank; }
+inline void cluster_sync_all() { shim::sync_cluster(); }
+inline uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+  if (rank >= shim::cluster_size || rank >= (uint32_t)MAX_CLUSTER || local >= WINDOW_BYTES) { std::fprintf(stderr, "tcemu: mapa to CTA %u of a %u-CTA cluster / offset %u\n", rank, shim::cluster_size, local); std::abort(); }
+  return ((rank + 1u) << RANK_SHIFT) | local;
+}
+inline void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  const uint32_t r = addr >> RANK_SHIFT, off = addr & ((1u << RANK_SHIFT) - 1u);
+  if (r == 0 || r > shim::cluster_size || off + 16u > WINDOW_BYTES || (off & 15u)) { std::fprintf(stderr, "tcemu: bad st.shared::cluster address %u\n", addr); std::abort(); }
+  const float v[4] = {a, b, c, d};
+  std::memcpy(g_cta[r - 1].smem + off, v, 16);
+}
 
 }  // namespace tcemu

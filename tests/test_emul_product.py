@@ -35,8 +35,8 @@ def emul(built_lib, tmp_path_factory):
 def run_probe(emul, script, *args, tensor=False):
     rt, lib = emul
     env = dict(os.environ, LD_PRELOAD=rt, CUDA_VISIBLE_DEVICES='')
-    if tensor:          # tcgen05 kernels on the functional emulation; thread-block clusters are not emulated
-        env.update(HB_EMUL_TENSOR='1', HB_NO_SPLITK='1')
+    if tensor:          # tcgen05 kernels on the functional emulation, incl. the 4-CTA-cluster split-K GEMMs of the decoder chain
+        env.update(HB_EMUL_TENSOR='1')
     r = subprocess.run([sys.executable, os.path.join(HERE, 'host', 'emul', script), ROOT, lib] + list(args),
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=900)
     lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
@@ -158,6 +158,21 @@ def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
     assert f3['used'] == [2, 3] and f3['finite'] and f3['v_vs_oracle'] < 1e-4 and f3['v_vs_oracle'] > 1e-6, f3
     # forms (3, 3) / (3, 4) - the fused kernel's mixed-precision modes: tests/test_host_tc.py at kernel level, and (3, 4) through this
     # dispatch in test_forms_verification_tool below; `python tests/host/emul/probe_lbs_forms.py ... 140 "33;34"` runs them here
+
+
+def test_umma_gemm_single_cta_and_split_k_cluster(emul):
+    """humor_umma_gemm through the library's dispatch: few-tile shapes with K >= 256 take the split-K path (a 4-CTA thread-block
+    cluster whose partial accumulators meet in the leader's shared memory through DSMEM stores between two cluster barriers;
+    the emulation runs the four CTAs concurrently), the others the single-CTA tiles; ragged M / N / K-per-rank."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'host', 'emul', 'probe_umma.py'), ROOT, emul[1]], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=900,
+                       env=dict(os.environ, LD_PRELOAD=emul[0], CUDA_VISIBLE_DEVICES='', HB_EMUL_TENSOR='1', HB_EMUL_TRACE='1'))
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith('{')][-1])
+    for c in out['cases']:
+        assert c['rc'] == 0 and c['finite'] and c['rel_err'] < 3e-6, c
+    launched = [l.split()[1] + ' ' + ' '.join(l.split()[2:4]) for l in r.stderr.splitlines() if l.startswith('EMUL hb::umma_gemm3_kernel')]
+    assert sum(', 4>' in k for k in launched) == 2 and sum(', 1>' in k for k in launched) == 2, launched
 
 
 def test_forms_verification_tool(emul):

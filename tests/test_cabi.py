@@ -108,3 +108,14 @@ def test_argument_errors_are_reported_before_any_launch(built_lib):
     assert L.humor_lbs_configure(4, 0, 0) == ARG and L.humor_lbs_configure(0, 5, 0) == ARG and L.humor_lbs_configure(0, 0, 64) == ARG
     assert L.humor_lbs_configure(0, 0, 0) == 0
     assert nl.value == 0
+
+
+def test_integration_doc_stub_mirrors_the_struct():
+    """The ctypes stub INTEGRATION.md shows a maintainer must list every field of HbLbsModel (the library reads all of them)."""
+    import ctypes as C
+    src = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    code = src[src.index('P, I = C.c_void_p, C.c_int'):src.index('# the first 13 fields')]
+    ns = {'C': C}
+    exec(code, ns)
+    assert [n for n, _ in ns['HbLbsModel']._fields_] == [n for n, _ in _ext.HbLbsModel._fields_]
+    assert C.sizeof(ns['HbLbsModel']) == C.sizeof(_ext.HbLbsModel)

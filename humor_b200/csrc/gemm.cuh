@@ -23,6 +23,9 @@ struct GemmEpi {
   int ldxh;
   int Cch;              // number of normalised channels
   int gsize;            // channels per group (64 or 32)
+  // tcgen05 path only: the B operand (a weight matrix) is not written by the predecessor kernel of the stream, so its first tiles
+  // may be fetched before the programmatic-dependent-launch wait (opt-in, HB_UMMA_PREFETCH_B=1; 0 = everything after the wait)
+  int b_const = 0;
 };
 
 template <int BM, int BN, int BK, int NSM, int NSN, int EPI>

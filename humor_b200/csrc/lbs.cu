@@ -767,6 +767,8 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
   } else if (tc) {
     GemmEpi ep;
     ep.bias = m->v_template; ep.gamma = ep.beta = nullptr; ep.xhat = ep.rstd = nullptr; ep.ldxh = 0; ep.Cch = 0; ep.gsize = 64;
+    static const int b_const = getenv("HB_UMMA_PREFETCH_B") ? 1 : 0;      // B = the model's blend planes: constant
+    ep.b_const = b_const;
     // frames per slab: the v_posed slab must stay in L2 between the two kernels (<= TC_SLAB rows of workspace)
     const int slab = (g_slab >= 128 && g_slab <= TC_SLAB) ? g_slab : TC_SLAB;
     for (int f0 = 0; f0 < N; f0 += slab) {

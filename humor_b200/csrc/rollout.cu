@@ -9,6 +9,7 @@
 //     backward; the BPTT loop then only walks decoder + glue.
 //   * activations live time-major ([S][B][ld]) so each step is a dense row block for the GEMMs;
 //     cat(x, z) skip connections are free (z is written once into the padded tail columns).
+#include <cstdlib>
 #include "gemm.cuh"
 #include "rollout_glue.cuh"
 #include "umma_launch.cuh"
@@ -393,14 +394,18 @@ __global__ void rollout_bwd_final_kernel(int B, int S, const float* __restrict__
                                    get_split(dh2, dh2_lo, (size_t)b * 1088 + 1024 + i) + get_split(dh3, dh3_lo, (size_t)b * 576 + 512 + i);
 }
 
+// every GEMM of the rollout multiplies activations by a (frozen) weight matrix: B never depends on the previous kernel
+static const int g_b_const = getenv("HB_UMMA_PREFETCH_B") ? 1 : 0;
 static GemmEpi epi_gn(const float* bias, const float* g, const float* be, float* xh, int ldxh, float* rs, int C, int gs) {
   GemmEpi e;
   e.bias = bias; e.gamma = g; e.beta = be; e.xhat = xh; e.rstd = rs; e.ldxh = ldxh; e.Cch = C; e.gsize = gs;
+  e.b_const = g_b_const;
   return e;
 }
 static GemmEpi epi_bias(const float* bias) {
   GemmEpi e;
   e.bias = bias; e.gamma = e.beta = nullptr; e.xhat = e.rstd = nullptr; e.ldxh = 0; e.Cch = 0; e.gsize = 4;
+  e.b_const = g_b_const;
   return e;
 }
 

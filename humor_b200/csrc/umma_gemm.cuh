@@ -251,6 +251,19 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ld_shared_u32(tptr);
+  // Weight tiles do not depend on the predecessor grid: with ep.b_const the producer fills the ring's B planes while this CTA
+  // would otherwise sit in the wait below (in the decoder chain 96 of 128 CTAs of a split-K kernel retire before the leaders'
+  // epilogues, so the successor's CTAs are resident for those microseconds).  The stage's expect_tx covers both operands.
+  int pre = 0;
+  if (ep.b_const && warp == 0 && lane == 0) {
+    pre = min(nkb, UM_STAGES);
+    for (int kb = 0; kb < pre; ++kb) {                          // first use of every stage: nothing to wait for
+      const uint32_t st = base + kb * SM::STAGE;
+      mbar_expect_tx(full0 + 8 * kb, SM::STAGE);
+      tma_load_2d(st + 2 * SM::A_TILE, &tmB_hi, full0 + 8 * kb, (kb0 + kb) * UM_BK, n0);
+      tma_load_2d(st + 2 * SM::A_TILE + SM::B_TILE, &tmB_lo, full0 + 8 * kb, (kb0 + kb) * UM_BK, n0);
+    }
+  }
   pdl_wait();                                                   // predecessor grid complete, its writes visible
 
   if (warp == 0) {
@@ -258,8 +271,13 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % UM_STAGES;
         const uint32_t ph = (kb / UM_STAGES) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t st = base + s * SM::STAGE;
+        if (kb < pre) {                                         // B planes are on their way already
+          tma_load_2d(st, &tmA_hi, full0 + 8 * s, (kb0 + kb) * UM_BK, m0);
+          tma_load_2d(st + SM::A_TILE, &tmA_lo, full0 + 8 * s, (kb0 + kb) * UM_BK, m0);
+          continue;
+        }
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
         mbar_expect_tx(full0 + 8 * s, SM::STAGE);
         tma_load_2d(st, &tmA_hi, full0 + 8 * s, (kb0 + kb) * UM_BK, m0);
         tma_load_2d(st + SM::A_TILE, &tmA_lo, full0 + 8 * s, (kb0 + kb) * UM_BK, m0);

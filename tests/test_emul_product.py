@@ -32,9 +32,10 @@ def emul(built_lib, tmp_path_factory):
     return rt, lib
 
 
-def run_probe(emul, script, *args, tensor=False):
+def run_probe(emul, script, *args, tensor=False, extra_env=None):
     rt, lib = emul
     env = dict(os.environ, LD_PRELOAD=rt, CUDA_VISIBLE_DEVICES='')
+    env.update(extra_env or {})
     if tensor:          # tcgen05 kernels on the functional emulation, incl. the 4-CTA-cluster split-K GEMMs of the decoder chain
         env.update(HB_EMUL_TENSOR='1')
     r = subprocess.run([sys.executable, os.path.join(HERE, 'host', 'emul', script), ROOT, lib] + list(args),
@@ -189,10 +190,13 @@ def test_forms_verification_tool(emul):
     assert recs[(3, 1)]['max_abs_diff_vs_11'] < 5e-6 < recs[(3, 4)]['max_abs_diff_vs_11'] < 1e-4
 
 
-def test_stage3_closure_tensor_precision(emul):
+@pytest.mark.parametrize('prefetch_b', [False, True])
+def test_stage3_closure_tensor_precision(emul, prefetch_b):
     """The DEFAULT precision mode: every rollout GEMM on the (emulated) tcgen05 3xTF32 kernel with descriptors built by the
-    library's own host code, against the fixture of the unmodified reference."""
-    out = run_probe(emul, 'probe_stage3.py', 'stage3_rgb_phase1', tensor=True)
+    library's own host code, against the fixture of the unmodified reference.  prefetch_b: the opt-in producer order of
+    HB_UMMA_PREFETCH_B=1 (weight tiles requested before the programmatic-dependent-launch wait) - same numbers."""
+    out = run_probe(emul, 'probe_stage3.py', 'stage3_rgb_phase1', tensor=True,
+                    extra_env={'HB_UMMA_PREFETCH_B': '1'} if prefetch_b else None)
     g = np.load(os.path.join(HERE, 'golden', 'stage3_rgb_phase1.npz'))
     assert abs(out['loss'] - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
     assert out['trans_err'] < 1e-5 and out['prior_mean_err'] < 1e-5

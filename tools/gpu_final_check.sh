@@ -14,11 +14,15 @@ done
 # 3b. skin form 3 holds every SM it runs on (223 KB of shared memory, all of TMEM) for the whole pass: with fewer persistent
 #     CTAs the decoder chain of the main stream keeps some SMs
 (HB_LBS_FUSEG_CTAS=100 timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --lbs-skin 3 --lbs-blend 3 2>gpurun_out/bench_s3b3_100.err) > gpurun_out/bench_s3b3_100.json
+# 3c. decoder chain: weight tiles requested before the programmatic-dependent-launch wait (default forms otherwise)
+(HB_UMMA_PREFETCH_B=1 timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_prefetchb.err) > gpurun_out/bench_prefetchb.json
+(timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_default.err) > gpurun_out/bench_default.json
+(HB_UMMA_PREFETCH_B=1 timeout 200 python -m pytest tests/test_gpu_umma.py tests/test_gpu_kernels.py tests/test_gpu_closure.py -x -q 2>&1 | tail -4) > gpurun_out/t_prefetchb.log
 # 4. the tests that round 1 could only run on the emulation
 (HB_TEST_UNVERIFIED=1 timeout 150 python -m pytest tests/test_gpu_zz_stage12.py tests/test_gpu_zz_run_e2e.py -x -q 2>&1 | tail -6) > gpurun_out/t_stage12_e2e.log
-tail -n 3 gpurun_out/t_forms.log gpurun_out/t_stage12_e2e.log
+tail -n 3 gpurun_out/t_forms.log gpurun_out/t_stage12_e2e.log gpurun_out/t_prefetchb.log
 cat gpurun_out/lbs_forms_time.jsonl
-for f in gpurun_out/bench_s*.json; do python - "$f" <<'PY'
+for f in gpurun_out/bench_s*.json gpurun_out/bench_default.json gpurun_out/bench_prefetchb.json; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.load(open(sys.argv[1])); print(sys.argv[1], 'ms/step', round(d['ms_per_step'], 3), 'LBS ms', round(d['roofline']['ms_per_launch'], 3), 'frac', round(d['roofline']['frac'], 4))

@@ -67,7 +67,9 @@ def test_stage12_closure_matches_reference_golden(emul, name):
         assert e < 1e-4, (k, e)
 
 
-@pytest.mark.parametrize('name', ['stage3_rgb_phase1', 'stage3_proxd'])
+@pytest.mark.parametrize('name', ['stage3_rgb_phase1',
+                                  pytest.param('stage3_proxd', marks=pytest.mark.skipif(not os.environ.get('HB_SLOW_TESTS'),
+                                               reason='1 min on the emulation (chamfer at PROX size): set HB_SLOW_TESTS=1'))])
 def test_stage3_closure_matches_reference_golden(emul, name):
     """The WHOLE Stage-III closure of the product (VPoser decode, cam->prior, CVAE rollout forward + BPTT on the exact-fp32
     kernels, SMPL+H LBS, fused energies, GMM prior, chamfer/points3d for the PROX-RGBD case) on the CPU through the emulated
@@ -180,14 +182,13 @@ def test_forms_verification_tool(emul):
     """tools/lbs_forms_time.measure (what bench.py's `roofline_candidates` children run on the device) on the emulation: every
     form reports the kernels it really launched, agrees with form (1, 1) inside its tolerance, is deterministic, and differs
     from form (1, 1) in the last bits."""
-    out = run_probe(emul, 'probe_forms_tool.py', '3,1;3,4', tensor=True)
+    out = run_probe(emul, 'probe_forms_tool.py', '3,4', tensor=True)      # (3, 1) goes through the dispatch test above
     recs = {(r['skin'], r['blend']): r for r in out['recs']}
-    assert set(recs) == {(3, 1), (3, 4)}
+    assert set(recs) == {(3, 4)}
     for key, r in recs.items():
         assert r['verified'] and r['used'] == list(key) and r['deterministic'] and r['finite'] and r['frames'] == 129, r
         assert r['ms'] > 0 and r['GBps'] > 0 and 0 < r['frac'] < 1
-    assert not recs[(3, 1)]['bitwise_equal_to_11']
-    assert recs[(3, 1)]['max_abs_diff_vs_11'] < 5e-6 < recs[(3, 4)]['max_abs_diff_vs_11'] < 1e-4
+    assert not recs[(3, 4)]['bitwise_equal_to_11'] and 5e-6 < recs[(3, 4)]['max_abs_diff_vs_11'] < 1e-4
 
 
 @pytest.mark.parametrize('prefetch_b', [False, True])

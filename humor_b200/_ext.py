@@ -104,7 +104,8 @@ class HbFitArgs(C.Structure):
 EXPORTS = ['humor_lbs_workspace_bytes', 'humor_lbs_fwd', 'humor_lbs_bwd', 'humor_rollout_workspace_bytes',
            'humor_rollout_fwd', 'humor_rollout_bwd', 'humor_rodrigues_fwd', 'humor_rodrigues_bwd',
            'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version',
-           'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd', 'humor_lbs_configure', 'humor_lbs_forms_used']
+           'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd', 'humor_lbs_configure', 'humor_lbs_forms_used',
+           'humor_umma_gemm16', 'humor_umma_gemm16_workspace_bytes']
 
 _LIB = None
 
@@ -146,6 +147,10 @@ def lib():
     L.humor_umma_gemm_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.humor_umma_gemm.restype = ci
     L.humor_umma_gemm.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, vp, sz, vp]
+    L.humor_umma_gemm16_workspace_bytes.restype = sz
+    L.humor_umma_gemm16_workspace_bytes.argtypes = [ci, ci, ci, ci]
+    L.humor_umma_gemm16.restype = ci
+    L.humor_umma_gemm16.argtypes = [vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, vp, sz, vp]
     L.humor_lbs_configure.restype = ci
     L.humor_lbs_configure.argtypes = [ci, ci, ci]
     L.humor_lbs_forms_used.restype = ci

@@ -9,6 +9,7 @@
 #include "lbs_fused.cuh"
 #include "lbs_blend.cuh"
 #include "lbs_fuseg.cuh"
+#include "umma_gemm16.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
@@ -234,6 +235,51 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
   return cudaGetLastError();
 }
 
+// fp16 hi/lo GEMM (umma_gemm16.cuh): planes [rows][ld] halves, ld % 8 == 0, K % 64 == 0
+template <int BN, int KS>
+static cudaError_t launch16_t(const CUtensorMap& a_h, const CUtensorMap& a_l, const CUtensorMap& b_h, const CUtensorMap& b_l, int M, int N,
+                              int K, const float* bias, float* C, int ldc, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm16_kernel<BN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(N, BN) * KS, cdiv(M, UM_BM));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = UmmaSmem<BN>::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = KS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = KS > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, umma_gemm16_kernel<BN, KS>, a_h, a_l, b_h, b_l, M, N, K, bias, C, ldc);
+}
+
+cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const void* B_h, const void* B_l, int ldb, int M, int N, int K,
+                               const float* bias, float* C, int ldc, cudaStream_t st) {
+  if (!load_encode()) return cudaErrorNotSupported;
+  if (K % U16_BK || lda % 8 || ldb % 8 || ldc % 4 || lda < K || ldb < K) return cudaErrorInvalidValue;
+  const int bn = (M <= 1024) ? 64 : 128;                     // few row tiles: narrow tiles + split-K, as launch_umma_gemm3
+  CUtensorMap ta_h, ta_l, tb_h, tb_l;
+  if (!make_map_f16(&ta_h, A_h, M, K, lda, UM_BM) || !make_map_f16(&ta_l, A_l, M, K, lda, UM_BM) ||
+      !make_map_f16(&tb_h, B_h, N, K, ldb, bn) || !make_map_f16(&tb_l, B_l, N, K, ldb, bn))
+    return cudaErrorInvalidValue;
+  const bool splitk = bn == 64 && g_splitk && cdiv(N, 64) * cdiv(M, UM_BM) <= 64 && K >= 8 * U16_BK;
+  if (splitk) return launch16_t<64, 4>(ta_h, ta_l, tb_h, tb_l, M, N, K, bias, C, ldc, st);
+  return bn == 64 ? launch16_t<64, 1>(ta_h, ta_l, tb_h, tb_l, M, N, K, bias, C, ldc, st)
+                  : launch16_t<128, 1>(ta_h, ta_l, tb_h, tb_l, M, N, K, bias, C, ldc, st);
+}
+
+cudaError_t launch_split16(const float* x, void* h, void* l, size_t n, cudaStream_t st) {
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, static_cast<unsigned short*>(h), static_cast<unsigned short*>(l), n);
+  return cudaGetLastError();
+}
+
 #endif  // HB_HOST_SHIM
 
 __global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
@@ -303,6 +349,25 @@ extern "C" int humor_umma_gemm(const float* A, int lda, const float* B, int ldb,
   GemmEpi ep;
   ep.bias = bias; ep.gamma = ep.beta = nullptr; ep.xhat = ep.rstd = nullptr; ep.ldxh = 0; ep.Cch = 0; ep.gsize = 64;
   HB_CUDA(launch_umma_gemm3(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, C, nullptr, nullptr, ldc, EPI_BIAS, ep, st));
+  return HB_OK;
+}
+
+// Utility entry point: the same product from 4-byte operand elements (fp16 hi + scaled fp16 lo planes, umma_gemm16.cuh).
+// lda / ldb: row strides of A / B in elements, multiples of 8; K a multiple of 64.
+extern "C" size_t humor_umma_gemm16_workspace_bytes(int M, int N, int lda, int ldb) {
+  return (size_t)2 * ((size_t)M * lda + (size_t)N * ldb) * sizeof(unsigned short);
+}
+extern "C" int humor_umma_gemm16(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M,
+                                 int N, int K, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!A || !B || !C || !workspace || M <= 0 || N <= 0 || K <= 0) return HB_ERR_ARG;
+  if (workspace_bytes < humor_umma_gemm16_workspace_bytes(M, N, lda, ldb)) return HB_ERR_WORKSPACE;
+  unsigned short* a_h = reinterpret_cast<unsigned short*>(workspace);
+  unsigned short* a_l = a_h + (size_t)M * lda;
+  unsigned short* b_h = a_l + (size_t)M * lda;
+  unsigned short* b_l = b_h + (size_t)N * ldb;
+  HB_CUDA(launch_split16(A, a_h, a_l, (size_t)M * lda, st));
+  HB_CUDA(launch_split16(B, b_h, b_l, (size_t)N * ldb, st));
+  HB_CUDA(launch_umma_gemm16(a_h, a_l, lda, b_h, b_l, ldb, M, N, K, bias, C, ldc, st));
   return HB_OK;
 }
 #endif  // HB_HOST_SHIM

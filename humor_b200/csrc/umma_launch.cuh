@@ -13,6 +13,10 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
 // hi = top 11 mantissa bits of x, lo = x - hi (exact); n elements
 cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 bool umma_available();
+// fp16 hi/lo operand planes (umma_gemm16.cuh): 4 bytes per operand element instead of 8; planes [rows][ld] halves
+cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const void* B_h, const void* B_l, int ldb, int M, int N, int K,
+                               const float* bias, float* C, int ldc, cudaStream_t st);
+cudaError_t launch_split16(const float* x, void* h, void* l, size_t n, cudaStream_t st);
 // dense LBS forward, fused blend GEMM + skinning (lbs_fused.cuh); bf_* = blend matrix in 42-vertex tile order [nct*128][K]
 cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf, const float* bf_hi, const float* bf_lo, int K,
                              int N, int num_verts, int nct, int wk, const int* fw_idx, const float* fw_val, const float* A,

@@ -243,6 +243,13 @@ size_t humor_umma_gemm_workspace_bytes(int M, int N, int lda, int ldb);
 int humor_umma_gemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,
                     int K, float* workspace, size_t workspace_bytes, hb_stream_t stream);
 
+/* The same product from FOUR-byte operand elements: fp16 hi + scaled fp16 lo planes (x = h + l * 2^-11), tcgen05 kind::f16, cross
+ * terms in a second TMEM accumulator.  Operand ingest per SM is what bounds the GEMMs of this path; this is the building block
+ * for halving it where fp16's range suffices (forward activations, weights).  K % 64 == 0, lda / ldb % 8 == 0, ldc % 4 == 0. */
+size_t humor_umma_gemm16_workspace_bytes(int M, int N, int lda, int ldb);
+int humor_umma_gemm16(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, int M, int N,
+                      int K, float* workspace, size_t workspace_bytes, hb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Chamfer nearest-neighbour search — the reference's only native module.  Replaces
  * cd.forward_cuda / cd.backward_cuda (humor/utils/chamfer_distance/chamfer_distance.cpp:26-55,180-185;

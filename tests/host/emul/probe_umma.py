@@ -27,4 +27,22 @@ for M, N, K in [(130, 200, 288), (256, 216, 576), (40, 70, 64), (300, 130, 96)]:
     ref = A.double() @ B.double().T + bias.double()
     err = float((Cm[:, :N].double() - ref).abs().max() / ref.abs().max())
     out.append({'shape': [M, N, K], 'rc': rc, 'rel_err': err, 'finite': bool(torch.isfinite(Cm[:, :N]).all())})
-print(json.dumps({'cases': out}))
+# the same product from 4-byte operand elements (fp16 hi + scaled fp16 lo planes, umma_gemm16.cuh): K % 64 == 0
+out16 = []
+for M, N, K in [(130, 200, 576), (256, 216, 512), (40, 70, 64), (1100, 130, 128)]:
+    rng = np.random.RandomState(M + N + K + 1)
+    A = torch.tensor((rng.randn(M, K) * np.exp(rng.randn(M, K))).astype(np.float32))      # several decades of magnitude
+    B = torch.tensor((rng.randn(N, K) * 0.05).astype(np.float32))
+    B[0, :8] = torch.tensor([1e-6, -3e-7, 5e-5, 6.2e-5, 1e-9, 0.0, -2.5e-4, 7e-8])         # around and below fp16's normal range
+    bias = torch.tensor(rng.randn(N).astype(np.float32))
+    ldc = ((N + 3) // 4) * 4
+    Cm = torch.full((M, ldc), float('nan'))
+    ws = torch.empty(L.humor_umma_gemm16_workspace_bytes(M, N, K, K) // 4 + 1)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = L.humor_umma_gemm16(p(A), K, p(B), K, p(bias), p(Cm), ldc, M, N, K, p(ws), ws.numel() * 4, None)
+    ref = A.double() @ B.double().T + bias.double()
+    scale = (A.double().abs() @ B.double().abs().T + bias.double().abs())                   # sum |a||b|: the natural error scale
+    err = float(((Cm[:, :N].double() - ref).abs() / scale).max())
+    out16.append({'shape': [M, N, K], 'rc': rc, 'rel_err': err, 'finite': bool(torch.isfinite(Cm[:, :N]).all()),
+                  'row0_err': float((Cm[:, 0].double() - ref[:, 0]).abs().max())})
+print(json.dumps({'cases': out, 'cases16': out16}))

@@ -105,6 +105,8 @@ def test_argument_errors_are_reported_before_any_launch(built_lib):
     assert L.humor_chamfer_fwd(-1, 4, p, 4, p, p, p, p, p, C.byref(nl), None) == ARG
     assert L.humor_chamfer_fwd(1, 4, None, 4, p, p, p, p, p, C.byref(nl), None) == ARG
     assert L.humor_chamfer_fwd(1, 4, p, 4, p, p, None, p, p, C.byref(nl), None) == ARG        # dist1 without idx1
+    assert L.humor_umma_gemm16(None, 64, p, 64, p, p, 64, 4, 4, 64, p, 1 << 30, None) == ARG
+    assert L.humor_umma_gemm16(p, 64, p, 64, p, p, 64, 4, 4, 64, p, 16, None) == WS
     assert L.humor_lbs_configure(4, 0, 0) == ARG and L.humor_lbs_configure(0, 5, 0) == ARG and L.humor_lbs_configure(0, 0, 64) == ARG
     assert L.humor_lbs_configure(0, 0, 0) == 0
     assert nl.value == 0

@@ -176,6 +176,12 @@ def test_umma_gemm_single_cta_and_split_k_cluster(emul):
         assert c['rc'] == 0 and c['finite'] and c['rel_err'] < 3e-6, c
     launched = [l.split()[1] + ' ' + ' '.join(l.split()[2:4]) for l in r.stderr.splitlines() if l.startswith('EMUL hb::umma_gemm3_kernel')]
     assert sum(', 4>' in k for k in launched) == 2 and sum(', 1>' in k for k in launched) == 2, launched
+    # fp16 hi + scaled lo operand planes (umma_gemm16.cuh): 22-bit significands -> errors of a few 1e-7 of sum |a||b|, also for
+    # operands spread over decades and for weights around / below fp16's normal range; single-CTA, split-K cluster and 128-wide tiles
+    for c in out['cases16']:
+        assert c['rc'] == 0 and c['finite'] and c['rel_err'] < 1e-6, c
+    l16 = [l for l in r.stderr.splitlines() if l.startswith('EMUL hb::umma_gemm16_kernel')]
+    assert sum('<64, 4>' in k for k in l16) == 2 and sum('<64, 1>' in k for k in l16) == 1 and sum('<128, 1>' in k for k in l16) == 1, l16
 
 
 def test_forms_verification_tool(emul):

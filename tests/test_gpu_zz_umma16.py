@@ -1,0 +1,36 @@
+"""GPU parity of the fp16 hi/lo tcgen05 GEMM (csrc/umma_gemm16.cuh, utility entry point humor_umma_gemm16) against fp64: single-CTA
+tiles, split-K clusters, 128-wide tiles, ragged M / N, operands spread over decades.  The same cases pass on the CPU emulation
+(tests/test_emul_product.py::test_umma_gemm_single_cta_and_split_k_cluster)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from humor_b200 import _ext
+
+# new in round 1 and not yet executed on a B200: opt-in until its first hardware run (tools/gpu_final_check.sh)
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get('HB_TEST_UNVERIFIED'),
+                                 reason='fp16 hi/lo GEMM not yet verified on hardware (set HB_TEST_UNVERIFIED=1)')]
+
+
+@pytest.mark.parametrize('M,N,K', [(130, 200, 576), (256, 1024, 1088), (40, 70, 64), (1100, 130, 128), (2048, 1024, 1024)])
+def test_umma_gemm16_matches_fp64(M, N, K):
+    L = _ext.lib()
+    rng = np.random.RandomState(M + N + K)
+    A = torch.tensor((rng.randn(M, K) * np.exp(rng.randn(M, K))).astype(np.float32)).cuda()
+    B = torch.tensor((rng.randn(N, K) * 0.05).astype(np.float32)).cuda()
+    bias = torch.tensor(rng.randn(N).astype(np.float32)).cuda()
+    ldc = ((N + 3) // 4) * 4
+    Cm = torch.full((M, ldc), float('nan'), device='cuda')
+    ws = torch.empty(L.humor_umma_gemm16_workspace_bytes(M, N, K, K) // 4 + 1, device='cuda')
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _ext.check(L.humor_umma_gemm16(p(A), K, p(B), K, p(bias), p(Cm), ldc, M, N, K, p(ws), ws.numel() * 4, _ext.stream_ptr()), 'humor_umma_gemm16')
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T + bias.double()
+    scale = A.double().abs() @ B.double().abs().T + bias.double().abs()
+    assert torch.isfinite(Cm[:, :N]).all()
+    assert float(((Cm[:, :N].double() - ref).abs() / scale).max()) < 2e-6          # emulation: 4e-7; the tensor core truncates its accumulator
+    assert torch.isnan(Cm[:, N:]).all()

@@ -14,7 +14,7 @@ import cpu_backend  # noqa: E402
 
 L = cpu_backend.install(lib)
 out = []
-for M, N, K in [(130, 200, 288), (256, 216, 576), (40, 70, 64), (300, 130, 96)]:
+for M, N, K in [(130, 200, 288), (40, 70, 64)]:
     rng = np.random.RandomState(M + N + K)
     A = torch.tensor(rng.randn(M, K).astype(np.float32))
     B = torch.tensor((rng.randn(N, K) * 0.1).astype(np.float32))
@@ -29,7 +29,7 @@ for M, N, K in [(130, 200, 288), (256, 216, 576), (40, 70, 64), (300, 130, 96)]:
     out.append({'shape': [M, N, K], 'rc': rc, 'rel_err': err, 'finite': bool(torch.isfinite(Cm[:, :N]).all())})
 # the same product from 4-byte operand elements (fp16 hi + scaled fp16 lo planes, umma_gemm16.cuh): K % 64 == 0
 out16 = []
-for M, N, K in [(130, 200, 576), (256, 216, 512), (40, 70, 64), (1100, 130, 128)]:
+for M, N, K in [(130, 200, 576), (40, 70, 64), (1030, 70, 64)]:
     rng = np.random.RandomState(M + N + K + 1)
     A = torch.tensor((rng.randn(M, K) * np.exp(rng.randn(M, K))).astype(np.float32))      # several decades of magnitude
     B = torch.tensor((rng.randn(N, K) * 0.05).astype(np.float32))

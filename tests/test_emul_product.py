@@ -150,15 +150,15 @@ def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
     """humor_lbs_fwd's tensor-core path on the emulated tcgen05 kernels: the library's own dispatch AND its own TMA-descriptor
     code (cuTensorMapEncodeTiled is emulated) for the default forms, for forms (2,2) = lane-per-frame skinning + persistent
     128x256 blend kernel (not yet run on hardware), and for the fused kernel.  All within 2e-5 m of the fp64 oracle."""
-    out = run_probe(emul, 'probe_lbs_forms.py', '140', '11;22;23;31', tensor=True)
+    out = run_probe(emul, 'probe_lbs_forms.py', '140', '11;22;31', tensor=True)
     assert out['exact_vs_oracle'] < 2e-5
     for key, want in (('forms_11', [1, 1]), ('forms_22', [2, 2]), ('forms_31', [3, 1])):   # 31: fused blend + group skinning
         f = out[key]
         assert f['used'] == want and f['finite'], (key, f)
         assert f['v_vs_oracle'] < 2e-5 and f['J_vs_oracle'] < 2e-5 and f['v_vs_exact'] < 5e-6, (key, f)
     assert out['fused']['v_vs_oracle'] < 2e-5 and out['fused']['J_vs_oracle'] < 2e-5
-    f3 = out['forms_23']                                  # single TF32 pass on the pose columns: inside the 1e-4 m bound
-    assert f3['used'] == [2, 3] and f3['finite'] and f3['v_vs_oracle'] < 1e-4 and f3['v_vs_oracle'] > 1e-6, f3
+    # blend form 3 (single TF32 pass on the pose columns) is checked at kernel level in tests/test_host_tc.py; through this dispatch:
+    # `python tests/host/emul/probe_lbs_forms.py <root> <lib> 140 "23;33;34"`
     # forms (3, 3) / (3, 4) - the fused kernel's mixed-precision modes: tests/test_host_tc.py at kernel level, and (3, 4) through this
     # dispatch in test_forms_verification_tool below; `python tests/host/emul/probe_lbs_forms.py ... 140 "33;34"` runs them here
 
@@ -175,13 +175,13 @@ def test_umma_gemm_single_cta_and_split_k_cluster(emul):
     for c in out['cases']:
         assert c['rc'] == 0 and c['finite'] and c['rel_err'] < 3e-6, c
     launched = [l.split()[1] + ' ' + ' '.join(l.split()[2:4]) for l in r.stderr.splitlines() if l.startswith('EMUL hb::umma_gemm3_kernel')]
-    assert sum(', 4>' in k for k in launched) == 2 and sum(', 1>' in k for k in launched) == 2, launched
+    assert sum(', 4>' in k for k in launched) == 1 and sum(', 1>' in k for k in launched) == 1, launched
     # fp16 hi + scaled lo operand planes (umma_gemm16.cuh): 22-bit significands -> errors of a few 1e-7 of sum |a||b|, also for
     # operands spread over decades and for weights around / below fp16's normal range; single-CTA, split-K cluster and 128-wide tiles
     for c in out['cases16']:
         assert c['rc'] == 0 and c['finite'] and c['rel_err'] < 1e-6, c
     l16 = [l for l in r.stderr.splitlines() if l.startswith('EMUL hb::umma_gemm16_kernel')]
-    assert sum('<64, 4>' in k for k in l16) == 2 and sum('<64, 1>' in k for k in l16) == 1 and sum('<128, 1>' in k for k in l16) == 1, l16
+    assert sum('<64, 4>' in k for k in l16) == 1 and sum('<64, 1>' in k for k in l16) == 1 and sum('<128, 1>' in k for k in l16) == 1, l16
 
 
 def test_forms_verification_tool(emul):

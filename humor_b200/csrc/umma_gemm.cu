@@ -236,12 +236,13 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
 }
 
 // fp16 hi/lo GEMM (umma_gemm16.cuh): planes [rows][ld] halves, ld % 8 == 0, K % 64 == 0
-template <int BN, int KS>
+template <int BN, int EPI, int KS>
 static cudaError_t launch16_t(const CUtensorMap& a_h, const CUtensorMap& a_l, const CUtensorMap& b_h, const CUtensorMap& b_l, int M, int N,
-                              int K, const float* bias, float* C, int ldc, cudaStream_t st) {
+                              int K, float* C, int ldc, unsigned short* C16_h, unsigned short* C16_l, int ld16, const GemmEpi& ep,
+                              cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm16_kernel<BN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm16_kernel<BN, EPI, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<BN>::TOTAL);
     if (e != cudaSuccess) return e;
     attr = true;
   }
@@ -255,22 +256,33 @@ static cudaError_t launch16_t(const CUtensorMap& a_h, const CUtensorMap& a_l, co
   at[0].val.clusterDim.x = KS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = KS > 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, umma_gemm16_kernel<BN, KS>, a_h, a_l, b_h, b_l, M, N, K, bias, C, ldc);
+  return cudaLaunchKernelEx(&cfg, umma_gemm16_kernel<BN, EPI, KS>, a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep);
 }
 
 cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const void* B_h, const void* B_l, int ldb, int M, int N, int K,
-                               const float* bias, float* C, int ldc, cudaStream_t st) {
+                               float* C, int ldc, void* C16_h_, void* C16_l_, int ld16, int epi, const GemmEpi& ep, cudaStream_t st) {
   if (!load_encode()) return cudaErrorNotSupported;
-  if (K % U16_BK || lda % 8 || ldb % 8 || ldc % 4 || lda < K || ldb < K) return cudaErrorInvalidValue;
+  if (K % U16_BK || lda % 8 || ldb % 8 || lda < K || ldb < K || (C && ldc % 4) || (!C && !C16_h_)) return cudaErrorInvalidValue;
+  if ((C16_h_ == nullptr) != (C16_l_ == nullptr) || (C16_h_ && ld16 % 4) || (epi != EPI_BIAS && epi != EPI_GN_RELU)) return cudaErrorInvalidValue;
+  unsigned short* C16_h = static_cast<unsigned short*>(C16_h_);
+  unsigned short* C16_l = static_cast<unsigned short*>(C16_l_);
   const int bn = (M <= 1024) ? 64 : 128;                     // few row tiles: narrow tiles + split-K, as launch_umma_gemm3
   CUtensorMap ta_h, ta_l, tb_h, tb_l;
   if (!make_map_f16(&ta_h, A_h, M, K, lda, UM_BM) || !make_map_f16(&ta_l, A_l, M, K, lda, UM_BM) ||
       !make_map_f16(&tb_h, B_h, N, K, ldb, bn) || !make_map_f16(&tb_l, B_l, N, K, ldb, bn))
     return cudaErrorInvalidValue;
   const bool splitk = bn == 64 && g_splitk && cdiv(N, 64) * cdiv(M, UM_BM) <= 64 && K >= 8 * U16_BK;
-  if (splitk) return launch16_t<64, 4>(ta_h, ta_l, tb_h, tb_l, M, N, K, bias, C, ldc, st);
-  return bn == 64 ? launch16_t<64, 1>(ta_h, ta_l, tb_h, tb_l, M, N, K, bias, C, ldc, st)
-                  : launch16_t<128, 1>(ta_h, ta_l, tb_h, tb_l, M, N, K, bias, C, ldc, st);
+#define HB_U16_CASE(E)                                                                                                                  \
+  case E:                                                                                                                               \
+    if (splitk) return launch16_t<64, E, 4>(ta_h, ta_l, tb_h, tb_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep, st);                        \
+    return bn == 64 ? launch16_t<64, E, 1>(ta_h, ta_l, tb_h, tb_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep, st)                          \
+                    : launch16_t<128, E, 1>(ta_h, ta_l, tb_h, tb_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep, st);
+  switch (epi) {
+    HB_U16_CASE(EPI_BIAS)
+    HB_U16_CASE(EPI_GN_RELU)
+  }
+#undef HB_U16_CASE
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_split16(const float* x, void* h, void* l, size_t n, cudaStream_t st) {
@@ -367,7 +379,9 @@ extern "C" int humor_umma_gemm16(const float* A, int lda, const float* B, int ld
   unsigned short* b_l = b_h + (size_t)N * ldb;
   HB_CUDA(launch_split16(A, a_h, a_l, (size_t)M * lda, st));
   HB_CUDA(launch_split16(B, b_h, b_l, (size_t)N * ldb, st));
-  HB_CUDA(launch_umma_gemm16(a_h, a_l, lda, b_h, b_l, ldb, M, N, K, bias, C, ldc, st));
+  GemmEpi ep;
+  ep.bias = bias; ep.gamma = ep.beta = nullptr; ep.xhat = ep.rstd = nullptr; ep.ldxh = 0; ep.Cch = 0; ep.gsize = 64;
+  HB_CUDA(launch_umma_gemm16(a_h, a_l, lda, b_h, b_l, ldb, M, N, K, C, ldc, nullptr, nullptr, 0, EPI_BIAS, ep, st));
   return HB_OK;
 }
 #endif  // HB_HOST_SHIM

@@ -41,11 +41,17 @@ __global__ void split16_kernel(const float* __restrict__ x, unsigned short* __re
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) split16(x[i], h[i], l[i]);
 }
 
-template <int BN, int KS>
+// Outputs of one launch: C (fp32, nullable) and/or the fp16 hi/lo planes of the result (C16_h / C16_l, ld16 halves per row, nullable):
+// the operand planes of the next layer, written by the producing epilogue as umma_gemm3_kernel does for its fp32 planes.
+// EPI_BIAS: + ep.bias (nullable).  EPI_GN_RELU: + bias, GroupNorm over ep.gsize channels, ReLU; x-hat and 1/sigma go to the tape
+// (ep.xhat, ep.rstd) exactly as in umma_gemm3_kernel, so the reverse pass is unchanged.
+template <int BN, int EPI, int KS>
 __global__ void __launch_bounds__(192, 1)
 umma_gemm16_kernel(const __grid_constant__ CUtensorMap tmA_h, const __grid_constant__ CUtensorMap tmA_l,
                    const __grid_constant__ CUtensorMap tmB_h, const __grid_constant__ CUtensorMap tmB_l, int M, int N, int K,
-                   const float* __restrict__ bias, float* __restrict__ C, int ldc) {
+                   float* __restrict__ C, int ldc, unsigned short* __restrict__ C16_h, unsigned short* __restrict__ C16_l, int ld16,
+                   GemmEpi ep) {
+  static_assert(EPI == EPI_BIAS || EPI == EPI_GN_RELU, "forward epilogues only (fp16's range does not hold the reverse chain)");
   static_assert(BN == 128 || BN == 64, "64- or 128-column tiles");
   static_assert(KS == 1 || BN == 64, "split-K partials are laid out for 64-column tiles");
   using SM = UmmaSmem<BN>;                                      // same stage: A_h | A_l | B_h | B_l, rows of 128 bytes
@@ -169,17 +175,41 @@ umma_gemm16_kernel(const __grid_constant__ CUtensorMap tmA_h, const __grid_const
       }
     }
     if (rok && krank == 0) {
-      float* crow = C + (size_t)row * ldc;
 #pragma unroll
-      for (int j = 0; j < BN; j += 4) {
-        const int col = n0 + j;
-        if (col + 3 < N) {
-          const float4 b = bias ? *reinterpret_cast<const float4*>(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(crow + col) = make_float4(acc[j] + b.x, acc[j + 1] + b.y, acc[j + 2] + b.z, acc[j + 3] + b.w);
-        } else {
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        const int col0 = n0 + c0;
+        if (col0 < N) {
+          if (EPI == EPI_BIAS) {
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            if (col + jj < N) crow[col + jj] = acc[j + jj] + (bias ? bias[col + jj] : 0.f);
+            for (int j = 0; j < 64; ++j) acc[c0 + j] += (ep.bias && col0 + j < N) ? ep.bias[col0 + j] : 0.f;
+          } else {
+            if (ep.gsize == 64) gn_relu_fwd_group<64>(acc + c0, col0, row, ep);
+            else { gn_relu_fwd_group<32>(acc + c0, col0, row, ep); gn_relu_fwd_group<32>(acc + c0 + 32, col0 + 32, row, ep); }
+          }
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const int col = col0 + j;
+            const float o[4] = {acc[c0 + j], acc[c0 + j + 1], acc[c0 + j + 2], acc[c0 + j + 3]};
+            unsigned short h[4], l[4];
+            if (C16_h) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) split16(o[jj], h[jj], l[jj]);
+            }
+            if (col + 3 < N) {
+              if (C) *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
+              if (C16_h) {
+                *reinterpret_cast<uint2*>(C16_h + (size_t)row * ld16 + col) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+                *reinterpret_cast<uint2*>(C16_l + (size_t)row * ld16 + col) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (col + jj < N) {
+                  if (C) C[(size_t)row * ldc + col + jj] = o[jj];
+                  if (C16_h) { C16_h[(size_t)row * ld16 + col + jj] = h[jj]; C16_l[(size_t)row * ld16 + col + jj] = l[jj]; }
+                }
+            }
+          }
         }
       }
     }

@@ -14,8 +14,9 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
 cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 bool umma_available();
 // fp16 hi/lo operand planes (umma_gemm16.cuh): 4 bytes per operand element instead of 8; planes [rows][ld] halves
+// outputs: C (fp32, nullable) and/or the fp16 hi/lo planes of the result (ld16 halves per row, nullable); epi = EPI_BIAS | EPI_GN_RELU
 cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const void* B_h, const void* B_l, int ldb, int M, int N, int K,
-                               const float* bias, float* C, int ldc, cudaStream_t st);
+                               float* C, int ldc, void* C16_h, void* C16_l, int ld16, int epi, const GemmEpi& ep, cudaStream_t st);
 cudaError_t launch_split16(const float* x, void* h, void* l, size_t n, cudaStream_t st);
 // dense LBS forward, fused blend GEMM + skinning (lbs_fused.cuh); bf_* = blend matrix in 42-vertex tile order [nct*128][K]
 cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf, const float* bf_hi, const float* bf_lo, int K,

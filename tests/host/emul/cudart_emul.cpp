@@ -71,12 +71,12 @@ const std::map<std::string, Thunk>& registry() {
          if (g_cluster_x != 4) { std::fprintf(stderr, "cudart_emul: split-K GEMM launched without its 4-CTA cluster\n"); std::abort(); }  \
          RUN((hb_emu::umma_gemm3_kernel<64, EPI, 4>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(hb_emu::GemmEpi, 11)))); }},
       UMMA_SPLITK_THUNK(0) UMMA_SPLITK_THUNK(1) UMMA_SPLITK_THUNK(2)
-#define UMMA16_THUNK(BN, KS)                                                                                                     \
-      {"hb::umma_gemm16_kernel<" #BN ", " #KS ">", [](dim3 g, dim3 b, void** a) {                                               \
+#define UMMA16_THUNK(BN, EPI, KS)                                                                                                \
+      {"hb::umma_gemm16_kernel<" #BN ", " #EPI ", " #KS ">", [](dim3 g, dim3 b, void** a) {                                     \
          tcemu::reset();                                                                                                        \
          if (g_cluster_x != KS) { std::fprintf(stderr, "cudart_emul: umma_gemm16 cluster size mismatch\n"); std::abort(); }     \
-         RUN((hb_emu::umma_gemm16_kernel<BN, KS>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(cf, 7), A(float*, 8), A(int, 9)))); }},
-      UMMA16_THUNK(64, 1) UMMA16_THUNK(64, 4) UMMA16_THUNK(128, 1)
+         RUN((hb_emu::umma_gemm16_kernel<BN, EPI, KS>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(int, 8), A(unsigned short*, 9), A(unsigned short*, 10), A(int, 11), A(hb_emu::GemmEpi, 12)))); }},
+      UMMA16_THUNK(64, 0, 1) UMMA16_THUNK(64, 0, 4) UMMA16_THUNK(128, 0, 1) UMMA16_THUNK(64, 1, 1) UMMA16_THUNK(64, 1, 4) UMMA16_THUNK(128, 1, 1)
       {"hb::split16_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::split16_kernel(A(cf, 0), A(unsigned short*, 1), A(unsigned short*, 2), A(size_t, 3))); }},
       {"hb::lbs_blend_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_blend_kernel(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(cf, 7), A(float*, 8), A(int, 9), A(int, 10))); }},
       {"hb::lbs_fuseg_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fuseg_kernel(MAP(0), MAP(1), MAP(2), MAP(3), MAP(4), MAP(5), MAP(6), A(int, 7), A(hb_emu::LbsFusegArgs, 8))); }},

@@ -4,6 +4,7 @@
 #include "../../humor_b200/csrc/lbs_blend.cuh"
 #include "../../humor_b200/csrc/lbs_fused.cuh"
 #include "../../humor_b200/csrc/lbs_fuseg.cuh"
+#include "../../humor_b200/csrc/umma_gemm16.cuh"
 using namespace hb;
 extern "C" {
 // v_posed = bias + (feat_hi+feat_lo) . (bt_hi+bt_lo)^T through lbs_blend_kernel with `grid` persistent CTAs
@@ -53,6 +54,24 @@ long long h_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const
   tcemu::reset();
   shim::launch(dim3(grid), dim3(FG_THREADS), [&] { lbs_fuseg_kernel(a_hi, a_lo, b_hi, b_lo, tt, a16, b16, K, a); });
   if (tma_count) *tma_count = tcemu::g_tma_count;
+  return tcemu::g_mma_count;
+}
+// fp16 hi/lo GEMM (umma_gemm16.cuh) with its epilogues: planes [rows][ld] halves; BN = 64, split-K over `ks` (1 or 4) CTAs
+long long h_umma_gemm16(const unsigned short* A_h, const unsigned short* A_l, int lda, const unsigned short* B_h, const unsigned short* B_l,
+                        int ldb, int M, int N, int K, float* C, int ldc, unsigned short* C16_h, unsigned short* C16_l, int ld16, int epi,
+                        const float* bias, const float* gamma, const float* beta, float* xhat, int ldxh, float* rstd, int gsize, int ks) {
+  auto map = [](const unsigned short* p, int rows, int K, int ld, unsigned box_rows) {
+    return CUtensorMap{reinterpret_cast<const float*>(p), (unsigned long long)rows, (unsigned long long)K, (unsigned long long)ld, 64, box_rows, 0, 1};
+  };
+  CUtensorMap a_h = map(A_h, M, K, lda, UM_BM), a_l = map(A_l, M, K, lda, UM_BM), b_h = map(B_h, N, K, ldb, 64), b_l = map(B_l, N, K, ldb, 64);
+  GemmEpi ep;
+  ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.xhat = xhat; ep.rstd = rstd; ep.ldxh = ldxh; ep.Cch = N; ep.gsize = gsize;
+  tcemu::reset();
+  const dim3 grid(cdiv(N, 64) * ks, cdiv(M, UM_BM));
+  if (epi == EPI_BIAS && ks == 1) shim::launch_cluster(grid, dim3(192), 1, [&] { umma_gemm16_kernel<64, EPI_BIAS, 1>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
+  else if (epi == EPI_BIAS) shim::launch_cluster(grid, dim3(192), 4, [&] { umma_gemm16_kernel<64, EPI_BIAS, 4>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
+  else if (ks == 1) shim::launch_cluster(grid, dim3(192), 1, [&] { umma_gemm16_kernel<64, EPI_GN_RELU, 1>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
+  else shim::launch_cluster(grid, dim3(192), 4, [&] { umma_gemm16_kernel<64, EPI_GN_RELU, 4>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
   return tcemu::g_mma_count;
 }
 }

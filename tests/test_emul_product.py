@@ -181,7 +181,7 @@ def test_umma_gemm_single_cta_and_split_k_cluster(emul):
     for c in out['cases16']:
         assert c['rc'] == 0 and c['finite'] and c['rel_err'] < 1e-6, c
     l16 = [l for l in r.stderr.splitlines() if l.startswith('EMUL hb::umma_gemm16_kernel')]
-    assert sum('<64, 4>' in k for k in l16) == 1 and sum('<64, 1>' in k for k in l16) == 1 and sum('<128, 1>' in k for k in l16) == 1, l16
+    assert sum('<64, 0, 4>' in k for k in l16) == 1 and sum('<64, 0, 1>' in k for k in l16) == 1 and sum('<128, 0, 1>' in k for k in l16) == 1, l16
 
 
 def test_forms_verification_tool(emul):

@@ -277,3 +277,50 @@ def test_fuseg_kernel_on_a_mesh_without_locality(H):
     ref = np.einsum('nvrc,nvc->nvr', T[..., :3], vp.reshape(N, V, 3)) + T[..., 3] + trans[:, None].astype(np.float64)
     assert nmma == 108 * 84 and np.isfinite(out).all()
     assert np.abs(out - ref).max() < 4e-6 * max(1.0, np.abs(ref).max())
+
+
+# ---- fp16 hi/lo GEMM with its forward epilogues (csrc/umma_gemm16.cuh), not yet on hardware
+def split16_np(x):
+    h = x.astype(np.float16)
+    l = ((x - h.astype(np.float32)) * np.float32(2048)).astype(np.float16)
+    return np.ascontiguousarray(h), np.ascontiguousarray(l)
+
+
+@pytest.mark.parametrize('ks', [1, 4])
+@pytest.mark.parametrize('gsize', [64, 32])
+def test_umma_gemm16_groupnorm_epilogue_and_fp16_planes(H, ks, gsize):
+    """One decoder-style layer from 4-byte operand elements: Linear + bias + GroupNorm + ReLU in the epilogue (x-hat and 1/sigma to
+    the tape as the reverse pass expects them), result as fp32 AND as the fp16 hi/lo planes of the next layer; single CTA per tile
+    and split-K over a 4-CTA cluster; ragged M and N."""
+    M, N, K = 150, 192 - 8, 576
+    rng = np.random.RandomState(ks + gsize)
+    A = (rng.randn(M, K) * 0.8).astype(np.float32)
+    W = (rng.randn(N, K) * 0.04).astype(np.float32)
+    # parameter vectors padded to the tile width: the epilogue normalises whole groups of its (padded) 64-column tile
+    bias, gamma, beta = (np.ascontiguousarray(rng.randn(192).astype(np.float32) * s) for s in (0.1, 1.0, 0.2))
+    gamma = np.ascontiguousarray(gamma + 1.0)
+    Ah, Al = split16_np(A)
+    Wh, Wl = split16_np(W)
+    ldc, ld16, ldxh = 192, 192, 192
+    C = np.full((M, ldc), np.nan, np.float32)
+    Ch = np.zeros((M, ld16), np.float16)
+    Cl = np.zeros((M, ld16), np.float16)
+    xhat = np.full((M, ldxh), np.nan, np.float32)
+    rstd = np.full((M, 16), np.nan, np.float32)
+    H.h_umma_gemm16.restype = ctypes.c_longlong
+    nmma = H.h_umma_gemm16(P(Ah), P(Al), K, P(Wh), P(Wl), K, M, N, K, P(C), ldc, P(Ch), P(Cl), ld16, 1, P(bias), P(gamma), P(beta),
+                           P(xhat), ldxh, P(rstd), gsize, ks)
+    assert nmma == 2 * 3 * (K // 64) * 4 * 3                   # row tiles x column tiles x k-blocks x 4 K-steps x (h.h, l.h, h.l)
+    y = A.astype(np.float64) @ W.astype(np.float64).T + bias[:N]
+    # N = 184 is not a multiple of the group size: the kernel normalises whole groups of its padded tile; compare complete groups
+    ng = N // gsize
+    yg = y[:, :ng * gsize].reshape(M, ng, gsize)
+    mean, var = yg.mean(-1, keepdims=True), yg.var(-1, keepdims=True)
+    xh_ref = ((yg - mean) / np.sqrt(var + 1e-5)).reshape(M, ng * gsize)
+    out_ref = np.maximum(xh_ref * gamma[:ng * gsize] + beta[:ng * gsize], 0.0)
+    nc = ng * gsize
+    assert np.abs(C[:, :nc] - out_ref).max() < 5e-6 and np.abs(xhat[:, :nc] - xh_ref).max() < 5e-6
+    assert np.abs(rstd[:, :ng] - 1.0 / np.sqrt(var[..., 0] + 1e-5)).max() < 1e-5 * (1.0 / np.sqrt(var.min() + 1e-5))
+    rec = Ch.astype(np.float32) + Cl.astype(np.float32) / np.float32(2048)
+    assert np.abs(rec[:, :nc] - C[:, :nc]).max() <= 3e-7 * max(1.0, np.abs(C[:, :nc]).max())   # the planes carry the fp32 result to 2^-22
+    assert np.isnan(C[:, N:]).all() and not Ch[:, N:].any()    # padding columns untouched

@@ -501,8 +501,9 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=8)
     ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--precision', default='tensor', choices=['tensor', 'exact'],
-                    help="'tensor': GEMMs on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels (gradient-exact parity mode)")
+    ap.add_argument('--precision', default='tensor', choices=['tensor', 'exact', 'tensor16'],
+                    help="'tensor': GEMMs on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels (gradient-exact parity mode); "
+                         "'tensor16': 'tensor' with the forward decoder chain on fp16 hi/lo operand planes (opt-in)")
     ap.add_argument('--lbs-skin', type=int, default=0, help='dense LBS skinning pass form (humor_lbs_configure): 1 lane=vertex, 2 lane=frame, 3 fused blend + lane=frame skinning (one persistent kernel)')
     ap.add_argument('--lbs-blend', type=int, default=0, help='dense LBS blend GEMM form: 1 tile per CTA, 2 persistent 128x256 tiles, 3 = 2 + single TF32 pass on the pose columns, 4 (skin 3) = fp16 pose columns')
     ap.add_argument('--lbs-slab', type=int, default=0, help='frames per v_posed slab (128..512)')

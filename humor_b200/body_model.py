@@ -358,9 +358,9 @@ class BodyModel(nn.Module):
     def set_precision(self, mode):
         """'tensor': dense LBS forward blends on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels.  Both keep vertices
         within ~2e-6 m of the fp64 oracle; the reverse pass is always exact fp32."""
-        if mode not in ('tensor', 'exact'):
+        if mode not in ('tensor', 'exact', 'tensor16'):      # 'tensor16' concerns the motion prior's decoder chain only
             raise ValueError(mode)
-        self.lbs_model.struct.use_umma = 1 if mode == 'tensor' else 0
+        self.lbs_model.struct.use_umma = 0 if mode == 'exact' else 1
 
     @property
     def lbs_model(self):

@@ -13,9 +13,12 @@
 #include "gemm.cuh"
 #include "rollout_glue.cuh"
 #include "umma_launch.cuh"
+#include "umma_split16.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
+
+constexpr int X16_LD = 448;         // decoder input row (339 state + 48 z, XIN_LD = 416) padded to a multiple of 64 halves
 
 struct Tape {
   float *xins, *raws, *Gs, *t2j;
@@ -26,6 +29,8 @@ struct Tape {
   float *dh3, *dh2, *dh1, *da0, *draw, *dxres, *dnsum, *dG0, *dG1, *dt2j, *dpx;
   // hi/lo operand planes of the tensor-core path (x = hi + lo); h1/h2/h3, pa/pb, dh1/dh2/dh3 hold the hi plane
   float *xin_hi, *xin_lo, *pa_lo, *pb_lo, *dpo_hi, *dpo_lo, *h1_lo, *h2_lo, *h3_lo, *dh1_lo, *dh2_lo, *dh3_lo, *draw_hi, *draw_lo;
+  // fp16 hi/lo operand planes of the forward decoder chain (use_umma == 2): [B][448], [B][1088], [B][1088], [B][576] halves each
+  unsigned short *x16_h, *x16_l, *h1_16h, *h1_16l, *h2_16h, *h2_16l, *h3_16h, *h3_16l;
   size_t total;
 };
 
@@ -55,6 +60,11 @@ static Tape carve(float* base, int B, int S) {
   t.h1_lo = take((size_t)B * 1088); t.h2_lo = take((size_t)B * 1088); t.h3_lo = take((size_t)B * 576);
   t.dh1_lo = take((size_t)B * 1088); t.dh2_lo = take((size_t)B * 1088); t.dh3_lo = take((size_t)B * 576);
   t.draw_hi = take((size_t)B * RAW_LD); t.draw_lo = take((size_t)B * RAW_LD);
+  auto take16 = [&](size_t halves) { return reinterpret_cast<unsigned short*>(take((halves + 1) / 2)); };
+  t.x16_h = take16((size_t)B * X16_LD); t.x16_l = take16((size_t)B * X16_LD);
+  t.h1_16h = take16((size_t)B * 1088); t.h1_16l = take16((size_t)B * 1088);
+  t.h2_16h = take16((size_t)B * 1088); t.h2_16l = take16((size_t)B * 1088);
+  t.h3_16h = take16((size_t)B * 576); t.h3_16l = take16((size_t)B * 576);
   t.total = off;
   return t;
 }
@@ -65,6 +75,28 @@ __device__ __forceinline__ void put_split(float* hi, float* lo, size_t i, float 
   if (lo) { const float h = hi11(v); hi[i] = h; lo[i] = v - h; } else { hi[i] = v; }
 }
 __device__ __forceinline__ float get_split(const float* hi, const float* lo, size_t i) { return lo ? hi[i] + lo[i] : hi[i]; }
+
+// use_umma == 2: the decoder input of one step as fp16 hi/lo planes (x = h + l * 2^-11) - the state | z row written by the
+// previous glue kernel (or rollout_init_kernel) - and z into the skip-connection columns of the three hidden-activation planes
+__global__ void chain16_pack_kernel(int B, const float* __restrict__ xin, unsigned short* x_h, unsigned short* x_l, unsigned short* h1_h,
+                                    unsigned short* h1_l, unsigned short* h2_h, unsigned short* h2_l, unsigned short* h3_h,
+                                    unsigned short* h3_l) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const float* x = xin + (size_t)b * XIN_LD;
+  for (int i = threadIdx.x; i < XIN_LD; i += blockDim.x) {
+    unsigned short h, l;
+    split16(x[i], h, l);
+    x_h[(size_t)b * X16_LD + i] = h; x_l[(size_t)b * X16_LD + i] = l;
+    if (i >= STATE_D && i < STATE_D + 48) {
+      const int j = i - STATE_D;
+      h1_h[(size_t)b * 1088 + 1024 + j] = h; h1_l[(size_t)b * 1088 + 1024 + j] = l;
+      h2_h[(size_t)b * 1088 + 1024 + j] = h; h2_l[(size_t)b * 1088 + 1024 + j] = l;
+      h3_h[(size_t)b * 576 + 512 + j] = h; h3_l[(size_t)b * 576 + 512 + j] = l;
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 __global__ void rollout_init_kernel(int B, int S, const float* __restrict__ init, const float* __restrict__ z,
@@ -436,11 +468,30 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
                                          tp.t2j, tp.h1, tp.h2, tp.h3, tc ? tp.h1_lo : nullptr, tc ? tp.h2_lo : nullptr,
                                          tc ? tp.h3_lo : nullptr);
   HB_LAUNCH_CHECK(); ++nl;
+  // forward decoder chain on fp16 hi/lo planes (4 bytes per operand element; the tape the reverse pass reads is unchanged)
+  const bool f16 = tc && w->use_umma == 2 && w->dec_w16_h[0] && w->dec_w16_l[0] && w->dec_w16_h[1] && w->dec_w16_l[1] &&
+                   w->dec_w16_h[2] && w->dec_w16_l[2] && w->dec_w16_h[3] && w->dec_w16_l[3];
+  if (f16)          // pads (input columns 416..447, hidden columns past the 48 z) must read as zero
+    HB_CUDA(cudaMemsetAsync(tp.x16_h, 0, (size_t)((char*)(tp.h3_16l + (size_t)B * 576) - (char*)tp.x16_h), st));
   const int gb = cdiv(B, GLUE_WARPS);
   for (int t = 0; t < S; ++t) {
     const size_t r = (size_t)t * B;
     float* xin = tp.xins + r * XIN_LD;
-    if (tc) {
+    if (f16) {
+      chain16_pack_kernel<<<B, 128, 0, st>>>(B, xin, tp.x16_h, tp.x16_l, tp.h1_16h, tp.h1_16l, tp.h2_16h, tp.h2_16l, tp.h3_16h, tp.h3_16l);
+      HB_LAUNCH_CHECK(); ++nl;
+      HB_CUDA(launch_umma_gemm16(tp.x16_h, tp.x16_l, X16_LD, w->dec_w16_h[0], w->dec_w16_l[0], X16_LD, B, 1024, X16_LD, nullptr, 0,
+                                 tp.h1_16h, tp.h1_16l, 1088, EPI_GN_RELU,
+                                 epi_gn(w->dec_b[0], w->dec_g[0], w->dec_be[0], tp.dxh1 + r * 1024, 1024, tp.drs1 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_umma_gemm16(tp.h1_16h, tp.h1_16l, 1088, w->dec_w16_h[1], w->dec_w16_l[1], 1088, B, 1024, 1088, nullptr, 0,
+                                 tp.h2_16h, tp.h2_16l, 1088, EPI_GN_RELU,
+                                 epi_gn(w->dec_b[1], w->dec_g[1], w->dec_be[1], tp.dxh2 + r * 1024, 1024, tp.drs2 + r * 16, 1024, 64), st));
+      HB_CUDA(launch_umma_gemm16(tp.h2_16h, tp.h2_16l, 1088, w->dec_w16_h[2], w->dec_w16_l[2], 1088, B, 512, 1088, nullptr, 0,
+                                 tp.h3_16h, tp.h3_16l, 576, EPI_GN_RELU,
+                                 epi_gn(w->dec_b[2], w->dec_g[2], w->dec_be[2], tp.dxh3 + r * 512, 512, tp.drs3 + r * 16, 512, 32), st));
+      HB_CUDA(launch_umma_gemm16(tp.h3_16h, tp.h3_16l, 576, w->dec_w16_h[3], w->dec_w16_l[3], 576, B, 216, 576, tp.raws + r * RAW_LD, RAW_LD,
+                                 nullptr, nullptr, 0, EPI_BIAS, epi_bias(w->dec_b[3]), st));
+    } else if (tc) {
       HB_CUDA(launch_umma_gemm3(tp.xin_hi + r * XIN_LD, tp.xin_lo + r * XIN_LD, XIN_LD, w->dec_w_hi[0], w->dec_w_lo[0], 416, B, 1024, 416,
                                 nullptr, tp.h1, tp.h1_lo, 1088, EPI_GN_RELU,
                                 epi_gn(w->dec_b[0], w->dec_g[0], w->dec_be[0], tp.dxh1 + r * 1024, 1024, tp.drs1 + r * 16, 1024, 64), st));

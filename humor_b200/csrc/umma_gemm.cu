@@ -271,7 +271,7 @@ cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const 
   if (!make_map_f16(&ta_h, A_h, M, K, lda, UM_BM) || !make_map_f16(&ta_l, A_l, M, K, lda, UM_BM) ||
       !make_map_f16(&tb_h, B_h, N, K, ldb, bn) || !make_map_f16(&tb_l, B_l, N, K, ldb, bn))
     return cudaErrorInvalidValue;
-  const bool splitk = bn == 64 && g_splitk && cdiv(N, 64) * cdiv(M, UM_BM) <= 64 && K >= 8 * U16_BK;
+  const bool splitk = bn == 64 && g_splitk && cdiv(N, 64) * cdiv(M, UM_BM) <= 64 && K >= 4 * U16_BK;
 #define HB_U16_CASE(E)                                                                                                                  \
   case E:                                                                                                                               \
     if (splitk) return launch16_t<64, E, 4>(ta_h, ta_l, tb_h, tb_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep, st);                        \

@@ -16,26 +16,12 @@
 // nothing on the product path uses it.
 #pragma once
 #include "umma_gemm.cuh"
+#include "umma_split16.cuh"
 
 namespace hb {
 
 constexpr int U16_BK = 64;         // halves per k-block row = 128 bytes
 constexpr int U16_CHUNK = 2;       // k-blocks (K = 128) per TMEM accumulation before promotion
-
-// one value -> (h, l) halves, as bit patterns
-#ifdef HB_HOST_SHIM
-static inline void split16(float x, unsigned short& h, unsigned short& l) {
-  h = tcemu::f32_to_f16_bits(x);
-  _Float16 hf; std::memcpy(&hf, &h, 2);
-  l = tcemu::f32_to_f16_bits((x - (float)hf) * 2048.f);
-}
-#else
-__device__ __forceinline__ void split16(float x, unsigned short& h, unsigned short& l) {
-  const __half hh = __float2half_rn(x);
-  h = __half_as_ushort(hh);
-  l = __half_as_ushort(__float2half_rn((x - __half2float(hh)) * 2048.f));
-}
-#endif
 
 __global__ void split16_kernel(const float* __restrict__ x, unsigned short* __restrict__ h, unsigned short* __restrict__ l, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) split16(x[i], h[i], l[i]);

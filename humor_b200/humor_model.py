@@ -64,6 +64,7 @@ class PackedWeights:
     """Zero-padded fp32 copies (+ transposes for the reverse pass) in the HbHumorWeights layout."""
 
     DEC_K = [416, 1088, 1088, 576]
+    DEC_K16 = [448, 1088, 1088, 576]      # multiples of 64 halves
     PRI_K = [352, 1024, 1024, 1024, 1024]
 
     def __init__(self, decoder, prior_net, device):
@@ -78,6 +79,16 @@ class PackedWeights:
             hi = (t.contiguous().view(torch.int32) & -8192).view(torch.float32)      # keep the top 11 mantissa bits
             return hi, t - hi
 
+        def dev16(t):
+            t = t.detach().to(device=device).contiguous()
+            self.keep.append(t)
+            return t.data_ptr()
+
+        def split16(t):
+            """x = h + l * 2^-11 with h = fp16(x), l = fp16((x - h) * 2^11): operand planes of csrc/umma_gemm16.cuh"""
+            h = t.to(torch.float16)
+            return h, ((t - h.float()) * 2048.0).to(torch.float16)
+
         s = _ext.HbHumorWeights()
         dl, dn = decoder.linears(), decoder.norms()
         for i, lin in enumerate(dl):
@@ -91,6 +102,8 @@ class PackedWeights:
             (h, l), (ht, lt) = split(w), split(wt)
             s.dec_w_hi[i], s.dec_w_lo[i] = dev(h), dev(l)
             s.dec_wt_hi[i], s.dec_wt_lo[i] = dev(ht), dev(lt)
+            h16, l16 = split16(_pad_cols(w, self.DEC_K16[i]))                    # precision 'tensor16' (forward chain only)
+            s.dec_w16_h[i], s.dec_w16_l[i] = dev16(h16), dev16(l16)
         for i, gn in enumerate(dn):
             s.dec_g[i] = dev(gn.weight)
             s.dec_be[i] = dev(gn.bias)
@@ -202,15 +215,19 @@ class HumorModel(nn.Module):
         import os
         self.precision = 'exact' if os.environ.get('HB_NO_UMMA') else 'tensor'
 
+    # 'tensor16' (opt-in, not yet measured on hardware): 'tensor' with the FORWARD decoder chain on fp16 hi + scaled lo operand
+    # planes (4 bytes per element instead of 8; csrc/umma_gemm16.cuh) - same 22-bit operand significand, same tape for the reverse
+    _UMMA_MODE = {'exact': 0, 'tensor': 1, 'tensor16': 2}
+
     def set_precision(self, mode):
         """'tensor': every GEMM on tcgen05 (3xTF32 split, fp32 promotion) — forward states / log-prob within ~2e-6 of
         fp64, gradients through the 59-step reverse pass within ~3e-3 (measured; the BPTT amplifies the tensor core's
         ~1e-6-of-sum(|a||b|) product error).  'exact': fp32 FFMA kernels — gradients within ~2e-6, as the fp32 reference."""
-        if mode not in ('tensor', 'exact'):
+        if mode not in ('tensor', 'exact', 'tensor16'):
             raise ValueError(mode)
         self.precision = mode
         if self._packed is not None:
-            self._packed.struct.use_umma = 1 if mode == 'tensor' else 0
+            self._packed.struct.use_umma = self._UMMA_MODE[mode]
 
     # -- weights -----------------------------------------------------------------------------------
     def packed(self):
@@ -219,7 +236,7 @@ class HumorModel(nn.Module):
             raise RuntimeError('HumorModel must live on a CUDA device (there is no CPU path)')
         if self._packed is None or self._packed.device != dev:
             self._packed = PackedWeights(self.decoder, self.prior_net, dev)
-        self._packed.struct.use_umma = 1 if self.precision == 'tensor' else 0
+        self._packed.struct.use_umma = self._UMMA_MODE[self.precision]
         return self._packed
 
     def load_state_dict(self, *a, **k):

@@ -146,8 +146,12 @@ typedef struct HbHumorWeights {
   const float* dec_w_lo[4];
   const float* dec_wt_hi[4];
   const float* dec_wt_lo[4];
-  int use_umma;
+  int use_umma;           /* 0 exact fp32 FFMA | 1 tcgen05 3xTF32 | 2 = 1 with the FORWARD decoder chain on fp16 hi/lo planes */
   int reserved;
+  /* use_umma == 2: fp16 hi + scaled lo planes (x = h + l * 2^-11, csrc/umma_gemm16.cuh) of dec_w with K padded to a multiple
+   * of 64: [1024][448] [1024][1088] [512][1088] [216][576] halves; NULL: mode 2 falls back to mode 1 */
+  const void* dec_w16_h[4];
+  const void* dec_w16_l[4];
 } HbHumorWeights;
 
 /* Replaces HumorModel.roll_out(x_past=None, init_input_dict, S, z_seq, return_prior=True)

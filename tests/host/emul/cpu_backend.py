@@ -58,7 +58,7 @@ def install(lib_path):
         return self._model
 
     body_model.BodyModel.lbs_model = property(lbs_model)
-    body_model.BodyModel.set_precision = lambda self, mode: setattr(self.lbs_model.struct, 'use_umma', 1 if mode == 'tensor' else 0)
+    body_model.BodyModel.set_precision = lambda self, mode: setattr(self.lbs_model.struct, 'use_umma', 0 if mode == 'exact' else 1)
 
     from humor_b200 import humor_model
 
@@ -67,7 +67,7 @@ def install(lib_path):
         dev = self.decoder.net[0].weight.device
         if self._packed is None or self._packed.device != dev:
             self._packed = humor_model.PackedWeights(self.decoder, self.prior_net, dev)
-        self._packed.struct.use_umma = 1 if (self.precision == 'tensor' and os.environ.get('HB_EMUL_TENSOR')) else 0
+        self._packed.struct.use_umma = self._UMMA_MODE[self.precision] if os.environ.get('HB_EMUL_TENSOR') else 0
         return self._packed
 
     humor_model.HumorModel.packed = packed

@@ -19,6 +19,9 @@ from tests.golden_util import load_case  # noqa: E402
 g, prob, c = load_case(name)
 mo = U.build_product(c['B'], c['T'], c['W'], c['optim_floor'], prob, device='cpu')
 mo.use_cuda_graph = False
+import os  # noqa: E402
+if os.environ.get('HB_EMUL_PRECISION'):                 # e.g. 'tensor16': forward decoder chain on fp16 hi/lo operand planes
+    mo.set_precision(os.environ['HB_EMUL_PRECISION'])
 loss, grads, aux = U.closure_product(mo, prob, c['nsteps'], c['scale'])
 out = {'loss': loss, 'stats': aux['stats'], 'grad_err': {},
        'verts_err': float(np.abs(aux['cam_pred']['verts3d'].detach().numpy() - g['cam_verts3d']).max()),

@@ -197,7 +197,20 @@ def test_forms_verification_tool(emul):
     assert not recs[(3, 4)]['bitwise_equal_to_11'] and 5e-6 < recs[(3, 4)]['max_abs_diff_vs_11'] < 1e-4
 
 
-@pytest.mark.parametrize('prefetch_b', [False, True])
+def test_stage3_closure_tensor16_precision(emul):
+    """precision 'tensor16' (opt-in): the FORWARD decoder chain on fp16 hi + scaled lo operand planes (4 bytes per element;
+    csrc/umma_gemm16.cuh with its GroupNorm epilogues, chain16_pack_kernel for the step inputs), the tape, the batched prior and
+    the whole reverse pass as in 'tensor' - against the same fixture of the unmodified reference, same tolerances."""
+    out = run_probe(emul, 'probe_stage3.py', 'stage3_rgb_phase1', tensor=True, extra_env={'HB_EMUL_PRECISION': 'tensor16'})
+    g = np.load(os.path.join(HERE, 'golden', 'stage3_rgb_phase1.npz'))
+    assert abs(out['loss'] - float(g['loss'])) <= 1e-5 * abs(float(g['loss']))
+    assert out['trans_err'] < 1e-5 and out['prior_mean_err'] < 1e-5
+    for k, e in out['grad_err'].items():
+        assert e < 1e-3, (k, e)
+
+
+@pytest.mark.parametrize('prefetch_b', [False, pytest.param(True, marks=pytest.mark.skipif(
+    not os.environ.get('HB_SLOW_TESTS'), reason='second producer order of the same kernels: set HB_SLOW_TESTS=1'))])
 def test_stage3_closure_tensor_precision(emul, prefetch_b):
     """The DEFAULT precision mode: every rollout GEMM on the (emulated) tcgen05 3xTF32 kernel with descriptors built by the
     library's own host code, against the fixture of the unmodified reference.  prefetch_b: the opt-in producer order of

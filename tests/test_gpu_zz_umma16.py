@@ -34,3 +34,25 @@ def test_umma_gemm16_matches_fp64(M, N, K):
     assert torch.isfinite(Cm[:, :N]).all()
     assert float(((Cm[:, :N].double() - ref).abs() / scale).max()) < 2e-6          # emulation: 4e-7; the tensor core truncates its accumulator
     assert torch.isnan(Cm[:, N:]).all()
+
+
+@pytest.mark.parametrize('name', ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_amass'])
+def test_closure_tensor16_matches_reference_golden(name):
+    """precision 'tensor16': the forward decoder chain on fp16 hi/lo operand planes (umma_gemm16 + chain16_pack_kernel), everything
+    else as 'tensor' - against the fixtures of the unmodified reference, with the tolerances of the 'tensor' mode."""
+    from humor_b200 import synth  # noqa: F401
+    from tests import util_stage3 as U
+    from tests.golden_util import load_case, check_against_golden
+    g, prob, c = load_case(name)
+    mo = U.build_product(c['B'], c['T'], c['W'], c['optim_floor'], prob)
+    mo.set_precision('tensor16')
+    loss, grads, aux = U.closure_product(mo, prob, c['nsteps'], c['scale'])
+    check_against_golden(g, loss, aux['stats'], grads, loss_tol=1e-5, stat_tol=1e-4, grad_tol=1e-2)
+    assert np.abs(aux['cam_pred']['verts3d'].detach().cpu().numpy() - g['cam_verts3d']).max() < 1e-4
+    assert np.abs(aux['roll']['trans'].detach().cpu().numpy() - g['rollout_trans']).max() < 2e-5
+    pm = aux['roll']['cond_prior'][0].detach().cpu().numpy()
+    assert np.abs(pm - g['cond_prior_mean']).max() / np.abs(g['cond_prior_mean']).max() < 1e-5
+    # and the mode really changes the kernels: same closure in 'tensor' differs in the last bits
+    mo.set_precision('tensor')
+    loss_t, _, _ = U.closure_product(mo, prob, c['nsteps'], c['scale'])
+    assert loss_t != loss and abs(loss_t - loss) <= 2e-6 * abs(loss)

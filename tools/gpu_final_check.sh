@@ -19,14 +19,16 @@ done
 (timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_default.err) > gpurun_out/bench_default.json
 (HB_UMMA_PREFETCH_B=1 timeout 200 python -m pytest tests/test_gpu_umma.py tests/test_gpu_kernels.py tests/test_gpu_closure.py -x -q 2>&1 | tail -4) > gpurun_out/t_prefetchb.log
 # 3d. the fp16 hi/lo GEMM (4-byte operand elements): parity, then accuracy + in-situ kernel time against the 3xTF32 GEMM
-(HB_TEST_UNVERIFIED=1 timeout 120 python -m pytest tests/test_gpu_zz_umma16.py -x -q 2>&1 | tail -4) > gpurun_out/t_umma16.log
+(HB_TEST_UNVERIFIED=1 timeout 180 python -m pytest tests/test_gpu_zz_umma16.py -x -q 2>&1 | tail -4) > gpurun_out/t_umma16.log
 (timeout 120 python tools/umma16_probe.py 2>gpurun_out/umma16_probe.err) > gpurun_out/umma16_probe.jsonl
+# 3e. precision 'tensor16': forward decoder chain on 4-byte operand elements - parity against the reference fixtures, then the step time
+(timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --precision tensor16 2>gpurun_out/bench_tensor16.err) > gpurun_out/bench_tensor16.json
 # 4. the tests that round 1 could only run on the emulation
 (HB_TEST_UNVERIFIED=1 timeout 150 python -m pytest tests/test_gpu_zz_stage12.py tests/test_gpu_zz_run_e2e.py -x -q 2>&1 | tail -6) > gpurun_out/t_stage12_e2e.log
 tail -n 3 gpurun_out/t_forms.log gpurun_out/t_stage12_e2e.log gpurun_out/t_prefetchb.log gpurun_out/t_umma16.log
 cat gpurun_out/lbs_forms_time.jsonl
 cat gpurun_out/umma16_probe.jsonl
-for f in gpurun_out/bench_s*.json gpurun_out/bench_default.json gpurun_out/bench_prefetchb.json; do python - "$f" <<'PY'
+for f in gpurun_out/bench_s*.json gpurun_out/bench_default.json gpurun_out/bench_prefetchb.json gpurun_out/bench_tensor16.json; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.load(open(sys.argv[1])); print(sys.argv[1], 'ms/step', round(d['ms_per_step'], 3), 'LBS ms', round(d['roofline']['ms_per_launch'], 3), 'frac', round(d['roofline']['frac'], 4))

@@ -29,8 +29,9 @@ struct Tape {
   float *dh3, *dh2, *dh1, *da0, *draw, *dxres, *dnsum, *dG0, *dG1, *dt2j, *dpx;
   // hi/lo operand planes of the tensor-core path (x = hi + lo); h1/h2/h3, pa/pb, dh1/dh2/dh3 hold the hi plane
   float *xin_hi, *xin_lo, *pa_lo, *pb_lo, *dpo_hi, *dpo_lo, *h1_lo, *h2_lo, *h3_lo, *dh1_lo, *dh2_lo, *dh3_lo, *draw_hi, *draw_lo;
-  // fp16 hi/lo operand planes of the forward decoder chain (use_umma == 2): [B][448], [B][1088], [B][1088], [B][576] halves each
-  unsigned short *x16_h, *x16_l, *h1_16h, *h1_16l, *h2_16h, *h2_16l, *h3_16h, *h3_16l;
+  // fp16 hi/lo operand planes of the forward pass (use_umma == 2): step inputs [S][B][448] (decoder K = 448, prior K = 384), decoder
+  // transients [B][1088], [B][1088], [B][576], prior ping-pong [S*B][1024]; halves
+  unsigned short *x16_h, *x16_l, *h1_16h, *h1_16l, *h2_16h, *h2_16l, *h3_16h, *h3_16l, *pa16_h, *pa16_l, *pb16_h, *pb16_l;
   size_t total;
 };
 
@@ -61,10 +62,11 @@ static Tape carve(float* base, int B, int S) {
   t.dh1_lo = take((size_t)B * 1088); t.dh2_lo = take((size_t)B * 1088); t.dh3_lo = take((size_t)B * 576);
   t.draw_hi = take((size_t)B * RAW_LD); t.draw_lo = take((size_t)B * RAW_LD);
   auto take16 = [&](size_t halves) { return reinterpret_cast<unsigned short*>(take((halves + 1) / 2)); };
-  t.x16_h = take16((size_t)B * X16_LD); t.x16_l = take16((size_t)B * X16_LD);
+  t.x16_h = take16(M * X16_LD); t.x16_l = take16(M * X16_LD);
   t.h1_16h = take16((size_t)B * 1088); t.h1_16l = take16((size_t)B * 1088);
   t.h2_16h = take16((size_t)B * 1088); t.h2_16l = take16((size_t)B * 1088);
   t.h3_16h = take16((size_t)B * 576); t.h3_16l = take16((size_t)B * 576);
+  t.pa16_h = take16(M * 1024); t.pa16_l = take16(M * 1024); t.pb16_h = take16(M * 1024); t.pb16_l = take16(M * 1024);
   t.total = off;
   return t;
 }
@@ -478,9 +480,11 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
     const size_t r = (size_t)t * B;
     float* xin = tp.xins + r * XIN_LD;
     if (f16) {
-      chain16_pack_kernel<<<B, 128, 0, st>>>(B, xin, tp.x16_h, tp.x16_l, tp.h1_16h, tp.h1_16l, tp.h2_16h, tp.h2_16l, tp.h3_16h, tp.h3_16l);
+      unsigned short* x16h = tp.x16_h + r * X16_LD;             // kept per step: the batched prior reads all of them afterwards
+      unsigned short* x16l = tp.x16_l + r * X16_LD;
+      chain16_pack_kernel<<<B, 128, 0, st>>>(B, xin, x16h, x16l, tp.h1_16h, tp.h1_16l, tp.h2_16h, tp.h2_16l, tp.h3_16h, tp.h3_16l);
       HB_LAUNCH_CHECK(); ++nl;
-      HB_CUDA(launch_umma_gemm16(tp.x16_h, tp.x16_l, X16_LD, w->dec_w16_h[0], w->dec_w16_l[0], X16_LD, B, 1024, X16_LD, nullptr, 0,
+      HB_CUDA(launch_umma_gemm16(x16h, x16l, X16_LD, w->dec_w16_h[0], w->dec_w16_l[0], X16_LD, B, 1024, X16_LD, nullptr, 0,
                                  tp.h1_16h, tp.h1_16l, 1088, EPI_GN_RELU,
                                  epi_gn(w->dec_b[0], w->dec_g[0], w->dec_be[0], tp.dxh1 + r * 1024, 1024, tp.drs1 + r * 16, 1024, 64), st));
       HB_CUDA(launch_umma_gemm16(tp.h1_16h, tp.h1_16l, 1088, w->dec_w16_h[1], w->dec_w16_l[1], 1088, B, 1024, 1088, nullptr, 0,
@@ -529,7 +533,26 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
   }
   if (prior_out) {
     const int M = S * B;
-    if (tc) {
+    bool p16 = f16;
+    for (int l = 0; l < 5; ++l) p16 = p16 && w->pri_w16_h[l] && w->pri_w16_l[l];
+    if (p16) {
+      // batched prior on the fp16 hi/lo planes the pack kernel left for every step (K = 384 of the 448-half rows: state | pad)
+      unsigned short* h16[2] = {tp.pa16_h, tp.pb16_h};
+      unsigned short* l16[2] = {tp.pa16_l, tp.pb16_l};
+      float* xh[4] = {tp.pxh1, tp.pxh2, tp.pxh3, tp.pxh4};
+      float* rs[4] = {tp.prs1, tp.prs2, tp.prs3, tp.prs4};
+      const unsigned short* a_h = tp.x16_h;
+      const unsigned short* a_l = tp.x16_l;
+      int lda = X16_LD, K = 384;
+      for (int l = 0; l < 4; ++l) {
+        HB_CUDA(launch_umma_gemm16(a_h, a_l, lda, w->pri_w16_h[l], w->pri_w16_l[l], K, M, 1024, K, nullptr, 0, h16[l & 1], l16[l & 1], 1024,
+                                   EPI_GN_RELU, epi_gn(w->pri_b[l], w->pri_g[l], w->pri_be[l], xh[l], 1024, rs[l], 1024, 64), st));
+        a_h = h16[l & 1]; a_l = l16[l & 1]; lda = 1024; K = 1024;
+      }
+      HB_CUDA(launch_umma_gemm16(a_h, a_l, 1024, w->pri_w16_h[4], w->pri_w16_l[4], 1024, M, 96, 1024, prior_out, 96, nullptr, nullptr, 0,
+                                 EPI_BIAS, epi_bias(w->pri_b[4]), st));
+      nl += 5;
+    } else if (tc) {
       // batched prior on the 5th-gen tensor cores (3xTF32): activations travel as hi/lo planes
       // (the input planes xin_hi/xin_lo were written step by step by the glue kernel)
       float* hi[2] = {tp.pa, tp.pb};

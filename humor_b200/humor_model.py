@@ -65,6 +65,7 @@ class PackedWeights:
 
     DEC_K = [416, 1088, 1088, 576]
     DEC_K16 = [448, 1088, 1088, 576]      # multiples of 64 halves
+    PRI_K16 = [384, 1024, 1024, 1024, 1024]
     PRI_K = [352, 1024, 1024, 1024, 1024]
 
     def __init__(self, decoder, prior_net, device):
@@ -117,6 +118,8 @@ class PackedWeights:
             (h, l), (ht, lt) = split(w), split(wt)
             s.pri_w_hi[i], s.pri_w_lo[i] = dev(h), dev(l)
             s.pri_wt_hi[i], s.pri_wt_lo[i] = dev(ht), dev(lt)
+            h16, l16 = split16(_pad_cols(w, self.PRI_K16[i]))
+            s.pri_w16_h[i], s.pri_w16_l[i] = dev16(h16), dev16(l16)
         for i, gn in enumerate(pn):
             s.pri_g[i] = dev(gn.weight)
             s.pri_be[i] = dev(gn.bias)

@@ -152,6 +152,9 @@ typedef struct HbHumorWeights {
    * of 64: [1024][448] [1024][1088] [512][1088] [216][576] halves; NULL: mode 2 falls back to mode 1 */
   const void* dec_w16_h[4];
   const void* dec_w16_l[4];
+  /* the same for the batched prior: pri_w as [1024][384] [1024][1024]x3 [96][1024] halves; NULL: the prior stays on 3xTF32 */
+  const void* pri_w16_h[5];
+  const void* pri_w16_l[5];
 } HbHumorWeights;
 
 /* Replaces HumorModel.roll_out(x_past=None, init_input_dict, S, z_seq, return_prior=True)

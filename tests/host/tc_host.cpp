@@ -59,16 +59,20 @@ long long h_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const
 // fp16 hi/lo GEMM (umma_gemm16.cuh) with its epilogues: planes [rows][ld] halves; BN = 64, split-K over `ks` (1 or 4) CTAs
 long long h_umma_gemm16(const unsigned short* A_h, const unsigned short* A_l, int lda, const unsigned short* B_h, const unsigned short* B_l,
                         int ldb, int M, int N, int K, float* C, int ldc, unsigned short* C16_h, unsigned short* C16_l, int ld16, int epi,
-                        const float* bias, const float* gamma, const float* beta, float* xhat, int ldxh, float* rstd, int gsize, int ks) {
+                        const float* bias, const float* gamma, const float* beta, float* xhat, int ldxh, float* rstd, int gsize, int ks,
+                        int bn) {
   auto map = [](const unsigned short* p, int rows, int K, int ld, unsigned box_rows) {
     return CUtensorMap{reinterpret_cast<const float*>(p), (unsigned long long)rows, (unsigned long long)K, (unsigned long long)ld, 64, box_rows, 0, 1};
   };
-  CUtensorMap a_h = map(A_h, M, K, lda, UM_BM), a_l = map(A_l, M, K, lda, UM_BM), b_h = map(B_h, N, K, ldb, 64), b_l = map(B_l, N, K, ldb, 64);
+  CUtensorMap a_h = map(A_h, M, K, lda, UM_BM), a_l = map(A_l, M, K, lda, UM_BM), b_h = map(B_h, N, K, ldb, (unsigned)bn),
+              b_l = map(B_l, N, K, ldb, (unsigned)bn);
   GemmEpi ep;
   ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.xhat = xhat; ep.rstd = rstd; ep.ldxh = ldxh; ep.Cch = N; ep.gsize = gsize;
   tcemu::reset();
-  const dim3 grid(cdiv(N, 64) * ks, cdiv(M, UM_BM));
-  if (epi == EPI_BIAS && ks == 1) shim::launch_cluster(grid, dim3(192), 1, [&] { umma_gemm16_kernel<64, EPI_BIAS, 1>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
+  const dim3 grid(cdiv(N, bn) * ks, cdiv(M, UM_BM));
+  if (bn == 128 && epi == EPI_BIAS) shim::launch_cluster(grid, dim3(192), 1, [&] { umma_gemm16_kernel<128, EPI_BIAS, 1>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
+  else if (bn == 128) shim::launch_cluster(grid, dim3(192), 1, [&] { umma_gemm16_kernel<128, EPI_GN_RELU, 1>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
+  else if (epi == EPI_BIAS && ks == 1) shim::launch_cluster(grid, dim3(192), 1, [&] { umma_gemm16_kernel<64, EPI_BIAS, 1>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
   else if (epi == EPI_BIAS) shim::launch_cluster(grid, dim3(192), 4, [&] { umma_gemm16_kernel<64, EPI_BIAS, 4>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
   else if (ks == 1) shim::launch_cluster(grid, dim3(192), 1, [&] { umma_gemm16_kernel<64, EPI_GN_RELU, 1>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
   else shim::launch_cluster(grid, dim3(192), 4, [&] { umma_gemm16_kernel<64, EPI_GN_RELU, 4>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });

@@ -286,9 +286,9 @@ def split16_np(x):
     return np.ascontiguousarray(h), np.ascontiguousarray(l)
 
 
-@pytest.mark.parametrize('ks', [1, 4])
+@pytest.mark.parametrize('ks,bn', [(1, 64), (4, 64), (1, 128)])          # 128-wide tiles: the batched prior's shape class
 @pytest.mark.parametrize('gsize', [64, 32])
-def test_umma_gemm16_groupnorm_epilogue_and_fp16_planes(H, ks, gsize):
+def test_umma_gemm16_groupnorm_epilogue_and_fp16_planes(H, ks, bn, gsize):
     """One decoder-style layer from 4-byte operand elements: Linear + bias + GroupNorm + ReLU in the epilogue (x-hat and 1/sigma to
     the tape as the reverse pass expects them), result as fp32 AND as the fp16 hi/lo planes of the next layer; single CTA per tile
     and split-K over a 4-CTA cluster; ragged M and N."""
@@ -297,11 +297,11 @@ def test_umma_gemm16_groupnorm_epilogue_and_fp16_planes(H, ks, gsize):
     A = (rng.randn(M, K) * 0.8).astype(np.float32)
     W = (rng.randn(N, K) * 0.04).astype(np.float32)
     # parameter vectors padded to the tile width: the epilogue normalises whole groups of its (padded) 64-column tile
-    bias, gamma, beta = (np.ascontiguousarray(rng.randn(192).astype(np.float32) * s) for s in (0.1, 1.0, 0.2))
+    bias, gamma, beta = (np.ascontiguousarray(rng.randn(256).astype(np.float32) * s) for s in (0.1, 1.0, 0.2))
     gamma = np.ascontiguousarray(gamma + 1.0)
     Ah, Al = split16_np(A)
     Wh, Wl = split16_np(W)
-    ldc, ld16, ldxh = 192, 192, 192
+    ldc, ld16, ldxh = 256, 256, 256                            # room for the 128-wide tiles' padded columns (x-hat is written per whole group)
     C = np.full((M, ldc), np.nan, np.float32)
     Ch = np.zeros((M, ld16), np.float16)
     Cl = np.zeros((M, ld16), np.float16)
@@ -309,8 +309,8 @@ def test_umma_gemm16_groupnorm_epilogue_and_fp16_planes(H, ks, gsize):
     rstd = np.full((M, 16), np.nan, np.float32)
     H.h_umma_gemm16.restype = ctypes.c_longlong
     nmma = H.h_umma_gemm16(P(Ah), P(Al), K, P(Wh), P(Wl), K, M, N, K, P(C), ldc, P(Ch), P(Cl), ld16, 1, P(bias), P(gamma), P(beta),
-                           P(xhat), ldxh, P(rstd), gsize, ks)
-    assert nmma == 2 * 3 * (K // 64) * 4 * 3                   # row tiles x column tiles x k-blocks x 4 K-steps x (h.h, l.h, h.l)
+                           P(xhat), ldxh, P(rstd), gsize, ks, bn)
+    assert nmma == 2 * -(-N // bn) * (K // 64) * 4 * 3          # row tiles x column tiles x k-blocks x 4 K-steps x (h.h, l.h, h.l)
     y = A.astype(np.float64) @ W.astype(np.float64).T + bias[:N]
     # N = 184 is not a multiple of the group size: the kernel normalises whole groups of its padded tile; compare complete groups
     ng = N // gsize

@@ -251,11 +251,13 @@ static cudaError_t launch16_t(const CUtensorMap& a_h, const CUtensorMap& a_l, co
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = UmmaSmem<BN>::TOTAL;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = KS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL: see griddepcontrol in the kernel
+  at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = KS; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
   cfg.attrs = at;
-  cfg.numAttrs = KS > 1 ? 1 : 0;
+  cfg.numAttrs = KS > 1 ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, umma_gemm16_kernel<BN, EPI, KS>, a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep);
 }
 

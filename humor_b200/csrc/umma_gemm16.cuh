@@ -56,6 +56,7 @@ umma_gemm16_kernel(const __grid_constant__ CUtensorMap tmA_h, const __grid_const
   const int nkb = max(0, min(nkb_all, kb0 + nkb_per) - kb0);
   const int nchunk = (nkb + U16_CHUNK - 1) / U16_CHUNK;
 
+  pdl_launch_dependents();             // programmatic dependent launch, as umma_gemm3_kernel: prologue under the predecessor's tail
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
@@ -69,6 +70,7 @@ umma_gemm16_kernel(const __grid_constant__ CUtensorMap tmA_h, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ld_shared_u32(tptr);
+  pdl_wait();                          // predecessor grid complete, its writes (our A planes) visible
 
   if (warp == 0) {
     if (lane == 0) {

@@ -213,6 +213,11 @@ def run_product(args):
                      'slab_frames': args.lbs_slab or int(os.environ.get('HB_LBS_SLAB', 512))}
     shares = kernel_shares(mo, obs, params, dev)
     cpu = torch_cuda = None
+    try:        # what the last end-to-end step returned to the host: lets runs of the same seeded problem be compared across modes
+        result_check = {'loss': float(host_loss[0]),
+                        'grad_l2': float(torch.sqrt(sum((host_out[n].double() ** 2).sum() for n in names)))}
+    except Exception:  # noqa: BLE001
+        result_check = None
     out = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -227,7 +232,7 @@ def run_product(args):
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches), 'gpu_launches_per_step': launches / args.steps,
         'clocks': clocks, 'roofline': roof, 'step_breakdown_ms': shares, 'cpu_baseline': cpu,
-        'torch_cuda_port': torch_cuda,
+        'torch_cuda_port': torch_cuda, 'result_check': result_check,
         'lbs_bytes_roofline_frac_of_step': value * (2.0 + 3.0 / T) * (LBS_BYTES_FWD + LBS_BYTES_BWD) / (hbm_peak * 1e9),
     }
     # The two context numbers run in bounded child processes AFTER the measurement, inside what is left of the run's time
@@ -248,6 +253,9 @@ def run_product(args):
         # the opt-in kernel forms of the dense LBS forward, verified against the default forms and timed stand-alone on this GPU
         # (separate child processes: a form that faults must not take the measurement down).  The step above ran forms 1/1.
         out['roofline_candidates'] = lbs_candidates(B, T, hbm_peak)
+        # opt-in modes of the STEP (never the default), each a complete child run of this script on the same seeded problem;
+        # `verified` = its loss and gradient norm agree with the run above
+        out['step_candidates'] = step_candidates(args, result_check)
     _PARTIAL = None
     print(json.dumps(out))
 
@@ -425,6 +433,38 @@ def lbs_candidates(B, T, hbm_peak):
             done = {(g['skin'], g['blend']) for g in got}
             missing = [f for f in forms.split(';') if tuple(int(x) for x in f.split(',')) not in done]
             recs.append({'forms': ';'.join(missing), 'error': f'child ended with {rc}', 'stderr_tail': tail})
+    return recs
+
+
+def step_candidates(args, ref_check):
+    """Child runs of bench.py with an opt-in mode switched on: {what, ms_per_step, value, e2e, loss / grad-norm difference to this
+    run, verified}.  Last in line: whatever does not fit into the run's time limit is reported as skipped."""
+    cands = [('precision tensor16 (forward decoder chain + prior on fp16 hi/lo operand planes)', ['--precision', 'tensor16'], {}),
+             ('HB_UMMA_PREFETCH_B=1 (weight tiles requested before the dependent-launch wait)', [], {'HB_UMMA_PREFETCH_B': '1'})]
+    recs = []
+    for what, flags, extra in cands:
+        left = _time_left() - 15.0
+        if left < 60.0 or args.precision != 'tensor':
+            recs.append({'what': what, 'error': 'skipped: the run\'s time limit was nearly spent'})
+            continue
+        cmd = [sys.executable, os.path.abspath(__file__), '--steps', str(args.steps), '--warmup', str(args.warmup), '--batch', str(args.batch),
+               '--seq-len', str(args.seq_len), '--no-cpu-baseline'] + flags
+        env = dict(os.environ, **extra)
+        for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
+            env.pop(k, None)
+        env['HB_BENCH_LIMIT_S'] = str(int(min(100.0, left)))
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=min(100.0, left), env=env)
+            d = json.loads([l for l in r.stdout.splitlines() if l.startswith('{')][-1])
+            rec = {'what': what, 'ms_per_step': d['ms_per_step'], 'value': d['value'], 'e2e': d['e2e']['value'],
+                   'result_check': d.get('result_check')}
+            if ref_check and d.get('result_check'):
+                dl = abs(d['result_check']['loss'] - ref_check['loss']) / max(1.0, abs(ref_check['loss']))
+                dg = abs(d['result_check']['grad_l2'] - ref_check['grad_l2']) / max(1e-30, abs(ref_check['grad_l2']))
+                rec.update(loss_rel_diff=dl, grad_l2_rel_diff=dg, verified=bool(dl < 1e-5 and dg < 1e-2))
+            recs.append(rec)
+        except Exception as e:  # noqa: BLE001
+            recs.append({'what': what, 'error': f'{type(e).__name__}: {str(e)[:200]}'})
     return recs
 
 

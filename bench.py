@@ -292,7 +292,7 @@ def lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind):
         blend = {1: 'umma_gemm3_kernel<128,BIAS>', 2: 'lbs_blend_kernel', 3: 'lbs_blend_kernel (single-pass pose columns)'}.get(ub.value)
         skin = {1: 'lbs_skin_apply_kernel', 2: 'lbs_skin_group_kernel'}.get(us.value)
         name = ('dense LBS forward: lbs_pose_kernel + lbs_fuseg_kernel (persistent tcgen05 blend + group skinning' +
-                ({3: ', single-pass pose columns)', 4: ', fp16 pose columns)'}.get(ub.value, ')'))) if us.value == 3 else \
+                ({3: ', single-pass pose columns)', 4: ', fp16 pose columns)', 5: ', fp16 hi/lo planes)'}.get(ub.value, ')'))) if us.value == 3 else \
             f'dense LBS forward: lbs_pose_kernel + per slab {blend} + {skin}'
         return {'kernel': name, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'peak_source': peak_kind, 'unit': 'GB/s',
                 'frac': achieved / hbm_peak, 'traffic': None, 'ms_per_launch': ms, 'frames_per_launch': N,
@@ -407,7 +407,7 @@ def lbs_candidates(B, T, hbm_peak):
     for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'HB_LBS_SKIN', 'HB_LBS_BLEND'):
         env.pop(k, None)
     recs = []
-    for forms in ('2,1;1,2;2,2;2,3', '3,1;3,3;3,4'):
+    for forms in ('2,1;1,2;2,2;2,3', '3,1;3,3;3,4;3,5'):
         left = _time_left() - 20.0
         if left < 40.0:
             recs.append({'forms': forms, 'error': 'skipped: the run\'s time limit was nearly spent'})
@@ -545,7 +545,7 @@ def main():
                     help="'tensor': GEMMs on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels (gradient-exact parity mode); "
                          "'tensor16': 'tensor' with the forward decoder chain on fp16 hi/lo operand planes (opt-in)")
     ap.add_argument('--lbs-skin', type=int, default=0, help='dense LBS skinning pass form (humor_lbs_configure): 1 lane=vertex, 2 lane=frame, 3 fused blend + lane=frame skinning (one persistent kernel)')
-    ap.add_argument('--lbs-blend', type=int, default=0, help='dense LBS blend GEMM form: 1 tile per CTA, 2 persistent 128x256 tiles, 3 = 2 + single TF32 pass on the pose columns, 4 (skin 3) = fp16 pose columns')
+    ap.add_argument('--lbs-blend', type=int, default=0, help='dense LBS blend GEMM form: 1 tile per CTA, 2 persistent 128x256 tiles, 3 = 2 + single TF32 pass on the pose columns, 4 (skin 3) = fp16 pose columns, 5 (skin 3) = fp16 hi/lo planes for every column (fp32-level)')
     ap.add_argument('--lbs-slab', type=int, default=0, help='frames per v_posed slab (128..512)')
     ap.add_argument('--no-graph', action='store_true', help='evaluate the closure eagerly instead of replaying a CUDA graph')
     ap.add_argument('--port-cuda', default='', help='comma list of batch sizes: time the oracle port as eager PyTorch on cuda:0')

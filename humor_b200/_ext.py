@@ -72,7 +72,8 @@ class HbLbsModel(C.Structure):
                 ('fused_nct', C.c_int), ('fused_wk', C.c_int),
                 ('g_start', C.c_void_p), ('g_joint', C.c_void_p), ('g_w', C.c_void_p), ('num_groups', C.c_int),
                 ('ft_nct', C.c_int), ('g_slot', C.c_void_p), ('ft_tab', C.c_void_p),
-                ('blend_k0_hi', C.c_void_p), ('blend_k0_lo', C.c_void_p), ('blend16', C.c_void_p)]
+                ('blend_k0_hi', C.c_void_p), ('blend_k0_lo', C.c_void_p), ('blend16', C.c_void_p),
+                ('blend16a_h', C.c_void_p), ('blend16a_l', C.c_void_p)]
 
 
 class HbHumorWeights(C.Structure):

@@ -210,6 +210,12 @@ class LbsModel:
         self.t['blend_k0_hi'], self.t['blend_k0_lo'] = k0h.contiguous(), (k0 - k0h).contiguous()
         self.t['blend16'] = (bt[:, 32:] * 1024.0).to(torch.float16).contiguous()
         s.blend_k0_hi, s.blend_k0_lo, s.blend16 = (self.t[k].data_ptr() for k in ('blend_k0_hi', 'blend_k0_lo', 'blend16'))
+        # blend form 5: every column, K padded to 256, fp16 hi + UNSCALED fp16 lo plane (x = h + l)
+        bs = torch.zeros(packed['v3_ld'], 256, device=self.device)
+        bs[:, :224] = bt * 1024.0
+        bh = bs.to(torch.float16)
+        self.t['blend16a_h'], self.t['blend16a_l'] = bh.contiguous(), (bs - bh.float()).to(torch.float16).contiguous()
+        s.blend16a_h, s.blend16a_l = self.t['blend16a_h'].data_ptr(), self.t['blend16a_l'].data_ptr()
         self.ws_slot = 0
         s.max_depth = packed['max_depth']
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))

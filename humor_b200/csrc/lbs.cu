@@ -48,7 +48,7 @@ static LbsWs lbs_carve(float* base, int N) {
   w.feat_hi = take(Np * TC_KF);
   w.feat_lo = take(Np * TC_KF);
   w.vposed = take((size_t)TC_SLAB * 20736);
-  w.feat16 = take(Np * 96);                     // [Np][192] halves: fp16 plane of the pose-feature columns (blend form 4)
+  w.feat16 = take(Np * 256);                    // fp16 planes of the feature rows: [Np][192] halves (blend form 4) or 2 x [Np][256] (form 5)
   w.total = off;
   return w;
 }
@@ -690,7 +690,7 @@ static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + 
 using namespace hb;
 
 extern "C" int humor_lbs_configure(int skin_form, int blend_form, int slab_frames) {
-  if ((skin_form < 0 || skin_form > 3) || (blend_form < 0 || blend_form > 4) ||
+  if ((skin_form < 0 || skin_form > 3) || (blend_form < 0 || blend_form > 5) ||
       (slab_frames != 0 && (slab_frames < 128 || slab_frames > TC_SLAB)))
     return HB_ERR_ARG;
   if (skin_form) g_skin_form = skin_form;
@@ -735,21 +735,30 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
   if (fuseg) {
     LbsFusegArgs fa;
     const bool f16 = g_blend_form == 4 && m->blend16 && m->blend_k0_hi && m->blend_k0_lo;
+    const bool f16x3 = g_blend_form == 5 && m->blend16a_h && m->blend16a_l;
     fa.N = N; fa.num_verts = m->num_verts; fa.num_groups = m->num_groups; fa.nrt = fa.nct = 0; fa.fast = g_blend_form == 3 || f16;
-    fa.nkb16 = f16 ? 3 : 0; fa.out_scale = f16 ? 0.0009765625f : 1.f;
+    fa.nkb16 = f16x3 ? 4 : (f16 ? 3 : 0); fa.f16x3 = f16x3 ? 1 : 0; fa.out_scale = (f16 || f16x3) ? 0.0009765625f : 1.f;
     fa.g_start = m->g_start; fa.g_joint = m->g_joint; fa.g_slot = m->g_slot; fa.g_w = m->g_w; fa.ft_tab = m->ft_tab;
     fa.v_template = m->v_template; fa.A = ws.A; fa.trans = trans; fa.out = verts;
-    if (f16) {
-      // columns 0..31 (betas + first pose columns): three tf32 passes on the 2^10-scaled planes; columns 32..223: one fp16 pass
-      HB_CUDA(launch_feat_f16(ws.feat, LBS_KF, LBS_KF, N, 32, 3, ws.feat16, st));
+    if (f16x3) {
+      // every column as fp16 hi + (unscaled) lo planes, K = 256: three products per k-block, no tf32 k-blocks
+      unsigned short* f16h = reinterpret_cast<unsigned short*>(ws.feat16);
+      unsigned short* f16l = f16h + (size_t)align_up((size_t)N, 64) * 256;
+      HB_CUDA(launch_feat_f16(ws.feat, LBS_KF, LBS_KF, N, 0, 4, f16h, f16l, st));
       ++nl;
-      HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_k0_hi, m->blend_k0_lo, 32, m->v3_ld, 32, ws.feat16, m->blend16, 192,
+      HB_CUDA(launch_lbs_fuseg(nullptr, nullptr, TC_KF, nullptr, nullptr, TC_KF, m->v3_ld, 0, f16h, m->blend16a_h, f16l, m->blend16a_l, 256,
                                fa, st));
+    } else if (f16) {
+      // columns 0..31 (betas + first pose columns): three tf32 passes on the 2^10-scaled planes; columns 32..223: one fp16 pass
+      HB_CUDA(launch_feat_f16(ws.feat, LBS_KF, LBS_KF, N, 32, 3, ws.feat16, nullptr, st));
+      ++nl;
+      HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_k0_hi, m->blend_k0_lo, 32, m->v3_ld, 32, ws.feat16, m->blend16, nullptr,
+                               nullptr, 192, fa, st));
     } else {
-      HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_t_hi, m->blend_t_lo, TC_KF, m->v3_ld, TC_KF, nullptr, nullptr, 0,
-                               fa, st));
+      HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_t_hi, m->blend_t_lo, TC_KF, m->v3_ld, TC_KF, nullptr, nullptr, nullptr,
+                               nullptr, 0, fa, st));
     }
-    g_used_skin = 3; g_used_blend = f16 ? 4 : (fa.fast ? 3 : 1);
+    g_used_skin = 3; g_used_blend = f16x3 ? 5 : (f16 ? 4 : (fa.fast ? 3 : 1));
     ++nl;
     if (joints && njo == 73) {
       lbs_gather_extra_kernel<<<cdiv(N * 21, 256), 256, 0, st>>>(*m, N, verts, joints);

@@ -32,6 +32,10 @@
 //           the 11-bit significand of tf32; the blend planes are pre-scaled by 2^10 so that pose offsets of 1e-6 m stay in
 //           fp16's normal range, the epilogue scales back): 3 entries of 64 halves instead of 6 of 32 floats - 200 KB of
 //           operand planes and 24 MMA issue slots per tile.
+//   fp16x3  (blend form 5) EVERY column as fp16 hi + lo planes, three products per k-block (h.h + l.h + h.l) into the one accumulator:
+//           the lo planes are UNSCALED (l = fp16(x - h)); what that costs is an absolute floor of 3e-8 on tiny operands, i.e.
+//           ~1e-9 m after the 2^-10 scale-back - irrelevant here, and it keeps one accumulator per tile (a scaled lo part would
+//           need a second one: 768 TMEM columns).  fp32-level accuracy (as three TF32 passes) at 320 instead of 560 KB per tile.
 // Barrier protocol (all mbarriers, phases counted per use):
 //   full[s]/empty[s]   operand ring (TMA complete_tx / tcgen05.commit), as lbs_blend_kernel
 //   tfull[b]/tempty[b] TMEM buffer b = tile parity (tcgen05.commit / one arrive per epilogue warp), as lbs_blend_kernel
@@ -95,7 +99,8 @@ __global__ void __launch_bounds__(FG_THREADS, 1)
 lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmA16,
-                 const __grid_constant__ CUtensorMap tmB16, int K, LbsFusegArgs a) {
+                 const __grid_constant__ CUtensorMap tmB16, const __grid_constant__ CUtensorMap tmA16l,
+                 const __grid_constant__ CUtensorMap tmB16l, int K, LbsFusegArgs a) {
   HB_DYN_SMEM(smem_raw);
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -156,13 +161,15 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             tma_load_2d(st + FG_A_PLANE, pl ? &tmB_lo : &tmB_hi, full0 + 8 * s, kb * UM_BK, n0);
           }
         }
-        for (int kb = 0; kb < a.nkb16; ++kb, ++g) {             // fp16 k-blocks: 64 halves = the same 128-byte rows, same entry
-          const int s = g % FG_RING;
-          mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
-          const uint32_t st = base + s * FG_ENTRY;
-          mbar_expect_tx(full0 + 8 * s, FG_ENTRY);
-          tma_load_2d(st, &tmA16, full0 + 8 * s, kb * 64, m0);
-          tma_load_2d(st + FG_A_PLANE, &tmB16, full0 + 8 * s, kb * 64, n0);
+        for (int kb = 0; kb < a.nkb16; ++kb) {                  // fp16 k-blocks: 64 halves = the same 128-byte rows, same entry
+          for (int pl = 0; pl < (a.f16x3 ? 2 : 1); ++pl, ++g) {   // hi entry, then (three-product form) the lo entry
+            const int s = g % FG_RING;
+            mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
+            const uint32_t st = base + s * FG_ENTRY;
+            mbar_expect_tx(full0 + 8 * s, FG_ENTRY);
+            tma_load_2d(st, pl ? &tmA16l : &tmA16, full0 + 8 * s, kb * 64, m0);
+            tma_load_2d(st + FG_A_PLANE, pl ? &tmB16l : &tmB16, full0 + 8 * s, kb * 64, n0);
+          }
         }
       }
     }
@@ -209,9 +216,24 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           tc_fence_after();
           const uint32_t sth = base + sh * FG_ENTRY;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc16, 1);
-          umma_commit(empty0 + 8 * sh);
+          for (int k = 0; k < 4; ++k)                           // h . h (the tile's very first MMA overwrites the accumulator)
+            umma_f16(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc16, (nkb != 0) || (kb != 0) || (k != 0));
+          if (a.f16x3) {                                        // + l . h + h . l: x = h + l with UNSCALED fp16 lo planes, one accumulator
+            const int gl = g++;
+            const int sl = gl % FG_RING;
+            mbar_wait(full0 + 8 * sl, (gl / FG_RING) & 1);
+            tc_fence_after();
+            const uint32_t stl = base + sl * FG_ENTRY;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(tacc, umma_desc_sw128(stl + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc16, 1);
+              umma_f16(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(stl + FG_A_PLANE + k * 32), idesc16, 1);
+            }
+            umma_commit(empty0 + 8 * sh);
+            umma_commit(empty0 + 8 * sl);
+          } else {
+            umma_commit(empty0 + 8 * sh);
+          }
         }
         umma_commit(tfull0 + 8 * buf);
       }

@@ -195,12 +195,15 @@ cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf
 // skin form 3: blend + group skinning in one persistent kernel (lbs_fuseg.cuh).  `a` arrives with the model tables, A, trans,
 // out, N, num_verts, num_groups and fast filled in; tile counts are set here.
 cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
-                             int b_rows, int K, const void* feat16, const void* bt16, int ld16, LbsFusegArgs a, cudaStream_t st) {
+                             int b_rows, int K, const void* feat16, const void* bt16, const void* feat16l, const void* bt16l, int ld16,
+                             LbsFusegArgs a, cudaStream_t st) {
   if (!load_encode()) return cudaErrorNotSupported;
   if (K % UM_BK || ldf % 4 || ldb % 4 || a.N <= 0 || a.num_groups <= 0 || (a.num_verts & 1) ||
       a.num_groups != cdiv(a.num_verts, FG_G) || !a.g_start || !a.g_joint || !a.g_slot || !a.g_w || !a.ft_tab)
     return cudaErrorInvalidValue;
   if (a.nkb16 < 0 || (a.nkb16 > 0 && (!feat16 || !bt16 || ld16 % 8 || ld16 < 64 * a.nkb16))) return cudaErrorInvalidValue;
+  if (a.f16x3 && (a.nkb16 <= 0 || !feat16l || !bt16l)) return cudaErrorInvalidValue;
+  if (K == 0 && a.nkb16 <= 0) return cudaErrorInvalidValue;
   static int sms = 0, want = 0, direct = 0;
   if (!sms) {
     int dev = 0;
@@ -217,21 +220,23 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
   a.direct_store = direct;
   a.nrt = cdiv(a.N, UM_BM);
   a.nct = cdiv(a.num_groups, FG_GPT);
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16;
-  if (!make_map(&ta_hi, feat_hi, a.N, K, ldf, UM_BM) || !make_map(&ta_lo, feat_lo, a.N, K, ldf, UM_BM) ||
-      !make_map(&tb_hi, bt_hi, b_rows, K, ldb, FG_BN) || !make_map(&tb_lo, bt_lo, b_rows, K, ldb, FG_BN) ||
-      !make_map_plain(&tt, a.A, a.N, 624, 624, 12, UM_BM))
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16, ta16l, tb16l;
+  if (!make_map_plain(&tt, a.A, a.N, 624, 624, 12, UM_BM)) return cudaErrorInvalidValue;
+  if (K > 0 && (!make_map(&ta_hi, feat_hi, a.N, K, ldf, UM_BM) || !make_map(&ta_lo, feat_lo, a.N, K, ldf, UM_BM) ||
+                !make_map(&tb_hi, bt_hi, b_rows, K, ldb, FG_BN) || !make_map(&tb_lo, bt_lo, b_rows, K, ldb, FG_BN)))
     return cudaErrorInvalidValue;
-  if (a.nkb16 > 0) {
-    if (!make_map_f16(&ta16, feat16, a.N, 64 * a.nkb16, ld16, UM_BM) || !make_map_f16(&tb16, bt16, b_rows, 64 * a.nkb16, ld16, FG_BN))
-      return cudaErrorInvalidValue;
-  } else {                                                    // never dereferenced: any valid descriptor
-    ta16 = ta_hi; tb16 = tb_hi;
-  }
+  if (a.nkb16 > 0 && (!make_map_f16(&ta16, feat16, a.N, 64 * a.nkb16, ld16, UM_BM) || !make_map_f16(&tb16, bt16, b_rows, 64 * a.nkb16, ld16, FG_BN)))
+    return cudaErrorInvalidValue;
+  if (a.f16x3 && (!make_map_f16(&ta16l, feat16l, a.N, 64 * a.nkb16, ld16, UM_BM) || !make_map_f16(&tb16l, bt16l, b_rows, 64 * a.nkb16, ld16, FG_BN)))
+    return cudaErrorInvalidValue;
+  // descriptors of operand kinds this launch does not use are never dereferenced: any valid one stands in
+  if (K == 0) { ta_hi = ta_lo = ta16; tb_hi = tb_lo = tb16; }
+  if (a.nkb16 <= 0) { ta16 = ta_hi; tb16 = tb_hi; }
+  if (!a.f16x3) { ta16l = ta16; tb16l = tb16; }
   const int ntiles = a.nrt * a.nct;
   int grid = ntiles < sms ? ntiles : sms;
   if (want > 0 && want < grid) grid = want;
-  lbs_fuseg_kernel<<<grid, FG_THREADS, FG_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16, K, a);
+  lbs_fuseg_kernel<<<grid, FG_THREADS, FG_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16, ta16l, tb16l, K, a);
   return cudaGetLastError();
 }
 
@@ -313,21 +318,31 @@ static inline unsigned short f16_bits(float x) { return tcemu::f32_to_f16_bits(x
 #else
 __device__ __forceinline__ unsigned short f16_bits(float x) { return __half_as_ushort(__float2half_rn(x)); }
 #endif
-__global__ void feat_f16_kernel(const float* __restrict__ feat, int ldf, int ncols, int N, int c0, int w, unsigned short* __restrict__ out) {
+#ifdef HB_HOST_SHIM
+static inline float f16_value(unsigned short b) { _Float16 h; std::memcpy(&h, &b, 2); return (float)h; }
+#else
+__device__ __forceinline__ float f16_value(unsigned short b) { return __half2float(__ushort_as_half(b)); }
+#endif
+__global__ void feat_f16_kernel(const float* __restrict__ feat, int ldf, int ncols, int N, int c0, int w, unsigned short* __restrict__ out,
+                                unsigned short* __restrict__ out_lo) {
   const size_t n = (size_t)N * w;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / w;
     const int j = (int)(i - r * w);
-    out[i] = f16_bits(c0 + j < ncols ? feat[r * ldf + c0 + j] : 0.f);
+    const float x = c0 + j < ncols ? feat[r * ldf + c0 + j] : 0.f;
+    const unsigned short h = f16_bits(x);
+    out[i] = h;
+    if (out_lo) out_lo[i] = f16_bits(x - f16_value(h));        // unscaled lo plane of blend form 5
   }
 }
 #ifndef HB_HOST_SHIM
-cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, cudaStream_t st) {
+cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, void* out_lo, cudaStream_t st) {
   if (!feat || !out || N <= 0 || nkb16 <= 0) return cudaErrorInvalidValue;
   const size_t n = (size_t)N * 64 * nkb16;
   size_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  feat_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(feat, ldf, ncols, N, c0, 64 * nkb16, static_cast<unsigned short*>(out));
+  feat_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(feat, ldf, ncols, N, c0, 64 * nkb16, static_cast<unsigned short*>(out),
+                                                    static_cast<unsigned short*>(out_lo));
   return cudaGetLastError();
 }
 cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {

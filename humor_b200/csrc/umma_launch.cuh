@@ -33,7 +33,8 @@ struct LbsFusegArgs {
   int num_groups;
   int nrt, nct;            // row tiles (128 frames), column tiles (64 vertices)
   int fast;                // 1: only k-block 0 keeps three TF32 passes
-  int nkb16;               // > 0 (blend form 4): after the tf32 k-blocks, this many 64-wide fp16 k-blocks (one pass, kind::f16)
+  int nkb16;               // > 0 (blend forms 4, 5): after the tf32 k-blocks, this many 64-wide fp16 k-blocks (kind::f16)
+  int f16x3;               // 1 (blend form 5): the fp16 k-blocks have lo planes too: h.h + l.h + h.l (fp32-level); 0: one pass on h
   float out_scale;         // accumulator -> metres (2^-10 when the blend planes are pre-scaled for the fp16 range, else 1)
   int direct_store;        // 1: lane = frame stores straight from registers (A/B variant), 0: staged row stores; set by the launcher
   const int* g_start;      // [num_groups + 1]
@@ -48,8 +49,11 @@ struct LbsFusegArgs {
 };
 // bt_* = blend_t hi/lo planes [b_rows][K] (ldb floats per row); the caller fills every field of `a` except nrt / nct.
 // a.nkb16 > 0: feat16 [N][ld16] / bt16 [b_rows][ld16] fp16 planes of the remaining K columns (ld16 halves per row, >= 64 * nkb16)
+// a.f16x3: feat16l / bt16l = the lo planes (same shapes); K may be 0 (no tf32 k-blocks)
 cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
-                             int b_rows, int K, const void* feat16, const void* bt16, int ld16, LbsFusegArgs a, cudaStream_t st);
-// fp16 plane of the pose-feature columns [c0, c0 + 64 * nkb16) of feat[N][ldf] (columns >= ncols read as zero)
-cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, cudaStream_t st);
+                             int b_rows, int K, const void* feat16, const void* bt16, const void* feat16l, const void* bt16l, int ld16,
+                             LbsFusegArgs a, cudaStream_t st);
+// fp16 plane(s) of the feature columns [c0, c0 + 64 * nkb16) of feat[N][ldf] (columns >= ncols read as zero): out = fp16(x),
+// out_lo (nullable) = fp16(x - out)
+cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, void* out_lo, cudaStream_t st);
 }  // namespace hb

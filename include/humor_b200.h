@@ -87,6 +87,10 @@ typedef struct HbLbsModel {
   const float* blend_k0_hi;
   const float* blend_k0_lo;
   const void* blend16;
+  /* blend form 5 (skin form 3 only): blend_t * 2^10, all 208 columns padded to 256, as fp16 hi plane and UNSCALED fp16 lo
+     plane (x = h + l) [v3_ld][256] each; NULL: form unavailable */
+  const void* blend16a_h;
+  const void* blend16a_l;
 } HbLbsModel;
 
 /* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs
@@ -106,6 +110,8 @@ int humor_lbs_fwd(const HbLbsModel* m, int N, int frames_per_beta, const float* 
  *               3 = 2 with a single TF32 pass on the pose-offset columns (<= 7e-5 m vertex error; forms 1, 2: 1e-6 m)
  *               4 (with skin_form 3 only) = 3 with those columns as fp16 operand planes (same 11-bit significand, half the
  *                 bytes, kind::f16 MMAs)
+ *               5 (with skin_form 3 only) every column as fp16 hi + lo planes, three products: the accuracy of forms 1, 2
+ *                 (1e-6 m) from 4 instead of 8 bytes per operand element
  *   slab_frames frames per v_posed slab kept in L2 between the two kernels (128..512)
  * Process-wide; not to be changed while a call is in flight.  Environment defaults: HB_LBS_SKIN, HB_LBS_BLEND, HB_LBS_SLAB. */
 int humor_lbs_configure(int skin_form, int blend_form, int slab_frames);

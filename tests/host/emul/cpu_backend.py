@@ -44,6 +44,11 @@ def install(lib_path):
         self.t['blend_k0_hi'], self.t['blend_k0_lo'] = k0h, (k0 - k0h).contiguous()
         self.t['blend16'] = (bt[:, 32:] * 1024.0).to(torch.float16).contiguous()
         s.blend_k0_hi, s.blend_k0_lo, s.blend16 = (self.t[k].data_ptr() for k in ('blend_k0_hi', 'blend_k0_lo', 'blend16'))
+        bs = torch.zeros(packed['v3_ld'], 256)
+        bs[:, :224] = bt * 1024.0
+        bh = bs.to(torch.float16)
+        self.t['blend16a_h'], self.t['blend16a_l'] = bh.contiguous(), (bs - bh.float()).to(torch.float16).contiguous()
+        s.blend16a_h, s.blend16a_l = self.t['blend16a_h'].data_ptr(), self.t['blend16a_l'].data_ptr()
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))
         self.fused_wk = packed['fused_wk']
         self.ws_slot = 0

@@ -23,7 +23,7 @@ for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_
 s.ft_nct = packed['ft_nct']
 planes = torch.zeros(packed['v3_ld'], 224)
 s.blend_t_hi = s.blend_t_lo = s.fblend_hi = s.fblend_lo = planes.data_ptr()
-s.blend_k0_hi = s.blend_k0_lo = s.blend16 = planes.data_ptr()
+s.blend_k0_hi = s.blend_k0_lo = s.blend16 = s.blend16a_h = s.blend16a_l = planes.data_ptr()
 s.use_umma, s.max_depth, s.num_groups, s.fused_nct, s.fused_wk = 1, packed['max_depth'], packed['num_groups'], packed['fused_nct'], 0
 L = _ext.lib()
 ws = torch.empty(L.humor_lbs_workspace_bytes(N) // 4)

@@ -35,7 +35,7 @@ def test_struct_sizes_match_header():
     import ctypes as C
     # pointers-only structs: one slot per array entry
     assert C.sizeof(_ext.HbHumorWeights) == 8 * (4 + 4 + 3 + 3 + 4 + 5 + 5 + 4 + 4 + 5 + 20 + 16) + 8 + 8 * 8 + 8 * 10
-    assert C.sizeof(_ext.HbLbsModel) == 16 + 8 * 9 + 8 * 2 + 8 + 8 * 3 + 8 * 4 + 8 + 8 * 3 + 8 + 8 * 2 + 8 * 3
+    assert C.sizeof(_ext.HbLbsModel) == 16 + 8 * 9 + 8 * 2 + 8 + 8 * 3 + 8 * 4 + 8 + 8 * 3 + 8 + 8 * 2 + 8 * 3 + 8 * 2
 
 
 def test_lbs_model_layout_matches_the_compiled_header(tmp_path):
@@ -107,7 +107,7 @@ def test_argument_errors_are_reported_before_any_launch(built_lib):
     assert L.humor_chamfer_fwd(1, 4, p, 4, p, p, None, p, p, C.byref(nl), None) == ARG        # dist1 without idx1
     assert L.humor_umma_gemm16(None, 64, p, 64, p, p, 64, 4, 4, 64, p, 1 << 30, None) == ARG
     assert L.humor_umma_gemm16(p, 64, p, 64, p, p, 64, 4, 4, 64, p, 16, None) == WS
-    assert L.humor_lbs_configure(4, 0, 0) == ARG and L.humor_lbs_configure(0, 5, 0) == ARG and L.humor_lbs_configure(0, 0, 64) == ARG
+    assert L.humor_lbs_configure(4, 0, 0) == ARG and L.humor_lbs_configure(0, 6, 0) == ARG and L.humor_lbs_configure(0, 0, 64) == ARG
     assert L.humor_lbs_configure(0, 0, 0) == 0
     assert nl.value == 0
 

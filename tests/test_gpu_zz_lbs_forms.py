@@ -42,7 +42,7 @@ def configure(skin, blend, slab=512):
     _ext.check(_ext.lib().humor_lbs_configure(skin, blend, slab), 'humor_lbs_configure')
 
 
-@pytest.mark.parametrize('skin,blend,slab', [(2, 1, 512), (1, 2, 512), (2, 2, 512), (2, 2, 256), (3, 1, 512)])   # 3 = fused (lbs_fuseg.cuh)
+@pytest.mark.parametrize('skin,blend,slab', [(2, 1, 512), (1, 2, 512), (2, 2, 512), (2, 2, 256), (3, 1, 512), (3, 5, 512)])   # skin 3 = fused (lbs_fuseg.cuh); blend 5 = fp16 hi/lo planes
 @pytest.mark.parametrize('n', [300, 1100])
 def test_forms_agree_with_default(bm, skin, blend, slab, n):
     ro, pb, be, tr = rand_pose(n, n)                     # 300: ragged row tile / frame block; 1100: 3 slabs
@@ -117,5 +117,5 @@ def test_fused_group_form_over_many_row_tiles(bm):
 
 def test_configure_rejects_bad_values():
     L = _ext.lib()
-    assert L.humor_lbs_configure(4, 0, 0) != 0 and L.humor_lbs_configure(0, 7, 0) != 0 and L.humor_lbs_configure(0, 0, 64) != 0
+    assert L.humor_lbs_configure(4, 0, 0) != 0 and L.humor_lbs_configure(0, 7, 0) != 0 and L.humor_lbs_configure(0, 6, 0) != 0 and L.humor_lbs_configure(0, 0, 64) != 0
     assert L.humor_lbs_configure(0, 0, 0) == 0

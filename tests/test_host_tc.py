@@ -175,16 +175,26 @@ def _run_fuseg(H, p, feat, bt, A, trans, grid, fast, f16=False):
     H.h_lbs_fuseg.restype = ctypes.c_longlong
     tabs = (N, V, p['num_groups'], P(p['g_start']), P(p['g_joint']), P(p['g_slot']), P(p['g_w']), P(p['ft_tab']), P(p['v_template']),
             P(A), P(trans), P(out), grid)
-    if f16:     # blend form 4: columns 0..31 three tf32 passes on planes scaled by 2^10, columns 32..223 one fp16 pass
+    if f16 == 'x3':   # blend form 5: every column as fp16 hi + unscaled lo planes (K padded to 256), three products, no tf32 k-blocks
+        fp = np.zeros((N, 256), np.float32)
+        fp[:, :K] = feat
+        bp = np.zeros((bt.shape[0], 256), np.float32)
+        bp[:, :K] = bt * np.float32(1024)
+        f_h, b_h = fp.astype(np.float16), bp.astype(np.float16)
+        f_l, b_l = (fp - f_h.astype(np.float32)).astype(np.float16), (bp - b_h.astype(np.float32)).astype(np.float16)
+        keep = [np.ascontiguousarray(x) for x in (f_h, b_h, f_l, b_l)]
+        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(fh), P(fl), K, bt.shape[0], 0, *tabs, 1, ctypes.byref(ntma), P(keep[0]), P(keep[1]), 256, 4,
+                             ctypes.c_float(2.0 ** -10), P(keep[2]), P(keep[3]))
+    elif f16:   # blend form 4: columns 0..31 three tf32 passes on planes scaled by 2^10, columns 32..223 one fp16 pass
         bh, bl = split_rn(np.ascontiguousarray(bt[:, :32] * np.float32(1024)))
         f16p = np.ascontiguousarray(feat[:, 32:].astype(np.float16))
         b16p = np.ascontiguousarray((bt[:, 32:] * np.float32(1024)).astype(np.float16))
         nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), 32, bt.shape[0], 32, *tabs, 1, ctypes.byref(ntma), P(f16p), P(b16p), 192, 3,
-                             ctypes.c_float(2.0 ** -10))
+                             ctypes.c_float(2.0 ** -10), None, None)
     else:
         bh, bl = split_rn(bt)
         nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, *tabs, fast, ctypes.byref(ntma), None, None, 0, 0,
-                             ctypes.c_float(1.0))
+                             ctypes.c_float(1.0), None, None)
     return out, nmma, ntma.value
 
 
@@ -324,3 +334,16 @@ def test_umma_gemm16_groupnorm_epilogue_and_fp16_planes(H, ks, bn, gsize):
     rec = Ch.astype(np.float32) + Cl.astype(np.float32) / np.float32(2048)
     assert np.abs(rec[:, :nc] - C[:, :nc]).max() <= 3e-7 * max(1.0, np.abs(C[:, :nc]).max())   # the planes carry the fp32 result to 2^-22
     assert np.isnan(C[:, N:]).all() and not Ch[:, N:].any()    # padding columns untouched
+
+
+def test_fuseg_kernel_fp16_three_products(H):
+    """blend form 5: all 208 feature columns as fp16 hi + unscaled lo planes, h.h + l.h + h.l per 64-wide k-block into the one
+    accumulator - the accuracy class of three TF32 passes (1e-6) from 4-byte operand elements: 8 ring entries and 48 MMAs per tile."""
+    N, grid = 140, 2
+    p, feat, bt, A, trans, ref = _fuseg_problem(N, N + grid)
+    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid, 1, f16='x3')
+    ntiles = 2 * 108
+    assert nmma == ntiles * 4 * 4 * 3
+    assert np.isfinite(out).all()
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(out - ref).max() < 4e-6 * scale, np.abs(out - ref).max()

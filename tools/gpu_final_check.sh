@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 # 2. stand-alone dense LBS forward per form (ms, GB/s, forms used, bitwise difference vs form 1)
 (timeout 120 python tools/lbs_forms_time.py --peak-gbs 6490.5 2>gpurun_out/lbs_forms_time.err) > gpurun_out/lbs_forms_time.jsonl
 # 3. step time with each candidate (the dense pass runs on a side stream under the decoder chain: persistent CTAs may delay it)
-for cfg in "2 1" "2 2" "2 3" "3 1" "3 3" "3 4"; do set -- $cfg
+for cfg in "2 1" "2 2" "2 3" "3 1" "3 3" "3 4" "3 5"; do set -- $cfg
   (timeout 80 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --lbs-skin $1 --lbs-blend $2 2>gpurun_out/bench_s$1b$2.err) > gpurun_out/bench_s$1b$2.json
 done
 # 3b. skin form 3 holds every SM it runs on (223 KB of shared memory, all of TMEM) for the whole pass: with fewer persistent

@@ -1,7 +1,7 @@
 #!/bin/bash
-# First GPU call of the next round (≈16 min of box time): put the kernel forms that round 1 verified only on the CPU
+# First GPU call of the next round (≈22 min of box time): put the kernel forms that round 1 verified only on the CPU
 # emulation onto the B200, time them, and decide the defaults from the STEP time.
-#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/gpu_final_check.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_final_check.sh'
 mkdir -p gpurun_out
 # 1. correctness of the opt-in forms (asserts humor_lbs_forms_used == requested and a last-bit difference vs form 1)
 (HB_TEST_UNVERIFIED=1 timeout 180 python -m pytest tests/test_gpu_zz_lbs_forms.py -x -q 2>&1 | tail -12) > gpurun_out/t_forms.log

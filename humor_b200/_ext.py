@@ -84,7 +84,7 @@ class HbHumorWeights(C.Structure):
                 ('pri_wt_hi', C.c_void_p * 5), ('pri_wt_lo', C.c_void_p * 5), ('dec_w_hi', C.c_void_p * 4),
                 ('dec_w_lo', C.c_void_p * 4), ('dec_wt_hi', C.c_void_p * 4), ('dec_wt_lo', C.c_void_p * 4),
                 ('use_umma', C.c_int), ('reserved', C.c_int), ('dec_w16_h', C.c_void_p * 4), ('dec_w16_l', C.c_void_p * 4),
-                ('pri_w16_h', C.c_void_p * 5), ('pri_w16_l', C.c_void_p * 5)]
+                ('pri_w16_h', C.c_void_p * 5), ('pri_w16_l', C.c_void_p * 5), ('dec_wz_hi', C.c_void_p), ('dec_wz_lo', C.c_void_p)]
 
 
 class HbFitArgs(C.Structure):

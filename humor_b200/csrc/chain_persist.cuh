@@ -1,0 +1,409 @@
+// The sequential decoder chain of the HuMoR rollout as ONE persistent kernel per direction
+// (reference loop: models/humor_model.py:870-1001 roll_out; :445-498 decode; :696-772 apply_world2local_trans).
+//
+// The launch-per-layer chain (rollout.cu: 4 GEMM + 1 glue launch per step and direction, x 59 steps) spent most of its
+// 13-30 us per launch on launch latency, prologues (barrier init, TMEM allocation), an un-overlapped leader epilogue and the
+// kernel tail.  Here 32 clusters of 4 CTAs stay resident for all S steps of one direction:
+//   * every GEMM phase is tiled 128 rows x 64 columns; the 4 CTAs of a cluster split K (as umma_gemm3_kernel<64,.,4>: TMA ->
+//     3-stage mbarrier ring -> tcgen05.mma kind::tf32, 3xTF32 split operands, K-chunks of 128 promoted from two ping-pong
+//     TMEM buffers to fp32 registers);
+//   * the split-K partials are REDUCE-SCATTERED through distributed shared memory: epilogue warp q of every CTA owns TMEM
+//     lanes 32q..32q+31 and sends those 32 rows to CTA q of the cluster, so each CTA finalises 32 rows x 64 columns with all of
+//     its 128 epilogue threads (4 threads per row, GroupNorm statistics by two shuffles) - the epilogue and the DSMEM
+//     traffic are spread over 4 SMs instead of serialised on a leader; hand-shake by remote mbarrier arrivals (no cluster
+//     barrier: the TMA and MMA warps never stall on the exchange and run ahead into the next tile);
+//   * phases are ordered by DATA-FLOW FLAGS in global memory instead of grid barriers: a finished 32x64 slab bumps its tile's
+//     counter (release), the TMA producer of a consuming tile polls exactly the counters of the k-blocks it is about to load
+//     (acquire) - weights (B operand) are requested before that wait;
+//   * the per-row glue (delta composition, canonicalisation, world transform; glue_warp.cuh) runs on the epilogue warps of
+//     all CTAs, one warp per sub-sequence, between the last and the first GEMM phase of consecutive steps;
+//   * reverse direction: the z-skip columns of the transposed GEMMs are NOT on the recurrence; every step's operand planes
+//     (d raw | d pre3 | d pre2 | d pre1) are kept and d z for all steps comes from ONE batched GEMM afterwards (rollout.cu).
+// Any number of resident clusters >= 1 is correct (tiles are strided over clusters; dependencies only point to earlier
+// phases), so the kernel also runs on the CPU emulation of tests/host with two clusters.
+#pragma once
+#include "chain_args.cuh"
+#include "glue_warp.cuh"
+#include "umma_gemm.cuh"
+
+namespace hb {
+
+constexpr int CH_STAGES = 3;
+constexpr int CH_A_TILE = UM_BM * 128;                         // bytes of one operand plane tile
+constexpr int CH_B_TILE = CH_BN * 128;
+constexpr int CH_STAGE = 2 * CH_A_TILE + 2 * CH_B_TILE;        // 48 KB: A_hi | A_lo | B_hi | B_lo
+constexpr int CH_XROWS = UM_BM / CH_CS;                        // rows a CTA finalises
+constexpr int CH_XLD = 68;                                     // floats per row of a partial slab (64 + pad: conflict-free v4 stores)
+constexpr int CH_XBUF = CH_CS * CH_XROWS * CH_XLD * 4;         // one slab per source CTA
+constexpr int CH_GLUE = 4 * GLUE_BWD_SMEM * 4;                 // row staging of the four epilogue warps
+constexpr int CH_BARS = 256;
+constexpr int CH_SMEM = CH_STAGES * CH_STAGE + CH_XBUF + CH_GLUE + CH_BARS + 1024 /*align slack*/;
+constexpr int CHAIN_THREADS = 192;
+
+struct alignas(64) ChainParams {
+  CUtensorMap map_hi[CH_NMAPS];
+  CUtensorMap map_lo[CH_NMAPS];
+  ChainGemm g[CH_NGEMM];
+  ChainGlue glue;
+  unsigned* flags;
+  int B, S, dir;
+};
+
+#ifdef HB_HOST_SHIM
+using tcemu::cluster_id_x; using tcemu::cluster_nid_x; using tcemu::mbar_arrive_remote; using tcemu::mbar_wait_cluster;
+using tcemu::flag_wait_ge; using tcemu::flag_add_release; using tcemu::fence_proxy_async; using tcemu::epi_bar_sync;
+#else
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+// arrive on an mbarrier of another CTA of the cluster (address from mapa); orders this thread's earlier DSMEM stores
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// data-flow flags in global memory: monotonic counters, bumped with release, polled with acquire (bounded: a protocol bug traps)
+__device__ __forceinline__ void flag_wait_ge(const unsigned* p, unsigned target) {
+  const long long t0 = clock64();
+  while (true) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= target) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void flag_add_release(unsigned* p, unsigned v) {
+  asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy global writes -> visible to (and ordered before) TMA reads issued after the flag hand-off
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+#endif
+
+__device__ __forceinline__ unsigned* chain_tile_flag(unsigned* flags, int gi, int mt, int nt) {
+  return flags + (gi * CH_MAX_MT + mt) * CH_MAX_NT + nt;
+}
+__device__ __forceinline__ unsigned* chain_glue_flag(unsigned* flags, int mt) { return flags + CH_NGEMM * CH_MAX_MT * CH_MAX_NT + mt; }
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1)
+chain_kernel(const __grid_constant__ ChainParams p) {
+  HB_DYN_SMEM(smem_raw);
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t xbuf = base + CH_STAGES * CH_STAGE;
+  const uint32_t glue_s = xbuf + CH_XBUF;
+  const uint32_t bars = glue_s + CH_GLUE;
+  const uint32_t full0 = bars, empty0 = bars + 8 * CH_STAGES, tfull0 = bars + 16 * CH_STAGES, tempty0 = tfull0 + 16,
+                 xfull = tempty0 + 16, xfree = xfull + 8, tptr = xfree + 8;
+  float* glue_f = reinterpret_cast<float*>(smem_raw + (glue_s - raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t krank = cluster_ctarank();
+  const int cid = (int)cluster_id_x(), ncl = (int)cluster_nid_x();
+  const int cta = blockIdx.x, nctas = gridDim.x;
+  const int B = p.B, S = p.S, dir = p.dir;
+  const int MT = (B + UM_BM - 1) / UM_BM;
+  unsigned* const flags = p.flags;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < CH_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
+    mbar_init(xfull, CH_CS * 32);          // every lane of the sending warp of every CTA (incl. this one)
+    mbar_init(xfree, CH_CS);               // one arrival per CTA of the cluster once its slab has been consumed
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tptr, (uint32_t)(2 * CH_BN));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ld_shared_u32(tptr);
+  cluster_sync_all();                      // peers' barriers are initialised before anyone arrives on them remotely
+
+  // rows of row tile mt (the last one may be ragged)
+  auto rows_of = [&](int mt) { return min(UM_BM, B - mt * UM_BM); };
+  // glue completions an A operand / a z tail written by the glue needs before step u of this direction
+  auto glue_need = [&](int mt, int u) { return (unsigned)(rows_of(mt) * (dir ? u + 1 : u)); };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int u = 0; u < S; ++u) {
+        const int t = dir ? S - 1 - u : u;
+        for (int gi = 0; gi < CH_NGEMM; ++gi) {
+          const ChainGemm& g = p.g[gi];
+          const int nkb_per = (g.nkb + CH_CS - 1) / CH_CS;
+          const int kb0 = (int)krank * nkb_per, kb1 = min(g.nkb, kb0 + nkb_per);
+          const CUtensorMap* a_hi = &p.map_hi[g.a_map]; const CUtensorMap* a_lo = &p.map_lo[g.a_map];
+          const CUtensorMap* b_hi = &p.map_hi[g.b_map]; const CUtensorMap* b_lo = &p.map_lo[g.b_map];
+          for (int tile = cid; tile < g.ntn * MT; tile += ncl) {
+            const int mt = tile / g.ntn, nt = tile % g.ntn;
+            const int m0 = mt * UM_BM, n0 = nt * CH_BN;
+            int dep_ok = -2;                                    // producer tile already seen complete (-1: the glue)
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+              const int s = it % CH_STAGES;
+              const uint32_t ph = (it / CH_STAGES) & 1;
+              const uint32_t st = base + s * CH_STAGE;
+              mbar_wait(empty0 + 8 * s, ph ^ 1);
+              mbar_expect_tx(full0 + 8 * s, CH_STAGE);
+              tma_load_2d(st + 2 * CH_A_TILE, b_hi, full0 + 8 * s, kb * UM_BK, n0);            // weights: no dependency
+              tma_load_2d(st + 2 * CH_A_TILE + CH_B_TILE, b_lo, full0 + 8 * s, kb * UM_BK, n0);
+              const int ptile = (gi > 0 && (kb >> 1) < g.dep_ntn) ? (kb >> 1) : -1;
+              if (ptile != dep_ok) {
+                if (ptile >= 0) flag_wait_ge(chain_tile_flag(flags, gi - 1, mt, ptile), (unsigned)(CH_CS * (u + 1)));
+                else { const unsigned need = glue_need(mt, u); if (need) flag_wait_ge(chain_glue_flag(flags, mt), need); }
+                fence_proxy_async();
+                dep_ok = ptile;
+              }
+              tma_load_2d(st, a_hi, full0 + 8 * s, g.a_col0 + kb * UM_BK, t * g.a_row_step + m0);
+              tma_load_2d(st + CH_A_TILE, a_lo, full0 + 8 * s, g.a_col0 + kb * UM_BK, t * g.a_row_step + m0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CH_BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+      uint32_t it = 0, ck = 0;
+      for (int u = 0; u < S; ++u)
+        for (int gi = 0; gi < CH_NGEMM; ++gi) {
+          const ChainGemm& g = p.g[gi];
+          const int nkb_per = (g.nkb + CH_CS - 1) / CH_CS;
+          const int kb0 = (int)krank * nkb_per, kb1 = min(g.nkb, kb0 + nkb_per);
+          for (int tile = cid; tile < g.ntn * MT; tile += ncl) {
+            for (int c0 = kb0; c0 < kb1; c0 += UM_CHUNK, ++ck) {
+              const int buf = ck & 1;
+              mbar_wait(tempty0 + 8 * buf, ((ck >> 1) & 1) ^ 1);           // the epilogue has drained this TMEM buffer
+              tc_fence_after();
+              const uint32_t tacc = tmem_base + buf * CH_BN;
+              const int c1 = min(kb1, c0 + UM_CHUNK);
+              for (int kb = c0; kb < c1; ++kb, ++it) {
+                const int s = it % CH_STAGES;
+                mbar_wait(full0 + 8 * s, (it / CH_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t st = base + s * CH_STAGE;
+#pragma unroll
+                for (int k = 0; k < UM_BK / 8; ++k) {
+                  const uint64_t ah = umma_desc_sw128(st + k * 32);
+                  const uint64_t al = umma_desc_sw128(st + CH_A_TILE + k * 32);
+                  const uint64_t bh = umma_desc_sw128(st + 2 * CH_A_TILE + k * 32);
+                  const uint64_t bl = umma_desc_sw128(st + 2 * CH_A_TILE + CH_B_TILE + k * 32);
+                  umma_tf32(tacc, ah, bh, idesc, (kb != c0) || (k != 0));
+                  umma_tf32(tacc, al, bh, idesc, 1);
+                  umma_tf32(tacc, ah, bl, idesc, 1);
+                }
+                umma_commit(empty0 + 8 * s);
+              }
+              umma_commit(tfull0 + 8 * buf);
+            }
+          }
+        }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ epilogue + glue warps
+    const int q = warp & 3;                                    // TMEM lane quadrant of this warp = destination CTA of its rows
+    const int ew = warp - 2;                                   // 0..3
+    const int et = threadIdx.x - 64;                           // 0..127
+    const int fr = et >> 2, cq = et & 3;                       // finalise: row inside this CTA's slab, 16-column quarter
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* gs = glue_f + ew * GLUE_BWD_SMEM;
+    uint32_t ck = 0, tl = 0;
+
+    auto run_glue = [&](int u, int t) {
+      const ChainGlue& gl = p.glue;
+      const ChainGemm& gp = p.g[CH_NGEMM - 1];                  // the phase that feeds the glue in either direction
+      for (int b = ew * nctas + cta; b < B; b += 4 * nctas) {
+        const int mt = b / UM_BM;
+        const unsigned need = (unsigned)(CH_CS * (dir ? u : u + 1));
+        if (lane == 0 && need) {
+          for (int nt = 0; nt < gp.ntn; ++nt) flag_wait_ge(chain_tile_flag(flags, CH_NGEMM - 1, mt, nt), need);
+        }
+        __syncwarp();
+        const size_t r = (size_t)t * B + b;
+        if (!dir) {
+          GlueFwdRow io;
+          io.xr = gl.xins + r * XIN_LD; io.rr = gl.raws + r * RAW_LD; io.G = gl.Gs + r * 12; io.t2j = gl.t2j + b * 4;
+          io.zt = (t + 1 < S) ? gl.z + ((size_t)b * S + (t + 1)) * 48 : nullptr;
+          io.xn = gl.xins + (r + B) * XIN_LD; io.xn_hi = gl.xin_hi + (r + B) * XIN_LD; io.xn_lo = gl.xin_lo + (r + B) * XIN_LD;
+          io.wo = gl.world + r * WORLD_LD; io.gn = gl.Gs + (r + B) * 12;
+          io.h1 = gl.h1 + (size_t)b * 1088 + 1024; io.h1_lo = gl.h1_lo + (size_t)b * 1088 + 1024;
+          io.h2 = gl.h2 + (size_t)b * 1088 + 1024; io.h2_lo = gl.h2_lo + (size_t)b * 1088 + 1024;
+          io.h3 = gl.h3 + (size_t)b * 576 + 512; io.h3_lo = gl.h3_lo + (size_t)b * 576 + 512;
+          glue_fwd_warp<true>(io, lane, gs, gs + 340, gs + 556, gs + 896);
+        } else {
+          GlueBwdRow io;
+          io.xr = gl.xins + r * XIN_LD; io.rr = gl.raws + r * RAW_LD; io.wr = gl.dworld + r * WORLD_LD; io.G = gl.Gs + r * 12;
+          io.t2j = gl.t2j + b * 4; io.have_next = u > 0;
+          io.a0 = gl.da0 + (size_t)b * XIN_LD; io.px = gl.dpx + (r + B) * 352; io.xs = gl.dxres + (size_t)b * 340;
+          io.dGn = ((t + 1) & 1 ? gl.dG1 : gl.dG0) + (size_t)b * 12; io.dG = (t & 1 ? gl.dG1 : gl.dG0) + (size_t)b * 12;
+          io.dt2j = gl.dt2j + b * 4; io.dzt = nullptr;
+          io.dh1 = io.dh1_lo = io.dh2 = io.dh2_lo = io.dh3 = io.dh3_lo = nullptr;
+          io.draw = nullptr; io.draw_hi = gl.bp_hi + r * gl.bp_ld; io.draw_lo = gl.bp_lo + r * gl.bp_ld;
+          glue_bwd_warp<true>(io, lane, gs, gs + 340, gs + 556, gs + 896, gs + 1244, gs + 1584);
+        }
+        fence_proxy_async();                                    // this lane's rows -> TMA reads of the consuming GEMM phase
+        __syncwarp();
+        if (lane == 0) flag_add_release(chain_glue_flag(flags, mt), 1u);
+      }
+    };
+
+    for (int u = 0; u < S; ++u) {
+      const int t = dir ? S - 1 - u : u;
+      if (dir) run_glue(u, t);
+      for (int gi = 0; gi < CH_NGEMM; ++gi) {
+        const ChainGemm& g = p.g[gi];
+        const int nkb_per = (g.nkb + CH_CS - 1) / CH_CS;
+        const int kb0 = (int)krank * nkb_per, kb1 = min(g.nkb, kb0 + nkb_per);
+        for (int tile = cid; tile < g.ntn * MT; tile += ncl, ++tl) {
+          const int mt = tile / g.ntn, nt = tile % g.ntn;
+          const int m0 = mt * UM_BM, n0 = nt * CH_BN;
+          float acc[CH_BN];
+#pragma unroll
+          for (int j = 0; j < CH_BN; ++j) acc[j] = 0.f;
+          for (int c0 = kb0; c0 < kb1; c0 += UM_CHUNK, ++ck) {
+            const int buf = ck & 1;
+            mbar_wait(tfull0 + 8 * buf, (ck >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < CH_BN; cc += 32) {
+              float tv[32];
+              tmem_ld32(trow + buf * CH_BN + cc, tv);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[cc + j] += tv[j];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+          }
+          // ---- reduce-scatter of the split-K partials: my quadrant's 32 rows go to CTA q
+          if (tl > 0) mbar_wait_cluster(xfree, (tl - 1) & 1);   // every CTA of the cluster has consumed its previous slab
+          {
+            const uint32_t dst = map_to_cta(xbuf + (uint32_t)(((int)krank * CH_XROWS + lane) * CH_XLD) * 4u, (uint32_t)q);
+#pragma unroll
+            for (int j = 0; j < CH_BN; j += 4) st_cluster_v4(dst + j * 4, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            mbar_arrive_remote(map_to_cta(xfull, (uint32_t)q));
+          }
+          mbar_wait_cluster(xfull, tl & 1);
+          // ---- finalise rows krank*32 .. +31 of the tile: 4 threads per row, 16 columns each
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+          for (int src = 0; src < CH_CS; ++src) {
+            const uint32_t a = xbuf + (uint32_t)((src * CH_XROWS + fr) * CH_XLD + cq * 16) * 4u;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 x = ld_shared_v4(a + j * 4);
+              v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+            }
+          }
+          const int row = m0 + (int)krank * CH_XROWS + fr;
+          const bool rok = row < B;
+          const int col = n0 + cq * 16;
+          const size_t trw = (size_t)t * B + row;               // row of the per-step tapes
+          const int gl_lanes = (g.gsize == 64) ? 3 : 1;         // xor-shuffle masks that span one GroupNorm group
+          auto group_sum = [&](float x) {
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            if (gl_lanes == 3) x += __shfl_xor_sync(0xffffffffu, x, 2);
+            return x;
+          };
+          if (g.epi == EPI_BIAS) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += (g.bias && col + j < g.N) ? g.bias[col + j] : 0.f;
+          } else if (g.epi == EPI_GN_RELU) {
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j] += g.bias[col + j]; sum += v[j]; }
+            const float inv = 1.f / (float)g.gsize;
+            const float mean = group_sum(sum) * inv;
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float d = v[j] - mean; sq += d * d; }
+            const float rs = rsqrtf(group_sum(sq) * inv + 1e-5f);
+            if (rok && (cq & gl_lanes) == 0) g.rstd[trw * 16 + col / g.gsize] = rs;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 xh;
+              float* xp = &xh.x;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                xp[e] = (v[j + e] - mean) * rs;
+                v[j + e] = fmaxf(fmaf(g.gamma[col + j + e], xp[e], g.beta[col + j + e]), 0.f);
+              }
+              if (rok) *reinterpret_cast<float4*>(g.xhat + trw * g.ldxh + col + j) = xh;
+            }
+          } else {                                              // EPI_GN_RELU_BWD: every column of these tiles is normalised
+            float xh[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 x4 = rok ? *reinterpret_cast<const float4*>(g.xhat + trw * g.ldxh + col + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              xh[j] = x4.x; xh[j + 1] = x4.y; xh[j + 2] = x4.z; xh[j + 3] = x4.w;
+            }
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float gm = g.gamma[col + j];
+              const bool on = fmaf(gm, xh[j], g.beta[col + j]) > 0.f;
+              const float uu = on ? gm * v[j] : 0.f;
+              v[j] = uu;
+              s1 += uu;
+              s2 += uu * xh[j];
+            }
+            s1 = group_sum(s1); s2 = group_sum(s2);
+            const float rs = rok ? g.rstd[trw * 16 + col / g.gsize] : 0.f;
+            const float inv = 1.f / (float)g.gsize;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = rs * (v[j] - s1 * inv - xh[j] * s2 * inv);
+          }
+          if (rok) {
+            const size_t crow = (size_t)t * g.c_row_step + row;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const int c = col + j;
+              if (c + 3 < g.N) {
+                if (g.C) *reinterpret_cast<float4*>(g.C + crow * g.ldc + g.c_col0 + c) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (g.C_hi) {
+                  const float4 h = make_float4(tf32_hi(v[j]), tf32_hi(v[j + 1]), tf32_hi(v[j + 2]), tf32_hi(v[j + 3]));
+                  *reinterpret_cast<float4*>(g.C_hi + crow * g.ldc + g.c_col0 + c) = h;
+                  *reinterpret_cast<float4*>(g.C_lo + crow * g.ldc + g.c_col0 + c) = make_float4(v[j] - h.x, v[j + 1] - h.y, v[j + 2] - h.z, v[j + 3] - h.w);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (c + e < g.N) {
+                    if (g.C) g.C[crow * g.ldc + g.c_col0 + c + e] = v[j + e];
+                    if (g.C_hi) { const float h = tf32_hi(v[j + e]); g.C_hi[crow * g.ldc + g.c_col0 + c + e] = h; g.C_lo[crow * g.ldc + g.c_col0 + c + e] = v[j + e] - h; }
+                  }
+              }
+            }
+          }
+          fence_proxy_async();                                  // the slab -> TMA reads of the next phase
+          epi_bar_sync();                                       // all 128 epilogue threads: slab read and written
+          if (et == 0) {
+#pragma unroll
+            for (uint32_t rk = 0; rk < (uint32_t)CH_CS; ++rk) mbar_arrive_remote(map_to_cta(xfree, rk));
+            flag_add_release(chain_tile_flag(flags, gi, mt, nt), 1u);
+          }
+        }
+      }
+      if (!dir) run_glue(u, t);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                        // no CTA leaves while a peer may still write to its shared memory / barriers
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)(2 * CH_BN));
+}
+
+}  // namespace hb

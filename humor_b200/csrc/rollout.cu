@@ -12,12 +12,15 @@
 #include <cstdlib>
 #include "gemm.cuh"
 #include "rollout_glue.cuh"
+#include "glue_warp.cuh"
 #include "umma_launch.cuh"
 #include "umma_split16.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
 
+constexpr int BP_LD = 224 + 512 + 1024 + 1024;   // reverse operand planes of the persistent chain: d raw | d pre3 | d pre2 | d pre1
+constexpr int BP_C3 = 224, BP_C2 = 736, BP_C1 = 1760;
 constexpr int X16_LD = 448;         // decoder input row (339 state + 48 z, XIN_LD = 416) padded to a multiple of 64 halves
 
 struct Tape {
@@ -32,6 +35,10 @@ struct Tape {
   // fp16 hi/lo operand planes of the forward pass (use_umma == 2): step inputs [S][B][448] (decoder K = 448, prior K = 384), decoder
   // transients [B][1088], [B][1088], [B][576], prior ping-pong [S*B][1024]; halves
   unsigned short *x16_h, *x16_l, *h1_16h, *h1_16l, *h2_16h, *h2_16l, *h3_16h, *h3_16l, *pa16_h, *pa16_l, *pb16_h, *pb16_l;
+  // persistent decoder chain (chain_persist.cuh): data-flow flags, the reverse pass's per-step operand planes
+  // [S*B][BP_LD] = d raw 224 | d pre3 512 | d pre2 1024 | d pre1 1024, and d z of every step [S*B][48]
+  unsigned* chain_flags;
+  float *bp_hi, *bp_lo, *dz_all;
   size_t total;
 };
 
@@ -67,6 +74,8 @@ static Tape carve(float* base, int B, int S) {
   t.h2_16h = take16((size_t)B * 1088); t.h2_16l = take16((size_t)B * 1088);
   t.h3_16h = take16((size_t)B * 576); t.h3_16l = take16((size_t)B * 576);
   t.pa16_h = take16(M * 1024); t.pa16_l = take16(M * 1024); t.pb16_h = take16(M * 1024); t.pb16_l = take16(M * 1024);
+  t.chain_flags = reinterpret_cast<unsigned*>(take(CH_FLAGS));
+  t.bp_hi = take(M * BP_LD); t.bp_lo = take(M * BP_LD); t.dz_all = take(M * 48);
   t.total = off;
   return t;
 }
@@ -131,13 +140,6 @@ __global__ void rollout_init_kernel(int B, int S, const float* __restrict__ init
 // ------------------------------------------------------------------------------------------------
 constexpr int GLUE_WARPS = 4;
 
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 __global__ void __launch_bounds__(GLUE_WARPS * 32)
 glue_fwd_kernel(int B, int S, int t, const float* __restrict__ xin, const float* __restrict__ raw,
                 const float* __restrict__ G, const float* __restrict__ t2jg, const float* __restrict__ z,
@@ -149,90 +151,16 @@ glue_fwd_kernel(int B, int S, int t, const float* __restrict__ xin, const float*
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * GLUE_WARPS + wid;
   if (b >= B) return;
-  float* sx = s_x[wid]; float* sr = s_r[wid]; float* sn = s_n[wid]; float* sw = s_w[wid];
-  const float* xr = xin + (size_t)b * XIN_LD;
-  const float* rr = raw + (size_t)b * RAW_LD;
-  for (int i = lane; i < STATE_D; i += 32) sx[i] = xr[i];
-  for (int i = lane; i < RAW_D; i += 32) sr[i] = rr[i];
-  __syncwarp();
-  float Gr[9], Gt[3], t2j[3], tr[3], R0[9], D[9], Ra[9];
-#pragma unroll
-  for (int e = 0; e < 9; ++e) Gr[e] = G[(size_t)b * 12 + e];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { Gt[i] = G[(size_t)b * 12 + 9 + i]; t2j[i] = t2jg[b * 4 + i]; tr[i] = sx[i] + sr[i]; }
-  rodrigues_fwd(sr + 6, D);
-  mat3_mul(D, sx + 6, R0);
-  w2a_fwd(R0, Ra);
-  const float ta[3] = {-tr[0], -tr[1], 0.f};
-  if (lane < NJ) {
-    const int k = lane;
-    float p[3], v[3], a[3], o[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      p[i] = sx[207 + 3 * k + i] + sr[75 + 3 * k + i];
-      v[i] = sx[273 + 3 * k + i] + sr[141 + 3 * k + i];
-      a[i] = p[i] + ta[i] + t2j[i];
-    }
-    mat3_vec(Ra, a, o);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { sn[207 + 3 * k + i] = o[i] - t2j[i]; a[i] = p[i] + t2j[i]; }
-    mat3_tvec(Gr, a, o);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) sw[207 + 3 * k + i] = o[i] - t2j[i] - Gt[i];
-    mat3_vec(Ra, v, sn + 273 + 3 * k);
-    mat3_tvec(Gr, v, sw + 273 + 3 * k);
-    if (k == 0) {
-      mat3_mul(Ra, R0, sn + 6);
-      mat3_mul_tn(Gr, R0, sw + 6);
-    } else {
-      const int j = k - 1;
-      float Dj[9], Rj[9];
-      rodrigues_fwd(sr + 12 + 3 * j, Dj);
-      mat3_mul(Dj, sx + 18 + 9 * j, Rj);
-#pragma unroll
-      for (int e = 0; e < 9; ++e) { sn[18 + 9 * j + e] = Rj[e]; sw[18 + 9 * j + e] = Rj[e]; }
-    }
-  } else if (lane == 22) {
-    float u[3] = {tr[0] + ta[0], tr[1] + ta[1], tr[2] + ta[2]};
-    mat3_vec(Ra, u, sn + 0);
-    float wt[3];
-    mat3_tvec(Gr, tr, wt);
-    float* gn = Gnext + (size_t)b * 12;
-    mat3_mul(Gr, Ra, gn);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { wt[i] -= Gt[i]; sw[i] = wt[i]; }
-    gn[9] = -wt[0]; gn[10] = -wt[1]; gn[11] = 0.f;
-  } else if (lane == 23) {
-    float tv[3] = {sx[3] + sr[3], sx[4] + sr[4], sx[5] + sr[5]};
-    mat3_vec(Ra, tv, sn + 3);
-    mat3_tvec(Gr, tv, sw + 3);
-  } else if (lane == 24) {
-    float rv[3] = {sx[15] + sr[9], sx[16] + sr[10], sx[17] + sr[11]};
-    mat3_vec(Ra, rv, sn + 15);
-    mat3_tvec(Gr, rv, sw + 15);
-  } else if (lane == 25) {
-#pragma unroll
-    for (int c = 0; c < 9; ++c) sw[339 + c] = sr[207 + c];
-  }
-  __syncwarp();
-  float* xn = xnext + (size_t)b * XIN_LD;
-  float* wo = world + (size_t)b * WORLD_LD;
-  for (int i = lane; i < STATE_D; i += 32) {
-    xn[i] = sn[i];
-    if (xnext_lo) put_split(xnext_hi, xnext_lo, (size_t)b * XIN_LD + i, sn[i]);
-  }
-  for (int i = lane; i < WORLD_LD; i += 32) wo[i] = sw[i];
-  if (t + 1 < S) {
-    const float* zt = z + ((size_t)b * S + (t + 1)) * 48;
-    for (int i = lane; i < 48; i += 32) {
-      const float v = zt[i];
-      xn[STATE_D + i] = v;
-      if (xnext_lo) put_split(xnext_hi, xnext_lo, (size_t)b * XIN_LD + STATE_D + i, v);
-      put_split(h1, h1_lo, (size_t)b * 1088 + 1024 + i, v);
-      put_split(h2, h2_lo, (size_t)b * 1088 + 1024 + i, v);
-      put_split(h3, h3_lo, (size_t)b * 576 + 512 + i, v);
-    }
-  }
+  GlueFwdRow io;
+  io.xr = xin + (size_t)b * XIN_LD; io.rr = raw + (size_t)b * RAW_LD; io.G = G + (size_t)b * 12; io.t2j = t2jg + b * 4;
+  io.zt = (t + 1 < S) ? z + ((size_t)b * S + (t + 1)) * 48 : nullptr;
+  io.xn = xnext + (size_t)b * XIN_LD;
+  io.xn_hi = xnext_lo ? xnext_hi + (size_t)b * XIN_LD : nullptr; io.xn_lo = xnext_lo ? xnext_lo + (size_t)b * XIN_LD : nullptr;
+  io.wo = world + (size_t)b * WORLD_LD; io.gn = Gnext + (size_t)b * 12;
+  io.h1 = h1 + (size_t)b * 1088 + 1024; io.h2 = h2 + (size_t)b * 1088 + 1024; io.h3 = h3 + (size_t)b * 576 + 512;
+  io.h1_lo = h1_lo ? h1_lo + (size_t)b * 1088 + 1024 : nullptr; io.h2_lo = h2_lo ? h2_lo + (size_t)b * 1088 + 1024 : nullptr;
+  io.h3_lo = h3_lo ? h3_lo + (size_t)b * 576 + 512 : nullptr;
+  glue_fwd_warp<false>(io, lane, s_x[wid], s_r[wid], s_n[wid], s_w[wid]);
 }
 
 // reverse of one step.  have_next: grads from step t+1 exist (da0/dxres/dpx_next) and dz[:,t+1] is emitted.
@@ -250,166 +178,19 @@ glue_bwd_kernel(int B, int S, int t, int have_next, const float* __restrict__ xi
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * GLUE_WARPS + wid;
   if (b >= B) return;
-  float* sx = s_x[wid]; float* sr = s_r[wid]; float* dn = s_dn[wid]; float* dw = s_dw[wid];
-  float* dx = s_dx[wid]; float* dr = s_dr[wid];
-  {
-    const float* xr = xin + (size_t)b * XIN_LD;
-    const float* rr = raw + (size_t)b * RAW_LD;
-    const float* wr = dworld + (size_t)b * WORLD_LD;
-    for (int i = lane; i < STATE_D; i += 32) sx[i] = xr[i];
-    for (int i = lane; i < RAW_D; i += 32) sr[i] = rr[i];
-    for (int i = lane; i < WORLD_LD; i += 32) dw[i] = wr[i];
-    if (have_next) {
-      const float* a0 = da0 + (size_t)b * XIN_LD;
-      const float* px = dpx_next + (size_t)b * 352;
-      const float* xs = dxres + (size_t)b * 340;
-      for (int i = lane; i < STATE_D; i += 32) dn[i] = xs[i] + a0[i] + px[i];
-      float* dzt = dz + ((size_t)b * S + (t + 1)) * 48;
-      for (int i = lane; i < 48; i += 32)
-        dzt[i] = a0[STATE_D + i] + get_split(dh1, dh1_lo, (size_t)b * 1088 + 1024 + i) +
-                 get_split(dh2, dh2_lo, (size_t)b * 1088 + 1024 + i) + get_split(dh3, dh3_lo, (size_t)b * 576 + 512 + i);
-    } else {
-      for (int i = lane; i < STATE_D; i += 32) dn[i] = 0.f;
-    }
-  }
-  __syncwarp();
-  float Gr[9], Gt[3], t2j[3], tr[3], R0[9], D[9], Ra[9], dGn[12];
-#pragma unroll
-  for (int e = 0; e < 9; ++e) Gr[e] = G[(size_t)b * 12 + e];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { Gt[i] = G[(size_t)b * 12 + 9 + i]; t2j[i] = t2jg[b * 4 + i]; tr[i] = sx[i] + sr[i]; }
-#pragma unroll
-  for (int i = 0; i < 12; ++i) dGn[i] = have_next ? dGn_g[(size_t)b * 12 + i] : 0.f;
-  rodrigues_fwd(sr + 6, D);
-  mat3_mul(D, sx + 6, R0);
-  w2a_fwd(R0, Ra);
-  const float ta[3] = {-tr[0], -tr[1], 0.f};
-  // per-lane partial sums of the root-level adjoints
-  float dRa[9], dGr[9], dGt[3] = {0.f, 0.f, 0.f}, dta[3] = {0.f, 0.f, 0.f}, d2j[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int e = 0; e < 9; ++e) { dRa[e] = 0.f; dGr[e] = 0.f; }
-  float dR0[9], dtr[3] = {0.f, 0.f, 0.f};            // lane 25 / lane 22 private
-#pragma unroll
-  for (int e = 0; e < 9; ++e) dR0[e] = 0.f;
-
-  if (lane < NJ) {
-    const int k = lane;
-    float p[3], v[3], a[3], dp[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f}, du[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      p[i] = sx[207 + 3 * k + i] + sr[75 + 3 * k + i];
-      v[i] = sx[273 + 3 * k + i] + sr[141 + 3 * k + i];
-      a[i] = p[i] + ta[i] + t2j[i];
-    }
-    const float* dnj = dn + 207 + 3 * k;
-    const float* dwj = dw + 207 + 3 * k;
-    mv_bwd(Ra, a, dnj, dRa, du);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { dp[i] += du[i]; dta[i] += du[i]; d2j[i] += du[i] - dnj[i]; du[i] = 0.f; a[i] = p[i] + t2j[i]; }
-    mtv_bwd(Gr, a, dwj, dGr, du);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { dp[i] += du[i]; d2j[i] += du[i] - dwj[i]; dGt[i] -= dwj[i]; }
-    mv_bwd(Ra, v, dn + 273 + 3 * k, dRa, dv);
-    mtv_bwd(Gr, v, dw + 273 + 3 * k, dGr, dv);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      dx[207 + 3 * k + i] = dp[i]; dr[75 + 3 * k + i] = dp[i];
-      dx[273 + 3 * k + i] = dv[i]; dr[141 + 3 * k + i] = dv[i];
-    }
-    if (k > 0) {
-      const int j = k - 1;
-      float Dj[9], dRj[9], dD[9], dRin[9];
-      rodrigues_fwd(sr + 12 + 3 * j, Dj);
-#pragma unroll
-      for (int e = 0; e < 9; ++e) { dRj[e] = dn[18 + 9 * j + e] + dw[18 + 9 * j + e]; dD[e] = 0.f; dRin[e] = 0.f; }
-      mat3_mul_bwd(Dj, sx + 18 + 9 * j, dRj, dD, dRin);
-      float daa[3] = {0.f, 0.f, 0.f};
-      rodrigues_bwd(sr + 12 + 3 * j, dD, daa);
-#pragma unroll
-      for (int e = 0; e < 9; ++e) dx[18 + 9 * j + e] = dRin[e];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) dr[12 + 3 * j + i] = daa[i];
-    }
-  } else if (lane == 22) {
-    float dwt[3] = {dw[0] - dGn[9], dw[1] - dGn[10], dw[2]};
-    mtv_bwd(Gr, tr, dwt, dGr, dtr);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) dGt[i] -= dwt[i];
-    float u[3] = {tr[0] + ta[0], tr[1] + ta[1], tr[2] + ta[2]};
-    float du[3] = {0.f, 0.f, 0.f};
-    mv_bwd(Ra, u, dn + 0, dRa, du);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { dtr[i] += du[i]; dta[i] += du[i]; }
-  } else if (lane == 23) {
-    float tv[3] = {sx[3] + sr[3], sx[4] + sr[4], sx[5] + sr[5]}, dtv[3] = {0.f, 0.f, 0.f};
-    mv_bwd(Ra, tv, dn + 3, dRa, dtv);
-    mtv_bwd(Gr, tv, dw + 3, dGr, dtv);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { dx[3 + i] = dtv[i]; dr[3 + i] = dtv[i]; }
-  } else if (lane == 24) {
-    float rv[3] = {sx[15] + sr[9], sx[16] + sr[10], sx[17] + sr[11]}, drv[3] = {0.f, 0.f, 0.f};
-    mv_bwd(Ra, rv, dn + 15, dRa, drv);
-    mtv_bwd(Gr, rv, dw + 15, dGr, drv);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { dx[15 + i] = drv[i]; dr[9 + i] = drv[i]; }
-  } else if (lane == 25) {
-    mat3_mul_bwd(Gr, Ra, dGn, dGr, dRa);                 // Gnext = Gr Ra
-    const float* dW = dw + 6;                            // world.R0 = Gr^T R0
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        float a = 0.f, bb = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { a += R0[i * 3 + k] * dW[j * 3 + k]; bb += Gr[i * 3 + k] * dW[k * 3 + j]; }
-        dGr[i * 3 + j] += a;
-        dR0[i * 3 + j] += bb;
-      }
-    mat3_mul_bwd(Ra, R0, dn + 6, dRa, dR0);              // next.R0 = Ra R0
-#pragma unroll
-    for (int c = 0; c < 9; ++c) dr[207 + c] = dw[339 + c];
-    for (int c = RAW_D; c < RAW_LD; ++c) dr[c] = 0.f;
-  }
-  // ---- warp totals (every lane receives them)
-#pragma unroll
-  for (int e = 0; e < 9; ++e) { dRa[e] = warp_sum(dRa[e]); dGr[e] = warp_sum(dGr[e]); }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { dGt[i] = warp_sum(dGt[i]); dta[i] = warp_sum(dta[i]); d2j[i] = warp_sum(d2j[i]); }
-  if (lane == 25) {
-    w2a_bwd(R0, dRa, dR0);                               // Ra = w2a(R0)
-    float dD[9], dRin[9];
-#pragma unroll
-    for (int e = 0; e < 9; ++e) { dD[e] = 0.f; dRin[e] = 0.f; }
-    mat3_mul_bwd(D, sx + 6, dR0, dD, dRin);              // R0 = D xin.R0
-    float daa[3] = {0.f, 0.f, 0.f};
-    rodrigues_bwd(sr + 6, dD, daa);
-#pragma unroll
-    for (int e = 0; e < 9; ++e) dx[6 + e] = dRin[e];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) dr[6 + i] = daa[i];
-  } else if (lane == 22) {
-    dtr[0] -= dta[0];                                    // ta = (-tr.x, -tr.y, 0)
-    dtr[1] -= dta[1];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { dx[i] = dtr[i]; dr[i] = dtr[i]; }
-  } else if (lane == 0) {
-    float* g = dG + (size_t)b * 12;
-#pragma unroll
-    for (int e = 0; e < 9; ++e) g[e] = dGr[e];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      g[9 + i] = dGt[i];
-      dt2j[b * 4 + i] = (have_next ? dt2j[b * 4 + i] : 0.f) + d2j[i];
-    }
-  }
-  __syncwarp();
-  float* xo = dxres + (size_t)b * 340;
-  float* ro = draw + (size_t)b * RAW_LD;
-  for (int i = lane; i < STATE_D; i += 32) xo[i] = dx[i];
-  for (int i = lane; i < RAW_LD; i += 32) {
-    ro[i] = dr[i];
-    if (draw_lo) put_split(draw_hi, draw_lo, (size_t)b * RAW_LD + i, dr[i]);
-  }
+  GlueBwdRow io;
+  io.xr = xin + (size_t)b * XIN_LD; io.rr = raw + (size_t)b * RAW_LD; io.wr = dworld + (size_t)b * WORLD_LD;
+  io.G = G + (size_t)b * 12; io.t2j = t2jg + b * 4; io.have_next = have_next;
+  io.a0 = da0 + (size_t)b * XIN_LD; io.px = dpx_next + (size_t)b * 352; io.xs = dxres + (size_t)b * 340;
+  io.dGn = dGn_g + (size_t)b * 12; io.dG = dG + (size_t)b * 12; io.dt2j = dt2j + b * 4;
+  io.dzt = dz + ((size_t)b * S + (t + 1)) * 48;
+  io.dh1 = dh1 + (size_t)b * 1088 + 1024; io.dh2 = dh2 + (size_t)b * 1088 + 1024; io.dh3 = dh3 + (size_t)b * 576 + 512;
+  io.dh1_lo = dh1_lo ? dh1_lo + (size_t)b * 1088 + 1024 : nullptr; io.dh2_lo = dh2_lo ? dh2_lo + (size_t)b * 1088 + 1024 : nullptr;
+  io.dh3_lo = dh3_lo ? dh3_lo + (size_t)b * 576 + 512 : nullptr;
+  io.draw = draw + (size_t)b * RAW_LD;
+  io.draw_hi = draw_lo ? draw_hi + (size_t)b * RAW_LD : nullptr; io.draw_lo = draw_lo ? draw_lo + (size_t)b * RAW_LD : nullptr;
+  (void)dnsum;
+  glue_bwd_warp<false>(io, lane, s_x[wid], s_r[wid], s_dn[wid], s_dw[wid], s_dx[wid], s_dr[wid]);
 }
 
 __global__ void rollout_bwd_final_kernel(int B, int S, const float* __restrict__ dxres, const float* __restrict__ da0,
@@ -426,6 +207,22 @@ __global__ void rollout_bwd_final_kernel(int B, int S, const float* __restrict__
   for (int i = threadIdx.x; i < 48; i += blockDim.x)
     dz[((size_t)b * S) * 48 + i] = da0[(size_t)b * XIN_LD + STATE_D + i] + get_split(dh1, dh1_lo, (size_t)b * 1088 + 1024 + i) +
                                    get_split(dh2, dh2_lo, (size_t)b * 1088 + 1024 + i) + get_split(dh3, dh3_lo, (size_t)b * 576 + 512 + i);
+}
+
+// persistent chain, after the last reverse step: d init, and d z [B][S][48] from the batched tail GEMM's [S*B][48]
+__global__ void chain_bwd_final_kernel(int B, int S, const float* __restrict__ dxres, const float* __restrict__ da0,
+                                       const float* __restrict__ dpx0, const float* __restrict__ dt2j, const float* __restrict__ dz_all,
+                                       float* dinit, float* dz) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < STATE_D; i += blockDim.x) {
+    float v = dxres[(size_t)b * 340 + i] + da0[(size_t)b * XIN_LD + i] + dpx0[(size_t)b * 352 + i];
+    if (i == 207 || i == 208) v -= dt2j[b * 4 + (i - 207)];     // t2j = -(joints0.x, joints0.y, 0)
+    dinit[(size_t)b * STATE_D + i] = v;
+  }
+  for (int i = threadIdx.x; i < S * 48; i += blockDim.x) {
+    const int t = i / 48, j = i - t * 48;
+    dz[((size_t)b * S + t) * 48 + j] = dz_all[((size_t)t * B + b) * 48 + j];
+  }
 }
 
 // every GEMM of the rollout multiplies activations by a (frozen) weight matrix: B never depends on the previous kernel
@@ -447,6 +244,77 @@ static GemmEpi epi_bias(const float* bias) {
 
 #ifndef HB_HOST_SHIM   // host side of the C-ABI (launch syntax): device builds only
 using namespace hb;
+
+// ---- persistent decoder chain (chain_persist.cuh): default for use_umma == 1; HB_CHAIN=0 keeps the launch-per-layer chain
+static bool chain_ok(const HbHumorWeights* w, int B) {
+  const char* e = getenv("HB_CHAIN");            // read per call: tests switch between the two chains inside one process
+  const int on = e ? atoi(e) : 1;
+  return on && w->use_umma == 1 && umma_available() && w->dec_wz_hi && w->dec_wz_lo && B <= CH_MAX_MT * 128;
+}
+static ChainGemm chain_gemm(int a_map, int a_col0, int a_row_step, int nkb, int b_map, int ntn, int N, int epi, int gsize, int dep_ntn) {
+  ChainGemm g = {};
+  g.a_map = a_map; g.b_map = b_map; g.a_col0 = a_col0; g.a_row_step = a_row_step; g.nkb = nkb; g.ntn = ntn; g.N = N; g.epi = epi;
+  g.gsize = gsize; g.dep_ntn = dep_ntn;
+  return g;
+}
+static ChainPlane chain_plane(const float* hi, const float* lo, int rows, int cols, int ld, int box_rows) {
+  ChainPlane p; p.hi = hi; p.lo = lo; p.rows = rows; p.cols = cols; p.ld = ld; p.box_rows = box_rows; return p;
+}
+static void chain_glue_common(ChainGlue& gl, const Tape& tp, const float* z_seq, float* world) {
+  gl.z = z_seq; gl.xins = tp.xins; gl.xin_hi = tp.xin_hi; gl.xin_lo = tp.xin_lo; gl.raws = tp.raws; gl.Gs = tp.Gs; gl.t2j = tp.t2j;
+  gl.world = world; gl.h1 = tp.h1; gl.h1_lo = tp.h1_lo; gl.h2 = tp.h2; gl.h2_lo = tp.h2_lo; gl.h3 = tp.h3; gl.h3_lo = tp.h3_lo;
+}
+static cudaError_t chain_forward(const HbHumorWeights* w, const Tape& tp, int B, int S, const float* z_seq, float* world, cudaStream_t st) {
+  ChainLaunch a = {};
+  a.B = B; a.S = S; a.dir = 0; a.flags = tp.chain_flags;
+  a.planes[0] = chain_plane(tp.xin_hi, tp.xin_lo, (S + 1) * B, XIN_LD, XIN_LD, 128);
+  a.planes[1] = chain_plane(tp.h1, tp.h1_lo, B, 1088, 1088, 128);
+  a.planes[2] = chain_plane(tp.h2, tp.h2_lo, B, 1088, 1088, 128);
+  a.planes[3] = chain_plane(tp.h3, tp.h3_lo, B, 576, 576, 128);
+  a.planes[4] = chain_plane(w->dec_w_hi[0], w->dec_w_lo[0], 1024, 416, 416, CH_BN);
+  a.planes[5] = chain_plane(w->dec_w_hi[1], w->dec_w_lo[1], 1024, 1088, 1088, CH_BN);
+  a.planes[6] = chain_plane(w->dec_w_hi[2], w->dec_w_lo[2], 512, 1088, 1088, CH_BN);
+  a.planes[7] = chain_plane(w->dec_w_hi[3], w->dec_w_lo[3], 216, 576, 576, CH_BN);
+  ChainGemm& g0 = a.g[0]; ChainGemm& g1 = a.g[1]; ChainGemm& g2 = a.g[2]; ChainGemm& g3 = a.g[3];
+  g0 = chain_gemm(0, 0, B, 13, 4, 16, 1024, EPI_GN_RELU, 64, 0);
+  g0.bias = w->dec_b[0]; g0.gamma = w->dec_g[0]; g0.beta = w->dec_be[0]; g0.xhat = tp.dxh1; g0.ldxh = 1024; g0.rstd = tp.drs1;
+  g0.C_hi = tp.h1; g0.C_lo = tp.h1_lo; g0.ldc = 1088;
+  g1 = chain_gemm(1, 0, 0, 34, 5, 16, 1024, EPI_GN_RELU, 64, 16);
+  g1.bias = w->dec_b[1]; g1.gamma = w->dec_g[1]; g1.beta = w->dec_be[1]; g1.xhat = tp.dxh2; g1.ldxh = 1024; g1.rstd = tp.drs2;
+  g1.C_hi = tp.h2; g1.C_lo = tp.h2_lo; g1.ldc = 1088;
+  g2 = chain_gemm(2, 0, 0, 34, 6, 8, 512, EPI_GN_RELU, 32, 16);
+  g2.bias = w->dec_b[2]; g2.gamma = w->dec_g[2]; g2.beta = w->dec_be[2]; g2.xhat = tp.dxh3; g2.ldxh = 512; g2.rstd = tp.drs3;
+  g2.C_hi = tp.h3; g2.C_lo = tp.h3_lo; g2.ldc = 576;
+  g3 = chain_gemm(3, 0, 0, 18, 7, 4, 216, EPI_BIAS, 64, 8);
+  g3.bias = w->dec_b[3]; g3.C = tp.raws; g3.ldc = RAW_LD; g3.c_row_step = B;
+  chain_glue_common(a.glue, tp, z_seq, world);
+  return launch_chain(a, st);
+}
+static cudaError_t chain_backward(const HbHumorWeights* w, const Tape& tp, int B, int S, const float* d_world, cudaStream_t st) {
+  ChainLaunch a = {};
+  a.B = B; a.S = S; a.dir = 1; a.flags = tp.chain_flags;
+  a.planes[0] = chain_plane(tp.bp_hi, tp.bp_lo, S * B, BP_LD, BP_LD, 128);
+  a.planes[1] = chain_plane(w->dec_wt_hi[3], w->dec_wt_lo[3], 576, 224, 224, CH_BN);
+  a.planes[2] = chain_plane(w->dec_wt_hi[2], w->dec_wt_lo[2], 1088, 512, 512, CH_BN);
+  a.planes[3] = chain_plane(w->dec_wt_hi[1], w->dec_wt_lo[1], 1088, 1024, 1024, CH_BN);
+  a.planes[4] = chain_plane(w->dec_wt_hi[0], w->dec_wt_lo[0], 416, 1024, 1024, CH_BN);
+  ChainGemm& g0 = a.g[0]; ChainGemm& g1 = a.g[1]; ChainGemm& g2 = a.g[2]; ChainGemm& g3 = a.g[3];
+  g0 = chain_gemm(0, 0, B, 7, 1, 8, 512, EPI_GN_RELU_BWD, 32, 0);
+  g0.gamma = w->dec_g[2]; g0.beta = w->dec_be[2]; g0.xhat = tp.dxh3; g0.ldxh = 512; g0.rstd = tp.drs3;
+  g0.C_hi = tp.bp_hi; g0.C_lo = tp.bp_lo; g0.ldc = BP_LD; g0.c_col0 = BP_C3; g0.c_row_step = B;
+  g1 = chain_gemm(0, BP_C3, B, 16, 2, 16, 1024, EPI_GN_RELU_BWD, 64, 8);
+  g1.gamma = w->dec_g[1]; g1.beta = w->dec_be[1]; g1.xhat = tp.dxh2; g1.ldxh = 1024; g1.rstd = tp.drs2;
+  g1.C_hi = tp.bp_hi; g1.C_lo = tp.bp_lo; g1.ldc = BP_LD; g1.c_col0 = BP_C2; g1.c_row_step = B;
+  g2 = chain_gemm(0, BP_C2, B, 32, 3, 16, 1024, EPI_GN_RELU_BWD, 64, 16);
+  g2.gamma = w->dec_g[0]; g2.beta = w->dec_be[0]; g2.xhat = tp.dxh1; g2.ldxh = 1024; g2.rstd = tp.drs1;
+  g2.C_hi = tp.bp_hi; g2.C_lo = tp.bp_lo; g2.ldc = BP_LD; g2.c_col0 = BP_C1; g2.c_row_step = B;
+  g3 = chain_gemm(0, BP_C1, B, 32, 4, 6, STATE_D, EPI_BIAS, 64, 16);
+  g3.C = tp.da0; g3.ldc = XIN_LD;
+  chain_glue_common(a.glue, tp, nullptr, nullptr);
+  a.glue.dworld = d_world; a.glue.da0 = tp.da0; a.glue.dpx = tp.dpx; a.glue.dxres = tp.dxres; a.glue.dG0 = tp.dG0; a.glue.dG1 = tp.dG1;
+  a.glue.dt2j = tp.dt2j; a.glue.bp_hi = tp.bp_hi; a.glue.bp_lo = tp.bp_lo; a.glue.bp_ld = BP_LD;
+  return launch_chain(a, st);
+}
 
 extern "C" size_t humor_rollout_workspace_bytes(int B, int S) { return carve(nullptr, B, S).total * sizeof(float); }
 
@@ -476,7 +344,12 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
   if (f16)          // pads (input columns 416..447, hidden columns past the 48 z) must read as zero
     HB_CUDA(cudaMemsetAsync(tp.x16_h, 0, (size_t)((char*)(tp.h3_16l + (size_t)B * 576) - (char*)tp.x16_h), st));
   const int gb = cdiv(B, GLUE_WARPS);
-  for (int t = 0; t < S; ++t) {
+  const bool persistent = tc && !f16 && chain_ok(w, B);
+  if (persistent) {                 // all S steps of the decoder chain in ONE launch
+    HB_CUDA(chain_forward(w, tp, B, S, z_seq, world, st));
+    nl += 1;
+  }
+  for (int t = 0; t < S && !persistent; ++t) {
     const size_t r = (size_t)t * B;
     float* xin = tp.xins + r * XIN_LD;
     if (f16) {
@@ -630,6 +503,17 @@ extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* w
   }
   const int gb = cdiv(B, GLUE_WARPS);
   float* dGbuf[2] = {tp.dG0, tp.dG1};
+  if (tc && w->use_umma == 1 && chain_ok(w, B)) {
+    // all S reverse steps in ONE launch, then d z of every step as one batched GEMM over the operand planes it left
+    HB_CUDA(chain_backward(w, tp, B, S, d_world, st));
+    HB_CUDA(launch_umma_gemm3_bn(tp.bp_hi, tp.bp_lo, BP_LD, w->dec_wz_hi, w->dec_wz_lo, BP_LD, M, 48, BP_LD, tp.dz_all, nullptr, nullptr, 48,
+                                 EPI_BIAS, epi_bias(nullptr), 64, st));
+    chain_bwd_final_kernel<<<B, 128, 0, st>>>(B, S, tp.dxres, tp.da0, tp.dpx, tp.dt2j, tp.dz_all, d_init, d_z);
+    HB_LAUNCH_CHECK();
+    nl += 3;
+    if (launches) *launches = nl;
+    return HB_OK;
+  }
   for (int t = S - 1; t >= 0; --t) {
     const size_t r = (size_t)t * B;
     const int have_next = (t + 1 < S);

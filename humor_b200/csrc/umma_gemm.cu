@@ -10,6 +10,7 @@
 #include "lbs_blend.cuh"
 #include "lbs_fuseg.cuh"
 #include "umma_gemm16.cuh"
+#include "chain_persist.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
@@ -290,6 +291,59 @@ cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const 
   }
 #undef HB_U16_CASE
   return cudaErrorInvalidValue;
+}
+
+// persistent decoder chain (chain_persist.cuh): one launch per direction.  Clusters resident at once are bounded by what the
+// device can co-schedule (cudaOccupancyMaxActiveClusters): the kernel's data-flow flags need every launched cluster running.
+static int g_chain_clusters = 0;        // 0: not yet queried
+int chain_max_clusters() { return g_chain_clusters; }
+cudaError_t launch_chain(const ChainLaunch& a, cudaStream_t st) {
+  if (!load_encode()) return cudaErrorNotSupported;
+  if (a.B <= 0 || a.B > CH_MAX_MT * UM_BM || a.S <= 0 || !a.flags) return cudaErrorInvalidValue;
+  if (!g_chain_clusters) {              // once per process, on the first (un-captured) call
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(32 * CH_CS); q.blockDim = dim3(CHAIN_THREADS); q.dynamicSmemBytes = CH_SMEM;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = CH_CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, chain_kernel, &q);
+    if (e != cudaSuccess) return e;
+    const char* w = getenv("HB_CHAIN_CLUSTERS");
+    int want = w ? atoi(w) : 32;
+    if (want < 1) want = 1;
+    g_chain_clusters = n < want ? n : want;
+    if (g_chain_clusters < 1) return cudaErrorInvalidConfiguration;
+  }
+  static ChainParams p;                  // 64-byte aligned (CUtensorMap); filled per launch, copied by the launch itself
+  for (int i = 0; i < CH_NMAPS; ++i) {
+    const ChainPlane& pl = a.planes[i];
+    if (!pl.hi) { if (i == 0) return cudaErrorInvalidValue; p.map_hi[i] = p.map_hi[0]; p.map_lo[i] = p.map_lo[0]; continue; }
+    if (pl.cols % UM_BK || pl.ld % 4 || !pl.lo) return cudaErrorInvalidValue;
+    if (!make_map(&p.map_hi[i], pl.hi, pl.rows, pl.cols, pl.ld, pl.box_rows) ||
+        !make_map(&p.map_lo[i], pl.lo, pl.rows, pl.cols, pl.ld, pl.box_rows))
+      return cudaErrorInvalidValue;
+  }
+  for (int i = 0; i < CH_NGEMM; ++i) {
+    p.g[i] = a.g[i];
+    if (a.g[i].ntn < 1 || a.g[i].ntn > CH_MAX_NT || a.g[i].nkb < 1 || (a.g[i].gsize != 64 && a.g[i].gsize != 32)) return cudaErrorInvalidValue;
+  }
+  p.glue = a.glue; p.flags = a.flags; p.B = a.B; p.S = a.S; p.dir = a.dir;
+  cudaError_t e = cudaMemsetAsync(a.flags, 0, CH_FLAGS * sizeof(unsigned), st);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g_chain_clusters * CH_CS);
+  cfg.blockDim = dim3(CHAIN_THREADS);
+  cfg.dynamicSmemBytes = CH_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CH_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, chain_kernel, p);
 }
 
 cudaError_t launch_split16(const float* x, void* h, void* l, size_t n, cudaStream_t st) {

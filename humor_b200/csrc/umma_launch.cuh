@@ -1,5 +1,6 @@
 #pragma once
 #include "gemm.cuh"
+#include "chain_args.cuh"
 namespace hb {
 // C[M,N] = (A_hi+A_lo)[M,K] * (B_hi+B_lo)[N,K]^T on tcgen05 (3xTF32).  Operand planes are fp32 arrays with the
 // given leading dimensions (multiples of 4); K a multiple of 32.  Outputs: C (exact value) and/or the hi/lo planes.
@@ -13,6 +14,9 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
 // hi = top 11 mantissa bits of x, lo = x - hi (exact); n elements
 cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 bool umma_available();
+// persistent decoder chain (chain_persist.cuh): S steps of one direction in one launch; zeroes a.flags on the stream first
+cudaError_t launch_chain(const ChainLaunch& a, cudaStream_t st);
+int chain_max_clusters();
 // fp16 hi/lo operand planes (umma_gemm16.cuh): 4 bytes per operand element instead of 8; planes [rows][ld] halves
 // outputs: C (fp32, nullable) and/or the fp16 hi/lo planes of the result (ld16 halves per row, nullable); epi = EPI_BIAS | EPI_GN_RELU
 cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const void* B_h, const void* B_l, int ldb, int M, int N, int K,

@@ -92,6 +92,7 @@ class PackedWeights:
 
         s = _ext.HbHumorWeights()
         dl, dn = decoder.linears(), decoder.norms()
+        wts = []
         for i, lin in enumerate(dl):
             w = _pad_cols(lin.weight.detach().float(), self.DEC_K[i])
             s.dec_w[i] = dev(w)
@@ -100,6 +101,7 @@ class PackedWeights:
             if i == 3:
                 wt = _pad_cols(wt, 224)
             s.dec_wt[i] = dev(wt)
+            wts.append(wt)
             (h, l), (ht, lt) = split(w), split(wt)
             s.dec_w_hi[i], s.dec_w_lo[i] = dev(h), dev(l)
             s.dec_wt_hi[i], s.dec_wt_lo[i] = dev(ht), dev(lt)
@@ -108,6 +110,10 @@ class PackedWeights:
         for i, gn in enumerate(dn):
             s.dec_g[i] = dev(gn.weight)
             s.dec_be[i] = dev(gn.bias)
+        # persistent decoder chain: z-skip rows of the transposed weights side by side (d raw | d pre3 | d pre2 | d pre1 columns)
+        wz = torch.cat([wts[3][512:560, :224], wts[2][1024:1072, :512], wts[1][1024:1072, :1024], wts[0][339:387, :1024]], 1).contiguous()
+        wzh, wzl = split(wz)
+        s.dec_wz_hi, s.dec_wz_lo = dev(wzh), dev(wzl)
         pl, pn = prior_net.linears(), prior_net.norms()
         for i, lin in enumerate(pl):
             w = _pad_cols(lin.weight.detach().float(), self.PRI_K[i])

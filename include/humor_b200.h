@@ -161,6 +161,12 @@ typedef struct HbHumorWeights {
   /* the same for the batched prior: pri_w as [1024][384] [1024][1024]x3 [96][1024] halves; NULL: the prior stays on 3xTF32 */
   const void* pri_w16_h[5];
   const void* pri_w16_l[5];
+  /* persistent decoder chain (use_umma == 1; csrc/chain_persist.cuh): the z-skip rows of the four transposed decoder weights side
+   * by side, [48][2784] = dec_wt[3][512:560][0:224] | dec_wt[2][1024:1072][0:512] | dec_wt[1][1024:1072][0:1024] |
+   * dec_wt[0][339:387][0:1024], as hi/lo planes: d z of all steps is ONE batched GEMM over the reverse pass's operand tape.
+   * NULL: the launch-per-layer chain runs instead */
+  const float* dec_wz_hi;
+  const float* dec_wz_lo;
 } HbHumorWeights;
 
 /* Replaces HumorModel.roll_out(x_past=None, init_input_dict, S, z_seq, return_prior=True)

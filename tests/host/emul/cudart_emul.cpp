@@ -11,6 +11,7 @@
 #include <cxxabi.h>
 #include <dlfcn.h>
 
+#include <cstddef>
 #include <cstdio>
 #include <map>
 #include <string>
@@ -84,6 +85,21 @@ const std::map<std::string, Thunk>& registry() {
       {"hb::feat_f16_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::feat_f16_kernel(A(cf, 0), A(int, 1), A(int, 2), A(int, 3), A(int, 4), A(int, 5), A(unsigned short*, 6), A(unsigned short*, 7))); }},
       {"hb::lbs_fused_kernel<4>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<4>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
       {"hb::lbs_fused_kernel<8>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<8>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
+      // persistent decoder chain: the WHOLE grid runs at once (clusters wait on each other through global-memory flags); the
+      // launcher's parameter block holds 128-byte driver tensor maps, the emulated kernel's block the emulated ones
+      {"hb::chain_kernel", [](dim3 g, dim3 b, void** a) {
+         tcemu::reset();
+         if (g_cluster_x != (unsigned)hb_emu::CH_CS || g.x > (unsigned)tcemu::MAX_CTAS) { std::fprintf(stderr, "cudart_emul: chain_kernel grid %u / cluster %u not emulated\n", g.x, g_cluster_x); std::abort(); }
+         const unsigned char* raw = static_cast<const unsigned char*>(a[0]);
+         static hb_emu::ChainParams q;
+         for (int i = 0; i < hb_emu::CH_NMAPS; ++i) {
+           std::memcpy(&q.map_hi[i], raw + 128 * i, sizeof(CUtensorMap));
+           std::memcpy(&q.map_lo[i], raw + 128 * (hb_emu::CH_NMAPS + i), sizeof(CUtensorMap));
+         }
+         std::memcpy(reinterpret_cast<unsigned char*>(&q) + offsetof(hb_emu::ChainParams, g), raw + 2 * hb_emu::CH_NMAPS * 128,
+                     offsetof(hb_emu::ChainParams, dir) + sizeof(int) - offsetof(hb_emu::ChainParams, g));
+         shim::launch_cluster(g, b, g_cluster_x, [&] { hb_emu::chain_kernel(q); }, true); }},
+      {"hb::chain_bwd_final_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chain_bwd_final_kernel(A(int, 0), A(int, 1), A(cf, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8))); }},
       {"hb::split_hilo_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::split_hilo_kernel(A(cf, 0), A(float*, 1), A(float*, 2), A(size_t, 3))); }},
       {"hb::chamfer_nn_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_nn_kernel(A(int, 0), A(cf, 1), A(int, 2), A(cf, 3), A(float*, 4), A(int*, 5))); }},
       {"hb::chamfer_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chamfer_bwd_kernel(A(int, 0), A(cf, 1), A(int, 2), A(cf, 3), A(cf, 4), A(ci, 5), A(cf, 6), A(ci, 7), A(float*, 8), A(float*, 9))); }},
@@ -136,6 +152,7 @@ int cudaPeekAtLastError() { return 0; }
 int emul_get_last_error() __asm__("cudaGetLastError");
 int emul_get_last_error() { return 0; }
 int cudaFuncSetAttribute(const void*, int, int) { return 0; }
+int cudaOccupancyMaxActiveClusters(int* n, const void*, const void*) { *n = tcemu::MAX_CTAS / 4; return 0; }
 int cudaGetDevice(int* d) { *d = 0; return 0; }
 int cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return 0; }
 int cudaMemsetAsync(void* p, int v, size_t n, void*) { std::memset(p, v, n); return 0; }

@@ -46,11 +46,13 @@ struct Cta {
   std::unique_ptr<std::barrier<>> bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bars;
   std::vector<uint32_t> warp_xchg;         // one slot per thread: shuffle exchange area
+  std::unique_ptr<std::barrier<>> epi_bar; // named barrier of threads 64.. (bar.sync 1, nt - 64)
 };
 inline thread_local uint3 t_idx{0, 0, 0};
 inline thread_local uint3 t_bidx{0, 0, 0};
 inline thread_local Cta* t_cta = nullptr;
 inline thread_local unsigned t_crank = 0;          // rank of the thread's CTA inside its cluster
+inline thread_local unsigned t_slot = 0;           // per-CTA emulation state slot (= rank; = block index when the whole grid runs at once)
 inline thread_local std::barrier<>* t_cluster_bar = nullptr;
 inline unsigned cluster_size = 1;
 inline dim3 b_dim, g_dim;
@@ -62,22 +64,52 @@ inline void sync_warp() { t_cta->warp_bars[t_lin / 32]->arrive_and_wait(); }
 inline void sync_cluster() { t_cluster_bar->arrive_and_wait(); }
 
 // Runs `body` once per thread of every block of the grid; `csize` consecutive blocks along x form a cluster and run together.
+// concurrent = true: ALL clusters of a 1-D grid run at once (persistent kernels whose clusters wait on each other through
+// global-memory flags); every CTA then has its own emulation state slot (t_slot = block index).
 template <class F>
-void launch_cluster(dim3 grid, dim3 block, unsigned csize, F body) {
+void launch_cluster(dim3 grid, dim3 block, unsigned csize, F body, bool concurrent = false) {
   g_dim = grid;
   b_dim = block;
   cluster_size = csize;
   const int nt = (int)(block.x * block.y * block.z);
+  auto make_ctas = [&](std::vector<Cta>& ctas) {
+    for (auto& c : ctas) {
+      c.bar.reset(new std::barrier<>(nt));
+      for (int w = 0; w < (nt + 31) / 32; ++w) c.warp_bars.emplace_back(new std::barrier<>(std::min(32, nt - 32 * w)));
+      c.warp_xchg.assign(nt, 0u);
+      if (nt > 64) c.epi_bar.reset(new std::barrier<>(nt - 64));
+    }
+  };
+  if (concurrent) {
+    const unsigned nb = grid.x, ncl = (nb + csize - 1) / csize;
+    std::vector<Cta> ctas(nb);
+    make_ctas(ctas);
+    std::vector<std::unique_ptr<std::barrier<>>> cbars;
+    for (unsigned c = 0; c < ncl; ++c) cbars.emplace_back(new std::barrier<>((std::ptrdiff_t)std::min(csize, nb - c * csize) * nt));
+    std::vector<std::thread> th;
+    th.reserve((size_t)nb * nt);
+    for (unsigned bx = 0; bx < nb; ++bx)
+      for (int t = 0; t < nt; ++t)
+        th.emplace_back([=, &body, &ctas, &cbars] {
+          t_lin = t;
+          t_idx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+          t_bidx = {bx, 0, 0};
+          t_cta = &ctas[bx];
+          t_crank = bx % csize;
+          t_slot = bx;
+          t_cluster_bar = cbars[bx / csize].get();
+          body();
+        });
+    for (auto& x : th) x.join();
+    cluster_size = 1;
+    return;
+  }
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx0 = 0; bx0 < grid.x; bx0 += csize) {
         const unsigned nc = std::min(csize, grid.x - bx0);
         std::vector<Cta> ctas(nc);
-        for (auto& c : ctas) {
-          c.bar.reset(new std::barrier<>(nt));
-          for (int w = 0; w < (nt + 31) / 32; ++w) c.warp_bars.emplace_back(new std::barrier<>(std::min(32, nt - 32 * w)));
-          c.warp_xchg.assign(nt, 0u);
-        }
+        make_ctas(ctas);
         std::barrier<> cbar((std::ptrdiff_t)nc * nt);
         std::vector<std::thread> th;
         th.reserve((size_t)nc * nt);
@@ -89,6 +121,7 @@ void launch_cluster(dim3 grid, dim3 block, unsigned csize, F body) {
               t_bidx = {bx0 + r, by, bz};
               t_cta = &ctas[r];
               t_crank = r;
+              t_slot = r;
               t_cluster_bar = &cbar;
               body();
             });
@@ -122,6 +155,7 @@ static inline float __fmul_rn(float a, float b) { volatile float r = a * b; retu
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __ldg(const float* p) { return *p; }
+static inline float __ldcg(const float* p) { return *p; }
 static inline int __ldg(const int* p) { return *p; }
 static inline float4 __ldg(const float4* p) { return *p; }
 static inline void __stcs(float* p, float v) { *p = v; }
@@ -143,6 +177,7 @@ static inline float __shfl_sync(unsigned, float v, int src) {
 }
 using std::max;
 using std::min;
+static inline float fmaxf_(float a, float b) { return a > b ? a : b; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline int __ldg(const unsigned* p) { return (int)*p; }
 typedef unsigned long long cuuint64_t;

@@ -28,6 +28,7 @@ namespace tcemu {
 constexpr uint32_t WINDOW_BYTES = 256 * 1024;
 constexpr uint32_t DYN_OFFSET = 16;
 constexpr int MAX_CLUSTER = 8;
+constexpr int MAX_CTAS = 16;                           // emulation state slots: a cluster, or a whole (small) concurrent grid
 constexpr uint32_t RANK_SHIFT = 24;                    // mapa result: (rank + 1) << 24 | offset in that CTA's window
 struct Bar { int expected = 0, pending = 0; long long tx = 0; int phase = 0; };
 struct Guard { uint32_t lo, hi; int count; };
@@ -38,10 +39,10 @@ struct CtaState {
   std::map<uint32_t, Bar> bars;
   std::map<uint32_t, Guard> guards;
 };
-inline CtaState g_cta[MAX_CLUSTER];
+inline CtaState g_cta[MAX_CTAS];
 inline std::mutex g_mu;
 inline long long g_mma_count = 0, g_tma_count = 0;
-inline CtaState& cur() { return g_cta[shim::t_crank]; }
+inline CtaState& cur() { return g_cta[shim::t_slot]; }
 #define g_smem (tcemu::cur().smem)
 #define g_tmem (tcemu::cur().tmem)
 #define g_bars (tcemu::cur().bars)
@@ -258,14 +259,41 @@ inline float4 ld_shared_v4(uint32_t addr) { float4 v; std::memcpy(&v, g_smem + a
 inline uint32_t cluster_ctarank() { return shim::t_crank; }
 inline void cluster_sync_all() { shim::sync_cluster(); }
 inline uint32_t map_to_cta(uint32_t local, uint32_t rank) {
-  if (rank >= shim::cluster_size || rank >= (uint32_t)MAX_CLUSTER || local >= WINDOW_BYTES) { std::fprintf(stderr, "tcemu: mapa to CTA %u of a %u-CTA cluster / offset %u\n", rank, shim::cluster_size, local); std::abort(); }
-  return ((rank + 1u) << RANK_SHIFT) | local;
+  const uint32_t slot = shim::t_slot - shim::t_crank + rank;      // the cluster's CTAs occupy consecutive state slots
+  if (rank >= shim::cluster_size || slot >= (uint32_t)MAX_CTAS || local >= WINDOW_BYTES) { std::fprintf(stderr, "tcemu: mapa to CTA %u of a %u-CTA cluster / offset %u\n", rank, shim::cluster_size, local); std::abort(); }
+  return ((slot + 1u) << RANK_SHIFT) | local;
 }
 inline void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
   const uint32_t r = addr >> RANK_SHIFT, off = addr & ((1u << RANK_SHIFT) - 1u);
-  if (r == 0 || r > shim::cluster_size || off + 16u > WINDOW_BYTES || (off & 15u)) { std::fprintf(stderr, "tcemu: bad st.shared::cluster address %u\n", addr); std::abort(); }
+  if (r == 0 || r > (uint32_t)MAX_CTAS || off + 16u > WINDOW_BYTES || (off & 15u)) { std::fprintf(stderr, "tcemu: bad st.shared::cluster address %u\n", addr); std::abort(); }
   const float v[4] = {a, b, c, d};
   std::memcpy(g_cta[r - 1].smem + off, v, 16);
 }
+// ---- persistent decoder chain (chain_persist.cuh): cluster ids, remote mbarrier arrivals, data-flow flags, named barrier
+inline uint32_t cluster_id_x() { return blockIdx.x / shim::cluster_size; }
+inline uint32_t cluster_nid_x() { return gridDim.x / shim::cluster_size; }
+inline void mbar_arrive_remote(uint32_t addr) {                  // addr from map_to_cta
+  const uint32_t r = addr >> RANK_SHIFT, off = addr & ((1u << RANK_SHIFT) - 1u);
+  if (r == 0 || r > (uint32_t)MAX_CTAS) { std::fprintf(stderr, "tcemu: bad remote mbarrier address %u\n", addr); std::abort(); }
+  std::lock_guard<std::mutex> l(g_mu);
+  Bar& b = g_cta[r - 1].bars.at(off);
+  b.pending -= 1;
+  if (b.pending < 0) { std::fprintf(stderr, "tcemu: mbarrier %u of CTA slot %u over-arrived\n", off, r - 1); std::abort(); }
+  complete_if_done(b);
+}
+inline void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+inline void flag_wait_ge(const unsigned* p, unsigned target) {
+  const auto t0 = std::chrono::steady_clock::now();
+  while (__atomic_load_n(p, __ATOMIC_ACQUIRE) < target) {
+    std::this_thread::yield();
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+      std::fprintf(stderr, "tcemu: data-flow flag %p stuck at %u < %u: protocol deadlock\n", (const void*)p, *p, target);
+      std::abort();
+    }
+  }
+}
+inline void flag_add_release(unsigned* p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+inline void fence_proxy_async() {}
+inline void epi_bar_sync() { shim::t_cta->epi_bar->arrive_and_wait(); }
 
 }  // namespace tcemu

@@ -35,6 +35,7 @@ def emul(built_lib, tmp_path_factory):
 def run_probe(emul, script, *args, tensor=False, extra_env=None):
     rt, lib = emul
     env = dict(os.environ, LD_PRELOAD=rt, CUDA_VISIBLE_DEVICES='')
+    env.setdefault('HB_CHAIN_CLUSTERS', '2')      # persistent decoder chain: 2 clusters x 4 CTAs x 192 threads run at once
     env.update(extra_env or {})
     if tensor:          # tcgen05 kernels on the functional emulation, incl. the 4-CTA-cluster split-K GEMMs of the decoder chain
         env.update(HB_EMUL_TENSOR='1')
@@ -199,6 +200,20 @@ def test_forms_verification_tool(emul):
     assert not recs[(3, 5)]['bitwise_equal_to_11'] and recs[(3, 5)]['max_abs_diff_vs_11'] < 5e-6
 
 
+def test_persistent_chain_matches_launch_per_layer_chain(emul):
+    """csrc/chain_persist.cuh on the emulation (ALL clusters of the grid run concurrently: data-flow flags, remote mbarrier
+    hand-shakes, DSMEM reduce-scatter) against the launch-per-layer chain: a batch of two ragged 128-row tiles, three resident
+    clusters (tiles strided unevenly over clusters), forward states / prior and the reverse pass incl. the batched d z GEMM."""
+    rt, lib = emul
+    env = dict(os.environ, LD_PRELOAD=rt, CUDA_VISIBLE_DEVICES='')
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'host', 'emul', 'probe_chain.py'), ROOT, lib, '131', '3', '3'],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=1500)
+    lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    assert r.returncode == 0 and lines, (r.stdout[-1500:], r.stderr[-3000:])
+    out = json.loads(lines[-1])
+    assert out['finite'] and out['world'] < 5e-6 and out['prior'] < 1e-5 and out['d_init'] < 1e-4 and out['d_z'] < 1e-4, out
+
+
 def test_stage3_closure_tensor16_precision(emul):
     """precision 'tensor16' (opt-in): the FORWARD decoder chain on fp16 hi + scaled lo operand planes (4 bytes per element;
     csrc/umma_gemm16.cuh with its GroupNorm epilogues, chain16_pack_kernel for the step inputs), the tape, the batched prior and
@@ -214,8 +229,9 @@ def test_stage3_closure_tensor16_precision(emul):
 @pytest.mark.parametrize('prefetch_b', [False, pytest.param(True, marks=pytest.mark.skipif(
     not os.environ.get('HB_SLOW_TESTS'), reason='second producer order of the same kernels: set HB_SLOW_TESTS=1'))])
 def test_stage3_closure_tensor_precision(emul, prefetch_b):
-    """The DEFAULT precision mode: every rollout GEMM on the (emulated) tcgen05 3xTF32 kernel with descriptors built by the
-    library's own host code, against the fixture of the unmodified reference.  prefetch_b: the opt-in producer order of
+    """The DEFAULT precision mode: every rollout GEMM on the (emulated) tcgen05 3xTF32 kernels with descriptors built by the
+    library's own host code - the decoder chain as the PERSISTENT kernel of csrc/chain_persist.cuh (two resident clusters), the
+    batched prior on umma_gemm3_kernel - against the fixture of the unmodified reference.  prefetch_b: the opt-in producer order of
     HB_UMMA_PREFETCH_B=1 (weight tiles requested before the programmatic-dependent-launch wait) - same numbers."""
     out = run_probe(emul, 'probe_stage3.py', 'stage3_rgb_phase1', tensor=True,
                     extra_env={'HB_UMMA_PREFETCH_B': '1'} if prefetch_b else None)

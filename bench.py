@@ -71,22 +71,43 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
-def build_problem(B, T, seed=4):
-    return synth.make_stage3_problem(B, T, seed=seed, overlap=10, cam=True)
+CONFIGS = {
+    # BASELINE.json configs[2] / [3]: fit_rgb_demo_use_split stage-3 weights, optim_floor, 2-D keypoints + overlap consistency
+    'rgb': dict(optim_floor=True, weights='RGB_STAGE3_WEIGHTS', obs=('joints2d', 'floor_plane', 'seq_interval'),
+                what='RGB config (optim_floor, fit_rgb_demo_use_split stage-3 weights, rgb_overlap_consist 200, overlap 10)'),
+    # BASELINE.json configs[4]: fit_amass_keypts - 3-D key vertices with occlusions (inf), no floor optimisation
+    'amass': dict(optim_floor=False, weights='AMASS_STAGE3_WEIGHTS', obs=('verts3d',),
+                  what='AMASS key-vertex config (fit_amass_keypts stage-3 weights, verts3d observations with inf-masked occlusions, no floor)'),
+}
 
 
-def make_optimizer(B, T, prob, dev):
+def build_problem(B, T, seed=4, config='rgb'):
+    return synth.make_stage3_problem(B, T, seed=seed, overlap=10, cam=CONFIGS[config]['optim_floor'])
+
+
+def workload_config(args, world):
+    """The `config` object both arms print: what is computed, not how."""
+    c = CONFIGS[args.config]
+    return {'workload': f'Stage-III full-T closure fwd+bwd, B={args.batch} sub-sequences/GPU x T={args.seq_len}, {c["what"]}',
+            'config_name': args.config, 'batch_per_gpu': args.batch, 'seq_len': args.seq_len,
+            'parallelism': f'dp{world} over sub-sequences',
+            'l2': 'working set per step (rollout tape + dense vertices, > 1 GB at B=256) exceeds the 126 MB L2'}
+
+
+def make_optimizer(B, T, prob, dev, config='rgb'):
     from humor_b200.body_model import BodyModel
     from humor_b200.humor_model import HumorModel
     from humor_b200.motion_optimizer import MotionOptimizer
-    bm = BodyModel(synth.make_smplh_asset(), num_betas=16, batch_size=B * T, use_vtx_selector=True).to(dev)
+    cfg = CONFIGS[config]
+    of = cfg['optim_floor']
+    bm = BodyModel(synth.make_smplh_asset(), num_betas=16, batch_size=B * T, use_vtx_selector=of).to(dev)
     humor = HumorModel(in_rot_rep='mat', out_rot_rep='aa', latent_size=48, model_data_config='smpl+joints+contacts', steps_in=1)
     humor.load_state_dict(synth.make_humor_state_dict())
     humor.to(dev).eval()
     gmm = tuple(g.to(dev) for g in synth.make_gmm())
-    w = dict(synth.RGB_STAGE3_WEIGHTS)
-    mo = MotionOptimizer(dev, bm, 16, B, T, ['joints2d', 'floor_plane', 'seq_interval'], [dict(w), dict(w), dict(w)],
-                         synth.FakeVPoser().to(dev), humor, {'gmm': gmm}, True, torch.as_tensor(prob['cam_mat']).to(dev),
+    w = dict(getattr(synth, cfg['weights']))
+    mo = MotionOptimizer(dev, bm, 16, B, T, list(cfg['obs']), [dict(w), dict(w), dict(w)],
+                         synth.FakeVPoser().to(dev), humor, {'gmm': gmm}, of, torch.as_tensor(prob['cam_mat']).to(dev) if of else None,
                          'bisquare', 4.6851, 100.0)
     mo.fitting_loss.assume_unit_grad = True
     return mo
@@ -95,12 +116,20 @@ def make_optimizer(B, T, prob, dev):
 OBS_KEYS = ('joints2d', 'floor_plane', 'seq_interval')
 
 
-def project_obs_from_product(mo, prob, dev):
-    """Informative 2-D keypoints: project the product's own camera-frame joints at the initial state (+noise)."""
+def project_obs_from_product(mo, prob, dev, config='rgb'):
+    """Informative observations: the product's own prediction at the initial state + noise (2-D keypoints for the RGB config,
+    key vertices with the synthetic occlusion mask for the AMASS config)."""
+    keys = CONFIGS[config]['obs']
     mo.set_stage3_state(prob['params'])
-    obs = {k: torch.as_tensor(prob['obs'][k]).to(dev) for k in OBS_KEYS}
+    obs = {k: torch.as_tensor(prob['obs'][k]).to(dev) for k in keys}
     with torch.no_grad():
         _, _, _, _, cam_pred = mo.stage3_forward(obs)
+    if config == 'amass':
+        v = cam_pred['verts3d'].cpu().numpy()
+        rng = np.random.RandomState(5)
+        occl = np.isinf(prob['obs']['verts3d'])
+        prob['obs']['verts3d'] = np.where(occl, np.inf, v + rng.randn(*v.shape) * 0.01).astype(np.float32)
+        return prob
     from humor_b200.fitting_loss import SMPL2OP
     j = cam_pred['Jtr'][:, :, SMPL2OP].cpu().numpy()
     rng = np.random.RandomState(5)
@@ -121,18 +150,19 @@ def run_product(args):
     torch.cuda.set_device(dev)
     _ext.check(_ext.lib().humor_lbs_configure(args.lbs_skin, args.lbs_blend, args.lbs_slab), 'humor_lbs_configure')
     B, T = args.batch, args.seq_len
-    prob = build_problem(B, T, seed=4 + rank)
-    mo = make_optimizer(B, T, prob, dev)
-    prob = project_obs_from_product(mo, prob, dev)
+    OBS_KEYS = CONFIGS[args.config]['obs']
+    prob = build_problem(B, T, seed=4 + rank, config=args.config)
+    mo = make_optimizer(B, T, prob, dev, args.config)
+    prob = project_obs_from_product(mo, prob, dev, args.config)
     # global frame intervals of this rank's block of sub-sequences (one video split across the ranks)
     prob['obs']['seq_interval'] = prob['obs']['seq_interval'] + rank * B * (T - 10)
-    if world > 1:
+    if world > 1 and 'seq_interval' in OBS_KEYS:
         from humor_b200.parallel import Shard
         mo.shard = Shard.from_env(ov_max=16)
     names = mo.set_stage3_state(prob['params'])
     obs = {k: torch.as_tensor(prob['obs'][k]).to(dev) for k in OBS_KEYS}
     params = [getattr(mo, n) for n in names]
-    if world > 1:
+    if world > 1 and mo.shard is not None:
         mo.shard.prepare(obs['seq_interval'])
     mo.use_cuda_graph = not args.no_graph
     mo.set_precision(args.precision)
@@ -208,6 +238,7 @@ def run_product(args):
     e2e = frames / (ms_e2e * 1e-3)
     hbm_peak, _, peak_kind = load_peaks()
     graphed = bool(mo.use_cuda_graph)
+    mo_shard_off = 'seq_interval' not in OBS_KEYS
     roof = lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind)
     roof['forms'] = {'skin': args.lbs_skin or int(os.environ.get('HB_LBS_SKIN', 1)), 'blend': args.lbs_blend or int(os.environ.get('HB_LBS_BLEND', 1)),
                      'slab_frames': args.lbs_slab or int(os.environ.get('HB_LBS_SLAB', 512))}
@@ -222,12 +253,9 @@ def run_product(args):
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic (seeded SMPL+H-shaped asset, random-init HuMoR weights, projected 2-D keypoints)',
-        'config': {'workload': f'Stage-III full-T closure fwd+bwd, B={B} sub-sequences/GPU x T={T}, RGB config '
-                               '(optim_floor, fit_rgb_demo_use_split stage-3 weights, overlap 10)',
-                   'batch_per_gpu': B, 'seq_len': T, 'parallelism': f'dp{world} over sub-sequences',
-                   'cuda_graph': graphed, 'precision': args.precision,
-                   'collectives_per_step': 0 if world == 1 else 'all_gather(halo pack) fwd + all_reduce(halo grad) bwd',
-                   'l2': 'working set per step (rollout tape 0.45 GB + dense vertices 1.3 GB) exceeds the 126 MB L2'},
+        'config': workload_config(args, world),
+        'impl_details': {'cuda_graph': graphed, 'precision': args.precision, 'decoder_chain': 'launch-per-layer' if os.environ.get('HB_CHAIN') == '0' else 'persistent kernel (csrc/chain_persist.cuh)',
+                         'collectives_per_step': 0 if (world == 1 or mo_shard_off) else 'halo exchange of the overlap pack fwd + its gradient bwd'},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches), 'gpu_launches_per_step': launches / args.steps,
@@ -242,14 +270,18 @@ def run_product(args):
     if not args.no_cpu_baseline and world == 1:          # context numbers: rank 0 at N = 1 only
         left = _time_left() - 20.0
         if left - 45.0 >= 30.0:
+            args.cpu_steps, args.cpu_warmup, args.cpu_budget = 3, 1, min(args.cpu_budget, 25.0)
             out['cpu_baseline'] = cpu_baseline(args, limit_s=min(150.0, left - 45.0))
         else:
             out['cpu_baseline'] = {'value': None, 'unit': 'frames/s', 'cores': cpu_threads(), 'kind': 'port',
                                    'sample': 'skipped: the run\'s time limit was nearly spent'}
         # the same algorithm as eager PyTorch on this GPU (context for the '>= 20x the reference PyTorch-CUDA step' target)
         left = _time_left() - 20.0
-        out['torch_cuda_port'] = port_cuda_child(args, limit_s=min(120.0, left)) if left >= 25.0 else \
-            {'batch': 64, 'error': 'skipped: the run\'s time limit was nearly spent'}
+        out['torch_cuda_port'] = port_cuda_child(args, batch=B, limit_s=min(150.0, left)) if left >= 40.0 else \
+            {'batch': B, 'error': 'skipped: the run\'s time limit was nearly spent'}
+        if out['torch_cuda_port'].get('frames_per_s'):
+            out['vs_torch_cuda_port'] = {'ratio': value / out['torch_cuda_port']['frames_per_s'], 'e2e_ratio': e2e / out['torch_cuda_port']['frames_per_s'],
+                                         'same_batch': out['torch_cuda_port'].get('batch') == B, 'target': 20.0}
         # the opt-in kernel forms of the dense LBS forward, verified against the default forms and timed stand-alone on this GPU
         # (separate child processes: a form that faults must not take the measurement down).  The step above ran forms 1/1.
         out['roofline_candidates'] = lbs_candidates(B, T, hbm_peak)
@@ -328,22 +360,43 @@ def kernel_shares(mo, obs, params, dev):
 
 
 def cpu_baseline_inproc(args, threads):
-    """The oracle port (plain-torch restatement of the reference closure) on the host cores, bounded sample."""
+    """The oracle port (plain-torch restatement of the reference closure) on the host cores.  One step = one full-T closure
+    (fwd+bwd) of the SAME configuration at a bounded sample batch: the largest power of two <= --batch for which warm-up + steps
+    fit the time budget, calibrated on one closure at B=8 (the port's cost is ~linear in B beyond B=8: 590 frames/s at B=8,
+    755 frames/s at B=64 on 8 threads, so frames/s of the sample stands for the full batch)."""
     from tests import util_stage3 as U
     torch.set_num_threads(max(1, threads))
-    Bc, T = args.cpu_batch, args.seq_len
-    prob = build_problem(Bc, T, seed=4)
-    port = U.build_port(Bc, T, synth.RGB_STAGE3_WEIGHTS, True, prob)
-    U.closure_port(port, prob, True)                 # warm-up
-    ts = []
-    for _ in range(args.cpu_steps):
-        t0 = time.perf_counter()
-        U.closure_port(port, prob, True)
-        ts.append(time.perf_counter() - t0)
+    T = args.seq_len
+    cfg = CONFIGS[args.config]
+    W = getattr(synth, cfg['weights'])
+    of = cfg['optim_floor']
+
+    def one(Bc, n_warm, n_steps):
+        prob = build_problem(Bc, T, seed=4, config=args.config)
+        port = U.build_port(Bc, T, W, of, prob)
+        for _ in range(n_warm):
+            U.closure_port(port, prob, of)
+        ts = []
+        for _ in range(n_steps):
+            t0 = time.perf_counter()
+            U.closure_port(port, prob, of)
+            ts.append(time.perf_counter() - t0)
+        return ts
+
+    Bc = args.cpu_batch
+    calib = None
+    if Bc <= 0:
+        calib = one(8, 1, 1)[0]
+        Bc = 8
+        while Bc * 2 <= args.batch and (args.cpu_warmup + args.cpu_steps) * calib * (Bc * 2 / 8.0) <= args.cpu_budget:
+            Bc *= 2
+    ts = one(Bc, args.cpu_warmup, args.cpu_steps)
     med = float(np.median(ts))
     return {'value': Bc * T / med, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-            'sample': f'{args.cpu_steps} full-T closures (fwd+bwd) at B={Bc}, T={T} (same config, smaller batch), median',
-            's_per_step': med}
+            'sample': f'{args.cpu_steps} full-T closures (fwd+bwd) after {args.cpu_warmup} warm-up at B={Bc} of the B={args.batch} workload, T={T}, '
+                      f'config {args.config}, median; sample batch chosen for a {args.cpu_budget:.0f} s budget'
+                      + (f' from a {calib:.2f} s calibration closure at B=8' if calib is not None else ''),
+            's_per_step': med, 'sample_batch': Bc, 'steps': args.cpu_steps, 'warmup': args.cpu_warmup}
 
 
 def port_on_cuda(args):
@@ -357,14 +410,16 @@ def port_on_cuda(args):
     res = []
     for Bc in [int(b) for b in args.port_cuda.split(',')]:
         try:
-            prob = build_problem(Bc, T, seed=4)
-            port = U.build_port(Bc, T, synth.RGB_STAGE3_WEIGHTS, True, prob, device='cuda')
-            U.closure_port(port, prob, True, device='cuda')
+            cfg = CONFIGS[args.config]
+            of = cfg['optim_floor']
+            prob = build_problem(Bc, T, seed=4, config=args.config)
+            port = U.build_port(Bc, T, getattr(synth, cfg['weights']), of, prob, device='cuda')
+            U.closure_port(port, prob, of, device='cuda')
             torch.cuda.synchronize()
             ts = []
             for _ in range(args.cpu_steps):
                 t0 = time.perf_counter()
-                U.closure_port(port, prob, True, device='cuda')
+                U.closure_port(port, prob, of, device='cuda')
                 torch.cuda.synchronize()
                 ts.append(time.perf_counter() - t0)
             med = float(np.median(ts))
@@ -377,15 +432,16 @@ def port_on_cuda(args):
         finally:
             port = None
             torch.cuda.empty_cache()
-    print(json.dumps({'impl': 'port-cuda', 'metric': METRIC, 'unit': 'frames/s', 'kind': 'oracle port, eager PyTorch on cuda:0',
-                      'steps': args.cpu_steps, 'results': res}))
+    print(json.dumps({'impl': 'port-cuda', 'metric': METRIC, 'unit': 'frames/s', 'kind': 'oracle port of the reference closure, eager PyTorch (fp32) on cuda:0',
+                      'config_name': args.config, 'steps': args.cpu_steps, 'results': res}))
 
 
 def port_cuda_child(args, batch=64, limit_s=150):
-    """the reference ALGORITHM as eager PyTorch on the same B200 (the oracle port on device='cuda'; the
-    reference itself cannot travel to the GPU box), timed in a child process with a hard limit.  Launch/dispatch-bound:
-    its time per closure barely depends on the batch, so frames/s is quoted at the batch given."""
-    cmd = [sys.executable, os.path.abspath(__file__), '--port-cuda', str(batch), '--cpu-steps', '3', '--seq-len', str(args.seq_len)]
+    """SURVEY.md 8(d) / BASELINE.md section 3 - the denominator of the '>= 20x the reference PyTorch-CUDA step' target: the
+    reference ALGORITHM as eager PyTorch on the same B200 (the oracle port on device='cuda'; the reference itself cannot travel
+    to the GPU box), same configuration and batch as this run, in a child process with a hard limit."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--port-cuda', str(batch), '--cpu-steps', '3', '--seq-len', str(args.seq_len),
+           '--config', args.config]
     env = dict(os.environ)
     for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
         env.pop(k, None)
@@ -476,8 +532,9 @@ def cpu_threads():
 def cpu_baseline(args, threads=None, limit_s=150):
     """Runs cpu_baseline_inproc in a child process with a hard time limit so the bench always finishes."""
     threads = threads or cpu_threads()
-    cmd = [sys.executable, os.path.abspath(__file__), '--_cpu-child', '--cpu-batch', str(args.cpu_batch),
-           '--cpu-steps', str(args.cpu_steps), '--seq-len', str(args.seq_len), '--cpu-threads', str(threads)]
+    cmd = [sys.executable, os.path.abspath(__file__), '--_cpu-child', '--cpu-batch', str(args.cpu_batch), '--batch', str(args.batch),
+           '--cpu-steps', str(args.cpu_steps), '--cpu-warmup', str(args.cpu_warmup), '--cpu-budget', str(args.cpu_budget),
+           '--seq-len', str(args.seq_len), '--cpu-threads', str(threads), '--config', args.config]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads))
     for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT'):
         env.pop(k, None)
@@ -490,19 +547,21 @@ def cpu_baseline(args, threads=None, limit_s=150):
 
 
 def run_reference(args):
+    """Reference arm: the reference ALGORITHM (oracle port; the reference itself is Python + smplx, absent from the box) on the
+    host cores, on THIS arm's configuration, metric and unit, with the driver's --steps / --warmup: every step is one full-T
+    closure at a calibrated sample batch of the B = --batch workload (frames/s is intensive; see cpu_baseline_inproc)."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    cb = cpu_baseline(args, limit_s=240)
-    B, T = args.batch, args.seq_len
-    out = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'frames/s',
-           'n_gpus': int(os.environ.get('WORLD_SIZE', 1)), 'steps': args.cpu_steps, 'warmup': 1,
-           'ms_per_step': (cb.get('s_per_step') or 0.0) * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-           'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': f'Stage-III full-T closure fwd+bwd, B={B} x T={T}, RGB config; timed on a bounded sample '
-                                  f'of B={args.cpu_batch} on the host CPUs (oracle port of the reference algorithm; the '
-                                  'reference itself is Python + unavailable smplx and cannot travel to this box)'},
-           'cpu_baseline': cb,
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    args.cpu_steps, args.cpu_warmup = args.steps, args.warmup
+    args.cpu_budget = max(args.cpu_budget, 170.0)
+    cb = cpu_baseline(args, limit_s=330)
+    out = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'frames/s', 'n_gpus': world,
+           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': (cb.get('s_per_step') or 0.0) * 1e3,
+           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+           'data': 'synthetic (same seeded generator as the humor_b200 arm)',
+           'config': workload_config(args, world), 'cpu_baseline': cb,
            'e2e': {'value': cb['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(out))
 
@@ -538,8 +597,11 @@ def main():
     ap.add_argument('--impl', default='humor_b200', choices=['humor_b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='sub-sequences per GPU')
     ap.add_argument('--seq-len', type=int, default=60)
-    ap.add_argument('--cpu-batch', type=int, default=8)
+    ap.add_argument('--config', default='rgb', choices=sorted(CONFIGS), help='rgb: fit_rgb_demo_use_split (BASELINE configs 2-3); amass: fit_amass_keypts (config 4)')
+    ap.add_argument('--cpu-batch', type=int, default=0, help='sample batch of the host-CPU baseline (0: calibrated to --cpu-budget)')
     ap.add_argument('--cpu-steps', type=int, default=3)
+    ap.add_argument('--cpu-warmup', type=int, default=1)
+    ap.add_argument('--cpu-budget', type=float, default=25.0, help='seconds of host-CPU work the baseline may use')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='tensor', choices=['tensor', 'exact', 'tensor16'],
                     help="'tensor': GEMMs on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels (gradient-exact parity mode); "

@@ -135,6 +135,7 @@ class PackedWeights:
         self.struct = s
         self.device = device
         self._ws = {}
+        self._gen = {}          # (B, S) -> number of forwards that wrote the cached tape (a reverse pass must see ITS forward's tape)
 
     def workspace(self, B, S):
         ws = self._ws.get((B, S))
@@ -162,6 +163,7 @@ class _RolloutFn(torch.autograd.Function):
                                                 _ext.stream_ptr()), 'humor_rollout_fwd')
         _ext.LaunchCounter.total += nl.value
         ctx.pw, ctx.B, ctx.S, ctx.want_prior = pw, B, S, want_prior
+        pw._gen[(B, S)] = ctx.gen = pw._gen.get((B, S), 0) + 1
         ctx.set_materialize_grads(False)
         if prior is None:
             prior = torch.empty(0, device=x0.device)
@@ -171,6 +173,11 @@ class _RolloutFn(torch.autograd.Function):
     def backward(ctx, d_world, d_prior):
         pw, B, S = ctx.pw, ctx.B, ctx.S
         dev = pw.device
+        if pw._gen.get((B, S)) != ctx.gen:
+            # the tape (step inputs, decoder outputs, GroupNorm statistics) lives in ONE workspace per (B, S): a later forward of
+            # the same shape has overwritten what this reverse pass needs - wrong gradients, so refuse instead
+            raise RuntimeError(f'humor_b200 rollout: the BPTT tape for (B={B}, S={S}) was overwritten by a later forward pass of the '
+                               'same shape before this backward ran; call backward() before the next roll_out of that shape')
         ws = pw.workspace(B, S)
         if d_world is None:
             d_world = torch.zeros(S, B, WORLD_D, device=dev, dtype=torch.float32)

@@ -324,10 +324,18 @@ class MotionOptimizer():
             return loss
         from . import _ext
         w = self.fitting_loss.loss_weights
-        key = (nsteps, float(init_motion_scale), getattr(self.motion_prior, 'precision', None),
+        for p in params:
+            if p.requires_grad and p.grad is None:
+                p.grad = torch.zeros_like(p)          # static gradient buffers the graph writes into
+        packed = self.motion_prior.packed() if hasattr(self.motion_prior, 'packed') else None
+        # a captured graph holds raw pointers: variables, their gradient buffers, the packed weights and the observations all
+        # belong to its identity (and are kept alive by the cache entry below)
+        key = (tuple(0 if p.grad is None else p.grad.data_ptr() for p in params), tuple(p.data_ptr() for p in params), id(packed),
+               nsteps, float(init_motion_scale), getattr(self.motion_prior, 'precision', None),
                int(self.body_model.lbs_model.struct.use_umma), tuple(bool(p.requires_grad) for p in params),
                tuple(sorted((k, float(v)) for k, v in w.items())), tuple(id(p) for p in params),
-               tuple((k, v.data_ptr()) for k, v in sorted(observed_data.items()) if torch.is_tensor(v)))
+               tuple((k, v.data_ptr()) for k, v in sorted(observed_data.items()) if torch.is_tensor(v)),
+               tuple((k, v.data_ptr()) for k, v in sorted(observed_data.get('prev_batch_overlap_res', {}).items()) if torch.is_tensor(v)))
         g = self._graphs.get(key)
         if g is None:
             for p in params:
@@ -356,7 +364,8 @@ class MotionOptimizer():
                 self.use_cuda_graph = False
                 torch.cuda.synchronize()
                 return self.stage3_step(observed_data, nsteps, init_motion_scale, params)
-            g = (graph, static_loss, _ext.LaunchCounter.total - l0)
+            g = (graph, static_loss, _ext.LaunchCounter.total - l0, list(params), [p.grad for p in params], packed,
+                 {k: v for k, v in observed_data.items()})
             self._graphs[key] = g
         g[0].replay()
         _ext.LaunchCounter.total += g[2]
@@ -416,6 +425,7 @@ class MotionOptimizer():
         for n in names:
             setattr(self, n, torch.as_tensor(params[n], dtype=torch.float32, device=self.device).clone().requires_grad_(True))
         self.fitting_loss.set_stage(2)
+        self._graphs.clear()                      # graphs captured for the previous variables point at their storage
         return names
 
     # ------------------------------------------------------------------------------------------------
@@ -569,6 +579,7 @@ class MotionOptimizer():
         if len(num_iter) != 3:
             raise ValueError('Must have num iters for 3 stages!')
         per_stage_outputs = {}
+        self._graphs.clear()                      # a new run installs new variables: graphs of an earlier run are stale
         self.initialize(observed_data)
         per_stage_outputs['stage1'], body_pose = self._stage12(observed_data, 0, num_iter[0], lr, lbfgs_max_iter)
         self._save_stage(stages_res_out, 'stage1_results.npz', body_pose)

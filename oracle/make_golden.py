@@ -26,6 +26,9 @@ CASES = {
     'stage3_amass': dict(optim_floor=False, B=2, T=6, seed=24, overlap=2, nsteps=None, scale=1.0),
     # PROX RGB-D (configs/fit_proxd.cfg): point-cloud energy through the reference's compiled chamfer module
     'stage3_proxd': dict(optim_floor=True, B=2, T=6, seed=25, overlap=2, nsteps=None, scale=1.0, wset='proxd', n_obs=96),
+    # second batch of a split video: the first sequence is tied to the LAST sequence of the previous batch
+    # (observed_data['prev_batch_overlap_res'], run_fitting.py:428-435 -> fitting_loss.py:159-179,216-222,301-307)
+    'stage3_rgb_xbatch': dict(optim_floor=True, B=4, T=8, seed=26, overlap=3, nsteps=None, scale=1.0, xbatch=3),
 }
 SMPL2OP = [52, 12, 17, 19, 21, 16, 18, 20, 0, 2, 5, 8, 1, 4, 7, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62]
 
@@ -50,15 +53,37 @@ def run_case(c):
             obs['points3d'] = torch.as_tensor(synth.sample_point_cloud(inter['cam_pred']['points3d'].numpy(), c['n_obs'],
                                                                         seed=c['seed'] + 200))
             keys = keys + ('points3d',)
+        if c.get('xbatch'):
+            # what run_fitting.py:428-435 caches after the previous batch: key vertices of its last sequence (here: the current
+            # first sequence's own start + noise, so the term sits in a realistic range), betas, 4-parameter floor, interval
+            ov, T = c['xbatch'], c['T']
+            rng = np.random.RandomState(c['seed'] + 300)
+            cv = inter['cam_pred']['verts3d'][0].numpy()                      # (T, 43, 3)
+            pv = cv[0][None] + np.cumsum(rng.randn(T, 43, 3) * 0.01, 0)
+            pv[T - ov:] = cv[:ov] + rng.randn(ov, 43, 3) * 0.02
+            n = rng.randn(3) * 0.1 + [0.0, -1.0, 0.0]
+            n /= np.linalg.norm(n)
+            s0 = int(obs['seq_interval'][0, 0])
+            obs['prev_batch_overlap_res'] = {
+                'verts3d': torch.as_tensor(pv.astype(np.float32)),
+                'betas': torch.as_tensor((prob['params']['betas'][0] + rng.randn(16) * 0.1).astype(np.float32)),
+                'floor_plane': torch.as_tensor(np.concatenate([n, [1.1 + 0.1 * rng.randn()]]).astype(np.float32)),
+                'seq_interval': torch.as_tensor(np.array([s0 + ov - T, s0 + ov], dtype=np.int64))}
+            keys = keys + ('prev_batch_overlap_res',)
     names = ref_closure.set_params(mo, prob['params'])
-    loss, stats, inter = ref_closure.stage3_closure(ref, mo, {k: v.clone() for k, v in obs.items()}, c['nsteps'], c['scale'])
+    clone = lambda v: {a: b.clone() for a, b in v.items()} if isinstance(v, dict) else v.clone()
+    loss, stats, inter = ref_closure.stage3_closure(ref, mo, {k: clone(v) for k, v in obs.items()}, c['nsteps'], c['scale'])
     out = {'loss': np.float32(loss.item())}
     for k, v in stats.items():
         out['stat_' + k] = np.float32(float(v))
     for n in names:
         out['grad_' + n] = getattr(mo, n).grad.numpy()
     for k in keys:
-        out['obs_' + k] = obs[k].numpy()
+        if isinstance(obs[k], dict):
+            for a, b in obs[k].items():
+                out['obs_prevres_' + a] = b.numpy()
+        else:
+            out['obs_' + k] = obs[k].numpy()
     out['cam_verts3d'] = inter['cam_pred']['verts3d'].detach().numpy()
     out['cam_joints3d'] = inter['cam_pred']['joints3d'].detach().numpy()
     out['rollout_trans'] = inter['rollout']['trans'].detach().numpy()

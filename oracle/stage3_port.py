@@ -351,6 +351,20 @@ class Stage3Port:
                     vel = vel + 0.5 * (((a[1:] - a[:-1]) - (c[1:] - c[:-1])) ** 2).sum()
             st['rgb_overlap_consist_verts3d_pos'], st['rgb_overlap_consist_verts3d_vel'] = pos, vel
             loss = loss + w['rgb_overlap_consist'] * (pos + vel)
+            if 'prev_batch_overlap_res' in obs:            # fitting_loss.py:159-179: first sequence vs the previous batch's last one
+                prev = obs['prev_batch_overlap_res']
+                cur_ov = int(prev['seq_interval'][1] - iv[0, 0])
+                ov_len = min(v.shape[1], cur_ov)
+                a, c = prev['verts3d'][-cur_ov:][:ov_len], v[0, :ov_len]
+                vis = ~torch.isinf(a)
+                xpos = 0.5 * ((a[vis] - c[vis]) ** 2).sum()
+                xvel = 0.0
+                if cur_ov > 1:
+                    da, dc = a[1:] - a[:-1], c[1:] - c[:-1]
+                    vv = ~torch.isinf(da)
+                    xvel = 0.5 * ((da[vv] - dc[vv]) ** 2).sum()
+                st['rgb_overlap_xbatch_verts3d_pos'], st['rgb_overlap_xbatch_verts3d_vel'] = xpos, xvel
+                loss = loss + w['rgb_overlap_consist'] * (xpos + xvel)
         if smpl and w['pose_prior'] > 0:
             st['pose_prior'] = (cam_pred['latent_pose'] ** 2).sum()
             loss = loss + w['pose_prior'] * st['pose_prior']
@@ -364,6 +378,9 @@ class Stage3Port:
         if smpl and ov_on:
             st['rgb_overlap_consist_betas'] = 0.5 * ((p['betas'][:-1] - p['betas'][1:]) ** 2).sum()
             loss = loss + w['rgb_overlap_consist'] * st['rgb_overlap_consist_betas']
+            if 'prev_batch_overlap_res' in obs:            # fitting_loss.py:217-222
+                st['rgb_overlap_xbatch_betas'] = 0.5 * ((p['betas'][0] - obs['prev_batch_overlap_res']['betas']) ** 2).sum()
+                loss = loss + w['rgb_overlap_consist'] * st['rgb_overlap_xbatch_betas']
         if not motion:
             return loss, st
         if w['motion_prior'] > 0:
@@ -402,6 +419,10 @@ class Stage3Port:
             fp = p['floor_plane']
             st['rgb_overlap_consist_floor'] = 0.5 * ((fp[:-1] - fp[1:]) ** 2).sum()
             loss = loss + w['rgb_overlap_consist'] * st['rgb_overlap_consist_floor']
+            if 'prev_batch_overlap_res' in obs:            # fitting_loss.py:302-307: floor_reg_loss against the previous 4-parameter plane
+                o = obs['prev_batch_overlap_res']['floor_plane']
+                st['rgb_overlap_xbatch_floor'] = 0.5 * ((fp[0] - o[:3] * o[3:]) ** 2).sum()
+                loss = loss + w['rgb_overlap_consist'] * st['rgb_overlap_xbatch_floor']
         return loss, st
 
     # -- Stage I / II closures ---------------------------------------------------------------------
@@ -436,7 +457,7 @@ class Stage3Port:
         w = dict(self.w)
         o, n = obs, self.T
         if nsteps is not None:
-            o = {k: v[:, :nsteps] for k, v in obs.items()}
+            o = {k: v[:, :nsteps] for k, v in obs.items() if k != 'prev_batch_overlap_res'}     # motion_optimizer.py:590 (overlap weight is 0 in this phase)
             n = nsteps
             w['rgb_overlap_consist'] = 0.0
         loss, st = self.motion_fit(o, pred, cam_pred, p, z, roll['cond_prior'], n, init_motion_scale, w)

@@ -3,7 +3,7 @@ import numpy as np
 from humor_b200 import synth
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass', 'stage3_proxd']
+CASES = ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass', 'stage3_proxd', 'stage3_rgb_xbatch']
 
 
 def load_case(name):
@@ -12,7 +12,9 @@ def load_case(name):
     optim_floor = bool(of)
     prob = synth.make_stage3_problem(B, T, seed=seed, overlap=overlap, cam=optim_floor)
     for k in g:
-        if k.startswith('obs_'):
+        if k.startswith('obs_prevres_'):          # observed_data['prev_batch_overlap_res'] (run_fitting.py:428-435)
+            prob['obs'].setdefault('prev_batch_overlap_res', {})[k[12:]] = g[k]
+        elif k.startswith('obs_'):
             prob['obs'][k[4:]] = g[k]
     W = synth.RGB_STAGE3_WEIGHTS if optim_floor else synth.AMASS_STAGE3_WEIGHTS
     if 'wset' in g:

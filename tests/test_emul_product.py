@@ -68,7 +68,7 @@ def test_stage12_closure_matches_reference_golden(emul, name):
         assert e < 1e-4, (k, e)
 
 
-@pytest.mark.parametrize('name', ['stage3_rgb_phase1',
+@pytest.mark.parametrize('name', ['stage3_rgb_phase1', 'stage3_rgb_xbatch',          # xbatch: prev_batch_overlap_res terms
                                   pytest.param('stage3_proxd', marks=pytest.mark.skipif(not os.environ.get('HB_SLOW_TESTS'),
                                                reason='1 min on the emulation (chamfer at PROX size): set HB_SLOW_TESTS=1'))])
 def test_stage3_closure_matches_reference_golden(emul, name):

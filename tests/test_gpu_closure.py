@@ -111,7 +111,7 @@ def test_motion_optimizer_run_smoke():
 
 
 @pytest.mark.parametrize('precision', ['exact', 'tensor'])
-@pytest.mark.parametrize('name', ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass'])
+@pytest.mark.parametrize('name', ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass', 'stage3_rgb_xbatch'])
 def test_closure_matches_reference_golden(name, precision):
     """CUDA path against fixtures produced by the UNMODIFIED reference in the build container.
     'exact' (fp32 FFMA GEMMs): every gradient within 1e-4 of its scale.  'tensor' (tcgen05 3xTF32): forward states,

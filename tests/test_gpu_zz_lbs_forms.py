@@ -10,13 +10,8 @@ from humor_b200 import synth, _ext
 
 import os
 
-# Round-1 status: both forms are correct on the CPU side (the skin kernel runs through the SIMT shim, the host dispatch
-# through tests/test_host_dispatch.py) but have NOT executed on a B200 yet - the GPU budget of the round ended before the
-# run that would have exercised them (an earlier run fell back to form 1 because of a layout guard and proved nothing).
-# They stay opt-in, and so do these tests: HB_TEST_UNVERIFIED=1 python -m pytest tests/test_gpu_zz_lbs_forms.py
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get('HB_TEST_UNVERIFIED'),
-                                 reason='opt-in kernel forms not yet verified on hardware (set HB_TEST_UNVERIFIED=1)')]
+# First hardware run: round 2, call r02a (profiles/r02a_gpu_tests_ungated.txt): all 18 cases green on the B200.
+pytestmark = pytest.mark.gpu
 
 
 def forms_used():

@@ -10,12 +10,8 @@ import torch
 from humor_b200 import synth
 from tests import util_stage3 as U
 
-# Not yet run on a B200 (the round's GPU budget ended first): 7 L-BFGS iterations amplify rounding-order differences (the CPU
-# emulation rebuilt with FMA contraction moves latent_motion by 2e-4), so the first hardware run is part of
-# tools/gpu_final_check.sh and the test joins the default GPU suite once its tolerances are confirmed there.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get('HB_TEST_UNVERIFIED'),
-                                 reason='end-to-end run() not yet verified on hardware (set HB_TEST_UNVERIFIED=1)')]
+# First hardware run: round 2, call r02a (profiles/r02a_gpu_tests_ungated.txt): green on the B200 with the tolerances below.
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 

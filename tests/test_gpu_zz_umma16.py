@@ -10,10 +10,8 @@ import torch
 
 from humor_b200 import _ext
 
-# new in round 1 and not yet executed on a B200: opt-in until its first hardware run (tools/gpu_final_check.sh)
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get('HB_TEST_UNVERIFIED'),
-                                 reason='fp16 hi/lo GEMM not yet verified on hardware (set HB_TEST_UNVERIFIED=1)')]
+# First hardware run: round 2, call r02a (profiles/r02a_gpu_tests_ungated.txt): green on the B200.
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('M,N,K', [(130, 200, 576), (256, 1024, 1088), (40, 70, 64), (1100, 130, 128), (2048, 1024, 1024)])

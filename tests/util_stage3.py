@@ -12,7 +12,15 @@ def obs_keys(optim_floor, prob=None):
     keys = ('joints2d', 'floor_plane', 'seq_interval') if optim_floor else ('verts3d',)
     if prob is not None and 'points3d' in prob['obs']:
         keys = keys + ('points3d',)          # PROX RGB-D style problems (golden case stage3_proxd)
+    if prob is not None and 'prev_batch_overlap_res' in prob['obs']:
+        keys = keys + ('prev_batch_overlap_res',)          # second batch of a split video (golden case stage3_rgb_xbatch)
     return keys
+
+
+def obs_to(v, device):
+    if isinstance(v, dict):
+        return {a: torch.as_tensor(b).to(device).clone() for a, b in v.items()}
+    return torch.as_tensor(v).to(device).clone()
 
 
 def project_joints2d(prob, cam_joints73, seed=5, noise=2.0):
@@ -37,7 +45,7 @@ def build_port(B, T, weights, optim_floor, prob, dtype=torch.float32, device='cp
 def closure_port(port, prob, optim_floor, nsteps=None, scale=1.0, device='cpu'):
     names = PARAM_NAMES + (['floor_plane'] if optim_floor else [])
     p = {k: torch.as_tensor(prob['params'][k]).to(device).clone().requires_grad_(True) for k in names}
-    obs = {k: torch.as_tensor(v).to(device).clone() for k, v in prob['obs'].items() if k in obs_keys(optim_floor, prob)}
+    obs = {k: obs_to(v, device) for k, v in prob['obs'].items() if k in obs_keys(optim_floor, prob)}
     loss, stats, inter = port.closure(p, obs, nsteps, scale)
     loss.backward()
     return float(loss.detach()), {k: p[k].grad.detach() for k in names}, {'stats': {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in stats.items()}, 'inter': inter}
@@ -64,7 +72,7 @@ def build_product(B, T, weights, optim_floor, prob, device='cuda', contact_refin
 
 def closure_product(mo, prob, nsteps=None, scale=1.0):
     names = mo.set_stage3_state(prob['params'])
-    obs = {k: torch.as_tensor(v).to(mo.device) for k, v in prob['obs'].items() if k in obs_keys(mo.optim_floor, prob)}
+    obs = {k: obs_to(v, mo.device) for k, v in prob['obs'].items() if k in obs_keys(mo.optim_floor, prob)}
     loss, stats, roll, cam, cam_pred = mo.stage3_forward(obs, nsteps, scale)
     loss.backward()
     grads = {n: getattr(mo, n).grad.detach() for n in names}

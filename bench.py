@@ -240,7 +240,7 @@ def run_product(args):
     graphed = bool(mo.use_cuda_graph)
     mo_shard_off = 'seq_interval' not in OBS_KEYS
     roof = lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind)
-    roof['forms'] = {'skin': args.lbs_skin or int(os.environ.get('HB_LBS_SKIN', 1)), 'blend': args.lbs_blend or int(os.environ.get('HB_LBS_BLEND', 1)),
+    roof['forms'] = {'skin': args.lbs_skin or int(os.environ.get('HB_LBS_SKIN', 3)), 'blend': args.lbs_blend or int(os.environ.get('HB_LBS_BLEND', 5)),
                      'slab_frames': args.lbs_slab or int(os.environ.get('HB_LBS_SLAB', 512))}
     shares = kernel_shares(mo, obs, params, dev)
     cpu = torch_cuda = None
@@ -326,8 +326,13 @@ def lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind):
         name = ('dense LBS forward: lbs_pose_kernel + lbs_fuseg_kernel (persistent tcgen05 blend + group skinning' +
                 ({3: ', single-pass pose columns)', 4: ', fp16 pose columns)', 5: ', fp16 hi/lo planes)'}.get(ub.value, ')'))) if us.value == 3 else \
             f'dense LBS forward: lbs_pose_kernel + per slab {blend} + {skin}'
+        traffic, tsrc = None, None
+        if (us.value, ub.value) == (3, 5):
+            # dram__bytes_read.sum + dram__bytes_write.sum of lbs_fuseg_kernel, ncu --set full of one 15 360-frame launch
+            # (364.1 MB read + 1 234.8 MB written; the algorithmic 1 288.6 MB are 94 % output vertices)
+            traffic, tsrc = 1598.9e6 * N / 15360.0, 'profiles/r02a_fuseg35_set_full_details.txt (gpurun_out/r02a_fuseg35_set_full.ncu-rep)'
         return {'kernel': name, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'peak_source': peak_kind, 'unit': 'GB/s',
-                'frac': achieved / hbm_peak, 'traffic': None, 'ms_per_launch': ms, 'frames_per_launch': N,
+                'frac': achieved / hbm_peak, 'traffic': traffic, 'traffic_source': tsrc, 'ms_per_launch': ms, 'frames_per_launch': N,
                 'algorithmic_bytes_per_frame': LBS_BYTES_FWD, 'forms_used': [us.value, ub.value]}
     return {'kernel': 'dense LBS forward: lbs_pose_kernel + per 512-frame slab umma_gemm3_kernel<128,BIAS> (tcgen05 blend) + '
                       'lbs_skin_apply_kernel', 'bound': 'hbm', 'achieved': achieved,

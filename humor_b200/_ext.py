@@ -107,7 +107,7 @@ EXPORTS = ['humor_lbs_workspace_bytes', 'humor_lbs_fwd', 'humor_lbs_bwd', 'humor
            'humor_rollout_fwd', 'humor_rollout_bwd', 'humor_rodrigues_fwd', 'humor_rodrigues_bwd',
            'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version',
            'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd', 'humor_lbs_configure', 'humor_lbs_forms_used',
-           'humor_umma_gemm16', 'humor_umma_gemm16_workspace_bytes']
+           'humor_umma_gemm16', 'humor_umma_gemm16_workspace_bytes', 'humor_chain_debug']
 
 _LIB = None
 
@@ -161,6 +161,8 @@ def lib():
     L.humor_chamfer_fwd.argtypes = [ci, ci, vp, ci, vp, vp, vp, vp, vp, i64p, vp]
     L.humor_chamfer_bwd.restype = ci
     L.humor_chamfer_bwd.argtypes = [ci, ci, vp, ci, vp, vp, vp, vp, vp, vp, vp, i64p, vp]
+    L.humor_chain_debug.restype = ci
+    L.humor_chain_debug.argtypes = [vp, sz]
     L.humor_b200_version.restype = C.c_char_p
     _LIB = L
     return L

@@ -60,5 +60,6 @@ struct ChainLaunch {
   unsigned* flags;          // CH_FLAGS words, zeroed by the launcher
   int B, S, dir;            // dir 0: forward steps 0..S-1; 1: reverse steps S-1..0
 };
+constexpr int CH_DBG_EV = 16;       // humor_chain_debug: clock64 stamps of CTA 0, [step][phase 0..4][CH_DBG_EV]
 
 }  // namespace hb

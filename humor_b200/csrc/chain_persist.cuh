@@ -47,12 +47,29 @@ struct alignas(64) ChainParams {
   ChainGlue glue;
   unsigned* flags;
   int B, S, dir;
+  long long* dbg;          // optional clock64 stamps of CTA 0 (humor_chain_debug), else nullptr
 };
+// stamp event `ev` of (step u, phase ph: GEMM phases 0..3, glue 4) - one thread of CTA 0 only
+#define CH_STAMP(u, ph, ev) do { if (p.dbg && blockIdx.x == 0) p.dbg[((u) * 5 + (ph)) * CH_DBG_EV + (ev)] = hb_clock64(); } while (0)
+
+#ifdef HB_HOST_SHIM
+static inline long long hb_clock64() { return 0; }
+#else
+__device__ __forceinline__ long long hb_clock64() { return clock64(); }
+#endif
 
 #ifdef HB_HOST_SHIM
 using tcemu::cluster_id_x; using tcemu::cluster_nid_x; using tcemu::mbar_arrive_remote; using tcemu::mbar_wait_cluster;
 using tcemu::flag_wait_ge; using tcemu::flag_add_release; using tcemu::fence_proxy_async; using tcemu::epi_bar_sync;
+using tcemu::st_async_v4; using tcemu::fence_gpu;
 #else
+// 16-byte store into another CTA's shared memory that completes 16 transaction bytes on an mbarrier of THAT CTA when it lands:
+// data and signal travel together, no release fence / separate arrival on the critical path
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, float a, float b, float c, float d, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_mbar) : "memory");
+}
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 // arrive on an mbarrier of another CTA of the cluster (address from mapa); orders this thread's earlier DSMEM stores
@@ -71,13 +88,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 }
 // data-flow flags in global memory: monotonic counters, bumped with release, polled with acquire (bounded: a protocol bug traps)
 __device__ __forceinline__ void flag_wait_ge(const unsigned* p, unsigned target) {
+  // poll with relaxed loads (an acquire load invalidates the SM's L1 on EVERY iteration - CCTL.IVALL - under the feet of the
+  // warps that are computing), then one fence: ld.relaxed + fence.acq_rel is an acquire pattern
   const long long t0 = clock64();
   while (true) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     if (v >= target) break;
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void flag_add_release(unsigned* p, unsigned v) {
   asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -114,9 +134,10 @@ chain_kernel(const __grid_constant__ ChainParams p) {
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < CH_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
-    mbar_init(xfull, CH_CS * 32);          // every lane of the sending warp of every CTA (incl. this one)
+    mbar_init(xfull, 1);                   // the receiver's own arrive.expect_tx; the partial slabs arrive as transaction bytes
     mbar_init(xfree, CH_CS);               // one arrival per CTA of the cluster once its slab has been consumed
     mbar_fence_init();
+    mbar_expect_tx(xfull, CH_CS * CH_XROWS * CH_BN * 4);     // tile 0: four slabs of 32 rows x 64 floats
   }
   if (warp == 1) {
     tmem_alloc(tptr, (uint32_t)(2 * CH_BN));
@@ -158,12 +179,15 @@ chain_kernel(const __grid_constant__ ChainParams p) {
               tma_load_2d(st + 2 * CH_A_TILE, b_hi, full0 + 8 * s, kb * UM_BK, n0);            // weights: no dependency
               tma_load_2d(st + 2 * CH_A_TILE + CH_B_TILE, b_lo, full0 + 8 * s, kb * UM_BK, n0);
               const int ptile = (gi > 0 && (kb >> 1) < g.dep_ntn) ? (kb >> 1) : -1;
+              if (kb == kb0) CH_STAMP(u, gi, 0);
               if (ptile != dep_ok) {
                 if (ptile >= 0) flag_wait_ge(chain_tile_flag(flags, gi - 1, mt, ptile), (unsigned)(CH_CS * (u + 1)));
                 else { const unsigned need = glue_need(mt, u); if (need) flag_wait_ge(chain_glue_flag(flags, mt), need); }
                 fence_proxy_async();
                 dep_ok = ptile;
               }
+              if (kb == kb0) CH_STAMP(u, gi, 1);
+              if (kb == kb1 - 1) CH_STAMP(u, gi, 2);
               tma_load_2d(st, a_hi, full0 + 8 * s, g.a_col0 + kb * UM_BK, t * g.a_row_step + m0);
               tma_load_2d(st + CH_A_TILE, a_lo, full0 + 8 * s, g.a_col0 + kb * UM_BK, t * g.a_row_step + m0);
             }
@@ -192,6 +216,8 @@ chain_kernel(const __grid_constant__ ChainParams p) {
                 const int s = it % CH_STAGES;
                 mbar_wait(full0 + 8 * s, (it / CH_STAGES) & 1);
                 tc_fence_after();
+                if (kb == kb0) CH_STAMP(u, gi, 3);
+                if (kb == kb1 - 1) CH_STAMP(u, gi, 4);
                 const uint32_t st = base + s * CH_STAGE;
 #pragma unroll
                 for (int k = 0; k < UM_BK / 8; ++k) {
@@ -220,16 +246,27 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     float* gs = glue_f + ew * GLUE_BWD_SMEM;
     uint32_t ck = 0, tl = 0;
 
+    // Glue rows: with at least two epilogue warps per sub-sequence in the grid (B = 256 on 128 CTAs) a row is split over a warp
+    // PAIR (glue_*_pair: joint rotations | everything else), else one warp takes a row.
+    const bool pairs = 2 * nctas >= B;
+    const int pi = ew >> 1, role = ew & 1;                      // pair of this warp, its role inside the pair
+    float* gsp = glue_f + 2 * pi * GLUE_BWD_SMEM;               // the pair shares the staging arrays of its first warp
     auto run_glue = [&](int u, int t) {
       const ChainGlue& gl = p.glue;
       const ChainGemm& gp = p.g[CH_NGEMM - 1];                  // the phase that feeds the glue in either direction
-      for (int b = ew * nctas + cta; b < B; b += 4 * nctas) {
+      const int b_first = pairs ? pi * nctas + cta : ew * nctas + cta;
+      const int b_step = pairs ? 2 * nctas : 4 * nctas;
+      for (int b = b_first; b < B; b += b_step) {
         const int mt = b / UM_BM;
         const unsigned need = (unsigned)(CH_CS * (dir ? u : u + 1));
-        if (lane == 0 && need) {
+        const bool lead = lane == 0 && (!pairs || role == 0);   // the lane that waits / releases for this row
+        if (lead && ew == 0) CH_STAMP(u, 4, 0);
+        if (lead && need) {
           for (int nt = 0; nt < gp.ntn; ++nt) flag_wait_ge(chain_tile_flag(flags, CH_NGEMM - 1, mt, nt), need);
         }
-        __syncwarp();
+        if (pairs) glue_pair_sync(pi); else __syncwarp();
+        if (lead && ew == 0) CH_STAMP(u, 4, 1);
+        float* gs = pairs ? gsp : glue_f + ew * GLUE_BWD_SMEM;
         const size_t r = (size_t)t * B + b;
         if (!dir) {
           GlueFwdRow io;
@@ -240,7 +277,8 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           io.h1 = gl.h1 + (size_t)b * 1088 + 1024; io.h1_lo = gl.h1_lo + (size_t)b * 1088 + 1024;
           io.h2 = gl.h2 + (size_t)b * 1088 + 1024; io.h2_lo = gl.h2_lo + (size_t)b * 1088 + 1024;
           io.h3 = gl.h3 + (size_t)b * 576 + 512; io.h3_lo = gl.h3_lo + (size_t)b * 576 + 512;
-          glue_fwd_warp<true>(io, lane, gs, gs + 340, gs + 556, gs + 896);
+          if (pairs) glue_fwd_pair<true>(io, role, lane, pi, gs, gs + 340, gs + 556, gs + 896);
+          else glue_fwd_warp<true>(io, lane, gs, gs + 340, gs + 556, gs + 896);
         } else {
           GlueBwdRow io;
           io.xr = gl.xins + r * XIN_LD; io.rr = gl.raws + r * RAW_LD; io.wr = gl.dworld + r * WORLD_LD; io.G = gl.Gs + r * 12;
@@ -250,11 +288,15 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           io.dt2j = gl.dt2j + b * 4; io.dzt = nullptr;
           io.dh1 = io.dh1_lo = io.dh2 = io.dh2_lo = io.dh3 = io.dh3_lo = nullptr;
           io.draw = nullptr; io.draw_hi = gl.bp_hi + r * gl.bp_ld; io.draw_lo = gl.bp_lo + r * gl.bp_ld;
-          glue_bwd_warp<true>(io, lane, gs, gs + 340, gs + 556, gs + 896, gs + 1244, gs + 1584);
+          if (pairs) glue_bwd_pair<true>(io, role, lane, pi, gs, gs + 340, gs + 556, gs + 896, gs + 1244, gs + 1584);
+          else glue_bwd_warp<true>(io, lane, gs, gs + 340, gs + 556, gs + 896, gs + 1244, gs + 1584);
         }
+        if (lead && ew == 0) CH_STAMP(u, 4, 2);
         fence_proxy_async();                                    // this lane's rows -> TMA reads of the consuming GEMM phase
-        __syncwarp();
-        if (lane == 0) flag_add_release(chain_glue_flag(flags, mt), 1u);
+        fence_gpu();                                            // every writer waits for its own stores
+        if (pairs) glue_pair_sync(pi); else __syncwarp();
+        if (lead) flag_add_release(chain_glue_flag(flags, mt), 1u);
+        if (lead && ew == 0) CH_STAMP(u, 4, 3);
       }
     };
 
@@ -287,15 +329,53 @@ chain_kernel(const __grid_constant__ ChainParams p) {
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
           }
           // ---- reduce-scatter of the split-K partials: my quadrant's 32 rows go to CTA q
+          if (et == 0) CH_STAMP(u, gi, 5);
           if (tl > 0) mbar_wait_cluster(xfree, (tl - 1) & 1);   // every CTA of the cluster has consumed its previous slab
+          if (et == 0) CH_STAMP(u, gi, 6);
           {
             const uint32_t dst = map_to_cta(xbuf + (uint32_t)(((int)krank * CH_XROWS + lane) * CH_XLD) * 4u, (uint32_t)q);
+            const uint32_t dbar = map_to_cta(xfull, (uint32_t)q);
 #pragma unroll
-            for (int j = 0; j < CH_BN; j += 4) st_cluster_v4(dst + j * 4, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            mbar_arrive_remote(map_to_cta(xfull, (uint32_t)q));
+            for (int j = 0; j < CH_BN; j += 4) st_async_v4(dst + j * 4, acc[j], acc[j + 1], acc[j + 2], acc[j + 3], dbar);
+          }
+          if (et == 0) CH_STAMP(u, gi, 7);
+          // ---- finalise rows krank*32 .. +31 of the tile: 4 threads per row, 16 columns each.  Everything the epilogue needs from
+          // global memory is requested NOW, under the exchange
+          const int row = m0 + (int)krank * CH_XROWS + fr;
+          const bool rok = row < B;
+          const int col = n0 + cq * 16;
+          const size_t trw = (size_t)t * B + row;               // row of the per-step tapes
+          float cb[16], cg[16], ce[16], xh[16];                 // bias | gamma | beta | saved x-hat (reverse)
+          float rs_saved = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { cb[j] = 0.f; cg[j] = 0.f; ce[j] = 0.f; xh[j] = 0.f; }
+          if (g.epi == EPI_BIAS) {
+            if (g.bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) cb[j] = (col + j < g.N) ? g.bias[col + j] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 g4 = *reinterpret_cast<const float4*>(g.gamma + col + j);
+              const float4 e4 = *reinterpret_cast<const float4*>(g.beta + col + j);
+              cg[j] = g4.x; cg[j + 1] = g4.y; cg[j + 2] = g4.z; cg[j + 3] = g4.w;
+              ce[j] = e4.x; ce[j + 1] = e4.y; ce[j + 2] = e4.z; ce[j + 3] = e4.w;
+              if (g.epi == EPI_GN_RELU) {
+                const float4 b4 = *reinterpret_cast<const float4*>(g.bias + col + j);
+                cb[j] = b4.x; cb[j + 1] = b4.y; cb[j + 2] = b4.z; cb[j + 3] = b4.w;
+              } else if (rok) {
+                const float4 x4 = *reinterpret_cast<const float4*>(g.xhat + trw * g.ldxh + col + j);
+                xh[j] = x4.x; xh[j + 1] = x4.y; xh[j + 2] = x4.z; xh[j + 3] = x4.w;
+              }
+            }
+            if (g.epi == EPI_GN_RELU_BWD && rok) rs_saved = g.rstd[trw * 16 + col / g.gsize];
           }
           mbar_wait_cluster(xfull, tl & 1);
-          // ---- finalise rows krank*32 .. +31 of the tile: 4 threads per row, 16 columns each
+          if (et == 0) {
+            mbar_expect_tx(xfull, CH_CS * CH_XROWS * CH_BN * 4);   // arm the next tile (peers send it only after xfree below)
+            CH_STAMP(u, gi, 8);
+          }
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -308,10 +388,6 @@ chain_kernel(const __grid_constant__ ChainParams p) {
               v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
             }
           }
-          const int row = m0 + (int)krank * CH_XROWS + fr;
-          const bool rok = row < B;
-          const int col = n0 + cq * 16;
-          const size_t trw = (size_t)t * B + row;               // row of the per-step tapes
           const int gl_lanes = (g.gsize == 64) ? 3 : 1;         // xor-shuffle masks that span one GroupNorm group
           auto group_sum = [&](float x) {
             x += __shfl_xor_sync(0xffffffffu, x, 1);
@@ -320,11 +396,11 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           };
           if (g.epi == EPI_BIAS) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += (g.bias && col + j < g.N) ? g.bias[col + j] : 0.f;
+            for (int j = 0; j < 16; ++j) v[j] += cb[j];
           } else if (g.epi == EPI_GN_RELU) {
             float sum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j] += g.bias[col + j]; sum += v[j]; }
+            for (int j = 0; j < 16; ++j) { v[j] += cb[j]; sum += v[j]; }
             const float inv = 1.f / (float)g.gsize;
             const float mean = group_sum(sum) * inv;
             float sq = 0.f;
@@ -339,29 +415,23 @@ chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 xp[e] = (v[j + e] - mean) * rs;
-                v[j + e] = fmaxf(fmaf(g.gamma[col + j + e], xp[e], g.beta[col + j + e]), 0.f);
+                v[j + e] = fmaxf(fmaf(cg[j + e], xp[e], ce[j + e]), 0.f);
               }
               if (rok) *reinterpret_cast<float4*>(g.xhat + trw * g.ldxh + col + j) = xh;
             }
           } else {                                              // EPI_GN_RELU_BWD: every column of these tiles is normalised
-            float xh[16];
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 x4 = rok ? *reinterpret_cast<const float4*>(g.xhat + trw * g.ldxh + col + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              xh[j] = x4.x; xh[j + 1] = x4.y; xh[j + 2] = x4.z; xh[j + 3] = x4.w;
-            }
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float gm = g.gamma[col + j];
-              const bool on = fmaf(gm, xh[j], g.beta[col + j]) > 0.f;
+              const float gm = cg[j];
+              const bool on = fmaf(gm, xh[j], ce[j]) > 0.f;
               const float uu = on ? gm * v[j] : 0.f;
               v[j] = uu;
               s1 += uu;
               s2 += uu * xh[j];
             }
             s1 = group_sum(s1); s2 = group_sum(s2);
-            const float rs = rok ? g.rstd[trw * 16 + col / g.gsize] : 0.f;
+            const float rs = rs_saved;
             const float inv = 1.f / (float)g.gsize;
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = rs * (v[j] - s1 * inv - xh[j] * s2 * inv);
@@ -388,12 +458,16 @@ chain_kernel(const __grid_constant__ ChainParams p) {
               }
             }
           }
+          if (et == 0) CH_STAMP(u, gi, 9);
           fence_proxy_async();                                  // the slab -> TMA reads of the next phase
+          fence_gpu();                                          // every writer waits for ITS stores (in parallel), not one thread for all
           epi_bar_sync();                                       // all 128 epilogue threads: slab read and written
           if (et == 0) {
+            CH_STAMP(u, gi, 10);
+            flag_add_release(chain_tile_flag(flags, gi, mt, nt), 1u);     // consumers first ...
+            CH_STAMP(u, gi, 11);
 #pragma unroll
-            for (uint32_t rk = 0; rk < (uint32_t)CH_CS; ++rk) mbar_arrive_remote(map_to_cta(xfree, rk));
-            flag_add_release(chain_tile_flag(flags, gi, mt, nt), 1u);
+            for (uint32_t rk = 0; rk < (uint32_t)CH_CS; ++rk) mbar_arrive_remote(map_to_cta(xfree, rk));   // ... then the peers' next slab
           }
         }
       }

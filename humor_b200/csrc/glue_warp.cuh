@@ -301,4 +301,251 @@ __device__ __forceinline__ void glue_bwd_warp(const GlueBwdRow& io, int lane, fl
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// TWO warps per row (persistent chain, when the grid has at least two epilogue warps per sub-sequence): the serial instruction
+// stream of one warp is the cost of the glue (3 300 instructions in reverse, ~8.6 clk each with one warp per scheduler), so the
+// row is split by data dependence, not by lanes:
+//   role 1 ("J")  the 21 body-joint rotations R_j = D_j(raw) xin.R_j - Rodrigues + 3x3 products and their reverse - touch no
+//                 root-level quantity: independent of everything role 0 does
+//   role 0 ("R")  root frame (D, R0, Ra), joint positions / velocities (lanes 0..21), root velocities as two more "velocity items"
+//                 (lanes 22, 23: same code path as the joint velocities, no extra divergent branch), translation + running
+//                 transform (lane 24), root-orientation chain (lane 25), the root-level reductions and their serial tail
+// Both roles load the row into the shared staging arrays together (64 lanes) and store the results together; `pair_sync` is a
+// named barrier of the two warps.  Same arithmetic per element as the one-warp functions above; only the order of the
+// root-level warp sums over lanes is unchanged too (role 0 holds every summand).
+// ------------------------------------------------------------------------------------------------------------------------
+#ifdef HB_HOST_SHIM
+static inline void glue_pair_sync(int pi) { shim::sync_pair(pi); }
+#else
+__device__ __forceinline__ void glue_pair_sync(int pi) { asm volatile("bar.sync %0, 64;" ::"r"(2 + pi) : "memory"); }
+#endif
+
+template <bool CG>
+__device__ __forceinline__ void glue_fwd_pair(const GlueFwdRow& io, int role, int lane, int pi, float* sx, float* sr, float* sn, float* sw) {
+  const int l64 = role * 32 + lane;
+  for (int i = l64; i < STATE_D; i += 64) sx[i] = glue_ld<CG>(io.xr + i);
+  for (int i = l64; i < RAW_D; i += 64) sr[i] = glue_ld<CG>(io.rr + i);
+  glue_pair_sync(pi);
+  if (role == 1) {
+    if (lane >= 1 && lane < NJ) {
+      const int j = lane - 1;
+      float Dj[9], Rj[9];
+      rodrigues_fwd(sr + 12 + 3 * j, Dj);
+      mat3_mul(Dj, sx + 18 + 9 * j, Rj);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { sn[18 + 9 * j + e] = Rj[e]; sw[18 + 9 * j + e] = Rj[e]; }
+    }
+  } else {
+    float Gr[9], Gt[3], t2j[3], tr[3], R0[9], D[9], Ra[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Gr[e] = glue_ld<CG>(io.G + e);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { Gt[i] = glue_ld<CG>(io.G + 9 + i); t2j[i] = io.t2j[i]; tr[i] = sx[i] + sr[i]; }
+    rodrigues_fwd(sr + 6, D);
+    mat3_mul(D, sx + 6, R0);
+    w2a_fwd(R0, Ra);
+    const float ta[3] = {-tr[0], -tr[1], 0.f};
+    if (lane < 24) {
+      // velocity items: joint velocities (lanes 0..21), root translation velocity (22), root angular velocity (23)
+      const int xo = lane < NJ ? 273 + 3 * lane : (lane == 22 ? 3 : 15);
+      const int ro = lane < NJ ? 141 + 3 * lane : (lane == 22 ? 3 : 9);
+      float v[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[i] = sx[xo + i] + sr[ro + i];
+      mat3_vec(Ra, v, sn + xo);
+      mat3_tvec(Gr, v, sw + xo);
+      if (lane < NJ) {
+        const int k = lane;
+        float p[3], a[3], o[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { p[i] = sx[207 + 3 * k + i] + sr[75 + 3 * k + i]; a[i] = p[i] + ta[i] + t2j[i]; }
+        mat3_vec(Ra, a, o);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { sn[207 + 3 * k + i] = o[i] - t2j[i]; a[i] = p[i] + t2j[i]; }
+        mat3_tvec(Gr, a, o);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sw[207 + 3 * k + i] = o[i] - t2j[i] - Gt[i];
+        if (k == 0) {
+          mat3_mul(Ra, R0, sn + 6);
+          mat3_mul_tn(Gr, R0, sw + 6);
+        }
+      }
+    } else if (lane == 24) {
+      float u[3] = {tr[0] + ta[0], tr[1] + ta[1], tr[2] + ta[2]};
+      mat3_vec(Ra, u, sn + 0);
+      float wt[3];
+      mat3_tvec(Gr, tr, wt);
+      float gn[12];
+      mat3_mul(Gr, Ra, gn);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { wt[i] -= Gt[i]; sw[i] = wt[i]; }
+      gn[9] = -wt[0]; gn[10] = -wt[1]; gn[11] = 0.f;
+#pragma unroll
+      for (int e = 0; e < 12; ++e) io.gn[e] = gn[e];
+    } else if (lane == 25) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) sw[339 + c] = sr[207 + c];
+    }
+  }
+  glue_pair_sync(pi);
+  for (int i = l64; i < STATE_D; i += 64) {
+    io.xn[i] = sn[i];
+    if (io.xn_lo) glue_put(io.xn_hi, io.xn_lo, i, sn[i]);
+  }
+  for (int i = l64; i < WORLD_LD; i += 64) io.wo[i] = sw[i];
+  if (io.zt) {
+    for (int i = l64; i < 48; i += 64) {
+      const float v = io.zt[i];
+      io.xn[STATE_D + i] = v;
+      if (io.xn_lo) glue_put(io.xn_hi, io.xn_lo, STATE_D + i, v);
+      glue_put(io.h1, io.h1_lo, i, v);
+      glue_put(io.h2, io.h2_lo, i, v);
+      glue_put(io.h3, io.h3_lo, i, v);
+    }
+  }
+}
+
+template <bool CG>
+__device__ __forceinline__ void glue_bwd_pair(const GlueBwdRow& io, int role, int lane, int pi, float* sx, float* sr, float* dn, float* dw,
+                                              float* dx, float* dr) {
+  const int l64 = role * 32 + lane;
+  for (int i = l64; i < STATE_D; i += 64) sx[i] = io.xr[i];
+  for (int i = l64; i < RAW_D; i += 64) sr[i] = io.rr[i];
+  for (int i = l64; i < WORLD_LD; i += 64) dw[i] = io.wr[i];
+  if (io.have_next) {
+    for (int i = l64; i < STATE_D; i += 64) dn[i] = glue_ld<CG>(io.xs + i) + glue_ld<CG>(io.a0 + i) + io.px[i];
+  } else {
+    for (int i = l64; i < STATE_D; i += 64) dn[i] = 0.f;
+  }
+  glue_pair_sync(pi);
+  if (role == 1) {
+    if (lane >= 1 && lane < NJ) {
+      const int j = lane - 1;
+      float Dj[9], dRj[9], dD[9], dRin[9];
+      rodrigues_fwd(sr + 12 + 3 * j, Dj);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { dRj[e] = dn[18 + 9 * j + e] + dw[18 + 9 * j + e]; dD[e] = 0.f; dRin[e] = 0.f; }
+      mat3_mul_bwd(Dj, sx + 18 + 9 * j, dRj, dD, dRin);
+      float daa[3] = {0.f, 0.f, 0.f};
+      rodrigues_bwd(sr + 12 + 3 * j, dD, daa);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) dx[18 + 9 * j + e] = dRin[e];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dr[12 + 3 * j + i] = daa[i];
+    }
+  } else {
+    float Gr[9], Gt[3], t2j[3], tr[3], R0[9], D[9], Ra[9], dGn[12];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Gr[e] = io.G[e];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { Gt[i] = io.G[9 + i]; t2j[i] = io.t2j[i]; tr[i] = sx[i] + sr[i]; }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) dGn[i] = io.have_next ? glue_ld<CG>(io.dGn + i) : 0.f;
+    rodrigues_fwd(sr + 6, D);
+    mat3_mul(D, sx + 6, R0);
+    w2a_fwd(R0, Ra);
+    const float ta[3] = {-tr[0], -tr[1], 0.f};
+    float dRa[9], dGr[9], dGt[3] = {0.f, 0.f, 0.f}, dta[3] = {0.f, 0.f, 0.f}, d2j[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { dRa[e] = 0.f; dGr[e] = 0.f; }
+    float dR0[9], dtr[3] = {0.f, 0.f, 0.f};            // lane 25 / lane 24 private
+#pragma unroll
+    for (int e = 0; e < 9; ++e) dR0[e] = 0.f;
+    (void)Gt;
+    if (lane < 24) {
+      // velocity items (joint velocities 0..21, root translation velocity 22, root angular velocity 23)
+      const int xo = lane < NJ ? 273 + 3 * lane : (lane == 22 ? 3 : 15);
+      const int ro = lane < NJ ? 141 + 3 * lane : (lane == 22 ? 3 : 9);
+      float v[3], dv[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[i] = sx[xo + i] + sr[ro + i];
+      if (lane < NJ) {
+        const int k = lane;
+        float p[3], a[3], dp[3] = {0.f, 0.f, 0.f}, du[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { p[i] = sx[207 + 3 * k + i] + sr[75 + 3 * k + i]; a[i] = p[i] + ta[i] + t2j[i]; }
+        const float* dnj = dn + 207 + 3 * k;
+        const float* dwj = dw + 207 + 3 * k;
+        mv_bwd(Ra, a, dnj, dRa, du);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { dp[i] += du[i]; dta[i] += du[i]; d2j[i] += du[i] - dnj[i]; du[i] = 0.f; a[i] = p[i] + t2j[i]; }
+        mtv_bwd(Gr, a, dwj, dGr, du);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { dp[i] += du[i]; d2j[i] += du[i] - dwj[i]; dGt[i] -= dwj[i]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { dx[207 + 3 * k + i] = dp[i]; dr[75 + 3 * k + i] = dp[i]; }
+      }
+      mv_bwd(Ra, v, dn + xo, dRa, dv);
+      mtv_bwd(Gr, v, dw + xo, dGr, dv);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { dx[xo + i] = dv[i]; dr[ro + i] = dv[i]; }
+    } else if (lane == 24) {
+      float dwt[3] = {dw[0] - dGn[9], dw[1] - dGn[10], dw[2]};
+      mtv_bwd(Gr, tr, dwt, dGr, dtr);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dGt[i] -= dwt[i];
+      float u[3] = {tr[0] + ta[0], tr[1] + ta[1], tr[2] + ta[2]};
+      float du[3] = {0.f, 0.f, 0.f};
+      mv_bwd(Ra, u, dn + 0, dRa, du);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { dtr[i] += du[i]; dta[i] += du[i]; }
+    } else if (lane == 25) {
+      mat3_mul_bwd(Gr, Ra, dGn, dGr, dRa);                 // Gnext = Gr Ra
+      const float* dW = dw + 6;                            // world.R0 = Gr^T R0
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float a = 0.f, bb = 0.f;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { a += R0[i * 3 + k] * dW[j * 3 + k]; bb += Gr[i * 3 + k] * dW[k * 3 + j]; }
+          dGr[i * 3 + j] += a;
+          dR0[i * 3 + j] += bb;
+        }
+      mat3_mul_bwd(Ra, R0, dn + 6, dRa, dR0);              // next.R0 = Ra R0
+#pragma unroll
+      for (int c = 0; c < 9; ++c) dr[207 + c] = dw[339 + c];
+      for (int c = RAW_D; c < RAW_LD; ++c) dr[c] = 0.f;
+    }
+    // ---- warp totals (every lane receives them)
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { dRa[e] = glue_warp_sum(dRa[e]); dGr[e] = glue_warp_sum(dGr[e]); }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { dGt[i] = glue_warp_sum(dGt[i]); dta[i] = glue_warp_sum(dta[i]); d2j[i] = glue_warp_sum(d2j[i]); }
+    if (lane == 25) {
+      w2a_bwd(R0, dRa, dR0);                               // Ra = w2a(R0)
+      float dD[9], dRin[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { dD[e] = 0.f; dRin[e] = 0.f; }
+      mat3_mul_bwd(D, sx + 6, dR0, dD, dRin);              // R0 = D xin.R0
+      float daa[3] = {0.f, 0.f, 0.f};
+      rodrigues_bwd(sr + 6, dD, daa);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) dx[6 + e] = dRin[e];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dr[6 + i] = daa[i];
+    } else if (lane == 24) {
+      dtr[0] -= dta[0];                                    // ta = (-tr.x, -tr.y, 0)
+      dtr[1] -= dta[1];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { dx[i] = dtr[i]; dr[i] = dtr[i]; }
+    } else if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) io.dG[e] = dGr[e];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        io.dG[9 + i] = dGt[i];
+        io.dt2j[i] = (io.have_next ? glue_ld<CG>(io.dt2j + i) : 0.f) + d2j[i];
+      }
+    }
+  }
+  glue_pair_sync(pi);
+  for (int i = l64; i < STATE_D; i += 64) io.xs[i] = dx[i];
+  for (int i = l64; i < RAW_LD; i += 64) {
+    if (io.draw) io.draw[i] = dr[i];
+    if (io.draw_lo) glue_put(io.draw_hi, io.draw_lo, i, dr[i]);
+  }
+}
+
 }  // namespace hb
+

@@ -674,12 +674,16 @@ __global__ void lbs_pose_bwd_kernel(HbLbsModel m, int N, int fpb, const float* _
 
 static const bool g_thread_pose = (getenv("HB_LBS_THREAD") != nullptr);
 static const bool g_unfused = (getenv("HB_LBS_UNFUSED") != nullptr);
-// dense skinning pass: 1 = lane-per-vertex (lbs_skin_apply_kernel), 2 = lane-per-frame over vertex groups (lbs_skin_group.cuh)
-static int g_skin_form = getenv("HB_LBS_SKIN") ? atoi(getenv("HB_LBS_SKIN")) : 1;
+// dense skinning pass: 1 = lane-per-vertex (lbs_skin_apply_kernel), 2 = lane-per-frame over vertex groups (lbs_skin_group.cuh),
+// 3 (DEFAULT since round 2: 1.49 ms vs 3.35 ms per 15 360 frames on the B200, profiles/r02a_bench_s3b5.json) = blend GEMM + group
+// skinning fused in one persistent tcgen05 kernel (lbs_fuseg.cuh)
+static int g_skin_form = getenv("HB_LBS_SKIN") ? atoi(getenv("HB_LBS_SKIN")) : 3;
 static int g_sm_count = 0;
 static int g_used_skin = 0, g_used_blend = 0;   // forms the last dense tensor-core call actually ran (0: none yet)
-// blend GEMM of the dense forward: 1 = one 128x128 tile per CTA (umma_gemm3_kernel), 2 = persistent 128x256 tiles (lbs_blend.cuh)
-static int g_blend_form = getenv("HB_LBS_BLEND") ? atoi(getenv("HB_LBS_BLEND")) : 1;
+// blend GEMM of the dense forward: 1 = one 128x128 tile per CTA (umma_gemm3_kernel), 2 = persistent 128x256 tiles (lbs_blend.cuh);
+// with skin form 3: 5 (DEFAULT) = fp16 hi + lo operand planes, three products per k-block - the accuracy of three TF32 passes
+// (vertices within 5e-6 m of form 1) from 4-byte operand elements
+static int g_blend_form = getenv("HB_LBS_BLEND") ? atoi(getenv("HB_LBS_BLEND")) : 5;
 static int g_slab = getenv("HB_LBS_SLAB") ? atoi(getenv("HB_LBS_SLAB")) : 0;
 static const size_t SKIN_FWD_SMEM = (size_t)SK_FT * LBS_KF * sizeof(float);
 static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + BW_FT * 624) * sizeof(float);

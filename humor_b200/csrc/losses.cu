@@ -338,69 +338,81 @@ __global__ void fit_reduce_kernel(HbFitArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// GMM negative log-likelihood: one block per row; warp-per-component Mahalanobis via Linv (lower)
+// GMM negative log-likelihood (init_motion_prior_loss, fitting_loss.py:504-518) and its gradient.
+// One block per GMM_RT = 8 rows, one warp per row.  For every component the lower-triangular Linv_k (D x D, 76 KB at D = 138) is
+// staged in shared memory ONCE per block with coalesced loads and serves all 8 rows in both passes (round 1 read it row-per-lane
+// straight from global memory, one block per row: 684 us per call in situ, profiles/r02b_profile_step.txt):
+//   pass 1   y_k = Linv_k (x - mu_k) (lane = output row i, conflict-light row reads), maha_k = |y_k|^2, y kept in shared memory
+//   LSE      per row over the K components -> nll, responsibilities
+//   pass 2   d nll / dx = sum_k resp_k Linv_k^T y_k (thread = column, conflict-free column reads; 8 row accumulators)
 // ------------------------------------------------------------------------------------------------
-constexpr int GMM_MAXD = 160, GMM_MAXK = 32;
-__global__ void __launch_bounds__(256) gmm_nll_kernel(int D, int K, const float* __restrict__ x, const float* __restrict__ logw,
+constexpr int GMM_MAXD = 160, GMM_MAXK = 32, GMM_RT = 8;
+static inline size_t gmm_smem_bytes(int D, int K) { return ((size_t)D * D + (size_t)K * GMM_RT * D + (size_t)GMM_RT * D) * sizeof(float); }
+__global__ void __launch_bounds__(256) gmm_nll_kernel(int B, int D, int K, const float* __restrict__ x, const float* __restrict__ logw,
                                                        const float* __restrict__ mean, const float* __restrict__ Linv,
                                                        const float* __restrict__ logdet, float* nll, float* dx) {
-  __shared__ float xs[GMM_MAXD];
-  __shared__ float ys[8][GMM_MAXD];
-  __shared__ float lp[GMM_MAXK];
-  __shared__ float resp[GMM_MAXK];
-  const int b = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < D; i += 256) xs[i] = x[(size_t)b * D + i];
-  __syncthreads();
-  // pass 1: log p_k
-  for (int k = w; k < K; k += 8) {
+  HB_DYN_SMEM_F32(sm);
+  float* Ls = sm;                                   // [D][D]
+  float* ys = Ls + (size_t)D * D;                   // [K][GMM_RT][D]
+  float* xs = ys + (size_t)K * GMM_RT * D;          // [GMM_RT][D]
+  __shared__ float lp[GMM_RT][GMM_MAXK];
+  __shared__ float resp[GMM_RT][GMM_MAXK];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int b0 = blockIdx.x * GMM_RT;
+  const int nr = min(GMM_RT, B - b0);
+  for (int i = tid; i < GMM_RT * D; i += 256) { const int r = i / D; xs[i] = r < nr ? x[(size_t)(b0 + r) * D + (i - r * D)] : 0.f; }
+  // pass 1
+  for (int k = 0; k < K; ++k) {
+    __syncthreads();                                // xs ready (k = 0) / previous component's reads of Ls done
     const float* L = Linv + (size_t)k * D * D;
+    for (int i = tid; i < D * D; i += 256) Ls[i] = L[i];
+    __syncthreads();
     const float* mu = mean + (size_t)k * D;
     float maha = 0.f;
     for (int i = lane; i < D; i += 32) {
       float y = 0.f;
-      for (int j = 0; j <= i; ++j) y = fmaf(L[(size_t)i * D + j], xs[j] - mu[j], y);
+      for (int j = 0; j <= i; ++j) y = fmaf(Ls[i * D + j], xs[w * D + j] - mu[j], y);
+      ys[((size_t)k * GMM_RT + w) * D + i] = y;
       maha += y * y;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maha += __shfl_xor_sync(0xffffffffu, maha, o);
-    if (lane == 0) lp[k] = logw[k] - 0.5f * ((float)D * 1.8378770664093453f + maha) - logdet[k];
+    if (lane == 0) lp[w][k] = logw[k] - 0.5f * ((float)D * 1.8378770664093453f + maha) - logdet[k];
   }
   __syncthreads();
-  if (tid == 0) {
+  if (lane == 0) {                                  // one thread per row
     float mx = -INFINITY;
-    for (int k = 0; k < K; ++k) mx = fmaxf(mx, lp[k]);
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, lp[w][k]);
     float se = 0.f;
-    for (int k = 0; k < K; ++k) se += expf(lp[k] - mx);
+    for (int k = 0; k < K; ++k) se += expf(lp[w][k] - mx);
     const float lse = mx + logf(se);
-    nll[b] = -lse;
-    for (int k = 0; k < K; ++k) resp[k] = expf(lp[k] - lse);
+    if (w < nr) nll[b0 + w] = -lse;
+    for (int k = 0; k < K; ++k) resp[w][k] = expf(lp[w][k] - lse);
   }
-  __syncthreads();
-  // pass 2: d nll / dx = sum_k resp_k * Sigma_k^{-1} (x - mu_k) = sum_k resp_k * Linv_k^T (Linv_k (x-mu_k))
-  float g = 0.f;                                    // thread tid < D owns dx[tid]
-  for (int k0 = 0; k0 < K; k0 += 8) {
-    const int k = k0 + w;
-    if (k < K) {
-      const float* L = Linv + (size_t)k * D * D;
-      const float* mu = mean + (size_t)k * D;
-      for (int i = lane; i < D; i += 32) {
-        float y = 0.f;
-        for (int j = 0; j <= i; ++j) y = fmaf(L[(size_t)i * D + j], xs[j] - mu[j], y);
-        ys[w][i] = y;
-      }
-    }
+  // pass 2: thread tid < D owns column tid of every row of the block
+  float g[GMM_RT];
+#pragma unroll
+  for (int r = 0; r < GMM_RT; ++r) g[r] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    __syncthreads();                                // resp ready (k = 0) / previous component's reads of Ls done
+    const float* L = Linv + (size_t)k * D * D;
+    for (int i = tid; i < D * D; i += 256) Ls[i] = L[i];
     __syncthreads();
     if (tid < D) {
-      for (int kk = 0; kk < 8 && k0 + kk < K; ++kk) {
-        const float* L = Linv + (size_t)(k0 + kk) * D * D;
-        float acc = 0.f;
-        for (int i = tid; i < D; ++i) acc = fmaf(L[(size_t)i * D + tid], ys[kk][i], acc);
-        g = fmaf(resp[k0 + kk], acc, g);
+      float acc[GMM_RT];
+#pragma unroll
+      for (int r = 0; r < GMM_RT; ++r) acc[r] = 0.f;
+      for (int i = tid; i < D; ++i) {
+        const float l = Ls[i * D + tid];
+#pragma unroll
+        for (int r = 0; r < GMM_RT; ++r) acc[r] = fmaf(l, ys[((size_t)k * GMM_RT + r) * D + i], acc[r]);
       }
+#pragma unroll
+      for (int r = 0; r < GMM_RT; ++r) g[r] = fmaf(resp[r][k], acc[r], g[r]);
     }
-    __syncthreads();
   }
-  if (tid < D) dx[(size_t)b * D + tid] = g;
+  if (tid < D)
+    for (int r = 0; r < nr; ++r) dx[(size_t)(b0 + r) * D + tid] = g[r];
 }
 
 }  // namespace hb
@@ -424,7 +436,14 @@ extern "C" int humor_gmm_nll(int B, int D, int K, const float* x, const float* l
                              const float* logdet, float* nll, float* d_x, cudaStream_t st) {
   if (B <= 0 || D <= 0 || D > GMM_MAXD || K <= 0 || K > GMM_MAXK || !x || !logw || !mean || !Linv || !logdet || !nll || !d_x)
     return HB_ERR_ARG;
-  gmm_nll_kernel<<<B, 256, 0, st>>>(D, K, x, logw, mean, Linv, logdet, nll, d_x);
+  static size_t granted = 0;
+  const size_t need = gmm_smem_bytes(D, K);     // 134 KB at D = 138, K = 12: Linv_k + K * 8 rows of y + 8 rows of x
+  if (need > 227 * 1024) return HB_ERR_ARG;
+  if (need > granted) {
+    HB_CUDA(cudaFuncSetAttribute(gmm_nll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    granted = need;
+  }
+  gmm_nll_kernel<<<cdiv(B, GMM_RT), 256, gmm_smem_bytes(D, K), st>>>(B, D, K, x, logw, mean, Linv, logdet, nll, d_x);
   HB_LAUNCH_CHECK();
   return HB_OK;
 }

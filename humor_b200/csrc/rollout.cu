@@ -316,6 +316,11 @@ static cudaError_t chain_backward(const HbHumorWeights* w, const Tape& tp, int B
   return launch_chain(a, st);
 }
 
+extern "C" int humor_chain_debug(void* buf, size_t bytes) {
+  chain_set_debug(static_cast<long long*>(buf), bytes);
+  return HB_OK;
+}
+
 extern "C" size_t humor_rollout_workspace_bytes(int B, int S) { return carve(nullptr, B, S).total * sizeof(float); }
 
 extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const float* init_state, const float* z_seq,

@@ -296,6 +296,9 @@ cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const 
 // persistent decoder chain (chain_persist.cuh): one launch per direction.  Clusters resident at once are bounded by what the
 // device can co-schedule (cudaOccupancyMaxActiveClusters): the kernel's data-flow flags need every launched cluster running.
 static int g_chain_clusters = 0;        // 0: not yet queried
+static long long* g_chain_dbg = nullptr;   // humor_chain_debug: per-phase clock stamps of CTA 0 for tools/chain_timeline.py
+static size_t g_chain_dbg_bytes = 0;
+void chain_set_debug(long long* buf, size_t bytes) { g_chain_dbg = buf; g_chain_dbg_bytes = bytes; }
 int chain_max_clusters() { return g_chain_clusters; }
 cudaError_t launch_chain(const ChainLaunch& a, cudaStream_t st) {
   if (!load_encode()) return cudaErrorNotSupported;
@@ -332,6 +335,7 @@ cudaError_t launch_chain(const ChainLaunch& a, cudaStream_t st) {
     if (a.g[i].ntn < 1 || a.g[i].ntn > CH_MAX_NT || a.g[i].nkb < 1 || (a.g[i].gsize != 64 && a.g[i].gsize != 32)) return cudaErrorInvalidValue;
   }
   p.glue = a.glue; p.flags = a.flags; p.B = a.B; p.S = a.S; p.dir = a.dir;
+  p.dbg = (g_chain_dbg && g_chain_dbg_bytes >= (size_t)a.S * 5 * CH_DBG_EV * sizeof(long long)) ? g_chain_dbg : nullptr;
   cudaError_t e = cudaMemsetAsync(a.flags, 0, CH_FLAGS * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};

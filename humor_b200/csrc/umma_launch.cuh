@@ -17,6 +17,7 @@ bool umma_available();
 // persistent decoder chain (chain_persist.cuh): S steps of one direction in one launch; zeroes a.flags on the stream first
 cudaError_t launch_chain(const ChainLaunch& a, cudaStream_t st);
 int chain_max_clusters();
+void chain_set_debug(long long* buf, size_t bytes);
 // fp16 hi/lo operand planes (umma_gemm16.cuh): 4 bytes per operand element instead of 8; planes [rows][ld] halves
 // outputs: C (fp32, nullable) and/or the fp16 hi/lo planes of the result (ld16 halves per row, nullable); epi = EPI_BIAS | EPI_GN_RELU
 cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const void* B_h, const void* B_l, int ldb, int M, int N, int K,

@@ -182,6 +182,9 @@ size_t humor_rollout_workspace_bytes(int B, int S);
 int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const float* init_state, const float* z_seq,
                       float* workspace, size_t workspace_bytes, float* world, float* prior_out,
                       int64_t* launches, hb_stream_t stream);
+/* Diagnostics of the persistent decoder chain (csrc/chain_persist.cuh): when `buf` (device, >= S*5*16 int64) is set, the next
+ * rollout launches record clock64 stamps of CTA 0 per step and phase (tools/chain_timeline.py); NULL switches it off. */
+int humor_chain_debug(void* buf, size_t bytes);
 /* BPTT through the rollout: d_world [S][B][348], d_prior_out [S][B][96] (nullable) ->
  * d_init [B][339], d_z [B][S][48].  Must follow humor_rollout_fwd on the same workspace. */
 int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* workspace, size_t workspace_bytes,

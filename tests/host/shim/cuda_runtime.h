@@ -47,6 +47,7 @@ struct Cta {
   std::vector<std::unique_ptr<std::barrier<>>> warp_bars;
   std::vector<uint32_t> warp_xchg;         // one slot per thread: shuffle exchange area
   std::unique_ptr<std::barrier<>> epi_bar; // named barrier of threads 64.. (bar.sync 1, nt - 64)
+  std::unique_ptr<std::barrier<>> pair_bar[2];   // named barriers of warp pairs (2, 3) and (4, 5): bar.sync 2 + i, 64
 };
 inline thread_local uint3 t_idx{0, 0, 0};
 inline thread_local uint3 t_bidx{0, 0, 0};
@@ -62,6 +63,7 @@ inline float* dyn_smem_f32() { return dyn_smem_buf; }
 inline void sync_block() { t_cta->bar->arrive_and_wait(); }
 inline void sync_warp() { t_cta->warp_bars[t_lin / 32]->arrive_and_wait(); }
 inline void sync_cluster() { t_cluster_bar->arrive_and_wait(); }
+inline void sync_pair(int pi) { t_cta->pair_bar[pi]->arrive_and_wait(); }
 
 // Runs `body` once per thread of every block of the grid; `csize` consecutive blocks along x form a cluster and run together.
 // concurrent = true: ALL clusters of a 1-D grid run at once (persistent kernels whose clusters wait on each other through
@@ -78,6 +80,7 @@ void launch_cluster(dim3 grid, dim3 block, unsigned csize, F body, bool concurre
       for (int w = 0; w < (nt + 31) / 32; ++w) c.warp_bars.emplace_back(new std::barrier<>(std::min(32, nt - 32 * w)));
       c.warp_xchg.assign(nt, 0u);
       if (nt > 64) c.epi_bar.reset(new std::barrier<>(nt - 64));
+      if (nt >= 192) { c.pair_bar[0].reset(new std::barrier<>(64)); c.pair_bar[1].reset(new std::barrier<>(64)); }
     }
   };
   if (concurrent) {

@@ -282,6 +282,17 @@ inline void mbar_arrive_remote(uint32_t addr) {                  // addr from ma
   complete_if_done(b);
 }
 inline void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+// st.async ... mbarrier::complete_tx::bytes.v4: 16 bytes into a peer's window + 16 transaction bytes on the peer's barrier
+inline void st_async_v4(uint32_t addr, float a, float b, float c, float d, uint32_t mbar) {
+  st_cluster_v4(addr, a, b, c, d);
+  const uint32_t r = mbar >> RANK_SHIFT, off = mbar & ((1u << RANK_SHIFT) - 1u);
+  if (r == 0 || r > (uint32_t)MAX_CTAS || r != (addr >> RANK_SHIFT)) { std::fprintf(stderr, "tcemu: st.async barrier %u is not in the destination CTA of %u\n", mbar, addr); std::abort(); }
+  std::lock_guard<std::mutex> l(g_mu);
+  Bar& bb = g_cta[r - 1].bars.at(off);
+  bb.tx -= 16;
+  complete_if_done(bb);
+}
+inline void fence_gpu() {}
 inline void flag_wait_ge(const unsigned* p, unsigned target) {
   const auto t0 = std::chrono::steady_clock::now();
   while (__atomic_load_n(p, __ATOMIC_ACQUIRE) < target) {

@@ -61,7 +61,7 @@ __device__ __forceinline__ long long hb_clock64() { return clock64(); }
 #ifdef HB_HOST_SHIM
 using tcemu::cluster_id_x; using tcemu::cluster_nid_x; using tcemu::mbar_arrive_remote; using tcemu::mbar_wait_cluster;
 using tcemu::flag_wait_ge; using tcemu::flag_add_release; using tcemu::fence_proxy_async; using tcemu::epi_bar_sync;
-using tcemu::st_async_v4; using tcemu::fence_gpu;
+using tcemu::st_async_v4; using tcemu::fence_gpu; using tcemu::bulk_g2s;
 #else
 // 16-byte store into another CTA's shared memory that completes 16 transaction bytes on an mbarrier of THAT CTA when it lands:
 // data and signal travel together, no release fence / separate arrival on the critical path
@@ -70,6 +70,11 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, float a, floa
                ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_mbar) : "memory");
 }
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// 1-D bulk copy global -> this CTA's shared memory, completing `bytes` on an mbarrier (addresses and size multiples of 16)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 // arrive on an mbarrier of another CTA of the cluster (address from mapa); orders this thread's earlier DSMEM stores
@@ -88,16 +93,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 }
 // data-flow flags in global memory: monotonic counters, bumped with release, polled with acquire (bounded: a protocol bug traps)
 __device__ __forceinline__ void flag_wait_ge(const unsigned* p, unsigned target) {
-  // poll with relaxed loads (an acquire load invalidates the SM's L1 on EVERY iteration - CCTL.IVALL - under the feet of the
-  // warps that are computing), then one fence: ld.relaxed + fence.acq_rel is an acquire pattern
+  // (measured on the B200, profiles/r02d-e: polling with ld.relaxed + one fence.acq_rel afterwards hands over 0.2 us LATER
+  // than acquire loads - the fence costs more than the per-iteration L1 invalidation saves)
   const long long t0 = clock64();
   while (true) {
     unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     if (v >= target) break;
     if (clock64() - t0 > 4000000000LL) __trap();
   }
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void flag_add_release(unsigned* p, unsigned v) {
   asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -121,7 +125,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
   const uint32_t glue_s = xbuf + CH_XBUF;
   const uint32_t bars = glue_s + CH_GLUE;
   const uint32_t full0 = bars, empty0 = bars + 8 * CH_STAGES, tfull0 = bars + 16 * CH_STAGES, tempty0 = tfull0 + 16,
-                 xfull = tempty0 + 16, xfree = xfull + 8, tptr = xfree + 8;
+                 xfull = tempty0 + 16, xfree = xfull + 8, tptr = xfree + 8, gbar0 = tptr + 8;
   float* glue_f = reinterpret_cast<float*>(smem_raw + (glue_s - raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t krank = cluster_ctarank();
@@ -136,6 +140,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
     mbar_init(xfull, 1);                   // the receiver's own arrive.expect_tx; the partial slabs arrive as transaction bytes
     mbar_init(xfree, CH_CS);               // one arrival per CTA of the cluster once its slab has been consumed
+    for (int i = 0; i < 4; ++i) mbar_init(gbar0 + 8 * i, 1);   // reverse glue: tape rows of the next step prefetched into the staging arrays
     mbar_fence_init();
     mbar_expect_tx(xfull, CH_CS * CH_XROWS * CH_BN * 4);     // tile 0: four slabs of 32 rows x 64 floats
   }
@@ -243,7 +248,6 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     const int et = threadIdx.x - 64;                           // 0..127
     const int fr = et >> 2, cq = et & 3;                       // finalise: row inside this CTA's slab, 16-column quarter
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* gs = glue_f + ew * GLUE_BWD_SMEM;
     uint32_t ck = 0, tl = 0;
 
     // Glue rows: with at least two epilogue warps per sub-sequence in the grid (B = 256 on 128 CTAs) a row is split over a warp
@@ -251,22 +255,40 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     const bool pairs = 2 * nctas >= B;
     const int pi = ew >> 1, role = ew & 1;                      // pair of this warp, its role inside the pair
     float* gsp = glue_f + 2 * pi * GLUE_BWD_SMEM;               // the pair shares the staging arrays of its first warp
+    const int b_first = pairs ? pi * nctas + cta : ew * nctas + cta;
+    const int b_step = pairs ? 2 * nctas : 4 * nctas;
+    const bool lead = lane == 0 && (!pairs || role == 0);     // the lane that waits / releases / prefetches for this warp's rows
+    float* const gs = pairs ? gsp : glue_f + ew * GLUE_BWD_SMEM;
+    // Reverse glue: xin / raw / d world / G rows of a step come from the forward tape in HBM (~2 us of load latency on the
+    // recurrence, measured: profiles/r02d).  With one row per warp (pair) and step they are known a whole step ahead: the lead lane
+    // bulk-copies the NEXT step's rows into the staging arrays as soon as this step's row is done.
+    const bool prefetch = dir && b_first < B && b_first + b_step >= B;
+    const uint32_t gbar = gbar0 + 8 * (pairs ? pi : ew);
+    const uint32_t gs_s = glue_s + (uint32_t)((pairs ? 2 * pi : ew) * GLUE_BWD_SMEM) * 4u;
+    auto prefetch_rows = [&](int t) {                            // lead lane only
+      const ChainGlue& gl = p.glue;
+      const size_t r = (size_t)t * B + b_first;
+      fence_proxy_async();                                       // generic reads / writes of the staging arrays -> async-proxy writes
+      mbar_expect_tx(gbar, (340 + RAW_D + WORLD_LD + 12) * 4);
+      bulk_g2s(gs_s, gl.xins + r * XIN_LD, 340 * 4, gbar);
+      bulk_g2s(gs_s + 340 * 4, gl.raws + r * RAW_LD, RAW_D * 4, gbar);
+      bulk_g2s(gs_s + 896 * 4, gl.dworld + r * WORLD_LD, WORLD_LD * 4, gbar);
+      bulk_g2s(gs_s + 1808 * 4, gl.Gs + r * 12, 12 * 4, gbar);
+    };
+    if (prefetch && lead) prefetch_rows(S - 1);
     auto run_glue = [&](int u, int t) {
       const ChainGlue& gl = p.glue;
       const ChainGemm& gp = p.g[CH_NGEMM - 1];                  // the phase that feeds the glue in either direction
-      const int b_first = pairs ? pi * nctas + cta : ew * nctas + cta;
-      const int b_step = pairs ? 2 * nctas : 4 * nctas;
       for (int b = b_first; b < B; b += b_step) {
         const int mt = b / UM_BM;
         const unsigned need = (unsigned)(CH_CS * (dir ? u : u + 1));
-        const bool lead = lane == 0 && (!pairs || role == 0);   // the lane that waits / releases for this row
         if (lead && ew == 0) CH_STAMP(u, 4, 0);
         if (lead && need) {
           for (int nt = 0; nt < gp.ntn; ++nt) flag_wait_ge(chain_tile_flag(flags, CH_NGEMM - 1, mt, nt), need);
         }
+        if (lead && prefetch) mbar_wait(gbar, u & 1);           // landed long ago
         if (pairs) glue_pair_sync(pi); else __syncwarp();
         if (lead && ew == 0) CH_STAMP(u, 4, 1);
-        float* gs = pairs ? gsp : glue_f + ew * GLUE_BWD_SMEM;
         const size_t r = (size_t)t * B + b;
         if (!dir) {
           GlueFwdRow io;
@@ -281,7 +303,8 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           else glue_fwd_warp<true>(io, lane, gs, gs + 340, gs + 556, gs + 896);
         } else {
           GlueBwdRow io;
-          io.xr = gl.xins + r * XIN_LD; io.rr = gl.raws + r * RAW_LD; io.wr = gl.dworld + r * WORLD_LD; io.G = gl.Gs + r * 12;
+          io.xr = gl.xins + r * XIN_LD; io.rr = gl.raws + r * RAW_LD; io.wr = gl.dworld + r * WORLD_LD;
+          io.G = prefetch ? gs + 1808 : gl.Gs + r * 12; io.staged = prefetch ? 1 : 0;
           io.t2j = gl.t2j + b * 4; io.have_next = u > 0;
           io.a0 = gl.da0 + (size_t)b * XIN_LD; io.px = gl.dpx + (r + B) * 352; io.xs = gl.dxres + (size_t)b * 340;
           io.dGn = ((t + 1) & 1 ? gl.dG1 : gl.dG0) + (size_t)b * 12; io.dG = (t & 1 ? gl.dG1 : gl.dG0) + (size_t)b * 12;
@@ -293,10 +316,10 @@ chain_kernel(const __grid_constant__ ChainParams p) {
         }
         if (lead && ew == 0) CH_STAMP(u, 4, 2);
         fence_proxy_async();                                    // this lane's rows -> TMA reads of the consuming GEMM phase
-        fence_gpu();                                            // every writer waits for its own stores
         if (pairs) glue_pair_sync(pi); else __syncwarp();
         if (lead) flag_add_release(chain_glue_flag(flags, mt), 1u);
         if (lead && ew == 0) CH_STAMP(u, 4, 3);
+        if (lead && prefetch && u + 1 < S) prefetch_rows(t - 1);
       }
     };
 

@@ -30,7 +30,7 @@ __device__ __forceinline__ float glue_warp_sum(float v) {
 }
 
 constexpr int GLUE_FWD_SMEM = 340 + 216 + 340 + 348;              // floats per warp
-constexpr int GLUE_BWD_SMEM = 340 + 216 + 340 + 348 + 340 + 224;
+constexpr int GLUE_BWD_SMEM = 340 + 216 + 340 + 348 + 340 + 224 + 16;   // + the step's G when the tape rows are prefetched
 
 struct GlueFwdRow {                 // every pointer addresses THIS row
   const float* xr;                  // xin [339]
@@ -136,6 +136,7 @@ struct GlueBwdRow {                 // every pointer addresses THIS row
   const float* G;                   // [12]
   const float* t2j;                 // [3]
   int have_next;                    // gradients from step t+1 exist
+  int staged;                       // 1: xin / raw / d world rows are in the staging arrays already (prefetched), do not load them
   const float* a0;                  // d xin of step t+1 from the decoder's first layer [>= 339 (+48 z when dzt)]
   const float* px;                  // d xin of step t+1 from the prior [352]
   float* xs;                        // in: d xin residual path of step t+1 [340]; out: that of this step
@@ -151,9 +152,11 @@ struct GlueBwdRow {                 // every pointer addresses THIS row
 template <bool CG>
 __device__ __forceinline__ void glue_bwd_warp(const GlueBwdRow& io, int lane, float* sx, float* sr, float* dn, float* dw, float* dx,
                                               float* dr) {
-  for (int i = lane; i < STATE_D; i += 32) sx[i] = io.xr[i];          // forward tape: written by an earlier launch
-  for (int i = lane; i < RAW_D; i += 32) sr[i] = io.rr[i];
-  for (int i = lane; i < WORLD_LD; i += 32) dw[i] = io.wr[i];
+  if (!io.staged) {
+    for (int i = lane; i < STATE_D; i += 32) sx[i] = io.xr[i];          // forward tape: written by an earlier launch
+    for (int i = lane; i < RAW_D; i += 32) sr[i] = io.rr[i];
+    for (int i = lane; i < WORLD_LD; i += 32) dw[i] = io.wr[i];
+  }
   if (io.have_next) {
     for (int i = lane; i < STATE_D; i += 32) dn[i] = glue_ld<CG>(io.xs + i) + glue_ld<CG>(io.a0 + i) + io.px[i];
     if (io.dzt)
@@ -409,9 +412,11 @@ template <bool CG>
 __device__ __forceinline__ void glue_bwd_pair(const GlueBwdRow& io, int role, int lane, int pi, float* sx, float* sr, float* dn, float* dw,
                                               float* dx, float* dr) {
   const int l64 = role * 32 + lane;
-  for (int i = l64; i < STATE_D; i += 64) sx[i] = io.xr[i];
-  for (int i = l64; i < RAW_D; i += 64) sr[i] = io.rr[i];
-  for (int i = l64; i < WORLD_LD; i += 64) dw[i] = io.wr[i];
+  if (!io.staged) {
+    for (int i = l64; i < STATE_D; i += 64) sx[i] = io.xr[i];
+    for (int i = l64; i < RAW_D; i += 64) sr[i] = io.rr[i];
+    for (int i = l64; i < WORLD_LD; i += 64) dw[i] = io.wr[i];
+  }
   if (io.have_next) {
     for (int i = l64; i < STATE_D; i += 64) dn[i] = glue_ld<CG>(io.xs + i) + glue_ld<CG>(io.a0 + i) + io.px[i];
   } else {

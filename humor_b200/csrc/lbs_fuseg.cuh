@@ -20,8 +20,9 @@
 //           keeps its slot while consecutive tiles need it, so a tile loads ~1 new slot (6 KB) instead of ~6
 //   warp 1  tcgen05.mma issuer; a tile's k-blocks accumulate into ONE of two 192-column TMEM buffers (K = 224: no
 //           promotion chunks needed, lbs_blend.cuh), so tile i+1's MMAs run under tile i's epilogue
-//   warps 2..9  epilogue: TMEM lane quadrant q = warp % 4, column half h = (warp - 2) / 4 -> 4 groups each.  Per group:
-//           tcgen05.ld 24 columns (8 vertices of the thread's frame), + template, skin with the group's joint list
+//   warps 2..17 epilogue: TMEM lane quadrant q = warp % 4, column quarter (warp - 2) / 4 -> 2 groups each, a group as two half
+//           groups of 4 vertices.  Per half group: tcgen05.ld 12 columns (4 vertices of the thread's frame), + template, skin with
+//           the group's joint list
 //           (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), + trans, park the 24 floats in a
 //           per-warp staging tile and write two 96-byte frame rows per instruction (a lane = frame store would touch
 //           32 different lines per instruction).
@@ -61,8 +62,10 @@ constexpr int FG_B_PLANE = FG_BN * 128;
 constexpr int FG_ENTRY = FG_A_PLANE + FG_B_PLANE;   // 40 KB
 constexpr int FG_NSLOT = 12;                        // body_model.FG_NSLOT
 constexpr int FG_SLOT = UM_BM * 48;                 // [128 frames][12 floats]
-constexpr int FG_EPI_WARPS = 8;
-constexpr int FG_SLD = 25;                          // staging row stride in floats (odd: conflict-free lane = row writes)
+constexpr int FG_EPI_WARPS = 16;                    // 4 per TMEM lane quadrant: two vertex groups of the tile each
+constexpr int FG_HV = FG_G / 2;                     // vertices per half group: what one pass of an epilogue warp skins
+constexpr int FG_HC = 3 * FG_HV;                    // its columns
+constexpr int FG_SLD = 13;                          // staging row stride in floats (odd: conflict-free lane = row writes)
 constexpr int FG_STAGE_W = 32 * FG_SLD * 4;         // bytes per epilogue warp
 constexpr int FG_OFF_SLOTS = FG_RING * FG_ENTRY;
 constexpr int FG_OFF_STAGE = FG_OFF_SLOTS + FG_NSLOT * FG_SLOT;
@@ -84,11 +87,20 @@ __device__ __forceinline__ void tmem_ld24(uint32_t taddr, float* v) {
                  : "r"(taddr + 8u * c) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// tcgen05.ld of half a vertex group: 12 consecutive columns as three 4-column loads (half-group offsets are multiples of 12)
+__device__ __forceinline__ void tmem_ld12(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[4 * c]), "=r"(r[4 * c + 1]), "=r"(r[4 * c + 2]), "=r"(r[4 * c + 3]) : "r"(taddr + 4u * c) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void stcs2(float* p, float x, float y) { __stcs(reinterpret_cast<float2*>(p), make_float2(x, y)); }
 #define HB_EMU_GUARD_ACQ(addr, bytes)
 #define HB_EMU_GUARD_REL(addr)
 #else
-using tcemu::tmem_ld24;
+using tcemu::tmem_ld24; using tcemu::tmem_ld12;
 static inline void stcs2(float* p, float x, float y) { p[0] = x; p[1] = y; }
 // tests/host: tell the emulation which shared-memory ranges are being read, so that a TMA write into them aborts
 #define HB_EMU_GUARD_ACQ(addr, bytes) tcemu::guard_acquire(addr, bytes)
@@ -241,11 +253,11 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   } else {
     const int ew = warp - 2;
     const int q = warp & 3;                                     // TMEM lane quadrant of this warp
-    const int h = ew >> 2;                                      // column half: groups 4h .. 4h+3 of the tile
+    const int h4 = ew >> 2;                                     // column quarter: groups 2*h4, 2*h4+1 of the tile
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     float* S = reinterpret_cast<float*>(gbase + FG_OFF_STAGE + ew * FG_STAGE_W);
     const uint32_t tsl = base + FG_OFF_SLOTS + (uint32_t)(q * 32 + lane) * 48u;       // this thread's frame inside a slot
-    const int sub = lane / 12, idx = lane - 12 * sub;           // store phase: lanes 0..23 = 2 rows x 12 float2
+    const int sub = lane / 6, idx = lane - 6 * sub;             // store phase: lanes 0..23 = 4 frame rows x 6 float2
     int tc = 0;
     for (int t = t_begin; t < t_end; ++t, ++tc) {
       const int buf = tc & 1;
@@ -263,92 +275,98 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int i = 0; i < tab[0]; ++i) HB_EMU_GUARD_ACQ(base + FG_OFF_SLOTS + (uint32_t)(tab[2 + i] >> 16) * FG_SLOT, FG_SLOT);
       }
 #endif
+      // Two groups per warp, each as two half groups of 4 vertices: 12 accumulators + 12 blend values live per thread keeps the
+      // kernel at <= 112 registers, i.e. 16 epilogue warps (4 per scheduler) instead of 8 - the round-1 form issued on 42 % of the
+      // cycles with 2.5 warps per scheduler (profiles/r02a_fuseg35_set_full_details.txt).  A half group skips a joint none of
+      // its 4 vertices is bound to (one warp-uniform test), otherwise its 48 FMAs run unconditionally: the per-vertex tests of
+      // the old form cost more issue slots than the zero products they saved.
 #pragma unroll 1
-      for (int gg = 0; gg < FG_GPT / 2; ++gg) {
-        const int g = c * FG_GPT + h * (FG_GPT / 2) + gg;
+      for (int hh = 0; hh < 4; ++hh) {
+        const int gg = hh >> 1, half = hh & 1;
+        const int g = c * FG_GPT + h4 * 2 + gg;
         if (g >= a.num_groups) break;                           // warp-uniform
-        float p[FG_GC], acc[FG_GC];
-        tmem_ld24(trow + buf * FG_BN + (h * (FG_GPT / 2) + gg) * FG_GC, p);
-        const int col0 = g * FG_GC;
-        const int nv3 = min(FG_G, a.num_verts - g * FG_G) * 3;  // floats of this group inside the mesh
-        if (nv3 == FG_GC) {                                     // warp-uniform; a group's 96 template bytes are 16-byte aligned
+        const int nvh = min(FG_HC, max(0, (a.num_verts - g * FG_G) * 3 - half * FG_HC));   // floats of this half group inside the mesh
+        if (nvh <= 0) continue;
+        float p[FG_HC], acc[FG_HC];
+        tmem_ld12(trow + buf * FG_BN + (h4 * 2 + gg) * FG_GC + half * FG_HC, p);
+        const int col0 = g * FG_GC + half * FG_HC;
+        if (nvh == FG_HC) {                                     // warp-uniform; 48 template bytes, 16-byte aligned
           const float4* tp = reinterpret_cast<const float4*>(a.v_template + col0);
 #pragma unroll
-          for (int i4 = 0; i4 < FG_GC / 4; ++i4) {
+          for (int i4 = 0; i4 < FG_HC / 4; ++i4) {
             const float4 tv = __ldg(tp + i4);
             p[4 * i4] = fmaf(p[4 * i4], a.out_scale, tv.x); p[4 * i4 + 1] = fmaf(p[4 * i4 + 1], a.out_scale, tv.y);
             p[4 * i4 + 2] = fmaf(p[4 * i4 + 2], a.out_scale, tv.z); p[4 * i4 + 3] = fmaf(p[4 * i4 + 3], a.out_scale, tv.w);
           }
         } else {                                                // the mesh's last, partial group
 #pragma unroll
-          for (int i = 0; i < FG_GC; ++i) p[i] = fmaf(p[i], a.out_scale, (i < nv3) ? __ldg(a.v_template + col0 + i) : 0.f);
+          for (int i = 0; i < FG_HC; ++i) p[i] = fmaf(p[i], a.out_scale, (i < nvh) ? __ldg(a.v_template + col0 + i) : 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < FG_GC; ++i) acc[i] = 0.f;
+        for (int i = 0; i < FG_HC; ++i) acc[i] = 0.f;
         const int e0 = __ldg(a.g_start + g), e1 = __ldg(a.g_start + g + 1);
         // one entry of look-ahead on the (warp-uniform) slot and weight row
         int son = 0, jn = 0;
-        float4 wan = make_float4(0.f, 0.f, 0.f, 0.f), wbn = wan;
+        float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e0 < e1) {
           son = __ldg(a.g_slot + e0); jn = __ldg(a.g_joint + e0);
-          wan = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e0 * FG_G));
-          wbn = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e0 * FG_G) + 1);
+          wn = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e0 * FG_G) + half);
         }
         for (int e = e0; e < e1; ++e) {
-          float4 r0, r1, r2;
-          if (son >= 0) {                                       // warp-uniform
-            r0 = ld_shared_v4(tsl + (uint32_t)son); r1 = ld_shared_v4(tsl + (uint32_t)son + 16u); r2 = ld_shared_v4(tsl + (uint32_t)son + 32u);
-          } else {                                              // joint without a slot in this tile (rare): from L1/L2
-            const float4* ap = reinterpret_cast<const float4*>(Arow + jn);
-            r0 = __ldg(ap); r1 = __ldg(ap + 1); r2 = __ldg(ap + 2);
-          }
-          const float w[FG_G] = {wan.x, wan.y, wan.z, wan.w, wbn.x, wbn.y, wbn.z, wbn.w};
+          const float4 w4 = wn;
+          const int so = son, jo = jn;
           if (e + 1 < e1) {
             son = __ldg(a.g_slot + e + 1); jn = __ldg(a.g_joint + e + 1);
-            wan = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)(e + 1) * FG_G));
-            wbn = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)(e + 1) * FG_G) + 1);
+            wn = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)(e + 1) * FG_G) + half);
           }
+          if (w4.x == 0.f && w4.y == 0.f && w4.z == 0.f && w4.w == 0.f) continue;     // warp-uniform: weights depend on the vertex only
+          float4 r0, r1, r2;
+          if (so >= 0) {                                        // warp-uniform
+            r0 = ld_shared_v4(tsl + (uint32_t)so); r1 = ld_shared_v4(tsl + (uint32_t)so + 16u); r2 = ld_shared_v4(tsl + (uint32_t)so + 32u);
+          } else {                                              // joint without a slot in this tile (rare): from L1/L2
+            const float4* ap = reinterpret_cast<const float4*>(Arow + jo);
+            r0 = __ldg(ap); r1 = __ldg(ap + 1); r2 = __ldg(ap + 2);
+          }
+          const float w[FG_HV] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-          for (int i = 0; i < FG_G; ++i) {
-            if (w[i] != 0.f) {                                  // warp-uniform: weights depend on the vertex only
-              const float px = p[3 * i], py = p[3 * i + 1], pz = p[3 * i + 2];
-              acc[3 * i] = fmaf(w[i], fmaf(r0.x, px, fmaf(r0.y, py, fmaf(r0.z, pz, r0.w))), acc[3 * i]);
-              acc[3 * i + 1] = fmaf(w[i], fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w))), acc[3 * i + 1]);
-              acc[3 * i + 2] = fmaf(w[i], fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))), acc[3 * i + 2]);
-            }
+          for (int i = 0; i < FG_HV; ++i) {
+            const float px = p[3 * i], py = p[3 * i + 1], pz = p[3 * i + 2];
+            acc[3 * i] = fmaf(w[i], fmaf(r0.x, px, fmaf(r0.y, py, fmaf(r0.z, pz, r0.w))), acc[3 * i]);
+            acc[3 * i + 1] = fmaf(w[i], fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w))), acc[3 * i + 1]);
+            acc[3 * i + 2] = fmaf(w[i], fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))), acc[3 * i + 2]);
           }
         }
+        float* obase = a.out + ((size_t)g * FG_G + (size_t)half * FG_HV) * 3;
         if (a.direct_store) {
-          // A/B variant (HB_LBS_FUSEG_DIRECT=1): every thread writes its frame's 96 bytes itself - 12 STG.64 and no staging,
+          // A/B variant (HB_LBS_FUSEG_DIRECT=1): every thread writes its frame's 48 bytes itself - 6 STG.64 and no staging,
           // but 32 different lines per instruction
           if (f0 + lane < a.N) {
-            float* dst = a.out + ((size_t)(f0 + lane) * a.num_verts + (size_t)g * FG_G) * 3;
+            float* dst = obase + (size_t)(f0 + lane) * a.num_verts * 3;
 #pragma unroll
-            for (int q2 = 0; q2 < FG_GC / 2; ++q2) {
+            for (int q2 = 0; q2 < FG_HC / 2; ++q2) {
               const float x = acc[2 * q2] + ((2 * q2) % 3 == 0 ? t0 : ((2 * q2) % 3 == 1 ? t1 : t2));
               const float y = acc[2 * q2 + 1] + ((2 * q2 + 1) % 3 == 0 ? t0 : ((2 * q2 + 1) % 3 == 1 ? t1 : t2));
-              if (2 * q2 + 1 < nv3) stcs2(dst + 2 * q2, x, y);
-              else if (2 * q2 < nv3) __stcs(dst + 2 * q2, x);
+              if (2 * q2 + 1 < nvh) stcs2(dst + 2 * q2, x, y);
+              else if (2 * q2 < nvh) __stcs(dst + 2 * q2, x);
             }
           }
           continue;
         }
-        // park the group (lane = frame), then two 96-byte frame rows per store instruction
+        // park the half group (lane = frame), then four 48-byte frame rows per store instruction
         float* Sr = S + lane * FG_SLD;
 #pragma unroll
-        for (int i = 0; i < FG_GC; ++i) Sr[i] = acc[i] + ((i % 3) == 0 ? t0 : ((i % 3) == 1 ? t1 : t2));
+        for (int i = 0; i < FG_HC; ++i) Sr[i] = acc[i] + ((i % 3) == 0 ? t0 : ((i % 3) == 1 ? t1 : t2));
         __syncwarp();
         if (lane < 24) {
-          float* obase = a.out + ((size_t)g * FG_G) * 3 + 2 * idx;
 #pragma unroll 4
-          for (int rr = 0; rr < 32; rr += 2) {
+          for (int rr = 0; rr < 32; rr += 4) {
             const int row = rr + sub;
             const int frame = f0 + row;
             if (frame < a.N) {
               const float x = S[row * FG_SLD + 2 * idx], y = S[row * FG_SLD + 2 * idx + 1];
-              float* dst = obase + (size_t)frame * a.num_verts * 3;
-              if (2 * idx + 1 < nv3) stcs2(dst, x, y);
-              else if (2 * idx < nv3) __stcs(dst, x);
+              float* dst = obase + (size_t)frame * a.num_verts * 3 + 2 * idx;
+              if (2 * idx + 1 < nvh) stcs2(dst, x, y);
+              else if (2 * idx < nvh) __stcs(dst, x);
             }
           }
         }

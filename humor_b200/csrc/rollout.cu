@@ -180,7 +180,7 @@ glue_bwd_kernel(int B, int S, int t, int have_next, const float* __restrict__ xi
   if (b >= B) return;
   GlueBwdRow io;
   io.xr = xin + (size_t)b * XIN_LD; io.rr = raw + (size_t)b * RAW_LD; io.wr = dworld + (size_t)b * WORLD_LD;
-  io.G = G + (size_t)b * 12; io.t2j = t2jg + b * 4; io.have_next = have_next;
+  io.G = G + (size_t)b * 12; io.t2j = t2jg + b * 4; io.have_next = have_next; io.staged = 0;
   io.a0 = da0 + (size_t)b * XIN_LD; io.px = dpx_next + (size_t)b * 352; io.xs = dxres + (size_t)b * 340;
   io.dGn = dGn_g + (size_t)b * 12; io.dG = dG + (size_t)b * 12; io.dt2j = dt2j + b * 4;
   io.dzt = dz + ((size_t)b * S + (t + 1)) * 48;

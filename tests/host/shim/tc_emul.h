@@ -243,6 +243,12 @@ inline void tmem_ld24(uint32_t taddr, float* v) {              // 32x32b.x16 + .
   if ((taddr >> 16) != ((threadIdx.x >> 5) & 3u) * 32u) { std::fprintf(stderr, "tcemu: warp reads a foreign TMEM quadrant\n"); std::abort(); }
   for (int j = 0; j < 24; ++j) v[j] = g_tmem[lane][col + j];
 }
+inline void tmem_ld12(uint32_t taddr, float* v) {              // 32x32b.x4 three times: 12 consecutive columns
+  const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31u), col = taddr & 0xFFFFu;
+  if (lane >= 128u || col + 12u > 512u || (col & 3u)) { std::fprintf(stderr, "tcemu: tcgen05.ld outside TMEM / misaligned\n"); std::abort(); }
+  if ((taddr >> 16) != ((threadIdx.x >> 5) & 3u) * 32u) { std::fprintf(stderr, "tcemu: warp reads a foreign TMEM quadrant\n"); std::abort(); }
+  for (int j = 0; j < 12; ++j) v[j] = g_tmem[lane][col + j];
+}
 inline void tmem_alloc(uint32_t dst, uint32_t ncols) {
   if (ncols < 32 || ncols > 512 || (ncols & (ncols - 1))) { std::fprintf(stderr, "tcemu: bad TMEM allocation %u\n", ncols); std::abort(); }
   const uint32_t base = 0;
@@ -293,6 +299,15 @@ inline void st_async_v4(uint32_t addr, float a, float b, float c, float d, uint3
   complete_if_done(bb);
 }
 inline void fence_gpu() {}
+// cp.async.bulk global -> shared (1-D) with mbarrier::complete_tx
+inline void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  if ((dst & 15u) || (bytes & 15u) || (reinterpret_cast<uintptr_t>(src) & 15u) || dst + bytes > WINDOW_BYTES) {
+    std::fprintf(stderr, "tcemu: bulk copy %p -> %u (%u bytes) is not 16-byte aligned / in range\n", src, dst, bytes);
+    std::abort();
+  }
+  std::memcpy(g_smem + dst, src, bytes);
+  complete_tx(bar, bytes);
+}
 inline void flag_wait_ge(const unsigned* p, unsigned target) {
   const auto t0 = std::chrono::steady_clock::now();
   while (__atomic_load_n(p, __ATOMIC_ACQUIRE) < target) {

@@ -156,7 +156,7 @@ def run_product(args):
     prob = project_obs_from_product(mo, prob, dev, args.config)
     # global frame intervals of this rank's block of sub-sequences (one video split across the ranks)
     prob['obs']['seq_interval'] = prob['obs']['seq_interval'] + rank * B * (T - 10)
-    if world > 1 and 'seq_interval' in OBS_KEYS:
+    if world > 1 and 'seq_interval' in OBS_KEYS and not args.no_halo:
         from humor_b200.parallel import Shard
         mo.shard = Shard.from_env(ov_max=16)
     names = mo.set_stage3_state(prob['params'])
@@ -185,12 +185,24 @@ def run_product(args):
         sampler.start()
     l0 = _ext.LaunchCounter.total
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]     # per-step stamps inside the ONE timed region
     e0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for i in range(args.steps):
         loss = step()
+        marks[i + 1].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    per = torch.tensor([marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)], device=dev)
+    per_all = per[None]
+    if world > 1:
+        import torch.distributed as dist
+        buf = [torch.empty_like(per) for _ in range(world)]
+        dist.all_gather(buf, per)
+        per_all = torch.stack(buf, 0)
+    per_step = {'median': float(per_all.median()), 'p95': float(torch.quantile(per_all.flatten(), 0.95)), 'max': float(per_all.max()),
+                'by_rank_median': [float(x) for x in per_all.median(1).values], 'by_rank_max': [float(x) for x in per_all.max(1).values]}
     launches = _ext.LaunchCounter.total - l0
     clocks = sampler.stop() if rank == 0 else None
     # ---- end-to-end timing: host params/observations in pinned memory in, loss + gradients out, every step
@@ -238,7 +250,7 @@ def run_product(args):
     e2e = frames / (ms_e2e * 1e-3)
     hbm_peak, _, peak_kind = load_peaks()
     graphed = bool(mo.use_cuda_graph)
-    mo_shard_off = 'seq_interval' not in OBS_KEYS
+    mo_shard_off = 'seq_interval' not in OBS_KEYS or args.no_halo
     roof = lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind)
     roof['forms'] = {'skin': args.lbs_skin or int(os.environ.get('HB_LBS_SKIN', 3)), 'blend': args.lbs_blend or int(os.environ.get('HB_LBS_BLEND', 5)),
                      'slab_frames': args.lbs_slab or int(os.environ.get('HB_LBS_SLAB', 512))}
@@ -258,7 +270,7 @@ def run_product(args):
                          'collectives_per_step': 0 if (world == 1 or mo_shard_off) else 'halo exchange of the overlap pack fwd + its gradient bwd'},
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
-        'gpu_launches': int(launches), 'gpu_launches_per_step': launches / args.steps,
+        'gpu_launches': int(launches), 'gpu_launches_per_step': launches / args.steps, 'per_step_ms': per_step,
         'clocks': clocks, 'roofline': roof, 'step_breakdown_ms': shares, 'cpu_baseline': cpu,
         'torch_cuda_port': torch_cuda, 'result_check': result_check,
         'lbs_bytes_roofline_frac_of_step': value * (2.0 + 3.0 / T) * (LBS_BYTES_FWD + LBS_BYTES_BWD) / (hbm_peak * 1e9),
@@ -614,6 +626,7 @@ def main():
     ap.add_argument('--lbs-skin', type=int, default=0, help='dense LBS skinning pass form (humor_lbs_configure): 1 lane=vertex, 2 lane=frame, 3 fused blend + lane=frame skinning (one persistent kernel)')
     ap.add_argument('--lbs-blend', type=int, default=0, help='dense LBS blend GEMM form: 1 tile per CTA, 2 persistent 128x256 tiles, 3 = 2 + single TF32 pass on the pose columns, 4 (skin 3) = fp16 pose columns, 5 (skin 3) = fp16 hi/lo planes for every column (fp32-level)')
     ap.add_argument('--lbs-slab', type=int, default=0, help='frames per v_posed slab (128..512)')
+    ap.add_argument('--no-halo', action='store_true', help='diagnostic: N independent replicas (no overlap coupling between ranks, no collective)')
     ap.add_argument('--no-graph', action='store_true', help='evaluate the closure eagerly instead of replaying a CUDA graph')
     ap.add_argument('--port-cuda', default='', help='comma list of batch sizes: time the oracle port as eager PyTorch on cuda:0')
     ap.add_argument('--_cpu-child', dest='cpu_child', action='store_true', help=argparse.SUPPRESS)

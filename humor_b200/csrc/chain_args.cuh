@@ -30,6 +30,7 @@ struct ChainGemm {
   float* rstd;              // [S*B][16]
   float* C; float* C_hi; float* C_lo;   // fp32 result and/or its hi/lo planes (nullable)
   int ldc, c_col0, c_row_step;
+  unsigned short* C16_h; unsigned short* C16_l; int ld16;   // fp16 hi / scaled-lo planes of the result (forward chain on 4-byte operand elements)
 };
 
 struct ChainGlue {
@@ -49,9 +50,12 @@ struct ChainGlue {
   float* dG0; float* dG1;   // [B][12] ping-pong
   float* dt2j;              // [B][4]
   float* bp_hi; float* bp_lo; int bp_ld;   // per-step reverse operand planes [S*B][bp_ld]: d raw | d pre3 | d pre2 | d pre1
+  // forward chain on fp16 hi / scaled-lo planes (ChainLaunch::f16): step inputs [S*B][x16_ld] and the z skip columns of the hidden planes
+  unsigned short *x16_h, *x16_l; int x16_ld;
+  unsigned short *h1_16h, *h1_16l, *h2_16h, *h2_16l, *h3_16h, *h3_16l;
 };
 
-struct ChainPlane { const float* hi; const float* lo; int rows, cols, ld, box_rows; };
+struct ChainPlane { const void* hi; const void* lo; int rows, cols, ld, box_rows, half; };   // half: fp16 elements, 64-wide boxes
 
 struct ChainLaunch {
   ChainPlane planes[CH_NMAPS];
@@ -59,6 +63,7 @@ struct ChainLaunch {
   ChainGlue glue;
   unsigned* flags;          // CH_FLAGS words, zeroed by the launcher
   int B, S, dir;            // dir 0: forward steps 0..S-1; 1: reverse steps S-1..0
+  int f16;                  // forward only: operands are fp16 hi / scaled-lo planes (x = h + l * 2^-11; umma_gemm16.cuh), k-blocks of 64
 };
 constexpr int CH_DBG_EV = 16;       // humor_chain_debug: clock64 stamps of CTA 0, [step][phase 0..4][CH_DBG_EV]
 

@@ -47,6 +47,7 @@ struct alignas(64) ChainParams {
   ChainGlue glue;
   unsigned* flags;
   int B, S, dir;
+  int f16;                 // forward only: operand planes are fp16 hi / scaled-lo (k-blocks of 64 halves, kind::f16 MMAs, D1 | D2 accumulators)
   long long* dbg;          // optional clock64 stamps of CTA 0 (humor_chain_debug), else nullptr
 };
 // stamp event `ev` of (step u, phase ph: GEMM phases 0..3, glue 4) - one thread of CTA 0 only
@@ -134,6 +135,9 @@ chain_kernel(const __grid_constant__ ChainParams p) {
   const int B = p.B, S = p.S, dir = p.dir;
   const int MT = (B + UM_BM - 1) / UM_BM;
   unsigned* const flags = p.flags;
+  const bool f16 = p.f16 != 0;
+  const int bk = f16 ? 64 : UM_BK;                             // operand elements per k-block (always 128-byte rows)
+  const int chunk = f16 ? 2 : UM_CHUNK;                        // k-blocks (K = 128) accumulated in TMEM before promotion
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < CH_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -145,7 +149,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     mbar_expect_tx(xfull, CH_CS * CH_XROWS * CH_BN * 4);     // tile 0: four slabs of 32 rows x 64 floats
   }
   if (warp == 1) {
-    tmem_alloc(tptr, (uint32_t)(2 * CH_BN));
+    tmem_alloc(tptr, (uint32_t)(4 * CH_BN));               // two ping-pong buffers x (D1 | D2): the fp16 form keeps the cross terms apart
     tmem_relinquish();
   }
   tc_fence_before();
@@ -181,9 +185,10 @@ chain_kernel(const __grid_constant__ ChainParams p) {
               const uint32_t st = base + s * CH_STAGE;
               mbar_wait(empty0 + 8 * s, ph ^ 1);
               mbar_expect_tx(full0 + 8 * s, CH_STAGE);
-              tma_load_2d(st + 2 * CH_A_TILE, b_hi, full0 + 8 * s, kb * UM_BK, n0);            // weights: no dependency
-              tma_load_2d(st + 2 * CH_A_TILE + CH_B_TILE, b_lo, full0 + 8 * s, kb * UM_BK, n0);
-              const int ptile = (gi > 0 && (kb >> 1) < g.dep_ntn) ? (kb >> 1) : -1;
+              tma_load_2d(st + 2 * CH_A_TILE, b_hi, full0 + 8 * s, kb * bk, n0);               // weights: no dependency
+              tma_load_2d(st + 2 * CH_A_TILE + CH_B_TILE, b_lo, full0 + 8 * s, kb * bk, n0);
+              const int pt = (kb * bk) / CH_BN;                 // producer tile that holds this k-block's columns
+              const int ptile = (gi > 0 && pt < g.dep_ntn) ? pt : -1;
               if (kb == kb0) CH_STAMP(u, gi, 0);
               if (ptile != dep_ok) {
                 if (ptile >= 0) flag_wait_ge(chain_tile_flag(flags, gi - 1, mt, ptile), (unsigned)(CH_CS * (u + 1)));
@@ -193,8 +198,8 @@ chain_kernel(const __grid_constant__ ChainParams p) {
               }
               if (kb == kb0) CH_STAMP(u, gi, 1);
               if (kb == kb1 - 1) CH_STAMP(u, gi, 2);
-              tma_load_2d(st, a_hi, full0 + 8 * s, g.a_col0 + kb * UM_BK, t * g.a_row_step + m0);
-              tma_load_2d(st + CH_A_TILE, a_lo, full0 + 8 * s, g.a_col0 + kb * UM_BK, t * g.a_row_step + m0);
+              tma_load_2d(st, a_hi, full0 + 8 * s, g.a_col0 + kb * bk, t * g.a_row_step + m0);
+              tma_load_2d(st + CH_A_TILE, a_lo, full0 + 8 * s, g.a_col0 + kb * bk, t * g.a_row_step + m0);
             }
           }
         }
@@ -211,12 +216,12 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           const int nkb_per = (g.nkb + CH_CS - 1) / CH_CS;
           const int kb0 = (int)krank * nkb_per, kb1 = min(g.nkb, kb0 + nkb_per);
           for (int tile = cid; tile < g.ntn * MT; tile += ncl) {
-            for (int c0 = kb0; c0 < kb1; c0 += UM_CHUNK, ++ck) {
+            for (int c0 = kb0; c0 < kb1; c0 += chunk, ++ck) {
               const int buf = ck & 1;
               mbar_wait(tempty0 + 8 * buf, ((ck >> 1) & 1) ^ 1);           // the epilogue has drained this TMEM buffer
               tc_fence_after();
-              const uint32_t tacc = tmem_base + buf * CH_BN;
-              const int c1 = min(kb1, c0 + UM_CHUNK);
+              const uint32_t tacc = tmem_base + buf * 2 * CH_BN;            // D1 (and, fp16 form, D2 = the cross terms at + CH_BN)
+              const int c1 = min(kb1, c0 + chunk);
               for (int kb = c0; kb < c1; ++kb, ++it) {
                 const int s = it % CH_STAGES;
                 mbar_wait(full0 + 8 * s, (it / CH_STAGES) & 1);
@@ -224,15 +229,31 @@ chain_kernel(const __grid_constant__ ChainParams p) {
                 if (kb == kb0) CH_STAMP(u, gi, 3);
                 if (kb == kb1 - 1) CH_STAMP(u, gi, 4);
                 const uint32_t st = base + s * CH_STAGE;
+                if (!f16) {
 #pragma unroll
-                for (int k = 0; k < UM_BK / 8; ++k) {
-                  const uint64_t ah = umma_desc_sw128(st + k * 32);
-                  const uint64_t al = umma_desc_sw128(st + CH_A_TILE + k * 32);
-                  const uint64_t bh = umma_desc_sw128(st + 2 * CH_A_TILE + k * 32);
-                  const uint64_t bl = umma_desc_sw128(st + 2 * CH_A_TILE + CH_B_TILE + k * 32);
-                  umma_tf32(tacc, ah, bh, idesc, (kb != c0) || (k != 0));
-                  umma_tf32(tacc, al, bh, idesc, 1);
-                  umma_tf32(tacc, ah, bl, idesc, 1);
+                  for (int k = 0; k < UM_BK / 8; ++k) {
+                    const uint64_t ah = umma_desc_sw128(st + k * 32);
+                    const uint64_t al = umma_desc_sw128(st + CH_A_TILE + k * 32);
+                    const uint64_t bh = umma_desc_sw128(st + 2 * CH_A_TILE + k * 32);
+                    const uint64_t bl = umma_desc_sw128(st + 2 * CH_A_TILE + CH_B_TILE + k * 32);
+                    umma_tf32(tacc, ah, bh, idesc, (kb != c0) || (k != 0));
+                    umma_tf32(tacc, al, bh, idesc, 1);
+                    umma_tf32(tacc, ah, bl, idesc, 1);
+                  }
+                } else {
+                  // x = h + l 2^-11: h.h into D1, l.h + h.l into D2 (umma_gemm16.cuh); one UMMA consumes K = 16 halves = 32 bytes
+                  constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(CH_BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t ah = umma_desc_sw128(st + k * 32);
+                    const uint64_t al = umma_desc_sw128(st + CH_A_TILE + k * 32);
+                    const uint64_t bh = umma_desc_sw128(st + 2 * CH_A_TILE + k * 32);
+                    const uint64_t bl = umma_desc_sw128(st + 2 * CH_A_TILE + CH_B_TILE + k * 32);
+                    const uint32_t first = (kb != c0) || (k != 0);
+                    umma_f16(tacc, ah, bh, idesc16, first);
+                    umma_f16(tacc + CH_BN, al, bh, idesc16, first);
+                    umma_f16(tacc + CH_BN, ah, bl, idesc16, 1);
+                  }
                 }
                 umma_commit(empty0 + 8 * s);
               }
@@ -299,6 +320,14 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           io.h1 = gl.h1 + (size_t)b * 1088 + 1024; io.h1_lo = gl.h1_lo + (size_t)b * 1088 + 1024;
           io.h2 = gl.h2 + (size_t)b * 1088 + 1024; io.h2_lo = gl.h2_lo + (size_t)b * 1088 + 1024;
           io.h3 = gl.h3 + (size_t)b * 576 + 512; io.h3_lo = gl.h3_lo + (size_t)b * 576 + 512;
+          io.xn16_h = io.xn16_l = io.h1_16h = io.h1_16l = io.h2_16h = io.h2_16l = io.h3_16h = io.h3_16l = nullptr;
+          if (f16) {                                            // operand planes of the next step as fp16 hi / scaled lo; no fp32 planes
+            io.xn_hi = io.xn_lo = nullptr;
+            io.xn16_h = gl.x16_h + (r + B) * gl.x16_ld; io.xn16_l = gl.x16_l + (r + B) * gl.x16_ld;
+            io.h1_16h = gl.h1_16h + (size_t)b * 1088 + 1024; io.h1_16l = gl.h1_16l + (size_t)b * 1088 + 1024;
+            io.h2_16h = gl.h2_16h + (size_t)b * 1088 + 1024; io.h2_16l = gl.h2_16l + (size_t)b * 1088 + 1024;
+            io.h3_16h = gl.h3_16h + (size_t)b * 576 + 512; io.h3_16l = gl.h3_16l + (size_t)b * 576 + 512;
+          }
           if (pairs) glue_fwd_pair<true>(io, role, lane, pi, gs, gs + 340, gs + 556, gs + 896);
           else glue_fwd_warp<true>(io, lane, gs, gs + 340, gs + 556, gs + 896);
         } else {
@@ -336,14 +365,20 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           float acc[CH_BN];
 #pragma unroll
           for (int j = 0; j < CH_BN; ++j) acc[j] = 0.f;
-          for (int c0 = kb0; c0 < kb1; c0 += UM_CHUNK, ++ck) {
+          for (int c0 = kb0; c0 < kb1; c0 += chunk, ++ck) {
             const int buf = ck & 1;
             mbar_wait(tfull0 + 8 * buf, (ck >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int cc = 0; cc < CH_BN; cc += 32) {
               float tv[32];
-              tmem_ld32(trow + buf * CH_BN + cc, tv);
+              tmem_ld32(trow + buf * 2 * CH_BN + cc, tv);
+              if (f16) {                                          // + 2^-11 x the cross terms
+                float tw[32];
+                tmem_ld32(trow + buf * 2 * CH_BN + CH_BN + cc, tw);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tv[j] = fmaf(tw[j], 0.00048828125f, tv[j]);
+              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc[cc + j] += tv[j];
             }
@@ -459,6 +494,19 @@ chain_kernel(const __grid_constant__ ChainParams p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = rs * (v[j] - s1 * inv - xh[j] * s2 * inv);
           }
+          if (rok && g.C16_h) {                                 // fp16 hi / scaled-lo planes of the next layer: 32 bytes per plane and thread
+            unsigned short hh[16], ll[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split16(v[j], hh[j], ll[j]);
+            uint4* dh = reinterpret_cast<uint4*>(g.C16_h + (size_t)row * g.ld16 + col);
+            uint4* dl = reinterpret_cast<uint4*>(g.C16_l + (size_t)row * g.ld16 + col);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const unsigned short* a = hh + 8 * j; const unsigned short* b = ll + 8 * j;
+              dh[j] = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), a[4] | (a[5] << 16), a[6] | (a[7] << 16));
+              dl[j] = make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
+            }
+          }
           if (rok) {
             const size_t crow = (size_t)t * g.c_row_step + row;
 #pragma unroll
@@ -500,7 +548,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                        // no CTA leaves while a peer may still write to its shared memory / barriers
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)(2 * CH_BN));
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)(4 * CH_BN));
 }
 
 }  // namespace hb

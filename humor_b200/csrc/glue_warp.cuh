@@ -9,6 +9,7 @@
 // read with ld.global.cg (L2) because another CTA of the SAME launch produced it.
 #pragma once
 #include "rollout_glue.cuh"
+#include "umma_split16.cuh"
 
 namespace hb {
 
@@ -43,7 +44,10 @@ struct GlueFwdRow {                 // every pointer addresses THIS row
   float* wo;                        // world row [WORLD_LD]
   float* gn;                        // next G [12]
   float* h1; float* h1_lo; float* h2; float* h2_lo; float* h3; float* h3_lo;   // z skip columns of the hidden-activation rows (48 each)
+  // forward chain on fp16 hi / scaled-lo planes: next step's input row [>= 387 halves] and the z skip columns (nullable: fp32 planes above)
+  unsigned short *xn16_h, *xn16_l, *h1_16h, *h1_16l, *h2_16h, *h2_16l, *h3_16h, *h3_16l;
 };
+__device__ __forceinline__ void glue_put16(unsigned short* h, unsigned short* l, int i, float v) { split16(v, h[i], l[i]); }
 
 template <bool CG>
 __device__ __forceinline__ void glue_fwd_warp(const GlueFwdRow& io, int lane, float* sx, float* sr, float* sn, float* sw) {
@@ -115,6 +119,7 @@ __device__ __forceinline__ void glue_fwd_warp(const GlueFwdRow& io, int lane, fl
   for (int i = lane; i < STATE_D; i += 32) {
     io.xn[i] = sn[i];
     if (io.xn_lo) glue_put(io.xn_hi, io.xn_lo, i, sn[i]);
+    if (io.xn16_h && io.zt) glue_put16(io.xn16_h, io.xn16_l, i, sn[i]);
   }
   for (int i = lane; i < WORLD_LD; i += 32) io.wo[i] = sw[i];
   if (io.zt) {
@@ -122,9 +127,14 @@ __device__ __forceinline__ void glue_fwd_warp(const GlueFwdRow& io, int lane, fl
       const float v = io.zt[i];
       io.xn[STATE_D + i] = v;
       if (io.xn_lo) glue_put(io.xn_hi, io.xn_lo, STATE_D + i, v);
-      glue_put(io.h1, io.h1_lo, i, v);
-      glue_put(io.h2, io.h2_lo, i, v);
-      glue_put(io.h3, io.h3_lo, i, v);
+      if (io.xn16_h) {
+        glue_put16(io.xn16_h, io.xn16_l, STATE_D + i, v);
+        glue_put16(io.h1_16h, io.h1_16l, i, v); glue_put16(io.h2_16h, io.h2_16l, i, v); glue_put16(io.h3_16h, io.h3_16l, i, v);
+      } else {
+        glue_put(io.h1, io.h1_lo, i, v);
+        glue_put(io.h2, io.h2_lo, i, v);
+        glue_put(io.h3, io.h3_lo, i, v);
+      }
     }
   }
 }
@@ -394,6 +404,7 @@ __device__ __forceinline__ void glue_fwd_pair(const GlueFwdRow& io, int role, in
   for (int i = l64; i < STATE_D; i += 64) {
     io.xn[i] = sn[i];
     if (io.xn_lo) glue_put(io.xn_hi, io.xn_lo, i, sn[i]);
+    if (io.xn16_h && io.zt) glue_put16(io.xn16_h, io.xn16_l, i, sn[i]);
   }
   for (int i = l64; i < WORLD_LD; i += 64) io.wo[i] = sw[i];
   if (io.zt) {
@@ -401,9 +412,14 @@ __device__ __forceinline__ void glue_fwd_pair(const GlueFwdRow& io, int role, in
       const float v = io.zt[i];
       io.xn[STATE_D + i] = v;
       if (io.xn_lo) glue_put(io.xn_hi, io.xn_lo, STATE_D + i, v);
-      glue_put(io.h1, io.h1_lo, i, v);
-      glue_put(io.h2, io.h2_lo, i, v);
-      glue_put(io.h3, io.h3_lo, i, v);
+      if (io.xn16_h) {
+        glue_put16(io.xn16_h, io.xn16_l, STATE_D + i, v);
+        glue_put16(io.h1_16h, io.h1_16l, i, v); glue_put16(io.h2_16h, io.h2_16l, i, v); glue_put16(io.h3_16h, io.h3_16l, i, v);
+      } else {
+        glue_put(io.h1, io.h1_lo, i, v);
+        glue_put(io.h2, io.h2_lo, i, v);
+        glue_put(io.h3, io.h3_lo, i, v);
+      }
     }
   }
 }

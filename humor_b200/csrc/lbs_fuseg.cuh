@@ -20,9 +20,8 @@
 //           keeps its slot while consecutive tiles need it, so a tile loads ~1 new slot (6 KB) instead of ~6
 //   warp 1  tcgen05.mma issuer; a tile's k-blocks accumulate into ONE of two 192-column TMEM buffers (K = 224: no
 //           promotion chunks needed, lbs_blend.cuh), so tile i+1's MMAs run under tile i's epilogue
-//   warps 2..17 epilogue: TMEM lane quadrant q = warp % 4, column quarter (warp - 2) / 4 -> 2 groups each, a group as two half
-//           groups of 4 vertices.  Per half group: tcgen05.ld 12 columns (4 vertices of the thread's frame), + template, skin with
-//           the group's joint list
+//   warps 2..17 epilogue: TMEM lane quadrant q = warp % 4, column quarter (warp - 2) / 4 -> 2 groups each.  Per group:
+//           tcgen05.ld 24 columns (8 vertices of the thread's frame), + template, skin with the group's joint list
 //           (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), + trans, park the 24 floats in a
 //           per-warp staging tile and write two 96-byte frame rows per instruction (a lane = frame store would touch
 //           32 different lines per instruction).
@@ -56,16 +55,14 @@ constexpr int FG_BN = 192;                          // columns per tile = 64 ver
 constexpr int FG_GPT = 8;                           // vertex groups per tile
 constexpr int FG_G = 8;                             // vertices per group
 constexpr int FG_GC = 3 * FG_G;                     // columns per group
-constexpr int FG_RING = 3;
+constexpr int FG_RING = 2;                           // operand entries in flight (the epilogue, not the operand stream, paces a tile)
 constexpr int FG_A_PLANE = UM_BM * 128;             // bytes: 128 rows x 128 B
 constexpr int FG_B_PLANE = FG_BN * 128;
 constexpr int FG_ENTRY = FG_A_PLANE + FG_B_PLANE;   // 40 KB
 constexpr int FG_NSLOT = 12;                        // body_model.FG_NSLOT
 constexpr int FG_SLOT = UM_BM * 48;                 // [128 frames][12 floats]
 constexpr int FG_EPI_WARPS = 16;                    // 4 per TMEM lane quadrant: two vertex groups of the tile each
-constexpr int FG_HV = FG_G / 2;                     // vertices per half group: what one pass of an epilogue warp skins
-constexpr int FG_HC = 3 * FG_HV;                    // its columns
-constexpr int FG_SLD = 13;                          // staging row stride in floats (odd: conflict-free lane = row writes)
+constexpr int FG_SLD = 25;                          // staging row stride in floats (odd: conflict-free lane = row writes)
 constexpr int FG_STAGE_W = 32 * FG_SLD * 4;         // bytes per epilogue warp
 constexpr int FG_OFF_SLOTS = FG_RING * FG_ENTRY;
 constexpr int FG_OFF_STAGE = FG_OFF_SLOTS + FG_NSLOT * FG_SLOT;
@@ -257,7 +254,7 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     float* S = reinterpret_cast<float*>(gbase + FG_OFF_STAGE + ew * FG_STAGE_W);
     const uint32_t tsl = base + FG_OFF_SLOTS + (uint32_t)(q * 32 + lane) * 48u;       // this thread's frame inside a slot
-    const int sub = lane / 6, idx = lane - 6 * sub;             // store phase: lanes 0..23 = 4 frame rows x 6 float2
+    const int sub = lane / 12, idx = lane - 12 * sub;           // store phase: lanes 0..23 = 2 frame rows x 12 float2
     int tc = 0;
     for (int t = t_begin; t < t_end; ++t, ++tc) {
       const int buf = tc & 1;
@@ -275,98 +272,86 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int i = 0; i < tab[0]; ++i) HB_EMU_GUARD_ACQ(base + FG_OFF_SLOTS + (uint32_t)(tab[2 + i] >> 16) * FG_SLOT, FG_SLOT);
       }
 #endif
-      // Two groups per warp, each as two half groups of 4 vertices: 12 accumulators + 12 blend values live per thread keeps the
-      // kernel at <= 112 registers, i.e. 16 epilogue warps (4 per scheduler) instead of 8 - the round-1 form issued on 42 % of the
-      // cycles with 2.5 warps per scheduler (profiles/r02a_fuseg35_set_full_details.txt).  A half group skips a joint none of
-      // its 4 vertices is bound to (one warp-uniform test), otherwise its 48 FMAs run unconditionally: the per-vertex tests of
-      // the old form cost more issue slots than the zero products they saved.
+      // Two groups of 8 vertices per warp.  Sixteen epilogue warps (four per scheduler) hide the latency of the table / shared-
+      // memory loads, so the joint loop carries no software look-ahead and no per-vertex zero-weight tests: 96 FMAs per
+      // (group, joint) against ~20 other instructions, 95 registers.  (Round 1 ran 8 warps at 135 registers with look-ahead
+      // registers and a branch per vertex and joint: 42 % of the issue slots, profiles/r02a_fuseg35_set_full_details.txt; a
+      // half-group form at 16 warps doubled the loop overhead instead: profiles/r02f_*.)
 #pragma unroll 1
-      for (int hh = 0; hh < 4; ++hh) {
-        const int gg = hh >> 1, half = hh & 1;
+      for (int gg = 0; gg < 2; ++gg) {
         const int g = c * FG_GPT + h4 * 2 + gg;
         if (g >= a.num_groups) break;                           // warp-uniform
-        const int nvh = min(FG_HC, max(0, (a.num_verts - g * FG_G) * 3 - half * FG_HC));   // floats of this half group inside the mesh
-        if (nvh <= 0) continue;
-        float p[FG_HC], acc[FG_HC];
-        tmem_ld12(trow + buf * FG_BN + (h4 * 2 + gg) * FG_GC + half * FG_HC, p);
-        const int col0 = g * FG_GC + half * FG_HC;
-        if (nvh == FG_HC) {                                     // warp-uniform; 48 template bytes, 16-byte aligned
+        float p[FG_GC], acc[FG_GC];
+        tmem_ld24(trow + buf * FG_BN + (h4 * 2 + gg) * FG_GC, p);
+        const int col0 = g * FG_GC;
+        const int nv3 = min(FG_G, a.num_verts - g * FG_G) * 3;  // floats of this group inside the mesh
+        if (nv3 == FG_GC) {                                     // warp-uniform; a group's 96 template bytes are 16-byte aligned
           const float4* tp = reinterpret_cast<const float4*>(a.v_template + col0);
 #pragma unroll
-          for (int i4 = 0; i4 < FG_HC / 4; ++i4) {
+          for (int i4 = 0; i4 < FG_GC / 4; ++i4) {
             const float4 tv = __ldg(tp + i4);
             p[4 * i4] = fmaf(p[4 * i4], a.out_scale, tv.x); p[4 * i4 + 1] = fmaf(p[4 * i4 + 1], a.out_scale, tv.y);
             p[4 * i4 + 2] = fmaf(p[4 * i4 + 2], a.out_scale, tv.z); p[4 * i4 + 3] = fmaf(p[4 * i4 + 3], a.out_scale, tv.w);
           }
         } else {                                                // the mesh's last, partial group
 #pragma unroll
-          for (int i = 0; i < FG_HC; ++i) p[i] = fmaf(p[i], a.out_scale, (i < nvh) ? __ldg(a.v_template + col0 + i) : 0.f);
+          for (int i = 0; i < FG_GC; ++i) p[i] = fmaf(p[i], a.out_scale, (i < nv3) ? __ldg(a.v_template + col0 + i) : 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < FG_HC; ++i) acc[i] = 0.f;
+        for (int i = 0; i < FG_GC; ++i) acc[i] = 0.f;
         const int e0 = __ldg(a.g_start + g), e1 = __ldg(a.g_start + g + 1);
-        // one entry of look-ahead on the (warp-uniform) slot and weight row
-        int son = 0, jn = 0;
-        float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e0 < e1) {
-          son = __ldg(a.g_slot + e0); jn = __ldg(a.g_joint + e0);
-          wn = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e0 * FG_G) + half);
-        }
+#pragma unroll 1
         for (int e = e0; e < e1; ++e) {
-          const float4 w4 = wn;
-          const int so = son, jo = jn;
-          if (e + 1 < e1) {
-            son = __ldg(a.g_slot + e + 1); jn = __ldg(a.g_joint + e + 1);
-            wn = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)(e + 1) * FG_G) + half);
-          }
-          if (w4.x == 0.f && w4.y == 0.f && w4.z == 0.f && w4.w == 0.f) continue;     // warp-uniform: weights depend on the vertex only
+          const int so = __ldg(a.g_slot + e);                   // warp-uniform
+          const float4 wa = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e * FG_G));
+          const float4 wb = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e * FG_G) + 1);
           float4 r0, r1, r2;
-          if (so >= 0) {                                        // warp-uniform
+          if (so >= 0) {
             r0 = ld_shared_v4(tsl + (uint32_t)so); r1 = ld_shared_v4(tsl + (uint32_t)so + 16u); r2 = ld_shared_v4(tsl + (uint32_t)so + 32u);
           } else {                                              // joint without a slot in this tile (rare): from L1/L2
-            const float4* ap = reinterpret_cast<const float4*>(Arow + jo);
+            const float4* ap = reinterpret_cast<const float4*>(Arow + __ldg(a.g_joint + e));
             r0 = __ldg(ap); r1 = __ldg(ap + 1); r2 = __ldg(ap + 2);
           }
-          const float w[FG_HV] = {w4.x, w4.y, w4.z, w4.w};
+          const float w[FG_G] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-          for (int i = 0; i < FG_HV; ++i) {
+          for (int i = 0; i < FG_G; ++i) {
             const float px = p[3 * i], py = p[3 * i + 1], pz = p[3 * i + 2];
             acc[3 * i] = fmaf(w[i], fmaf(r0.x, px, fmaf(r0.y, py, fmaf(r0.z, pz, r0.w))), acc[3 * i]);
             acc[3 * i + 1] = fmaf(w[i], fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w))), acc[3 * i + 1]);
             acc[3 * i + 2] = fmaf(w[i], fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))), acc[3 * i + 2]);
           }
         }
-        float* obase = a.out + ((size_t)g * FG_G + (size_t)half * FG_HV) * 3;
+        float* obase = a.out + ((size_t)g * FG_G) * 3;
         if (a.direct_store) {
-          // A/B variant (HB_LBS_FUSEG_DIRECT=1): every thread writes its frame's 48 bytes itself - 6 STG.64 and no staging,
-          // but 32 different lines per instruction
+          // A/B variant (HB_LBS_FUSEG_DIRECT=1): every thread writes its frame's 96 bytes itself - 12 STG.64 and no staging,
+          // but 32 different lines per instruction (5x slower on the B200: profiles/r02f_lbs_forms_time.jsonl)
           if (f0 + lane < a.N) {
             float* dst = obase + (size_t)(f0 + lane) * a.num_verts * 3;
 #pragma unroll
-            for (int q2 = 0; q2 < FG_HC / 2; ++q2) {
+            for (int q2 = 0; q2 < FG_GC / 2; ++q2) {
               const float x = acc[2 * q2] + ((2 * q2) % 3 == 0 ? t0 : ((2 * q2) % 3 == 1 ? t1 : t2));
               const float y = acc[2 * q2 + 1] + ((2 * q2 + 1) % 3 == 0 ? t0 : ((2 * q2 + 1) % 3 == 1 ? t1 : t2));
-              if (2 * q2 + 1 < nvh) stcs2(dst + 2 * q2, x, y);
-              else if (2 * q2 < nvh) __stcs(dst + 2 * q2, x);
+              if (2 * q2 + 1 < nv3) stcs2(dst + 2 * q2, x, y);
+              else if (2 * q2 < nv3) __stcs(dst + 2 * q2, x);
             }
           }
           continue;
         }
-        // park the half group (lane = frame), then four 48-byte frame rows per store instruction
+        // park the group (lane = frame), then two 96-byte frame rows per store instruction
         float* Sr = S + lane * FG_SLD;
 #pragma unroll
-        for (int i = 0; i < FG_HC; ++i) Sr[i] = acc[i] + ((i % 3) == 0 ? t0 : ((i % 3) == 1 ? t1 : t2));
+        for (int i = 0; i < FG_GC; ++i) Sr[i] = acc[i] + ((i % 3) == 0 ? t0 : ((i % 3) == 1 ? t1 : t2));
         __syncwarp();
         if (lane < 24) {
 #pragma unroll 4
-          for (int rr = 0; rr < 32; rr += 4) {
+          for (int rr = 0; rr < 32; rr += 2) {
             const int row = rr + sub;
             const int frame = f0 + row;
             if (frame < a.N) {
               const float x = S[row * FG_SLD + 2 * idx], y = S[row * FG_SLD + 2 * idx + 1];
               float* dst = obase + (size_t)frame * a.num_verts * 3 + 2 * idx;
-              if (2 * idx + 1 < nvh) stcs2(dst, x, y);
-              else if (2 * idx < nvh) __stcs(dst, x);
+              if (2 * idx + 1 < nv3) stcs2(dst, x, y);
+              else if (2 * idx < nv3) __stcs(dst, x);
             }
           }
         }

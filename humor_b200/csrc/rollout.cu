@@ -160,6 +160,7 @@ glue_fwd_kernel(int B, int S, int t, const float* __restrict__ xin, const float*
   io.h1 = h1 + (size_t)b * 1088 + 1024; io.h2 = h2 + (size_t)b * 1088 + 1024; io.h3 = h3 + (size_t)b * 576 + 512;
   io.h1_lo = h1_lo ? h1_lo + (size_t)b * 1088 + 1024 : nullptr; io.h2_lo = h2_lo ? h2_lo + (size_t)b * 1088 + 1024 : nullptr;
   io.h3_lo = h3_lo ? h3_lo + (size_t)b * 576 + 512 : nullptr;
+  io.xn16_h = io.xn16_l = io.h1_16h = io.h1_16l = io.h2_16h = io.h2_16l = io.h3_16h = io.h3_16l = nullptr;
   glue_fwd_warp<false>(io, lane, s_x[wid], s_r[wid], s_n[wid], s_w[wid]);
 }
 
@@ -249,7 +250,7 @@ using namespace hb;
 static bool chain_ok(const HbHumorWeights* w, int B) {
   const char* e = getenv("HB_CHAIN");            // read per call: tests switch between the two chains inside one process
   const int on = e ? atoi(e) : 1;
-  return on && w->use_umma == 1 && umma_available() && w->dec_wz_hi && w->dec_wz_lo && B <= CH_MAX_MT * 128;
+  return on && (w->use_umma == 1 || w->use_umma == 2) && umma_available() && w->dec_wz_hi && w->dec_wz_lo && B <= CH_MAX_MT * 128;
 }
 static ChainGemm chain_gemm(int a_map, int a_col0, int a_row_step, int nkb, int b_map, int ntn, int N, int epi, int gsize, int dep_ntn) {
   ChainGemm g = {};
@@ -257,16 +258,47 @@ static ChainGemm chain_gemm(int a_map, int a_col0, int a_row_step, int nkb, int 
   g.gsize = gsize; g.dep_ntn = dep_ntn;
   return g;
 }
-static ChainPlane chain_plane(const float* hi, const float* lo, int rows, int cols, int ld, int box_rows) {
-  ChainPlane p; p.hi = hi; p.lo = lo; p.rows = rows; p.cols = cols; p.ld = ld; p.box_rows = box_rows; return p;
+static ChainPlane chain_plane(const void* hi, const void* lo, int rows, int cols, int ld, int box_rows, int half = 0) {
+  ChainPlane p; p.hi = hi; p.lo = lo; p.rows = rows; p.cols = cols; p.ld = ld; p.box_rows = box_rows; p.half = half; return p;
 }
 static void chain_glue_common(ChainGlue& gl, const Tape& tp, const float* z_seq, float* world) {
   gl.z = z_seq; gl.xins = tp.xins; gl.xin_hi = tp.xin_hi; gl.xin_lo = tp.xin_lo; gl.raws = tp.raws; gl.Gs = tp.Gs; gl.t2j = tp.t2j;
   gl.world = world; gl.h1 = tp.h1; gl.h1_lo = tp.h1_lo; gl.h2 = tp.h2; gl.h2_lo = tp.h2_lo; gl.h3 = tp.h3; gl.h3_lo = tp.h3_lo;
 }
-static cudaError_t chain_forward(const HbHumorWeights* w, const Tape& tp, int B, int S, const float* z_seq, float* world, cudaStream_t st) {
+static cudaError_t chain_forward(const HbHumorWeights* w, const Tape& tp, int B, int S, const float* z_seq, float* world, bool f16,
+                                 cudaStream_t st) {
   ChainLaunch a = {};
   a.B = B; a.S = S; a.dir = 0; a.flags = tp.chain_flags;
+  if (f16) {
+    // forward chain on fp16 hi / scaled-lo operand planes (x = h + l 2^-11, umma_gemm16.cuh): 4 bytes per operand element, k-blocks
+    // of 64, half the MMA issue slots; the fp32 tape the reverse pass reads (xins, raws, x-hat, 1/sigma) is written exactly as before
+    a.f16 = 1;
+    a.planes[0] = chain_plane(tp.x16_h, tp.x16_l, S * B, X16_LD, X16_LD, 128, 1);
+    a.planes[1] = chain_plane(tp.h1_16h, tp.h1_16l, B, 1088, 1088, 128, 1);
+    a.planes[2] = chain_plane(tp.h2_16h, tp.h2_16l, B, 1088, 1088, 128, 1);
+    a.planes[3] = chain_plane(tp.h3_16h, tp.h3_16l, B, 576, 576, 128, 1);
+    a.planes[4] = chain_plane(w->dec_w16_h[0], w->dec_w16_l[0], 1024, X16_LD, X16_LD, CH_BN, 1);
+    a.planes[5] = chain_plane(w->dec_w16_h[1], w->dec_w16_l[1], 1024, 1088, 1088, CH_BN, 1);
+    a.planes[6] = chain_plane(w->dec_w16_h[2], w->dec_w16_l[2], 512, 1088, 1088, CH_BN, 1);
+    a.planes[7] = chain_plane(w->dec_w16_h[3], w->dec_w16_l[3], 216, 576, 576, CH_BN, 1);
+    ChainGemm& g0 = a.g[0]; ChainGemm& g1 = a.g[1]; ChainGemm& g2 = a.g[2]; ChainGemm& g3 = a.g[3];
+    g0 = chain_gemm(0, 0, B, X16_LD / 64, 4, 16, 1024, EPI_GN_RELU, 64, 0);
+    g0.bias = w->dec_b[0]; g0.gamma = w->dec_g[0]; g0.beta = w->dec_be[0]; g0.xhat = tp.dxh1; g0.ldxh = 1024; g0.rstd = tp.drs1;
+    g0.C16_h = tp.h1_16h; g0.C16_l = tp.h1_16l; g0.ld16 = 1088;
+    g1 = chain_gemm(1, 0, 0, 17, 5, 16, 1024, EPI_GN_RELU, 64, 16);
+    g1.bias = w->dec_b[1]; g1.gamma = w->dec_g[1]; g1.beta = w->dec_be[1]; g1.xhat = tp.dxh2; g1.ldxh = 1024; g1.rstd = tp.drs2;
+    g1.C16_h = tp.h2_16h; g1.C16_l = tp.h2_16l; g1.ld16 = 1088;
+    g2 = chain_gemm(2, 0, 0, 17, 6, 8, 512, EPI_GN_RELU, 32, 16);
+    g2.bias = w->dec_b[2]; g2.gamma = w->dec_g[2]; g2.beta = w->dec_be[2]; g2.xhat = tp.dxh3; g2.ldxh = 512; g2.rstd = tp.drs3;
+    g2.C16_h = tp.h3_16h; g2.C16_l = tp.h3_16l; g2.ld16 = 576;
+    g3 = chain_gemm(3, 0, 0, 9, 7, 4, 216, EPI_BIAS, 64, 8);
+    g3.bias = w->dec_b[3]; g3.C = tp.raws; g3.ldc = RAW_LD; g3.c_row_step = B;
+    chain_glue_common(a.glue, tp, z_seq, world);
+    a.glue.x16_h = tp.x16_h; a.glue.x16_l = tp.x16_l; a.glue.x16_ld = X16_LD;
+    a.glue.h1_16h = tp.h1_16h; a.glue.h1_16l = tp.h1_16l; a.glue.h2_16h = tp.h2_16h; a.glue.h2_16l = tp.h2_16l;
+    a.glue.h3_16h = tp.h3_16h; a.glue.h3_16l = tp.h3_16l;
+    return launch_chain(a, st);
+  }
   a.planes[0] = chain_plane(tp.xin_hi, tp.xin_lo, (S + 1) * B, XIN_LD, XIN_LD, 128);
   a.planes[1] = chain_plane(tp.h1, tp.h1_lo, B, 1088, 1088, 128);
   a.planes[2] = chain_plane(tp.h2, tp.h2_lo, B, 1088, 1088, 128);
@@ -349,9 +381,13 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
   if (f16)          // pads (input columns 416..447, hidden columns past the 48 z) must read as zero
     HB_CUDA(cudaMemsetAsync(tp.x16_h, 0, (size_t)((char*)(tp.h3_16l + (size_t)B * 576) - (char*)tp.x16_h), st));
   const int gb = cdiv(B, GLUE_WARPS);
-  const bool persistent = tc && !f16 && chain_ok(w, B);
+  const bool persistent = tc && chain_ok(w, B);
   if (persistent) {                 // all S steps of the decoder chain in ONE launch
-    HB_CUDA(chain_forward(w, tp, B, S, z_seq, world, st));
+    if (f16) {                      // step 0's input row and z skip columns as fp16 planes; the glue writes those of the later steps
+      chain16_pack_kernel<<<B, 128, 0, st>>>(B, tp.xins, tp.x16_h, tp.x16_l, tp.h1_16h, tp.h1_16l, tp.h2_16h, tp.h2_16l, tp.h3_16h, tp.h3_16l);
+      HB_LAUNCH_CHECK(); ++nl;
+    }
+    HB_CUDA(chain_forward(w, tp, B, S, z_seq, world, f16, st));
     nl += 1;
   }
   for (int t = 0; t < S && !persistent; ++t) {
@@ -508,7 +544,7 @@ extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* w
   }
   const int gb = cdiv(B, GLUE_WARPS);
   float* dGbuf[2] = {tp.dG0, tp.dG1};
-  if (tc && w->use_umma == 1 && chain_ok(w, B)) {
+  if (tc && chain_ok(w, B)) {
     // all S reverse steps in ONE launch, then d z of every step as one batched GEMM over the operand planes it left
     HB_CUDA(chain_backward(w, tp, B, S, d_world, st));
     HB_CUDA(launch_umma_gemm3_bn(tp.bp_hi, tp.bp_lo, BP_LD, w->dec_wz_hi, w->dec_wz_lo, BP_LD, M, 48, BP_LD, tp.dz_all, nullptr, nullptr, 48,

@@ -325,16 +325,24 @@ cudaError_t launch_chain(const ChainLaunch& a, cudaStream_t st) {
   for (int i = 0; i < CH_NMAPS; ++i) {
     const ChainPlane& pl = a.planes[i];
     if (!pl.hi) { if (i == 0) return cudaErrorInvalidValue; p.map_hi[i] = p.map_hi[0]; p.map_lo[i] = p.map_lo[0]; continue; }
-    if (pl.cols % UM_BK || pl.ld % 4 || !pl.lo) return cudaErrorInvalidValue;
-    if (!make_map(&p.map_hi[i], pl.hi, pl.rows, pl.cols, pl.ld, pl.box_rows) ||
-        !make_map(&p.map_lo[i], pl.lo, pl.rows, pl.cols, pl.ld, pl.box_rows))
+    if (!pl.lo) return cudaErrorInvalidValue;
+    if (pl.half) {                        // fp16 hi / scaled-lo planes: boxes of 64 halves
+      if (pl.cols % 64 || pl.ld % 8) return cudaErrorInvalidValue;
+      if (!make_map_f16(&p.map_hi[i], pl.hi, pl.rows, pl.cols, pl.ld, pl.box_rows) ||
+          !make_map_f16(&p.map_lo[i], pl.lo, pl.rows, pl.cols, pl.ld, pl.box_rows))
+        return cudaErrorInvalidValue;
+      continue;
+    }
+    if (pl.cols % UM_BK || pl.ld % 4) return cudaErrorInvalidValue;
+    if (!make_map(&p.map_hi[i], static_cast<const float*>(pl.hi), pl.rows, pl.cols, pl.ld, pl.box_rows) ||
+        !make_map(&p.map_lo[i], static_cast<const float*>(pl.lo), pl.rows, pl.cols, pl.ld, pl.box_rows))
       return cudaErrorInvalidValue;
   }
   for (int i = 0; i < CH_NGEMM; ++i) {
     p.g[i] = a.g[i];
     if (a.g[i].ntn < 1 || a.g[i].ntn > CH_MAX_NT || a.g[i].nkb < 1 || (a.g[i].gsize != 64 && a.g[i].gsize != 32)) return cudaErrorInvalidValue;
   }
-  p.glue = a.glue; p.flags = a.flags; p.B = a.B; p.S = a.S; p.dir = a.dir;
+  p.glue = a.glue; p.flags = a.flags; p.B = a.B; p.S = a.S; p.dir = a.dir; p.f16 = (a.f16 && a.dir == 0) ? 1 : 0;
   p.dbg = (g_chain_dbg && g_chain_dbg_bytes >= (size_t)a.S * 5 * CH_DBG_EV * sizeof(long long)) ? g_chain_dbg : nullptr;
   cudaError_t e = cudaMemsetAsync(a.flags, 0, CH_FLAGS * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;

@@ -8,9 +8,10 @@ last sequence of rank r and the first of rank r+1 exchange a halo:
 
     tail pack of rank r  = [ verts3d[-1, T-ov_max:T] (ov_max*43*3) | betas[-1] (16) | floor[-1] (3) ]
 
-Forward: one all_gather of the packs (a few KB, latency-bound; NCCL over NVLink on GPUs, gloo in the CPU
-tests); the receiving rank r+1 evaluates the boundary energy.  Backward: the gradient w.r.t. the received
-pack is all_gathered back and rank r adds the slice that belongs to its tail.  Scalars shared by a joint
+Forward: rank r sends its pack to r+1 and receives r-1's (a few KB, latency-bound; NCCL send/recv over NVLink on
+GPUs, gloo in the CPU tests); the receiving rank evaluates the boundary energy.  Backward: the gradient w.r.t. the
+received pack is sent back to r-1, which adds it to its tail (HB_HALO=allgather selects the round-1 world-wide
+all_gather / all_reduce pair instead).  Scalars shared by a joint
 L-BFGS (loss, directional derivatives) go through `allreduce_scalars` — one collective per evaluation.
 """
 import torch
@@ -62,6 +63,54 @@ class _GatherPacks(torch.autograd.Function):
         return None, d_all[shard.rank]
 
 
+class _NeighbourPack(torch.autograd.Function):
+    """Halo as a +-1 neighbour exchange: rank r sends its tail pack to r+1 and receives r-1's (zeros on rank 0); in reverse the
+    gradient w.r.t. the received pack travels back to r-1.  Same values as the all_gather / all_reduce pair (only rank r+1 ever
+    reads rank r's slot), but no rank waits for ranks it shares no frames with: with the world-wide collectives un-synchronised
+    back-to-back graph replays lost 21 % at 8 ranks (SCALE_r01: 0.789)."""
+
+    @staticmethod
+    def forward(ctx, shard, pack):
+        pack = pack.contiguous()
+        prev = torch.zeros_like(pack)
+        ops = []
+        if shard.rank + 1 < shard.world:
+            ops.append(dist.P2POp(dist.isend, pack, shard.rank + 1, shard.group))
+        if shard.rank > 0:
+            ops.append(dist.P2POp(dist.irecv, prev, shard.rank - 1, shard.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        ctx.shard = shard
+        return prev
+
+    @staticmethod
+    def backward(ctx, d_prev):
+        shard = ctx.shard
+        d_prev = d_prev.contiguous()
+        d_pack = torch.zeros_like(d_prev)
+        ops = []
+        if shard.rank > 0:
+            ops.append(dist.P2POp(dist.isend, d_prev, shard.rank - 1, shard.group))
+        if shard.rank + 1 < shard.world:
+            ops.append(dist.P2POp(dist.irecv, d_pack, shard.rank + 1, shard.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return None, d_pack
+
+
+def previous_pack(shard, pack):
+    """The tail pack of rank r-1 (zeros on rank 0) and a handle that keeps the reverse exchange symmetric on every rank."""
+    import os
+    if os.environ.get('HB_HALO', 'neighbour') == 'allgather':       # round-1 form, kept for A/B runs
+        allp = _GatherPacks.apply(shard, pack)
+        prev = allp[shard.rank - 1] if shard.rank > 0 else allp[0] * 0.0
+        return prev, allp.sum() * 0.0
+    prev = _NeighbourPack.apply(shard, pack)
+    return prev, prev.sum() * 0.0
+
+
 def tail_pack(shard, verts3d, betas, floor, T):
     """[ov_max*129 + 16 + 3] floats describing the LAST local sequence (zero-padded in front when T < ov_max)."""
     ov = shard.ov_max
@@ -80,13 +129,12 @@ def boundary_overlap_energy(shard, verts3d, betas, floor, seq_interval, T, with_
     if shard.ov_prev is None:
         shard.prepare(seq_interval)
     pack = tail_pack(shard, verts3d, betas, floor, T)
-    allp = _GatherPacks.apply(shard, pack)                              # (world, P)
+    prev, keep = previous_pack(shard, pack)                             # (P,), 0-valued handle on the exchange
     zero = verts3d.sum() * 0.0
     stats = {}
     ov = shard.ov_prev
     if shard.rank == 0 or ov <= 0:
-        return zero + allp.sum() * 0.0, stats                           # keeps the reverse collective symmetric
-    prev = allp[shard.rank - 1]
+        return zero + keep, stats                                       # keeps the reverse exchange symmetric
     if ov > ov_max or ov > T:
         raise ValueError(f'overlap {ov} exceeds the halo capacity {ov_max} / sequence length {T}')
     a = prev[:ov_max * 129].reshape(ov_max, 43, 3)[ov_max - ov:]        # tail of the previous rank's last sequence
@@ -104,7 +152,7 @@ def boundary_overlap_energy(shard, verts3d, betas, floor, seq_interval, T, with_
         fl = 0.5 * ((prev[ov_max * 129 + 16:ov_max * 129 + 19] - floor[0]) ** 2).sum()
         e = e + fl
         stats['rgb_overlap_consist_floor'] = fl.detach()
-    return e + allp.sum() * 0.0, stats
+    return e + keep, stats
 
 
 def allreduce_scalars(shard, values):

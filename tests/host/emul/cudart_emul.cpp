@@ -97,7 +97,7 @@ const std::map<std::string, Thunk>& registry() {
            std::memcpy(&q.map_lo[i], raw + 128 * (hb_emu::CH_NMAPS + i), sizeof(CUtensorMap));
          }
          std::memcpy(reinterpret_cast<unsigned char*>(&q) + offsetof(hb_emu::ChainParams, g), raw + 2 * hb_emu::CH_NMAPS * 128,
-                     offsetof(hb_emu::ChainParams, dir) + sizeof(int) - offsetof(hb_emu::ChainParams, g));
+                     offsetof(hb_emu::ChainParams, f16) + sizeof(int) - offsetof(hb_emu::ChainParams, g));     // everything but the debug pointer
          shim::launch_cluster(g, b, g_cluster_x, [&] { hb_emu::chain_kernel(q); }, true); }},
       {"hb::chain_bwd_final_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::chain_bwd_final_kernel(A(int, 0), A(int, 1), A(cf, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8))); }},
       {"hb::split_hilo_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::split_hilo_kernel(A(cf, 0), A(float*, 1), A(float*, 2), A(size_t, 3))); }},

@@ -24,6 +24,8 @@ struct dim3 {
 struct float2 { float x, y; };
 struct alignas(8) uint2 { unsigned x, y; };
 static inline uint2 make_uint2(unsigned x, unsigned y) { return {x, y}; }
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return {x, y, z, w}; }
 struct float3 { float x, y, z; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct int2 { int x, y; };

@@ -91,6 +91,14 @@ def test_full_size_properties():
         scale = float(g_c[k].abs().max()) + 1e-8
         assert float((g_sub[k].cpu() - g_c[k]).abs().max()) / scale < 5e-3, k          # vs oracle, T=60 BPTT
         assert float((g_sub[k] - g_full[k][:sub]).abs().max()) / scale < 5e-3, k       # slice of the full batch
+    # the default 'tensor' mode (tcgen05 3xTF32, persistent chain) through the full T = 60 reverse pass: its gradients agree with
+    # the exact-fp32 kernels far better than either agrees with the fp32 CPU oracle (profiles/r02g_tolerances.jsonl)
+    mo2.set_precision('tensor')
+    l_t, g_t, _ = U.closure_product(mo2, p2)
+    assert abs(l_t - l_sub) / max(1.0, abs(l_sub)) < 1e-5
+    for k in g_sub:
+        scale = float(g_sub[k].abs().max()) + 1e-8
+        assert float((g_t[k] - g_sub[k]).abs().max()) / scale < 5e-3, (k, float((g_t[k] - g_sub[k]).abs().max()) / scale)
 
 
 def test_motion_optimizer_run_smoke():

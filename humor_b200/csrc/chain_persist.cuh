@@ -35,9 +35,15 @@ constexpr int CH_STAGE = 2 * CH_A_TILE + 2 * CH_B_TILE;        // 48 KB: A_hi | 
 constexpr int CH_XROWS = UM_BM / CH_CS;                        // rows a CTA finalises
 constexpr int CH_XLD = 68;                                     // floats per row of a partial slab (64 + pad: conflict-free v4 stores)
 constexpr int CH_XBUF = CH_CS * CH_XROWS * CH_XLD * 4;         // one slab per source CTA
-constexpr int CH_GLUE = 4 * GLUE_BWD_SMEM * 4;                 // row staging of the four epilogue warps
+constexpr int CH_SLAB = CH_XROWS * CH_XLD * 4;                 // one 32-row partial slab: 8 704 bytes
+constexpr int CH_GLUE_W = CH_SLAB / 4;                         // floats of an epilogue warp's staging area: its outgoing slab, and the glue's
+static_assert(CH_GLUE_W >= GLUE_BWD_SMEM, "the glue's row arrays live in the slab staging area");   // row arrays between tiles
+constexpr int CH_GLUE = 4 * CH_SLAB;
+constexpr int CH_PF_W = 340 + 216 + 348 + 12;                  // reverse glue: prefetched xin | raw | d world | G of the next step
+constexpr int CH_PF = 2 * CH_PF_W * 4;                         // one set per warp pair
 constexpr int CH_BARS = 256;
-constexpr int CH_SMEM = CH_STAGES * CH_STAGE + CH_XBUF + CH_GLUE + CH_BARS + 1024 /*align slack*/;
+constexpr int CH_SMEM = CH_STAGES * CH_STAGE + CH_XBUF + CH_GLUE + CH_PF + CH_BARS + 1024 /*align slack*/;
+static_assert(CH_SMEM <= 232448, "shared memory of one CTA");
 constexpr int CHAIN_THREADS = 192;
 
 struct alignas(64) ChainParams {
@@ -62,7 +68,7 @@ __device__ __forceinline__ long long hb_clock64() { return clock64(); }
 #ifdef HB_HOST_SHIM
 using tcemu::cluster_id_x; using tcemu::cluster_nid_x; using tcemu::mbar_arrive_remote; using tcemu::mbar_wait_cluster;
 using tcemu::flag_wait_ge; using tcemu::flag_add_release; using tcemu::fence_proxy_async; using tcemu::epi_bar_sync;
-using tcemu::st_async_v4; using tcemu::fence_gpu; using tcemu::bulk_g2s;
+using tcemu::st_async_v4; using tcemu::fence_gpu; using tcemu::bulk_g2s; using tcemu::bulk_s2c; using tcemu::st_shared_v4;
 #else
 // 16-byte store into another CTA's shared memory that completes 16 transaction bytes on an mbarrier of THAT CTA when it lands:
 // data and signal travel together, no release fence / separate arrival on the critical path
@@ -71,6 +77,15 @@ __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, float a, floa
                ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_mbar) : "memory");
 }
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// 1-D bulk copy from this CTA's shared memory into a peer's (or its own) through the cluster's shared-memory network, completing
+// `bytes` on an mbarrier of the destination CTA: ONE copy per 8.7 KB slab instead of 512 st.async of 16 bytes
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // 1-D bulk copy global -> this CTA's shared memory, completing `bytes` on an mbarrier (addresses and size multiples of 16)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -86,8 +101,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   uint32_t ok = 0;
   const long long t0 = clock64();
   while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     if (ok) break;
     if (clock64() - t0 > 4000000000LL) __trap();
   }
@@ -124,10 +139,12 @@ chain_kernel(const __grid_constant__ ChainParams p) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t xbuf = base + CH_STAGES * CH_STAGE;
   const uint32_t glue_s = xbuf + CH_XBUF;
-  const uint32_t bars = glue_s + CH_GLUE;
+  const uint32_t pf_s = glue_s + CH_GLUE;
+  const uint32_t bars = pf_s + CH_PF;
   const uint32_t full0 = bars, empty0 = bars + 8 * CH_STAGES, tfull0 = bars + 16 * CH_STAGES, tempty0 = tfull0 + 16,
                  xfull = tempty0 + 16, xfree = xfull + 8, tptr = xfree + 8, gbar0 = tptr + 8;
   float* glue_f = reinterpret_cast<float*>(smem_raw + (glue_s - raw));
+  float* pf_f = reinterpret_cast<float*>(smem_raw + (pf_s - raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t krank = cluster_ctarank();
   const int cid = (int)cluster_id_x(), ncl = (int)cluster_nid_x();
@@ -146,7 +163,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     mbar_init(xfree, CH_CS);               // one arrival per CTA of the cluster once its slab has been consumed
     for (int i = 0; i < 4; ++i) mbar_init(gbar0 + 8 * i, 1);   // reverse glue: tape rows of the next step prefetched into the staging arrays
     mbar_fence_init();
-    mbar_expect_tx(xfull, CH_CS * CH_XROWS * CH_BN * 4);     // tile 0: four slabs of 32 rows x 64 floats
+    mbar_expect_tx(xfull, CH_CS * CH_SLAB);                 // tile 0: four slabs of 32 rows x 68 floats
   }
   if (warp == 1) {
     tmem_alloc(tptr, (uint32_t)(4 * CH_BN));               // two ping-pong buffers x (D1 | D2): the fp16 form keeps the cross terms apart
@@ -275,26 +292,26 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     // PAIR (glue_*_pair: joint rotations | everything else), else one warp takes a row.
     const bool pairs = 2 * nctas >= B;
     const int pi = ew >> 1, role = ew & 1;                      // pair of this warp, its role inside the pair
-    float* gsp = glue_f + 2 * pi * GLUE_BWD_SMEM;               // the pair shares the staging arrays of its first warp
     const int b_first = pairs ? pi * nctas + cta : ew * nctas + cta;
     const int b_step = pairs ? 2 * nctas : 4 * nctas;
     const bool lead = lane == 0 && (!pairs || role == 0);     // the lane that waits / releases / prefetches for this warp's rows
-    float* const gs = pairs ? gsp : glue_f + ew * GLUE_BWD_SMEM;
+    float* const gs = glue_f + (pairs ? 2 * pi : ew) * CH_GLUE_W;      // a pair shares the staging area of its first warp
     // Reverse glue: xin / raw / d world / G rows of a step come from the forward tape in HBM (~2 us of load latency on the
-    // recurrence, measured: profiles/r02d).  With one row per warp (pair) and step they are known a whole step ahead: the lead lane
-    // bulk-copies the NEXT step's rows into the staging arrays as soon as this step's row is done.
-    const bool prefetch = dir && b_first < B && b_first + b_step >= B;
-    const uint32_t gbar = gbar0 + 8 * (pairs ? pi : ew);
-    const uint32_t gs_s = glue_s + (uint32_t)((pairs ? 2 * pi : ew) * GLUE_BWD_SMEM) * 4u;
+    // recurrence, measured: profiles/r02d).  With one row per warp pair and step they are known a whole step ahead: the lead lane
+    // bulk-copies the NEXT step's rows into the pair's prefetch set as soon as this step's row is done.
+    const bool prefetch = dir && pairs && b_first < B && b_first + b_step >= B;
+    const uint32_t gbar = gbar0 + 8 * pi;
+    float* const pf = pf_f + pi * CH_PF_W;
+    const uint32_t pf_a = pf_s + (uint32_t)(pi * CH_PF_W) * 4u;
     auto prefetch_rows = [&](int t) {                            // lead lane only
       const ChainGlue& gl = p.glue;
       const size_t r = (size_t)t * B + b_first;
-      fence_proxy_async();                                       // generic reads / writes of the staging arrays -> async-proxy writes
-      mbar_expect_tx(gbar, (340 + RAW_D + WORLD_LD + 12) * 4);
-      bulk_g2s(gs_s, gl.xins + r * XIN_LD, 340 * 4, gbar);
-      bulk_g2s(gs_s + 340 * 4, gl.raws + r * RAW_LD, RAW_D * 4, gbar);
-      bulk_g2s(gs_s + 896 * 4, gl.dworld + r * WORLD_LD, WORLD_LD * 4, gbar);
-      bulk_g2s(gs_s + 1808 * 4, gl.Gs + r * 12, 12 * 4, gbar);
+      fence_proxy_async();                                       // generic reads of the prefetch set -> async-proxy writes
+      mbar_expect_tx(gbar, CH_PF_W * 4);
+      bulk_g2s(pf_a, gl.xins + r * XIN_LD, 340 * 4, gbar);
+      bulk_g2s(pf_a + 340 * 4, gl.raws + r * RAW_LD, RAW_D * 4, gbar);
+      bulk_g2s(pf_a + 556 * 4, gl.dworld + r * WORLD_LD, WORLD_LD * 4, gbar);
+      bulk_g2s(pf_a + 904 * 4, gl.Gs + r * 12, 12 * 4, gbar);
     };
     if (prefetch && lead) prefetch_rows(S - 1);
     auto run_glue = [&](int u, int t) {
@@ -308,7 +325,8 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           for (int nt = 0; nt < gp.ntn; ++nt) flag_wait_ge(chain_tile_flag(flags, CH_NGEMM - 1, mt, nt), need);
         }
         if (lead && prefetch) mbar_wait(gbar, u & 1);           // landed long ago
-        if (pairs) glue_pair_sync(pi); else __syncwarp();
+        if (tl > 0) mbar_wait_cluster(xfree, (tl - 1) & 1);     // the staging area doubles as the glue's row arrays: every peer has
+        if (pairs) glue_pair_sync(pi); else __syncwarp();       // consumed the last slab, so its bulk copy has read it
         if (lead && ew == 0) CH_STAMP(u, 4, 1);
         const size_t r = (size_t)t * B + b;
         if (!dir) {
@@ -333,14 +351,15 @@ chain_kernel(const __grid_constant__ ChainParams p) {
         } else {
           GlueBwdRow io;
           io.xr = gl.xins + r * XIN_LD; io.rr = gl.raws + r * RAW_LD; io.wr = gl.dworld + r * WORLD_LD;
-          io.G = prefetch ? gs + 1808 : gl.Gs + r * 12; io.staged = prefetch ? 1 : 0;
+          io.G = prefetch ? pf + 904 : gl.Gs + r * 12; io.staged = prefetch ? 1 : 0;
           io.t2j = gl.t2j + b * 4; io.have_next = u > 0;
           io.a0 = gl.da0 + (size_t)b * XIN_LD; io.px = gl.dpx + (r + B) * 352; io.xs = gl.dxres + (size_t)b * 340;
           io.dGn = ((t + 1) & 1 ? gl.dG1 : gl.dG0) + (size_t)b * 12; io.dG = (t & 1 ? gl.dG1 : gl.dG0) + (size_t)b * 12;
           io.dt2j = gl.dt2j + b * 4; io.dzt = nullptr;
           io.dh1 = io.dh1_lo = io.dh2 = io.dh2_lo = io.dh3 = io.dh3_lo = nullptr;
           io.draw = nullptr; io.draw_hi = gl.bp_hi + r * gl.bp_ld; io.draw_lo = gl.bp_lo + r * gl.bp_ld;
-          if (pairs) glue_bwd_pair<true>(io, role, lane, pi, gs, gs + 340, gs + 556, gs + 896, gs + 1244, gs + 1584);
+          if (pairs) glue_bwd_pair<true>(io, role, lane, pi, prefetch ? pf : gs, prefetch ? pf + 340 : gs + 340, gs + 556, prefetch ? pf + 556 : gs + 896,
+                                         gs + 1244, gs + 1584);
           else glue_bwd_warp<true>(io, lane, gs, gs + 340, gs + 556, gs + 896, gs + 1244, gs + 1584);
         }
         if (lead && ew == 0) CH_STAMP(u, 4, 2);
@@ -391,10 +410,14 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           if (tl > 0) mbar_wait_cluster(xfree, (tl - 1) & 1);   // every CTA of the cluster has consumed its previous slab
           if (et == 0) CH_STAMP(u, gi, 6);
           {
-            const uint32_t dst = map_to_cta(xbuf + (uint32_t)(((int)krank * CH_XROWS + lane) * CH_XLD) * 4u, (uint32_t)q);
-            const uint32_t dbar = map_to_cta(xfull, (uint32_t)q);
+            // park the warp's 32 x 64 block in its staging area (lane = row, conflict-free 272-byte stride), then ONE bulk copy
+            // carries the slab to CTA q and completes its bytes on that CTA's barrier
+            const uint32_t stg = glue_s + (uint32_t)ew * CH_SLAB;
 #pragma unroll
-            for (int j = 0; j < CH_BN; j += 4) st_async_v4(dst + j * 4, acc[j], acc[j + 1], acc[j + 2], acc[j + 3], dbar);
+            for (int j = 0; j < CH_BN; j += 4) st_shared_v4(stg + (uint32_t)lane * (CH_XLD * 4) + j * 4, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            fence_proxy_async();                                // generic writes of the slab -> the bulk copy's reads
+            __syncwarp();
+            if (lane == 0) bulk_s2c(map_to_cta(xbuf + (uint32_t)krank * CH_SLAB, (uint32_t)q), stg, CH_SLAB, map_to_cta(xfull, (uint32_t)q));
           }
           if (et == 0) CH_STAMP(u, gi, 7);
           // ---- finalise rows krank*32 .. +31 of the tile: 4 threads per row, 16 columns each.  Everything the epilogue needs from
@@ -431,7 +454,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           }
           mbar_wait_cluster(xfull, tl & 1);
           if (et == 0) {
-            mbar_expect_tx(xfull, CH_CS * CH_XROWS * CH_BN * 4);   // arm the next tile (peers send it only after xfree below)
+            mbar_expect_tx(xfull, CH_CS * CH_SLAB);                // arm the next tile (peers send it only after xfree below)
             CH_STAMP(u, gi, 8);
           }
           float v[16];

@@ -319,18 +319,42 @@ __global__ void __launch_bounds__(LB) fit_losses_kernel(HbFitArgs a) {
   if (tid == 0) { out[HB_T_INIT_PRIOR] = 0.f; for (int i = HB_T_OV_FLOOR + 1; i < NT; ++i) out[i] = 0.f; }
 }
 
-// warp w sums term w over all rows in a fixed order; thread 0 forms the weighted loss
-__global__ void fit_reduce_kernel(HbFitArgs a) {
-  __shared__ float tot[NT];
+// Deterministic two-level reduction of the per-row terms (fixed order at both levels).  Level 1: FIT_RB blocks, each sums its slice of
+// rows with lane = term (a row's 24 terms are one coalesced 96-byte read) into partials[(rows + block)][NT]; level 2: one warp
+// sums the block sums and forms the weighted loss.  (Round 1: one block, warp = term reading with a 96-byte lane stride:
+// 57-240 us on the step's critical path, profiles/r02j_profile_step.txt.)
+constexpr int FIT_RB = 64;
+__global__ void __launch_bounds__(256) fit_reduce1_kernel(HbFitArgs a) {
+  __shared__ float part[8][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = a.B * a.T;
-  float s = 0.f;
-  for (int r = lane; r < rows; r += 32) s += a.partials[(size_t)r * NT + w];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) { tot[w] = s; a.terms[w] = s; }
+  const int r0 = (int)((long long)rows * blockIdx.x / FIT_RB), r1 = (int)((long long)rows * (blockIdx.x + 1) / FIT_RB);
+  float s0 = 0.f, s1 = 0.f;
+  if (lane < NT) {
+    int r = r0 + w;
+    for (; r + 8 < r1; r += 16) { s0 += a.partials[(size_t)r * NT + lane]; s1 += a.partials[(size_t)(r + 8) * NT + lane]; }
+    if (r < r1) s0 += a.partials[(size_t)r * NT + lane];
+  }
+  part[w][lane] = s0 + s1;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (w == 0 && lane < NT) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += part[q][lane];
+    a.partials[((size_t)rows + blockIdx.x) * NT + lane] = s;
+  }
+}
+__global__ void fit_reduce_kernel(HbFitArgs a) {
+  __shared__ float tot[NT];
+  const int lane = threadIdx.x;
+  const int rows = a.B * a.T;
+  if (lane < NT) {
+    float s = 0.f;
+    for (int q = 0; q < FIT_RB; ++q) s += a.partials[((size_t)rows + q) * NT + lane];
+    tot[lane] = s; a.terms[lane] = s;
+  }
+  __syncwarp();
+  if (lane == 0) {
     float l = 0.f;
     for (int i = 0; i < NT; ++i) l += a.coef[i] * tot[i];
     a.loss[0] = l;
@@ -339,15 +363,18 @@ __global__ void fit_reduce_kernel(HbFitArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // GMM negative log-likelihood (init_motion_prior_loss, fitting_loss.py:504-518) and its gradient.
-// One block per GMM_RT = 8 rows, one warp per row.  For every component the lower-triangular Linv_k (D x D, 76 KB at D = 138) is
-// staged in shared memory ONCE per block with coalesced loads and serves all 8 rows in both passes (round 1 read it row-per-lane
+// One block per GMM_RT = 2 rows.  For every component the lower-triangular Linv_k (D x D, 76 KB at D = 138) is
+// staged in shared memory with coalesced loads and serves the block's rows in both passes (round 1 read it row-per-lane
 // straight from global memory, one block per row: 684 us per call in situ, profiles/r02b_profile_step.txt):
-//   pass 1   y_k = Linv_k (x - mu_k) (lane = output row i, conflict-light row reads), maha_k = |y_k|^2, y kept in shared memory
+//   pass 1   y_k = Linv_k (x - mu_k) (4 warps per row, lane = output row i, four partial sums per dot product), maha_k = |y_k|^2,
+//            y kept in shared memory
 //   LSE      per row over the K components -> nll, responsibilities
 //   pass 2   d nll / dx = sum_k resp_k Linv_k^T y_k (thread = column, conflict-free column reads; 8 row accumulators)
 // ------------------------------------------------------------------------------------------------
-constexpr int GMM_MAXD = 160, GMM_MAXK = 32, GMM_RT = 8;
-static inline size_t gmm_smem_bytes(int D, int K) { return ((size_t)D * D + (size_t)K * GMM_RT * D + (size_t)GMM_RT * D) * sizeof(float); }
+constexpr int GMM_MAXD = 160, GMM_MAXK = 32;
+constexpr int GMM_RT = 2;                           // rows per block: 128 blocks at B = 256 (the 8-row form left 116 SMs idle: 323 us)
+constexpr int GMM_WPR = 8 / GMM_RT;                 // warps per row in pass 1
+static inline size_t gmm_smem_bytes(int D, int K) { return ((size_t)D * D + (size_t)K * GMM_RT * D + (size_t)2 * GMM_RT * D) * sizeof(float); }
 __global__ void __launch_bounds__(256) gmm_nll_kernel(int B, int D, int K, const float* __restrict__ x, const float* __restrict__ logw,
                                                        const float* __restrict__ mean, const float* __restrict__ Linv,
                                                        const float* __restrict__ logdet, float* nll, float* dx) {
@@ -355,39 +382,57 @@ __global__ void __launch_bounds__(256) gmm_nll_kernel(int B, int D, int K, const
   float* Ls = sm;                                   // [D][D]
   float* ys = Ls + (size_t)D * D;                   // [K][GMM_RT][D]
   float* xs = ys + (size_t)K * GMM_RT * D;          // [GMM_RT][D]
+  float* ds = xs + (size_t)GMM_RT * D;              // [GMM_RT][D]  x - mu_k
   __shared__ float lp[GMM_RT][GMM_MAXK];
   __shared__ float resp[GMM_RT][GMM_MAXK];
+  __shared__ float mpart[8];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * GMM_RT;
   const int nr = min(GMM_RT, B - b0);
+  const int row = w / GMM_WPR, sub = w - row * GMM_WPR;
   for (int i = tid; i < GMM_RT * D; i += 256) { const int r = i / D; xs[i] = r < nr ? x[(size_t)(b0 + r) * D + (i - r * D)] : 0.f; }
   // pass 1
   for (int k = 0; k < K; ++k) {
-    __syncthreads();                                // xs ready (k = 0) / previous component's reads of Ls done
+    __syncthreads();                                // xs ready (k = 0) / previous component's reads of Ls, ds done
     const float* L = Linv + (size_t)k * D * D;
     for (int i = tid; i < D * D; i += 256) Ls[i] = L[i];
-    __syncthreads();
     const float* mu = mean + (size_t)k * D;
+    for (int i = tid; i < GMM_RT * D; i += 256) { const int r = i / D; ds[i] = xs[i] - mu[i - r * D]; }
+    __syncthreads();
+    const float* d = ds + row * D;
     float maha = 0.f;
-    for (int i = lane; i < D; i += 32) {
-      float y = 0.f;
-      for (int j = 0; j <= i; ++j) y = fmaf(Ls[i * D + j], xs[w * D + j] - mu[j], y);
-      ys[((size_t)k * GMM_RT + w) * D + i] = y;
+    for (int i = lane + 32 * sub; i < D; i += 32 * GMM_WPR) {
+      const float* Li = Ls + (size_t)i * D;
+      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;  // four partial sums: the dot product is not one dependent chain
+      int j = 0;
+      for (; j + 3 <= i; j += 4) {
+        y0 = fmaf(Li[j], d[j], y0); y1 = fmaf(Li[j + 1], d[j + 1], y1);
+        y2 = fmaf(Li[j + 2], d[j + 2], y2); y3 = fmaf(Li[j + 3], d[j + 3], y3);
+      }
+      for (; j <= i; ++j) y0 = fmaf(Li[j], d[j], y0);
+      const float y = (y0 + y1) + (y2 + y3);
+      ys[((size_t)k * GMM_RT + row) * D + i] = y;
       maha += y * y;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maha += __shfl_xor_sync(0xffffffffu, maha, o);
-    if (lane == 0) lp[w][k] = logw[k] - 0.5f * ((float)D * 1.8378770664093453f + maha) - logdet[k];
+    if (lane == 0) mpart[w] = maha;
+    __syncthreads();
+    if (tid < GMM_RT) {
+      float m = 0.f;
+      for (int q = 0; q < GMM_WPR; ++q) m += mpart[tid * GMM_WPR + q];
+      lp[tid][k] = logw[k] - 0.5f * ((float)D * 1.8378770664093453f + m) - logdet[k];
+    }
   }
   __syncthreads();
-  if (lane == 0) {                                  // one thread per row
+  if (tid < GMM_RT) {                               // one thread per row
     float mx = -INFINITY;
-    for (int k = 0; k < K; ++k) mx = fmaxf(mx, lp[w][k]);
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, lp[tid][k]);
     float se = 0.f;
-    for (int k = 0; k < K; ++k) se += expf(lp[w][k] - mx);
+    for (int k = 0; k < K; ++k) se += expf(lp[tid][k] - mx);
     const float lse = mx + logf(se);
-    if (w < nr) nll[b0 + w] = -lse;
-    for (int k = 0; k < K; ++k) resp[w][k] = expf(lp[w][k] - lse);
+    if (tid < nr) nll[b0 + tid] = -lse;
+    for (int k = 0; k < K; ++k) resp[tid][k] = expf(lp[tid][k] - lse);
   }
   // pass 2: thread tid < D owns column tid of every row of the block
   float g[GMM_RT];
@@ -399,16 +444,25 @@ __global__ void __launch_bounds__(256) gmm_nll_kernel(int B, int D, int K, const
     for (int i = tid; i < D * D; i += 256) Ls[i] = L[i];
     __syncthreads();
     if (tid < D) {
-      float acc[GMM_RT];
+      float acc[GMM_RT][2];
 #pragma unroll
-      for (int r = 0; r < GMM_RT; ++r) acc[r] = 0.f;
-      for (int i = tid; i < D; ++i) {
-        const float l = Ls[i * D + tid];
+      for (int r = 0; r < GMM_RT; ++r) acc[r][0] = acc[r][1] = 0.f;
+      int i = tid;
+      for (; i + 1 < D; i += 2) {
+        const float l0 = Ls[(size_t)i * D + tid], l1 = Ls[(size_t)(i + 1) * D + tid];
 #pragma unroll
-        for (int r = 0; r < GMM_RT; ++r) acc[r] = fmaf(l, ys[((size_t)k * GMM_RT + r) * D + i], acc[r]);
+        for (int r = 0; r < GMM_RT; ++r) {
+          acc[r][0] = fmaf(l0, ys[((size_t)k * GMM_RT + r) * D + i], acc[r][0]);
+          acc[r][1] = fmaf(l1, ys[((size_t)k * GMM_RT + r) * D + i + 1], acc[r][1]);
+        }
+      }
+      if (i < D) {
+        const float l0 = Ls[(size_t)i * D + tid];
+#pragma unroll
+        for (int r = 0; r < GMM_RT; ++r) acc[r][0] = fmaf(l0, ys[((size_t)k * GMM_RT + r) * D + i], acc[r][0]);
       }
 #pragma unroll
-      for (int r = 0; r < GMM_RT; ++r) g[r] = fmaf(resp[r][k], acc[r], g[r]);
+      for (int r = 0; r < GMM_RT; ++r) g[r] = fmaf(resp[r][k], acc[r][0] + acc[r][1], g[r]);
     }
   }
   if (tid < D)
@@ -426,9 +480,11 @@ extern "C" int humor_fit_losses(const HbFitArgs* a, int64_t* launches, cudaStrea
   if (a->T > 1 && !a->contact_logits) return HB_ERR_ARG;
   fit_losses_kernel<<<a->B * a->T, LB, 0, st>>>(*a);
   HB_LAUNCH_CHECK();
-  fit_reduce_kernel<<<1, NT * 32, 0, st>>>(*a);
+  fit_reduce1_kernel<<<FIT_RB, 256, 0, st>>>(*a);
   HB_LAUNCH_CHECK();
-  if (launches) *launches = 2;
+  fit_reduce_kernel<<<1, 32, 0, st>>>(*a);
+  HB_LAUNCH_CHECK();
+  if (launches) *launches = 3;
   return HB_OK;
 }
 

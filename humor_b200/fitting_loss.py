@@ -58,7 +58,7 @@ class _FitFn(torch.autograd.Function):
             setattr(a, k, None if v is None else v.data_ptr())
         terms = torch.empty(HB_NUM_TERMS, device=dev, dtype=torch.float32)
         loss = torch.empty(1, device=dev, dtype=torch.float32)
-        partials = torch.empty(B * T, HB_NUM_TERMS, device=dev, dtype=torch.float32)
+        partials = torch.empty(B * T + 64, HB_NUM_TERMS, device=dev, dtype=torch.float32)      # rows + the 64 block sums of level 1
         a.terms, a.loss, a.partials = terms.data_ptr(), loss.data_ptr(), partials.data_ptr()
         nl = C.c_int64(0)
         _ext.check(L.humor_fit_losses(C.byref(a), C.byref(nl), _ext.stream_ptr()), 'humor_fit_losses')

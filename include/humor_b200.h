@@ -249,7 +249,7 @@ typedef struct HbFitArgs {
   float* d_z;
   float* d_prior_out;
   float* d_latent_pose;
-  float* partials;           /* [B*T][HB_NUM_TERMS] scratch for the deterministic reduction */
+  float* partials;           /* [B*T + 64][HB_NUM_TERMS] scratch for the deterministic two-level reduction (rows, then 64 block sums) */
 } HbFitArgs;
 int humor_fit_losses(const HbFitArgs* a, int64_t* launches, hb_stream_t stream);
 

@@ -49,6 +49,7 @@ const std::map<std::string, Thunk>& registry() {
       {"hb::mat2aa_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::mat2aa_fwd_kernel(A(int, 0), A(cf, 1), A(float*, 2))); }},
       {"hb::mat2aa_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::mat2aa_bwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(float*, 3))); }},
       {"hb::fit_losses_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_losses_kernel(A(HbFitArgs, 0))); }},
+      {"hb::fit_reduce1_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce1_kernel(A(HbFitArgs, 0))); }},
       {"hb::fit_reduce_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce_kernel(A(HbFitArgs, 0))); }},
       {"hb::gmm_nll_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::gmm_nll_kernel(A(int, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(float*, 8), A(float*, 9))); }},
       {"hb::rollout_init_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rollout_init_kernel(A(int, 0), A(int, 1), A(cf, 2), A(cf, 3), A(float*, 4), A(float*, 5), A(float*, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(float*, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},

@@ -299,6 +299,24 @@ inline void st_async_v4(uint32_t addr, float a, float b, float c, float d, uint3
   complete_if_done(bb);
 }
 inline void fence_gpu() {}
+inline void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  if ((addr & 15u) || addr + 16u > WINDOW_BYTES) { std::fprintf(stderr, "tcemu: bad st.shared.v4 address %u\n", addr); std::abort(); }
+  const float v[4] = {a, b, c, d};
+  std::memcpy(g_smem + addr, v, 16);
+}
+// cp.async.bulk.shared::cluster.shared::cta: `bytes` from this CTA's window into a peer's, completing them on the peer's barrier
+inline void bulk_s2c(uint32_t dst, uint32_t src, uint32_t bytes, uint32_t mbar) {
+  const uint32_t r = dst >> RANK_SHIFT, off = dst & ((1u << RANK_SHIFT) - 1u), rb = mbar >> RANK_SHIFT, ob = mbar & ((1u << RANK_SHIFT) - 1u);
+  if (r == 0 || r > (uint32_t)MAX_CTAS || rb != r || (off & 15u) || (src & 15u) || (bytes & 15u) || off + bytes > WINDOW_BYTES || src + bytes > WINDOW_BYTES) {
+    std::fprintf(stderr, "tcemu: bad bulk shared->cluster copy %u -> %u (%u bytes, barrier %u)\n", src, dst, bytes, mbar);
+    std::abort();
+  }
+  std::memcpy(g_cta[r - 1].smem + off, g_smem + src, bytes);
+  std::lock_guard<std::mutex> l(g_mu);
+  Bar& bb = g_cta[r - 1].bars.at(ob);
+  bb.tx -= bytes;
+  complete_if_done(bb);
+}
 // cp.async.bulk global -> shared (1-D) with mbarrier::complete_tx
 inline void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   if ((dst & 15u) || (bytes & 15u) || (reinterpret_cast<uintptr_t>(src) & 15u) || dst + bytes > WINDOW_BYTES) {

@@ -118,7 +118,7 @@ def test_motion_optimizer_run_smoke():
         assert torch.isfinite(v).all()
 
 
-@pytest.mark.parametrize('precision', ['exact', 'tensor'])
+@pytest.mark.parametrize('precision', ['exact', 'tensor', 'tensor16'])
 @pytest.mark.parametrize('name', ['stage3_rgb', 'stage3_rgb_phase1', 'stage3_rgb_refine', 'stage3_amass', 'stage3_rgb_xbatch'])
 def test_closure_matches_reference_golden(name, precision):
     """CUDA path against fixtures produced by the UNMODIFIED reference in the build container.

@@ -23,9 +23,11 @@ from tests.test_gpu_kernels import make_state  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 59
 mhz = float(sys.argv[3]) if len(sys.argv) > 3 else 1965.0
+precision = sys.argv[4] if len(sys.argv) > 4 else 'tensor'
 m = HumorModel(in_rot_rep='mat', out_rot_rep='aa', latent_size=48, model_data_config='smpl+joints+contacts', steps_in=1)
 m.load_state_dict(synth.make_humor_state_dict())
 m = m.cuda().eval()
+m.set_precision(precision)
 x0 = torch.tensor(make_state(B, 1)).cuda().requires_grad_(True)
 z = (torch.randn(B, S, 48) * 0.5).cuda().requires_grad_(True)
 L = _ext.lib()
@@ -46,7 +48,7 @@ L.humor_chain_debug(C.c_void_p(bufs['bwd'].data_ptr()), bufs['bwd'].numel() * 8)
 e[2].record()
 torch.cuda.synchronize()
 L.humor_chain_debug(None, 0)
-out = {'B': B, 'S': S, 'sm_mhz': mhz, 'rollout_fwd_ms': e[0].elapsed_time(e[1]), 'rollout_bwd_ms': e[1].elapsed_time(e[2])}
+out = {'B': B, 'S': S, 'sm_mhz': mhz, 'precision': precision, 'rollout_fwd_ms': e[0].elapsed_time(e[1]), 'rollout_bwd_ms': e[1].elapsed_time(e[2])}
 us = lambda c: c / mhz
 for d in ('fwd', 'bwd'):
     t = bufs[d].cpu().numpy().reshape(S, 5, EV).astype(np.float64)

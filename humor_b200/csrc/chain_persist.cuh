@@ -39,7 +39,7 @@ constexpr int CH_SLAB = CH_XROWS * CH_XLD * 4;                 // one 32-row par
 constexpr int CH_GLUE_W = CH_SLAB / 4;                         // floats of an epilogue warp's staging area: its outgoing slab, and the glue's
 static_assert(CH_GLUE_W >= GLUE_BWD_SMEM, "the glue's row arrays live in the slab staging area");   // row arrays between tiles
 constexpr int CH_GLUE = 4 * CH_SLAB;
-constexpr int CH_PF_W = 340 + 216 + 348 + 12;                  // reverse glue: prefetched xin | raw | d world | G of the next step
+constexpr int CH_PF_W = 340 + 216 + 348 + 12 + 352;            // reverse glue: prefetched xin | raw | d world | G | d xin (prior) of the next step
 constexpr int CH_PF = 2 * CH_PF_W * 4;                         // one set per warp pair
 constexpr int CH_BARS = 256;
 constexpr int CH_SMEM = CH_STAGES * CH_STAGE + CH_XBUF + CH_GLUE + CH_PF + CH_BARS + 1024 /*align slack*/;
@@ -307,11 +307,13 @@ chain_kernel(const __grid_constant__ ChainParams p) {
       const ChainGlue& gl = p.glue;
       const size_t r = (size_t)t * B + b_first;
       fence_proxy_async();                                       // generic reads of the prefetch set -> async-proxy writes
-      mbar_expect_tx(gbar, CH_PF_W * 4);
+      const bool px = t + 1 < S;                                 // the last step has no successor: no d xin row from the prior
+      mbar_expect_tx(gbar, (CH_PF_W - (px ? 0 : 352)) * 4);
       bulk_g2s(pf_a, gl.xins + r * XIN_LD, 340 * 4, gbar);
       bulk_g2s(pf_a + 340 * 4, gl.raws + r * RAW_LD, RAW_D * 4, gbar);
       bulk_g2s(pf_a + 556 * 4, gl.dworld + r * WORLD_LD, WORLD_LD * 4, gbar);
       bulk_g2s(pf_a + 904 * 4, gl.Gs + r * 12, 12 * 4, gbar);
+      if (px) bulk_g2s(pf_a + 916 * 4, gl.dpx + (r + B) * 352, 352 * 4, gbar);   // the batched prior's d xin of step t+1
     };
     if (prefetch && lead) prefetch_rows(S - 1);
     auto run_glue = [&](int u, int t) {
@@ -353,7 +355,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           io.xr = gl.xins + r * XIN_LD; io.rr = gl.raws + r * RAW_LD; io.wr = gl.dworld + r * WORLD_LD;
           io.G = prefetch ? pf + 904 : gl.Gs + r * 12; io.staged = prefetch ? 1 : 0;
           io.t2j = gl.t2j + b * 4; io.have_next = u > 0;
-          io.a0 = gl.da0 + (size_t)b * XIN_LD; io.px = gl.dpx + (r + B) * 352; io.xs = gl.dxres + (size_t)b * 340;
+          io.a0 = gl.da0 + (size_t)b * XIN_LD; io.px = prefetch ? pf + 916 : gl.dpx + (r + B) * 352; io.xs = gl.dxres + (size_t)b * 340;
           io.dGn = ((t + 1) & 1 ? gl.dG1 : gl.dG0) + (size_t)b * 12; io.dG = (t & 1 ? gl.dG1 : gl.dG0) + (size_t)b * 12;
           io.dt2j = gl.dt2j + b * 4; io.dzt = nullptr;
           io.dh1 = io.dh1_lo = io.dh2 = io.dh2_lo = io.dh3 = io.dh3_lo = nullptr;

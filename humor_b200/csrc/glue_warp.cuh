@@ -336,6 +336,7 @@ __device__ __forceinline__ void glue_pair_sync(int pi) { asm volatile("bar.sync 
 template <bool CG>
 __device__ __forceinline__ void glue_fwd_pair(const GlueFwdRow& io, int role, int lane, int pi, float* sx, float* sr, float* sn, float* sw) {
   const int l64 = role * 32 + lane;
+  const float zv = (io.zt && l64 < 48) ? io.zt[l64] : 0.f;      // z of the next step: an HBM first touch, requested before anything else
   for (int i = l64; i < STATE_D; i += 64) sx[i] = glue_ld<CG>(io.xr + i);
   for (int i = l64; i < RAW_D; i += 64) sr[i] = glue_ld<CG>(io.rr + i);
   glue_pair_sync(pi);
@@ -409,7 +410,7 @@ __device__ __forceinline__ void glue_fwd_pair(const GlueFwdRow& io, int role, in
   for (int i = l64; i < WORLD_LD; i += 64) io.wo[i] = sw[i];
   if (io.zt) {
     for (int i = l64; i < 48; i += 64) {
-      const float v = io.zt[i];
+      const float v = zv;
       io.xn[STATE_D + i] = v;
       if (io.xn_lo) glue_put(io.xn_hi, io.xn_lo, STATE_D + i, v);
       if (io.xn16_h) {

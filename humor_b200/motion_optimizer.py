@@ -585,6 +585,8 @@ class MotionOptimizer():
         self._save_stage(stages_res_out, 'stage1_results.npz', body_pose)
         per_stage_outputs['stage2'], body_pose = self._stage12(observed_data, 1, num_iter[1], lr, lbfgs_max_iter)
         self._save_stage(stages_res_out, 'stage2_results.npz', body_pose)
+        stage2 = {'trans': self.trans.clone().detach(), 'root_orient': self.root_orient.clone().detach(),
+                  'pose_body': body_pose.clone().detach(), 'betas': self.betas.clone().detach()}
 
         # ---- Stage III set-up (motion_optimizer.py:332-404)
         self.fitting_loss.set_stage(2)
@@ -610,6 +612,19 @@ class MotionOptimizer():
         self.betas = leaf(self.betas)
         if self.optim_floor:
             self.floor_plane = leaf(self.floor_plane)
+        # ---- initialisation stats (motion_optimizer.py:406-455): one roll-out of the initial state, before any Stage-III iteration
+        with torch.no_grad():
+            roll0, cam0 = self.rollout_latent_motion(self.trans, self.root_orient, self.latent2pose(self.latent_pose), self.betas,
+                                                     [self.trans_vel, self.joints_vel, self.root_orient_vel], self.latent_motion,
+                                                     fit_gender=fit_gender)
+            init_pred, _ = self.smpl_results(cam0['trans'], cam0['root_orient'], cam0['pose_body'], self.betas)
+            init_pred['contacts'] = roll0['contacts']
+            per_stage_outputs['stage3_init'] = init_pred
+            self._save_dict(stages_res_out, 'stage3_init_results.npz', self.betas, cam0['trans'], cam0['root_orient'], cam0['pose_body'],
+                            contacts=roll0['contacts'], floor=self.floor_plane if self.optim_floor else None)
+            if self.optim_floor:
+                self._save_dict(stages_res_out, 'stage3_init_results_prior.npz', self.betas, roll0['trans'], roll0['root_orient'],
+                                cam0['pose_body'], contacts=roll0['contacts'])
         init_params = [self.trans, self.root_orient, self.latent_pose, self.trans_vel, self.joints_vel, self.root_orient_vel]
         all_params = self.stage3_params()
         frozen = [self.latent_motion, self.betas] + ([self.floor_plane] if self.optim_floor else [])
@@ -661,8 +676,29 @@ class MotionOptimizer():
             per_stage_outputs['stage3'] = stage3
             final = self.get_optim_result(body_pose)
             final['contacts'] = roll['contacts']
-        self._save_stage(stages_res_out, 'stage3_results.npz', body_pose, contacts=roll['contacts'])
+            if self.optim_floor and stages_res_out is not None:
+                # Stage-II result in the prior frame of the FINAL floor (motion_optimizer.py:650-674); stage3_results.npz itself is
+                # written by the caller's save_optim_result (io_formats.py), with the 4-parameter floor plane
+                j2 = self.joints_only(stage2['trans'], stage2['root_orient'], stage2['pose_body'], stage2['betas'])
+                R2, t2, h2 = compute_cam2prior(self.floor_plane, stage2['trans'][:, 0], stage2['root_orient'][:, 0], j2[:, 0])
+                p2 = self.apply_cam2prior(stage2, R2, t2, h2, stage2['pose_body'], stage2['betas'], self.init_fidx)
+                self._save_dict(stages_res_out, 'stage2_results_prior.npz', self.betas, p2['trans'], p2['root_orient'], stage2['pose_body'])
         return final, per_stage_outputs
+
+    def _save_dict(self, stages_res_out, fname, betas, trans, root_orient, pose_body, contacts=None, floor=None):
+        """One npz per sub-sequence with the reference's keys (motion_optimizer.py:424-455, 665-674)."""
+        if stages_res_out is None:
+            return
+        import os
+        cpu = lambda t: t.clone().detach().cpu().numpy()
+        b, tr, ro, bp = cpu(betas), cpu(trans), cpu(root_orient), cpu(pose_body)
+        for i, path in enumerate(stages_res_out):
+            d = {'betas': b[i], 'trans': tr[i], 'root_orient': ro[i], 'pose_body': bp[i]}
+            if contacts is not None:
+                d['contacts'] = cpu(contacts[i])
+            if floor is not None:
+                d['floor_plane'] = cpu(floor[i])
+            np.savez(os.path.join(path, fname), **d)
 
     def _save_stage(self, stages_res_out, fname, body_pose, contacts=None):
         """per-stage npz dumps with the reference's keys (motion_optimizer.py:260-270,312-322)."""
@@ -675,6 +711,4 @@ class MotionOptimizer():
             d = {'betas': b[i], 'trans': tr[i], 'root_orient': ro[i], 'pose_body': bp[i]}
             if contacts is not None:
                 d['contacts'] = cpu(contacts[i])
-            if self.optim_floor and fname.startswith('stage3'):
-                d['floor_plane'] = cpu(self.floor_plane[i])
             np.savez(os.path.join(path, fname), **d)

@@ -11,6 +11,7 @@ import torch
 
 from humor_b200 import synth
 from oracle import ref_closure
+from tests import golden_util as GU
 from tests import util_stage3 as U
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'run_rgb.npz')
@@ -24,8 +25,14 @@ def reference_run(cfg=CFG):
     mo.fitting_loss.set_stage(0)
     mo.stage3_tune_init_num_frames, mo.stage3_tune_init_freeze_start, mo.stage3_tune_init_freeze_end = cfg['tune_init']
     obs = {k: torch.as_tensor(v) for k, v in prob['obs'].items() if k in U.obs_keys(True)}
-    res, stages = mo.run(obs, num_iter=list(cfg['num_iter']), lbfgs_max_iter=cfg['lbfgs_max_iter'])
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        dirs = GU.make_stage_dirs(tmp, cfg['B'])
+        res, stages = mo.run(obs, num_iter=list(cfg['num_iter']), lbfgs_max_iter=cfg['lbfgs_max_iter'], stages_res_out=dirs)
+        files = GU.collect_stage_files(dirs)    # the per-stage dumps run() writes itself (motion_optimizer.py:424-455, 665-674)
     out = {k: v.detach().numpy() for k, v in res.items()}
+    out.update(files)
+    out['stage3_init_joints3d'] = stages['stage3_init']['joints3d'].detach().numpy()
     out['stage3_verts3d'] = stages['stage3']['verts3d'].detach().numpy()
     out['stage1_joints3d'] = stages['stage1']['joints3d'].detach().numpy()
     out['stage2_joints3d'] = stages['stage2']['joints3d'].detach().numpy()

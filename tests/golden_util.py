@@ -48,3 +48,27 @@ def load_case12(name):
     wset = str(g['wset'])
     return g, dict(B=B, T=T, stage=stage, optim_floor=bool(of), wset=wset, W12=synth.stage12_weights(wset),
                    W3=synth.WEIGHT_SETS[wset], obs=obs, params=synth.make_stage12_params(B, T, seed=seed + 1), cam_mat=prob['cam_mat'])
+
+
+STAGE_FILES = ('stage1_results', 'stage2_results', 'stage3_init_results', 'stage3_init_results_prior', 'stage2_results_prior')
+
+
+def make_stage_dirs(root, B):
+    """One output directory per sub-sequence, as run_fitting.py hands them to MotionOptimizer.run(stages_res_out=...)."""
+    import os
+    dirs = [os.path.join(str(root), str(i)) for i in range(B)]
+    for d in dirs:
+        os.makedirs(d, exist_ok=True)
+    return dirs
+
+
+def collect_stage_files(dirs):
+    """The per-stage npz dumps of run() as {'file_<name>_<key>': (B, ...)} - the layout oracle/make_golden_run.py stores."""
+    import os
+    import numpy as np
+    out = {}
+    for f in STAGE_FILES:
+        per = [np.load(os.path.join(d, f + '.npz')) for d in dirs]
+        for k in per[0].files:
+            out['file_%s_%s' % (f, k)] = np.stack([q[k] for q in per], 0)
+    return out

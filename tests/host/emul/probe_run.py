@@ -23,8 +23,15 @@ mo.fitting_loss.set_stage(0)
 mo.use_cuda_graph = False
 mo.stage3_tune_init_num_frames, mo.stage3_tune_init_freeze_start, mo.stage3_tune_init_freeze_end = 4, 1, 2
 obs = {k: torch.as_tensor(v) for k, v in prob['obs'].items() if k in U.obs_keys(True)}
-res, stages = mo.run(obs, num_iter=[n1, n2, n3], lbfgs_max_iter=mi)
+import tempfile  # noqa: E402
+from tests import golden_util as GU  # noqa: E402
+with tempfile.TemporaryDirectory() as tmp:
+    dirs = GU.make_stage_dirs(tmp, B)
+    res, stages = mo.run(obs, num_iter=[n1, n2, n3], lbfgs_max_iter=mi, stages_res_out=dirs)
+    files = GU.collect_stage_files(dirs)
+    assert not any(__import__('os').path.exists(d + '/stage3_results.npz') for d in dirs)      # written by save_optim_result only
 np.savez(out_path, **{k: v.detach().numpy() for k, v in res.items()},
          stage3_verts3d=stages['stage3']['verts3d'].detach().numpy(), stage1_joints3d=stages['stage1']['joints3d'].detach().numpy(),
-         stage2_joints3d=stages['stage2']['joints3d'].detach().numpy())
+         stage2_joints3d=stages['stage2']['joints3d'].detach().numpy(),
+         stage3_init_joints3d=stages['stage3_init']['joints3d'].detach().numpy(), **files)
 print('{"ok": true}')

@@ -101,6 +101,17 @@ def check_run_result(got, g):
     for k, tol in RUN_TOL.items():
         assert np.abs(got[k] - g[k]).max() <= tol, (k, float(np.abs(got[k] - g[k]).max()))
     assert np.array_equal(got['contacts'], g['contacts'])
+    # Stage-III initialisation outputs and the per-stage npz dumps of run() (motion_optimizer.py:406-455, 650-674): same files,
+    # same keys, same values as the reference wrote
+    assert np.abs(got['stage3_init_joints3d'] - g['stage3_init_joints3d']).max() <= 3e-5
+    names = [k for k in g.files if k.startswith('file_')]
+    assert sorted(names) == sorted(k for k in got.keys() if k.startswith('file_'))
+    for k in names:
+        assert got[k].shape == g[k].shape, k
+        if k.endswith('_contacts'):
+            assert np.array_equal(got[k], g[k]), k
+        else:
+            assert np.abs(got[k] - g[k]).max() <= 5e-5, (k, float(np.abs(got[k] - g[k]).max()))
 
 
 @pytest.mark.skipif(not os.environ.get('HB_SLOW_TESTS'), reason='~6 min on the CPU emulation: set HB_SLOW_TESTS=1')

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.parametrize('precision,graph', [('exact', False), ('tensor', True)])
-def test_run_end_to_end_matches_reference_run(precision, graph):
+def test_run_end_to_end_matches_reference_run(precision, graph, tmp_path):
     """'exact': fp32 FFMA kernels, eager launches.  'tensor' (the default mode of the product: tcgen05 3xTF32 GEMMs, persistent
     decoder chain, fused LBS, CUDA-graphed closure): measured on the B200 it lands as close to the reference's result as 'exact'
     does (profiles/r02g_tolerances.jsonl: trans 2.5e-6, pose_body 1.5e-6, latent_motion 1.06e-4 in both modes), so both share
@@ -32,8 +32,12 @@ def test_run_end_to_end_matches_reference_run(precision, graph):
     mo.use_cuda_graph = graph
     mo.stage3_tune_init_num_frames, mo.stage3_tune_init_freeze_start, mo.stage3_tune_init_freeze_end = CFG['tune_init']
     obs = {k: torch.as_tensor(v).cuda() for k, v in prob['obs'].items() if k in U.obs_keys(True)}
-    res, stages = mo.run(obs, num_iter=list(CFG['num_iter']), lbfgs_max_iter=CFG['lbfgs_max_iter'])
+    from tests import golden_util as GU
+    dirs = GU.make_stage_dirs(tmp_path, CFG['B'])
+    res, stages = mo.run(obs, num_iter=list(CFG['num_iter']), lbfgs_max_iter=CFG['lbfgs_max_iter'], stages_res_out=dirs)
     got = {k: v.detach().cpu().numpy() for k, v in res.items()}
+    got.update(GU.collect_stage_files(dirs))
+    got['stage3_init_joints3d'] = stages['stage3_init']['joints3d'].detach().cpu().numpy()
     for s in ('stage1', 'stage2'):
         got[s + '_joints3d'] = stages[s]['joints3d'].detach().cpu().numpy()
     got['stage3_verts3d'] = stages['stage3']['verts3d'].detach().cpu().numpy()

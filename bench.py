@@ -294,8 +294,8 @@ def run_product(args):
         if out['torch_cuda_port'].get('frames_per_s'):
             out['vs_torch_cuda_port'] = {'ratio': value / out['torch_cuda_port']['frames_per_s'], 'e2e_ratio': e2e / out['torch_cuda_port']['frames_per_s'],
                                          'same_batch': out['torch_cuda_port'].get('batch') == B, 'target': 20.0}
-        # the opt-in kernel forms of the dense LBS forward, verified against the default forms and timed stand-alone on this GPU
-        # (separate child processes: a form that faults must not take the measurement down).  The step above ran forms 1/1.
+        # the kernel forms of the dense LBS forward (default 3/5, its 3xTF32 sibling 3/1, the round-1 two-kernel form 1/1), verified
+        # against form 1/1 and timed stand-alone on this GPU (separate child processes: a fault must not take the measurement down)
         out['roofline_candidates'] = lbs_candidates(B, T, hbm_peak)
         # opt-in modes of the STEP (never the default), each a complete child run of this script on the same seeded problem;
         # `verified` = its loss and gradient norm agree with the run above
@@ -332,12 +332,9 @@ def lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind):
     from humor_b200 import _ext
     us, ub = C.c_int(0), C.c_int(0)
     _ext.lib().humor_lbs_forms_used(C.byref(us), C.byref(ub))
-    if (us.value, ub.value) != (1, 1):          # opt-in kernel forms (humor_lbs_configure): no ncu capture of these yet
-        blend = {1: 'umma_gemm3_kernel<128,BIAS>', 2: 'lbs_blend_kernel', 3: 'lbs_blend_kernel (single-pass pose columns)'}.get(ub.value)
-        skin = {1: 'lbs_skin_apply_kernel', 2: 'lbs_skin_group_kernel'}.get(us.value)
+    if (us.value, ub.value) != (1, 1):          # the fused kernel (humor_lbs_configure skin form 3)
         name = ('dense LBS forward: lbs_pose_kernel + lbs_fuseg_kernel (persistent tcgen05 blend + group skinning' +
-                ({3: ', single-pass pose columns)', 4: ', fp16 pose columns)', 5: ', fp16 hi/lo planes)'}.get(ub.value, ')'))) if us.value == 3 else \
-            f'dense LBS forward: lbs_pose_kernel + per slab {blend} + {skin}'
+                (', fp16 hi/lo planes)' if ub.value == 5 else ', 3xTF32 planes)'))
         traffic, tsrc = None, None
         if (us.value, ub.value) == (3, 5):
             # dram__bytes_read.sum + dram__bytes_write.sum of lbs_fuseg_kernel, ncu --set full of one 15 360-frame launch
@@ -474,13 +471,13 @@ def port_cuda_child(args, batch=64, limit_s=150):
 
 def lbs_candidates(B, T, hbm_peak):
     """tools/lbs_forms_time.py in bounded children: per opt-in form {used, ms, GBps, frac, max |dv| vs forms 1/1, deterministic,
-    verified}.  Two groups, the hardware-riskier fused forms last, so a fault there keeps the records of the first group."""
+    verified}.  One child per form, so a fault in one keeps the records of the others."""
     tool = os.path.join(ROOT, 'tools', 'lbs_forms_time.py')
     env = dict(os.environ)
     for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'HB_LBS_SKIN', 'HB_LBS_BLEND'):
         env.pop(k, None)
     recs = []
-    for forms in ('2,1;1,2;2,2;2,3', '3,1;3,3;3,4;3,5'):
+    for forms in ('1,1', '3,1', '3,5'):
         left = _time_left() - 20.0
         if left < 40.0:
             recs.append({'forms': forms, 'error': 'skipped: the run\'s time limit was nearly spent'})
@@ -623,8 +620,8 @@ def main():
     ap.add_argument('--precision', default='tensor', choices=['tensor', 'exact', 'tensor16'],
                     help="'tensor': GEMMs on tcgen05 (3xTF32); 'exact': fp32 FFMA kernels (gradient-exact parity mode); "
                          "'tensor16': 'tensor' with the forward decoder chain on fp16 hi/lo operand planes (opt-in)")
-    ap.add_argument('--lbs-skin', type=int, default=0, help='dense LBS skinning pass form (humor_lbs_configure): 1 lane=vertex, 2 lane=frame, 3 fused blend + lane=frame skinning (one persistent kernel)')
-    ap.add_argument('--lbs-blend', type=int, default=0, help='dense LBS blend GEMM form: 1 tile per CTA, 2 persistent 128x256 tiles, 3 = 2 + single TF32 pass on the pose columns, 4 (skin 3) = fp16 pose columns, 5 (skin 3) = fp16 hi/lo planes for every column (fp32-level)')
+    ap.add_argument('--lbs-skin', type=int, default=0, help='dense LBS form (humor_lbs_configure): 3 (default) fused blend + lane=frame group skinning in one persistent kernel, 1 blend GEMM + lane=vertex skin pass')
+    ap.add_argument('--lbs-blend', type=int, default=0, help='dense LBS blend operand form: 5 (default, skin 3) fp16 hi/lo planes for every column (fp32-level), 1 three TF32 passes on fp32 hi/lo planes')
     ap.add_argument('--lbs-slab', type=int, default=0, help='frames per v_posed slab (128..512)')
     ap.add_argument('--no-halo', action='store_true', help='diagnostic: N independent replicas (no overlap coupling between ranks, no collective)')
     ap.add_argument('--no-graph', action='store_true', help='evaluate the closure eagerly instead of replaying a CUDA graph')

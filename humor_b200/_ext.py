@@ -68,11 +68,8 @@ class HbLbsModel(C.Structure):
                 ('w_val', C.c_void_p), ('parents', C.c_void_p), ('extra_ids', C.c_void_p),
                 ('blend_t_hi', C.c_void_p), ('blend_t_lo', C.c_void_p), ('use_umma', C.c_int), ('max_depth', C.c_int),
                 ('depth', C.c_void_p), ('child_start', C.c_void_p), ('child_list', C.c_void_p),
-                ('fblend_hi', C.c_void_p), ('fblend_lo', C.c_void_p), ('fw_idx', C.c_void_p), ('fw_val', C.c_void_p),
-                ('fused_nct', C.c_int), ('fused_wk', C.c_int),
                 ('g_start', C.c_void_p), ('g_joint', C.c_void_p), ('g_w', C.c_void_p), ('num_groups', C.c_int),
                 ('ft_nct', C.c_int), ('g_slot', C.c_void_p), ('ft_tab', C.c_void_p),
-                ('blend_k0_hi', C.c_void_p), ('blend_k0_lo', C.c_void_p), ('blend16', C.c_void_p),
                 ('blend16a_h', C.c_void_p), ('blend16a_l', C.c_void_p)]
 
 

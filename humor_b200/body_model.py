@@ -73,23 +73,7 @@ def pack_smplh(asset, num_betas=16):
     kids = [[c for c in range(1, NUM_JOINTS) if par[c] == j] for j in range(NUM_JOINTS)]
     child_start = np.cumsum([0] + [len(k) for k in kids]).astype(np.int32)
     child_list = np.asarray([c for k in kids for c in k], np.int32)
-    # fused dense forward: blend matrix in 42-vertex tile order (+ template in feature column 205), weights by joint id
-    nct = (V + 41) // 42
-    fb = np.zeros((nct * 128, 224), np.float32)
-    vid = np.arange(V)
-    rows = (vid // 42) * 128 + ((vid % 42) // 21) * 64 + ((vid % 42) % 21) * 3
-    for d in range(3):
-        fb[rows + d, :KF] = blend[:, d:3 * V:3].T
-        fb[rows + d, 205] = vt[:, d]
-    fwk = 4 if wk <= 4 else (8 if wk <= 8 else 0)
-    fw_idx = np.zeros((V, max(fwk, 1)), np.int32)
-    fw_val = np.zeros((V, max(fwk, 1)), np.float32)
-    if fwk:
-        key = np.where(w_val != 0, w_idx, NUM_JOINTS + 1)                     # zero-weight slots last
-        o2 = np.argsort(key, axis=1, kind='stable')
-        fw_idx[:, :wk] = np.take_along_axis(w_idx, o2, axis=1) * 12
-        fw_val[:, :wk] = np.take_along_axis(w_val, o2, axis=1)
-    # lane = frame skinning pass: groups of 8 consecutive vertices -> union of their joints + per-joint weight rows
+    # lane = frame group skinning (csrc/lbs_fuseg.cuh): groups of 8 consecutive vertices -> union of their joints + per-joint weight rows
     G = 8
     ng = (V + G - 1) // G
     Wf = W.astype(np.float32)
@@ -110,7 +94,6 @@ def pack_smplh(asset, num_betas=16):
     return {
         'g_start': g_start, 'g_joint': g_joint, 'g_w': np.ascontiguousarray(g_w), 'num_groups': ng,
         'g_slot': g_slot, 'ft_tab': ft_tab, 'ft_nct': ft_tab.shape[0],
-        'fblend': fb, 'fw_idx': fw_idx, 'fw_val': fw_val, 'fused_nct': nct, 'fused_wk': fwk,
         'depth': depth, 'child_start': child_start, 'child_list': child_list, 'max_depth': int(depth.max()),
         'num_verts': V, 'v3_ld': v3_ld, 'wk': wk,
         'v_template': vt.astype(np.float32).reshape(-1), 'blend': blend,
@@ -191,26 +174,11 @@ class LbsModel:
         self.t['blend_t_hi'], self.t['blend_t_lo'] = hi.contiguous(), (bt - hi).contiguous()
         s.blend_t_hi, s.blend_t_lo = self.t['blend_t_hi'].data_ptr(), self.t['blend_t_lo'].data_ptr()
         s.use_umma = 0 if os.environ.get('HB_NO_UMMA') else 1
-        fh = _tf32_rn(self.t['fblend'])
-        self.t['fblend_hi'], self.t['fblend_lo'] = fh.contiguous(), (self.t['fblend'] - fh).contiguous()
-        del self.t['fblend']
-        s.fblend_hi, s.fblend_lo = self.t['fblend_hi'].data_ptr(), self.t['fblend_lo'].data_ptr()
-        s.fw_idx, s.fw_val = self.t['fw_idx'].data_ptr(), self.t['fw_val'].data_ptr()
-        # The fused kernel is numerically identical but slower than GEMM + skin pass on assets whose neighbouring vertices
-        # do not share joints ("fused dense LBS: measured and parked"): opt-in only.
-        self.fused_wk = packed['fused_wk']
-        s.fused_nct, s.fused_wk = packed['fused_nct'], (packed['fused_wk'] if os.environ.get('HB_LBS_FUSED') else 0)
         s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
         s.num_groups = packed['num_groups']
         s.g_slot, s.ft_tab, s.ft_nct = self.t['g_slot'].data_ptr(), self.t['ft_tab'].data_ptr(), packed['ft_nct']
-        # blend form 4: blend_t * 2^10 (exact) - columns 0..31 as tf32 hi/lo planes, columns 32..223 as ONE fp16 plane (the
-        # scale keeps pose offsets down to 1e-7 m in fp16's normal range; the kernel's epilogue scales back)
-        k0 = (bt[:, :32] * 1024.0).contiguous()
-        k0h = _tf32_rn(k0)
-        self.t['blend_k0_hi'], self.t['blend_k0_lo'] = k0h.contiguous(), (k0 - k0h).contiguous()
-        self.t['blend16'] = (bt[:, 32:] * 1024.0).to(torch.float16).contiguous()
-        s.blend_k0_hi, s.blend_k0_lo, s.blend16 = (self.t[k].data_ptr() for k in ('blend_k0_hi', 'blend_k0_lo', 'blend16'))
-        # blend form 5: every column, K padded to 256, fp16 hi + UNSCALED fp16 lo plane (x = h + l)
+        # blend form 5: blend_t * 2^10 (exact: keeps pose offsets down to 1e-7 m in fp16's normal range; the kernel's epilogue scales
+        # back), every column, K padded to 256, as fp16 hi + UNSCALED fp16 lo plane (x = h + l)
         bs = torch.zeros(packed['v3_ld'], 256, device=self.device)
         bs[:, :224] = bt * 1024.0
         bh = bs.to(torch.float16)

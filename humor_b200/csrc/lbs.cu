@@ -17,7 +17,6 @@
 #include "common.cuh"
 #include "lbs_chain.cuh"
 #include "umma_launch.cuh"
-#include "lbs_skin_group.cuh"
 #include "../../include/humor_b200.h"
 
 namespace hb {
@@ -673,16 +672,16 @@ __global__ void lbs_pose_bwd_kernel(HbLbsModel m, int N, int fpb, const float* _
 }
 
 static const bool g_thread_pose = (getenv("HB_LBS_THREAD") != nullptr);
-static const bool g_unfused = (getenv("HB_LBS_UNFUSED") != nullptr);
-// dense skinning pass: 1 = lane-per-vertex (lbs_skin_apply_kernel), 2 = lane-per-frame over vertex groups (lbs_skin_group.cuh),
-// 3 (DEFAULT since round 2: 1.49 ms vs 3.35 ms per 15 360 frames on the B200, profiles/r02a_bench_s3b5.json) = blend GEMM + group
-// skinning fused in one persistent tcgen05 kernel (lbs_fuseg.cuh)
+// dense skinning pass: 1 = blend GEMM (umma_gemm3_kernel, v_posed slabs through L2) + lane-per-vertex lbs_skin_apply_kernel (the
+// round-1 default, kept as the form for meshes without group tables and as the A/B partner), 3 (DEFAULT since round 2: 1.06 ms vs
+// 3.35 ms per 15 360 frames on the B200, profiles/r02g_*) = blend GEMM + group skinning fused in one persistent tcgen05 kernel
+// (lbs_fuseg.cuh).  Forms 2 (lane-per-frame skin pass, persistent 128x256 blend) and the round-1 fused kernel measured slower and
+// were removed (records: profiles/r01*, r02a*).
 static int g_skin_form = getenv("HB_LBS_SKIN") ? atoi(getenv("HB_LBS_SKIN")) : 3;
-static int g_sm_count = 0;
 static int g_used_skin = 0, g_used_blend = 0;   // forms the last dense tensor-core call actually ran (0: none yet)
-// blend GEMM of the dense forward: 1 = one 128x128 tile per CTA (umma_gemm3_kernel), 2 = persistent 128x256 tiles (lbs_blend.cuh);
-// with skin form 3: 5 (DEFAULT) = fp16 hi + lo operand planes, three products per k-block - the accuracy of three TF32 passes
-// (vertices within 5e-6 m of form 1) from 4-byte operand elements
+// blend contraction: 1 = three TF32 passes on fp32 hi/lo planes; with skin form 3 also 5 (DEFAULT) = fp16 hi + lo operand planes,
+// three products per k-block - the accuracy of three TF32 passes (vertices within 5e-6 m of form 1) from 4-byte operand elements.
+// (Forms 3 and 4 - single-pass pose columns in tf32 / fp16, <= 7e-5 m - lost to form 5 on both speed and accuracy: removed.)
 static int g_blend_form = getenv("HB_LBS_BLEND") ? atoi(getenv("HB_LBS_BLEND")) : 5;
 static int g_slab = getenv("HB_LBS_SLAB") ? atoi(getenv("HB_LBS_SLAB")) : 0;
 static const size_t SKIN_FWD_SMEM = (size_t)SK_FT * LBS_KF * sizeof(float);
@@ -694,7 +693,7 @@ static const size_t SKIN_BWD_SMEM = (size_t)(BW_FT * LBS_KF + 3 * BW_FT * 192 + 
 using namespace hb;
 
 extern "C" int humor_lbs_configure(int skin_form, int blend_form, int slab_frames) {
-  if ((skin_form < 0 || skin_form > 3) || (blend_form < 0 || blend_form > 5) ||
+  if ((skin_form != 0 && skin_form != 1 && skin_form != 3) || (blend_form != 0 && blend_form != 1 && blend_form != 5) ||
       (slab_frames != 0 && (slab_frames < 128 || slab_frames > TC_SLAB)))
     return HB_ERR_ARG;
   if (skin_form) g_skin_form = skin_form;
@@ -732,16 +731,14 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
                                                need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
                                                tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);
   HB_LAUNCH_CHECK(); ++nl;
-  // skin form 3: one persistent tcgen05 kernel, blend accumulators skinned straight out of TMEM by lane = frame (lbs_fuseg.cuh);
-  // blend form 3 selects its single-pass pose columns, any other value the three-pass blend (reported as 1)
+  // skin form 3: one persistent tcgen05 kernel, blend accumulators skinned straight out of TMEM by lane = frame (lbs_fuseg.cuh)
   const bool fuseg = tc && g_skin_form == 3 && m->ft_tab && m->g_slot && m->g_start && m->g_joint && m->g_w && m->num_groups > 0 &&
                      m->ft_nct == cdiv(m->num_groups, 8) && (m->num_verts % 2) == 0 && m->v3_ld % 4 == 0;
   if (fuseg) {
     LbsFusegArgs fa;
-    const bool f16 = g_blend_form == 4 && m->blend16 && m->blend_k0_hi && m->blend_k0_lo;
     const bool f16x3 = g_blend_form == 5 && m->blend16a_h && m->blend16a_l;
-    fa.N = N; fa.num_verts = m->num_verts; fa.num_groups = m->num_groups; fa.nrt = fa.nct = 0; fa.fast = g_blend_form == 3 || f16;
-    fa.nkb16 = f16x3 ? 4 : (f16 ? 3 : 0); fa.f16x3 = f16x3 ? 1 : 0; fa.out_scale = (f16 || f16x3) ? 0.0009765625f : 1.f;
+    fa.N = N; fa.num_verts = m->num_verts; fa.num_groups = m->num_groups; fa.nrt = fa.nct = 0;
+    fa.nkb16 = f16x3 ? 4 : 0; fa.out_scale = f16x3 ? 0.0009765625f : 1.f;
     fa.g_start = m->g_start; fa.g_joint = m->g_joint; fa.g_slot = m->g_slot; fa.g_w = m->g_w; fa.ft_tab = m->ft_tab;
     fa.v_template = m->v_template; fa.A = ws.A; fa.trans = trans; fa.out = verts;
     if (f16x3) {
@@ -752,26 +749,11 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
       ++nl;
       HB_CUDA(launch_lbs_fuseg(nullptr, nullptr, TC_KF, nullptr, nullptr, TC_KF, m->v3_ld, 0, f16h, m->blend16a_h, f16l, m->blend16a_l, 256,
                                fa, st));
-    } else if (f16) {
-      // columns 0..31 (betas + first pose columns): three tf32 passes on the 2^10-scaled planes; columns 32..223: one fp16 pass
-      HB_CUDA(launch_feat_f16(ws.feat, LBS_KF, LBS_KF, N, 32, 3, ws.feat16, nullptr, st));
-      ++nl;
-      HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_k0_hi, m->blend_k0_lo, 32, m->v3_ld, 32, ws.feat16, m->blend16, nullptr,
-                               nullptr, 192, fa, st));
     } else {
       HB_CUDA(launch_lbs_fuseg(ws.feat_hi, ws.feat_lo, TC_KF, m->blend_t_hi, m->blend_t_lo, TC_KF, m->v3_ld, TC_KF, nullptr, nullptr, nullptr,
                                nullptr, 0, fa, st));
     }
-    g_used_skin = 3; g_used_blend = f16x3 ? 5 : (f16 ? 4 : (fa.fast ? 3 : 1));
-    ++nl;
-    if (joints && njo == 73) {
-      lbs_gather_extra_kernel<<<cdiv(N * 21, 256), 256, 0, st>>>(*m, N, verts, joints);
-      HB_LAUNCH_CHECK(); ++nl;
-    }
-  } else if (tc && m->fblend_hi && m->fw_idx && (m->fused_wk == 4 || m->fused_wk == 8) && !g_unfused) {
-    // one persistent tcgen05 kernel: blend GEMM + skinning + coalesced store (lbs_fused.cuh)
-    HB_CUDA(launch_lbs_fused(ws.feat_hi, ws.feat_lo, TC_KF, m->fblend_hi, m->fblend_lo, TC_KF, N, m->num_verts, m->fused_nct,
-                             m->fused_wk, m->fw_idx, m->fw_val, ws.A, trans, verts, st));
+    g_used_skin = 3; g_used_blend = f16x3 ? 5 : 1;
     ++nl;
     if (joints && njo == 73) {
       lbs_gather_extra_kernel<<<cdiv(N * 21, 256), 256, 0, st>>>(*m, N, verts, joints);
@@ -784,42 +766,14 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
     ep.b_const = b_const;
     // frames per slab: the v_posed slab must stay in L2 between the two kernels (<= TC_SLAB rows of workspace)
     const int slab = (g_slab >= 128 && g_slab <= TC_SLAB) ? g_slab : TC_SLAB;
+    g_used_skin = g_used_blend = 1;
     for (int f0 = 0; f0 < N; f0 += slab) {
       const int nf = (N - f0 < slab) ? N - f0 : slab;
-      const bool blend2 = (g_blend_form == 2 || g_blend_form == 3) && m->v3_ld % 4 == 0;   // column tiles past v3_ld are zero-filled by TMA, never stored
-      g_used_blend = blend2 ? g_blend_form : 1;
-      if (blend2)
-        HB_CUDA(launch_lbs_blend(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
-                                 TC_KF, m->v3_ld, nf, 3 * m->num_verts, TC_KF, m->v_template, ws.vposed, m->v3_ld, g_blend_form == 3, st));
-      else
-        HB_CUDA(launch_umma_gemm3_bn(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
-                                     TC_KF, nf, 3 * m->num_verts, TC_KF, ws.vposed, nullptr, nullptr, m->v3_ld, EPI_BIAS, ep, 128, st));
-      // the last group reads up to 3*SG_G floats per row, i.e. past a row of v3_ld = 20 672 floats: harmless (zero weights, nothing
-      // stored) as long as the slab buffer has that slack after its last row - it is carved for TC_SLAB rows of 20 736 floats
-      const bool skin2 = g_skin_form == 2 && m->num_groups > 0 && m->g_start && (m->num_verts % 2) == 0 && m->v3_ld % 4 == 0 &&
-                         (size_t)TC_SLAB * 20736 >= (size_t)(nf - 1) * m->v3_ld + (size_t)m->num_groups * 3 * SG_G;
-      g_used_skin = skin2 ? 2 : 1;
-      if (skin2) {
-        static bool attr_sg = false;   // once per process, on the first (un-captured) call
-        if (!attr_sg) {
-          HB_CUDA(cudaFuncSetAttribute(lbs_skin_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_SMEM));
-          int dev = 0;
-          HB_CUDA(cudaGetDevice(&dev));
-          HB_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-          attr_sg = true;
-        }
-        // two resident blocks per SM: split the vertex groups so that one slab fills the chip about once
-        const int fblocks = cdiv(nf, SG_FT);
-        const int want = cdiv(2 * (g_sm_count > 0 ? g_sm_count : 148), fblocks);
-        const int gpb = align_up((size_t)cdiv(m->num_groups, want < 1 ? 1 : want), SG_WARPS);
-        dim3 grid(cdiv(m->num_groups, gpb), fblocks);
-        lbs_skin_group_kernel<<<grid, SG_WARPS * 32, SG_SMEM, st>>>(*m, nf, m->v3_ld, ws.vposed, ws.A + (size_t)f0 * 624,
-                                                                   trans + (size_t)f0 * 3, verts + (size_t)f0 * m->num_verts * 3, gpb);
-      } else {
-        dim3 grid(cdiv(m->num_verts, 128), cdiv(nf, SA_F));
-        lbs_skin_apply_kernel<<<grid, 128, 0, st>>>(*m, nf, m->v3_ld, ws.vposed, ws.A + (size_t)f0 * 624, trans + (size_t)f0 * 3,
-                                                    verts + (size_t)f0 * m->num_verts * 3);
-      }
+      HB_CUDA(launch_umma_gemm3_bn(ws.feat_hi + (size_t)f0 * TC_KF, ws.feat_lo + (size_t)f0 * TC_KF, TC_KF, m->blend_t_hi, m->blend_t_lo,
+                                   TC_KF, nf, 3 * m->num_verts, TC_KF, ws.vposed, nullptr, nullptr, m->v3_ld, EPI_BIAS, ep, 128, st));
+      dim3 grid(cdiv(m->num_verts, 128), cdiv(nf, SA_F));
+      lbs_skin_apply_kernel<<<grid, 128, 0, st>>>(*m, nf, m->v3_ld, ws.vposed, ws.A + (size_t)f0 * 624, trans + (size_t)f0 * 3,
+                                                  verts + (size_t)f0 * m->num_verts * 3);
       HB_LAUNCH_CHECK();
       nl += 2;
     }

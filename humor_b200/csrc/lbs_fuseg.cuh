@@ -1,50 +1,43 @@
 // Dense SMPL+H forward, skin form 3: blend GEMM + skinning in ONE persistent tcgen05 kernel with a lane = frame epilogue.
 //
-//   v_posed[frame, 3v+d] = v_template[3v+d] + feat[frame, :224] . blend_t[3v+d, :224]      (3xTF32, or `fast`: see below)
+//   v_posed[frame, 3v+d] = v_template[3v+d] + feat[frame, :224] . blend_t[3v+d, :224]      (blend form 1: 3xTF32; form 5: fp16 hi/lo, see below)
 //   out[frame, v, :]     = sum_j W[v][j] (A[frame, j] . [v_posed[frame, v]; 1]) + trans[frame]
 //
 // What the two measured predecessors taught (profiles/r01g):
 //   * lbs_skin_apply_kernel (lane = vertex) gathers <= 4 transforms of 48 B per (vertex, frame) from shared memory - the
-//     shared-memory port is its bound; lbs_fused_kernel (thread = frame, vertex by vertex) re-loads transforms from global
-//     memory whenever the joint of a weight slot changes.
+//     shared-memory port is its bound; a thread = frame kernel walking vertex by vertex (round 1, retired) re-loaded transforms
+//     from global memory whenever the joint of a weight slot changed.
 //   * the TMEM accumulator layout IS lane = frame (M = frames): a thread that reads its row with tcgen05.ld holds
-//     consecutive vertices of ONE frame, which is exactly the operand of the group-skinning form (lbs_skin_group.cuh): a
+//     consecutive vertices of ONE frame, which is exactly the operand of group skinning (vertices sorted by joint set): a
 //     transform is fetched once per (frame, joint, group of 8 vertices) and joint index / weights are warp-uniform.
 // Plan of one CTA (one per SM, 320 threads):
 //   tiles   128 frames x 192 columns (= 64 vertices = 8 groups), walked ROW-major in one contiguous chunk per CTA: ~88
 //           consecutive column tiles of the same 128 frames, so the frames' transforms stay on the SM
 //   warp 0  TMA producer: (a) operand ring of 3 entries of 40 KB = one A plane (128 x 32 floats) + one B plane (192 x 32);
-//           a three-pass k-block takes two entries (hi planes, lo planes), a single-pass one only the hi entry;
+//           a k-block takes two entries (hi planes, lo planes);
 //           (b) the 3x4 transforms of the joints the tile is skinned to, as [128 frames][12 floats] boxes cut from
 //           A[N][52*12] into 12 shared-memory slots under the host's static schedule (body_model.fuseg_tables): a joint
 //           keeps its slot while consecutive tiles need it, so a tile loads ~1 new slot (6 KB) instead of ~6
 //   warp 1  tcgen05.mma issuer; a tile's k-blocks accumulate into ONE of two 192-column TMEM buffers (K = 224: no
-//           promotion chunks needed, lbs_blend.cuh), so tile i+1's MMAs run under tile i's epilogue
+//           promotion chunks needed), so tile i+1's MMAs run under tile i's epilogue
 //   warps 2..17 epilogue: TMEM lane quadrant q = warp % 4, column quarter (warp - 2) / 4 -> 2 groups each.  Per group:
 //           tcgen05.ld 24 columns (8 vertices of the thread's frame), + template, skin with the group's joint list
 //           (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), + trans, park the 24 floats in a
 //           per-warp staging tile and write two 96-byte frame rows per instruction (a lane = frame store would touch
 //           32 different lines per instruction).
-//   `fast`  (blend form 3) k-block 0 (betas + first pose columns: shape offsets of up to 0.3 m) keeps three passes, the other
-//           six run one TF32 pass on the tf32-ROUNDED hi planes: 36 instead of 84 MMAs and 320 instead of 560 KB of operand
-//           planes per tile; <= 7e-5 m.
-//   fp16    (blend form 4) k-block 0 as in `fast`; the remaining pose columns travel as ONE fp16 plane per operand (fp16 has
-//           the 11-bit significand of tf32; the blend planes are pre-scaled by 2^10 so that pose offsets of 1e-6 m stay in
-//           fp16's normal range, the epilogue scales back): 3 entries of 64 halves instead of 6 of 32 floats - 200 KB of
-//           operand planes and 24 MMA issue slots per tile.
-//   fp16x3  (blend form 5) EVERY column as fp16 hi + lo planes, three products per k-block (h.h + l.h + h.l) into the one accumulator:
+//   fp16x3  (blend form 5, the default) EVERY column as fp16 hi + lo planes, three products per k-block (h.h + l.h + h.l) into the one accumulator:
 //           the lo planes are UNSCALED (l = fp16(x - h)); what that costs is an absolute floor of 3e-8 on tiny operands, i.e.
 //           ~1e-9 m after the 2^-10 scale-back - irrelevant here, and it keeps one accumulator per tile (a scaled lo part would
 //           need a second one: 768 TMEM columns).  fp32-level accuracy (as three TF32 passes) at 320 instead of 560 KB per tile.
 // Barrier protocol (all mbarriers, phases counted per use):
-//   full[s]/empty[s]   operand ring (TMA complete_tx / tcgen05.commit), as lbs_blend_kernel
-//   tfull[b]/tempty[b] TMEM buffer b = tile parity (tcgen05.commit / one arrive per epilogue warp), as lbs_blend_kernel
+//   full[s]/empty[s]   operand ring (TMA complete_tx / tcgen05.commit)
+//   tfull[b]/tempty[b] TMEM buffer b = tile parity (tcgen05.commit / one arrive per epilogue warp)
 //   ttf[b]             transforms of tile parity b have landed (arrive.expect_tx by the producer, complete_tx by TMA).
 //                      The producer issues tile i's transform loads only after tempty says the epilogue is done with tile
 //                      i-2 (slots tile i-1 uses are never chosen by the schedule), and after tile i-1 when the frames change
 //                      (then every slot is reloaded).
-// Same TMA / UMMA descriptor forms and TMEM protocol as lbs_fused_kernel (verified on the B200); executed on the CPU through
-// tests/host/shim/tc_emul.h (tests/test_host_tc.py).  NOT yet executed on hardware: opt-in (humor_lbs_configure(3, ...)).
+// Same TMA / UMMA descriptor forms and TMEM protocol as umma_gemm3_kernel; the default dense forward since round 2 (measured on
+// the B200: profiles/r02g_*).  Executed on the CPU through tests/host/shim/tc_emul.h (tests/test_host_tc.py).
 #pragma once
 #include "umma_gemm.cuh"
 #include "umma_launch.cuh"
@@ -160,8 +153,7 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         // ---- operand planes
         for (int kb = 0; kb < nkb; ++kb) {
-          const int npl = (!a.fast || kb == 0) ? 2 : 1;         // hi entry, then (three-pass k-blocks) lo entry
-          for (int pl = 0; pl < npl; ++pl, ++g) {
+          for (int pl = 0; pl < 2; ++pl, ++g) {                 // hi entry, then lo entry
             const int s = g % FG_RING;
             mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
             const uint32_t st = base + s * FG_ENTRY;
@@ -171,7 +163,7 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
         }
         for (int kb = 0; kb < a.nkb16; ++kb) {                  // fp16 k-blocks: 64 halves = the same 128-byte rows, same entry
-          for (int pl = 0; pl < (a.f16x3 ? 2 : 1); ++pl, ++g) {   // hi entry, then (three-product form) the lo entry
+          for (int pl = 0; pl < 2; ++pl, ++g) {                 // hi entry, then the lo entry
             const int s = g % FG_RING;
             mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
             const uint32_t st = base + s * FG_ENTRY;
@@ -200,24 +192,20 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
           for (int k = 0; k < UM_BK / 8; ++k)                   // hi . hi
             umma_tf32(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc, (kb != 0) || (k != 0));
-          if (!a.fast || kb == 0) {
-            const int gl = g++;
-            const int sl = gl % FG_RING;
-            mbar_wait(full0 + 8 * sl, (gl / FG_RING) & 1);
-            tc_fence_after();
-            const uint32_t stl = base + sl * FG_ENTRY;
+          const int gl = g++;
+          const int sl = gl % FG_RING;
+          mbar_wait(full0 + 8 * sl, (gl / FG_RING) & 1);
+          tc_fence_after();
+          const uint32_t stl = base + sl * FG_ENTRY;
 #pragma unroll
-            for (int k = 0; k < UM_BK / 8; ++k) {               // lo . hi + hi . lo
-              umma_tf32(tacc, umma_desc_sw128(stl + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc, 1);
-              umma_tf32(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(stl + FG_A_PLANE + k * 32), idesc, 1);
-            }
-            umma_commit(empty0 + 8 * sh);
-            umma_commit(empty0 + 8 * sl);
-          } else {
-            umma_commit(empty0 + 8 * sh);
+          for (int k = 0; k < UM_BK / 8; ++k) {                 // lo . hi + hi . lo
+            umma_tf32(tacc, umma_desc_sw128(stl + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc, 1);
+            umma_tf32(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(stl + FG_A_PLANE + k * 32), idesc, 1);
           }
+          umma_commit(empty0 + 8 * sh);
+          umma_commit(empty0 + 8 * sl);
         }
-        for (int kb = 0; kb < a.nkb16; ++kb) {                  // one fp16 pass: 4 MMAs of K = 16 per 64-wide k-block
+        for (int kb = 0; kb < a.nkb16; ++kb) {                  // fp16 planes: 4 MMAs of K = 16 per product and 64-wide k-block
           constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(FG_BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
           const int gh = g++;
           const int sh = gh % FG_RING;
@@ -227,22 +215,18 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
           for (int k = 0; k < 4; ++k)                           // h . h (the tile's very first MMA overwrites the accumulator)
             umma_f16(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc16, (nkb != 0) || (kb != 0) || (k != 0));
-          if (a.f16x3) {                                        // + l . h + h . l: x = h + l with UNSCALED fp16 lo planes, one accumulator
-            const int gl = g++;
-            const int sl = gl % FG_RING;
-            mbar_wait(full0 + 8 * sl, (gl / FG_RING) & 1);
-            tc_fence_after();
-            const uint32_t stl = base + sl * FG_ENTRY;
+          const int gl = g++;                                   // + l . h + h . l: x = h + l with UNSCALED fp16 lo planes, one accumulator
+          const int sl = gl % FG_RING;
+          mbar_wait(full0 + 8 * sl, (gl / FG_RING) & 1);
+          tc_fence_after();
+          const uint32_t stl = base + sl * FG_ENTRY;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(tacc, umma_desc_sw128(stl + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc16, 1);
-              umma_f16(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(stl + FG_A_PLANE + k * 32), idesc16, 1);
-            }
-            umma_commit(empty0 + 8 * sh);
-            umma_commit(empty0 + 8 * sl);
-          } else {
-            umma_commit(empty0 + 8 * sh);
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(tacc, umma_desc_sw128(stl + k * 32), umma_desc_sw128(sth + FG_A_PLANE + k * 32), idesc16, 1);
+            umma_f16(tacc, umma_desc_sw128(sth + k * 32), umma_desc_sw128(stl + FG_A_PLANE + k * 32), idesc16, 1);
           }
+          umma_commit(empty0 + 8 * sh);
+          umma_commit(empty0 + 8 * sl);
         }
         umma_commit(tfull0 + 8 * buf);
       }

@@ -6,8 +6,6 @@
 #endif
 #include "umma_gemm.cuh"
 #include "umma_launch.cuh"
-#include "lbs_fused.cuh"
-#include "lbs_blend.cuh"
 #include "lbs_fuseg.cuh"
 #include "umma_gemm16.cuh"
 #include "chain_persist.cuh"
@@ -131,70 +129,8 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
   return cudaErrorInvalidValue;
 }
 
-template <int WK>
-static cudaError_t launch_fused_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                                  int K, const LbsFusedArgs& a, int grid, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(lbs_fused_kernel<WK>, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
-  lbs_fused_kernel<WK><<<grid, 192, LF_SMEM, st>>>(a_hi, a_lo, b_hi, b_lo, K, a);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf, const float* bf_hi, const float* bf_lo, int K,
-                             int N, int num_verts, int nct, int wk, const int* fw_idx, const float* fw_val, const float* A,
-                             const float* trans, float* out, cudaStream_t st) {
-  if (!load_encode()) return cudaErrorNotSupported;
-  if (K % UM_BK || ldf % 4 || (wk != 4 && wk != 8) || nct * LF_VT < num_verts) return cudaErrorInvalidValue;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-  }
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-  if (!make_map(&ta_hi, feat_hi, N, K, ldf, UM_BM) || !make_map(&ta_lo, feat_lo, N, K, ldf, UM_BM) ||
-      !make_map(&tb_hi, bf_hi, nct * 128, K, K, 128) || !make_map(&tb_lo, bf_lo, nct * 128, K, K, 128))
-    return cudaErrorInvalidValue;
-  LbsFusedArgs a;
-  a.N = N; a.num_verts = num_verts; a.nrt = cdiv(N, UM_BM); a.nct = nct;
-  a.fw_idx = fw_idx; a.fw_val = fw_val; a.A = A; a.trans = trans; a.out = out;
-  const int ntiles = a.nrt * a.nct;
-  const int grid = ntiles < sms ? ntiles : sms;
-  return wk == 4 ? launch_fused_t<4>(ta_hi, ta_lo, tb_hi, tb_lo, K, a, grid, st)
-                 : launch_fused_t<8>(ta_hi, ta_lo, tb_hi, tb_lo, K, a, grid, st);
-}
-
-cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
-                             int b_rows, int M, int ncols, int K, const float* bias, float* C, int ldc, int fast, cudaStream_t st) {
-  if (!load_encode()) return cudaErrorNotSupported;
-  if (K % UM_BK || ldf % 4 || ldb % 4 || ldc % 4 || !bias || b_rows < ncols) return cudaErrorInvalidValue;
-  static int sms = 0;
-  static bool attr = false;
-  if (!attr) {                      // once per process, on the first (un-captured) call
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lbs_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LB_SMEM);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-  if (!make_map(&ta_hi, feat_hi, M, K, ldf, UM_BM) || !make_map(&ta_lo, feat_lo, M, K, ldf, UM_BM) ||
-      !make_map(&tb_hi, bt_hi, b_rows, K, ldb, LB_BN) || !make_map(&tb_lo, bt_lo, b_rows, K, ldb, LB_BN))
-    return cudaErrorInvalidValue;
-  const int ntiles = cdiv(M, UM_BM) * cdiv(ncols, LB_BN);
-  const int grid = ntiles < sms ? ntiles : sms;
-  lbs_blend_kernel<<<grid, 192, LB_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, M, ncols, K, bias, C, ldc, fast);
-  return cudaGetLastError();
-}
-
 // skin form 3: blend + group skinning in one persistent kernel (lbs_fuseg.cuh).  `a` arrives with the model tables, A, trans,
-// out, N, num_verts, num_groups and fast filled in; tile counts are set here.
+// out, N, num_verts, num_groups filled in; tile counts are set here.
 cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
                              int b_rows, int K, const void* feat16, const void* bt16, const void* feat16l, const void* bt16l, int ld16,
                              LbsFusegArgs a, cudaStream_t st) {
@@ -202,9 +138,8 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
   if (K % UM_BK || ldf % 4 || ldb % 4 || a.N <= 0 || a.num_groups <= 0 || (a.num_verts & 1) ||
       a.num_groups != cdiv(a.num_verts, FG_G) || !a.g_start || !a.g_joint || !a.g_slot || !a.g_w || !a.ft_tab)
     return cudaErrorInvalidValue;
-  if (a.nkb16 < 0 || (a.nkb16 > 0 && (!feat16 || !bt16 || ld16 % 8 || ld16 < 64 * a.nkb16))) return cudaErrorInvalidValue;
-  if (a.f16x3 && (a.nkb16 <= 0 || !feat16l || !bt16l)) return cudaErrorInvalidValue;
-  if (K == 0 && a.nkb16 <= 0) return cudaErrorInvalidValue;
+  if (a.nkb16 < 0 || (a.nkb16 > 0 && (!feat16 || !bt16 || !feat16l || !bt16l || ld16 % 8 || ld16 < 64 * a.nkb16))) return cudaErrorInvalidValue;
+  if ((K == 0) == (a.nkb16 <= 0)) return cudaErrorInvalidValue;          // either the tf32 planes or the fp16 planes
   static int sms = 0, want = 0, direct = 0;
   if (!sms) {
     int dev = 0;
@@ -226,14 +161,12 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
   if (K > 0 && (!make_map(&ta_hi, feat_hi, a.N, K, ldf, UM_BM) || !make_map(&ta_lo, feat_lo, a.N, K, ldf, UM_BM) ||
                 !make_map(&tb_hi, bt_hi, b_rows, K, ldb, FG_BN) || !make_map(&tb_lo, bt_lo, b_rows, K, ldb, FG_BN)))
     return cudaErrorInvalidValue;
-  if (a.nkb16 > 0 && (!make_map_f16(&ta16, feat16, a.N, 64 * a.nkb16, ld16, UM_BM) || !make_map_f16(&tb16, bt16, b_rows, 64 * a.nkb16, ld16, FG_BN)))
+  if (a.nkb16 > 0 && (!make_map_f16(&ta16, feat16, a.N, 64 * a.nkb16, ld16, UM_BM) || !make_map_f16(&tb16, bt16, b_rows, 64 * a.nkb16, ld16, FG_BN) ||
+                      !make_map_f16(&ta16l, feat16l, a.N, 64 * a.nkb16, ld16, UM_BM) || !make_map_f16(&tb16l, bt16l, b_rows, 64 * a.nkb16, ld16, FG_BN)))
     return cudaErrorInvalidValue;
-  if (a.f16x3 && (!make_map_f16(&ta16l, feat16l, a.N, 64 * a.nkb16, ld16, UM_BM) || !make_map_f16(&tb16l, bt16l, b_rows, 64 * a.nkb16, ld16, FG_BN)))
-    return cudaErrorInvalidValue;
-  // descriptors of operand kinds this launch does not use are never dereferenced: any valid one stands in
+  // descriptors of the operand kind this launch does not use are never dereferenced: any valid one stands in
   if (K == 0) { ta_hi = ta_lo = ta16; tb_hi = tb_lo = tb16; }
-  if (a.nkb16 <= 0) { ta16 = ta_hi; tb16 = tb_hi; }
-  if (!a.f16x3) { ta16l = ta16; tb16l = tb16; }
+  else { ta16 = ta16l = ta_hi; tb16 = tb16l = tb_hi; }
   const int ntiles = a.nrt * a.nct;
   int grid = ntiles < sms ? ntiles : sms;
   if (want > 0 && want < grid) grid = want;

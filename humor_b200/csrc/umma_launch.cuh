@@ -23,23 +23,13 @@ void chain_set_debug(long long* buf, size_t bytes);
 cudaError_t launch_umma_gemm16(const void* A_h, const void* A_l, int lda, const void* B_h, const void* B_l, int ldb, int M, int N, int K,
                                float* C, int ldc, void* C16_h, void* C16_l, int ld16, int epi, const GemmEpi& ep, cudaStream_t st);
 cudaError_t launch_split16(const float* x, void* h, void* l, size_t n, cudaStream_t st);
-// dense LBS forward, fused blend GEMM + skinning (lbs_fused.cuh); bf_* = blend matrix in 42-vertex tile order [nct*128][K]
-cudaError_t launch_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf, const float* bf_hi, const float* bf_lo, int K,
-                             int N, int num_verts, int nct, int wk, const int* fw_idx, const float* fw_val, const float* A,
-                             const float* trans, float* out, cudaStream_t st);
-// blend-shape contraction of the dense LBS forward as a persistent 128x256-tile kernel (lbs_blend.cuh):
-// C[M][ldc] (columns < ncols) = bias + (feat_hi+feat_lo)[M][K] . (bt_hi+bt_lo)[b_rows][K]^T
-cudaError_t launch_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
-                             int b_rows, int M, int ncols, int K, const float* bias, float* C, int ldc, int fast, cudaStream_t st);
 // dense LBS forward, skin form 3: blend GEMM + lane = frame group skinning in one persistent kernel (lbs_fuseg.cuh)
 struct LbsFusegArgs {
   int N;                   // frames
   int num_verts;
   int num_groups;
   int nrt, nct;            // row tiles (128 frames), column tiles (64 vertices)
-  int fast;                // 1: only k-block 0 keeps three TF32 passes
-  int nkb16;               // > 0 (blend forms 4, 5): after the tf32 k-blocks, this many 64-wide fp16 k-blocks (kind::f16)
-  int f16x3;               // 1 (blend form 5): the fp16 k-blocks have lo planes too: h.h + l.h + h.l (fp32-level); 0: one pass on h
+  int nkb16;               // > 0 (blend form 5): this many 64-wide fp16 k-blocks (kind::f16) on hi + lo planes: h.h + l.h + h.l
   float out_scale;         // accumulator -> metres (2^-10 when the blend planes are pre-scaled for the fp16 range, else 1)
   int direct_store;        // 1: lane = frame stores straight from registers (A/B variant), 0: staged row stores; set by the launcher
   const int* g_start;      // [num_groups + 1]
@@ -53,8 +43,8 @@ struct LbsFusegArgs {
   float* out;              // [N][num_verts][3]
 };
 // bt_* = blend_t hi/lo planes [b_rows][K] (ldb floats per row); the caller fills every field of `a` except nrt / nct.
-// a.nkb16 > 0: feat16 [N][ld16] / bt16 [b_rows][ld16] fp16 planes of the remaining K columns (ld16 halves per row, >= 64 * nkb16)
-// a.f16x3: feat16l / bt16l = the lo planes (same shapes); K may be 0 (no tf32 k-blocks)
+// a.nkb16 > 0: feat16 [N][ld16] / bt16 [b_rows][ld16] fp16 hi planes (ld16 halves per row, >= 64 * nkb16), feat16l / bt16l the
+// lo planes (same shapes); K (columns of the tf32 planes) is then 0
 cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
                              int b_rows, int K, const void* feat16, const void* bt16, const void* feat16l, const void* bt16l, int ld16,
                              LbsFusegArgs a, cudaStream_t st);

@@ -62,17 +62,8 @@ typedef struct HbLbsModel {
   const int* depth;        /* [52] */
   const int* child_start;  /* [53] */
   const int* child_list;   /* [51] */
-  /* fused dense forward (blend GEMM + skinning in one tcgen05 kernel): blend matrix in 42-vertex tile order,
-     row = tile*128 + half*64 + 3*i + d (i < 21; row 63 of each half is zero), K = 224 with column 205 = v_template,
-     split x = hi + lo; skinning weights padded to fused_wk (4 or 8) slots sorted by joint id, index = joint*12 */
-  const float* fblend_hi;  /* [fused_nct*128][224] */
-  const float* fblend_lo;
-  const int* fw_idx;       /* [num_verts][fused_wk] */
-  const float* fw_val;     /* [num_verts][fused_wk] */
-  int fused_nct;
-  int fused_wk;            /* 0: fused path unavailable */
-  /* lane = frame skinning pass (csrc/lbs_skin_group.cuh): groups of 8 consecutive vertices; per group the union of the
-     joints its vertices are skinned to and, per joint, the 8 weights (0 where a vertex is not influenced) */
+  /* lane = frame group skinning (the epilogue of csrc/lbs_fuseg.cuh): groups of 8 consecutive vertices; per group the union of
+     the joints its vertices are skinned to and, per joint, the 8 weights (0 where a vertex is not influenced) */
   const int* g_start;      /* [num_groups + 1] offsets into g_joint / g_w */
   const int* g_joint;      /* [E] joint * 12 */
   const float* g_w;        /* [E][8], 16-byte aligned */
@@ -82,11 +73,6 @@ typedef struct HbLbsModel {
   int ft_nct;              /* column tiles = ceil(num_groups / 8); 0: tables absent */
   const int* g_slot;       /* [E] byte offset of entry e's slot in the tile of its group, or -1: read A from global memory */
   const int* ft_tab;       /* [ft_nct][26] n_fresh, n_inc, 12 fresh + 12 incremental loads (joint*12 | slot << 16) */
-  /* blend form 4 (fp16 pose columns, skin form 3 only): blend_t scaled by 2^10 - columns 0..31 as tf32 hi/lo planes
-     [v3_ld][32], columns 32..223 as one fp16 plane [v3_ld][192]; NULL: form unavailable */
-  const float* blend_k0_hi;
-  const float* blend_k0_lo;
-  const void* blend16;
   /* blend form 5 (skin form 3 only): blend_t * 2^10, all 208 columns padded to 256, as fp16 hi plane and UNSCALED fp16 lo
      plane (x = h + l) [v3_ld][256] each; NULL: form unavailable */
   const void* blend16a_h;
@@ -103,16 +89,15 @@ int humor_lbs_fwd(const HbLbsModel* m, int N, int frames_per_beta, const float* 
                   size_t workspace_bytes, const int* vlist, int nv, float* verts, float* joints,
                   int num_joints_out, int64_t* launches, hb_stream_t stream);
 /* Kernel forms of the DENSE tensor-core forward (results agree to fp32 rounding; 0 leaves a setting unchanged):
- *   skin_form   1 lane = vertex (lbs_skin_apply_kernel)          2 lane = frame over vertex groups (lbs_skin_group.cuh)
- *               3 blend + lane = frame skinning fused in one persistent kernel (lbs_fuseg.cuh): blend_form 3 selects its
- *                 single-pass pose columns, any other value three passes (reported as 1); slab_frames unused
- *   blend_form  1 one 128x128 tile per CTA (umma_gemm3_kernel)   2 persistent 128x256 tiles (lbs_blend.cuh)
- *               3 = 2 with a single TF32 pass on the pose-offset columns (<= 7e-5 m vertex error; forms 1, 2: 1e-6 m)
- *               4 (with skin_form 3 only) = 3 with those columns as fp16 operand planes (same 11-bit significand, half the
- *                 bytes, kind::f16 MMAs)
- *               5 (with skin_form 3 only) every column as fp16 hi + lo planes, three products: the accuracy of forms 1, 2
+ *   skin_form   3 (default) blend + lane = frame group skinning fused in one persistent tcgen05 kernel (lbs_fuseg.cuh)
+ *               1 blend GEMM (umma_gemm3_kernel, 128x128 tiles) into v_posed slabs + lane = vertex lbs_skin_apply_kernel: the
+ *                 round-1 default; what a model without group tables falls back to
+ *   blend_form  5 (default, with skin_form 3) every column as fp16 hi + lo planes, three products: the accuracy of form 1
  *                 (1e-6 m) from 4 instead of 8 bytes per operand element
- *   slab_frames frames per v_posed slab kept in L2 between the two kernels (128..512)
+ *               1 three TF32 passes on fp32 hi/lo planes
+ *   slab_frames (skin_form 1) frames per v_posed slab kept in L2 between the two kernels (128..512)
+ * Forms 2 (lane = frame skin pass / persistent 128x256 blend), blend 3 and 4 (single-pass pose columns) and the round-1 fused
+ * kernel measured slower or less accurate on the B200 (profiles/r01*, r02a*, r02f*) and were removed: their numbers are refused.
  * Process-wide; not to be changed while a call is in flight.  Environment defaults: HB_LBS_SKIN, HB_LBS_BLEND, HB_LBS_SLAB. */
 int humor_lbs_configure(int skin_form, int blend_form, int slab_frames);
 /* The forms the most recent dense tensor-core call actually ran (a requested form falls back to form 1 when the model's

@@ -29,28 +29,17 @@ def install(lib_path):
         bt[:, :208] = self.t['blend_t']
         hi = split(bt)[0]
         self.t['blend_t_hi'], self.t['blend_t_lo'] = hi, (bt - hi).contiguous()
-        fh = split(self.t['fblend'])[0]
-        self.t['fblend_hi'], self.t['fblend_lo'] = fh, (self.t['fblend'] - fh).contiguous()
         s.blend_t_hi, s.blend_t_lo = self.t['blend_t_hi'].data_ptr(), self.t['blend_t_lo'].data_ptr()
-        s.fblend_hi, s.fblend_lo = self.t['fblend_hi'].data_ptr(), self.t['fblend_lo'].data_ptr()
-        s.fw_idx, s.fw_val = self.t['fw_idx'].data_ptr(), self.t['fw_val'].data_ptr()
         s.use_umma = 1 if os.environ.get('HB_EMUL_TENSOR') else 0
-        s.fused_nct, s.fused_wk = packed['fused_nct'], 0
         s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
         s.num_groups, s.max_depth = packed['num_groups'], packed['max_depth']
         s.g_slot, s.ft_tab, s.ft_nct = self.t['g_slot'].data_ptr(), self.t['ft_tab'].data_ptr(), packed['ft_nct']
-        k0 = (bt[:, :32] * 1024.0).contiguous()
-        k0h = split(k0)[0]
-        self.t['blend_k0_hi'], self.t['blend_k0_lo'] = k0h, (k0 - k0h).contiguous()
-        self.t['blend16'] = (bt[:, 32:] * 1024.0).to(torch.float16).contiguous()
-        s.blend_k0_hi, s.blend_k0_lo, s.blend16 = (self.t[k].data_ptr() for k in ('blend_k0_hi', 'blend_k0_lo', 'blend16'))
         bs = torch.zeros(packed['v3_ld'], 256)
         bs[:, :224] = bt * 1024.0
         bh = bs.to(torch.float16)
         self.t['blend16a_h'], self.t['blend16a_l'] = bh.contiguous(), (bs - bh.float()).to(torch.float16).contiguous()
         s.blend16a_h, s.blend16a_l = self.t['blend16a_h'].data_ptr(), self.t['blend16a_l'].data_ptr()
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))
-        self.fused_wk = packed['fused_wk']
         self.ws_slot = 0
         self.struct = s
         self._ws, self._vlists = {}, {}

@@ -3,8 +3,8 @@
 // carving, dispatch); every cudaLaunchKernel it issues is resolved here to the SAME kernel source compiled with g++ against
 // the SIMT shim (tests/host/shim) and run with the launch's grid/block on host memory.  "Device pointers" are host pointers.
 // Covers every SIMT kernel (lbs.cu, rot.cu, losses.cu, chamfer.cu, rollout.cu) and, on the functional tcgen05 / TMA / TMEM
-// emulation of tests/host/shim/tc_emul.h, the single-CTA tcgen05 kernels (umma_gemm3_kernel<.,.,1>, lbs_fused_kernel,
-// lbs_blend_kernel, lbs_fuseg_kernel) and the 4-CTA-cluster split-K instantiations of umma_gemm3_kernel (the CTAs of a cluster
+// emulation of tests/host/shim/tc_emul.h, the single-CTA tcgen05 kernels (umma_gemm3_kernel<.,.,1>,
+// lbs_fuseg_kernel) and the 4-CTA-cluster split-K instantiations of umma_gemm3_kernel (the CTAs of a cluster
 // run concurrently, DSMEM stores and cluster barriers are emulated); cuTensorMapEncodeTiled is emulated too, so the library's
 // own descriptor code runs.
 // Not a product path: nothing in humor_b200/ references it; the product rejects CPU tensors unless a test patches that out.
@@ -41,7 +41,6 @@ const std::map<std::string, Thunk>& registry() {
       {"hb::lbs_pose_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_bwd_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(cf, 8), A(cf, 9), A(int, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
       {"hb::lbs_skin_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_fwd_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(cf, 3), A(cf, 4), A(ci, 5), A(int, 6), A(float*, 7), A(size_t, 8))); }},
       {"hb::lbs_skin_apply_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_apply_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(float*, 6))); }},
-      {"hb::lbs_skin_group_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_group_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(float*, 6), A(int, 7))); }},
       {"hb::lbs_gather_extra_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_gather_extra_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(float*, 3))); }},
       {"hb::lbs_skin_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_bwd_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(cf, 3), A(ci, 4), A(int, 5), A(cf, 6), A(size_t, 7), A(float*, 8), A(float*, 9), A(float*, 10), A(int, 11), A(ci, 12), A(int, 13), A(cf, 14), A(size_t, 15))); }},
       {"hb::rodrigues_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rodrigues_fwd_kernel(A(int, 0), A(cf, 1), A(float*, 2))); }},
@@ -81,11 +80,8 @@ const std::map<std::string, Thunk>& registry() {
          RUN((hb_emu::umma_gemm16_kernel<BN, EPI, KS>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(int, 8), A(unsigned short*, 9), A(unsigned short*, 10), A(int, 11), A(hb_emu::GemmEpi, 12)))); }},
       UMMA16_THUNK(64, 0, 1) UMMA16_THUNK(64, 0, 4) UMMA16_THUNK(128, 0, 1) UMMA16_THUNK(64, 1, 1) UMMA16_THUNK(64, 1, 4) UMMA16_THUNK(128, 1, 1)
       {"hb::split16_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::split16_kernel(A(cf, 0), A(unsigned short*, 1), A(unsigned short*, 2), A(size_t, 3))); }},
-      {"hb::lbs_blend_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_blend_kernel(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(cf, 7), A(float*, 8), A(int, 9), A(int, 10))); }},
       {"hb::lbs_fuseg_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fuseg_kernel(MAP(0), MAP(1), MAP(2), MAP(3), MAP(4), MAP(5), MAP(6), MAP(7), MAP(8), A(int, 9), A(hb_emu::LbsFusegArgs, 10))); }},
       {"hb::feat_f16_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::feat_f16_kernel(A(cf, 0), A(int, 1), A(int, 2), A(int, 3), A(int, 4), A(int, 5), A(unsigned short*, 6), A(unsigned short*, 7))); }},
-      {"hb::lbs_fused_kernel<4>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<4>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
-      {"hb::lbs_fused_kernel<8>", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fused_kernel<8>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(hb_emu::LbsFusedArgs, 5))); }},
       // persistent decoder chain: the WHOLE grid runs at once (clusters wait on each other through global-memory flags); the
       // launcher's parameter block holds 128-byte driver tensor maps, the emulated kernel's block the emulated ones
       {"hb::chain_kernel", [](dim3 g, dim3 b, void** a) {

@@ -18,13 +18,12 @@ t = {k: torch.as_tensor(v).contiguous() for k, v in packed.items() if isinstance
 s = _ext.HbLbsModel()
 s.num_verts, s.v3_ld, s.wk = packed['num_verts'], packed['v3_ld'], packed['wk']
 for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_val', 'parents', 'extra_ids', 'depth',
-          'child_start', 'child_list', 'g_start', 'g_joint', 'g_w', 'fw_idx', 'fw_val', 'g_slot', 'ft_tab'):
+          'child_start', 'child_list', 'g_start', 'g_joint', 'g_w', 'g_slot', 'ft_tab'):
     setattr(s, k, t[k].data_ptr())
 s.ft_nct = packed['ft_nct']
 planes = torch.zeros(packed['v3_ld'], 224)
-s.blend_t_hi = s.blend_t_lo = s.fblend_hi = s.fblend_lo = planes.data_ptr()
-s.blend_k0_hi = s.blend_k0_lo = s.blend16 = s.blend16a_h = s.blend16a_l = planes.data_ptr()
-s.use_umma, s.max_depth, s.num_groups, s.fused_nct, s.fused_wk = 1, packed['max_depth'], packed['num_groups'], packed['fused_nct'], 0
+s.blend_t_hi = s.blend_t_lo = s.blend16a_h = s.blend16a_l = planes.data_ptr()
+s.use_umma, s.max_depth, s.num_groups = 1, packed['max_depth'], packed['num_groups']
 L = _ext.lib()
 ws = torch.empty(L.humor_lbs_workspace_bytes(N) // 4)
 x = torch.zeros(N * 64)

@@ -1,44 +1,15 @@
 // Test infrastructure: the tcgen05 kernels of the dense LBS forward executed on the CPU: SIMT shim (threads, barriers) +
 // functional emulation of mbarriers / TMA / UMMA / TMEM (tests/host/shim/tc_emul.h).
 //   g++ -O2 -std=c++20 -pthread -shared -fPIC -Itests/host/shim -DHB_HOST_SHIM tc_host.cpp
-#include "../../humor_b200/csrc/lbs_blend.cuh"
-#include "../../humor_b200/csrc/lbs_fused.cuh"
 #include "../../humor_b200/csrc/lbs_fuseg.cuh"
 #include "../../humor_b200/csrc/umma_gemm16.cuh"
 using namespace hb;
 extern "C" {
-// v_posed = bias + (feat_hi+feat_lo) . (bt_hi+bt_lo)^T through lbs_blend_kernel with `grid` persistent CTAs
-long long h_lbs_blend(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb, int b_rows,
-                      int M, int ncols, int K, const float* bias, float* C, int ldc, int grid, int fast) {
-  CUtensorMap a_hi{feat_hi, (unsigned long long)M, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM};
-  CUtensorMap a_lo{feat_lo, (unsigned long long)M, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM};
-  CUtensorMap b_hi{bt_hi, (unsigned long long)b_rows, (unsigned long long)K, (unsigned long long)ldb, 32, LB_BN};
-  CUtensorMap b_lo{bt_lo, (unsigned long long)b_rows, (unsigned long long)K, (unsigned long long)ldb, 32, LB_BN};
-  tcemu::reset();
-  shim::launch(dim3(grid), dim3(192), [&] { lbs_blend_kernel(a_hi, a_lo, b_hi, b_lo, M, ncols, K, bias, C, ldc, fast); });
-  return tcemu::g_mma_count;
-}
-// the fused blend + skinning kernel (verified on the B200): cross-check of the emulation model
-long long h_lbs_fused(const float* feat_hi, const float* feat_lo, int ldf, const float* bf_hi, const float* bf_lo, int K, int N,
-                      int num_verts, int nct, int wk, const int* fw_idx, const float* fw_val, const float* A, const float* trans,
-                      float* out, int grid) {
-  CUtensorMap a_hi{feat_hi, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM};
-  CUtensorMap a_lo{feat_lo, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM};
-  CUtensorMap b_hi{bf_hi, (unsigned long long)nct * 128, (unsigned long long)K, (unsigned long long)K, 32, 128};
-  CUtensorMap b_lo{bf_lo, (unsigned long long)nct * 128, (unsigned long long)K, (unsigned long long)K, 32, 128};
-  LbsFusedArgs a;
-  a.N = N; a.num_verts = num_verts; a.nrt = cdiv(N, UM_BM); a.nct = nct;
-  a.fw_idx = fw_idx; a.fw_val = fw_val; a.A = A; a.trans = trans; a.out = out;
-  tcemu::reset();
-  if (wk == 4) shim::launch(dim3(grid), dim3(192), [&] { lbs_fused_kernel<4>(a_hi, a_lo, b_hi, b_lo, K, a); });
-  else shim::launch(dim3(grid), dim3(192), [&] { lbs_fused_kernel<8>(a_hi, a_lo, b_hi, b_lo, K, a); });
-  return tcemu::g_mma_count;
-}
 // skin form 3 (lbs_fuseg.cuh): blend + lane = frame group skinning, `grid` persistent CTAs; transforms via un-swizzled TMA boxes
 long long h_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb, int b_rows,
                       int K, int N, int num_verts, int num_groups, const int* g_start, const int* g_joint, const int* g_slot,
                       const float* g_w, const int* ft_tab, const float* v_template, const float* A, const float* trans, float* out,
-                      int grid, int fast, long long* tma_count, const void* feat16, const void* bt16, int ld16, int nkb16, float out_scale,
+                      int grid, long long* tma_count, const void* feat16, const void* bt16, int ld16, int nkb16, float out_scale,
                       const void* feat16l, const void* bt16l) {
   CUtensorMap a_hi{feat_hi, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM, 0};
   CUtensorMap a_lo{feat_lo, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM, 0};
@@ -50,9 +21,8 @@ long long h_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const
   CUtensorMap a16l{static_cast<const float*>(feat16l), (unsigned long long)N, 64ull * nkb16, (unsigned long long)ld16, 64, UM_BM, 0, 1};
   CUtensorMap b16l{static_cast<const float*>(bt16l), (unsigned long long)b_rows, 64ull * nkb16, (unsigned long long)ld16, 64, FG_BN, 0, 1};
   LbsFusegArgs a;
-  a.f16x3 = feat16l ? 1 : 0;
   a.nkb16 = nkb16; a.out_scale = out_scale; a.direct_store = getenv("HB_LBS_FUSEG_DIRECT") ? 1 : 0;
-  a.N = N; a.num_verts = num_verts; a.num_groups = num_groups; a.nrt = cdiv(N, UM_BM); a.nct = cdiv(num_groups, FG_GPT); a.fast = fast;
+  a.N = N; a.num_verts = num_verts; a.num_groups = num_groups; a.nrt = cdiv(N, UM_BM); a.nct = cdiv(num_groups, FG_GPT);
   a.g_start = g_start; a.g_joint = g_joint; a.g_slot = g_slot; a.g_w = g_w; a.ft_tab = ft_tab;
   a.v_template = v_template; a.A = A; a.trans = trans; a.out = out;
   tcemu::reset();

@@ -35,7 +35,7 @@ def test_struct_sizes_match_header():
     import ctypes as C
     # pointers-only structs: one slot per array entry
     assert C.sizeof(_ext.HbHumorWeights) == 8 * (4 + 4 + 3 + 3 + 4 + 5 + 5 + 4 + 4 + 5 + 20 + 16) + 8 + 8 * 8 + 8 * 10 + 8 * 2
-    assert C.sizeof(_ext.HbLbsModel) == 16 + 8 * 9 + 8 * 2 + 8 + 8 * 3 + 8 * 4 + 8 + 8 * 3 + 8 + 8 * 2 + 8 * 3 + 8 * 2
+    assert C.sizeof(_ext.HbLbsModel) == 16 + 8 * 9 + 8 * 2 + 8 + 8 * 3 + 8 * 3 + 8 + 8 * 2 + 8 * 2
 
 
 def test_lbs_model_layout_matches_the_compiled_header(tmp_path):
@@ -108,6 +108,7 @@ def test_argument_errors_are_reported_before_any_launch(built_lib):
     assert L.humor_umma_gemm16(None, 64, p, 64, p, p, 64, 4, 4, 64, p, 1 << 30, None) == ARG
     assert L.humor_umma_gemm16(p, 64, p, 64, p, p, 64, 4, 4, 64, p, 16, None) == WS
     assert L.humor_lbs_configure(4, 0, 0) == ARG and L.humor_lbs_configure(0, 6, 0) == ARG and L.humor_lbs_configure(0, 0, 64) == ARG
+    assert L.humor_lbs_configure(2, 0, 0) == ARG and L.humor_lbs_configure(0, 3, 0) == ARG          # forms removed in round 2
     assert L.humor_lbs_configure(0, 0, 0) == 0
     assert nl.value == 0
 

@@ -50,24 +50,6 @@ def test_lbs_forward_matches_oracle(bm, oracle_bm, n):
     assert torch.equal(g.f.cpu(), o.f)
 
 
-def test_lbs_fused_dense_forward_matches_two_kernel_path(bm):
-    """The opt-in persistent kernel (blend GEMM + skinning fused, csrc/lbs_fused.cuh) against GEMM + skin pass."""
-    n = 300                                                        # 2 full row tiles + a ragged one
-    ro, pb, be, tr = (torch.tensor(a).cuda() for a in rand_pose(n, 11))
-    m = bm.lbs_model
-    if not m.fused_wk:
-        pytest.skip('asset has more than 8 skinning weights per vertex')
-    ref = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
-    m.struct.fused_wk = m.fused_wk
-    try:
-        got = bm(root_orient=ro, pose_body=pb, betas=be, trans=tr)
-        torch.cuda.synchronize()
-    finally:
-        m.struct.fused_wk = 0
-    assert float((got.v - ref.v).abs().max()) < 5e-6
-    assert float((got.Jtr - ref.Jtr).abs().max()) < 5e-6
-
-
 def test_lbs_known_answers(bm, asset):
     """zero pose + zero betas -> template + trans exactly; hands are identity -> no dependence on posedirs 189.."""
     n = 2

@@ -1,10 +1,9 @@
 """The tcgen05 kernels of the dense LBS forward executed on the CPU: SIMT shim + functional emulation of mbarriers, TMA
 (SWIZZLE_128B), tcgen05.mma kind::tf32 and TMEM (tests/host/shim/tc_emul.h), same kernel source as the GPU build.
 
-* lbs_fused_kernel is verified on the B200 (tests/test_gpu_kernels.py): running it here cross-checks the emulation MODEL
-  (descriptor / swizzle interpretation, barrier semantics) against a kernel known to be right on hardware.
-* lbs_blend_kernel (persistent 128x256 tiles) has not run on hardware yet: this is its functional check — tile order,
-  descriptor offsets, single-buffer-per-tile TMEM protocol, partial row/column tiles, operand planes past the matrix."""
+* lbs_fuseg_kernel (blend GEMM + group skinning, the default dense forward) in its two operand forms: 3xTF32 planes and fp16
+  hi/lo planes; tile order, slot schedule, descriptor offsets, partial row/column tiles, operand planes past the matrix.
+* umma_gemm16_kernel with its GroupNorm epilogue and fp16 output planes."""
 import ctypes
 import os
 import subprocess
@@ -26,127 +25,17 @@ def H():
     subprocess.check_call(['g++', '-O2', '-std=c++20', '-pthread', '-shared', '-fPIC', '-I' + os.path.join(HERE, 'host', 'shim'),
                            '-DHB_HOST_SHIM', src, '-o', so])
     L = ctypes.CDLL(so)
-    L.h_lbs_blend.restype = ctypes.c_longlong
-    L.h_lbs_fused.restype = ctypes.c_longlong
     return L
 
 
-def split(x):
-    hi = (x.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
-    return np.ascontiguousarray(hi), np.ascontiguousarray(x - hi)
-
-
-@pytest.mark.parametrize('M,ncols,b_rows,grid', [(300, 700, 704, 3), (128, 256, 256, 1), (129, 257, 260, 7), (40, 1030, 1056, 2)])
-def test_blend_kernel_matches_fp64(H, M, ncols, b_rows, grid):
-    K = 224
-    rng = np.random.RandomState(M + ncols)
-    feat = np.zeros((M, K), np.float32)
-    feat[:, :205] = rng.randn(M, 205).astype(np.float32)
-    bt = np.zeros((b_rows, K), np.float32)
-    bt[:ncols, :205] = (rng.randn(ncols, 205) * 0.01).astype(np.float32)
-    bias = rng.randn(ncols).astype(np.float32)
-    fh, fl = split(feat)
-    bh, bl = split(bt)
-    ldc = ((ncols + 63) // 64) * 64
-    C = np.full((M, ldc), np.nan, np.float32)
-    nmma = H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, b_rows, M, ncols, K, P(bias), P(C), ldc, grid, 0)
-    ntiles = ((M + 127) // 128) * ((ncols + 255) // 256)
-    assert nmma == ntiles * 7 * 4 * 3                          # 7 k-blocks x 4 UMMAs of K = 8 x (hi.hi + lo.hi + hi.lo)
-    ref = feat.astype(np.float64) @ bt[:ncols].astype(np.float64).T + bias
-    assert np.isfinite(C[:, :ncols]).all()
-    assert np.abs(C[:, :ncols] - ref).max() < 3e-6 * max(1.0, np.abs(ref).max())
-    assert np.isnan(C[:, ncols:]).all()                        # padding columns are never written
-
-
-def test_blend_kernel_on_the_model_layout(H):
-    """v3_ld = 20 672 rows of operand planes, 3V = 20 670 columns: the last 256-column tile reads 64 rows past the planes
-    (TMA zero fill) and stores only 190 columns; 2 persistent CTAs walk the last tiles of 2 row tiles."""
-    p = pack_smplh(synth.make_smplh_asset(), 16)
-    K, v3_ld, V3 = 224, p['v3_ld'], 3 * 6890
-    assert v3_ld == 20672
-    c0 = 20480 - 256                                           # keep the run short: the last two column tiles only
-    bt = np.zeros((v3_ld - c0, K), np.float32)
-    bt[:, :208] = p['blend_t'][c0:]
-    M = 130
-    rng = np.random.RandomState(0)
-    feat = np.zeros((M, K), np.float32)
-    feat[:, :205] = rng.randn(M, 205).astype(np.float32) * 0.5
-    fh, fl = split(feat)
-    bh, bl = split(bt)
-    ncols = V3 - c0
-    bias = p['v_template'][c0:V3].copy()
-    ldc = v3_ld - c0
-    C = np.full((M, ldc), np.nan, np.float32)
-    H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], M, ncols, K, P(bias), P(C), ldc, 2, 0)
-    ref = feat.astype(np.float64) @ bt[:ncols].astype(np.float64).T + bias
-    assert np.abs(C[:, :ncols] - ref).max() < 3e-6 and np.isnan(C[:, ncols:]).all()
-
-
 def split_rn(x):
+    """x = hi + lo with hi = x rounded to nearest-even on tf32's 10 mantissa bits (what the product's plane kernels write)."""
     u = x.view(np.uint32).astype(np.uint64)
     hi = ((u + 0x0fff + ((u >> 13) & 1)) & 0xffffe000).astype(np.uint32).view(np.float32)
     return np.ascontiguousarray(hi), np.ascontiguousarray(x - hi)
 
 
-def test_blend_kernel_mixed_precision_form(H):
-    """blend form 3: three passes on k-block 0 (betas + 16 pose columns), ONE pass on the tf32-ROUNDED hi planes for the rest.
-    36 MMAs per tile instead of 84; error of the single-pass columns ~2^-12 per product (sub-1e-4 m at SMPL magnitudes)."""
-    K, M, ncols, b_rows = 224, 200, 520, 528
-    rng = np.random.RandomState(5)
-    feat = np.zeros((M, K), np.float32)
-    feat[:, :16] = rng.randn(M, 16).astype(np.float32) * 0.7           # betas
-    feat[:, 16:205] = (rng.randn(M, 189) * 0.3).astype(np.float32)     # R - I at moderate poses
-    bt = np.zeros((b_rows, K), np.float32)
-    bt[:ncols, :16] = (rng.randn(ncols, 16) * 0.02).astype(np.float32)
-    bt[:ncols, 16:205] = (rng.randn(ncols, 189) * 0.004).astype(np.float32)
-    bias = rng.randn(ncols).astype(np.float32)
-    fh, fl = split_rn(feat)
-    bh, bl = split_rn(bt)
-    assert np.array_equal(fh + fl, feat) and np.array_equal(bh + bl, bt)       # the rounded split is still exact
-    ldc = 576
-    C = np.full((M, ldc), np.nan, np.float32)
-    nmma = H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, b_rows, M, ncols, K, P(bias), P(C), ldc, 3, 1)
-    ntiles = 2 * 3
-    assert nmma == ntiles * (4 * 3 + 6 * 4 * 1)
-    ref = feat.astype(np.float64) @ bt[:ncols].astype(np.float64).T + bias
-    err = np.abs(C[:, :ncols] - ref).max()
-    assert 1e-7 < err < 3e-5, err                       # measurably single-pass, far inside the 1e-4 m bound
-    C3 = np.full((M, ldc), np.nan, np.float32)
-    H.h_lbs_blend(P(fh), P(fl), K, P(bh), P(bl), K, b_rows, M, ncols, K, P(bias), P(C3), ldc, 3, 0)
-    assert np.abs(C3[:, :ncols] - ref).max() < 3e-6     # the same rounded planes through three passes: fp32-level
-
-
-def test_fused_kernel_cross_checks_the_emulation(H):
-    """lbs_fused_kernel (hardware-verified) through the same emulation against the dense skinning formula."""
-    asset = synth.make_smplh_asset()
-    p = pack_smplh(asset, 16)
-    V = 6890
-    nct_all, wk = p['fused_nct'], p['fused_wk']
-    nct = 2                                                    # the first 84 vertices are enough to exercise every stage
-    nv = 84
-    K, N = 224, 200                                            # 2 row tiles, the second ragged
-    rng = np.random.RandomState(1)
-    feat = np.zeros((N, K), np.float32)
-    feat[:, :205] = rng.randn(N, 205).astype(np.float32) * 0.5
-    feat[:, 205] = 1.0                                         # picks up the template column of the fused blend matrix
-    fb = np.ascontiguousarray(p['fblend'][:nct * 128])
-    fh, fl = split(feat)
-    bh, bl = split(fb)
-    A = rng.randn(N, 52, 3, 4).astype(np.float32)
-    trans = rng.randn(N, 3).astype(np.float32)
-    out = np.full((N, nv, 3), np.nan, np.float32)
-    fw_idx, fw_val = np.ascontiguousarray(p['fw_idx'][:nv]), np.ascontiguousarray(p['fw_val'][:nv])
-    H.h_lbs_fused(P(fh), P(fl), K, P(bh), P(bl), K, N, nv, nct, wk, P(fw_idx), P(fw_val), P(A), P(trans), P(out), 3)
-    blend = p['blend'][:, :3 * nv].astype(np.float64)          # (208, 3nv)
-    vp = feat[:, :208].astype(np.float64) @ blend + p['v_template'][:3 * nv].astype(np.float64)
-    vp = vp.reshape(N, nv, 3)
-    T = np.einsum('vj,njrc->nvrc', asset['weights'][:nv].astype(np.float64), A.astype(np.float64))
-    ref = np.einsum('nvrc,nvc->nvr', T[..., :3], vp) + T[..., 3] + trans[:, None]
-    assert np.isfinite(out).all()
-    assert np.abs(out - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
-
-
-# ---- skin form 3: fused blend + lane = frame group skinning (csrc/lbs_fuseg.cuh), not yet on hardware
+# ---- skin form 3: fused blend + lane = frame group skinning (csrc/lbs_fuseg.cuh)
 def _fuseg_problem(N, seed):
     asset = synth.make_smplh_asset()
     p = pack_smplh(asset, 16)
@@ -167,7 +56,7 @@ def _fuseg_problem(N, seed):
     return p, feat, bt, A, trans, ref
 
 
-def _run_fuseg(H, p, feat, bt, A, trans, grid, fast, f16=False):
+def _run_fuseg(H, p, feat, bt, A, trans, grid, f16=False):
     N, K, V = feat.shape[0], 224, 6890
     fh, fl = split_rn(feat)
     out = np.full((N, V, 3), np.nan, np.float32)
@@ -175,7 +64,7 @@ def _run_fuseg(H, p, feat, bt, A, trans, grid, fast, f16=False):
     H.h_lbs_fuseg.restype = ctypes.c_longlong
     tabs = (N, V, p['num_groups'], P(p['g_start']), P(p['g_joint']), P(p['g_slot']), P(p['g_w']), P(p['ft_tab']), P(p['v_template']),
             P(A), P(trans), P(out), grid)
-    if f16 == 'x3':   # blend form 5: every column as fp16 hi + unscaled lo planes (K padded to 256), three products, no tf32 k-blocks
+    if f16:   # blend form 5: every column as fp16 hi + unscaled lo planes (K padded to 256), three products, no tf32 k-blocks
         fp = np.zeros((N, 256), np.float32)
         fp[:, :K] = feat
         bp = np.zeros((bt.shape[0], 256), np.float32)
@@ -183,17 +72,11 @@ def _run_fuseg(H, p, feat, bt, A, trans, grid, fast, f16=False):
         f_h, b_h = fp.astype(np.float16), bp.astype(np.float16)
         f_l, b_l = (fp - f_h.astype(np.float32)).astype(np.float16), (bp - b_h.astype(np.float32)).astype(np.float16)
         keep = [np.ascontiguousarray(x) for x in (f_h, b_h, f_l, b_l)]
-        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(fh), P(fl), K, bt.shape[0], 0, *tabs, 1, ctypes.byref(ntma), P(keep[0]), P(keep[1]), 256, 4,
+        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(fh), P(fl), K, bt.shape[0], 0, *tabs, ctypes.byref(ntma), P(keep[0]), P(keep[1]), 256, 4,
                              ctypes.c_float(2.0 ** -10), P(keep[2]), P(keep[3]))
-    elif f16:   # blend form 4: columns 0..31 three tf32 passes on planes scaled by 2^10, columns 32..223 one fp16 pass
-        bh, bl = split_rn(np.ascontiguousarray(bt[:, :32] * np.float32(1024)))
-        f16p = np.ascontiguousarray(feat[:, 32:].astype(np.float16))
-        b16p = np.ascontiguousarray((bt[:, 32:] * np.float32(1024)).astype(np.float16))
-        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), 32, bt.shape[0], 32, *tabs, 1, ctypes.byref(ntma), P(f16p), P(b16p), 192, 3,
-                             ctypes.c_float(2.0 ** -10), None, None)
     else:
         bh, bl = split_rn(bt)
-        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, *tabs, fast, ctypes.byref(ntma), None, None, 0, 0,
+        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, *tabs, ctypes.byref(ntma), None, None, 0, 0,
                              ctypes.c_float(1.0), None, None)
     return out, nmma, ntma.value
 
@@ -222,42 +105,23 @@ def test_fuseg_slot_schedule_is_consistent():
     assert (gsl < 0).mean() < 0.05                               # SMPL-like locality: few joints are left to global loads
 
 
-@pytest.mark.parametrize('N,grid,fast', [(200, 3, 0), (40, 7, 0), (140, 2, 1)])
-def test_fuseg_kernel_matches_fp64(H, N, grid, fast):
+@pytest.mark.parametrize('N,grid', [(200, 3), (40, 7), (140, 2)])
+def test_fuseg_kernel_matches_fp64(H, N, grid):
     """The whole mesh (108 column tiles, the last one 64 operand rows past the planes) x 1-2 row tiles (ragged), CTA chunks that
-    start in the middle of a row and cross into the next one (fresh slot loads + full drain), three-pass and mixed precision."""
+    start in the middle of a row and cross into the next one (fresh slot loads + full drain); blend form 1 (3xTF32)."""
     p, feat, bt, A, trans, ref = _fuseg_problem(N, N + grid)
-    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid, fast)
+    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid)
     ntiles = ((N + 127) // 128) * 108
-    assert nmma == ntiles * (4 * 3 + 6 * 4 * (1 if fast else 3))
+    assert nmma == ntiles * 7 * 4 * 3
     assert np.isfinite(out).all()                                # every vertex of every frame written
     err = np.abs(out - ref).max()
     scale = max(1.0, np.abs(ref).max())
-    if fast:
-        assert 1e-7 * scale < err < 6e-5 * scale, err            # single pass on the pose columns: visible, inside the 1e-4 m bound
-    else:
-        assert err < 4e-6 * scale, err
+    assert err < 4e-6 * scale, err
     # operand entries (2 TMA boxes each) + transform slots: at most the fresh list per tile, at least the incremental one
-    ent = ntiles * (8 if fast else 14) * 2
+    ent = ntiles * 14 * 2
     tab = p['ft_tab']
     nrt = (N + 127) // 128
     assert ent + nrt * int(tab[:, 1].sum()) <= ntma <= ent + nrt * int(tab[:, 1].sum()) + (grid + nrt) * 12
-
-
-def test_fuseg_kernel_fp16_pose_columns(H):
-    """blend form 4: the pose columns past k-block 0 as ONE fp16 plane per operand (kind::f16, K = 16 per MMA): 12 + 12 MMAs and
-    5 ring entries per tile; fp16 carries tf32's 11-bit significand, so the error matches the single-pass tf32 form."""
-    N, grid = 140, 2
-    p, feat, bt, A, trans, ref = _fuseg_problem(N, N + grid)
-    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid, 1, f16=True)
-    ntiles = 2 * 108
-    assert nmma == ntiles * (4 * 3 + 3 * 4)
-    assert np.isfinite(out).all()
-    err = np.abs(out - ref).max()
-    scale = max(1.0, np.abs(ref).max())
-    assert 1e-7 * scale < err < 6e-5 * scale, err
-    fast, _, _ = _run_fuseg(H, p, feat, bt, A, trans, grid, 1)
-    assert np.abs(fast - ref).max() < 6e-5 * scale and np.abs(out - fast).max() < 8e-5 * scale
 
 
 def test_fuseg_kernel_on_a_mesh_without_locality(H):
@@ -281,7 +145,7 @@ def test_fuseg_kernel_on_a_mesh_without_locality(H):
     bt[:, :208] = p['blend_t']
     A = rng.randn(N, 52, 3, 4).astype(np.float32)
     trans = rng.randn(N, 3).astype(np.float32)
-    out, nmma, _ = _run_fuseg(H, p, feat, bt, A, trans, 2, 0)
+    out, nmma, _ = _run_fuseg(H, p, feat, bt, A, trans, 2)
     vp = feat[:, :208].astype(np.float64) @ p['blend'][:, :3 * V].astype(np.float64) + p['v_template'].astype(np.float64)
     T = np.einsum('vj,njrc->nvrc', asset['weights'].astype(np.float64), A.astype(np.float64))
     ref = np.einsum('nvrc,nvc->nvr', T[..., :3], vp.reshape(N, V, 3)) + T[..., 3] + trans[:, None].astype(np.float64)
@@ -289,7 +153,7 @@ def test_fuseg_kernel_on_a_mesh_without_locality(H):
     assert np.abs(out - ref).max() < 4e-6 * max(1.0, np.abs(ref).max())
 
 
-# ---- fp16 hi/lo GEMM with its forward epilogues (csrc/umma_gemm16.cuh), not yet on hardware
+# ---- fp16 hi/lo GEMM with its forward epilogues (csrc/umma_gemm16.cuh)
 def split16_np(x):
     h = x.astype(np.float16)
     l = ((x - h.astype(np.float32)) * np.float32(2048)).astype(np.float16)
@@ -341,7 +205,7 @@ def test_fuseg_kernel_fp16_three_products(H):
     accumulator - the accuracy class of three TF32 passes (1e-6) from 4-byte operand elements: 8 ring entries and 48 MMAs per tile."""
     N, grid = 140, 2
     p, feat, bt, A, trans, ref = _fuseg_problem(N, N + grid)
-    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid, 1, f16='x3')
+    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid, f16=True)
     ntiles = 2 * 108
     assert nmma == ntiles * 4 * 4 * 3
     assert np.isfinite(out).all()

@@ -20,6 +20,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static const bool g_splitk = (getenv("HB_NO_SPLITK") == nullptr);
 static const bool g_pdl = (getenv("HB_NO_PDL") == nullptr);
+static const bool g_persist = (getenv("HB_GEMM_ONE_TILE") == nullptr);   // A/B: one 128x128 tile per CTA (round 1) instead of persistent CTAs
 static int g_encode_state = 0;      // 0 unknown, 1 ok, -1 unavailable
 
 static bool load_encode() {
@@ -95,6 +96,36 @@ static cudaError_t launch_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
   return cudaLaunchKernelEx(&cfg, umma_gemm3_kernel<BN, EPI, KS>, a_hi, a_lo, b_hi, b_lo, M, N, K, C, C_hi, C_lo, ldc, ep);
 }
 
+// persistent 128x128 tiles with two epilogue groups (umma_gemm3p_kernel): the batched products
+template <int EPI>
+static cudaError_t launch_p(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                            int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, const GemmEpi& ep, cudaStream_t st) {
+  static int sms = 0, want = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_gemm3p_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<128>::TOTAL);
+    if (e != cudaSuccess) { sms = 0; return e; }
+    const char* w = getenv("HB_GEMM_CTAS");                    // tests: fewer CTAs than tiles on small problems
+    want = w ? atoi(w) : 0;
+  }
+  const int ntiles = cdiv(N, 128) * cdiv(M, UM_BM);
+  int grid = ntiles < sms ? ntiles : sms;
+  if (want > 0 && want < grid) grid = want;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(UMP_THREADS);
+  cfg.dynamicSmemBytes = UmmaSmem<128>::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, umma_gemm3p_kernel<EPI>, a_hi, a_lo, b_hi, b_lo, M, N, K, C, C_hi, C_lo, ldc, ep);
+}
+
 cudaError_t launch_umma_gemm3(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb,
                               int M, int N, int K, float* C, float* C_hi, float* C_lo, int ldc, int epi, const GemmEpi& ep,
                               cudaStream_t st) {
@@ -118,8 +149,9 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
 #define HB_UMMA_CASE(E)                                                                                              \
   case E:                                                                                                            \
     if (splitk) return launch_t<64, E, 4>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);          \
-    return bn == 64 ? launch_t<64, E, 1>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st)            \
-                    : launch_t<128, E, 1>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
+    if (bn == 64) return launch_t<64, E, 1>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);         \
+    return g_persist ? launch_p<E>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st)                  \
+                     : launch_t<128, E, 1>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
   switch (epi) {
     HB_UMMA_CASE(EPI_BIAS)
     HB_UMMA_CASE(EPI_GN_RELU)

@@ -410,4 +410,178 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Persistent form of the 128x128-tile kernel for the BATCHED products (the prior network over all S*B rows, 118 x 8 tiles at the
+// benchmark size; the blend GEMM of dense-LBS form 1).  Measured on the B200 (profiles/r02m_prior_gemm_*): one tile per CTA spent
+// 18.6 us of its 37.6 us in prologue + epilogue with the tensor pipe idle (the K = 96 reverse GEMM is 119 us of pure epilogue:
+// issue slots 9 % busy, 1.5 warps per scheduler).  Here a CTA per SM walks tiles blockIdx.x, + gridDim.x, ...; TMEM holds FOUR
+// 128-column buffers = two ping-pong pairs, one pair per EPILOGUE GROUP of four warps: group g promotes the chunks of tiles
+// g, g+2, ... and runs their epilogue while the MMA lane is already accumulating the next tile into the other pair and group 1-g
+// promotes it.  The operand ring runs across tiles, so the next tile's loads are in flight during the last chunk as well.
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int UMP_THREADS = 64 + 2 * 128;
+
+template <int EPI>
+__global__ void __launch_bounds__(UMP_THREADS, 1)
+umma_gemm3p_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   int M, int N, int K, float* __restrict__ C, float* __restrict__ C_hi, float* __restrict__ C_lo, int ldc,
+                   GemmEpi ep) {
+  constexpr int BN = 128;
+  using SM = UmmaSmem<BN>;
+  constexpr int UM_STAGES = SM::STAGES;
+  HB_DYN_SMEM(smem_raw);
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + UM_STAGES * SM::STAGE;          // full[3] | empty[3] | tfull[4] | tempty[4] | tmem_ptr
+  const uint32_t full0 = bars, empty0 = bars + 8 * UM_STAGES, tfull0 = bars + 16 * UM_STAGES, tempty0 = tfull0 + 32,
+                 tptr = tempty0 + 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntn = (N + BN - 1) / BN, ntm = (M + UM_BM - 1) / UM_BM;
+  const int ntiles = ntn * ntm;
+  const int nkb = K / UM_BK;
+  const int nchunk = (nkb + UM_CHUNK - 1) / UM_CHUNK;
+  const int nuse0 = (nchunk + 1) >> 1, nuse1 = nchunk >> 1;   // uses of a pair's even / odd buffer per tile
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int b = 0; b < 4; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tptr, 512u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ld_shared_u32(tptr);
+  pdl_wait();                                                   // predecessor grid complete, its writes visible
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;                                               // k-blocks issued by this CTA (ring position)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / ntn) * UM_BM, n0 = (tile % ntn) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % UM_STAGES;
+          const uint32_t st = base + s * SM::STAGE;
+          mbar_wait(empty0 + 8 * s, ((it / UM_STAGES) & 1) ^ 1);
+          mbar_expect_tx(full0 + 8 * s, SM::STAGE);
+          tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * UM_BK, m0);
+          tma_load_2d(st + SM::A_TILE, &tmA_lo, full0 + 8 * s, kb * UM_BK, m0);
+          tma_load_2d(st + 2 * SM::A_TILE, &tmB_hi, full0 + 8 * s, kb * UM_BK, n0);
+          tma_load_2d(st + 2 * SM::A_TILE + SM::B_TILE, &tmB_lo, full0 + 8 * s, kb * UM_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+      int it = 0, i = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int g = i & 1, j = i >> 1;                        // epilogue group of this tile, its tile count
+        for (int c = 0; c < nchunk; ++c) {
+          const int b = 2 * g + (c & 1);
+          const int u = j * ((c & 1) ? nuse1 : nuse0) + (c >> 1);   // uses of buffer b before this one
+          mbar_wait(tempty0 + 8 * b, (u & 1) ^ 1);              // group g has promoted that chunk
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + b * BN;
+          const int kb_end = min(nkb, (c + 1) * UM_CHUNK);
+          for (int kb = c * UM_CHUNK; kb < kb_end; ++kb, ++it) {
+            const int s = it % UM_STAGES;
+            mbar_wait(full0 + 8 * s, (it / UM_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t st = base + s * SM::STAGE;
+#pragma unroll
+            for (int k = 0; k < UM_BK / 8; ++k) {
+              const uint64_t a_hi = umma_desc_sw128(st + k * 32);
+              const uint64_t a_lo = umma_desc_sw128(st + SM::A_TILE + k * 32);
+              const uint64_t b_hi = umma_desc_sw128(st + 2 * SM::A_TILE + k * 32);
+              const uint64_t b_lo = umma_desc_sw128(st + 2 * SM::A_TILE + SM::B_TILE + k * 32);
+              umma_tf32(tacc, a_hi, b_hi, idesc, (kb != c * UM_CHUNK) || (k != 0));
+              umma_tf32(tacc, a_lo, b_hi, idesc, 1);
+              umma_tf32(tacc, a_hi, b_lo, idesc, 1);
+            }
+            umma_commit(empty0 + 8 * s);
+          }
+          umma_commit(tfull0 + 8 * b);
+        }
+      }
+    }
+  } else {
+    const int g = (warp - 2) >> 2;                              // epilogue group
+    const int q = warp & 3;                                     // TMEM lane quadrant this warp may access
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    int i = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < ntiles; tile += 2 * gridDim.x, i += 2) {
+      const int j = i >> 1;
+      const int m0 = (tile / ntn) * UM_BM, n0 = (tile % ntn) * BN;
+      const int row = m0 + q * 32 + lane;
+      const bool rok = row < M;
+      float acc[BN];
+#pragma unroll
+      for (int jj = 0; jj < BN; ++jj) acc[jj] = 0.f;
+      for (int c = 0; c < nchunk; ++c) {
+        const int b = 2 * g + (c & 1);
+        const int u = j * ((c & 1) ? nuse1 : nuse0) + (c >> 1);
+        mbar_wait(tfull0 + 8 * b, u & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float t[32];
+          tmem_ld32(trow + b * BN + c0, t);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) acc[c0 + jj] += t[jj];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * b);
+      }
+      auto store4 = [&](int col, float a, float b_, float c_, float d) {
+        if (col + 3 < N) {
+          if (C) *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = make_float4(a, b_, c_, d);
+          if (C_hi) {
+            const float4 h = make_float4(tf32_hi(a), tf32_hi(b_), tf32_hi(c_), tf32_hi(d));
+            *reinterpret_cast<float4*>(C_hi + (size_t)row * ldc + col) = h;
+            *reinterpret_cast<float4*>(C_lo + (size_t)row * ldc + col) = make_float4(a - h.x, b_ - h.y, c_ - h.z, d - h.w);
+          }
+        } else {
+          const float o[4] = {a, b_, c_, d};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            if (col + jj < N) {
+              if (C) C[(size_t)row * ldc + col + jj] = o[jj];
+              if (C_hi) { const float h = tf32_hi(o[jj]); C_hi[(size_t)row * ldc + col + jj] = h; C_lo[(size_t)row * ldc + col + jj] = o[jj] - h; }
+            }
+        }
+      };
+      if (rok) {
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          const int col = n0 + c0;
+          if (col < N) {
+            if (EPI == EPI_BIAS) {
+#pragma unroll
+              for (int jj = 0; jj < 64; ++jj) acc[c0 + jj] += (ep.bias && col + jj < N) ? ep.bias[col + jj] : 0.f;
+            } else if (EPI == EPI_GN_RELU) {
+              if (ep.gsize == 64) gn_relu_fwd_group<64>(acc + c0, col, row, ep);
+              else { gn_relu_fwd_group<32>(acc + c0, col, row, ep); gn_relu_fwd_group<32>(acc + c0 + 32, col + 32, row, ep); }
+            } else if (col < ep.Cch) {
+              if (ep.gsize == 64) gn_relu_bwd_group<64>(acc + c0, col, row, ep);
+              else { gn_relu_bwd_group<32>(acc + c0, col, row, ep); gn_relu_bwd_group<32>(acc + c0 + 32, col + 32, row, ep); }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 64; jj += 4) store4(col + jj, acc[c0 + jj], acc[c0 + jj + 1], acc[c0 + jj + 2], acc[c0 + jj + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
 }  // namespace hb

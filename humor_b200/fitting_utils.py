@@ -1,8 +1,10 @@
 """Camera <-> prior-frame geometry of the fitting path (humor/fitting/fitting_utils.py:61-103,
-:149-190, :678-682).  Per-sequence (B rows, once per closure) so it is a handful of torch ops around
-the native Rodrigues kernel; the per-frame work lives in the CUDA kernels."""
+:149-190, :678-682).  Per-sequence (B rows, once per closure): compute_cam2prior on the optimised (B,3) floor is ONE kernel
+forward and one in reverse (csrc/rot.cu: as torch ops it was ~60 launches forward and ~150 autograd nodes in reverse, the largest
+group of tiny launches in the Stage-III graph); the torch form below remains for the already-parsed (B,4) plane of the cold paths."""
 import torch
 
+from . import _ext
 from .transforms import batch_rodrigues
 
 OP_NUM_JOINTS = 25
@@ -29,9 +31,47 @@ def compute_plane_intersection(point, direction, plane):
     return point + s[:, None] * direction, s
 
 
+class _Cam2Prior(torch.autograd.Function):
+    """humor_cam2prior_fwd / _bwd: (floor (B,3), trans0 (B,3), root_orient0 (B,3), root joint (B,3)) -> (R (B,3,3), t (B,3), h (B,1))."""
+
+    @staticmethod
+    def forward(ctx, floor, trans0, orient0, joint0):
+        _ext.require_cuda(floor, trans0, orient0, joint0)
+        floor, trans0, orient0, joint0 = (_ext.f32c(x) for x in (floor, trans0, orient0, joint0))
+        B = floor.shape[0]
+        R = torch.empty(B, 3, 3, device=floor.device, dtype=torch.float32)
+        t = torch.empty(B, 3, device=floor.device, dtype=torch.float32)
+        h = torch.empty(B, 1, device=floor.device, dtype=torch.float32)
+        _ext.check(_ext.lib().humor_cam2prior_fwd(B, _ext.ptr(floor), _ext.ptr(trans0), 3, _ext.ptr(orient0), 3, _ext.ptr(joint0), 3,
+                                                  _ext.ptr(R), _ext.ptr(t), _ext.ptr(h), _ext.stream_ptr()), 'humor_cam2prior_fwd')
+        _ext.LaunchCounter.total += 1
+        ctx.save_for_backward(floor, trans0, orient0, joint0)
+        return R, t, h
+
+    @staticmethod
+    def backward(ctx, gR, gt, gh):
+        floor, trans0, orient0, joint0 = ctx.saved_tensors
+        B = floor.shape[0]
+        gR, gt, gh = (None if g is None else _ext.f32c(g) for g in (gR, gt, gh))
+        out = torch.empty(4, B, 3, device=floor.device, dtype=torch.float32)
+        _ext.check(_ext.lib().humor_cam2prior_bwd(B, _ext.ptr(floor), _ext.ptr(trans0), 3, _ext.ptr(orient0), 3, _ext.ptr(joint0), 3,
+                                                  _ext.ptr(gR), _ext.ptr(gt), _ext.ptr(gh), _ext.ptr(out[0]), _ext.ptr(out[1]),
+                                                  _ext.ptr(out[2]), _ext.ptr(out[3]), _ext.stream_ptr()), 'humor_cam2prior_bwd')
+        _ext.LaunchCounter.total += 1
+        return out[0], out[1], out[2], out[3]
+
+
 def compute_cam2prior(floor_plane, trans, root_orient, joints):
     """Rotation/translation from the camera frame to the prior's canonical frame and the root height
     above the floor (fitting_utils.py:149-190): up = floor normal, right = body -x projected on the floor."""
+    if floor_plane.size(1) == 3:
+        return _Cam2Prior.apply(floor_plane, trans, root_orient, joints[:, 0])
+    return compute_cam2prior_torch(floor_plane, trans, root_orient, joints)
+
+
+def compute_cam2prior_torch(floor_plane, trans, root_orient, joints):
+    """The same in torch ops (the form round 1 ran everywhere); kept for a plane that arrives parsed, (B,4), and as the
+    autograd cross-check of the kernel pair in the tests."""
     plane = parse_floor_plane(floor_plane) if floor_plane.size(1) == 3 else floor_plane
     up = plane[:, :3]
     foot, _ = compute_plane_intersection(trans, -up, plane)

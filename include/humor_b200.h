@@ -185,6 +185,17 @@ int humor_rodrigues_bwd(int n, const float* aa, const float* dR, float* daa, hb_
 int humor_mat2aa_fwd(int n, const float* R, float* aa, hb_stream_t stream);
 int humor_mat2aa_bwd(int n, const float* R, const float* daa, float* dR, hb_stream_t stream);
 
+/* Camera -> prior frame of B sub-sequences: replaces fitting_utils.compute_cam2prior (humor/fitting/fitting_utils.py:149-190) on a
+ * (B,3) floor (normal * offset, parsed as fitting_utils.py:61-103) - what motion_optimizer.py:519-524 evaluates at the top of every
+ * Stage-III closure.  trans0 / orient0 / joint0: frame-0 root translation, root orientation (axis-angle) and root joint of every
+ * sequence, rows ld_* floats apart.  Outputs R [B][3][3] (rows right, forward, up), t [B][3] = -trans0, root_height [B].
+ * Reverse: gR / gt / gh nullable (zero); all four gradients are [B][3]. */
+int humor_cam2prior_fwd(int B, const float* floor_plane, const float* trans0, int ld_t, const float* orient0, int ld_r,
+                        const float* joint0, int ld_j, float* R, float* t, float* root_height, hb_stream_t stream);
+int humor_cam2prior_bwd(int B, const float* floor_plane, const float* trans0, int ld_t, const float* orient0, int ld_r,
+                        const float* joint0, int ld_j, const float* gR, const float* gt, const float* gh, float* d_floor,
+                        float* d_trans0, float* d_orient0, float* d_joint0, hb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused Stage-III energies (humor/fitting/fitting_loss.py:94-309 motion_fit/smpl_fit/root_fit and
  * the per-term functions :317-484, :504-518) — loss terms and their gradients in one pass.

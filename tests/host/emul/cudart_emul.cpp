@@ -47,6 +47,8 @@ const std::map<std::string, Thunk>& registry() {
       {"hb::rodrigues_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rodrigues_bwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(float*, 3))); }},
       {"hb::mat2aa_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::mat2aa_fwd_kernel(A(int, 0), A(cf, 1), A(float*, 2))); }},
       {"hb::mat2aa_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::mat2aa_bwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(float*, 3))); }},
+      {"hb::cam2prior_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::cam2prior_fwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(int, 3), A(cf, 4), A(int, 5), A(cf, 6), A(int, 7), A(float*, 8), A(float*, 9), A(float*, 10))); }},
+      {"hb::cam2prior_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::cam2prior_bwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(int, 3), A(cf, 4), A(int, 5), A(cf, 6), A(int, 7), A(cf, 8), A(cf, 9), A(cf, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
       {"hb::fit_losses_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_losses_kernel(A(HbFitArgs, 0))); }},
       {"hb::fit_reduce1_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce1_kernel(A(HbFitArgs, 0))); }},
       {"hb::fit_reduce_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce_kernel(A(HbFitArgs, 0))); }},
@@ -67,6 +69,11 @@ const std::map<std::string, Thunk>& registry() {
          tcemu::reset();                                                                                                        \
          RUN((hb_emu::umma_gemm3_kernel<BN, EPI, 1>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(hb_emu::GemmEpi, 11)))); }},
       UMMA_THUNK(64, 0) UMMA_THUNK(64, 1) UMMA_THUNK(64, 2) UMMA_THUNK(128, 0) UMMA_THUNK(128, 1) UMMA_THUNK(128, 2)
+#define UMMAP_THUNK(EPI)   /* persistent 128x128 tiles, two epilogue groups: CTAs are independent, run one after another */             \
+      {"hb::umma_gemm3p_kernel<" #EPI ">", [](dim3 g, dim3 b, void** a) {                                                       \
+         tcemu::reset();                                                                                                        \
+         RUN((hb_emu::umma_gemm3p_kernel<EPI>(MAP(0), MAP(1), MAP(2), MAP(3), A(int, 4), A(int, 5), A(int, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(hb_emu::GemmEpi, 11)))); }},
+      UMMAP_THUNK(0) UMMAP_THUNK(1) UMMAP_THUNK(2)
 #define UMMA_SPLITK_THUNK(EPI)   /* split-K over a 4-CTA cluster: the four CTAs run concurrently, partials meet through DSMEM stores */      \
       {"hb::umma_gemm3_kernel<64, " #EPI ", 4>", [](dim3 g, dim3 b, void** a) {                                                 \
          tcemu::reset();                                                                                                        \

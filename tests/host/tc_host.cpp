@@ -52,4 +52,21 @@ long long h_umma_gemm16(const unsigned short* A_h, const unsigned short* A_l, in
   else shim::launch_cluster(grid, dim3(192), 4, [&] { umma_gemm16_kernel<64, EPI_GN_RELU, 4>(a_h, a_l, b_h, b_l, M, N, K, C, ldc, C16_h, C16_l, ld16, ep); });
   return tcemu::g_mma_count;
 }
+
+// persistent 128x128-tile 3xTF32 GEMM with two epilogue groups (umma_gemm3p_kernel): `grid` CTAs walk the tiles round-robin
+long long h_umma_gemm3p(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb, int M, int N, int K,
+                        float* C, float* C_hi, float* C_lo, int ldc, int epi, const float* bias, const float* gamma, const float* beta,
+                        float* xhat, int ldxh, float* rstd, int gsize, int cch, int grid) {
+  CUtensorMap a_hi{A_hi, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 32, UM_BM};
+  CUtensorMap a_lo{A_lo, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 32, UM_BM};
+  CUtensorMap b_hi{B_hi, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 32, 128};
+  CUtensorMap b_lo{B_lo, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 32, 128};
+  GemmEpi ep;
+  ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.xhat = xhat; ep.rstd = rstd; ep.ldxh = ldxh; ep.Cch = cch; ep.gsize = gsize;
+  tcemu::reset();
+  if (epi == EPI_BIAS) shim::launch(dim3(grid), dim3(UMP_THREADS), [&] { umma_gemm3p_kernel<EPI_BIAS>(a_hi, a_lo, b_hi, b_lo, M, N, K, C, C_hi, C_lo, ldc, ep); });
+  else if (epi == EPI_GN_RELU) shim::launch(dim3(grid), dim3(UMP_THREADS), [&] { umma_gemm3p_kernel<EPI_GN_RELU>(a_hi, a_lo, b_hi, b_lo, M, N, K, C, C_hi, C_lo, ldc, ep); });
+  else shim::launch(dim3(grid), dim3(UMP_THREADS), [&] { umma_gemm3p_kernel<EPI_GN_RELU_BWD>(a_hi, a_lo, b_hi, b_lo, M, N, K, C, C_hi, C_lo, ldc, ep); });
+  return tcemu::g_mma_count;
+}
 }

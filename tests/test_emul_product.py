@@ -158,6 +158,17 @@ def test_sharded_run_matches_single_process_run(emul, tmp_path):
             assert np.abs(both - single[k]).max() < 5e-5, (k, float(np.abs(both - single[k]).max()))
 
 
+def test_cam2prior_kernel_pair_matches_the_torch_form(emul):
+    """humor_cam2prior_fwd / _bwd (one launch each instead of ~60 torch ops forward and ~150 autograd nodes in reverse) against
+    fitting_utils.compute_cam2prior_torch in float64 with autograd: both signs of the floor normal's y (the flip of
+    parse_floor_plane), a near-identity root orientation, gradient of the root joint only.  Measured: forward 9e-7, gradients 1.4e-5
+    relative (fp32 Rodrigues near the identity)."""
+    out = run_probe(emul, 'probe_cam2prior.py')
+    assert out['finite'] and out['joint_grad_only_root'] and out['orthonormal'] < 3e-6
+    assert max(out['fwd']) < 5e-6 and max(out['bwd_rel']) < 1e-4, out
+    assert out['parsed_plane_vs_kernel'] < 5e-6
+
+
 def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
     """humor_lbs_fwd's tensor-core path on the emulated tcgen05 kernels: the library's own dispatch AND its own TMA-descriptor
     code (cuTensorMapEncodeTiled is emulated) for the two-kernel form (1, 1) and the fused blend + group-skinning kernel on 3xTF32

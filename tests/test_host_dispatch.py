@@ -50,7 +50,7 @@ def test_two_kernel_form_runs_slab_by_slab(mock):
     assert info['rc_cfg'] == 0 and info['rc'] == 0
     assert info['used'] == [1, 1], (info, k[:8])
     assert count(k, 'lbs_pose_warp_kernel') == 1 and count(k, 'lbs_gather_extra_kernel') == 1
-    assert count(k, 'lbs_skin_apply_kernel') == 3 and count(k, 'umma_gemm3_kernel<128') == 3
+    assert count(k, 'lbs_skin_apply_kernel') == 3 and count(k, 'umma_gemm3p_kernel<0>') == 3      # persistent 128x128-tile blend GEMM
     assert info['launches'] == len(k) == 8
 
 

@@ -211,3 +211,56 @@ def test_fuseg_kernel_fp16_three_products(H):
     assert np.isfinite(out).all()
     scale = max(1.0, np.abs(ref).max())
     assert np.abs(out - ref).max() < 4e-6 * scale, np.abs(out - ref).max()
+
+
+# ---- persistent 128x128-tile 3xTF32 GEMM with two epilogue groups (csrc/umma_gemm.cuh: umma_gemm3p_kernel)
+@pytest.mark.parametrize('K,grid', [(96, 3), (352, 2), (1024, 5)])        # 1, 3 and 8 promotion chunks; 12 tiles over 2-5 CTAs
+def test_persistent_gemm_groupnorm_forward_reverse_and_bias(H, K, grid):
+    """The batched prior's shape class: ragged M (5 row tiles + 37 rows) x 256 columns.  CTAs take several tiles each, so both
+    epilogue groups, the re-use of their TMEM buffer pairs across tiles (odd and even chunk counts) and the operand ring running
+    across tile boundaries are exercised; forward GroupNorm + ReLU with hi/lo output planes and the x-hat / 1/sigma tape, the
+    reverse of it, and the plain bias epilogue."""
+    M, N = 5 * 128 + 37, 256
+    rng = np.random.RandomState(K + grid)
+    A = (rng.randn(M, K) * 0.8).astype(np.float32)
+    W = (rng.randn(N, K) * (1.5 / np.sqrt(K))).astype(np.float32)
+    bias, gamma, beta = (np.ascontiguousarray(rng.randn(N).astype(np.float32) * s) for s in (0.1, 1.0, 0.2))
+    gamma = np.ascontiguousarray(gamma + 1.0)
+    (Ah, Al), (Wh, Wl) = split_rn(A), split_rn(W)
+    H.h_umma_gemm3p.restype = ctypes.c_longlong
+    ntiles = 6 * 2
+    # forward: Linear + bias + GroupNorm(64) + ReLU
+    Chi, Clo = np.full((M, N), np.nan, np.float32), np.full((M, N), np.nan, np.float32)
+    xhat, rstd = np.full((M, N), np.nan, np.float32), np.full((M, 16), np.nan, np.float32)
+    nmma = H.h_umma_gemm3p(P(Ah), P(Al), K, P(Wh), P(Wl), K, M, N, K, None, P(Chi), P(Clo), N, 1, P(bias), P(gamma), P(beta), P(xhat), N,
+                           P(rstd), 64, N, grid)
+    assert nmma == ntiles * (K // 32) * 4 * 3
+    y = A.astype(np.float64) @ W.astype(np.float64).T + bias
+    yg = y.reshape(M, N // 64, 64)
+    mean, var = yg.mean(-1, keepdims=True), yg.var(-1, keepdims=True)
+    xh_ref = ((yg - mean) / np.sqrt(var + 1e-5)).reshape(M, N)
+    out_ref = np.maximum(xh_ref * gamma + beta, 0.0)
+    out = Chi.astype(np.float64) + Clo
+    assert np.abs(out - out_ref).max() < 3e-6 * max(1.0, np.abs(out_ref).max()) and np.abs(xhat - xh_ref).max() < 3e-6 * np.abs(xh_ref).max()
+    assert np.abs(rstd[:, :N // 64] - 1.0 / np.sqrt(var[..., 0] + 1e-5)).max() < 1e-5 * (1.0 / np.sqrt(var.min() + 1e-5))
+    assert (Chi.view(np.uint32) & 0x1fff).max() == 0                        # hi plane: tf32-representable
+    # reverse: d y (N = Cch) -> d of the GroupNorm input, through ReLU mask and the saved x-hat / 1/sigma
+    G = (rng.randn(M, K) * 0.5).astype(np.float32)                        # upstream gradient, as the K-wide operand
+    (Gh, Gl) = split_rn(G)
+    Dhi, Dlo = np.full((M, N), np.nan, np.float32), np.full((M, N), np.nan, np.float32)
+    H.h_umma_gemm3p(P(Gh), P(Gl), K, P(Wh), P(Wl), K, M, N, K, None, P(Dhi), P(Dlo), N, 2, None, P(gamma), P(beta), P(xhat), N, P(rstd), 64, N,
+                    grid)
+    dy = G.astype(np.float64) @ W.astype(np.float64).T
+    u = np.where(xh_ref * gamma + beta > 0.0, dy * gamma, 0.0).reshape(M, N // 64, 64)
+    xg = xh_ref.reshape(M, N // 64, 64)
+    d_ref = ((u - u.mean(-1, keepdims=True) - xg * (u * xg).mean(-1, keepdims=True)) / np.sqrt(var + 1e-5)).reshape(M, N)
+    d = Dhi.astype(np.float64) + Dlo
+    # entries whose ReLU argument is within rounding of zero may fall on the other side of the mask
+    close = np.abs(xh_ref * gamma + beta) < 1e-5
+    bad_rows = close.reshape(M, N // 64, 64).any(-1).repeat(64, -1).reshape(M, N)
+    assert np.abs(d - d_ref)[~bad_rows].max() < 2e-5 * max(1.0, np.abs(d_ref).max())
+    # bias epilogue, fp32 output, ragged N
+    Nr = 256 - 24
+    Cb = np.full((M, N), np.nan, np.float32)
+    H.h_umma_gemm3p(P(Ah), P(Al), K, P(Wh), P(Wl), K, M, Nr, K, P(Cb), None, None, N, 0, P(bias), None, None, None, 0, None, 64, 0, grid)
+    assert np.abs(Cb[:, :Nr] - y[:, :Nr]).max() < 4e-6 * max(1.0, np.abs(y).max()) and np.isnan(Cb[:, Nr:]).all()

@@ -1,8 +1,8 @@
 #!/bin/bash
-# Round 2, GPU call 13: run() end-to-end test with the stage files, where the library-L-BFGS run at B=256 leaves the finite
+# Round 2, GPU call 13: full GPU suite after the LBS form pruning (incl. run() end-to-end with the stage files), where the library-L-BFGS run at B=256 leaves the finite
 # numbers (tools/diag_nonfinite.py), and one ncu --set full capture of the batched prior GEMMs (forward GroupNorm and reverse).
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_zz_run_e2e.py -q --timeout 600 -p no:cacheprovider 2>&1 | grep -v "^  " | tail -12 | cut -c1-400) > gpurun_out/r02m_tests.txt
+(timeout 900 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider 2>&1 | grep -v "^  " | tail -25 | cut -c1-400) > gpurun_out/r02m_tests.txt
 tail -4 gpurun_out/r02m_tests.txt
 for prec in tensor exact; do
   (timeout 400 python tools/diag_nonfinite.py 256 $prec torch gpurun_out/r02m_diag_$prec 2>gpurun_out/r02m_diag_$prec.err) > gpurun_out/r02m_diag_$prec.jsonl

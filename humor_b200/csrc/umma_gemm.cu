@@ -105,7 +105,7 @@ static cudaError_t launch_p(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_gemm3p_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<128>::TOTAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_gemm3p_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, UMP_SMEM);
     if (e != cudaSuccess) { sms = 0; return e; }
     const char* w = getenv("HB_GEMM_CTAS");                    // tests: fewer CTAs than tiles on small problems
     want = w ? atoi(w) : 0;
@@ -116,7 +116,7 @@ static cudaError_t launch_p(const CUtensorMap& a_hi, const CUtensorMap& a_lo, co
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(UMP_THREADS);
-  cfg.dynamicSmemBytes = UmmaSmem<128>::TOTAL;
+  cfg.dynamicSmemBytes = UMP_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -150,7 +150,7 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
   case E:                                                                                                            \
     if (splitk) return launch_t<64, E, 4>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);          \
     if (bn == 64) return launch_t<64, E, 1>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);         \
-    return g_persist ? launch_p<E>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st)                  \
+    return (g_persist && (E == EPI_BIAS || ep.gsize == 64)) ? launch_p<E>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st)                  \
                      : launch_t<128, E, 1>(ta_hi, ta_lo, tb_hi, tb_lo, M, N, K, C, C_hi, C_lo, ldc, ep, st);
   switch (epi) {
     HB_UMMA_CASE(EPI_BIAS)

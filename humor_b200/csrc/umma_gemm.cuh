@@ -419,7 +419,16 @@ umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 // g, g+2, ... and runs their epilogue while the MMA lane is already accumulating the next tile into the other pair and group 1-g
 // promotes it.  The operand ring runs across tiles, so the next tile's loads are in flight during the last chunk as well.
 // ------------------------------------------------------------------------------------------------------------------------------
+// Epilogue I/O: a thread owns a ROW of the tile (the TMEM lane), so stores straight from registers touch 32 different 128-byte
+// lines per instruction with 16 of 32 bytes per sector used - with both groups' epilogues running the K = 96 reverse GEMM stayed at
+// 114 us (profiles/r02n_prior_gemm_persistent_set_full.txt).  Every global access of the epilogue therefore goes through a per-warp
+// staging tile of 32 rows x 16 columns (row stride 20 floats: 128-bit accesses conflict-free in both directions): registers ->
+// tile -> 8 rows x 64 contiguous bytes per instruction, and the reverse for the saved x-hat of the GroupNorm reverse.
 constexpr int UMP_THREADS = 64 + 2 * 128;
+constexpr int UMP_SLD = 20;                                    // floats per staging row
+constexpr int UMP_STAGE_W = 32 * UMP_SLD * 4;                  // bytes per epilogue warp
+constexpr int UMP_STAGING = 8 * UMP_STAGE_W;
+constexpr int UMP_SMEM = UmmaSmem<128>::TOTAL + UMP_STAGING;
 
 template <int EPI>
 __global__ void __launch_bounds__(UMP_THREADS, 1)
@@ -433,7 +442,8 @@ umma_gemm3p_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   HB_DYN_SMEM(smem_raw);
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bars = base + UM_STAGES * SM::STAGE;          // full[3] | empty[3] | tfull[4] | tempty[4] | tmem_ptr
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bars = base + UM_STAGES * SM::STAGE + UMP_STAGING;   // full[3] | empty[3] | tfull[4] | tempty[4] | tmem_ptr
   const uint32_t full0 = bars, empty0 = bars + 8 * UM_STAGES, tfull0 = bars + 16 * UM_STAGES, tempty0 = tfull0 + 32,
                  tptr = tempty0 + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -539,41 +549,111 @@ umma_gemm3p_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * b);
       }
-      auto store4 = [&](int col, float a, float b_, float c_, float d) {
-        if (col + 3 < N) {
-          if (C) *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = make_float4(a, b_, c_, d);
-          if (C_hi) {
-            const float4 h = make_float4(tf32_hi(a), tf32_hi(b_), tf32_hi(c_), tf32_hi(d));
-            *reinterpret_cast<float4*>(C_hi + (size_t)row * ldc + col) = h;
-            *reinterpret_cast<float4*>(C_lo + (size_t)row * ldc + col) = make_float4(a - h.x, b_ - h.y, c_ - h.z, d - h.w);
-          }
-        } else {
-          const float o[4] = {a, b_, c_, d};
+      float* S = reinterpret_cast<float*>(gbase + UM_STAGES * SM::STAGE + (warp - 2) * UMP_STAGE_W);
+      const int r8 = lane >> 2, cg = (lane & 3) * 4;            // transfer phase: 8 rows x 4 column quads per instruction
+      const int row0 = m0 + q * 32;
+      // 16 values of this thread's row (columns col0 .. col0+15) -> dst[row][col0 ..], coalesced
+      auto put16 = [&](float* dst, int ld, int col0, const float* v) {
+        float4* sr = reinterpret_cast<float4*>(S + lane * UMP_SLD);
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            if (col + jj < N) {
-              if (C) C[(size_t)row * ldc + col + jj] = o[jj];
-              if (C_hi) { const float h = tf32_hi(o[jj]); C_hi[(size_t)row * ldc + col + jj] = h; C_lo[(size_t)row * ldc + col + jj] = o[jj] - h; }
-            }
+        for (int k = 0; k < 4; ++k) sr[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int p_ = 0; p_ < 4; ++p_) {
+          const int r = p_ * 8 + r8, grow = row0 + r, col = col0 + cg;
+          const float4 x = *reinterpret_cast<const float4*>(S + r * UMP_SLD + cg);
+          if (grow < M) {
+            float* o = dst + (size_t)grow * ld + col;
+            if (col + 3 < N) *reinterpret_cast<float4*>(o) = x;
+            else { if (col < N) o[0] = x.x; if (col + 1 < N) o[1] = x.y; if (col + 2 < N) o[2] = x.z; }
+          }
+        }
+        __syncwarp();
+      };
+      // the reverse: src[row][col0 .. col0+15] of the warp's 32 rows -> 16 values of this thread's row (columns < width, else 0)
+      auto get16 = [&](const float* src, int ld, int width, int col0, float* v) {
+#pragma unroll
+        for (int p_ = 0; p_ < 4; ++p_) {
+          const int r = p_ * 8 + r8, grow = row0 + r, col = col0 + cg;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow < M && col + 3 < width) x = *reinterpret_cast<const float4*>(src + (size_t)grow * ld + col);
+          *reinterpret_cast<float4*>(S + r * UMP_SLD + cg) = x;
+        }
+        __syncwarp();
+        const float4* sr = reinterpret_cast<const float4*>(S + lane * UMP_SLD);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float4 x = sr[k]; v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w; }
+        __syncwarp();
+      };
+      // result columns col0 .. col0+15 of the row: exact value and / or hi/lo planes
+      auto put_result16 = [&](int col0, const float* v) {
+        if (C) put16(C, ldc, col0, v);
+        if (C_hi) {
+          float h[16], l[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { h[e] = tf32_hi(v[e]); l[e] = v[e] - h[e]; }
+          put16(C_hi, ldc, col0, h);
+          put16(C_lo, ldc, col0, l);
         }
       };
-      if (rok) {
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-          const int col = n0 + c0;
-          if (col < N) {
-            if (EPI == EPI_BIAS) {
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        const int col = n0 + c0;
+        if (col >= N) break;                                    // warp-uniform
+        float* v = acc + c0;
+        if (EPI == EPI_BIAS) {
 #pragma unroll
-              for (int jj = 0; jj < 64; ++jj) acc[c0 + jj] += (ep.bias && col + jj < N) ? ep.bias[col + jj] : 0.f;
-            } else if (EPI == EPI_GN_RELU) {
-              if (ep.gsize == 64) gn_relu_fwd_group<64>(acc + c0, col, row, ep);
-              else { gn_relu_fwd_group<32>(acc + c0, col, row, ep); gn_relu_fwd_group<32>(acc + c0 + 32, col + 32, row, ep); }
-            } else if (col < ep.Cch) {
-              if (ep.gsize == 64) gn_relu_bwd_group<64>(acc + c0, col, row, ep);
-              else { gn_relu_bwd_group<32>(acc + c0, col, row, ep); gn_relu_bwd_group<32>(acc + c0 + 32, col + 32, row, ep); }
+          for (int k = 0; k < 64; k += 16) {
+            if (col + k >= N) break;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[k + e] += (ep.bias && col + k + e < N) ? ep.bias[col + k + e] : 0.f;
+            put_result16(col + k, v + k);
+          }
+        } else if (EPI == EPI_GN_RELU) {
+          // GroupNorm over the 64 columns (one group: the launcher sends other group sizes to the one-tile kernel) + ReLU;
+          // x-hat and 1/sigma go to the tape for the reverse pass
+          float sum = 0.f, sq = 0.f;
+#pragma unroll
+          for (int e = 0; e < 64; ++e) { v[e] += ep.bias[col + e]; sum += v[e]; }
+          const float mean = sum * (1.f / 64.f);
+#pragma unroll
+          for (int e = 0; e < 64; ++e) { const float d = v[e] - mean; sq += d * d; }
+          const float rs = rsqrtf(sq * (1.f / 64.f) + 1e-5f);
+          if (rok) ep.rstd[(size_t)row * 16 + col / 64] = rs;
+#pragma unroll
+          for (int k = 0; k < 64; k += 16) {
+            float xh[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              xh[e] = (v[k + e] - mean) * rs;
+              v[k + e] = fmaxf(fmaf(ep.gamma[col + k + e], xh[e], ep.beta[col + k + e]), 0.f);
             }
+            put16(ep.xhat, ep.ldxh, col + k, xh);
+            put_result16(col + k, v + k);
+          }
+        } else {
+          if (col < ep.Cch) {
+            float xh[64];
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < 64; jj += 4) store4(col + jj, acc[c0 + jj], acc[c0 + jj + 1], acc[c0 + jj + 2], acc[c0 + jj + 3]);
+            for (int k = 0; k < 64; k += 16) get16(ep.xhat, ep.ldxh, ep.ldxh, col + k, xh + k);
+#pragma unroll
+            for (int e = 0; e < 64; ++e) {
+              const float gm = ep.gamma[col + e];
+              const bool on = fmaf(gm, xh[e], ep.beta[col + e]) > 0.f;
+              const float u = on ? gm * v[e] : 0.f;
+              v[e] = u;
+              s1 += u;
+              s2 += u * xh[e];
+            }
+            const float rs = ep.rstd[(size_t)(rok ? row : 0) * 16 + col / 64];
+#pragma unroll
+            for (int e = 0; e < 64; ++e) v[e] = rs * (v[e] - s1 * (1.f / 64.f) - xh[e] * s2 * (1.f / 64.f));
+          }
+#pragma unroll
+          for (int k = 0; k < 64; k += 16) {
+            if (col + k >= N) break;
+            put_result16(col + k, v + k);
           }
         }
       }

@@ -70,7 +70,8 @@ class HbLbsModel(C.Structure):
                 ('depth', C.c_void_p), ('child_start', C.c_void_p), ('child_list', C.c_void_p),
                 ('g_start', C.c_void_p), ('g_joint', C.c_void_p), ('g_w', C.c_void_p), ('num_groups', C.c_int),
                 ('ft_nct', C.c_int), ('g_slot', C.c_void_p), ('ft_tab', C.c_void_p),
-                ('blend16a_h', C.c_void_p), ('blend16a_l', C.c_void_p)]
+                ('blend16a_h', C.c_void_p), ('blend16a_l', C.c_void_p),
+                ('sel_ids', C.c_void_p), ('sel_blend', C.c_void_p), ('sel_nv', C.c_int), ('reserved2', C.c_int)]
 
 
 class HbHumorWeights(C.Structure):

@@ -207,7 +207,20 @@ class LbsModel:
         if t is None:
             t = torch.tensor(list(ids), dtype=torch.int32, device=self.device)
             self._vlists[key] = t
+            if self.struct.sel_nv == 0 and 0 < len(key) <= 43:
+                self._select(t)
         return t
+
+    def _select(self, ids):
+        """The first short vertex list a caller asks for (the 43 key vertices of the fitting energies) becomes the model's selected
+        set: its blend columns and those of the 21 vertex-picked joints are packed once as [208][192], and calls that pass this very
+        tensor as vlist read them contiguously (csrc/lbs.cu, HbLbsModel.sel_blend)."""
+        cols = torch.cat([ids.long(), self.t['extra_ids'].long()])
+        tab = torch.zeros(self.t['blend'].shape[0], 192, device=self.device)
+        src = (cols[:, None] * 3 + torch.arange(3, device=self.device)[None]).reshape(-1)
+        tab[:, :src.numel()] = self.t['blend'][:, src]
+        self.t['sel_ids'], self.t['sel_blend'] = ids, tab.contiguous()
+        self.struct.sel_ids, self.struct.sel_blend, self.struct.sel_nv = ids.data_ptr(), self.t['sel_blend'].data_ptr(), ids.numel()
 
 
 class _LbsFn(torch.autograd.Function):

@@ -25,6 +25,7 @@ constexpr int SK_VT = 64;    // vertices per block tile
 constexpr int SK_FT = 64;    // frames per block tile (forward)
 constexpr int SK_FPT = 16;   // frames per thread (forward)
 constexpr int BW_FT = 16;    // frames per block (backward)
+constexpr int LBS_SEL_LD = 192;   // floats per row of HbLbsModel.sel_blend: 64 vertex slots x 3
 
 constexpr int TC_SLAB = 512;     // frames per tensor-core slab: v_posed slab (512 x 20736 fp32 = 42 MB) stays in L2
 constexpr int TC_KF = 224;
@@ -394,13 +395,17 @@ lbs_skin_fwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const f
   float acc[SK_FPT][3];
 #pragma unroll
   for (int f = 0; f < SK_FPT; ++f) acc[f][0] = acc[f][1] = acc[f][2] = 0.f;
-  const float* bp = m.blend + (size_t)vid * 3;
+  // the model's selected set (key vertices + the 21 vertex-picked joints): their blend columns are packed [208][192], so a warp
+  // reads 384 contiguous bytes per k instead of 32 lines 12 bytes each out of the [208][3V] matrix
+  const bool tab = m.sel_blend && ((vlist == m.sel_ids && nv == m.sel_nv) || vlist == m.extra_ids);
+  const float* bp = tab ? m.sel_blend + (size_t)(slot + (vlist == m.extra_ids ? m.sel_nv : 0)) * 3 : m.blend + (size_t)vid * 3;
+  const size_t bld = tab ? (size_t)LBS_SEL_LD : (size_t)m.v3_ld;
   const float* fs = Fs + (size_t)(fg * SK_FPT) * LBS_KF;
   for (int k = 0; k < 205; k += 4) {            // rows 205..207 are padding (zero)
     float p[4][3];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const float* b = bp + (size_t)(k + kk) * m.v3_ld;
+      const float* b = bp + (size_t)(k + kk) * bld;
       p[kk][0] = __ldg(b); p[kk][1] = __ldg(b + 1); p[kk][2] = __ldg(b + 2);
     }
 #pragma unroll
@@ -540,9 +545,13 @@ lbs_skin_bwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const f
       float acc[4][3];
 #pragma unroll
       for (int f = 0; f < 4; ++f) acc[f][0] = acc[f][1] = acc[f][2] = 0.f;
-      const float* bp = m.blend + (size_t)vid * 3;
+      const bool tab = m.sel_blend && ((vlist == m.sel_ids && nv1 == m.sel_nv && (nv1 == nv || vlist2 == m.extra_ids)) ||
+                                       (vlist == m.extra_ids && nv1 == nv));
+      const float* bp = tab ? m.sel_blend + (size_t)(slot + (vlist == m.extra_ids ? m.sel_nv : 0)) * 3 : m.blend + (size_t)vid * 3;
+      const size_t bld = tab ? (size_t)LBS_SEL_LD : (size_t)m.v3_ld;
+#pragma unroll 5
       for (int k = 0; k < 205; ++k) {
-        const float* b = bp + (size_t)k * m.v3_ld;
+        const float* b = bp + (size_t)k * bld;
         const float p0 = __ldg(b), p1 = __ldg(b + 1), p2 = __ldg(b + 2);
 #pragma unroll
         for (int f = 0; f < 4; ++f) {

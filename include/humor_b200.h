@@ -77,6 +77,14 @@ typedef struct HbLbsModel {
      plane (x = h + l) [v3_ld][256] each; NULL: form unavailable */
   const void* blend16a_h;
   const void* blend16a_l;
+  /* selected-vertex set of the fitting energies (the key vertices of fitting_utils.KEYPT_VERTS, then the 21 vertex-picked
+     joints): when humor_lbs_fwd / _bwd are called with vlist == sel_ids (the same device pointer) and nv == sel_nv, the skinning
+     passes read the blend columns of those vertices from sel_blend [208][192] (slot s at columns 3s..3s+2; slots sel_nv ..
+     sel_nv+20 = extra_ids) instead of gathering them from blend.  NULL / 0: no such set (any vlist works, gathered). */
+  const int* sel_ids;      /* [sel_nv], sel_nv + 21 <= 64 */
+  const float* sel_blend;
+  int sel_nv;
+  int reserved2;
 } HbLbsModel;
 
 /* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs

@@ -105,7 +105,7 @@ EXPORTS = ['humor_lbs_workspace_bytes', 'humor_lbs_fwd', 'humor_lbs_bwd', 'humor
            'humor_rollout_fwd', 'humor_rollout_bwd', 'humor_rodrigues_fwd', 'humor_rodrigues_bwd',
            'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version',
            'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd', 'humor_lbs_configure', 'humor_lbs_forms_used',
-           'humor_umma_gemm16', 'humor_umma_gemm16_workspace_bytes', 'humor_chain_debug', 'humor_cam2prior_fwd', 'humor_cam2prior_bwd']
+           'humor_umma_gemm16', 'humor_umma_gemm16_workspace_bytes', 'humor_chain_debug', 'humor_cam2prior_fwd', 'humor_cam2prior_bwd', 'humor_rollout_outputs_fwd', 'humor_rollout_outputs_bwd']
 
 _LIB = None
 
@@ -143,6 +143,10 @@ def lib():
     L.humor_cam2prior_fwd.argtypes = [ci, vp, vp, ci, vp, ci, vp, ci, vp, vp, vp, vp]
     L.humor_cam2prior_bwd.restype = ci
     L.humor_cam2prior_bwd.argtypes = [ci, vp, vp, ci, vp, ci, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.humor_rollout_outputs_fwd.restype = ci
+    L.humor_rollout_outputs_fwd.argtypes = [ci, ci] + [vp] * 8 + [C.c_float] + [vp] * 10
+    L.humor_rollout_outputs_bwd.restype = ci
+    L.humor_rollout_outputs_bwd.argtypes = [ci, ci] + [vp] * 19
     L.humor_fit_losses.restype = ci
     L.humor_fit_losses.argtypes = [C.POINTER(HbFitArgs), i64p, vp]
     L.humor_gmm_nll.restype = ci

@@ -166,6 +166,212 @@ __global__ void cam2prior_bwd_kernel(int B, const float* __restrict__ floor, con
     d_joint0[3 * b + i] = g_j0[i];
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Outputs of the latent roll-out in the layout the energies read (humor/fitting/motion_optimizer.py:964-1019, :678-741):
+// world rows (S,B,348) of the CVAE chain + the frame-0 state -> (B,T,.) prior-frame translation / root orientation / body pose
+// (axis-angle) / joints / contact logits, contact confidences and labels, and - with a camera->prior transform (R, t) - the
+// camera-frame root orientation and translation of apply_cam2prior(inverse=True).  As torch ops this was a permute, 5 slices, the
+// matrix->axis-angle kernel, 4 concatenations, sigmoid / index_copy / cat / compare, and Rodrigues + 2 batched matmuls + matrix->
+// axis-angle for the camera frame; in reverse 5 zero-filled (S,B,348) buffers added together.  One block per sub-sequence.
+// World columns: 0 trans | 3 trans_vel | 6 root R | 15 root vel | 18 body R (21) | 207 joints | 273 joint vel | 339 contact logits.
+// ------------------------------------------------------------------------------------------------
+constexpr int RO_LD = 348;
+constexpr int RO_THREADS = 128;
+struct RollOut {
+  int B, S;
+  const float* world;      // [S][B][348]
+  const float* trans0;     // [B][3]   frame 0 (prior frame)
+  const float* orient0;    // [B][3]
+  const float* pose0;      // [B][63]
+  const float* joints0;    // [B][66]
+  const float* R;          // [B][9] rows right/forward/up of the prior frame in camera coordinates, or NULL (no camera frame)
+  const float* t;          // [B][3]
+  const int* contact_idx;  // [9] joint of every contact logit
+  float thresh;
+  float *trans, *orient, *pose, *joints;     // [B][T][3|3|63|66]
+  float *logits;                              // [B][S][9]
+  float *conf, *labels;                       // [B][T][22]
+  float *cam_trans, *cam_orient;              // [B][T][3] (R != NULL)
+};
+__global__ void __launch_bounds__(RO_THREADS) rollout_outputs_fwd_kernel(RollOut a) {
+  const int b = blockIdx.x, tid = threadIdx.x, T = a.S + 1;
+  const float* R = a.R ? a.R + 9 * b : nullptr;
+  for (int idx = tid; idx < T * 22; idx += RO_THREADS) {         // rotations: root (j = 0) and the 21 body joints
+    const int t = idx / 22, j = idx - 22 * t;
+    float aa[3];
+    if (t == 0) {
+      const float* src = j == 0 ? a.orient0 + 3 * b : a.pose0 + 63 * b + 3 * (j - 1);
+      aa[0] = src[0]; aa[1] = src[1]; aa[2] = src[2];
+    } else {
+      const float* w = a.world + ((size_t)(t - 1) * a.B + b) * RO_LD + (j == 0 ? 6 : 18 + 9 * (j - 1));
+      float M[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) M[e] = w[e];
+      mat2aa_fwd(M, aa);
+    }
+    float* dst = j == 0 ? a.orient + ((size_t)b * T + t) * 3 : a.pose + ((size_t)b * T + t) * 63 + 3 * (j - 1);
+    dst[0] = aa[0]; dst[1] = aa[1]; dst[2] = aa[2];
+    if (j == 0 && R) {                                          // camera frame: R^T Rodrigues(aa) -> axis-angle
+      float Rq[9], Mc[9], ca[3];
+      rodrigues_fwd(aa, Rq);
+      mat3_mul_tn(R, Rq, Mc);
+      mat2aa_fwd(Mc, ca);
+      float* o = a.cam_orient + ((size_t)b * T + t) * 3;
+      o[0] = ca[0]; o[1] = ca[1]; o[2] = ca[2];
+    }
+  }
+  for (int idx = tid; idx < T * 66; idx += RO_THREADS) {         // joints
+    const int t = idx / 66, e = idx - 66 * t;
+    a.joints[((size_t)b * T + t) * 66 + e] = t == 0 ? a.joints0[66 * b + e] : a.world[((size_t)(t - 1) * a.B + b) * RO_LD + 207 + e];
+  }
+  for (int t = tid; t < T; t += RO_THREADS) {                    // translation, prior and camera frame
+    float p[3], p0[3] = {a.trans0[3 * b], a.trans0[3 * b + 1], a.trans0[3 * b + 2]};
+    for (int i = 0; i < 3; ++i) p[i] = t == 0 ? p0[i] : a.world[((size_t)(t - 1) * a.B + b) * RO_LD + i];
+    float* o = a.trans + ((size_t)b * T + t) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    if (R) {
+      const float d[3] = {p[0] - p0[0], p[1] - p0[1], p[2] - p0[2]};
+      float c[3];
+      mat3_tvec(R, d, c);
+      float* oc = a.cam_trans + ((size_t)b * T + t) * 3;
+      for (int i = 0; i < 3; ++i) oc[i] = c[i] - a.t[3 * b + i];
+    }
+  }
+  for (int idx = tid; idx < a.S * 9; idx += RO_THREADS) {        // contact logits
+    const int s = idx / 9, c = idx - 9 * s;
+    a.logits[((size_t)b * a.S + s) * 9 + c] = a.world[((size_t)s * a.B + b) * RO_LD + 339 + c];
+  }
+  for (int idx = tid; idx < T * 22; idx += RO_THREADS) {         // confidences on the 22 joints (frame 0 repeats step 0), labels
+    const int t = idx / 22, j = idx - 22 * t;
+    const int s = t == 0 ? 0 : t - 1;
+    float cf = 0.f;
+#pragma unroll
+    for (int c = 0; c < 9; ++c)
+      if (a.contact_idx[c] == j) cf = 1.f / (1.f + expf(-a.world[((size_t)s * a.B + b) * RO_LD + 339 + c]));
+    a.conf[((size_t)b * T + t) * 22 + j] = cf;
+    a.labels[((size_t)b * T + t) * 22 + j] = cf > a.thresh ? 1.f : 0.f;
+  }
+}
+struct RollOutBwd {
+  int B, S;
+  const float* world; const float* trans0; const float* orient0; const float* R;      // forward inputs the reverse needs
+  const float *g_trans, *g_orient, *g_pose, *g_joints, *g_logits, *g_cam_trans, *g_cam_orient;   // nullable = zero
+  float* d_world;          // [S][B][348], every element written
+  float *d_trans0, *d_orient0, *d_pose0, *d_joints0;   // [B][3|3|63|66]
+  float *d_R, *d_t;        // [B][9], [B][3] (R != NULL)
+};
+__global__ void __launch_bounds__(RO_THREADS) rollout_outputs_bwd_kernel(RollOutBwd a) {
+  __shared__ float red[RO_THREADS][15];                          // per-thread partials of d R (9), d t (3), d trans0 via the camera frame (3)
+  const int b = blockIdx.x, tid = threadIdx.x, T = a.S + 1;
+  const float* R = a.R ? a.R + 9 * b : nullptr;
+  float acc[15];
+#pragma unroll
+  for (int e = 0; e < 15; ++e) acc[e] = 0.f;
+  for (int idx = tid; idx < T * 22; idx += RO_THREADS) {         // rotations
+    const int t = idx / 22, j = idx - 22 * t;
+    const float* gsrc = j == 0 ? (a.g_orient ? a.g_orient + ((size_t)b * T + t) * 3 : nullptr)
+                               : (a.g_pose ? a.g_pose + ((size_t)b * T + t) * 63 + 3 * (j - 1) : nullptr);
+    float g[3] = {gsrc ? gsrc[0] : 0.f, gsrc ? gsrc[1] : 0.f, gsrc ? gsrc[2] : 0.f};
+    const float* w = t == 0 ? nullptr : a.world + ((size_t)(t - 1) * a.B + b) * RO_LD + (j == 0 ? 6 : 18 + 9 * (j - 1));
+    float M[9];
+    if (w) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) M[e] = w[e];
+    }
+    if (j == 0 && R && a.g_cam_orient) {
+      float aa[3];
+      if (w) mat2aa_fwd(M, aa);
+      else { aa[0] = a.orient0[3 * b]; aa[1] = a.orient0[3 * b + 1]; aa[2] = a.orient0[3 * b + 2]; }
+      const float* gc = a.g_cam_orient + ((size_t)b * T + t) * 3;
+      float Rq[9], Mc[9], gM[9], gRq[9], ga[3] = {0.f, 0.f, 0.f};
+      rodrigues_fwd(aa, Rq);
+      mat3_mul_tn(R, Rq, Mc);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) gM[e] = 0.f;
+      mat2aa_bwd(Mc, gc, gM);
+      mat3_mul(R, gM, gRq);                                      // Mc = R^T Rq: d Rq = R d Mc, d R = Rq d Mc^T
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[3 * i + k] += Rq[3 * i] * gM[3 * k] + Rq[3 * i + 1] * gM[3 * k + 1] + Rq[3 * i + 2] * gM[3 * k + 2];
+      rodrigues_bwd(aa, gRq, ga);
+      g[0] += ga[0]; g[1] += ga[1]; g[2] += ga[2];
+    }
+    if (t == 0) {
+      float* d = j == 0 ? a.d_orient0 + 3 * b : a.d_pose0 + 63 * b + 3 * (j - 1);
+      d[0] = g[0]; d[1] = g[1]; d[2] = g[2];
+    } else {
+      float gW[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) gW[e] = 0.f;
+      mat2aa_bwd(M, g, gW);
+      float* d = a.d_world + ((size_t)(t - 1) * a.B + b) * RO_LD + (j == 0 ? 6 : 18 + 9 * (j - 1));
+#pragma unroll
+      for (int e = 0; e < 9; ++e) d[e] = gW[e];
+    }
+  }
+  for (int idx = tid; idx < T * 66; idx += RO_THREADS) {         // joints; velocity columns carry no gradient
+    const int t = idx / 66, e = idx - 66 * t;
+    const float g = a.g_joints ? a.g_joints[((size_t)b * T + t) * 66 + e] : 0.f;
+    if (t == 0) a.d_joints0[66 * b + e] = g;
+    else {
+      float* d = a.d_world + ((size_t)(t - 1) * a.B + b) * RO_LD;
+      d[207 + e] = g;
+      d[273 + e] = 0.f;
+    }
+  }
+  for (int idx = tid; idx < a.S * 15; idx += RO_THREADS) {       // trans_vel (3), root velocity (3), contact logits (9)
+    const int s = idx / 15, e = idx - 15 * s;
+    float* d = a.d_world + ((size_t)s * a.B + b) * RO_LD;
+    if (e < 3) d[3 + e] = 0.f;
+    else if (e < 6) d[15 + e - 3] = 0.f;
+    else d[339 + e - 6] = a.g_logits ? a.g_logits[((size_t)b * a.S + s) * 9 + e - 6] : 0.f;
+  }
+  float g0[3] = {0.f, 0.f, 0.f};                                  // d trans0 of the thread that owns frame 0
+  for (int t = tid; t < T; t += RO_THREADS) {                    // translation
+    float g[3];
+    for (int i = 0; i < 3; ++i) g[i] = a.g_trans ? a.g_trans[((size_t)b * T + t) * 3 + i] : 0.f;
+    if (R && a.g_cam_trans) {
+      const float* gc = a.g_cam_trans + ((size_t)b * T + t) * 3;
+      float p[3], d[3], gd[3];
+      for (int i = 0; i < 3; ++i) {
+        p[i] = t == 0 ? a.trans0[3 * b + i] : a.world[((size_t)(t - 1) * a.B + b) * RO_LD + i];
+        d[i] = p[i] - a.trans0[3 * b + i];
+      }
+      mat3_vec(R, gc, gd);                                       // c = R^T d - t: d d = R g, d R[i][k] += d[i] g[k], d t = -g
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[3 * i + k] += d[i] * gc[k];
+        acc[9 + i] -= gc[i];
+        acc[12 + i] -= gd[i];                                    // through d = p - p0 into frame 0
+        g[i] += gd[i];
+      }
+    }
+    if (t == 0) { g0[0] = g[0]; g0[1] = g[1]; g0[2] = g[2]; }
+    else {
+      float* d = a.d_world + ((size_t)(t - 1) * a.B + b) * RO_LD;
+      d[0] = g[0]; d[1] = g[1]; d[2] = g[2];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 15; ++e) red[tid][e] = acc[e];
+  __syncthreads();
+  if (tid < 15) {                                                // fixed order: deterministic
+    float s = 0.f;
+    for (int i = 0; i < RO_THREADS; ++i) s += red[i][tid];
+    red[0][tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {                                                // thread 0 owns frame 0
+    for (int i = 0; i < 3; ++i) a.d_trans0[3 * b + i] = g0[i] + red[0][12 + i];
+    if (R) {
+      for (int e = 0; e < 9; ++e) a.d_R[9 * b + e] = red[0][e];
+      for (int i = 0; i < 3; ++i) a.d_t[3 * b + i] = red[0][9 + i];
+    }
+  }
+}
 }  // namespace hb
 #ifndef HB_HOST_SHIM   // host side of the C-ABI (launch syntax): device builds only
 using namespace hb;
@@ -203,6 +409,36 @@ extern "C" int humor_cam2prior_bwd(int B, const float* floor_plane, const float*
     return HB_ERR_ARG;
   cam2prior_bwd_kernel<<<cdiv(B, 64), 64, 0, st>>>(B, floor_plane, trans0, ld_t, orient0, ld_r, joint0, ld_j, gR, gt, gh, d_floor, d_trans0,
                                                   d_orient0, d_joint0);
+  HB_LAUNCH_CHECK(); return HB_OK;
+}
+extern "C" int humor_rollout_outputs_fwd(int B, int S, const float* world, const float* trans0, const float* orient0, const float* pose0,
+                                         const float* joints0, const float* R, const float* t, const int* contact_idx, float thresh,
+                                         float* trans, float* orient, float* pose, float* joints, float* logits, float* conf,
+                                         float* labels, float* cam_trans, float* cam_orient, cudaStream_t st) {
+  if (B <= 0 || S <= 0 || !world || !trans0 || !orient0 || !pose0 || !joints0 || !contact_idx || !trans || !orient || !pose || !joints ||
+      !logits || !conf || !labels || ((R != nullptr) != (t != nullptr)) || (R && (!cam_trans || !cam_orient)))
+    return HB_ERR_ARG;
+  RollOut a;
+  a.B = B; a.S = S; a.world = world; a.trans0 = trans0; a.orient0 = orient0; a.pose0 = pose0; a.joints0 = joints0; a.R = R; a.t = t;
+  a.contact_idx = contact_idx; a.thresh = thresh; a.trans = trans; a.orient = orient; a.pose = pose; a.joints = joints; a.logits = logits;
+  a.conf = conf; a.labels = labels; a.cam_trans = cam_trans; a.cam_orient = cam_orient;
+  rollout_outputs_fwd_kernel<<<B, RO_THREADS, 0, st>>>(a);
+  HB_LAUNCH_CHECK(); return HB_OK;
+}
+extern "C" int humor_rollout_outputs_bwd(int B, int S, const float* world, const float* trans0, const float* orient0, const float* R,
+                                         const float* g_trans, const float* g_orient, const float* g_pose, const float* g_joints,
+                                         const float* g_logits, const float* g_cam_trans, const float* g_cam_orient, float* d_world,
+                                         float* d_trans0, float* d_orient0, float* d_pose0, float* d_joints0, float* d_R, float* d_t,
+                                         cudaStream_t st) {
+  if (B <= 0 || S <= 0 || !world || !trans0 || !orient0 || !d_world || !d_trans0 || !d_orient0 || !d_pose0 || !d_joints0 ||
+      (R && (!d_R || !d_t)))
+    return HB_ERR_ARG;
+  RollOutBwd a;
+  a.B = B; a.S = S; a.world = world; a.trans0 = trans0; a.orient0 = orient0; a.R = R; a.g_trans = g_trans; a.g_orient = g_orient;
+  a.g_pose = g_pose; a.g_joints = g_joints; a.g_logits = g_logits; a.g_cam_trans = R ? g_cam_trans : nullptr;
+  a.g_cam_orient = R ? g_cam_orient : nullptr; a.d_world = d_world; a.d_trans0 = d_trans0; a.d_orient0 = d_orient0; a.d_pose0 = d_pose0;
+  a.d_joints0 = d_joints0; a.d_R = d_R; a.d_t = d_t;
+  rollout_outputs_bwd_kernel<<<B, RO_THREADS, 0, st>>>(a);
   HB_LAUNCH_CHECK(); return HB_OK;
 }
 extern "C" const char* humor_b200_version(void) { return "humor_b200 0.1 (sm_100a)"; }

@@ -30,6 +30,57 @@ CONTACT_INDS = [0, 4, 5, 7, 8, 10, 11, 20, 21]
 NUM_JOINTS = 22
 
 
+class _RolloutOutputs(torch.autograd.Function):
+    """humor_rollout_outputs_fwd / _bwd (csrc/rot.cu): world rows of the CVAE chain + the frame-0 state -> the (B,T,.) tensors the
+    energies read, in the prior frame and (R, t given) in the camera frame.  Returns (trans, root_orient, pose_body, joints (B,T,22,3),
+    contacts_logits (B,S,9), contacts_conf, contacts, cam_trans | None, cam_root_orient | None)."""
+
+    @staticmethod
+    def forward(ctx, world, trans0, orient0, pose0, joints0, R, t, contact_idx):
+        from . import _ext
+        _ext.require_cuda(world, trans0, orient0, pose0, joints0)
+        world, trans0, orient0, pose0, joints0 = (_ext.f32c(x) for x in (world, trans0, orient0, pose0, joints0))
+        S, B = world.shape[0], world.shape[1]
+        T = S + 1
+        if R is not None:
+            R, t = _ext.f32c(R), _ext.f32c(t)
+        new = lambda *sh: torch.empty(*sh, device=world.device, dtype=torch.float32)
+        trans, orient, pose, joints = new(B, T, 3), new(B, T, 3), new(B, T, 63), new(B, T, NUM_JOINTS, 3)
+        logits, conf, labels = new(B, S, 9), new(B, T, NUM_JOINTS), new(B, T, NUM_JOINTS)
+        cam_t = new(B, T, 3) if R is not None else None
+        cam_o = new(B, T, 3) if R is not None else None
+        _ext.check(_ext.lib().humor_rollout_outputs_fwd(
+            B, S, _ext.ptr(world), _ext.ptr(trans0), _ext.ptr(orient0), _ext.ptr(pose0), _ext.ptr(joints0), _ext.ptr(R), _ext.ptr(t),
+            _ext.ptr(contact_idx), CONTACT_THRESH, _ext.ptr(trans), _ext.ptr(orient), _ext.ptr(pose), _ext.ptr(joints), _ext.ptr(logits),
+            _ext.ptr(conf), _ext.ptr(labels), _ext.ptr(cam_t), _ext.ptr(cam_o), _ext.stream_ptr()), 'humor_rollout_outputs_fwd')
+        _ext.LaunchCounter.total += 1
+        ctx.save_for_backward(world, trans0, orient0, R)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(conf, labels)
+        if R is None:
+            return trans, orient, pose, joints, logits, conf, labels
+        return trans, orient, pose, joints, logits, conf, labels, cam_t, cam_o
+
+    @staticmethod
+    def backward(ctx, g_trans, g_orient, g_pose, g_joints, g_logits, g_conf, g_labels, g_cam_t=None, g_cam_o=None):
+        from . import _ext
+        world, trans0, orient0, R = ctx.saved_tensors
+        S, B = world.shape[0], world.shape[1]
+        c = lambda g: None if g is None else _ext.f32c(g)
+        g_trans, g_orient, g_pose, g_joints, g_logits, g_cam_t, g_cam_o = (c(g) for g in (g_trans, g_orient, g_pose, g_joints, g_logits,
+                                                                                       g_cam_t, g_cam_o))
+        new = lambda *sh: torch.empty(*sh, device=world.device, dtype=torch.float32)
+        d_world, d_t0, d_o0, d_p0, d_j0 = new(S, B, 348), new(B, 3), new(B, 3), new(B, 63), new(B, 66)
+        d_R = new(B, 3, 3) if R is not None else None
+        d_t = new(B, 3) if R is not None else None
+        _ext.check(_ext.lib().humor_rollout_outputs_bwd(
+            B, S, _ext.ptr(world), _ext.ptr(trans0), _ext.ptr(orient0), _ext.ptr(R), _ext.ptr(g_trans), _ext.ptr(g_orient), _ext.ptr(g_pose),
+            _ext.ptr(g_joints), _ext.ptr(g_logits), _ext.ptr(g_cam_t), _ext.ptr(g_cam_o), _ext.ptr(d_world), _ext.ptr(d_t0), _ext.ptr(d_o0),
+            _ext.ptr(d_p0), _ext.ptr(d_j0), _ext.ptr(d_R), _ext.ptr(d_t), _ext.stream_ptr()), 'humor_rollout_outputs_bwd')
+        _ext.LaunchCounter.total += 1
+        return d_world, d_t0, d_o0, d_p0, d_j0, d_R, d_t, None
+
+
 class MotionOptimizer():
     """Fits SMPL shape and motion to an observation sequence (3 stages of L-BFGS)."""
 
@@ -102,6 +153,7 @@ class MotionOptimizer():
         self.use_cuda_graph = True       # falls back to eager launches (with a warning) if the closure cannot be captured
         self._graphs = {}
         self._contact_idx = torch.tensor(CONTACT_INDS, dtype=torch.long, device=device)
+        self._contact_idx32 = self._contact_idx.to(torch.int32)
 
     def set_precision(self, mode):
         """'tensor' (default) or 'exact' for the GEMM-shaped kernels of the motion prior and the body model
@@ -227,6 +279,27 @@ class MotionOptimizer():
         init_state = torch.cat([trans[:, 0], trans_vel[:, 0], R_all[:, :9], root_orient_vel[:, 0], R_all[:, 9:],
                                 joints.reshape(B, 66), joints_vel.reshape(B, 66)], 1)
         world, prior_out = self.motion_prior.roll_out_raw(init_state, latent_motion, return_prior)
+        if not return_vel:
+            # one kernel: matrix -> axis-angle of the 22 rotations, the frame-0 state in front, contact confidences / labels and the
+            # camera-frame root orientation / translation (apply_cam2prior inverse) - csrc/rot.cu, humor_rollout_outputs_*
+            res = _RolloutOutputs.apply(world, trans[:, 0], root_orient[:, 0], body_pose[:, 0], joints[:, 0].reshape(B, 66),
+                                        self.cam2prior_R if self.optim_floor else None,
+                                        self.cam2prior_t if self.optim_floor else None, self._contact_idx32)
+            out = {'trans': res[0], 'root_orient': res[1], 'pose_body': res[2], 'joints': res[3], 'contacts_logits': res[4],
+                   'contacts_conf': res[5], 'contacts': res[6]}
+            if return_prior:
+                out['prior_out'] = prior_out                                                  # (S,B,96) mean|logvar
+                out['cond_prior'] = (prior_out[..., :48].permute(1, 0, 2), torch.exp(prior_out[..., 48:]).permute(1, 0, 2))
+            cam = {'pose_body': out['pose_body']}
+            cam['trans'], cam['root_orient'] = (res[7], res[8]) if self.optim_floor else (out['trans'], out['root_orient'])
+            return out, cam
+        return self._rollout_outputs_torch(world, prior_out, trans, root_orient, body_pose, betas, joints, trans_vel, joints_vel,
+                                           root_orient_vel, return_prior, return_vel)
+
+    def _rollout_outputs_torch(self, world, prior_out, trans, root_orient, body_pose, betas, joints, trans_vel, joints_vel,
+                               root_orient_vel, return_prior, return_vel):
+        """The same in torch ops (round-1 form): the path with velocities (Stage-III initialisation) and the cross-check of the kernel."""
+        B, S = world.shape[1], world.shape[0]
         w = world.permute(1, 0, 2)                                                            # (B,S,348)
         rots = torch.cat([w[..., 6:15], w[..., 18:207]], -1).reshape(B * S * 22, 3, 3)
         aa = rotation_matrix_to_angle_axis(rots).reshape(B, S, 66)

@@ -204,6 +204,22 @@ int humor_cam2prior_bwd(int B, const float* floor_plane, const float* trans0, in
                         const float* joint0, int ld_j, const float* gR, const float* gt, const float* gh, float* d_floor,
                         float* d_trans0, float* d_orient0, float* d_joint0, hb_stream_t stream);
 
+/* Outputs of the latent roll-out in the layout the energies read: replaces the tensor shuffling of
+ * MotionOptimizer.rollout_latent_motion after roll_out (humor/fitting/motion_optimizer.py:964-1019: matrix -> axis-angle of the
+ * 22 rotations, concatenation with the frame-0 state, contact confidences / labels) and, when R / t are given, the camera-frame
+ * root orientation and translation of apply_cam2prior(inverse=True) (:678-741).  world [S][B][348] as humor_rollout_fwd wrote it;
+ * frame-0 state of every sub-sequence in the prior frame; outputs [B][T = S+1][.] except logits [B][S][9].
+ * Reverse: every g_* is nullable (zero); d_world is written completely (velocity columns carry no gradient). */
+int humor_rollout_outputs_fwd(int B, int S, const float* world, const float* trans0, const float* orient0, const float* pose0,
+                              const float* joints0, const float* R, const float* t, const int* contact_idx, float thresh,
+                              float* trans, float* orient, float* pose, float* joints, float* logits, float* conf, float* labels,
+                              float* cam_trans, float* cam_orient, hb_stream_t stream);
+int humor_rollout_outputs_bwd(int B, int S, const float* world, const float* trans0, const float* orient0, const float* R,
+                              const float* g_trans, const float* g_orient, const float* g_pose, const float* g_joints,
+                              const float* g_logits, const float* g_cam_trans, const float* g_cam_orient, float* d_world,
+                              float* d_trans0, float* d_orient0, float* d_pose0, float* d_joints0, float* d_R, float* d_t,
+                              hb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused Stage-III energies (humor/fitting/fitting_loss.py:94-309 motion_fit/smpl_fit/root_fit and
  * the per-term functions :317-484, :504-518) — loss terms and their gradients in one pass.

@@ -49,6 +49,8 @@ const std::map<std::string, Thunk>& registry() {
       {"hb::mat2aa_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::mat2aa_bwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(float*, 3))); }},
       {"hb::cam2prior_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::cam2prior_fwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(int, 3), A(cf, 4), A(int, 5), A(cf, 6), A(int, 7), A(float*, 8), A(float*, 9), A(float*, 10))); }},
       {"hb::cam2prior_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::cam2prior_bwd_kernel(A(int, 0), A(cf, 1), A(cf, 2), A(int, 3), A(cf, 4), A(int, 5), A(cf, 6), A(int, 7), A(cf, 8), A(cf, 9), A(cf, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
+      {"hb::rollout_outputs_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rollout_outputs_fwd_kernel(A(hb_emu::RollOut, 0))); }},
+      {"hb::rollout_outputs_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rollout_outputs_bwd_kernel(A(hb_emu::RollOutBwd, 0))); }},
       {"hb::fit_losses_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_losses_kernel(A(HbFitArgs, 0))); }},
       {"hb::fit_reduce1_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce1_kernel(A(HbFitArgs, 0))); }},
       {"hb::fit_reduce_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce_kernel(A(HbFitArgs, 0))); }},

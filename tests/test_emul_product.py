@@ -169,6 +169,17 @@ def test_cam2prior_kernel_pair_matches_the_torch_form(emul):
     assert out['parsed_plane_vs_kernel'] < 5e-6
 
 
+def test_rollout_outputs_kernel_pair_matches_the_torch_form(emul):
+    """humor_rollout_outputs_fwd / _bwd (world rows + frame-0 state -> the (B,T,.) tensors of the energies, prior and camera frame; one
+    launch each way) against MotionOptimizer._rollout_outputs_torch with autograd: values identical (same device functions, same
+    order), gradients to rounding; without a camera frame R / t receive no gradient."""
+    out = run_probe(emul, 'probe_rollout_outputs.py')
+    for tag in ('cam', 'nocam'):
+        assert max(out[tag + '_fwd'].values()) < 1e-6, out[tag + '_fwd']
+        assert max(v for v in out[tag + '_bwd_rel'].values() if v is not None) < 1e-5, out[tag + '_bwd_rel']
+        assert out[tag + '_unused_grads_none']
+
+
 def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
     """humor_lbs_fwd's tensor-core path on the emulated tcgen05 kernels: the library's own dispatch AND its own TMA-descriptor
     code (cuTensorMapEncodeTiled is emulated) for the two-kernel form (1, 1) and the fused blend + group-skinning kernel on 3xTF32

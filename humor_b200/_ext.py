@@ -105,7 +105,7 @@ EXPORTS = ['humor_lbs_workspace_bytes', 'humor_lbs_fwd', 'humor_lbs_bwd', 'humor
            'humor_rollout_fwd', 'humor_rollout_bwd', 'humor_rodrigues_fwd', 'humor_rodrigues_bwd',
            'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version',
            'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd', 'humor_lbs_configure', 'humor_lbs_forms_used',
-           'humor_umma_gemm16', 'humor_umma_gemm16_workspace_bytes', 'humor_chain_debug', 'humor_cam2prior_fwd', 'humor_cam2prior_bwd', 'humor_rollout_outputs_fwd', 'humor_rollout_outputs_bwd']
+           'humor_umma_gemm16', 'humor_umma_gemm16_workspace_bytes', 'humor_chain_debug', 'humor_cam2prior_fwd', 'humor_cam2prior_bwd', 'humor_rollout_outputs_fwd', 'humor_rollout_outputs_bwd', 'humor_gmm_workspace_bytes', 'humor_gmm_nll_ws']
 
 _LIB = None
 
@@ -151,6 +151,10 @@ def lib():
     L.humor_fit_losses.argtypes = [C.POINTER(HbFitArgs), i64p, vp]
     L.humor_gmm_nll.restype = ci
     L.humor_gmm_nll.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.humor_gmm_workspace_bytes.restype = sz
+    L.humor_gmm_workspace_bytes.argtypes = [ci, ci, ci]
+    L.humor_gmm_nll_ws.restype = ci
+    L.humor_gmm_nll_ws.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.humor_umma_gemm_workspace_bytes.restype = sz
     L.humor_umma_gemm_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.humor_umma_gemm.restype = ci

@@ -82,10 +82,15 @@ class _GmmFn(torch.autograd.Function):
         B, D = x.shape
         nll = torch.empty(B, device=x.device, dtype=torch.float32)
         dx = torch.empty_like(x)
-        _ext.check(_ext.lib().humor_gmm_nll(B, D, gmm['K'], _ext.ptr(x), _ext.ptr(gmm['logw']), _ext.ptr(gmm['mean']),
-                                            _ext.ptr(gmm['Linv']), _ext.ptr(gmm['logdet']), _ext.ptr(nll), _ext.ptr(dx),
-                                            _ext.stream_ptr()), 'humor_gmm_nll')
-        _ext.LaunchCounter.total += 1
+        L = _ext.lib()
+        ws = gmm.get('_ws')
+        if ws is None or ws[0] != (B, D):                      # scratch of the three-launch form, kept with the constants
+            ws = ((B, D), torch.empty(L.humor_gmm_workspace_bytes(B, D, gmm['K']) // 4, device=x.device, dtype=torch.float32))
+            gmm['_ws'] = ws
+        _ext.check(L.humor_gmm_nll_ws(B, D, gmm['K'], _ext.ptr(x), _ext.ptr(gmm['logw']), _ext.ptr(gmm['mean']), _ext.ptr(gmm['Linv']),
+                                      _ext.ptr(gmm['logdet']), _ext.ptr(nll), _ext.ptr(dx), _ext.ptr(ws[1]), ws[1].numel() * 4,
+                                      _ext.stream_ptr()), 'humor_gmm_nll_ws')
+        _ext.LaunchCounter.total += 3
         ctx.dx = dx
         return nll
 

@@ -278,6 +278,11 @@ int humor_fit_losses(const HbFitArgs* a, int64_t* launches, hb_stream_t stream);
  *   -> nll [B] and d_x [B][D] = d(sum nll)/dx.  D <= 160, K <= 32. */
 int humor_gmm_nll(int B, int D, int K, const float* x, const float* logw, const float* mean,
                   const float* Linv, const float* logdet, float* nll, float* d_x, hb_stream_t stream);
+/* The same with caller-owned scratch (humor_gmm_workspace_bytes): three launches over (component, 32-row chunk) blocks that stage
+ * every Linv_k once per chunk instead of once per pair of rows - what the Stage-III closure calls. */
+size_t humor_gmm_workspace_bytes(int B, int D, int K);
+int humor_gmm_nll_ws(int B, int D, int K, const float* x, const float* logw, const float* mean, const float* Linv,
+                     const float* logdet, float* nll, float* d_x, float* workspace, size_t workspace_bytes, hb_stream_t stream);
 
 /* C = A[M,K] * B[N,K]^T (+bias) at fp32-level accuracy on the 5th-gen tensor cores (tcgen05, 3xTF32 operand split,
  * TMA-staged tiles).  K % 32 == 0, leading dimensions % 4 == 0.  The building block of the batched prior MLP. */

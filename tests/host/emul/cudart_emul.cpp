@@ -55,6 +55,9 @@ const std::map<std::string, Thunk>& registry() {
       {"hb::fit_reduce1_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce1_kernel(A(HbFitArgs, 0))); }},
       {"hb::fit_reduce_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::fit_reduce_kernel(A(HbFitArgs, 0))); }},
       {"hb::gmm_nll_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::gmm_nll_kernel(A(int, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(float*, 8), A(float*, 9))); }},
+      {"hb::gmm_pass1_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::gmm_pass1_kernel(A(int, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(float*, 8), A(float*, 9))); }},
+      {"hb::gmm_pass2_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::gmm_pass2_kernel(A(int, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(float*, 6))); }},
+      {"hb::gmm_reduce_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::gmm_reduce_kernel(A(int, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(float*, 5), A(float*, 6))); }},
       {"hb::rollout_init_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rollout_init_kernel(A(int, 0), A(int, 1), A(cf, 2), A(cf, 3), A(float*, 4), A(float*, 5), A(float*, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(float*, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
       {"hb::glue_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::glue_fwd_kernel(A(int, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(float*, 8), A(float*, 9), A(float*, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14), A(float*, 15), A(float*, 16), A(float*, 17), A(float*, 18))); }},
       {"hb::glue_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::glue_bwd_kernel(A(int, 0), A(int, 1), A(int, 2), A(int, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(cf, 8), A(cf, 9), A(cf, 10), A(cf, 11), A(cf, 12), A(cf, 13), A(cf, 14), A(cf, 15), A(cf, 16), A(float*, 17), A(float*, 18), A(cf, 19), A(float*, 20), A(float*, 21), A(float*, 22), A(float*, 23), A(float*, 24), A(float*, 25))); }},

@@ -610,13 +610,38 @@ lbs_skin_bwd_kernel(HbLbsModel m, int N, const float* __restrict__ feat, const f
     }
     // ---- phase 2b: d feat[f][k] += sum_vc GP[f][vc] * blend_t[vc][k]   thread = k
     if (tid < LBS_KF) {
-      for (int i = 0; i < cn; ++i) {
-        const int v2 = (c0 + i) < nv1 ? (vlist ? vlist[c0 + i] : c0 + i) : vlist2[c0 + i - nv1];
+      const bool tab2 = m.sel_blend && vlist == m.sel_ids && nv1 == m.sel_nv && (nv1 == nv || vlist2 == m.extra_ids) && c0 == 0;
+      if (tab2) {
+        // packed columns: feature row tid of sel_blend holds the 3 * cn values of this chunk contiguously, in GP's own order;
+        // 16 of them are fetched before the first is used (one dependent L2 round trip per (vertex, coordinate) otherwise)
+        const float4* rowp = reinterpret_cast<const float4*>(m.sel_blend + (size_t)tid * LBS_SEL_LD);
+        const int ne = cn * 3;
+        for (int e0 = 0; e0 < ne; e0 += 16) {
+          float4 q4[4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float bt = __ldg(m.blend_t + ((size_t)v2 * 3 + c) * LBS_KF + tid);
+          for (int u = 0; u < 4; ++u) q4[u] = (e0 + 4 * u < ne) ? __ldg(rowp + (e0 >> 2) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int f = 0; f < BW_FT; ++f) accF[f] = fmaf(GP[f * 192 + i * 3 + c], bt, accF[f]);
+          for (int u = 0; u < 4; ++u) {
+            const float bv[4] = {q4[u].x, q4[u].y, q4[u].z, q4[u].w};
+#pragma unroll
+            for (int z = 0; z < 4; ++z) {
+              const int e = e0 + 4 * u + z;
+              if (e < ne) {
+#pragma unroll
+                for (int f = 0; f < BW_FT; ++f) accF[f] = fmaf(GP[f * 192 + e], bv[z], accF[f]);
+              }
+            }
+          }
+        }
+      } else {
+        for (int i = 0; i < cn; ++i) {
+          const int v2 = (c0 + i) < nv1 ? (vlist ? vlist[c0 + i] : c0 + i) : vlist2[c0 + i - nv1];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float bt = __ldg(m.blend_t + ((size_t)v2 * 3 + c) * LBS_KF + tid);
+#pragma unroll
+            for (int f = 0; f < BW_FT; ++f) accF[f] = fmaf(GP[f * 192 + i * 3 + c], bt, accF[f]);
+          }
         }
       }
     } else if (tid < LBS_KF + BW_FT * 3) {

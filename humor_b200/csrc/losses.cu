@@ -477,6 +477,31 @@ __global__ void __launch_bounds__(256) gmm_nll_kernel(int B, int D, int K, const
 // ------------------------------------------------------------------------------------------------
 constexpr int GMB_ROWS = 32;
 static inline size_t gmb_smem_bytes(int D) { return ((size_t)D * (D + 1) + (size_t)GMB_ROWS * D) * sizeof(float); }
+// Linv_k [D][D] -> shared memory rows of LD floats.  Four 16-byte loads in flight per thread: one element per iteration left every
+// load's ~1 us of latency exposed (75 dependent round trips per block: 0.10 ms of the first pass, profiles/r02r_profile_step.txt).
+__device__ __forceinline__ void gmb_stage_factor(const float* __restrict__ L, float* Ls, int D, int LD, int tid) {
+  const int n = D * D;
+  if ((n & 3) == 0) {
+    const float4* L4 = reinterpret_cast<const float4*>(L);
+    const int n4 = n >> 2;
+    for (int i0 = tid; i0 < n4; i0 += 4 * 256) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i4 = i0 + u * 256; v[u] = i4 < n4 ? __ldg(L4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i4 = i0 + u * 256;
+        if (i4 < n4) {
+          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const int idx = 4 * i4 + q, r = idx / D; Ls[r * LD + (idx - r * D)] = e[q]; }
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < n; i += 256) { const int r = i / D; Ls[r * LD + (i - r * D)] = L[i]; }
+  }
+}
 __global__ void __launch_bounds__(256) gmm_pass1_kernel(int B, int D, int K, const float* __restrict__ x, const float* __restrict__ logw,
                                                          const float* __restrict__ mean, const float* __restrict__ Linv,
                                                          const float* __restrict__ logdet, float* __restrict__ y, float* __restrict__ lp) {
@@ -486,8 +511,7 @@ __global__ void __launch_bounds__(256) gmm_pass1_kernel(int B, int D, int K, con
   float* ds = Ls + (size_t)D * LD;                  // [GMB_ROWS][D]  x - mu_k
   const int k = blockIdx.x, b0 = blockIdx.y * GMB_ROWS, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int nr = min(GMB_ROWS, B - b0);
-  const float* L = Linv + (size_t)k * D * D;
-  for (int i = tid; i < D * D; i += 256) { const int r = i / D; Ls[r * LD + (i - r * D)] = L[i]; }
+  gmb_stage_factor(Linv + (size_t)k * D * D, Ls, D, LD, tid);
   const float* mu = mean + (size_t)k * D;
   for (int i = tid; i < GMB_ROWS * D; i += 256) { const int r = i / D, c = i - r * D; ds[i] = r < nr ? x[(size_t)(b0 + r) * D + c] - mu[c] : 0.f; }
   __syncthreads();
@@ -521,8 +545,7 @@ __global__ void __launch_bounds__(256) gmm_pass2_kernel(int B, int D, int K, con
   __shared__ float resp[GMB_ROWS];
   const int k = blockIdx.x, b0 = blockIdx.y * GMB_ROWS, tid = threadIdx.x;
   const int nr = min(GMB_ROWS, B - b0);
-  const float* L = Linv + (size_t)k * D * D;
-  for (int i = tid; i < D * D; i += 256) { const int r = i / D; Ls[r * LD + (i - r * D)] = L[i]; }
+  gmb_stage_factor(Linv + (size_t)k * D * D, Ls, D, LD, tid);
   if (tid < nr) {                                   // responsibility of component k for every row of the chunk
     const float* l = lp + (size_t)(b0 + tid) * K;
     float mx = -INFINITY;

@@ -201,7 +201,9 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
   else { ta16 = ta16l = ta_hi; tb16 = tb16l = tb_hi; }
   const int ntiles = a.nrt * a.nct;
   int grid = ntiles < sms ? ntiles : sms;
-  if (want > 0 && want < grid) grid = want;
+  // HB_LBS_FUSEG_CTAS: fewer CTAs leave SMs to kernels of other streams; MORE CTAs than SMs (each walks a shorter chunk of the tile
+  // list and retires) let the hardware scheduler slot the pass into whatever SMs the main stream's kernels leave idle
+  if (want > 0) grid = want < ntiles ? want : ntiles;
   lbs_fuseg_kernel<<<grid, FG_THREADS, FG_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16, ta16l, tb16l, K, a);
   return cudaGetLastError();
 }

@@ -306,6 +306,23 @@ class _LbsFn(torch.autograd.Function):
         return None, d_ro, d_pb, d_betas, d_tr, None, None, None, None, None
 
 
+def lbs_dense_into(model, root_orient, pose_body, betas, trans, frames_per_beta, out):
+    """Dense vertices of N frames, gradient-free, into the caller's (N, V, 3) tensor on the current stream (the pass a caller queues
+    on a second stream, MotionOptimizer._launch_deferred_dense)."""
+    if betas.shape[1] < 16:
+        betas = torch.nn.functional.pad(betas, (0, 16 - betas.shape[1]))
+    ro, pb, be, tr = (_ext.f32c(x) for x in (root_orient, pose_body, betas, trans))
+    N = ro.shape[0]
+    ws = model.workspace(N)
+    joints = torch.empty(N, 52, 3, device=ro.device, dtype=torch.float32)
+    nl = C.c_int64(0)
+    _ext.check(_ext.lib().humor_lbs_fwd(C.byref(model.struct), N, frames_per_beta, _ext.ptr(ro), _ext.ptr(pb), _ext.ptr(be), _ext.ptr(tr),
+                                        _ext.ptr(ws), ws.numel() * 4, None, 0, _ext.ptr(out), _ext.ptr(joints), 52, C.byref(nl),
+                                        _ext.stream_ptr()), 'humor_lbs_fwd')
+    _ext.LaunchCounter.total += nl.value
+    return out
+
+
 def lbs(model, root_orient, pose_body, betas, trans, frames_per_beta=1, sel_ids=None, want_dense=True,
         dense_grad=True, num_joints_out=52):
     if betas.shape[1] < 16:

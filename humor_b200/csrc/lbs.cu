@@ -736,6 +736,12 @@ extern "C" int humor_lbs_configure(int skin_form, int blend_form, int slab_frame
   return HB_OK;
 }
 
+extern "C" int humor_lbs_set_fuseg_ctas(int n) {
+  if (n < 0) return HB_ERR_ARG;
+  lbs_set_fuseg_ctas(n);
+  return HB_OK;
+}
+
 extern "C" int humor_lbs_forms_used(int* skin_form, int* blend_form) {
   if (skin_form) *skin_form = g_used_skin;
   if (blend_form) *blend_form = g_used_blend;

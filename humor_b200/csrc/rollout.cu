@@ -501,6 +501,17 @@ extern "C" int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const fl
   return HB_OK;
 }
 
+// Event recorded on the caller's stream right before the reverse decoder chain is launched: work without a consumer inside the
+// closure (the dense, gradient-free LBS pass) is queued behind it on another stream and fills the SMs the latency-bound chain leaves
+// idle (20 of 148 at 32 clusters x 4 CTAs) instead of holding the whole chip for 1 ms in the middle of the forward pass.
+static cudaEvent_t g_chain_bwd_event = nullptr;
+static bool g_chain_bwd_recorded = false;
+extern "C" int humor_rollout_bwd_started_wait(cudaStream_t side) {
+  if (!g_chain_bwd_event || !g_chain_bwd_recorded) return HB_ERR_ARG;
+  HB_CUDA(cudaStreamWaitEvent(side, g_chain_bwd_event, 0));
+  return HB_OK;
+}
+
 extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* workspace, size_t workspace_bytes,
                                  const float* d_world, const float* d_prior_out, float* d_init, float* d_z,
                                  int64_t* launches, cudaStream_t st) {
@@ -544,6 +555,9 @@ extern "C" int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* w
   }
   const int gb = cdiv(B, GLUE_WARPS);
   float* dGbuf[2] = {tp.dG0, tp.dG1};
+  if (!g_chain_bwd_event) HB_CUDA(cudaEventCreateWithFlags(&g_chain_bwd_event, cudaEventDisableTiming));
+  HB_CUDA(cudaEventRecord(g_chain_bwd_event, st));
+  g_chain_bwd_recorded = true;
   if (tc && chain_ok(w, B)) {
     // all S reverse steps in ONE launch, then d z of every step as one batched GEMM over the operand planes it left
     HB_CUDA(chain_backward(w, tp, B, S, d_world, st));

@@ -161,6 +161,8 @@ cudaError_t launch_umma_gemm3_bn(const float* A_hi, const float* A_lo, int lda, 
   return cudaErrorInvalidValue;
 }
 
+static int g_fuseg_ctas = 0;
+void lbs_set_fuseg_ctas(int n) { g_fuseg_ctas = n > 0 ? n : 0; }
 // skin form 3: blend + group skinning in one persistent kernel (lbs_fuseg.cuh).  `a` arrives with the model tables, A, trans,
 // out, N, num_verts, num_groups filled in; tile counts are set here.
 cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
@@ -204,6 +206,7 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
   // HB_LBS_FUSEG_CTAS: fewer CTAs leave SMs to kernels of other streams; MORE CTAs than SMs (each walks a shorter chunk of the tile
   // list and retires) let the hardware scheduler slot the pass into whatever SMs the main stream's kernels leave idle
   if (want > 0) grid = want < ntiles ? want : ntiles;
+  if (g_fuseg_ctas > 0) grid = g_fuseg_ctas < ntiles ? g_fuseg_ctas : ntiles;      // per-call override (lbs_set_fuseg_ctas)
   lbs_fuseg_kernel<<<grid, FG_THREADS, FG_SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16, ta16l, tb16l, K, a);
   return cudaGetLastError();
 }

@@ -48,6 +48,8 @@ struct LbsFusegArgs {
 cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
                              int b_rows, int K, const void* feat16, const void* bt16, const void* feat16l, const void* bt16l, int ld16,
                              LbsFusegArgs a, cudaStream_t st);
+// CTAs of the next lbs_fuseg launches (0: one per SM); > SMs = shorter chunks that the scheduler slots next to other streams' kernels
+void lbs_set_fuseg_ctas(int n);
 // fp16 plane(s) of the feature columns [c0, c0 + 64 * nkb16) of feat[N][ldf] (columns >= ncols read as zero): out = fp16(x),
 // out_lo (nullable) = fp16(x - out)
 cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, void* out_lo, cudaStream_t st);

@@ -146,6 +146,11 @@ class PackedWeights:
         return ws
 
 
+# callables run right after the reverse roll-out's kernels were queued (MotionOptimizer queues its gradient-free dense LBS pass behind
+# the reverse decoder chain there); each is called once and removed
+AFTER_ROLLOUT_BWD = []
+
+
 class _RolloutFn(torch.autograd.Function):
     """(init_state (B,339), z_seq (B,S,48)) -> (world (S,B,348), prior_out (S,B,96))."""
 
@@ -190,6 +195,8 @@ class _RolloutFn(torch.autograd.Function):
                                                 _ext.ptr(dp), _ext.ptr(d_init), _ext.ptr(d_z), C.byref(nl),
                                                 _ext.stream_ptr()), 'humor_rollout_bwd')
         _ext.LaunchCounter.total += nl.value
+        while AFTER_ROLLOUT_BWD:
+            AFTER_ROLLOUT_BWD.pop(0)()
         return None, d_init, d_z, None
 
 

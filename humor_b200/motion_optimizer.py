@@ -144,6 +144,12 @@ class MotionOptimizer():
         self._capture_stream = None
         self._dense_pending = False
         self._defer_dense_join = False
+        # the gradient-free dense LBS pass of a closure evaluation is queued BEHIND the launch of the reverse decoder chain (which
+        # occupies 128 of 148 SMs for 3 ms without loading them) in short CTAs that fill the idle SMs; HB_DENSE_EARLY=1: right after
+        # the roll-out as in round 1
+        import os
+        self.dense_under_reverse_chain = os.environ.get('HB_DENSE_EARLY') is None
+        self._dense_deferred = None
         # multi-GPU: this process owns a contiguous block of the sub-sequences; the overlap energies that couple
         # the last sequence of rank r with the first of rank r+1 are exchanged as small halos (parallel.py)
         self.shard = None
@@ -199,6 +205,15 @@ class MotionOptimizer():
         if self._dense_stream is None:
             self._dense_stream = torch.cuda.Stream(device=trans.device)
         side = self._dense_stream
+        if self._defer_dense_join and self.dense_under_reverse_chain and beta.requires_grad and torch.is_grad_enabled():
+            # a reverse pass follows: allocate the output now, queue the kernels when the reverse roll-out has been launched
+            from . import humor_model
+            v = torch.empty(B * T, model.struct.num_verts, 3, device=trans.device, dtype=torch.float32)
+            self._dense_deferred = (v, root_orient.detach().reshape(B * T, 3), body_pose.detach().reshape(B * T, 63), beta.detach(),
+                                    trans.detach().reshape(B * T, 3), T)
+            humor_model.AFTER_ROLLOUT_BWD.append(self._launch_deferred_dense)
+            self._dense_pending = True
+            return v
         side.wait_stream(main)
         with torch.cuda.stream(side), torch.no_grad():
             model.ws_slot = 1
@@ -215,7 +230,39 @@ class MotionOptimizer():
             self.join_dense()
         return v
 
+    def _launch_deferred_dense(self, after_reverse_chain_launch=True):
+        """Queue the deferred dense pass on the side stream: behind the point where the reverse decoder chain was launched (called from
+        humor_model.AFTER_ROLLOUT_BWD), or - no reverse pass came - behind everything queued so far."""
+        if self._dense_deferred is None:
+            return
+        from . import _ext, humor_model
+        from .body_model import lbs_dense_into
+        v, ro, pb, be, tr, T = self._dense_deferred
+        self._dense_deferred = None
+        if self._launch_deferred_dense in humor_model.AFTER_ROLLOUT_BWD:
+            humor_model.AFTER_ROLLOUT_BWD.remove(self._launch_deferred_dense)
+        model = self.body_model.lbs_model
+        side = self._dense_stream
+        L = _ext.lib()
+        if after_reverse_chain_launch:
+            _ext.check(L.humor_rollout_bwd_started_wait(_ext.C.c_void_p(side.cuda_stream)), 'humor_rollout_bwd_started_wait')
+        else:
+            side.wait_stream(torch.cuda.current_stream())
+        sms = torch.cuda.get_device_properties(v.device).multi_processor_count if v.is_cuda else 148
+        with torch.cuda.stream(side), torch.no_grad():
+            model.ws_slot = 1
+            L.humor_lbs_set_fuseg_ctas(8 * sms if after_reverse_chain_launch else 0)
+            try:
+                lbs_dense_into(model, ro, pb, be, tr, T, v)
+            finally:
+                L.humor_lbs_set_fuseg_ctas(0)
+                model.ws_slot = 0
+        if not torch.cuda.is_current_stream_capturing():
+            v.record_stream(side)
+
     def join_dense(self):
+        if self._dense_deferred is not None:           # no reverse roll-out was launched after the forward: queue the pass now
+            self._launch_deferred_dense(after_reverse_chain_launch=False)
         if self._dense_pending:
             torch.cuda.current_stream().wait_stream(self._dense_stream)
             self._dense_pending = False

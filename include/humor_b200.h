@@ -111,6 +111,9 @@ int humor_lbs_configure(int skin_form, int blend_form, int slab_frames);
 /* The forms the most recent dense tensor-core call actually ran (a requested form falls back to form 1 when the model's
  * layout does not allow it); 0 before the first such call. */
 int humor_lbs_forms_used(int* skin_form, int* blend_form);
+/* CTAs of the fused dense forward from now on (0 = one persistent CTA per SM, the default).  More CTAs than SMs = shorter chunks of
+ * the tile list per CTA: a pass queued on a second stream then fills the SMs other kernels leave idle instead of holding the chip. */
+int humor_lbs_set_fuseg_ctas(int n);
 /* Reverse mode of the above (what autograd does through smplx in the reference).  d_verts follows the
  * same vlist convention; d_betas is per frame [N][16] (the caller reduces over frames_per_beta). */
 int humor_lbs_bwd(const HbLbsModel* m, int N, int frames_per_beta, const float* root_orient,
@@ -178,6 +181,9 @@ int humor_rollout_fwd(const HbHumorWeights* w, int B, int S, const float* init_s
 /* Diagnostics of the persistent decoder chain (csrc/chain_persist.cuh): when `buf` (device, >= S*5*16 int64) is set, the next
  * rollout launches record clock64 stamps of CTA 0 per step and phase (tools/chain_timeline.py); NULL switches it off. */
 int humor_chain_debug(void* buf, size_t bytes);
+/* Makes `side` wait for the point of the most recent humor_rollout_bwd right before its reverse decoder chain was launched
+ * (cudaStreamWaitEvent on an event the library records there; capturable).  HB_ERR_ARG before the first humor_rollout_bwd. */
+int humor_rollout_bwd_started_wait(hb_stream_t side);
 /* BPTT through the rollout: d_world [S][B][348], d_prior_out [S][B][96] (nullable) ->
  * d_init [B][339], d_z [B][S][48].  Must follow humor_rollout_fwd on the same workspace. */
 int humor_rollout_bwd(const HbHumorWeights* w, int B, int S, float* workspace, size_t workspace_bytes,

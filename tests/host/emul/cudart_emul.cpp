@@ -165,6 +165,10 @@ int cudaOccupancyMaxActiveClusters(int* n, const void*, const void*) { *n = tcem
 int cudaGetDevice(int* d) { *d = 0; return 0; }
 int cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return 0; }
 int cudaMemsetAsync(void* p, int v, size_t n, void*) { std::memset(p, v, n); return 0; }
+// events: execution is synchronous and in program order, so ordering primitives have nothing to do
+int cudaEventCreateWithFlags(void** e, unsigned) { static int dummy; *e = &dummy; return 0; }
+int cudaEventRecord(void*, void*) { return 0; }
+int cudaStreamWaitEvent(void*, void*, unsigned) { return 0; }
 // cuTensorMapEncodeTiled: 2-D fp32 maps only; the emulated description is stored in the caller's (128-byte) CUtensorMap
 static int emul_encode_tiled(void* m, int dtype, unsigned rank, void* base, const unsigned long long* gdim, const unsigned long long* gstr,
                              const unsigned* box, const unsigned*, int, int swizzle, int, int) {

@@ -19,6 +19,9 @@ cudaError_t cudaLaunchKernel(const void* f, dim3 g, dim3 b, void** a, size_t sm,
 struct cudaLaunchConfig_t { dim3 gridDim; dim3 blockDim; size_t dynamicSmemBytes; void* stream; void* attrs; unsigned numAttrs; };
 cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* c, const void* f, void** a) { report(f, c->gridDim, c->blockDim, c->dynamicSmemBytes); return 0; }
 cudaError_t cudaGetLastError() { return 0; }
+cudaError_t cudaEventCreateWithFlags(void** e, unsigned) { static int dummy; *e = &dummy; return 0; }
+cudaError_t cudaEventRecord(void*, void*) { return 0; }
+cudaError_t cudaStreamWaitEvent(void*, void*, unsigned) { return 0; }
 cudaError_t cudaPeekAtLastError() { return 0; }
 cudaError_t cudaFuncSetAttribute(const void*, int, int) { return 0; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }

@@ -165,3 +165,62 @@ def test_cuda_graph_step_matches_eager():
     assert abs(l_g2 - l_e2) <= 1e-6 * abs(l_e2) and abs(l_g2 - l_g) > 1e-3
     for a, p in zip(g_g2, params):
         assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-6 * float(a.abs().max()))
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_dense_vertices_queued_behind_the_reverse_chain_are_the_same_vertices(graph):
+    """The gradient-free dense LBS pass of a closure evaluation is queued on the side stream behind the launch of the reverse decoder
+    chain (short CTAs on the SMs the chain leaves idle).  What it writes must be what the immediate pass writes and
+    the loss must not change - eagerly and inside the captured graph - and a forward without a reverse pass must still get its
+    vertices (join_dense queues the pass itself)."""
+    B, T = 128, 12                                              # >= 128 frames: the tensor-core dense path
+    prob = synth.make_stage3_problem(B, T, seed=9, overlap=3, cam=True)
+    mo = U.build_product(B, T, synth.RGB_STAGE3_WEIGHTS, True, prob)
+    names = mo.set_stage3_state(prob['params'])
+    params = [getattr(mo, n) for n in names]
+    obs = {k: U.obs_to(v, mo.device) for k, v in prob['obs'].items() if k in U.obs_keys(True, prob)}
+    mo.use_cuda_graph = False
+    loss0, _, _, _, cam_pred0 = mo.stage3_forward(obs, None, 1.0)           # immediate placement
+    mo.join_dense()
+    torch.cuda.synchronize()
+    v0 = cam_pred0['points3d'].clone()
+    stash, seen = {}, []
+    orig = mo.stage3_forward
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        stash['v'] = out[4]['points3d']
+        seen.append(mo._dense_deferred is not None)             # still un-queued when the forward returns
+        return out
+
+    mo.stage3_forward = spy
+    if not graph:
+        loss1, _, _ = mo._eval_on_aliases(obs, None, 1.0, params)
+    else:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            mo._eval_on_aliases(obs, None, 1.0, params)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss1, _, _ = mo._eval_on_aliases(obs, None, 1.0, params)
+        stash['v'].zero_()
+        g.replay()
+    torch.cuda.synchronize()
+    assert all(seen) and mo._dense_deferred is None
+    v1 = stash['v']
+    assert torch.isfinite(v1).all() and torch.equal(v1.reshape(v0.shape), v0)
+    assert abs(float(loss1) - float(loss0)) <= 1e-6 * abs(float(loss0))
+    # a forward with no reverse pass behind it
+    mo.stage3_forward = orig
+    mo._defer_dense_join = True
+    try:
+        _, _, _, _, cam_pred2 = mo.stage3_forward(obs, None, 1.0)
+        assert mo._dense_deferred is not None
+    finally:
+        mo._defer_dense_join = False
+        mo.join_dense()
+    torch.cuda.synchronize()
+    assert torch.equal(cam_pred2['points3d'], v0)

@@ -208,7 +208,8 @@ class MotionOptimizer():
         if self._defer_dense_join and self.dense_under_reverse_chain and beta.requires_grad and torch.is_grad_enabled():
             # a reverse pass follows: allocate the output now, queue the kernels when the reverse roll-out has been launched
             from . import humor_model
-            v = torch.empty(B * T, model.struct.num_verts, 3, device=trans.device, dtype=torch.float32)
+            with torch.cuda.stream(side):            # the side stream's allocator pool: its blocks are only ever written there
+                v = torch.empty(B * T, model.struct.num_verts, 3, device=trans.device, dtype=torch.float32)
             self._dense_deferred = (v, root_orient.detach().reshape(B * T, 3), body_pose.detach().reshape(B * T, 63), beta.detach(),
                                     trans.detach().reshape(B * T, 3), T)
             humor_model.AFTER_ROLLOUT_BWD.append(self._launch_deferred_dense)
@@ -258,7 +259,7 @@ class MotionOptimizer():
                 L.humor_lbs_set_fuseg_ctas(0)
                 model.ws_slot = 0
         if not torch.cuda.is_current_stream_capturing():
-            v.record_stream(side)
+            v.record_stream(torch.cuda.current_stream())      # read on the caller's stream after join_dense
 
     def join_dense(self):
         if self._dense_deferred is not None:           # no reverse roll-out was launched after the forward: queue the pass now

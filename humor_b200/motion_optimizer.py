@@ -208,6 +208,7 @@ class MotionOptimizer():
         if self._defer_dense_join and self.dense_under_reverse_chain and beta.requires_grad and torch.is_grad_enabled():
             # a reverse pass follows: allocate the output now, queue the kernels when the reverse roll-out has been launched
             from . import humor_model
+            side.wait_stream(main)                   # (inside a capture: the side stream joins it, so the block below is graph-private)
             with torch.cuda.stream(side):            # the side stream's allocator pool: its blocks are only ever written there
                 v = torch.empty(B * T, model.struct.num_verts, 3, device=trans.device, dtype=torch.float32)
             self._dense_deferred = (v, root_orient.detach().reshape(B * T, 3), body_pose.detach().reshape(B * T, 63), beta.detach(),

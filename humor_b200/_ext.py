@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
 
 
 class HbLbsModel(C.Structure):
-    _fields_ = [('num_verts', C.c_int), ('v3_ld', C.c_int), ('wk', C.c_int), ('reserved', C.c_int),
+    _fields_ = [('num_verts', C.c_int), ('v3_ld', C.c_int), ('wk', C.c_int), ('flags', C.c_int),
                 ('v_template', C.c_void_p), ('blend', C.c_void_p), ('blend_t', C.c_void_p),
                 ('j_template', C.c_void_p), ('j_dirs', C.c_void_p), ('w_idx', C.c_void_p),
                 ('w_val', C.c_void_p), ('parents', C.c_void_p), ('extra_ids', C.c_void_p),
@@ -71,7 +71,8 @@ class HbLbsModel(C.Structure):
                 ('g_start', C.c_void_p), ('g_joint', C.c_void_p), ('g_w', C.c_void_p), ('num_groups', C.c_int),
                 ('ft_nct', C.c_int), ('g_slot', C.c_void_p), ('ft_tab', C.c_void_p),
                 ('blend16a_h', C.c_void_p), ('blend16a_l', C.c_void_p),
-                ('sel_ids', C.c_void_p), ('sel_blend', C.c_void_p), ('sel_nv', C.c_int), ('reserved2', C.c_int)]
+                ('sel_ids', C.c_void_p), ('sel_blend', C.c_void_p), ('sel_nv', C.c_int), ('ft_rec_stride', C.c_int),
+                ('ft_rec', C.c_void_p)]
 
 
 class HbHumorWeights(C.Structure):

@@ -91,9 +91,11 @@ def pack_smplh(asset, num_betas=16):
     g_joint = np.asarray(g_joint, np.int32)
     g_w = np.stack(g_w, 0) if g_w else np.zeros((1, G), np.float32)
     g_slot, ft_tab = fuseg_tables(g_start, g_joint, ng)
+    ft_rec = fuseg_records(g_start, g_joint, g_slot, g_w, ng, ft_tab)
     return {
         'g_start': g_start, 'g_joint': g_joint, 'g_w': np.ascontiguousarray(g_w), 'num_groups': ng,
-        'g_slot': g_slot, 'ft_tab': ft_tab, 'ft_nct': ft_tab.shape[0],
+        'g_slot': g_slot, 'ft_tab': ft_tab, 'ft_nct': ft_tab.shape[0], 'ft_rec': ft_rec,
+        'w_rows_sum_to_one': bool(np.abs(Wf.astype(np.float64).sum(1) - 1.0).max() < 1e-6),
         'depth': depth, 'child_start': child_start, 'child_list': child_list, 'max_depth': int(depth.max()),
         'num_verts': V, 'v3_ld': v3_ld, 'wk': wk,
         'v_template': vt.astype(np.float32).reshape(-1), 'blend': blend,
@@ -106,6 +108,10 @@ def pack_smplh(asset, num_betas=16):
 FG_NSLOT = 12          # csrc/lbs_fuseg.cuh: shared-memory slots for skinning transforms, [128 frames][12 floats] each
 FG_GPT = 8             # vertex groups per 192-column tile (64 vertices)
 FG_SLOT_BYTES = 128 * 48
+FG_TAB = 4 + 2 * FG_NSLOT      # ints per column tile of ft_tab: n_fresh, n_inc, record bytes, 0, fresh loads, incremental loads
+FG_REC_HEAD = 64               # bytes: 9 group offsets (entries, relative to the tile's first) + padding
+FG_REC_ENTRY = 48              # bytes: slot byte offset | joint * 12 | 0 | 0 | 8 weights
+FG_REC_MAX = FG_REC_HEAD + FG_REC_ENTRY * 256      # csrc/lbs_fuseg.cuh: one of the kernel's two record buffers
 
 
 def fuseg_tables(g_start, g_joint, num_groups, nslot=FG_NSLOT, gpt=FG_GPT):
@@ -118,11 +124,12 @@ def fuseg_tables(g_start, g_joint, num_groups, nslot=FG_NSLOT, gpt=FG_GPT):
     started), and a new joint never takes a slot tile c-1 used (its epilogue may still be reading).  Joints that find no slot
     are read from global memory by the epilogue (g_slot = -1): correct for any mesh, fast for SMPL-like locality.
 
-    Returns g_slot [E] (byte offset of the slot of group entry e in ITS tile, or -1) and ft_tab [nct][2 + 2*nslot]:
-    n_fresh, n_inc, fresh entries, inc entries; entry = joint*12 | slot << 16."""
+    Returns g_slot [E] (byte offset of the slot of group entry e in ITS tile, or -1) and ft_tab [nct][4 + 2*nslot]:
+    n_fresh, n_inc, bytes of the tile's skinning record (filled by fuseg_records), 0, fresh entries, inc entries;
+    entry = joint*12 | slot << 16."""
     nct = (num_groups + gpt - 1) // gpt
     g_slot = np.full(len(g_joint), -1, np.int32)
-    tab = np.zeros((nct, 2 + 2 * nslot), np.int32)
+    tab = np.zeros((nct, 4 + 2 * nslot), np.int32)
     prev = {}                                                   # joint*12 -> slot of tile c-1
     for c in range(nct):
         e0, e1 = int(g_start[min(c * gpt, num_groups)]), int(g_start[min((c + 1) * gpt, num_groups)])
@@ -137,14 +144,45 @@ def fuseg_tables(g_start, g_joint, num_groups, nslot=FG_NSLOT, gpt=FG_GPT):
                 inc.append(j)
         fresh = sorted(cur, key=lambda j: cur[j])
         tab[c, 0], tab[c, 1] = len(fresh), len(inc)
-        tab[c, 2:2 + len(fresh)] = [j | (cur[j] << 16) for j in fresh]
-        tab[c, 2 + nslot:2 + nslot + len(inc)] = [j | (cur[j] << 16) for j in inc]
+        tab[c, 4:4 + len(fresh)] = [j | (cur[j] << 16) for j in fresh]
+        tab[c, 4 + nslot:4 + nslot + len(inc)] = [j | (cur[j] << 16) for j in inc]
         for e in range(e0, e1):
             j = int(g_joint[e])
             if j in cur:
                 g_slot[e] = cur[j] * FG_SLOT_BYTES
         prev = cur
     return g_slot, tab
+
+
+def fuseg_records(g_start, g_joint, g_slot, g_w, num_groups, ft_tab, gpt=FG_GPT):
+    """Per column tile ONE contiguous skinning record, which the kernel's producer copies into shared memory with a single bulk
+    copy while the previous tile is skinned (csrc/lbs_fuseg.cuh): the epilogue warps then read joint lists and weights at
+    shared-memory latency, warp-uniformly (the same entries straight from global memory missed the 28 KB of L1 the kernel
+    leaves 3 times out of 4: 41 % of all stall cycles, profiles/r02g_fuseg35_set_full_details.txt).
+
+    record = 16 ints (offsets of the tile's 8 groups + end, in entries relative to the tile's first entry; padding) followed by
+    48-byte entries: slot byte offset (or -1) | joint * 12 | 0 | 0 | the 8 weights of the group's vertices.
+    Returns a uint8 array [nct][stride] (stride = the longest record, a multiple of 16) and writes every tile's byte count into
+    ft_tab[:, 2].  None when a tile has more entries than a record buffer holds (the dispatcher then takes skin form 1)."""
+    nct = ft_tab.shape[0]
+    gs = np.asarray(g_start, np.int64)
+    ends = gs[np.minimum((np.arange(nct) + 1) * gpt, num_groups)]
+    begs = gs[np.minimum(np.arange(nct) * gpt, num_groups)]
+    emax = int((ends - begs).max())
+    stride = FG_REC_HEAD + FG_REC_ENTRY * max(emax, 1)
+    if stride > FG_REC_MAX:
+        return None
+    rec = np.zeros((nct, stride // 4), np.int32)
+    gw = np.ascontiguousarray(g_w, np.float32).view(np.int32)
+    for c in range(nct):
+        e0, e1 = int(begs[c]), int(ends[c])
+        for i in range(gpt + 1):
+            rec[c, i] = int(gs[min(c * gpt + i, num_groups)]) - e0
+        body = rec[c, FG_REC_HEAD // 4:FG_REC_HEAD // 4 + 12 * (e1 - e0)].reshape(e1 - e0, 12)
+        body[:, 0], body[:, 1] = g_slot[e0:e1], g_joint[e0:e1]
+        body[:, 4:12] = gw[e0:e1]
+        ft_tab[c, 2] = FG_REC_HEAD + FG_REC_ENTRY * (e1 - e0)
+    return rec.view(np.uint8).reshape(nct, stride)
 
 
 def _tf32_rn(x):
@@ -157,19 +195,28 @@ class LbsModel:
     """Device copy of the packed constants + the ctypes HbLbsModel handed to the C-ABI."""
 
     def __init__(self, packed, device):
-        self.device = torch.device(device)
-        if self.device.type != 'cuda':
+        if torch.device(device).type != 'cuda':
             raise RuntimeError('humor_b200.BodyModel needs a CUDA device (there is no CPU path)')
+        self._build(packed, device)
+
+    def _build(self, packed, device):
+        """Tables, operand planes and the C struct in `device` memory (tests/host/emul builds them in host memory for the
+        kernel-executing CUDA runtime stand-in)."""
+        self.device = torch.device(device)
         self.t = {k: torch.as_tensor(v).to(self.device).contiguous() for k, v in packed.items()
                   if isinstance(v, np.ndarray)}
         s = _ext.HbLbsModel()
-        s.num_verts, s.v3_ld, s.wk, s.reserved = packed['num_verts'], packed['v3_ld'], packed['wk'], 0
+        s.num_verts, s.v3_ld, s.wk, s.flags = packed['num_verts'], packed['v3_ld'], packed['wk'], 0
         for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_val', 'parents', 'extra_ids'):
             setattr(s, k, self.t[k].data_ptr())
         # operand planes of the tensor-core blend GEMM: blend_t with K padded 208 -> 224, split x = hi + lo
         import os
         bt = torch.zeros(packed['v3_ld'], 224, device=self.device)
         bt[:, :KF] = self.t['blend_t']
+        # column 205 (a zero padding column of blend_t; the pose kernels write feature 205 = 1 into the operand planes) carries
+        # v_template: the tensor-core products return v_posed itself and no epilogue adds the template (HB_PLANES_TEMPLATE)
+        bt[:self.t['v_template'].numel(), 205] = self.t['v_template']
+        s.flags = 1 | (2 if packed.get('w_rows_sum_to_one') else 0)       # HB_LBS_PLANES_TEMPLATE | HB_LBS_WEIGHTS_SUM_1
         hi = _tf32_rn(bt)
         self.t['blend_t_hi'], self.t['blend_t_lo'] = hi.contiguous(), (bt - hi).contiguous()
         s.blend_t_hi, s.blend_t_lo = self.t['blend_t_hi'].data_ptr(), self.t['blend_t_lo'].data_ptr()
@@ -177,6 +224,8 @@ class LbsModel:
         s.g_start, s.g_joint, s.g_w = (self.t[k].data_ptr() for k in ('g_start', 'g_joint', 'g_w'))
         s.num_groups = packed['num_groups']
         s.g_slot, s.ft_tab, s.ft_nct = self.t['g_slot'].data_ptr(), self.t['ft_tab'].data_ptr(), packed['ft_nct']
+        if packed.get('ft_rec') is not None:
+            s.ft_rec, s.ft_rec_stride = self.t['ft_rec'].data_ptr(), packed['ft_rec'].shape[1]
         # blend form 5: blend_t * 2^10 (exact: keeps pose offsets down to 1e-7 m in fp16's normal range; the kernel's epilogue scales
         # back), every column, K padded to 256, as fp16 hi + UNSCALED fp16 lo plane (x = h + l)
         bs = torch.zeros(packed['v3_ld'], 256, device=self.device)

@@ -68,7 +68,7 @@ __device__ __forceinline__ long long hb_clock64() { return clock64(); }
 #ifdef HB_HOST_SHIM
 using tcemu::cluster_id_x; using tcemu::cluster_nid_x; using tcemu::mbar_arrive_remote; using tcemu::mbar_wait_cluster;
 using tcemu::flag_wait_ge; using tcemu::flag_add_release; using tcemu::fence_proxy_async; using tcemu::epi_bar_sync;
-using tcemu::st_async_v4; using tcemu::fence_gpu; using tcemu::bulk_g2s; using tcemu::bulk_s2c; using tcemu::st_shared_v4;
+using tcemu::st_async_v4; using tcemu::fence_gpu; using tcemu::bulk_s2c;
 #else
 // 16-byte store into another CTA's shared memory that completes 16 transaction bytes on an mbarrier of THAT CTA when it lands:
 // data and signal travel together, no release fence / separate arrival on the critical path
@@ -82,14 +82,6 @@ __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" 
 __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src, uint32_t bytes, uint32_t bar_cluster) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_cluster), "r"(src), "r"(bytes), "r"(bar_cluster) : "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-// 1-D bulk copy global -> this CTA's shared memory, completing `bytes` on an mbarrier (addresses and size multiples of 16)
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }

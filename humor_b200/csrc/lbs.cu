@@ -74,7 +74,7 @@ __device__ __forceinline__ void rest_joints(const HbLbsModel& m, const float* __
 __global__ void lbs_pose_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ root_orient,
                                 const float* __restrict__ pose_body, const float* __restrict__ betas,
                                 const float* __restrict__ trans, float* feat, float* A, float* joints, int njo,
-                                float* feat_hi, float* feat_lo) {
+                                float* feat_hi, float* feat_lo, float a_scale, int a_fold) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float* beta = betas + (size_t)(n / fpb) * LBS_NB;
@@ -90,6 +90,14 @@ __global__ void lbs_pose_kernel(HbLbsModel m, int N, int fpb, const float* __res
     f[205] = f[206] = f[207] = 0.f;
   }
   lbs_chain_fwd(pose, J, m.parents, f ? f + LBS_NB : nullptr, A ? A + (size_t)n * 624 : nullptr, Jp);
+  if (A && (a_scale != 1.f || a_fold)) {   // transforms of the fused dense pass (see lbs_pose_warp_kernel)
+    float* an = A + (size_t)n * 624;
+    for (int j = 0; j < LBS_J; ++j)
+      for (int i = 0; i < 3; ++i) {
+        an[j * 12 + i * 4] *= a_scale; an[j * 12 + i * 4 + 1] *= a_scale; an[j * 12 + i * 4 + 2] *= a_scale;
+        if (a_fold) an[j * 12 + i * 4 + 3] += trans[(size_t)n * 3 + i];
+      }
+  }
   if (feat_hi && f) {                 // hi/lo operand planes (x = hi + lo) of the feature row for the tensor-core blend
     for (int k = 0; k < TC_KF; ++k) {
       const float v = k < 205 ? f[k] : (k == 205 ? 1.f : 0.f);   // column 205 = 1: picks up the template row of the fused blend matrix
@@ -165,7 +173,10 @@ __device__ __forceinline__ void pose_forward_warp(const HbLbsModel& m, PoseSm& s
 __global__ void __launch_bounds__(PW * 32)
 lbs_pose_warp_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ root_orient, const float* __restrict__ pose_body,
                      const float* __restrict__ betas, const float* __restrict__ trans, float* feat, float* A, float* joints,
-                     int njo, float* feat_hi, float* feat_lo) {
+                     int njo, float* feat_hi, float* feat_lo, float a_scale, int a_fold) {
+  // a_scale / a_fold (fused dense pass only, lbs_fuseg.cuh; 1 / 0 everywhere else): A is written with its rotation part times
+  // a_scale (the 2^-10 that brings the fp16 planes' accumulators back to metres) and trans added to its translation column (exact
+  // for weights that sum to 1, HB_LBS_WEIGHTS_SUM_1) - both would otherwise cost the skinning epilogue 48 instructions per group
   __shared__ PoseSm sm[PW];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * PW + wid;
@@ -190,7 +201,9 @@ lbs_pose_warp_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ roo
       }
     }
   }
-  const float t0 = joints ? trans[(size_t)n * 3] : 0.f, t1 = joints ? trans[(size_t)n * 3 + 1] : 0.f, t2 = joints ? trans[(size_t)n * 3 + 2] : 0.f;
+  const bool need_t = joints || a_fold;
+  const float t0 = need_t ? trans[(size_t)n * 3] : 0.f, t1 = need_t ? trans[(size_t)n * 3 + 1] : 0.f, t2 = need_t ? trans[(size_t)n * 3 + 2] : 0.f;
+  const float f0 = a_fold ? t0 : 0.f, f1 = a_fold ? t1 : 0.f, f2 = a_fold ? t2 : 0.f;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int j = lane + 32 * h;
@@ -200,9 +213,9 @@ lbs_pose_warp_kernel(HbLbsModel m, int N, int fpb, const float* __restrict__ roo
         float c[3];
         mat3_vec(r, s.J + 3 * j, c);
         float4* a = reinterpret_cast<float4*>(A + (size_t)n * 624 + j * 12);
-        a[0] = make_float4(r[0], r[1], r[2], s.tw[3 * j] - c[0]);
-        a[1] = make_float4(r[3], r[4], r[5], s.tw[3 * j + 1] - c[1]);
-        a[2] = make_float4(r[6], r[7], r[8], s.tw[3 * j + 2] - c[2]);
+        a[0] = make_float4(r[0] * a_scale, r[1] * a_scale, r[2] * a_scale, s.tw[3 * j] - c[0] + f0);
+        a[1] = make_float4(r[3] * a_scale, r[4] * a_scale, r[5] * a_scale, s.tw[3 * j + 1] - c[1] + f1);
+        a[2] = make_float4(r[6] * a_scale, r[7] * a_scale, r[8] * a_scale, s.tw[3 * j + 2] - c[2] + f2);
       }
       if (joints) {
         float* jo = joints + ((size_t)n * njo + j) * 3;
@@ -706,6 +719,7 @@ __global__ void lbs_pose_bwd_kernel(HbLbsModel m, int N, int fpb, const float* _
 }
 
 static const bool g_thread_pose = (getenv("HB_LBS_THREAD") != nullptr);
+static const bool g_no_fold = (getenv("HB_LBS_NO_FOLD") != nullptr);   // A/B: the fused pass adds trans per vertex instead of inside A
 // dense skinning pass: 1 = blend GEMM (umma_gemm3_kernel, v_posed slabs through L2) + lane-per-vertex lbs_skin_apply_kernel (the
 // round-1 default, kept as the form for meshes without group tables and as the A/B partner), 3 (DEFAULT since round 2: 1.06 ms vs
 // 3.35 ms per 15 360 frames on the B200, profiles/r02g_*) = blend GEMM + group skinning fused in one persistent tcgen05 kernel
@@ -762,30 +776,33 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
   const bool need_skin = (verts != nullptr) || (joints && njo == 73);
   // dense output of >= 128 frames: blend on the 5th-gen tensor cores (UMMA 3xTF32) + shared-memory skinning pass
   const bool tc = verts && !vlist && N >= 128 && m->use_umma && m->blend_t_hi && m->v3_ld <= 20736 && umma_available();
+  // skin form 3: one persistent tcgen05 kernel, blend accumulators skinned straight out of TMEM by lane = frame (lbs_fuseg.cuh)
+  const bool fuseg = tc && g_skin_form == 3 && (m->flags & HB_LBS_PLANES_TEMPLATE) && m->ft_tab && m->ft_rec && m->ft_rec_stride > 0 &&
+                     m->num_groups > 0 && m->ft_nct == cdiv(m->num_groups, 8) && (m->num_verts % 2) == 0 && m->v3_ld % 4 == 0;
+  const bool f16x3 = fuseg && g_blend_form == 5 && m->blend16a_h && m->blend16a_l;
+  // the fused pass is the only reader of A then: its transforms come pre-scaled, and with the translation when that is exact
+  const float a_scale = f16x3 ? 0.0009765625f : 1.f;
+  const int a_fold = (fuseg && (m->flags & HB_LBS_WEIGHTS_SUM_1) && !g_no_fold) ? 1 : 0;
   if (m->depth && m->child_start && !g_thread_pose)
     lbs_pose_warp_kernel<<<cdiv(N, PW), PW * 32, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
                                                          need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
-                                                         tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);
+                                                         tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr, a_scale, a_fold);
   else
     lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
                                                need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
-                                               tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr);
+                                               tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr, a_scale, a_fold);
   HB_LAUNCH_CHECK(); ++nl;
-  // skin form 3: one persistent tcgen05 kernel, blend accumulators skinned straight out of TMEM by lane = frame (lbs_fuseg.cuh)
-  const bool fuseg = tc && g_skin_form == 3 && m->ft_tab && m->g_slot && m->g_start && m->g_joint && m->g_w && m->num_groups > 0 &&
-                     m->ft_nct == cdiv(m->num_groups, 8) && (m->num_verts % 2) == 0 && m->v3_ld % 4 == 0;
   if (fuseg) {
     LbsFusegArgs fa;
-    const bool f16x3 = g_blend_form == 5 && m->blend16a_h && m->blend16a_l;
     fa.N = N; fa.num_verts = m->num_verts; fa.num_groups = m->num_groups; fa.nrt = fa.nct = 0;
-    fa.nkb16 = f16x3 ? 4 : 0; fa.out_scale = f16x3 ? 0.0009765625f : 1.f;
-    fa.g_start = m->g_start; fa.g_joint = m->g_joint; fa.g_slot = m->g_slot; fa.g_w = m->g_w; fa.ft_tab = m->ft_tab;
-    fa.v_template = m->v_template; fa.A = ws.A; fa.trans = trans; fa.out = verts;
+    fa.nkb16 = f16x3 ? 4 : 0;
+    fa.ft_tab = m->ft_tab; fa.ft_rec = static_cast<const unsigned char*>(m->ft_rec); fa.ft_rec_stride = m->ft_rec_stride;
+    fa.A = ws.A; fa.trans = a_fold ? nullptr : trans; fa.out = verts;
     if (f16x3) {
       // every column as fp16 hi + (unscaled) lo planes, K = 256: three products per k-block, no tf32 k-blocks
       unsigned short* f16h = reinterpret_cast<unsigned short*>(ws.feat16);
       unsigned short* f16l = f16h + (size_t)align_up((size_t)N, 64) * 256;
-      HB_CUDA(launch_feat_f16(ws.feat, LBS_KF, LBS_KF, N, 0, 4, f16h, f16l, st));
+      HB_CUDA(launch_feat_f16(ws.feat, LBS_KF, LBS_KF, N, 0, 4, f16h, f16l, 205, st));
       ++nl;
       HB_CUDA(launch_lbs_fuseg(nullptr, nullptr, TC_KF, nullptr, nullptr, TC_KF, m->v3_ld, 0, f16h, m->blend16a_h, f16l, m->blend16a_l, 256,
                                fa, st));
@@ -801,7 +818,8 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
     }
   } else if (tc) {
     GemmEpi ep;
-    ep.bias = m->v_template; ep.gamma = ep.beta = nullptr; ep.xhat = ep.rstd = nullptr; ep.ldxh = 0; ep.Cch = 0; ep.gsize = 64;
+    ep.bias = (m->flags & HB_LBS_PLANES_TEMPLATE) ? nullptr : m->v_template;     // planes with the template in column 205 need no bias
+    ep.gamma = ep.beta = nullptr; ep.xhat = ep.rstd = nullptr; ep.ldxh = 0; ep.Cch = 0; ep.gsize = 64;
     static const int b_const = getenv("HB_UMMA_PREFETCH_B") ? 1 : 0;      // B = the model's blend planes: constant
     ep.b_const = b_const;
     // frames per slab: the v_posed slab must stay in L2 between the two kernels (<= TC_SLAB rows of workspace)
@@ -862,9 +880,9 @@ extern "C" int humor_lbs_bwd(const HbLbsModel* m, int N, int fpb, const float* r
     // recompute the per-frame forward (feature rows, skinning transforms): cheaper than keeping them
     if (m->depth && m->child_start && !g_thread_pose)
       lbs_pose_warp_kernel<<<cdiv(N, PW), PW * 32, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52,
-                                                           nullptr, nullptr);
+                                                           nullptr, nullptr, 1.f, 0);
     else
-      lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52, nullptr, nullptr);
+      lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans, ws.feat, ws.A, nullptr, 52, nullptr, nullptr, 1.f, 0);
     HB_LAUNCH_CHECK(); ++nl;
     static bool attr_bwd = false;
     if (!attr_bwd) {

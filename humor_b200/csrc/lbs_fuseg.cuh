@@ -20,11 +20,17 @@
 //           keeps its slot while consecutive tiles need it, so a tile loads ~1 new slot (6 KB) instead of ~6
 //   warp 1  tcgen05.mma issuer; a tile's k-blocks accumulate into ONE of two 192-column TMEM buffers (K = 224: no
 //           promotion chunks needed), so tile i+1's MMAs run under tile i's epilogue
+//           (c) the tile's skinning RECORD (group offsets, per entry slot | joint | 8 weights: HbLbsModel.ft_rec) with one
+//           bulk copy into one of two record buffers - the epilogue reads joint lists and weights at shared-memory latency
+//           (read straight from global memory they missed the 28 KB of L1 this kernel leaves 3 times out of 4 and made up
+//           41 % of all stall cycles: profiles/r02g_fuseg35_set_full_details.txt)
 //   warps 2..17 epilogue: TMEM lane quadrant q = warp % 4, column quarter (warp - 2) / 4 -> 2 groups each.  Per group:
-//           tcgen05.ld 24 columns (8 vertices of the thread's frame), + template, skin with the group's joint list
-//           (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), + trans, park the 24 floats in a
-//           per-warp staging tile and write two 96-byte frame rows per instruction (a lane = frame store would touch
-//           32 different lines per instruction).
+//           tcgen05.ld 24 columns (8 vertices of the thread's frame; the template rides in the GEMM, column 205 of the planes,
+//           and the 2^-10 scale-back / the root translation sit in the transforms the pose kernel wrote for this pass), skin
+//           with the group's joint list (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), park
+//           the 24 floats in a per-warp staging tile (6 x STS.128, chunks rotated by one for rows 4..7 mod 8: conflict-
+//           free at a dense 96-byte row) and write 2 2/3 frame rows of 96 bytes per store instruction with all 32 lanes
+//           (a lane = frame store would touch 32 different lines per instruction).
 //   fp16x3  (blend form 5, the default) EVERY column as fp16 hi + lo planes, three products per k-block (h.h + l.h + h.l) into the one accumulator:
 //           the lo planes are UNSCALED (l = fp16(x - h)); what that costs is an absolute floor of 3e-8 on tiny operands, i.e.
 //           ~1e-9 m after the 2^-10 scale-back - irrelevant here, and it keeps one accumulator per tile (a scaled lo part would
@@ -32,7 +38,7 @@
 // Barrier protocol (all mbarriers, phases counted per use):
 //   full[s]/empty[s]   operand ring (TMA complete_tx / tcgen05.commit)
 //   tfull[b]/tempty[b] TMEM buffer b = tile parity (tcgen05.commit / one arrive per epilogue warp)
-//   ttf[b]             transforms of tile parity b have landed (arrive.expect_tx by the producer, complete_tx by TMA).
+//   ttf[b]             transforms + record of tile parity b have landed (arrive.expect_tx by the producer, complete_tx by TMA).
 //                      The producer issues tile i's transform loads only after tempty says the epilogue is done with tile
 //                      i-2 (slots tile i-1 uses are never chosen by the schedule), and after tile i-1 when the frames change
 //                      (then every slot is reloaded).
@@ -55,14 +61,18 @@ constexpr int FG_ENTRY = FG_A_PLANE + FG_B_PLANE;   // 40 KB
 constexpr int FG_NSLOT = 12;                        // body_model.FG_NSLOT
 constexpr int FG_SLOT = UM_BM * 48;                 // [128 frames][12 floats]
 constexpr int FG_EPI_WARPS = 16;                    // 4 per TMEM lane quadrant: two vertex groups of the tile each
-constexpr int FG_SLD = 25;                          // staging row stride in floats (odd: conflict-free lane = row writes)
-constexpr int FG_STAGE_W = 32 * FG_SLD * 4;         // bytes per epilogue warp
+constexpr int FG_STAGE_W = 32 * FG_GC * 4;          // bytes per epilogue warp: 32 frame rows x 96 B, dense
+constexpr int FG_REC_HEAD = 64;                     // body_model.FG_REC_*: 9 group offsets + padding,
+constexpr int FG_REC_ENTRY = 48;                    //   then { slot byte offset | joint * 12 | 0 | 0 | 8 weights } per entry
+constexpr int FG_REC_MAX = FG_REC_HEAD + FG_REC_ENTRY * 256;
 constexpr int FG_OFF_SLOTS = FG_RING * FG_ENTRY;
 constexpr int FG_OFF_STAGE = FG_OFF_SLOTS + FG_NSLOT * FG_SLOT;
-constexpr int FG_OFF_BARS = FG_OFF_STAGE + FG_EPI_WARPS * FG_STAGE_W;
-constexpr int FG_SMEM = FG_OFF_BARS + 128 + 1024;   // + barriers + 1024-byte alignment slack = 223 360 B
+constexpr int FG_OFF_REC = FG_OFF_STAGE + FG_EPI_WARPS * FG_STAGE_W;
+constexpr int FG_OFF_BARS = FG_OFF_REC + 2 * FG_REC_MAX;
+constexpr int FG_SMEM = FG_OFF_BARS + 128 + 1024;   // + barriers + 1024-byte alignment slack = 230 656 B
 constexpr int FG_THREADS = 64 + 32 * FG_EPI_WARPS;
-constexpr int FG_TAB = 2 + 2 * FG_NSLOT;            // ints per column tile of ft_tab
+constexpr int FG_TAB = 4 + 2 * FG_NSLOT;            // ints per column tile of ft_tab
+static_assert(FG_SMEM <= 232448, "lbs_fuseg_kernel: shared memory");
 
 #ifndef HB_HOST_SHIM
 // tcgen05.ld of one vertex group: 24 consecutive columns of the thread's TMEM lane, as three naturally aligned 8-column loads
@@ -87,11 +97,13 @@ __device__ __forceinline__ void tmem_ld12(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void stcs2(float* p, float x, float y) { __stcs(reinterpret_cast<float2*>(p), make_float2(x, y)); }
+__device__ __forceinline__ void stcs1(float* p, float x) { __stcs(p, x); }
 #define HB_EMU_GUARD_ACQ(addr, bytes)
 #define HB_EMU_GUARD_REL(addr)
 #else
 using tcemu::tmem_ld24; using tcemu::tmem_ld12;
 static inline void stcs2(float* p, float x, float y) { p[0] = x; p[1] = y; }
+static inline void stcs1(float* p, float x) { p[0] = x; }
 // tests/host: tell the emulation which shared-memory ranges are being read, so that a TMA write into them aborts
 #define HB_EMU_GUARD_ACQ(addr, bytes) tcemu::guard_acquire(addr, bytes)
 #define HB_EMU_GUARD_REL(addr) tcemu::guard_release(addr)
@@ -106,7 +118,6 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   HB_DYN_SMEM(smem_raw);
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* gbase = smem_raw + (base - raw);
   const uint32_t bars = base + FG_OFF_BARS;
   const uint32_t full0 = bars, empty0 = bars + 8 * FG_RING, tfull0 = empty0 + 8 * FG_RING, tempty0 = tfull0 + 16, ttf0 = tempty0 + 16,
                  tptr = ttf0 + 16;
@@ -144,9 +155,11 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (tc >= 2) mbar_wait(tempty0 + 8 * (tc & 1), ((tc >> 1) & 1) ^ 1);                   // ... with tile tc-2
         const int* tab = a.ft_tab + (size_t)c * FG_TAB;
         const int nl = fresh ? tab[0] : tab[1];
-        const int* ent = tab + 2 + (fresh ? 0 : FG_NSLOT);
+        const int* ent = tab + 4 + (fresh ? 0 : FG_NSLOT);
         const uint32_t tb = ttf0 + 8 * (tc & 1);
-        mbar_expect_tx(tb, (uint32_t)nl * FG_SLOT);
+        const uint32_t recb = (uint32_t)tab[2];
+        mbar_expect_tx(tb, (uint32_t)nl * FG_SLOT + recb);
+        bulk_g2s(base + FG_OFF_REC + (uint32_t)(tc & 1) * FG_REC_MAX, a.ft_rec + (size_t)c * a.ft_rec_stride, recb, tb);
         for (int i = 0; i < nl; ++i) {
           const int e = ent[i];
           tma_load_2d(base + FG_OFF_SLOTS + (uint32_t)(e >> 16) * FG_SLOT, &tmT, tb, e & 0xffff, m0);
@@ -236,66 +249,76 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int q = warp & 3;                                     // TMEM lane quadrant of this warp
     const int h4 = ew >> 2;                                     // column quarter: groups 2*h4, 2*h4+1 of the tile
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* S = reinterpret_cast<float*>(gbase + FG_OFF_STAGE + ew * FG_STAGE_W);
+    const uint32_t stg = base + FG_OFF_STAGE + (uint32_t)ew * FG_STAGE_W;             // this warp's staging tile: [32 frames][96 B]
     const uint32_t tsl = base + FG_OFF_SLOTS + (uint32_t)(q * 32 + lane) * 48u;       // this thread's frame inside a slot
-    const int sub = lane / 12, idx = lane - 12 * sub;           // store phase: lanes 0..23 = 2 frame rows x 12 float2
+    // staging tile, written lane = frame: the six 16-byte chunks of row r sit at ((chunk + ((r >> 2) & 1)) % 6) * 16, which
+    // makes eight consecutive rows of a dense 96-byte stride hit eight different bank quads
+    const uint32_t rot = (uint32_t)(lane >> 2) & 1u;
+    const uint32_t sw0 = stg + (uint32_t)lane * 96u + rot * 16u;                      // chunks 0..4 at sw0 + 16 k
+    const uint32_t sw5 = stg + (uint32_t)lane * 96u + (rot ? 0u : 80u);               // chunk 5
+    // store phase: float2 number L = 32 it + lane of the tile's 32 x 12 (row L / 12, pair L % 12), it = 0..11; three iterations
+    // cover eight rows exactly, so a lane needs three (shared offset, global offset) pairs and adds 8 rows per round
+    const int rowf = a.num_verts * 3;                           // floats per output frame
+    uint32_t sr3[3];
+    int go3[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int L3 = 32 * i + lane, r3 = L3 / 12, j = L3 - 12 * r3;
+      int ch = (j >> 1) + ((r3 >> 2) & 1);
+      if (ch >= 6) ch -= 6;
+      sr3[i] = stg + (uint32_t)(r3 * 96 + ch * 16 + (j & 1) * 8);
+      go3[i] = r3 * rowf + 2 * j;
+    }
     int tc = 0;
     for (int t = t_begin; t < t_end; ++t, ++tc) {
       const int buf = tc & 1;
       const int r = t / a.nct, c = t - r * a.nct;
       const int f0 = r * UM_BM + q * 32;
       const int fr = min(f0 + lane, a.N - 1);                   // rows past N: computed on a valid frame, never stored
-      const float t0 = __ldg(a.trans + (size_t)fr * 3), t1 = __ldg(a.trans + (size_t)fr * 3 + 1), t2 = __ldg(a.trans + (size_t)fr * 3 + 2);
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      if (a.trans) {                                            // kernel-uniform: the translation is not folded into A
+        t0 = __ldg(a.trans + (size_t)fr * 3); t1 = __ldg(a.trans + (size_t)fr * 3 + 1); t2 = __ldg(a.trans + (size_t)fr * 3 + 2);
+      }
       const float* Arow = a.A + (size_t)fr * 624;
+      const uint32_t rec = base + FG_OFF_REC + (uint32_t)buf * FG_REC_MAX;
       mbar_wait(tfull0 + 8 * buf, (tc >> 1) & 1);
       mbar_wait(ttf0 + 8 * buf, (tc >> 1) & 1);
       tc_fence_after();
 #ifdef HB_HOST_SHIM
-      if (lane == 0) {                                          // (emulation only) the slots this tile reads
+      if (lane == 0) {                                          // (emulation only) the slots and the record this tile reads
         const int* tab = a.ft_tab + (size_t)c * FG_TAB;
-        for (int i = 0; i < tab[0]; ++i) HB_EMU_GUARD_ACQ(base + FG_OFF_SLOTS + (uint32_t)(tab[2 + i] >> 16) * FG_SLOT, FG_SLOT);
+        for (int i = 0; i < tab[0]; ++i) HB_EMU_GUARD_ACQ(base + FG_OFF_SLOTS + (uint32_t)(tab[4 + i] >> 16) * FG_SLOT, FG_SLOT);
+        HB_EMU_GUARD_ACQ(rec, FG_REC_MAX);
       }
 #endif
-      // Two groups of 8 vertices per warp.  Sixteen epilogue warps (four per scheduler) hide the latency of the table / shared-
-      // memory loads, so the joint loop carries no software look-ahead and no per-vertex zero-weight tests: 96 FMAs per
-      // (group, joint) against ~20 other instructions, 95 registers.  (Round 1 ran 8 warps at 135 registers with look-ahead
-      // registers and a branch per vertex and joint: 42 % of the issue slots, profiles/r02a_fuseg35_set_full_details.txt; a
-      // half-group form at 16 warps doubled the loop overhead instead: profiles/r02f_*.)
+      // Two groups of 8 vertices per warp.  Sixteen epilogue warps (four per scheduler) hide the latency of the shared-memory
+      // loads: 96 FMAs per (group, joint) against 5 warp-uniform LDS + 3 LDS.128 of the transform.  (Round 1 ran 8 warps at 135
+      // registers with look-ahead registers and a branch per vertex and joint: 42 % of the issue slots,
+      // profiles/r02a_fuseg35_set_full_details.txt; a half-group form at 16 warps doubled the loop overhead instead: r02f_*.)
 #pragma unroll 1
       for (int gg = 0; gg < 2; ++gg) {
-        const int g = c * FG_GPT + h4 * 2 + gg;
+        const int gi = h4 * 2 + gg;
+        const int g = c * FG_GPT + gi;
         if (g >= a.num_groups) break;                           // warp-uniform
         float p[FG_GC], acc[FG_GC];
-        tmem_ld24(trow + buf * FG_BN + (h4 * 2 + gg) * FG_GC, p);
-        const int col0 = g * FG_GC;
+        tmem_ld24(trow + buf * FG_BN + gi * FG_GC, p);
         const int nv3 = min(FG_G, a.num_verts - g * FG_G) * 3;  // floats of this group inside the mesh
-        if (nv3 == FG_GC) {                                     // warp-uniform; a group's 96 template bytes are 16-byte aligned
-          const float4* tp = reinterpret_cast<const float4*>(a.v_template + col0);
-#pragma unroll
-          for (int i4 = 0; i4 < FG_GC / 4; ++i4) {
-            const float4 tv = __ldg(tp + i4);
-            p[4 * i4] = fmaf(p[4 * i4], a.out_scale, tv.x); p[4 * i4 + 1] = fmaf(p[4 * i4 + 1], a.out_scale, tv.y);
-            p[4 * i4 + 2] = fmaf(p[4 * i4 + 2], a.out_scale, tv.z); p[4 * i4 + 3] = fmaf(p[4 * i4 + 3], a.out_scale, tv.w);
-          }
-        } else {                                                // the mesh's last, partial group
-#pragma unroll
-          for (int i = 0; i < FG_GC; ++i) p[i] = fmaf(p[i], a.out_scale, (i < nv3) ? __ldg(a.v_template + col0 + i) : 0.f);
-        }
 #pragma unroll
         for (int i = 0; i < FG_GC; ++i) acc[i] = 0.f;
-        const int e0 = __ldg(a.g_start + g), e1 = __ldg(a.g_start + g + 1);
-#pragma unroll 1
-        for (int e = e0; e < e1; ++e) {
-          const int so = __ldg(a.g_slot + e);                   // warp-uniform
-          const float4 wa = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e * FG_G));
-          const float4 wb = __ldg(reinterpret_cast<const float4*>(a.g_w + (size_t)e * FG_G) + 1);
+        uint32_t ea = rec + FG_REC_HEAD + ld_shared_u32(rec + 4u * gi) * FG_REC_ENTRY;
+        const uint32_t ee = rec + FG_REC_HEAD + ld_shared_u32(rec + 4u * gi + 4u) * FG_REC_ENTRY;
+        int so = (int)ld_shared_u32(ea);                        // warp-uniform, fetched one entry ahead (the read behind the last
+#pragma unroll 1                                                // entry stays inside the record buffer and is never used)
+        for (; ea < ee; ea += FG_REC_ENTRY) {
+          const float4 wa = ld_shared_v4(ea + 16u), wb = ld_shared_v4(ea + 32u);
           float4 r0, r1, r2;
           if (so >= 0) {
             r0 = ld_shared_v4(tsl + (uint32_t)so); r1 = ld_shared_v4(tsl + (uint32_t)so + 16u); r2 = ld_shared_v4(tsl + (uint32_t)so + 32u);
           } else {                                              // joint without a slot in this tile (rare): from L1/L2
-            const float4* ap = reinterpret_cast<const float4*>(Arow + __ldg(a.g_joint + e));
+            const float4* ap = reinterpret_cast<const float4*>(Arow + ld_shared_u32(ea + 4u));
             r0 = __ldg(ap); r1 = __ldg(ap + 1); r2 = __ldg(ap + 2);
           }
+          so = (int)ld_shared_u32(ea + FG_REC_ENTRY);
           const float w[FG_G] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
           for (int i = 0; i < FG_G; ++i) {
@@ -305,37 +328,36 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             acc[3 * i + 2] = fmaf(w[i], fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))), acc[3 * i + 2]);
           }
         }
-        float* obase = a.out + ((size_t)g * FG_G) * 3;
-        if (a.direct_store) {
-          // A/B variant (HB_LBS_FUSEG_DIRECT=1): every thread writes its frame's 96 bytes itself - 12 STG.64 and no staging,
-          // but 32 different lines per instruction (5x slower on the B200: profiles/r02f_lbs_forms_time.jsonl)
-          if (f0 + lane < a.N) {
-            float* dst = obase + (size_t)(f0 + lane) * a.num_verts * 3;
+        if (a.trans) {
 #pragma unroll
-            for (int q2 = 0; q2 < FG_GC / 2; ++q2) {
-              const float x = acc[2 * q2] + ((2 * q2) % 3 == 0 ? t0 : ((2 * q2) % 3 == 1 ? t1 : t2));
-              const float y = acc[2 * q2 + 1] + ((2 * q2 + 1) % 3 == 0 ? t0 : ((2 * q2 + 1) % 3 == 1 ? t1 : t2));
-              if (2 * q2 + 1 < nv3) stcs2(dst + 2 * q2, x, y);
-              else if (2 * q2 < nv3) __stcs(dst + 2 * q2, x);
+          for (int i = 0; i < FG_GC; ++i) acc[i] += (i % 3) == 0 ? t0 : ((i % 3) == 1 ? t1 : t2);
+        }
+        // park the group (lane = frame), then 2 2/3 frame rows of 96 bytes per store instruction
+#pragma unroll
+        for (int k = 0; k < 5; ++k) st_shared_v4(sw0 + 16u * k, acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+        st_shared_v4(sw5, acc[20], acc[21], acc[22], acc[23]);
+        __syncwarp();
+        float* tb = a.out + (size_t)f0 * rowf + (size_t)g * FG_GC;
+        if (f0 + 32 <= a.N && nv3 == FG_GC) {                   // warp-uniform: every row and every column is stored
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const float2 v = ld_shared_v2(sr3[i] + 768u * m);
+              stcs2(tb + (size_t)(8 * m) * rowf + go3[i], v.x, v.y);
             }
           }
-          continue;
-        }
-        // park the group (lane = frame), then two 96-byte frame rows per store instruction
-        float* Sr = S + lane * FG_SLD;
-#pragma unroll
-        for (int i = 0; i < FG_GC; ++i) Sr[i] = acc[i] + ((i % 3) == 0 ? t0 : ((i % 3) == 1 ? t1 : t2));
-        __syncwarp();
-        if (lane < 24) {
-#pragma unroll 4
-          for (int rr = 0; rr < 32; rr += 2) {
-            const int row = rr + sub;
-            const int frame = f0 + row;
-            if (frame < a.N) {
-              const float x = S[row * FG_SLD + 2 * idx], y = S[row * FG_SLD + 2 * idx + 1];
-              float* dst = obase + (size_t)frame * a.num_verts * 3 + 2 * idx;
-              if (2 * idx + 1 < nv3) stcs2(dst, x, y);
-              else if (2 * idx < nv3) __stcs(dst, x);
+        } else {                                                // ragged last row tile / the mesh's last, partial group
+#pragma unroll 1
+          for (int L = lane; L < 32 * 12; L += 32) {           // (offsets recomputed: no dynamic index into sr3 / go3)
+            const int row = L / 12, j = L - 12 * row;
+            int ch = (j >> 1) + ((row >> 2) & 1);
+            if (ch >= 6) ch -= 6;
+            if (f0 + row < a.N) {
+              const float2 v = ld_shared_v2(stg + (uint32_t)(row * 96 + ch * 16 + (j & 1) * 8));
+              float* dst = tb + (size_t)row * rowf + 2 * j;
+              if (2 * j + 1 < nv3) stcs2(dst, v.x, v.y);
+              else if (2 * j < nv3) stcs1(dst, v.x);
             }
           }
         }
@@ -346,7 +368,8 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #ifdef HB_HOST_SHIM
       if (lane == 0) {
         const int* tab = a.ft_tab + (size_t)c * FG_TAB;
-        for (int i = 0; i < tab[0]; ++i) HB_EMU_GUARD_REL(base + FG_OFF_SLOTS + (uint32_t)(tab[2 + i] >> 16) * FG_SLOT);
+        for (int i = 0; i < tab[0]; ++i) HB_EMU_GUARD_REL(base + FG_OFF_SLOTS + (uint32_t)(tab[4 + i] >> 16) * FG_SLOT);
+        HB_EMU_GUARD_REL(rec);
       }
 #endif
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);

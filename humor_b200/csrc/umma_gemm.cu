@@ -170,11 +170,12 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
                              LbsFusegArgs a, cudaStream_t st) {
   if (!load_encode()) return cudaErrorNotSupported;
   if (K % UM_BK || ldf % 4 || ldb % 4 || a.N <= 0 || a.num_groups <= 0 || (a.num_verts & 1) ||
-      a.num_groups != cdiv(a.num_verts, FG_G) || !a.g_start || !a.g_joint || !a.g_slot || !a.g_w || !a.ft_tab)
+      a.num_groups != cdiv(a.num_verts, FG_G) || !a.ft_tab || !a.ft_rec || a.ft_rec_stride < FG_REC_HEAD + FG_REC_ENTRY ||
+      a.ft_rec_stride > FG_REC_MAX || a.ft_rec_stride % 16 || (reinterpret_cast<uintptr_t>(a.ft_rec) & 15u) || !a.A || !a.out)
     return cudaErrorInvalidValue;
   if (a.nkb16 < 0 || (a.nkb16 > 0 && (!feat16 || !bt16 || !feat16l || !bt16l || ld16 % 8 || ld16 < 64 * a.nkb16))) return cudaErrorInvalidValue;
   if ((K == 0) == (a.nkb16 <= 0)) return cudaErrorInvalidValue;          // either the tf32 planes or the fp16 planes
-  static int sms = 0, want = 0, direct = 0;
+  static int sms = 0, want = 0;
   if (!sms) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -185,9 +186,7 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
     // kernels of other streams (the latency-bound decoder chain runs next to the dense pass)
     const char* w = getenv("HB_LBS_FUSEG_CTAS");
     want = w ? atoi(w) : 0;
-    direct = getenv("HB_LBS_FUSEG_DIRECT") ? 1 : 0;
   }
-  a.direct_store = direct;
   a.nrt = cdiv(a.N, UM_BM);
   a.nct = cdiv(a.num_groups, FG_GPT);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16, ta16l, tb16l;
@@ -360,25 +359,26 @@ static inline float f16_value(unsigned short b) { _Float16 h; std::memcpy(&h, &b
 __device__ __forceinline__ float f16_value(unsigned short b) { return __half2float(__ushort_as_half(b)); }
 #endif
 __global__ void feat_f16_kernel(const float* __restrict__ feat, int ldf, int ncols, int N, int c0, int w, unsigned short* __restrict__ out,
-                                unsigned short* __restrict__ out_lo) {
+                                unsigned short* __restrict__ out_lo, int one_col) {
   const size_t n = (size_t)N * w;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / w;
     const int j = (int)(i - r * w);
-    const float x = c0 + j < ncols ? feat[r * ldf + c0 + j] : 0.f;
+    const float x = c0 + j == one_col ? 1.f : (c0 + j < ncols ? feat[r * ldf + c0 + j] : 0.f);
     const unsigned short h = f16_bits(x);
     out[i] = h;
     if (out_lo) out_lo[i] = f16_bits(x - f16_value(h));        // unscaled lo plane of blend form 5
   }
 }
 #ifndef HB_HOST_SHIM
-cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, void* out_lo, cudaStream_t st) {
+cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, void* out_lo, int one_col,
+                            cudaStream_t st) {
   if (!feat || !out || N <= 0 || nkb16 <= 0) return cudaErrorInvalidValue;
   const size_t n = (size_t)N * 64 * nkb16;
   size_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   feat_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(feat, ldf, ncols, N, c0, 64 * nkb16, static_cast<unsigned short*>(out),
-                                                    static_cast<unsigned short*>(out_lo));
+                                                    static_cast<unsigned short*>(out_lo), one_col);
   return cudaGetLastError();
 }
 cudaError_t launch_split_hilo(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {

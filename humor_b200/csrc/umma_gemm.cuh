@@ -192,12 +192,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // through DSMEM stores between two cluster barriers; only the leader runs the epilogue.
 #ifdef HB_HOST_SHIM     // tests/host: single-CTA emulation; cluster instantiations (KS > 1) compile but must not run
 using tcemu::cluster_ctarank; using tcemu::cluster_sync_all; using tcemu::map_to_cta; using tcemu::st_cluster_v4;
-using tcemu::ld_shared_v4;
+using tcemu::ld_shared_v4; using tcemu::ld_shared_v2; using tcemu::st_shared_v4; using tcemu::bulk_g2s;
 #else
 __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ float2 ld_shared_v2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// 1-D bulk copy global -> this CTA's shared memory, completing `bytes` on an mbarrier (addresses and size multiples of 16)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {

@@ -28,21 +28,18 @@ struct LbsFusegArgs {
   int N;                   // frames
   int num_verts;
   int num_groups;
-  int nrt, nct;            // row tiles (128 frames), column tiles (64 vertices)
+  int nrt, nct;            // row tiles (128 frames), column tiles (64 vertices); set by the launcher
   int nkb16;               // > 0 (blend form 5): this many 64-wide fp16 k-blocks (kind::f16) on hi + lo planes: h.h + l.h + h.l
-  float out_scale;         // accumulator -> metres (2^-10 when the blend planes are pre-scaled for the fp16 range, else 1)
-  int direct_store;        // 1: lane = frame stores straight from registers (A/B variant), 0: staged row stores; set by the launcher
-  const int* g_start;      // [num_groups + 1]
-  const int* g_joint;      // [E] joint * 12
-  const int* g_slot;       // [E] byte offset of the entry's slot, -1: transform read from global memory
-  const float* g_w;        // [E][8]
+  int ft_rec_stride;       // bytes per column tile of ft_rec
   const int* ft_tab;       // [nct][FG_TAB]
-  const float* v_template; // [3 * num_verts]
-  const float* A;          // [N][52][12] skinning transforms
-  const float* trans;      // [N][3]
+  const unsigned char* ft_rec;   // [nct][ft_rec_stride] skinning records (HbLbsModel.ft_rec)
+  const float* A;          // [N][52][12] skinning transforms OF THIS PASS: rotation part times the accumulator scale (2^-10 when
+                           // the blend planes are pre-scaled for the fp16 range), translation column + trans unless `trans` is set
+  const float* trans;      // [N][3] added to every vertex, or nullptr: already inside A
   float* out;              // [N][num_verts][3]
 };
-// bt_* = blend_t hi/lo planes [b_rows][K] (ldb floats per row); the caller fills every field of `a` except nrt / nct.
+// bt_* = blend_t hi/lo planes [b_rows][K] (ldb floats per row) WITH the template in column 205 (HB_LBS_PLANES_TEMPLATE; the
+// feature planes carry 1 there); the caller fills every field of `a` except nrt / nct.
 // a.nkb16 > 0: feat16 [N][ld16] / bt16 [b_rows][ld16] fp16 hi planes (ld16 halves per row, >= 64 * nkb16), feat16l / bt16l the
 // lo planes (same shapes); K (columns of the tf32 planes) is then 0
 cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb,
@@ -51,6 +48,7 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
 // CTAs of the next lbs_fuseg launches (0: one per SM); > SMs = shorter chunks that the scheduler slots next to other streams' kernels
 void lbs_set_fuseg_ctas(int n);
 // fp16 plane(s) of the feature columns [c0, c0 + 64 * nkb16) of feat[N][ldf] (columns >= ncols read as zero): out = fp16(x),
-// out_lo (nullable) = fp16(x - out)
-cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, void* out_lo, cudaStream_t st);
+// out_lo (nullable) = fp16(x - out); column `one_col` (>= 0) is written as 1 whatever feat holds there
+cudaError_t launch_feat_f16(const float* feat, int ldf, int ncols, int N, int c0, int nkb16, void* out, void* out_lo, int one_col,
+                            cudaStream_t st);
 }  // namespace hb

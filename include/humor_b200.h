@@ -42,7 +42,7 @@ typedef struct HbLbsModel {
   int num_verts;           /* V = 6890 */
   int v3_ld;               /* leading dimension of blend (>= 3V, multiple of 64) */
   int wk;                  /* ELL width of the skinning weights = max non-zeros per vertex */
-  int reserved;
+  int flags;               /* HB_LBS_PLANES_TEMPLATE | HB_LBS_WEIGHTS_SUM_1 (below) */
   const float* v_template; /* [3V] */
   const float* blend;      /* [208][v3_ld]  row k: shapedirs (k<16) / posedirs (16<=k<205) of coord 3v+c */
   const float* blend_t;    /* [v3_ld][208]  transpose of blend */
@@ -53,7 +53,10 @@ typedef struct HbLbsModel {
   const int* parents;      /* [52] kintree_table[0], parents[0] = -1 */
   const int* extra_ids;    /* [21] smplx vertex_ids['smplh'] in VertexJointSelector order */
   /* tensor-core blend: hi/lo planes (x = hi + lo) of blend_t with K padded to 224: [v3_ld][224]; NULL / use_umma = 0
-   * keeps the exact-fp32 FFMA kernels */
+   * keeps the exact-fp32 FFMA kernels.  With HB_LBS_PLANES_TEMPLATE in flags, column 205 of these planes (a padding column of
+   * blend_t; the pose kernels write feature 205 = 1 into the operand planes) holds v_template - likewise column 205 of
+   * blend16a_* (times 2^10) - so that the products are v_posed itself and no epilogue adds the template.  The fused kernel
+   * (skin form 3) REQUIRES the flag. */
   const float* blend_t_hi;
   const float* blend_t_lo;
   int use_umma;
@@ -72,7 +75,8 @@ typedef struct HbLbsModel {
      joints live in 12 shared-memory slots that persist across the consecutive column tiles a CTA walks */
   int ft_nct;              /* column tiles = ceil(num_groups / 8); 0: tables absent */
   const int* g_slot;       /* [E] byte offset of entry e's slot in the tile of its group, or -1: read A from global memory */
-  const int* ft_tab;       /* [ft_nct][26] n_fresh, n_inc, 12 fresh + 12 incremental loads (joint*12 | slot << 16) */
+  const int* ft_tab;       /* [ft_nct][28] n_fresh, n_inc, bytes of the tile's record in ft_rec, 0, 12 fresh + 12 incremental
+                              loads (joint*12 | slot << 16) */
   /* blend form 5 (skin form 3 only): blend_t * 2^10, all 208 columns padded to 256, as fp16 hi plane and UNSCALED fp16 lo
      plane (x = h + l) [v3_ld][256] each; NULL: form unavailable */
   const void* blend16a_h;
@@ -84,8 +88,15 @@ typedef struct HbLbsModel {
   const int* sel_ids;      /* [sel_nv], sel_nv + 21 <= 64 */
   const float* sel_blend;
   int sel_nv;
-  int reserved2;
+  int ft_rec_stride;       /* bytes per column tile of ft_rec (multiple of 16, <= 64 + 48 * 256); 0: records absent */
+  /* skin form 3: per column tile one contiguous skinning record, bulk-copied into shared memory by the kernel's producer:
+     16 ints (entry offsets of the tile's 8 groups + end, relative to the tile's first entry; padding), then 48-byte entries
+     { slot byte offset or -1, joint*12, 0, 0, 8 weights } - the contents of g_slot / g_joint / g_w in tile order */
+  const void* ft_rec;      /* [ft_nct][ft_rec_stride], 16-byte aligned */
 } HbLbsModel;
+#define HB_LBS_PLANES_TEMPLATE 1 /* column 205 of blend_t_hi/lo and blend16a_h/l carries v_template (see above) */
+#define HB_LBS_WEIGHTS_SUM_1 2   /* the skinning weights of every vertex sum to 1 (|sum - 1| < 1e-6): the dense pass may add the
+                                    root translation to the transforms' translation column instead of to every vertex */
 
 /* Replaces BodyModel.forward -> smplx.SMPLH.forward -> smplx.lbs.lbs
  * (humor/body_model/body_model.py:72-115).  N frames; betas row of frame n is n / frames_per_beta.

@@ -35,8 +35,8 @@ unsigned g_cluster_x = 1;        // cluster dimension of the launch being execut
 #define RUN(...) shim::launch_cluster(g, b, g_cluster_x, [&] { __VA_ARGS__; })
 const std::map<std::string, Thunk>& registry() {
   static const std::map<std::string, Thunk> r = {
-      {"hb::lbs_pose_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(float*, 11), A(float*, 12))); }},
-      {"hb::lbs_pose_warp_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_warp_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(float*, 11), A(float*, 12))); }},
+      {"hb::lbs_pose_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(float*, 11), A(float*, 12), A(float, 13), A(int, 14))); }},
+      {"hb::lbs_pose_warp_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_warp_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(float*, 7), A(float*, 8), A(float*, 9), A(int, 10), A(float*, 11), A(float*, 12), A(float, 13), A(int, 14))); }},
       {"hb::lbs_pose_bwd_warp_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_bwd_warp_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(cf, 8), A(cf, 9), A(int, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
       {"hb::lbs_pose_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_bwd_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(cf, 8), A(cf, 9), A(int, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
       {"hb::lbs_skin_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_fwd_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(cf, 3), A(cf, 4), A(ci, 5), A(int, 6), A(float*, 7), A(size_t, 8))); }},
@@ -93,7 +93,7 @@ const std::map<std::string, Thunk>& registry() {
       UMMA16_THUNK(64, 0, 1) UMMA16_THUNK(64, 0, 4) UMMA16_THUNK(128, 0, 1) UMMA16_THUNK(64, 1, 1) UMMA16_THUNK(64, 1, 4) UMMA16_THUNK(128, 1, 1)
       {"hb::split16_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::split16_kernel(A(cf, 0), A(unsigned short*, 1), A(unsigned short*, 2), A(size_t, 3))); }},
       {"hb::lbs_fuseg_kernel", [](dim3 g, dim3 b, void** a) { tcemu::reset(); RUN(hb_emu::lbs_fuseg_kernel(MAP(0), MAP(1), MAP(2), MAP(3), MAP(4), MAP(5), MAP(6), MAP(7), MAP(8), A(int, 9), A(hb_emu::LbsFusegArgs, 10))); }},
-      {"hb::feat_f16_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::feat_f16_kernel(A(cf, 0), A(int, 1), A(int, 2), A(int, 3), A(int, 4), A(int, 5), A(unsigned short*, 6), A(unsigned short*, 7))); }},
+      {"hb::feat_f16_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::feat_f16_kernel(A(cf, 0), A(int, 1), A(int, 2), A(int, 3), A(int, 4), A(int, 5), A(unsigned short*, 6), A(unsigned short*, 7), A(int, 8))); }},
       // persistent decoder chain: the WHOLE grid runs at once (clusters wait on each other through global-memory flags); the
       // launcher's parameter block holds 128-byte driver tensor maps, the emulated kernel's block the emulated ones
       {"hb::chain_kernel", [](dim3 g, dim3 b, void** a) {

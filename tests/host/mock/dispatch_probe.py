@@ -18,9 +18,10 @@ t = {k: torch.as_tensor(v).contiguous() for k, v in packed.items() if isinstance
 s = _ext.HbLbsModel()
 s.num_verts, s.v3_ld, s.wk = packed['num_verts'], packed['v3_ld'], packed['wk']
 for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_val', 'parents', 'extra_ids', 'depth',
-          'child_start', 'child_list', 'g_start', 'g_joint', 'g_w', 'g_slot', 'ft_tab'):
+          'child_start', 'child_list', 'g_start', 'g_joint', 'g_w', 'g_slot', 'ft_tab', 'ft_rec'):
     setattr(s, k, t[k].data_ptr())
-s.ft_nct = packed['ft_nct']
+s.ft_nct, s.ft_rec_stride = packed['ft_nct'], packed['ft_rec'].shape[1]
+s.flags = 1 | (2 if packed['w_rows_sum_to_one'] else 0)      # as body_model.LbsModel: template in column 205 of the planes
 planes = torch.zeros(packed['v3_ld'], 224)
 s.blend_t_hi = s.blend_t_lo = s.blend16a_h = s.blend16a_l = planes.data_ptr()
 s.use_umma, s.max_depth, s.num_groups = 1, packed['max_depth'], packed['num_groups']

@@ -260,6 +260,10 @@ inline void tc_fence_before() {}
 inline void tc_fence_after() {}
 inline uint32_t ld_shared_u32(uint32_t addr) { uint32_t v; std::memcpy(&v, g_smem + addr, 4); return v; }
 inline float4 ld_shared_v4(uint32_t addr) { float4 v; std::memcpy(&v, g_smem + addr, 16); return v; }
+inline float2 ld_shared_v2(uint32_t addr) {
+  if (addr & 7u) { std::fprintf(stderr, "tcemu: bad ld.shared.v2 address %u\n", addr); std::abort(); }
+  float2 v; std::memcpy(&v, g_smem + addr, 8); return v;
+}
 // thread-block clusters: the CTAs of a cluster run concurrently (shim::launch_cluster), each on its own CtaState.  What the
 // split-K GEMM uses: %cluster_ctarank, barrier.cluster (all threads of all CTAs), mapa + st.shared::cluster (DSMEM stores).
 inline uint32_t cluster_ctarank() { return shim::t_crank; }
@@ -323,6 +327,7 @@ inline void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar
     std::fprintf(stderr, "tcemu: bulk copy %p -> %u (%u bytes) is not 16-byte aligned / in range\n", src, dst, bytes);
     std::abort();
   }
+  guard_check_write(dst, bytes);
   std::memcpy(g_smem + dst, src, bytes);
   complete_tx(bar, bytes);
 }

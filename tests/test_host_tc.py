@@ -44,9 +44,10 @@ def _fuseg_problem(N, seed):
     feat = np.zeros((N, K), np.float32)
     feat[:, :16] = rng.randn(N, 16).astype(np.float32) * 0.7            # betas
     feat[:, 16:205] = (rng.randn(N, 189) * 0.3).astype(np.float32)      # R - I at moderate poses
-    feat[:, 205] = 1.0                                                  # the pose kernels write 1 here; blend_t has a zero column
+    feat[:, 205] = 1.0                                                  # the pose kernels write 1 here ...
     bt = np.zeros((p['v3_ld'], K), np.float32)
     bt[:, :208] = p['blend_t']
+    bt[:3 * V, 205] = p['v_template']                                   # ... and column 205 of the planes carries the template
     A = rng.randn(N, 52, 3, 4).astype(np.float32)
     trans = rng.randn(N, 3).astype(np.float32)
     vp = feat[:, :208].astype(np.float64) @ p['blend'][:, :3 * V].astype(np.float64) + p['v_template'].astype(np.float64)
@@ -56,14 +57,22 @@ def _fuseg_problem(N, seed):
     return p, feat, bt, A, trans, ref
 
 
-def _run_fuseg(H, p, feat, bt, A, trans, grid, f16=False):
+def _run_fuseg(H, p, feat, bt, A, trans, grid, f16=False, fold=False):
+    """The kernel's contract (csrc/umma_launch.cuh LbsFusegArgs): A arrives with its rotation part times the accumulator scale and,
+    with fold, the root translation inside its translation column (trans = NULL) - what the pose kernels write for this pass."""
     N, K, V = feat.shape[0], 224, 6890
     fh, fl = split_rn(feat)
     out = np.full((N, V, 3), np.nan, np.float32)
     ntma = ctypes.c_longlong(0)
     H.h_lbs_fuseg.restype = ctypes.c_longlong
-    tabs = (N, V, p['num_groups'], P(p['g_start']), P(p['g_joint']), P(p['g_slot']), P(p['g_w']), P(p['ft_tab']), P(p['v_template']),
-            P(A), P(trans), P(out), grid)
+    A = A.copy()
+    if f16:
+        A[..., :3] *= np.float32(2.0 ** -10)
+    if fold:
+        A[..., 3] += trans[:, None, :]
+    rec = np.ascontiguousarray(p['ft_rec'])
+    assert rec.ctypes.data % 16 == 0
+    tabs = (N, V, p['num_groups'], P(p['ft_tab']), P(rec), rec.shape[1], P(A), None if fold else P(trans), P(out), grid)
     if f16:   # blend form 5: every column as fp16 hi + unscaled lo planes (K padded to 256), three products, no tf32 k-blocks
         fp = np.zeros((N, 256), np.float32)
         fp[:, :K] = feat
@@ -73,11 +82,10 @@ def _run_fuseg(H, p, feat, bt, A, trans, grid, f16=False):
         f_l, b_l = (fp - f_h.astype(np.float32)).astype(np.float16), (bp - b_h.astype(np.float32)).astype(np.float16)
         keep = [np.ascontiguousarray(x) for x in (f_h, b_h, f_l, b_l)]
         nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(fh), P(fl), K, bt.shape[0], 0, *tabs, ctypes.byref(ntma), P(keep[0]), P(keep[1]), 256, 4,
-                             ctypes.c_float(2.0 ** -10), P(keep[2]), P(keep[3]))
+                             P(keep[2]), P(keep[3]))
     else:
         bh, bl = split_rn(bt)
-        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, *tabs, ctypes.byref(ntma), None, None, 0, 0,
-                             ctypes.c_float(1.0), None, None)
+        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, *tabs, ctypes.byref(ntma), None, None, 0, 0, None, None)
     return out, nmma, ntma.value
 
 
@@ -90,8 +98,8 @@ def test_fuseg_slot_schedule_is_consistent():
     assert nct == (ng + 7) // 8 and len(gsl) == len(gj)
     state = {}                                                   # slot -> joint*12, as left by an incremental walk from tile 0
     for c in range(nct):
-        fresh = {int(e) >> 16: int(e) & 0xffff for e in tab[c, 2:2 + tab[c, 0]]}
-        inc = {int(e) >> 16: int(e) & 0xffff for e in tab[c, 14:14 + tab[c, 1]]}
+        fresh = {int(e) >> 16: int(e) & 0xffff for e in tab[c, 4:4 + tab[c, 0]]}
+        inc = {int(e) >> 16: int(e) & 0xffff for e in tab[c, 16:16 + tab[c, 1]]}
         assert len(fresh) == tab[c, 0] <= 12 and all(0 <= s < 12 for s in fresh)
         prev_used = set(state) if c else set()
         assert not (set(inc) & prev_used)                        # a new joint never overwrites a slot tile c-1 may be reading
@@ -103,14 +111,27 @@ def test_fuseg_slot_schedule_is_consistent():
                 if gsl[e] >= 0:
                     assert gsl[e] % (128 * 48) == 0 and fresh[gsl[e] // (128 * 48)] == gj[e]
     assert (gsl < 0).mean() < 0.05                               # SMPL-like locality: few joints are left to global loads
+    # the per-tile records the kernel's producer bulk-copies: the same entries, tile by tile
+    rec, gw = p['ft_rec'], p['g_w']
+    assert rec.shape[0] == nct and rec.shape[1] % 16 == 0 and rec.shape[1] <= 64 + 48 * 256
+    r32 = np.ascontiguousarray(rec).view(np.int32)
+    for c in range(nct):
+        e0 = gs[min(8 * c, ng)]
+        offs = r32[c, :9]
+        assert [int(o) for o in offs] == [int(gs[min(8 * c + i, ng)] - e0) for i in range(9)]
+        ne = int(offs[8])
+        assert tab[c, 2] == 64 + 48 * ne
+        body = r32[c, 16:16 + 12 * ne].reshape(ne, 12)
+        assert (body[:, 0] == gsl[e0:e0 + ne]).all() and (body[:, 1] == gj[e0:e0 + ne]).all()
+        assert (body[:, 4:].view(np.float32) == gw[e0:e0 + ne]).all()
 
 
-@pytest.mark.parametrize('N,grid', [(200, 3), (40, 7), (140, 2)])
-def test_fuseg_kernel_matches_fp64(H, N, grid):
+@pytest.mark.parametrize('N,grid,fold', [(200, 3, False), (40, 7, True), (140, 2, True)])
+def test_fuseg_kernel_matches_fp64(H, N, grid, fold):
     """The whole mesh (108 column tiles, the last one 64 operand rows past the planes) x 1-2 row tiles (ragged), CTA chunks that
     start in the middle of a row and cross into the next one (fresh slot loads + full drain); blend form 1 (3xTF32)."""
     p, feat, bt, A, trans, ref = _fuseg_problem(N, N + grid)
-    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid)
+    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid, fold=fold)
     ntiles = ((N + 127) // 128) * 108
     assert nmma == ntiles * 7 * 4 * 3
     assert np.isfinite(out).all()                                # every vertex of every frame written
@@ -127,22 +148,31 @@ def test_fuseg_kernel_matches_fp64(H, N, grid):
 def test_fuseg_kernel_on_a_mesh_without_locality(H):
     """Nothing in the slot schedule assumes SMPL: with skinning weights scattered over all 52 joints (up to 8 influences per
     vertex, every 64-vertex tile touching ~50 joints) most group entries find no slot and the epilogue reads their transforms
-    from global memory - same result."""
+    from global memory - same result.  A mesh whose tiles need more entries than a record buffer holds (16 scattered influences)
+    gets no records: the dispatcher then runs skin form 1."""
     asset = dict(synth.make_smplh_asset())
-    rng = np.random.RandomState(3)
     V = 6890
-    W = np.zeros((V, 52))
-    for v in range(V):
-        js = rng.choice(52, size=rng.randint(1, 9), replace=False)
-        W[v, js] = rng.rand(len(js)) + 0.05
-    asset['weights'] = (W / W.sum(1, keepdims=True)).astype(np.float32)
+
+    def scattered(kmax, seed):
+        rng = np.random.RandomState(seed)
+        W = np.zeros((V, 52))
+        for v in range(V):
+            js = rng.choice(52, size=rng.randint(1, kmax + 1), replace=False)
+            W[v, js] = rng.rand(len(js)) + 0.05
+        return (W / W.sum(1, keepdims=True)).astype(np.float32)
+    asset['weights'] = scattered(16, 5)
+    assert pack_smplh(asset, 16)['ft_rec'] is None
+    asset['weights'] = scattered(8, 3)
+    rng = np.random.RandomState(4)
     p = pack_smplh(asset, 16)
-    assert p['wk'] == 8 and (p['g_slot'] < 0).mean() > 0.5 and p['ft_tab'][:, 0].max() == 12
+    assert p['wk'] == 8 and (p['g_slot'] < 0).mean() > 0.5 and p['ft_tab'][:, 0].max() == 12 and p['ft_rec'] is not None
     N, K = 70, 224
     feat = np.zeros((N, K), np.float32)
     feat[:, :205] = (rng.randn(N, 205) * 0.3).astype(np.float32)
+    feat[:, 205] = 1.0
     bt = np.zeros((p['v3_ld'], K), np.float32)
     bt[:, :208] = p['blend_t']
+    bt[:3 * V, 205] = p['v_template']
     A = rng.randn(N, 52, 3, 4).astype(np.float32)
     trans = rng.randn(N, 3).astype(np.float32)
     out, nmma, _ = _run_fuseg(H, p, feat, bt, A, trans, 2)

@@ -111,7 +111,7 @@ FG_SLOT_BYTES = 128 * 48
 FG_TAB = 4 + 2 * FG_NSLOT      # ints per column tile of ft_tab: n_fresh, n_inc, record bytes, 0, fresh loads, incremental loads
 FG_REC_HEAD = 64               # bytes: 9 group offsets (entries, relative to the tile's first) + padding
 FG_REC_ENTRY = 48              # bytes: slot byte offset | joint * 12 | 0 | 0 | 8 weights
-FG_REC_MAX = FG_REC_HEAD + FG_REC_ENTRY * 256      # csrc/lbs_fuseg.cuh: one of the kernel's two record buffers
+FG_REC_MAX = FG_REC_HEAD + FG_REC_ENTRY * 96       # csrc/lbs_fuseg.cuh: one of the kernel's two record buffers (SMPL+H: <= 60 entries)
 
 
 def fuseg_tables(g_start, g_joint, num_groups, nslot=FG_NSLOT, gpt=FG_GPT):

@@ -10,27 +10,29 @@
 //   * the TMEM accumulator layout IS lane = frame (M = frames): a thread that reads its row with tcgen05.ld holds
 //     consecutive vertices of ONE frame, which is exactly the operand of group skinning (vertices sorted by joint set): a
 //     transform is fetched once per (frame, joint, group of 8 vertices) and joint index / weights are warp-uniform.
-// Plan of one CTA (one per SM, 320 threads):
+// Plan of one CTA (one per SM, 608 threads):
 //   tiles   128 frames x 192 columns (= 64 vertices = 8 groups), walked ROW-major in one contiguous chunk per CTA: ~88
 //           consecutive column tiles of the same 128 frames, so the frames' transforms stay on the SM
-//   warp 0  TMA producer: (a) operand ring of 3 entries of 40 KB = one A plane (128 x 32 floats) + one B plane (192 x 32);
-//           a k-block takes two entries (hi planes, lo planes);
-//           (b) the 3x4 transforms of the joints the tile is skinned to, as [128 frames][12 floats] boxes cut from
-//           A[N][52*12] into 12 shared-memory slots under the host's static schedule (body_model.fuseg_tables): a joint
-//           keeps its slot while consecutive tiles need it, so a tile loads ~1 new slot (6 KB) instead of ~6
+//   warp 0  TMA producer of the operand ring: 3 entries of 40 KB = one A plane (128 x 32 floats) + one B plane (192 x 32);
+//           a k-block takes two entries (hi planes, lo planes); gated by the ring only, L2 evict_last hint (every CTA re-reads
+//           the planes while 1.3 GB of output stream through the L2 evict-first)
 //   warp 1  tcgen05.mma issuer; a tile's k-blocks accumulate into ONE of two 192-column TMEM buffers (K = 224: no
 //           promotion chunks needed), so tile i+1's MMAs run under tile i's epilogue
-//           (c) the tile's skinning RECORD (group offsets, per entry slot | joint | 8 weights: HbLbsModel.ft_rec) with one
-//           bulk copy into one of two record buffers - the epilogue reads joint lists and weights at shared-memory latency
-//           (read straight from global memory they missed the 28 KB of L1 this kernel leaves 3 times out of 4 and made up
-//           41 % of all stall cycles: profiles/r02g_fuseg35_set_full_details.txt)
+//   warp 18 TMA producer, gated by the epilogue's progress, of (a) the 3x4 transforms of the joints the tile is skinned to, as
+//           [128 frames][12 floats] boxes cut from A[N][52*12] into 12 shared-memory slots under the host's static schedule
+//           (body_model.fuseg_tables): a joint keeps its slot while consecutive tiles need it, so a tile loads ~1 new slot (6 KB)
+//           instead of ~6; (b) the tile's skinning RECORD (group offsets, per entry slot | joint | 8 weights: HbLbsModel.ft_rec)
+//           with one bulk copy into one of two record buffers - the epilogue reads joint lists and weights at shared-memory
+//           latency (read straight from global memory they missed the 28 KB of L1 this kernel leaves 3 times out of 4 and made
+//           up 41 % of all stall cycles: profiles/r02g_fuseg35_set_full_details.txt)
 //   warps 2..17 epilogue: TMEM lane quadrant q = warp % 4, column quarter (warp - 2) / 4 -> 2 groups each.  Per group:
 //           tcgen05.ld 24 columns (8 vertices of the thread's frame; the template rides in the GEMM, column 205 of the planes,
 //           and the 2^-10 scale-back / the root translation sit in the transforms the pose kernel wrote for this pass), skin
-//           with the group's joint list (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), park
-//           the 24 floats in a per-warp staging tile (6 x STS.128, chunks rotated by one for rows 4..7 mod 8: conflict-
-//           free at a dense 96-byte row) and write 2 2/3 frame rows of 96 bytes per store instruction with all 32 lanes
-//           (a lane = frame store would touch 32 different lines per instruction).
+//           with the group's joint list (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), then in
+//           two passes of four vertices: park 12 floats in a per-warp staging tile (3 x STS.128 at a dense 48-byte row:
+//           conflict-free) and write 5 1/3 row segments of 48 bytes per store instruction with all 32 lanes (a lane = frame
+//           store would touch 32 different lines per instruction; a whole-group tile would cost 24 KB more shared memory,
+//           which the third ring entry needs).
 //   fp16x3  (blend form 5, the default) EVERY column as fp16 hi + lo planes, three products per k-block (h.h + l.h + h.l) into the one accumulator:
 //           the lo planes are UNSCALED (l = fp16(x - h)); what that costs is an absolute floor of 3e-8 on tiny operands, i.e.
 //           ~1e-9 m after the 2^-10 scale-back - irrelevant here, and it keeps one accumulator per tile (a scaled lo part would
@@ -54,23 +56,24 @@ constexpr int FG_BN = 192;                          // columns per tile = 64 ver
 constexpr int FG_GPT = 8;                           // vertex groups per tile
 constexpr int FG_G = 8;                             // vertices per group
 constexpr int FG_GC = 3 * FG_G;                     // columns per group
-constexpr int FG_RING = 2;                           // operand entries in flight (the epilogue, not the operand stream, paces a tile)
+constexpr int FG_RING = 3;                          // operand entries (40 KB: hi or lo planes of one k-block) in flight: with the per-tile table loads
+                                                    // gone the operand stream paces a tile, and two entries = one k-block exposed every load's latency
 constexpr int FG_A_PLANE = UM_BM * 128;             // bytes: 128 rows x 128 B
 constexpr int FG_B_PLANE = FG_BN * 128;
 constexpr int FG_ENTRY = FG_A_PLANE + FG_B_PLANE;   // 40 KB
 constexpr int FG_NSLOT = 12;                        // body_model.FG_NSLOT
 constexpr int FG_SLOT = UM_BM * 48;                 // [128 frames][12 floats]
 constexpr int FG_EPI_WARPS = 16;                    // 4 per TMEM lane quadrant: two vertex groups of the tile each
-constexpr int FG_STAGE_W = 32 * FG_GC * 4;          // bytes per epilogue warp: 32 frame rows x 96 B, dense
+constexpr int FG_STAGE_W = 32 * (FG_GC / 2) * 4;    // bytes per epilogue warp: 32 frame rows x 48 B (half a group per pass), dense
 constexpr int FG_REC_HEAD = 64;                     // body_model.FG_REC_*: 9 group offsets + padding,
 constexpr int FG_REC_ENTRY = 48;                    //   then { slot byte offset | joint * 12 | 0 | 0 | 8 weights } per entry
-constexpr int FG_REC_MAX = FG_REC_HEAD + FG_REC_ENTRY * 256;
+constexpr int FG_REC_MAX = FG_REC_HEAD + FG_REC_ENTRY * 96;
 constexpr int FG_OFF_SLOTS = FG_RING * FG_ENTRY;
 constexpr int FG_OFF_STAGE = FG_OFF_SLOTS + FG_NSLOT * FG_SLOT;
 constexpr int FG_OFF_REC = FG_OFF_STAGE + FG_EPI_WARPS * FG_STAGE_W;
 constexpr int FG_OFF_BARS = FG_OFF_REC + 2 * FG_REC_MAX;
-constexpr int FG_SMEM = FG_OFF_BARS + 128 + 1024;   // + barriers + 1024-byte alignment slack = 230 656 B
-constexpr int FG_THREADS = 64 + 32 * FG_EPI_WARPS;
+constexpr int FG_SMEM = FG_OFF_BARS + 128 + 1024;   // + barriers + 1024-byte alignment slack = 231 680 B
+constexpr int FG_THREADS = 96 + 32 * FG_EPI_WARPS;   // + TMA warp (operands), MMA warp, TMA warp (transforms + records)
 constexpr int FG_TAB = 4 + 2 * FG_NSLOT;            // ints per column tile of ft_tab
 static_assert(FG_SMEM <= 232448, "lbs_fuseg_kernel: shared memory");
 
@@ -144,11 +147,42 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      int g = 0, tc = 0, prev_r = -1;                           // ring entries issued, tiles started, row tile of the previous tile
-      for (int t = t_begin; t < t_end; ++t, ++tc) {
+      // ---- operand planes: gated by the ring only, so the first k-blocks of tile i+1 land while tile i is still being multiplied
+      const uint64_t keep = l2_policy_evict_last();             // every CTA re-reads the planes; the output streams through the L2
+      int g = 0;                                                // ring entries issued
+      for (int t = t_begin; t < t_end; ++t) {
         const int r = t / a.nct, c = t - r * a.nct;
         const int m0 = r * UM_BM, n0 = c * FG_BN;
-        // ---- skinning transforms of this tile's joints -> shared-memory slots
+        for (int kb = 0; kb < nkb; ++kb) {
+          for (int pl = 0; pl < 2; ++pl, ++g) {                 // hi entry, then lo entry
+            const int s = g % FG_RING;
+            mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
+            const uint32_t st = base + s * FG_ENTRY;
+            mbar_expect_tx(full0 + 8 * s, FG_ENTRY);
+            tma_load_2d_hint(st, pl ? &tmA_lo : &tmA_hi, full0 + 8 * s, kb * UM_BK, m0, keep);
+            tma_load_2d_hint(st + FG_A_PLANE, pl ? &tmB_lo : &tmB_hi, full0 + 8 * s, kb * UM_BK, n0, keep);
+          }
+        }
+        for (int kb = 0; kb < a.nkb16; ++kb) {                  // fp16 k-blocks: 64 halves = the same 128-byte rows, same entry
+          for (int pl = 0; pl < 2; ++pl, ++g) {                 // hi entry, then the lo entry
+            const int s = g % FG_RING;
+            mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
+            const uint32_t st = base + s * FG_ENTRY;
+            mbar_expect_tx(full0 + 8 * s, FG_ENTRY);
+            tma_load_2d_hint(st, pl ? &tmA16l : &tmA16, full0 + 8 * s, kb * 64, m0, keep);
+            tma_load_2d_hint(st + FG_A_PLANE, pl ? &tmB16l : &tmB16, full0 + 8 * s, kb * 64, n0, keep);
+          }
+        }
+      }
+    }
+  } else if (warp == FG_EPI_WARPS + 2) {
+    if (lane == 0) {
+      // ---- skinning transforms of a tile's joints -> shared-memory slots, and the tile's record -> record buffer tc & 1: gated by
+      // the epilogue's progress (tempty), on a warp of their own so that the operand stream above never waits for them
+      int tc = 0, prev_r = -1;                                  // tiles started, row tile of the previous tile
+      for (int t = t_begin; t < t_end; ++t, ++tc) {
+        const int r = t / a.nct, c = t - r * a.nct;
+        const int m0 = r * UM_BM;
         const bool fresh = r != prev_r;                         // first tile of the CTA, or other frames: reload every slot
         prev_r = r;
         if (fresh && tc >= 1) mbar_wait(tempty0 + 8 * ((tc - 1) & 1), ((tc - 1) >> 1) & 1);   // epilogue done with tile tc-1
@@ -163,27 +197,6 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int i = 0; i < nl; ++i) {
           const int e = ent[i];
           tma_load_2d(base + FG_OFF_SLOTS + (uint32_t)(e >> 16) * FG_SLOT, &tmT, tb, e & 0xffff, m0);
-        }
-        // ---- operand planes
-        for (int kb = 0; kb < nkb; ++kb) {
-          for (int pl = 0; pl < 2; ++pl, ++g) {                 // hi entry, then lo entry
-            const int s = g % FG_RING;
-            mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
-            const uint32_t st = base + s * FG_ENTRY;
-            mbar_expect_tx(full0 + 8 * s, FG_ENTRY);
-            tma_load_2d(st, pl ? &tmA_lo : &tmA_hi, full0 + 8 * s, kb * UM_BK, m0);
-            tma_load_2d(st + FG_A_PLANE, pl ? &tmB_lo : &tmB_hi, full0 + 8 * s, kb * UM_BK, n0);
-          }
-        }
-        for (int kb = 0; kb < a.nkb16; ++kb) {                  // fp16 k-blocks: 64 halves = the same 128-byte rows, same entry
-          for (int pl = 0; pl < 2; ++pl, ++g) {                 // hi entry, then the lo entry
-            const int s = g % FG_RING;
-            mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
-            const uint32_t st = base + s * FG_ENTRY;
-            mbar_expect_tx(full0 + 8 * s, FG_ENTRY);
-            tma_load_2d(st, pl ? &tmA16l : &tmA16, full0 + 8 * s, kb * 64, m0);
-            tma_load_2d(st + FG_A_PLANE, pl ? &tmB16l : &tmB16, full0 + 8 * s, kb * 64, n0);
-          }
         }
       }
     }
@@ -251,22 +264,17 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t stg = base + FG_OFF_STAGE + (uint32_t)ew * FG_STAGE_W;             // this warp's staging tile: [32 frames][96 B]
     const uint32_t tsl = base + FG_OFF_SLOTS + (uint32_t)(q * 32 + lane) * 48u;       // this thread's frame inside a slot
-    // staging tile, written lane = frame: the six 16-byte chunks of row r sit at ((chunk + ((r >> 2) & 1)) % 6) * 16, which
-    // makes eight consecutive rows of a dense 96-byte stride hit eight different bank quads
-    const uint32_t rot = (uint32_t)(lane >> 2) & 1u;
-    const uint32_t sw0 = stg + (uint32_t)lane * 96u + rot * 16u;                      // chunks 0..4 at sw0 + 16 k
-    const uint32_t sw5 = stg + (uint32_t)lane * 96u + (rot ? 0u : 80u);               // chunk 5
-    // store phase: float2 number L = 32 it + lane of the tile's 32 x 12 (row L / 12, pair L % 12), it = 0..11; three iterations
-    // cover eight rows exactly, so a lane needs three (shared offset, global offset) pairs and adds 8 rows per round
+    // staging tile [32 frames][48 B], written lane = frame (eight consecutive rows of the 48-byte stride hit eight different bank
+    // quads), read as float2 number L = 32 it + lane of its 32 x 6 (row L / 6, pair L % 6), it = 0..5: three iterations cover
+    // sixteen rows exactly, so a lane needs three (shared offset, global offset) pairs and adds 16 rows for the second round
+    const uint32_t sw = stg + (uint32_t)lane * 48u;
     const int rowf = a.num_verts * 3;                           // floats per output frame
     uint32_t sr3[3];
     int go3[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int L3 = 32 * i + lane, r3 = L3 / 12, j = L3 - 12 * r3;
-      int ch = (j >> 1) + ((r3 >> 2) & 1);
-      if (ch >= 6) ch -= 6;
-      sr3[i] = stg + (uint32_t)(r3 * 96 + ch * 16 + (j & 1) * 8);
+      const int L3 = 32 * i + lane, r3 = L3 / 6, j = L3 - 6 * r3;
+      sr3[i] = stg + (uint32_t)(r3 * 48 + j * 8);
       go3[i] = r3 * rowf + 2 * j;
     }
     int tc = 0;
@@ -332,36 +340,38 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
           for (int i = 0; i < FG_GC; ++i) acc[i] += (i % 3) == 0 ? t0 : ((i % 3) == 1 ? t1 : t2);
         }
-        // park the group (lane = frame), then 2 2/3 frame rows of 96 bytes per store instruction
-#pragma unroll
-        for (int k = 0; k < 5; ++k) st_shared_v4(sw0 + 16u * k, acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
-        st_shared_v4(sw5, acc[20], acc[21], acc[22], acc[23]);
-        __syncwarp();
+        // two passes of four vertices: park 12 floats (lane = frame), then 5 1/3 row segments of 48 bytes per store instruction
         float* tb = a.out + (size_t)f0 * rowf + (size_t)g * FG_GC;
-        if (f0 + 32 <= a.N && nv3 == FG_GC) {                   // warp-uniform: every row and every column is stored
+        const bool whole = f0 + 32 <= a.N && nv3 == FG_GC;      // warp-uniform: every row and every column is stored
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              const float2 v = ld_shared_v2(sr3[i] + 768u * m);
-              stcs2(tb + (size_t)(8 * m) * rowf + go3[i], v.x, v.y);
+          for (int k = 0; k < 3; ++k)
+            st_shared_v4(sw + 16u * k, acc[12 * h + 4 * k], acc[12 * h + 4 * k + 1], acc[12 * h + 4 * k + 2], acc[12 * h + 4 * k + 3]);
+          __syncwarp();
+          if (whole) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                const float2 v = ld_shared_v2(sr3[i] + 768u * m);
+                stcs2(tb + (size_t)(16 * m) * rowf + 12 * h + go3[i], v.x, v.y);
+              }
             }
-          }
-        } else {                                                // ragged last row tile / the mesh's last, partial group
+          } else {                                              // ragged last row tile / the mesh's last, partial group
 #pragma unroll 1
-          for (int L = lane; L < 32 * 12; L += 32) {           // (offsets recomputed: no dynamic index into sr3 / go3)
-            const int row = L / 12, j = L - 12 * row;
-            int ch = (j >> 1) + ((row >> 2) & 1);
-            if (ch >= 6) ch -= 6;
-            if (f0 + row < a.N) {
-              const float2 v = ld_shared_v2(stg + (uint32_t)(row * 96 + ch * 16 + (j & 1) * 8));
-              float* dst = tb + (size_t)row * rowf + 2 * j;
-              if (2 * j + 1 < nv3) stcs2(dst, v.x, v.y);
-              else if (2 * j < nv3) stcs1(dst, v.x);
+            for (int L = lane; L < 32 * 6; L += 32) {           // (offsets recomputed: no dynamic index into sr3 / go3)
+              const int row = L / 6, j = L - 6 * row;
+              if (f0 + row < a.N) {
+                const float2 v = ld_shared_v2(stg + (uint32_t)(row * 48 + j * 8));
+                float* dst = tb + (size_t)row * rowf + 12 * h + 2 * j;
+                if (12 * h + 2 * j + 1 < nv3) stcs2(dst, v.x, v.y);
+                else if (12 * h + 2 * j < nv3) stcs1(dst, v.x);
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

@@ -36,7 +36,8 @@ constexpr int UM_BK = 32;          // tf32 elements per stage row = 128 bytes = 
 using tcemu::smem_u32; using tcemu::mbar_init; using tcemu::mbar_expect_tx; using tcemu::mbar_wait; using tcemu::mbar_arrive;
 using tcemu::tma_load_2d; using tcemu::umma_tf32; using tcemu::umma_f16; using tcemu::umma_commit; using tcemu::tmem_ld32;
 using tcemu::tmem_alloc; using tcemu::tmem_relinquish; using tcemu::tmem_dealloc; using tcemu::tc_fence_before;
-using tcemu::tc_fence_after; using tcemu::mbar_fence_init; using tcemu::ld_shared_u32;
+using tcemu::tc_fence_after; using tcemu::mbar_fence_init; using tcemu::ld_shared_u32; using tcemu::l2_policy_evict_last;
+using tcemu::tma_load_2d_hint;
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // TMEM allocation (one warp, .sync.aligned): the base address lands in shared memory at `dst`
@@ -80,6 +81,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+// the same load with an L2 eviction-priority hint (createpolicy): operands every CTA re-reads stay resident while a kernel streams
+// gigabytes of output through the L2
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"

@@ -88,7 +88,7 @@ typedef struct HbLbsModel {
   const int* sel_ids;      /* [sel_nv], sel_nv + 21 <= 64 */
   const float* sel_blend;
   int sel_nv;
-  int ft_rec_stride;       /* bytes per column tile of ft_rec (multiple of 16, <= 64 + 48 * 256); 0: records absent */
+  int ft_rec_stride;       /* bytes per column tile of ft_rec (multiple of 16, <= 64 + 48 * 96); 0: records absent */
   /* skin form 3: per column tile one contiguous skinning record, bulk-copied into shared memory by the kernel's producer:
      16 ints (entry offsets of the tile's 8 groups + end, relative to the tile's first entry; padding), then 48-byte entries
      { slot byte offset or -1, joint*12, 0, 0, 8 weights } - the contents of g_slot / g_joint / g_w in tile order */

@@ -109,6 +109,9 @@ inline void mbar_wait(uint32_t bar, uint32_t parity) {
 // cp.async.bulk.tensor.2d ... mbarrier::complete_tx::bytes with a {32 floats, box_rows} box and SWIZZLE_128B
 // shared-memory ranges a kernel declares "being read" (HB_EMU_GUARD_* in the kernel source, no-ops on the device): a TMA
 // write into one of them is a protocol bug the synchronous emulation would otherwise hide
+inline unsigned long long l2_policy_evict_last() { return 0ull; }
+inline void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y);
+inline void tma_load_2d_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y, unsigned long long) { tma_load_2d(dst, m, bar, x, y); }
 inline void guard_acquire(uint32_t addr, uint32_t bytes) {
   std::lock_guard<std::mutex> l(g_mu);
   Guard& g = g_guards[addr];

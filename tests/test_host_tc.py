@@ -113,7 +113,7 @@ def test_fuseg_slot_schedule_is_consistent():
     assert (gsl < 0).mean() < 0.05                               # SMPL-like locality: few joints are left to global loads
     # the per-tile records the kernel's producer bulk-copies: the same entries, tile by tile
     rec, gw = p['ft_rec'], p['g_w']
-    assert rec.shape[0] == nct and rec.shape[1] % 16 == 0 and rec.shape[1] <= 64 + 48 * 256
+    assert rec.shape[0] == nct and rec.shape[1] % 16 == 0 and rec.shape[1] <= 64 + 48 * 96
     r32 = np.ascontiguousarray(rec).view(np.int32)
     for c in range(nct):
         e0 = gs[min(8 * c, ng)]
@@ -146,26 +146,26 @@ def test_fuseg_kernel_matches_fp64(H, N, grid, fold):
 
 
 def test_fuseg_kernel_on_a_mesh_without_locality(H):
-    """Nothing in the slot schedule assumes SMPL: with skinning weights scattered over all 52 joints (up to 8 influences per
-    vertex, every 64-vertex tile touching ~50 joints) most group entries find no slot and the epilogue reads their transforms
-    from global memory - same result.  A mesh whose tiles need more entries than a record buffer holds (16 scattered influences)
+    """Nothing in the slot schedule assumes SMPL: with skinning weights scattered over 20 joints (up to 2 influences per
+    vertex, every 64-vertex tile touching all 20) a third of the group entries find no slot and the epilogue reads their transforms
+    from global memory - same result.  A mesh whose tiles need more entries than a record buffer holds (8 scattered influences)
     gets no records: the dispatcher then runs skin form 1."""
     asset = dict(synth.make_smplh_asset())
     V = 6890
 
-    def scattered(kmax, seed):
+    def scattered(kmax, seed, pool=52):
         rng = np.random.RandomState(seed)
         W = np.zeros((V, 52))
         for v in range(V):
-            js = rng.choice(52, size=rng.randint(1, kmax + 1), replace=False)
+            js = rng.choice(pool, size=rng.randint(1, kmax + 1), replace=False)
             W[v, js] = rng.rand(len(js)) + 0.05
         return (W / W.sum(1, keepdims=True)).astype(np.float32)
-    asset['weights'] = scattered(16, 5)
+    asset['weights'] = scattered(8, 5)
     assert pack_smplh(asset, 16)['ft_rec'] is None
-    asset['weights'] = scattered(8, 3)
+    asset['weights'] = scattered(2, 3, pool=20)
     rng = np.random.RandomState(4)
     p = pack_smplh(asset, 16)
-    assert p['wk'] == 8 and (p['g_slot'] < 0).mean() > 0.5 and p['ft_tab'][:, 0].max() == 12 and p['ft_rec'] is not None
+    assert p['wk'] == 2 and (p['g_slot'] < 0).mean() > 0.3 and p['ft_tab'][:, 0].max() == 12 and p['ft_rec'] is not None
     N, K = 70, 224
     feat = np.zeros((N, K), np.float32)
     feat[:, :205] = (rng.randn(N, 205) * 0.3).astype(np.float32)

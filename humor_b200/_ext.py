@@ -72,7 +72,7 @@ class HbLbsModel(C.Structure):
                 ('ft_nct', C.c_int), ('g_slot', C.c_void_p), ('ft_tab', C.c_void_p),
                 ('blend16a_h', C.c_void_p), ('blend16a_l', C.c_void_p),
                 ('sel_ids', C.c_void_p), ('sel_blend', C.c_void_p), ('sel_nv', C.c_int), ('ft_rec_stride', C.c_int),
-                ('ft_rec', C.c_void_p)]
+                ('ft_rec', C.c_void_p), ('blend16p_h', C.c_void_p), ('blend16p_l', C.c_void_p)]
 
 
 class HbHumorWeights(C.Structure):

@@ -105,7 +105,7 @@ def pack_smplh(asset, num_betas=16):
     }
 
 
-FG_NSLOT = 12          # csrc/lbs_fuseg.cuh: shared-memory slots for skinning transforms, [128 frames][12 floats] each
+FG_NSLOT = 13          # csrc/lbs_fuseg.cuh: shared-memory slots for skinning transforms, [128 frames][12 floats] each
 FG_GPT = 8             # vertex groups per 192-column tile (64 vertices)
 FG_SLOT_BYTES = 128 * 48
 FG_TAB = 4 + 2 * FG_NSLOT      # ints per column tile of ft_tab: n_fresh, n_inc, record bytes, 0, fresh loads, incremental loads
@@ -233,6 +233,13 @@ class LbsModel:
         bh = bs.to(torch.float16)
         self.t['blend16a_h'], self.t['blend16a_l'] = bh.contiguous(), (bs - bh.float()).to(torch.float16).contiguous()
         s.blend16a_h, s.blend16a_l = self.t['blend16a_h'].data_ptr(), self.t['blend16a_l'].data_ptr()
+        # ... and the pose columns alone (features 16..204 -> 189 columns padded to 192) for calls with one shape per >= 32 frames:
+        # template + shape blend are then added per SEQUENCE by the kernel's epilogue, K drops from 256 to 192
+        bp = torch.zeros(packed['v3_ld'], 192, device=self.device)
+        bp[:, :189] = self.t['blend_t'][:, 16:205] * 1024.0
+        ph = bp.to(torch.float16)
+        self.t['blend16p_h'], self.t['blend16p_l'] = ph.contiguous(), (bp - ph.float()).to(torch.float16).contiguous()
+        s.blend16p_h, s.blend16p_l = self.t['blend16p_h'].data_ptr(), self.t['blend16p_l'].data_ptr()
         self.ws_slot = 0
         s.max_depth = packed['max_depth']
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))

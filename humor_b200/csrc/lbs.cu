@@ -718,7 +718,24 @@ __global__ void lbs_pose_bwd_kernel(HbLbsModel m, int N, int fpb, const float* _
   d_trans[(size_t)n * 3] = t[0]; d_trans[(size_t)n * 3 + 1] = t[1]; d_trans[(size_t)n * 3 + 2] = t[2];
 }
 
+// shaped template of every SEQUENCE for the fused dense pass (LbsFusegArgs.vs): out[s][c] = (v_template[c] + sum_l blend[l][c] beta[s][l])
+// * scale, c < 3V, zero in the padding columns.  One shape per frames_per_beta frames: 16 of the GEMM's 206 columns leave the per-frame
+// product (and the fourth k-block with them)
+__global__ void lbs_shape_rows_kernel(HbLbsModel m, int nseq, const float* __restrict__ betas, float scale, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  if (c >= m.v3_ld || s >= nseq) return;
+  float v = 0.f;
+  if (c < 3 * m.num_verts) {
+    v = m.v_template[c];
+#pragma unroll
+    for (int l = 0; l < LBS_NB; ++l) v = fmaf(m.blend[(size_t)l * m.v3_ld + c], __ldg(betas + (size_t)s * LBS_NB + l), v);
+  }
+  out[(size_t)s * m.v3_ld + c] = v * scale;
+}
+
 static const bool g_thread_pose = (getenv("HB_LBS_THREAD") != nullptr);
+static const bool g_no_vs = (getenv("HB_LBS_NO_SHAPE_ROWS") != nullptr);   // A/B: betas stay in the GEMM (K = 256) whatever frames_per_beta is
 static const bool g_no_fold = (getenv("HB_LBS_NO_FOLD") != nullptr);   // A/B: the fused pass adds trans per vertex instead of inside A
 // dense skinning pass: 1 = blend GEMM (umma_gemm3_kernel, v_posed slabs through L2) + lane-per-vertex lbs_skin_apply_kernel (the
 // round-1 default, kept as the form for meshes without group tables and as the A/B partner), 3 (DEFAULT since round 2: 1.06 ms vs
@@ -780,6 +797,9 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
   const bool fuseg = tc && g_skin_form == 3 && (m->flags & HB_LBS_PLANES_TEMPLATE) && m->ft_tab && m->ft_rec && m->ft_rec_stride > 0 &&
                      m->num_groups > 0 && m->ft_nct == cdiv(m->num_groups, 8) && (m->num_verts % 2) == 0 && m->v3_ld % 4 == 0;
   const bool f16x3 = fuseg && g_blend_form == 5 && m->blend16a_h && m->blend16a_l;
+  // one shape per >= 32 frames: template + shape blend per sequence (rows in the form-1 slab, unused on this path), pose columns only
+  const int nseq = cdiv(N, fpb);
+  const bool vsrows = f16x3 && fpb >= 32 && nseq <= TC_SLAB && m->blend16p_h && m->blend16p_l && !g_no_vs;
   // the fused pass is the only reader of A then: its transforms come pre-scaled, and with the translation when that is exact
   const float a_scale = f16x3 ? 0.0009765625f : 1.f;
   const int a_fold = (fuseg && (m->flags & HB_LBS_WEIGHTS_SUM_1) && !g_no_fold) ? 1 : 0;
@@ -798,7 +818,19 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
     fa.nkb16 = f16x3 ? 4 : 0;
     fa.ft_tab = m->ft_tab; fa.ft_rec = static_cast<const unsigned char*>(m->ft_rec); fa.ft_rec_stride = m->ft_rec_stride;
     fa.A = ws.A; fa.trans = a_fold ? nullptr : trans; fa.out = verts;
-    if (f16x3) {
+    fa.vs = nullptr; fa.vs_ld = 0; fa.fpb = fpb;
+    if (vsrows) {
+      // pose columns as fp16 hi + (unscaled) lo planes, K = 192; template + shape blend per sequence, added by the epilogue
+      unsigned short* f16h = reinterpret_cast<unsigned short*>(ws.feat16);
+      unsigned short* f16l = f16h + (size_t)align_up((size_t)N, 64) * 256;
+      lbs_shape_rows_kernel<<<dim3(cdiv(m->v3_ld, 256), nseq), 256, 0, st>>>(*m, nseq, betas, 1024.f, ws.vposed);
+      HB_LAUNCH_CHECK(); ++nl;
+      HB_CUDA(launch_feat_f16(ws.feat, LBS_KF, 205, N, LBS_NB, 3, f16h, f16l, -1, st));
+      ++nl;
+      fa.nkb16 = 3; fa.vs = ws.vposed; fa.vs_ld = m->v3_ld;
+      HB_CUDA(launch_lbs_fuseg(nullptr, nullptr, TC_KF, nullptr, nullptr, TC_KF, m->v3_ld, 0, f16h, m->blend16p_h, f16l, m->blend16p_l, 192,
+                               fa, st));
+    } else if (f16x3) {
       // every column as fp16 hi + (unscaled) lo planes, K = 256: three products per k-block, no tf32 k-blocks
       unsigned short* f16h = reinterpret_cast<unsigned short*>(ws.feat16);
       unsigned short* f16l = f16h + (size_t)align_up((size_t)N, 64) * 256;

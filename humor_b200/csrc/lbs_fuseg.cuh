@@ -56,23 +56,27 @@ constexpr int FG_BN = 192;                          // columns per tile = 64 ver
 constexpr int FG_GPT = 8;                           // vertex groups per tile
 constexpr int FG_G = 8;                             // vertices per group
 constexpr int FG_GC = 3 * FG_G;                     // columns per group
-constexpr int FG_RING = 3;                          // operand entries (40 KB: hi or lo planes of one k-block) in flight: with the per-tile table loads
-                                                    // gone the operand stream paces a tile, and two entries = one k-block exposed every load's latency
+constexpr int FG_RING = 2;                          // operand entries (40 KB: hi or lo planes of one k-block) in flight; a third entry bought nothing
+                                                    // (840 vs 842 us, profiles/r03d vs r03c): the kernel is bound by L2 <-> SM bytes, not by load latency
 constexpr int FG_A_PLANE = UM_BM * 128;             // bytes: 128 rows x 128 B
 constexpr int FG_B_PLANE = FG_BN * 128;
 constexpr int FG_ENTRY = FG_A_PLANE + FG_B_PLANE;   // 40 KB
-constexpr int FG_NSLOT = 12;                        // body_model.FG_NSLOT
+constexpr int FG_NSLOT = 13;                        // body_model.FG_NSLOT
 constexpr int FG_SLOT = UM_BM * 48;                 // [128 frames][12 floats]
 constexpr int FG_EPI_WARPS = 16;                    // 4 per TMEM lane quadrant: two vertex groups of the tile each
-constexpr int FG_STAGE_W = 32 * (FG_GC / 2) * 4;    // bytes per epilogue warp: 32 frame rows x 48 B (half a group per pass), dense
+constexpr int FG_STAGE_W = 32 * FG_GC * 4;          // bytes per epilogue warp: 32 frame rows x 96 B, dense
 constexpr int FG_REC_HEAD = 64;                     // body_model.FG_REC_*: 9 group offsets + padding,
 constexpr int FG_REC_ENTRY = 48;                    //   then { slot byte offset | joint * 12 | 0 | 0 | 8 weights } per entry
 constexpr int FG_REC_MAX = FG_REC_HEAD + FG_REC_ENTRY * 96;
 constexpr int FG_OFF_SLOTS = FG_RING * FG_ENTRY;
 constexpr int FG_OFF_STAGE = FG_OFF_SLOTS + FG_NSLOT * FG_SLOT;
 constexpr int FG_OFF_REC = FG_OFF_STAGE + FG_EPI_WARPS * FG_STAGE_W;
-constexpr int FG_OFF_BARS = FG_OFF_REC + 2 * FG_REC_MAX;
-constexpr int FG_SMEM = FG_OFF_BARS + 128 + 1024;   // + barriers + 1024-byte alignment slack = 231 680 B
+constexpr int FG_VS_ROWS = 5;                       // shaped-template rows (sequences) a 128-frame tile can span: frames_per_beta >= 32
+constexpr int FG_VS_ROW = FG_BN * 4;                // bytes of one row inside a column tile
+constexpr int FG_VS_BUF = FG_VS_ROWS * FG_VS_ROW;
+constexpr int FG_OFF_VS = FG_OFF_REC + 2 * FG_REC_MAX;
+constexpr int FG_OFF_BARS = FG_OFF_VS + 2 * FG_VS_BUF;
+constexpr int FG_SMEM = FG_OFF_BARS + 128 + 1024;   // + barriers + 1024-byte alignment slack = 229 120 B
 constexpr int FG_THREADS = 96 + 32 * FG_EPI_WARPS;   // + TMA warp (operands), MMA warp, TMA warp (transforms + records)
 constexpr int FG_TAB = 4 + 2 * FG_NSLOT;            // ints per column tile of ft_tab
 static_assert(FG_SMEM <= 232448, "lbs_fuseg_kernel: shared memory");
@@ -169,8 +173,13 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             mbar_wait(empty0 + 8 * s, ((g / FG_RING) & 1) ^ 1);
             const uint32_t st = base + s * FG_ENTRY;
             mbar_expect_tx(full0 + 8 * s, FG_ENTRY);
-            tma_load_2d_hint(st, pl ? &tmA16l : &tmA16, full0 + 8 * s, kb * 64, m0, keep);
-            tma_load_2d_hint(st + FG_A_PLANE, pl ? &tmB16l : &tmB16, full0 + 8 * s, kb * 64, n0, keep);
+            if (a.dbg & 4) {
+              tma_load_2d(st, pl ? &tmA16l : &tmA16, full0 + 8 * s, kb * 64, m0);
+              tma_load_2d(st + FG_A_PLANE, pl ? &tmB16l : &tmB16, full0 + 8 * s, kb * 64, n0);
+            } else {
+              tma_load_2d_hint(st, pl ? &tmA16l : &tmA16, full0 + 8 * s, kb * 64, m0, keep);
+              tma_load_2d_hint(st + FG_A_PLANE, pl ? &tmB16l : &tmB16, full0 + 8 * s, kb * 64, n0, keep);
+            }
           }
         }
       }
@@ -192,8 +201,17 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int* ent = tab + 4 + (fresh ? 0 : FG_NSLOT);
         const uint32_t tb = ttf0 + 8 * (tc & 1);
         const uint32_t recb = (uint32_t)tab[2];
-        mbar_expect_tx(tb, (uint32_t)nl * FG_SLOT + recb);
+        // shaped-template rows of the sequences this tile's frames belong to (a.vs; see LbsFusegArgs)
+        int s0 = 0, nvs = 0;
+        if (a.vs) {
+          s0 = m0 / a.fpb;
+          nvs = min(m0 + UM_BM - 1, a.N - 1) / a.fpb - s0 + 1;
+        }
+        mbar_expect_tx(tb, (uint32_t)nl * FG_SLOT + recb + (uint32_t)nvs * FG_VS_ROW);
         bulk_g2s(base + FG_OFF_REC + (uint32_t)(tc & 1) * FG_REC_MAX, a.ft_rec + (size_t)c * a.ft_rec_stride, recb, tb);
+        for (int i = 0; i < nvs; ++i)
+          bulk_g2s(base + FG_OFF_VS + (uint32_t)(tc & 1) * FG_VS_BUF + (uint32_t)i * FG_VS_ROW, a.vs + (size_t)(s0 + i) * a.vs_ld + (size_t)c * FG_BN,
+                   FG_VS_ROW, tb);
         for (int i = 0; i < nl; ++i) {
           const int e = ent[i];
           tma_load_2d(base + FG_OFF_SLOTS + (uint32_t)(e >> 16) * FG_SLOT, &tmT, tb, e & 0xffff, m0);
@@ -264,17 +282,22 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t stg = base + FG_OFF_STAGE + (uint32_t)ew * FG_STAGE_W;             // this warp's staging tile: [32 frames][96 B]
     const uint32_t tsl = base + FG_OFF_SLOTS + (uint32_t)(q * 32 + lane) * 48u;       // this thread's frame inside a slot
-    // staging tile [32 frames][48 B], written lane = frame (eight consecutive rows of the 48-byte stride hit eight different bank
-    // quads), read as float2 number L = 32 it + lane of its 32 x 6 (row L / 6, pair L % 6), it = 0..5: three iterations cover
-    // sixteen rows exactly, so a lane needs three (shared offset, global offset) pairs and adds 16 rows for the second round
-    const uint32_t sw = stg + (uint32_t)lane * 48u;
+    // staging tile, written lane = frame: the six 16-byte chunks of row r sit at ((chunk + ((r >> 2) & 1)) % 6) * 16, which
+    // makes eight consecutive rows of a dense 96-byte stride hit eight different bank quads
+    const uint32_t rot = (uint32_t)(lane >> 2) & 1u;
+    const uint32_t sw0 = stg + (uint32_t)lane * 96u + rot * 16u;                      // chunks 0..4 at sw0 + 16 k
+    const uint32_t sw5 = stg + (uint32_t)lane * 96u + (rot ? 0u : 80u);               // chunk 5
+    // store phase: float2 number L = 32 it + lane of the tile's 32 x 12 (row L / 12, pair L % 12), it = 0..11; three iterations
+    // cover eight rows exactly, so a lane needs three (shared offset, global offset) pairs and adds 8 rows per round
     const int rowf = a.num_verts * 3;                           // floats per output frame
     uint32_t sr3[3];
     int go3[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int L3 = 32 * i + lane, r3 = L3 / 6, j = L3 - 6 * r3;
-      sr3[i] = stg + (uint32_t)(r3 * 48 + j * 8);
+      const int L3 = 32 * i + lane, r3 = L3 / 12, j = L3 - 12 * r3;
+      int ch = (j >> 1) + ((r3 >> 2) & 1);
+      if (ch >= 6) ch -= 6;
+      sr3[i] = stg + (uint32_t)(r3 * 96 + ch * 16 + (j & 1) * 8);
       go3[i] = r3 * rowf + 2 * j;
     }
     int tc = 0;
@@ -289,6 +312,8 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
       const float* Arow = a.A + (size_t)fr * 624;
       const uint32_t rec = base + FG_OFF_REC + (uint32_t)buf * FG_REC_MAX;
+      // this frame's row of the shaped template inside the tile's buffer (lanes of a warp: at most two different rows)
+      const uint32_t vsr = a.vs ? base + FG_OFF_VS + (uint32_t)buf * FG_VS_BUF + (uint32_t)(fr / a.fpb - (r * UM_BM) / a.fpb) * FG_VS_ROW : 0u;
       mbar_wait(tfull0 + 8 * buf, (tc >> 1) & 1);
       mbar_wait(ttf0 + 8 * buf, (tc >> 1) & 1);
       tc_fence_after();
@@ -304,13 +329,20 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       // registers with look-ahead registers and a branch per vertex and joint: 42 % of the issue slots,
       // profiles/r02a_fuseg35_set_full_details.txt; a half-group form at 16 warps doubled the loop overhead instead: r02f_*.)
 #pragma unroll 1
-      for (int gg = 0; gg < 2; ++gg) {
+      for (int gg = 0; gg < ((a.dbg & 2) ? 0 : 2); ++gg) {
         const int gi = h4 * 2 + gg;
         const int g = c * FG_GPT + gi;
         if (g >= a.num_groups) break;                           // warp-uniform
         float p[FG_GC], acc[FG_GC];
         tmem_ld24(trow + buf * FG_BN + gi * FG_GC, p);
         const int nv3 = min(FG_G, a.num_verts - g * FG_G) * 3;  // floats of this group inside the mesh
+        if (a.vs) {                                             // kernel-uniform: + template + shape blend of the frame's sequence
+#pragma unroll
+          for (int k = 0; k < FG_GC / 4; ++k) {
+            const float4 v = ld_shared_v4(vsr + (uint32_t)gi * (FG_GC * 4) + 16u * k);
+            p[4 * k] += v.x; p[4 * k + 1] += v.y; p[4 * k + 2] += v.z; p[4 * k + 3] += v.w;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < FG_GC; ++i) acc[i] = 0.f;
         uint32_t ea = rec + FG_REC_HEAD + ld_shared_u32(rec + 4u * gi) * FG_REC_ENTRY;
@@ -340,38 +372,37 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 #pragma unroll
           for (int i = 0; i < FG_GC; ++i) acc[i] += (i % 3) == 0 ? t0 : ((i % 3) == 1 ? t1 : t2);
         }
-        // two passes of four vertices: park 12 floats (lane = frame), then 5 1/3 row segments of 48 bytes per store instruction
+        // park the group (lane = frame), then 2 2/3 frame rows of 96 bytes per store instruction
+#pragma unroll
+        for (int k = 0; k < 5; ++k) st_shared_v4(sw0 + 16u * k, acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+        st_shared_v4(sw5, acc[20], acc[21], acc[22], acc[23]);
+        __syncwarp();
         float* tb = a.out + (size_t)f0 * rowf + (size_t)g * FG_GC;
-        const bool whole = f0 + 32 <= a.N && nv3 == FG_GC;      // warp-uniform: every row and every column is stored
+        if (a.dbg & 1) continue;
+        if (f0 + 32 <= a.N && nv3 == FG_GC) {                   // warp-uniform: every row and every column is stored
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+          for (int m = 0; m < 4; ++m) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k)
-            st_shared_v4(sw + 16u * k, acc[12 * h + 4 * k], acc[12 * h + 4 * k + 1], acc[12 * h + 4 * k + 2], acc[12 * h + 4 * k + 3]);
-          __syncwarp();
-          if (whole) {
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-#pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                const float2 v = ld_shared_v2(sr3[i] + 768u * m);
-                stcs2(tb + (size_t)(16 * m) * rowf + 12 * h + go3[i], v.x, v.y);
-              }
-            }
-          } else {                                              // ragged last row tile / the mesh's last, partial group
-#pragma unroll 1
-            for (int L = lane; L < 32 * 6; L += 32) {           // (offsets recomputed: no dynamic index into sr3 / go3)
-              const int row = L / 6, j = L - 6 * row;
-              if (f0 + row < a.N) {
-                const float2 v = ld_shared_v2(stg + (uint32_t)(row * 48 + j * 8));
-                float* dst = tb + (size_t)row * rowf + 12 * h + 2 * j;
-                if (12 * h + 2 * j + 1 < nv3) stcs2(dst, v.x, v.y);
-                else if (12 * h + 2 * j < nv3) stcs1(dst, v.x);
-              }
+            for (int i = 0; i < 3; ++i) {
+              const float2 v = ld_shared_v2(sr3[i] + 768u * m);
+              stcs2(tb + (size_t)(8 * m) * rowf + go3[i], v.x, v.y);
             }
           }
-          __syncwarp();
+        } else {                                                // ragged last row tile / the mesh's last, partial group
+#pragma unroll 1
+          for (int L = lane; L < 32 * 12; L += 32) {           // (offsets recomputed: no dynamic index into sr3 / go3)
+            const int row = L / 12, j = L - 12 * row;
+            int ch = (j >> 1) + ((row >> 2) & 1);
+            if (ch >= 6) ch -= 6;
+            if (f0 + row < a.N) {
+              const float2 v = ld_shared_v2(stg + (uint32_t)(row * 96 + ch * 16 + (j & 1) * 8));
+              float* dst = tb + (size_t)row * rowf + 2 * j;
+              if (2 * j + 1 < nv3) stcs2(dst, v.x, v.y);
+              else if (2 * j < nv3) stcs1(dst, v.x);
+            }
+          }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

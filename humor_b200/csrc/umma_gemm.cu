@@ -175,6 +175,7 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
     return cudaErrorInvalidValue;
   if (a.nkb16 < 0 || (a.nkb16 > 0 && (!feat16 || !bt16 || !feat16l || !bt16l || ld16 % 8 || ld16 < 64 * a.nkb16))) return cudaErrorInvalidValue;
   if ((K == 0) == (a.nkb16 <= 0)) return cudaErrorInvalidValue;          // either the tf32 planes or the fp16 planes
+  if (a.vs && (a.fpb < 32 || a.vs_ld % 4 || (reinterpret_cast<uintptr_t>(a.vs) & 15u))) return cudaErrorInvalidValue;
   static int sms = 0, want = 0;
   if (!sms) {
     int dev = 0;
@@ -187,6 +188,8 @@ cudaError_t launch_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf
     const char* w = getenv("HB_LBS_FUSEG_CTAS");
     want = w ? atoi(w) : 0;
   }
+  static const int dbg = getenv("HB_LBS_FUSEG_DBG") ? atoi(getenv("HB_LBS_FUSEG_DBG")) : 0;
+  a.dbg = dbg;
   a.nrt = cdiv(a.N, UM_BM);
   a.nct = cdiv(a.num_groups, FG_GPT);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo, tt, ta16, tb16, ta16l, tb16l;

@@ -31,11 +31,20 @@ struct LbsFusegArgs {
   int nrt, nct;            // row tiles (128 frames), column tiles (64 vertices); set by the launcher
   int nkb16;               // > 0 (blend form 5): this many 64-wide fp16 k-blocks (kind::f16) on hi + lo planes: h.h + l.h + h.l
   int ft_rec_stride;       // bytes per column tile of ft_rec
+  int dbg;                 // measurement switches (HB_LBS_FUSEG_DBG; results are WRONG with any of them): 1 no output stores, 2 no skinning
+                           // at all (the epilogue only hands the TMEM buffer back), 4 operand loads without the L2 hint
   const int* ft_tab;       // [nct][FG_TAB]
   const unsigned char* ft_rec;   // [nct][ft_rec_stride] skinning records (HbLbsModel.ft_rec)
   const float* A;          // [N][52][12] skinning transforms OF THIS PASS: rotation part times the accumulator scale (2^-10 when
                            // the blend planes are pre-scaled for the fp16 range), translation column + trans unless `trans` is set
   const float* trans;      // [N][3] added to every vertex, or nullptr: already inside A
+  // shaped template per SEQUENCE, or nullptr.  HuMoR fits one shape per sub-sequence (frames_per_beta = T), so template + shape
+  // blend is a property of the sequence, not of the frame: with vs set, the GEMM carries the 189 pose columns only (K = 192: three
+  // k-blocks instead of four, a quarter of the operand bytes the kernel is bound by) and the epilogue adds row frame / fpb of
+  // vs [sequences][vs_ld] = (v_template + shapedirs . betas) / accumulator scale, staged per tile by the producer (fpb >= 32)
+  const float* vs;
+  int vs_ld;               // floats per row of vs (multiple of 4)
+  int fpb;                 // frames per sequence
   float* out;              // [N][num_verts][3]
 };
 // bt_* = blend_t hi/lo planes [b_rows][K] (ldb floats per row) WITH the template in column 205 (HB_LBS_PLANES_TEMPLATE; the

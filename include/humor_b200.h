@@ -72,10 +72,10 @@ typedef struct HbLbsModel {
   const float* g_w;        /* [E][8], 16-byte aligned */
   int num_groups;          /* 0: group tables absent */
   /* fused blend + group skinning (csrc/lbs_fuseg.cuh, skin form 3): 192-column tiles = 8 groups; the transforms of a tile's
-     joints live in 12 shared-memory slots that persist across the consecutive column tiles a CTA walks */
+     joints live in 13 shared-memory slots that persist across the consecutive column tiles a CTA walks */
   int ft_nct;              /* column tiles = ceil(num_groups / 8); 0: tables absent */
   const int* g_slot;       /* [E] byte offset of entry e's slot in the tile of its group, or -1: read A from global memory */
-  const int* ft_tab;       /* [ft_nct][28] n_fresh, n_inc, bytes of the tile's record in ft_rec, 0, 12 fresh + 12 incremental
+  const int* ft_tab;       /* [ft_nct][30] n_fresh, n_inc, bytes of the tile's record in ft_rec, 0, 13 fresh + 13 incremental
                               loads (joint*12 | slot << 16) */
   /* blend form 5 (skin form 3 only): blend_t * 2^10, all 208 columns padded to 256, as fp16 hi plane and UNSCALED fp16 lo
      plane (x = h + l) [v3_ld][256] each; NULL: form unavailable */
@@ -93,6 +93,11 @@ typedef struct HbLbsModel {
      16 ints (entry offsets of the tile's 8 groups + end, relative to the tile's first entry; padding), then 48-byte entries
      { slot byte offset or -1, joint*12, 0, 0, 8 weights } - the contents of g_slot / g_joint / g_w in tile order */
   const void* ft_rec;      /* [ft_nct][ft_rec_stride], 16-byte aligned */
+  /* blend form 5 when one shape serves >= 32 frames (frames_per_beta): the 189 POSE columns of blend_t * 2^10 (features 16..204)
+     padded to 192, fp16 hi plane and unscaled lo plane [v3_ld][192]; template and shape blend are then added per sequence.
+     NULL: the kernel keeps all columns in the product (blend16a_*) */
+  const void* blend16p_h;
+  const void* blend16p_l;
 } HbLbsModel;
 #define HB_LBS_PLANES_TEMPLATE 1 /* column 205 of blend_t_hi/lo and blend16a_h/l carries v_template (see above) */
 #define HB_LBS_WEIGHTS_SUM_1 2   /* the skinning weights of every vertex sum to 1 (|sum - 1| < 1e-6): the dense pass may add the

@@ -41,6 +41,7 @@ const std::map<std::string, Thunk>& registry() {
       {"hb::lbs_pose_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_pose_bwd_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(cf, 6), A(cf, 7), A(cf, 8), A(cf, 9), A(int, 10), A(float*, 11), A(float*, 12), A(float*, 13), A(float*, 14))); }},
       {"hb::lbs_skin_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_fwd_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(cf, 3), A(cf, 4), A(ci, 5), A(int, 6), A(float*, 7), A(size_t, 8))); }},
       {"hb::lbs_skin_apply_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_apply_kernel(A(HbLbsModel, 0), A(int, 1), A(int, 2), A(cf, 3), A(cf, 4), A(cf, 5), A(float*, 6))); }},
+      {"hb::lbs_shape_rows_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_shape_rows_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(float, 3), A(float*, 4))); }},
       {"hb::lbs_gather_extra_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_gather_extra_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(float*, 3))); }},
       {"hb::lbs_skin_bwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::lbs_skin_bwd_kernel(A(HbLbsModel, 0), A(int, 1), A(cf, 2), A(cf, 3), A(ci, 4), A(int, 5), A(cf, 6), A(size_t, 7), A(float*, 8), A(float*, 9), A(float*, 10), A(int, 11), A(ci, 12), A(int, 13), A(cf, 14), A(size_t, 15))); }},
       {"hb::rodrigues_fwd_kernel", [](dim3 g, dim3 b, void** a) { RUN(hb_emu::rodrigues_fwd_kernel(A(int, 0), A(cf, 1), A(float*, 2))); }},

@@ -23,7 +23,7 @@ for k in ('v_template', 'blend', 'blend_t', 'j_template', 'j_dirs', 'w_idx', 'w_
 s.ft_nct, s.ft_rec_stride = packed['ft_nct'], packed['ft_rec'].shape[1]
 s.flags = 1 | (2 if packed['w_rows_sum_to_one'] else 0)      # as body_model.LbsModel: template in column 205 of the planes
 planes = torch.zeros(packed['v3_ld'], 224)
-s.blend_t_hi = s.blend_t_lo = s.blend16a_h = s.blend16a_l = planes.data_ptr()
+s.blend_t_hi = s.blend_t_lo = s.blend16a_h = s.blend16a_l = s.blend16p_h = s.blend16p_l = planes.data_ptr()
 s.use_umma, s.max_depth, s.num_groups = 1, packed['max_depth'], packed['num_groups']
 L = _ext.lib()
 ws = torch.empty(L.humor_lbs_workspace_bytes(N) // 4)

@@ -9,7 +9,7 @@ extern "C" {
 long long h_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const float* bt_hi, const float* bt_lo, int ldb, int b_rows,
                       int K, int N, int num_verts, int num_groups, const int* ft_tab, const unsigned char* ft_rec, int ft_rec_stride,
                       const float* A, const float* trans, float* out, int grid, long long* tma_count, const void* feat16,
-                      const void* bt16, int ld16, int nkb16, const void* feat16l, const void* bt16l) {
+                      const void* bt16, int ld16, int nkb16, const void* feat16l, const void* bt16l, const float* vs, int vs_ld, int fpb) {
   CUtensorMap a_hi{feat_hi, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM, 0};
   CUtensorMap a_lo{feat_lo, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldf, 32, UM_BM, 0};
   CUtensorMap b_hi{bt_hi, (unsigned long long)b_rows, (unsigned long long)K, (unsigned long long)ldb, 32, FG_BN, 0};
@@ -20,10 +20,10 @@ long long h_lbs_fuseg(const float* feat_hi, const float* feat_lo, int ldf, const
   CUtensorMap a16l{static_cast<const float*>(feat16l), (unsigned long long)N, 64ull * nkb16, (unsigned long long)ld16, 64, UM_BM, 0, 1};
   CUtensorMap b16l{static_cast<const float*>(bt16l), (unsigned long long)b_rows, 64ull * nkb16, (unsigned long long)ld16, 64, FG_BN, 0, 1};
   LbsFusegArgs a;
-  a.nkb16 = nkb16;
+  a.nkb16 = nkb16; a.dbg = 0;
   a.N = N; a.num_verts = num_verts; a.num_groups = num_groups; a.nrt = cdiv(N, UM_BM); a.nct = cdiv(num_groups, FG_GPT);
   a.ft_tab = ft_tab; a.ft_rec = ft_rec; a.ft_rec_stride = ft_rec_stride;
-  a.A = A; a.trans = trans; a.out = out;
+  a.A = A; a.trans = trans; a.out = out; a.vs = vs; a.vs_ld = vs_ld; a.fpb = fpb;
   tcemu::reset();
   shim::launch(dim3(grid), dim3(FG_THREADS), [&] { lbs_fuseg_kernel(a_hi, a_lo, b_hi, b_lo, tt, a16, b16, a16l, b16l, K, a); });
   if (tma_count) *tma_count = tcemu::g_tma_count;

@@ -35,7 +35,7 @@ def test_struct_sizes_match_header():
     import ctypes as C
     # pointers-only structs: one slot per array entry
     assert C.sizeof(_ext.HbHumorWeights) == 8 * (4 + 4 + 3 + 3 + 4 + 5 + 5 + 4 + 4 + 5 + 20 + 16) + 8 + 8 * 8 + 8 * 10 + 8 * 2
-    assert C.sizeof(_ext.HbLbsModel) == 16 + 8 * 9 + 8 * 2 + 8 + 8 * 3 + 8 * 3 + 8 + 8 * 2 + 8 * 2 + 8 * 2 + 8 + 8
+    assert C.sizeof(_ext.HbLbsModel) == 16 + 8 * 9 + 8 * 2 + 8 + 8 * 3 + 8 * 3 + 8 + 8 * 2 + 8 * 2 + 8 * 2 + 8 + 8 + 8 * 2
 
 
 def test_lbs_model_layout_matches_the_compiled_header(tmp_path):

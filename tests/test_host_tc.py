@@ -57,7 +57,7 @@ def _fuseg_problem(N, seed):
     return p, feat, bt, A, trans, ref
 
 
-def _run_fuseg(H, p, feat, bt, A, trans, grid, f16=False, fold=False):
+def _run_fuseg(H, p, feat, bt, A, trans, grid, f16=False, fold=False, fpb=0):
     """The kernel's contract (csrc/umma_launch.cuh LbsFusegArgs): A arrives with its rotation part times the accumulator scale and,
     with fold, the root translation inside its translation column (trans = NULL) - what the pose kernels write for this pass."""
     N, K, V = feat.shape[0], 224, 6890
@@ -73,7 +73,21 @@ def _run_fuseg(H, p, feat, bt, A, trans, grid, f16=False, fold=False):
     rec = np.ascontiguousarray(p['ft_rec'])
     assert rec.ctypes.data % 16 == 0
     tabs = (N, V, p['num_groups'], P(p['ft_tab']), P(rec), rec.shape[1], P(A), None if fold else P(trans), P(out), grid)
-    if f16:   # blend form 5: every column as fp16 hi + unscaled lo planes (K padded to 256), three products, no tf32 k-blocks
+    if f16 and fpb:   # ... with one shape per fpb frames: pose columns only (K = 192), template + shape blend per sequence
+        nseq = -(-N // fpb)
+        assert all((feat[s * fpb:(s + 1) * fpb, :16] == feat[s * fpb, :16]).all() for s in range(nseq))
+        fp = np.zeros((N, 192), np.float32)
+        fp[:, :189] = feat[:, 16:205]
+        bp = np.zeros((bt.shape[0], 192), np.float32)
+        bp[:, :189] = bt[:, 16:205] * np.float32(1024)
+        vs = np.zeros((nseq, bt.shape[0]), np.float32)
+        vs[:] = (feat[::fpb, :16].astype(np.float64) @ bt[:, :16].astype(np.float64).T + bt[:, 205].astype(np.float64)) * 1024.0
+        f_h, b_h = fp.astype(np.float16), bp.astype(np.float16)
+        f_l, b_l = (fp - f_h.astype(np.float32)).astype(np.float16), (bp - b_h.astype(np.float32)).astype(np.float16)
+        keep = [np.ascontiguousarray(x) for x in (f_h, b_h, f_l, b_l, vs)]
+        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(fh), P(fl), K, bt.shape[0], 0, *tabs, ctypes.byref(ntma), P(keep[0]), P(keep[1]), 192, 3,
+                             P(keep[2]), P(keep[3]), P(keep[4]), bt.shape[0], fpb)
+    elif f16:   # blend form 5: every column as fp16 hi + unscaled lo planes (K padded to 256), three products, no tf32 k-blocks
         fp = np.zeros((N, 256), np.float32)
         fp[:, :K] = feat
         bp = np.zeros((bt.shape[0], 256), np.float32)
@@ -82,10 +96,10 @@ def _run_fuseg(H, p, feat, bt, A, trans, grid, f16=False, fold=False):
         f_l, b_l = (fp - f_h.astype(np.float32)).astype(np.float16), (bp - b_h.astype(np.float32)).astype(np.float16)
         keep = [np.ascontiguousarray(x) for x in (f_h, b_h, f_l, b_l)]
         nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(fh), P(fl), K, bt.shape[0], 0, *tabs, ctypes.byref(ntma), P(keep[0]), P(keep[1]), 256, 4,
-                             P(keep[2]), P(keep[3]))
+                             P(keep[2]), P(keep[3]), None, 0, 1)
     else:
         bh, bl = split_rn(bt)
-        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, *tabs, ctypes.byref(ntma), None, None, 0, 0, None, None)
+        nmma = H.h_lbs_fuseg(P(fh), P(fl), K, P(bh), P(bl), K, bt.shape[0], K, *tabs, ctypes.byref(ntma), None, None, 0, 0, None, None, None, 0, 1)
     return out, nmma, ntma.value
 
 
@@ -99,8 +113,8 @@ def test_fuseg_slot_schedule_is_consistent():
     state = {}                                                   # slot -> joint*12, as left by an incremental walk from tile 0
     for c in range(nct):
         fresh = {int(e) >> 16: int(e) & 0xffff for e in tab[c, 4:4 + tab[c, 0]]}
-        inc = {int(e) >> 16: int(e) & 0xffff for e in tab[c, 16:16 + tab[c, 1]]}
-        assert len(fresh) == tab[c, 0] <= 12 and all(0 <= s < 12 for s in fresh)
+        inc = {int(e) >> 16: int(e) & 0xffff for e in tab[c, 17:17 + tab[c, 1]]}
+        assert len(fresh) == tab[c, 0] <= 13 and all(0 <= s < 13 for s in fresh)
         prev_used = set(state) if c else set()
         assert not (set(inc) & prev_used)                        # a new joint never overwrites a slot tile c-1 may be reading
         kept = {s: j for s, j in state.items() if s in fresh and fresh[s] == j}
@@ -142,7 +156,7 @@ def test_fuseg_kernel_matches_fp64(H, N, grid, fold):
     ent = ntiles * 14 * 2
     tab = p['ft_tab']
     nrt = (N + 127) // 128
-    assert ent + nrt * int(tab[:, 1].sum()) <= ntma <= ent + nrt * int(tab[:, 1].sum()) + (grid + nrt) * 12
+    assert ent + nrt * int(tab[:, 1].sum()) <= ntma <= ent + nrt * int(tab[:, 1].sum()) + (grid + nrt) * 13
 
 
 def test_fuseg_kernel_on_a_mesh_without_locality(H):
@@ -165,7 +179,7 @@ def test_fuseg_kernel_on_a_mesh_without_locality(H):
     asset['weights'] = scattered(2, 3, pool=20)
     rng = np.random.RandomState(4)
     p = pack_smplh(asset, 16)
-    assert p['wk'] == 2 and (p['g_slot'] < 0).mean() > 0.3 and p['ft_tab'][:, 0].max() == 12 and p['ft_rec'] is not None
+    assert p['wk'] == 2 and (p['g_slot'] < 0).mean() > 0.3 and p['ft_tab'][:, 0].max() == 13 and p['ft_rec'] is not None
     N, K = 70, 224
     feat = np.zeros((N, K), np.float32)
     feat[:, :205] = (rng.randn(N, 205) * 0.3).astype(np.float32)
@@ -228,6 +242,23 @@ def test_umma_gemm16_groupnorm_epilogue_and_fp16_planes(H, ks, bn, gsize):
     rec = Ch.astype(np.float32) + Cl.astype(np.float32) / np.float32(2048)
     assert np.abs(rec[:, :nc] - C[:, :nc]).max() <= 3e-7 * max(1.0, np.abs(C[:, :nc]).max())   # the planes carry the fp32 result to 2^-22
     assert np.isnan(C[:, N:]).all() and not Ch[:, N:].any()    # padding columns untouched
+
+
+def test_fuseg_kernel_fp16_pose_columns_with_shape_rows(H):
+    """One shape per 40 frames (HuMoR: per sub-sequence): the GEMM carries the 189 pose columns (three fp16 k-blocks = 36 MMAs per
+    tile), the epilogue adds the sequence's shaped template from the rows the producer staged - a ragged last tile whose frames
+    span four sequences, transforms with the translation folded in."""
+    N, grid, fpb = 140, 3, 40
+    p, feat, bt, A, trans, _ = _fuseg_problem(N, 77)
+    feat[:, :16] = np.repeat(feat[::fpb, :16], fpb, axis=0)[:N]       # one shape per sequence
+    V = 6890
+    vp = feat[:, :208].astype(np.float64) @ p['blend'][:, :3 * V].astype(np.float64) + p['v_template'].astype(np.float64)
+    T = np.einsum('vj,njrc->nvrc', synth.make_smplh_asset()['weights'].astype(np.float64), A.astype(np.float64))
+    ref = np.einsum('nvrc,nvc->nvr', T[..., :3], vp.reshape(N, V, 3)) + T[..., 3] + trans[:, None].astype(np.float64)
+    out, nmma, ntma = _run_fuseg(H, p, feat, bt, A, trans, grid, f16=True, fold=True, fpb=fpb)
+    assert nmma == 2 * 108 * 3 * 4 * 3
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() < 4e-6 * max(1.0, np.abs(ref).max()), np.abs(out - ref).max()
 
 
 def test_fuseg_kernel_fp16_three_products(H):

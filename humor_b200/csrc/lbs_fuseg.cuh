@@ -107,6 +107,7 @@ __device__ __forceinline__ void stcs2(float* p, float x, float y) { __stcs(reint
 __device__ __forceinline__ void stcs1(float* p, float x) { __stcs(p, x); }
 #define HB_EMU_GUARD_ACQ(addr, bytes)
 #define HB_EMU_GUARD_REL(addr)
+#define HB_OPAQUE(x) asm volatile("" : "+r"(x))      // the value lives in a register from here on: not rematerialised
 #else
 using tcemu::tmem_ld24; using tcemu::tmem_ld12;
 static inline void stcs2(float* p, float x, float y) { p[0] = x; p[1] = y; }
@@ -114,6 +115,7 @@ static inline void stcs1(float* p, float x) { p[0] = x; }
 // tests/host: tell the emulation which shared-memory ranges are being read, so that a TMA write into them aborts
 #define HB_EMU_GUARD_ACQ(addr, bytes) tcemu::guard_acquire(addr, bytes)
 #define HB_EMU_GUARD_REL(addr) tcemu::guard_release(addr)
+#define HB_OPAQUE(x)
 #endif
 
 __global__ void __launch_bounds__(FG_THREADS, 1)
@@ -287,19 +289,24 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t rot = (uint32_t)(lane >> 2) & 1u;
     const uint32_t sw0 = stg + (uint32_t)lane * 96u + rot * 16u;                      // chunks 0..4 at sw0 + 16 k
     const uint32_t sw5 = stg + (uint32_t)lane * 96u + (rot ? 0u : 80u);               // chunk 5
-    // store phase: float2 number L = 32 it + lane of the tile's 32 x 12 (row L / 12, pair L % 12), it = 0..11; three iterations
-    // cover eight rows exactly, so a lane needs three (shared offset, global offset) pairs and adds 8 rows per round
+    // store phase: a lane reads float2 number P = 32 it + lane of the tile's PHYSICAL 32 x 12 (contiguous 256 bytes per instruction:
+    // conflict-free), which is row P / 12, chunk ((P % 12) / 2 - rot(row)) mod 6 of the group; three iterations cover eight rows
+    // exactly, so a lane needs three (shared offset, global offset) pairs and adds 8 rows per round
     const int rowf = a.num_verts * 3;                           // floats per output frame
     uint32_t sr3[3];
     int go3[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int L3 = 32 * i + lane, r3 = L3 / 12, j = L3 - 12 * r3;
-      int ch = (j >> 1) + ((r3 >> 2) & 1);
-      if (ch >= 6) ch -= 6;
-      sr3[i] = stg + (uint32_t)(r3 * 96 + ch * 16 + (j & 1) * 8);
-      go3[i] = r3 * rowf + 2 * j;
+      const int P3 = 32 * i + lane, r3 = P3 / 12, pos = P3 - 12 * r3;
+      int k = (pos >> 1) - ((r3 >> 2) & 1);
+      if (k < 0) k += 6;
+      sr3[i] = stg + (uint32_t)P3 * 8u;
+      go3[i] = r3 * rowf + 4 * k + 2 * (pos & 1);
     }
+    // (the compiler otherwise re-derives these shared-memory addresses from %cgaid inside the joint loop: an S2R on the critical
+    // path of every transform load, profiles/r03f)
+    uint32_t tsl_ = tsl, sw0_ = sw0, sw5_ = sw5;
+    HB_OPAQUE(tsl_); HB_OPAQUE(sw0_); HB_OPAQUE(sw5_); HB_OPAQUE(sr3[0]); HB_OPAQUE(sr3[1]); HB_OPAQUE(sr3[2]);
     int tc = 0;
     for (int t = t_begin; t < t_end; ++t, ++tc) {
       const int buf = tc & 1;
@@ -353,7 +360,7 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           const float4 wa = ld_shared_v4(ea + 16u), wb = ld_shared_v4(ea + 32u);
           float4 r0, r1, r2;
           if (so >= 0) {
-            r0 = ld_shared_v4(tsl + (uint32_t)so); r1 = ld_shared_v4(tsl + (uint32_t)so + 16u); r2 = ld_shared_v4(tsl + (uint32_t)so + 32u);
+            r0 = ld_shared_v4(tsl_ + (uint32_t)so); r1 = ld_shared_v4(tsl_ + (uint32_t)so + 16u); r2 = ld_shared_v4(tsl_ + (uint32_t)so + 32u);
           } else {                                              // joint without a slot in this tile (rare): from L1/L2
             const float4* ap = reinterpret_cast<const float4*>(Arow + ld_shared_u32(ea + 4u));
             r0 = __ldg(ap); r1 = __ldg(ap + 1); r2 = __ldg(ap + 2);
@@ -374,8 +381,8 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         // park the group (lane = frame), then 2 2/3 frame rows of 96 bytes per store instruction
 #pragma unroll
-        for (int k = 0; k < 5; ++k) st_shared_v4(sw0 + 16u * k, acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
-        st_shared_v4(sw5, acc[20], acc[21], acc[22], acc[23]);
+        for (int k = 0; k < 5; ++k) st_shared_v4(sw0_ + 16u * k, acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+        st_shared_v4(sw5_, acc[20], acc[21], acc[22], acc[23]);
         __syncwarp();
         float* tb = a.out + (size_t)f0 * rowf + (size_t)g * FG_GC;
         if (a.dbg & 1) continue;

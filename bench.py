@@ -339,30 +339,41 @@ def lbs_roofline(mo, B, T, dev, hbm_peak, peak_kind):
         for _ in range(3):
             lbs(m, ro, pb, be, tr, T, None, True, False, 73)
         torch.cuda.synchronize()
+        import ctypes as C
+        from humor_b200 import _ext
+        L = _ext.lib()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10
+        # the dominant kernel (lbs_fuseg_kernel) between its own event pair, recorded by the library on the launching stream
+        # (humor_lbs_fuseg_timing); the whole call (pose kernel, fp16 planes, shaped templates, joint gather, wrapper) around it
+        L.humor_lbs_fuseg_timing(1, None, None)
         e0.record()
         for _ in range(reps):
             lbs(m, ro, pb, be, tr, T, None, True, False, 73)
         e1.record()
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    achieved = N * LBS_BYTES_FWD / (ms * 1e-3) / 1e9
-    import ctypes as C
-    from humor_b200 import _ext
+        kms, kn = C.c_float(0.0), C.c_int(0)
+        L.humor_lbs_fuseg_timing(0, C.byref(kms), C.byref(kn))
+    ms_call = e0.elapsed_time(e1) / reps
     us, ub = C.c_int(0), C.c_int(0)
-    _ext.lib().humor_lbs_forms_used(C.byref(us), C.byref(ub))
+    L.humor_lbs_forms_used(C.byref(us), C.byref(ub))
+    fused_timed = us.value == 3 and kn.value == reps
+    ms = kms.value / kn.value if fused_timed else ms_call       # forms without the fused kernel: the whole call
+    achieved = N * LBS_BYTES_FWD / (ms * 1e-3) / 1e9
     if (us.value, ub.value) != (1, 1):          # the fused kernel (humor_lbs_configure skin form 3)
-        name = ('dense LBS forward: lbs_pose_kernel + lbs_fuseg_kernel (persistent tcgen05 blend + group skinning' +
-                (', fp16 hi/lo planes)' if ub.value == 5 else ', 3xTF32 planes)'))
+        name = ('lbs_fuseg_kernel, the dominant kernel of the dense LBS forward (persistent tcgen05 blend + group skinning' +
+                (', fp16 hi/lo planes' if ub.value == 5 else ', 3xTF32 planes') + '; all vertices of every frame out)')
         traffic, tsrc = None, None
         if (us.value, ub.value) == (3, 5):
-            # dram__bytes_read.sum + dram__bytes_write.sum of lbs_fuseg_kernel (16-warp epilogue), ncu --set full of one 15 360-frame launch
-            # (402.4 MB read + 1 259.0 MB written; the algorithmic 1 288.6 MB are 94 % output vertices)
-            traffic, tsrc = 1661.4e6 * N / 15360.0, 'profiles/r02g_fuseg35_set_full_details.txt (gpurun_out/r02g_fuseg35_set_full.ncu-rep)'
+            # dram__bytes_read.sum + dram__bytes_write.sum of lbs_fuseg_kernel, ncu --set full of one 15 360-frame launch
+            # (306.0 MB read + 1 262.5 MB written = 1.22 x the algorithmic 1 288.6 MB, which are 94 % output vertices)
+            traffic, tsrc = 1568.6e6 * N / 15360.0, 'profiles/r03g_fuseg35_set_full_details.txt (gpurun_out/r03g_fuseg35_set_full.ncu-rep)'
         return {'kernel': name, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'peak_source': peak_kind, 'unit': 'GB/s',
-                'frac': achieved / hbm_peak, 'traffic': traffic, 'traffic_source': tsrc, 'ms_per_launch': ms, 'frames_per_launch': N,
-                'algorithmic_bytes_per_frame': LBS_BYTES_FWD, 'forms_used': [us.value, ub.value]}
+                'frac': achieved / hbm_peak, 'traffic': traffic, 'traffic_source': tsrc, 'ms_per_launch': ms,
+                'timed': ('CUDA event pair around the kernel on its launching stream (humor_lbs_fuseg_timing), ' + str(kn.value) + ' launches'
+                          if fused_timed else 'CUDA events around the whole humor_lbs_fwd call'),
+                'ms_dense_forward_call': ms_call, 'frac_dense_forward_call': N * LBS_BYTES_FWD / (ms_call * 1e-3) / 1e9 / hbm_peak,
+                'frames_per_launch': N, 'algorithmic_bytes_per_frame': LBS_BYTES_FWD, 'forms_used': [us.value, ub.value]}
     return {'kernel': 'dense LBS forward: lbs_pose_kernel + per 512-frame slab umma_gemm3_kernel<128,BIAS> (tcgen05 blend) + '
                       'lbs_skin_apply_kernel', 'bound': 'hbm', 'achieved': achieved,
             'peak': hbm_peak, 'peak_source': peak_kind, 'unit': 'GB/s', 'frac': achieved / hbm_peak,

@@ -106,7 +106,7 @@ EXPORTS = ['humor_lbs_workspace_bytes', 'humor_lbs_fwd', 'humor_lbs_bwd', 'humor
            'humor_rollout_fwd', 'humor_rollout_bwd', 'humor_rodrigues_fwd', 'humor_rodrigues_bwd',
            'humor_mat2aa_fwd', 'humor_mat2aa_bwd', 'humor_fit_losses', 'humor_gmm_nll', 'humor_b200_version',
            'humor_umma_gemm', 'humor_umma_gemm_workspace_bytes', 'humor_chamfer_fwd', 'humor_chamfer_bwd', 'humor_lbs_configure', 'humor_lbs_forms_used',
-           'humor_umma_gemm16', 'humor_umma_gemm16_workspace_bytes', 'humor_chain_debug', 'humor_cam2prior_fwd', 'humor_cam2prior_bwd', 'humor_rollout_outputs_fwd', 'humor_rollout_outputs_bwd', 'humor_gmm_workspace_bytes', 'humor_gmm_nll_ws', 'humor_rollout_bwd_started_wait', 'humor_lbs_set_fuseg_ctas']
+           'humor_umma_gemm16', 'humor_umma_gemm16_workspace_bytes', 'humor_chain_debug', 'humor_cam2prior_fwd', 'humor_cam2prior_bwd', 'humor_rollout_outputs_fwd', 'humor_rollout_outputs_bwd', 'humor_gmm_workspace_bytes', 'humor_gmm_nll_ws', 'humor_rollout_bwd_started_wait', 'humor_lbs_set_fuseg_ctas', 'humor_lbs_fuseg_timing']
 
 _LIB = None
 
@@ -168,6 +168,8 @@ def lib():
     L.humor_rollout_bwd_started_wait.argtypes = [vp]
     L.humor_lbs_set_fuseg_ctas.restype = ci
     L.humor_lbs_set_fuseg_ctas.argtypes = [ci]
+    L.humor_lbs_fuseg_timing.restype = ci
+    L.humor_lbs_fuseg_timing.argtypes = [ci, C.POINTER(C.c_float), C.POINTER(ci)]
     L.humor_lbs_configure.restype = ci
     L.humor_lbs_configure.argtypes = [ci, ci, ci]
     L.humor_lbs_forms_used.restype = ci

@@ -779,6 +779,30 @@ extern "C" int humor_lbs_forms_used(int* skin_form, int* blend_form) {
   return HB_OK;
 }
 
+// measurement: CUDA events around the fused kernel of the next dense calls, on the stream it is launched on (eager calls only: an
+// event pair cannot be timed inside a stream capture)
+static int g_time_fuseg = 0, g_time_count = 0;
+static cudaEvent_t g_time_ev[2] = {nullptr, nullptr};
+static float g_time_ms = 0.f;
+static bool g_time_open = false;
+static void fuseg_time_collect() {
+  if (!g_time_open) return;
+  float ms = 0.f;
+  if (cudaEventSynchronize(g_time_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, g_time_ev[0], g_time_ev[1]) == cudaSuccess) {
+    g_time_ms += ms; ++g_time_count;
+  }
+  g_time_open = false;
+}
+extern "C" int humor_lbs_fuseg_timing(int enable, float* ms_sum, int* launches) {
+  fuseg_time_collect();
+  if (ms_sum) *ms_sum = g_time_ms;
+  if (launches) *launches = g_time_count;
+  if (enable && !g_time_ev[0] && (cudaEventCreate(&g_time_ev[0]) != cudaSuccess || cudaEventCreate(&g_time_ev[1]) != cudaSuccess)) return (int)cudaErrorUnknown;
+  if (enable != g_time_fuseg) { g_time_ms = 0.f; g_time_count = 0; }
+  g_time_fuseg = enable ? 1 : 0;
+  return HB_OK;
+}
+
 extern "C" size_t humor_lbs_workspace_bytes(int N) { return lbs_carve(nullptr, N).total * sizeof(float); }
 
 extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* root_orient, const float* pose_body,
@@ -803,14 +827,15 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
   // the fused pass is the only reader of A then: its transforms come pre-scaled, and with the translation when that is exact
   const float a_scale = f16x3 ? 0.0009765625f : 1.f;
   const int a_fold = (fuseg && (m->flags & HB_LBS_WEIGHTS_SUM_1) && !g_no_fold) ? 1 : 0;
+  const bool tf32_planes = tc && !f16x3;        // the fp16 forms read their own planes (feat_f16_kernel): 27 MB of tf32 planes not written
   if (m->depth && m->child_start && !g_thread_pose)
     lbs_pose_warp_kernel<<<cdiv(N, PW), PW * 32, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
                                                          need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
-                                                         tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr, a_scale, a_fold);
+                                                         tf32_planes ? ws.feat_hi : nullptr, tf32_planes ? ws.feat_lo : nullptr, a_scale, a_fold);
   else
     lbs_pose_kernel<<<cdiv(N, 64), 64, 0, st>>>(*m, N, fpb, root_orient, pose_body, betas, trans,
                                                need_skin ? ws.feat : nullptr, need_skin ? ws.A : nullptr, joints, njo,
-                                               tc ? ws.feat_hi : nullptr, tc ? ws.feat_lo : nullptr, a_scale, a_fold);
+                                               tf32_planes ? ws.feat_hi : nullptr, tf32_planes ? ws.feat_lo : nullptr, a_scale, a_fold);
   HB_LAUNCH_CHECK(); ++nl;
   if (fuseg) {
     LbsFusegArgs fa;
@@ -828,8 +853,10 @@ extern "C" int humor_lbs_fwd(const HbLbsModel* m, int N, int fpb, const float* r
       HB_CUDA(launch_feat_f16(ws.feat, LBS_KF, 205, N, LBS_NB, 3, f16h, f16l, -1, st));
       ++nl;
       fa.nkb16 = 3; fa.vs = ws.vposed; fa.vs_ld = m->v3_ld;
+      if (g_time_fuseg) { fuseg_time_collect(); HB_CUDA(cudaEventRecord(g_time_ev[0], st)); }
       HB_CUDA(launch_lbs_fuseg(nullptr, nullptr, TC_KF, nullptr, nullptr, TC_KF, m->v3_ld, 0, f16h, m->blend16p_h, f16l, m->blend16p_l, 192,
                                fa, st));
+      if (g_time_fuseg) { HB_CUDA(cudaEventRecord(g_time_ev[1], st)); g_time_open = true; }
     } else if (f16x3) {
       // every column as fp16 hi + (unscaled) lo planes, K = 256: three products per k-block, no tf32 k-blocks
       unsigned short* f16h = reinterpret_cast<unsigned short*>(ws.feat16);

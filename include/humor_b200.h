@@ -90,8 +90,9 @@ typedef struct HbLbsModel {
   int sel_nv;
   int ft_rec_stride;       /* bytes per column tile of ft_rec (multiple of 16, <= 64 + 48 * 96); 0: records absent */
   /* skin form 3: per column tile one contiguous skinning record, bulk-copied into shared memory by the kernel's producer:
-     16 ints (entry offsets of the tile's 8 groups + end, relative to the tile's first entry; padding), then 48-byte entries
-     { slot byte offset or -1, joint*12, 0, 0, 8 weights } - the contents of g_slot / g_joint / g_w in tile order */
+     16 ints (entry offsets of the tile's 8 groups + end, relative to the tile's first entry; bytes 36..43: per group the number
+     of leading entries without a slot; padding), then 48-byte entries { slot byte offset or -1, joint*12, 0, 0, 8 weights } - the
+     contents of g_slot / g_joint / g_w in tile order, within a group the slot-less entries first */
   const void* ft_rec;      /* [ft_nct][ft_rec_stride], 16-byte aligned */
   /* blend form 5 when one shape serves >= 32 frames (frames_per_beta): the 189 POSE columns of blend_t * 2^10 (features 16..204)
      padded to 192, fp16 hi plane and unscaled lo plane [v3_ld][192]; template and shape blend are then added per sequence.
@@ -130,6 +131,11 @@ int humor_lbs_forms_used(int* skin_form, int* blend_form);
 /* CTAs of the fused dense forward from now on (0 = one persistent CTA per SM, the default).  More CTAs than SMs = shorter chunks of
  * the tile list per CTA: a pass queued on a second stream then fills the SMs other kernels leave idle instead of holding the chip. */
 int humor_lbs_set_fuseg_ctas(int n);
+/* Measurement: with enable != 0 the library brackets the fused kernel (lbs_fuseg_kernel, the dominant kernel of the dense forward) of
+ * every following EAGER dense call with a CUDA event pair on the stream it is launched on.  Each call of this function first
+ * collects the pending pair and returns the accumulated milliseconds / number of launches since timing was switched on; switching
+ * it off (or on again) resets them.  Not for use while a stream capture is in progress. */
+int humor_lbs_fuseg_timing(int enable, float* ms_sum, int* launches);
 /* Reverse mode of the above (what autograd does through smplx in the reference).  d_verts follows the
  * same vlist convention; d_betas is per frame [N][16] (the caller reduces over frames_per_beta). */
 int humor_lbs_bwd(const HbLbsModel* m, int N, int frames_per_beta, const float* root_orient,

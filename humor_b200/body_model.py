@@ -160,9 +160,8 @@ def fuseg_records(g_start, g_joint, g_slot, g_w, num_groups, ft_tab, gpt=FG_GPT)
     shared-memory latency, warp-uniformly (the same entries straight from global memory missed the 28 KB of L1 the kernel
     leaves 3 times out of 4: 41 % of all stall cycles, profiles/r02g_fuseg35_set_full_details.txt).
 
-    record = 16 ints (offsets of the tile's 8 groups + end, in entries relative to the tile's first entry; 8 bytes = per group the
-    number of leading entries without a slot; padding) followed by 48-byte entries: slot byte offset (or -1) | joint * 12 | 0 | 0 |
-    the 8 weights of the group's vertices; within a group the slot-less entries come first.
+    record = 16 ints (offsets of the tile's 8 groups + end, in entries relative to the tile's first entry; padding) followed by
+    48-byte entries: slot byte offset (or -1) | joint * 12 | 0 | 0 | the 8 weights of the group's vertices.
     Returns a uint8 array [nct][stride] (stride = the longest record, a multiple of 16) and writes every tile's byte count into
     ft_tab[:, 2].  None when a tile has more entries than a record buffer holds (the dispatcher then takes skin form 1)."""
     nct = ft_tab.shape[0]
@@ -179,19 +178,9 @@ def fuseg_records(g_start, g_joint, g_slot, g_w, num_groups, ft_tab, gpt=FG_GPT)
         e0, e1 = int(begs[c]), int(ends[c])
         for i in range(gpt + 1):
             rec[c, i] = int(gs[min(c * gpt + i, num_groups)]) - e0
-        # entries of a group in the order the kernel walks them: the ones WITHOUT a slot first (their count per group in bytes
-        # 36..43 of the header: the epilogue prefetches those transform rows into L1 before it reads the group's accumulators)
-        order = []
-        for i in range(gpt):
-            a, b = int(gs[min(c * gpt + i, num_groups)]), int(gs[min(c * gpt + i + 1, num_groups)])
-            miss = [e for e in range(a, b) if g_slot[e] < 0]
-            order += miss + [e for e in range(a, b) if g_slot[e] >= 0]
-            rec[c, 9 + i // 4] |= min(len(miss), 255) << (8 * (i % 4))
-        order = np.asarray(order, np.int64)
         body = rec[c, FG_REC_HEAD // 4:FG_REC_HEAD // 4 + 12 * (e1 - e0)].reshape(e1 - e0, 12)
-        if len(order):
-            body[:, 0], body[:, 1] = g_slot[order], g_joint[order]
-            body[:, 4:12] = gw[order]
+        body[:, 0], body[:, 1] = g_slot[e0:e1], g_joint[e0:e1]
+        body[:, 4:12] = gw[e0:e1]
         ft_tab[c, 2] = FG_REC_HEAD + FG_REC_ENTRY * (e1 - e0)
     return rec.view(np.uint8).reshape(nct, stride)
 

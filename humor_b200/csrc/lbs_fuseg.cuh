@@ -105,7 +105,6 @@ __device__ __forceinline__ void tmem_ld12(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void stcs2(float* p, float x, float y) { __stcs(reinterpret_cast<float2*>(p), make_float2(x, y)); }
 __device__ __forceinline__ void stcs1(float* p, float x) { __stcs(p, x); }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #define HB_EMU_GUARD_ACQ(addr, bytes)
 #define HB_EMU_GUARD_REL(addr)
 #define HB_OPAQUE(x) asm volatile("" : "+r"(x))      // the value lives in a register from here on: not rematerialised
@@ -113,7 +112,6 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 using tcemu::tmem_ld24; using tcemu::tmem_ld12;
 static inline void stcs2(float* p, float x, float y) { p[0] = x; p[1] = y; }
 static inline void stcs1(float* p, float x) { p[0] = x; }
-static inline void prefetch_l1(const void*) {}
 // tests/host: tell the emulation which shared-memory ranges are being read, so that a TMA write into them aborts
 #define HB_EMU_GUARD_ACQ(addr, bytes) tcemu::guard_acquire(addr, bytes)
 #define HB_EMU_GUARD_REL(addr) tcemu::guard_release(addr)
@@ -343,14 +341,6 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int g = c * FG_GPT + gi;
         if (g >= a.num_groups) break;                           // warp-uniform
         float p[FG_GC], acc[FG_GC];
-        uint32_t ea = rec + FG_REC_HEAD + ld_shared_u32(rec + 4u * gi) * FG_REC_ENTRY;
-        // joints of this group that found no slot (rare; the record lists them first): their transform rows into L1 now, so that the
-        // three loads in the loop below do not pay an L2 round trip each - 16 % of all samples before (profiles/r03g)
-        const uint32_t nmiss = (ld_shared_u32(rec + 36u + 4u * (uint32_t)(gi >> 2)) >> (8 * (gi & 3))) & 0xffu;
-        for (uint32_t i = 0; i < nmiss; ++i) {                  // warp-uniform
-          const float* ap = Arow + ld_shared_u32(ea + i * FG_REC_ENTRY + 4u);
-          prefetch_l1(ap); prefetch_l1(ap + 8);
-        }
         tmem_ld24(trow + buf * FG_BN + gi * FG_GC, p);
         const int nv3 = min(FG_G, a.num_verts - g * FG_G) * 3;  // floats of this group inside the mesh
         if (a.vs) {                                             // kernel-uniform: + template + shape blend of the frame's sequence
@@ -362,6 +352,7 @@ lbs_fuseg_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
 #pragma unroll
         for (int i = 0; i < FG_GC; ++i) acc[i] = 0.f;
+        uint32_t ea = rec + FG_REC_HEAD + ld_shared_u32(rec + 4u * gi) * FG_REC_ENTRY;
         const uint32_t ee = rec + FG_REC_HEAD + ld_shared_u32(rec + 4u * gi + 4u) * FG_REC_ENTRY;
         int so = (int)ld_shared_u32(ea);                        // warp-uniform, fetched one entry ahead (the read behind the last
 #pragma unroll 1                                                // entry stays inside the record buffer and is never used)

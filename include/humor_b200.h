@@ -90,9 +90,8 @@ typedef struct HbLbsModel {
   int sel_nv;
   int ft_rec_stride;       /* bytes per column tile of ft_rec (multiple of 16, <= 64 + 48 * 96); 0: records absent */
   /* skin form 3: per column tile one contiguous skinning record, bulk-copied into shared memory by the kernel's producer:
-     16 ints (entry offsets of the tile's 8 groups + end, relative to the tile's first entry; bytes 36..43: per group the number
-     of leading entries without a slot; padding), then 48-byte entries { slot byte offset or -1, joint*12, 0, 0, 8 weights } - the
-     contents of g_slot / g_joint / g_w in tile order, within a group the slot-less entries first */
+     16 ints (entry offsets of the tile's 8 groups + end, relative to the tile's first entry; padding), then 48-byte entries
+     { slot byte offset or -1, joint*12, 0, 0, 8 weights } - the contents of g_slot / g_joint / g_w in tile order */
   const void* ft_rec;      /* [ft_nct][ft_rec_stride], 16-byte aligned */
   /* blend form 5 when one shape serves >= 32 frames (frames_per_beta): the 189 POSE columns of blend_t * 2^10 (features 16..204)
      padded to 192, fp16 hi plane and unscaled lo plane [v3_ld][192]; template and shape blend are then added per sequence.

@@ -14,6 +14,8 @@ the Stage-III closure (motion_optimizer.py:514-608) is re-planned around the nat
 L-BFGS itself is ``torch.optim.LBFGS`` with strong-Wolfe line search exactly as in the reference
 (:24,:461-478) — moving it onto the device is the scope table's next row.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -22,6 +24,10 @@ from .body_model import KEYPT_VERTS, lbs
 from .fitting_loss import FittingLoss, SMPL2OP
 from .fitting_utils import OP_EDGE_LIST, OP_IGNORE_JOINTS, compute_cam2prior, parse_floor_plane
 from .transforms import batch_rodrigues, rotation_matrix_to_angle_axis
+
+# CTAs per SM of the dense vertex pass queued behind the reverse decoder chain: short chunks of the tile list that the
+# hardware scheduler slots into the SMs the chain leaves idle.  8 was measured (profiles/r02x_*); HB_DENSE_CTAS_PER_SM for A/B runs.
+_DENSE_CTAS_PER_SM = int(os.environ.get('HB_DENSE_CTAS_PER_SM', '8'))
 
 LINE_SEARCH = 'strong_wolfe'
 J_BODY = 21
@@ -253,7 +259,7 @@ class MotionOptimizer():
         sms = torch.cuda.get_device_properties(v.device).multi_processor_count if v.is_cuda else 148
         with torch.cuda.stream(side), torch.no_grad():
             model.ws_slot = 1
-            L.humor_lbs_set_fuseg_ctas(8 * sms if after_reverse_chain_launch else 0)
+            L.humor_lbs_set_fuseg_ctas(_DENSE_CTAS_PER_SM * sms if after_reverse_chain_launch else 0)
             try:
                 lbs_dense_into(model, ro, pb, be, tr, T, v)
             finally:

@@ -100,3 +100,31 @@ def test_configure_rejects_bad_and_removed_values():
     assert L.humor_lbs_configure(0, 0, 0) == 0
     a = forms_used()
     assert L.humor_lbs_configure(*DEFAULT, 0) == 0 and a is not None
+
+
+def test_shaped_template_path_matches_oracle_and_the_all_columns_path(bm):
+    """One shape per T >= 32 frames (what MotionOptimizer passes: frames_per_beta = T): template + shape blend are added per SEQUENCE
+    by the fused kernel's epilogue and the GEMM carries the 189 pose columns only (lbs_shape_rows_kernel + K = 192; five launches).
+    Same vertices as the oracle, and as the all-columns path (K = 256, four launches) that a per-frame betas call takes - a ragged
+    last row tile, a 128-frame tile that spans four sequences."""
+    from humor_b200.body_model import lbs
+    from oracle.smplh_lbs import OracleBodyModel
+    B, T = 7, 40
+    N = B * T
+    ro, pb, _, tr = rand_pose(N, 9)
+    be = torch.tensor((np.random.RandomState(10).randn(B, 16) * 0.7).astype(np.float32)).cuda()
+    be_rep = be.repeat_interleave(T, 0).contiguous()
+    ob = OracleBodyModel(synth.make_smplh_asset(), use_vtx_selector=True)
+    o = ob(root_orient=ro.cpu(), pose_body=pb.cpu(), betas=be_rep.cpu(), trans=tr.cpu())
+    configure(*DEFAULT)
+    with torch.no_grad():
+        n0 = _ext.LaunchCounter.total
+        v, _, J = lbs(bm.lbs_model, ro, pb, be, tr, T, None, True, False, 73)
+        n1 = _ext.LaunchCounter.total
+        v2, _, J2 = lbs(bm.lbs_model, ro, pb, be_rep, tr, 1, None, True, False, 73)
+        n2 = _ext.LaunchCounter.total
+    torch.cuda.synchronize()
+    assert forms_used() == DEFAULT
+    assert (n1 - n0, n2 - n1) == (5, 4)                  # pose, [shaped templates,] fp16 feature planes, fused kernel, joint gather
+    assert torch.isfinite(v).all() and float((v.cpu() - o.v).abs().max()) < 2e-5 and float((J.cpu() - o.Jtr).abs().max()) < 2e-5
+    assert not torch.equal(v, v2) and float((v - v2).abs().max()) < 5e-6

@@ -13,26 +13,27 @@
 // Plan of one CTA (one per SM, 608 threads):
 //   tiles   128 frames x 192 columns (= 64 vertices = 8 groups), walked ROW-major in one contiguous chunk per CTA: ~88
 //           consecutive column tiles of the same 128 frames, so the frames' transforms stay on the SM
-//   warp 0  TMA producer of the operand ring: 3 entries of 40 KB = one A plane (128 x 32 floats) + one B plane (192 x 32);
+//   warp 0  TMA producer of the operand ring: 2 entries of 40 KB = one A plane (128 x 32 floats) + one B plane (192 x 32);
 //           a k-block takes two entries (hi planes, lo planes); gated by the ring only, L2 evict_last hint (every CTA re-reads
 //           the planes while 1.3 GB of output stream through the L2 evict-first)
 //   warp 1  tcgen05.mma issuer; a tile's k-blocks accumulate into ONE of two 192-column TMEM buffers (K = 224: no
 //           promotion chunks needed), so tile i+1's MMAs run under tile i's epilogue
 //   warp 18 TMA producer, gated by the epilogue's progress, of (a) the 3x4 transforms of the joints the tile is skinned to, as
-//           [128 frames][12 floats] boxes cut from A[N][52*12] into 12 shared-memory slots under the host's static schedule
+//           [128 frames][12 floats] boxes cut from A[N][52*12] into 13 shared-memory slots under the host's static schedule
 //           (body_model.fuseg_tables): a joint keeps its slot while consecutive tiles need it, so a tile loads ~1 new slot (6 KB)
 //           instead of ~6; (b) the tile's skinning RECORD (group offsets, per entry slot | joint | 8 weights: HbLbsModel.ft_rec)
 //           with one bulk copy into one of two record buffers - the epilogue reads joint lists and weights at shared-memory
 //           latency (read straight from global memory they missed the 28 KB of L1 this kernel leaves 3 times out of 4 and made
-//           up 41 % of all stall cycles: profiles/r02g_fuseg35_set_full_details.txt)
+//           up 41 % of all stall cycles: profiles/r02g_fuseg35_set_full_details.txt); (c) with LbsFusegArgs.vs (one shape per
+//           >= 32 frames) the rows of the shaped template [sequences][3V] that the tile's frames belong to (<= 5 x 768 B)
 //   warps 2..17 epilogue: TMEM lane quadrant q = warp % 4, column quarter (warp - 2) / 4 -> 2 groups each.  Per group:
 //           tcgen05.ld 24 columns (8 vertices of the thread's frame; the template rides in the GEMM, column 205 of the planes,
 //           and the 2^-10 scale-back / the root translation sit in the transforms the pose kernel wrote for this pass), skin
-//           with the group's joint list (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), then in
-//           two passes of four vertices: park 12 floats in a per-warp staging tile (3 x STS.128 at a dense 48-byte row:
-//           conflict-free) and write 5 1/3 row segments of 48 bytes per store instruction with all 32 lanes (a lane = frame
-//           store would touch 32 different lines per instruction; a whole-group tile would cost 24 KB more shared memory,
-//           which the third ring entry needs).
+//           with the group's joint list (3 x LDS.128 per joint from the slot, conflict-free: 48-byte frame stride), park
+//           the 24 floats in a per-warp staging tile (6 x STS.128, chunks rotated by one for rows 4..7 mod 8: conflict-
+//           free at a dense 96-byte row) and write 2 2/3 frame rows of 96 bytes per store instruction with all 32 lanes,
+//           reading the tile as contiguous 256-byte pieces (a lane = frame store would touch 32 different lines per
+//           instruction).  With LbsFusegArgs.vs the shaped template of the frame's sequence is added to the accumulators first.
 //   fp16x3  (blend form 5, the default) EVERY column as fp16 hi + lo planes, three products per k-block (h.h + l.h + h.l) into the one accumulator:
 //           the lo planes are UNSCALED (l = fp16(x - h)); what that costs is an absolute floor of 3e-8 on tiny operands, i.e.
 //           ~1e-9 m after the 2^-10 scale-back - irrelevant here, and it keeps one accumulator per tile (a scaled lo part would
@@ -45,7 +46,7 @@
 //                      i-2 (slots tile i-1 uses are never chosen by the schedule), and after tile i-1 when the frames change
 //                      (then every slot is reloaded).
 // Same TMA / UMMA descriptor forms and TMEM protocol as umma_gemm3_kernel; the default dense forward since round 2 (measured on
-// the B200: profiles/r02g_*).  Executed on the CPU through tests/host/shim/tc_emul.h (tests/test_host_tc.py).
+// the B200: profiles/r02g_* -> r03g_*; what bounds it now - the SM's L1 / shared-memory data pipe - is in DESIGN.md 4.2).  Executed on the CPU through tests/host/shim/tc_emul.h (tests/test_host_tc.py).
 #pragma once
 #include "umma_gemm.cuh"
 #include "umma_launch.cuh"

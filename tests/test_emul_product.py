@@ -183,10 +183,11 @@ def test_rollout_outputs_kernel_pair_matches_the_torch_form(emul):
 def test_dense_lbs_kernel_forms_through_the_real_dispatch(emul):
     """humor_lbs_fwd's tensor-core path on the emulated tcgen05 kernels: the library's own dispatch AND its own TMA-descriptor
     code (cuTensorMapEncodeTiled is emulated) for the two-kernel form (1, 1) and the fused blend + group-skinning kernel on 3xTF32
-    planes (3, 1); the default (3, 5) goes through test_forms_verification_tool below.  All within 2e-5 m of the fp64 oracle."""
-    out = run_probe(emul, 'probe_lbs_forms.py', '140', '11;31', tensor=True)
+    planes (3, 1) and on all-column fp16 planes (3, 5: one shape per FRAME here, so no shaped-template rows; the per-sequence form
+    of the default goes through test_forms_verification_tool below).  All within 2e-5 m of the fp64 oracle."""
+    out = run_probe(emul, 'probe_lbs_forms.py', '140', '11;31;35', tensor=True)
     assert out['exact_vs_oracle'] < 2e-5
-    for key, want in (('forms_11', [1, 1]), ('forms_31', [3, 1])):
+    for key, want in (('forms_11', [1, 1]), ('forms_31', [3, 1]), ('forms_35', [3, 5])):
         f = out[key]
         assert f['used'] == want and f['finite'], (key, f)
         assert f['v_vs_oracle'] < 2e-5 and f['J_vs_oracle'] < 2e-5 and f['v_vs_exact'] < 5e-6, (key, f)

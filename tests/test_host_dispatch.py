@@ -26,10 +26,11 @@ def mock(built_lib, tmp_path_factory):
     return stub, lib
 
 
-def probe(mock, skin, blend, N):
+def probe(mock, skin, blend, N, *extra):
     stub, lib = mock
     env = dict(os.environ, LD_PRELOAD=stub, CUDA_VISIBLE_DEVICES='')
-    r = subprocess.run([sys.executable, os.path.join(HERE, 'host', 'mock', 'dispatch_probe.py'), ROOT, lib, str(skin), str(blend), str(N)],
+    r = subprocess.run([sys.executable, os.path.join(HERE, 'host', 'mock', 'dispatch_probe.py'), ROOT, lib, str(skin), str(blend), str(N)] +
+                       [str(e) for e in extra],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
     lines = [l for l in r.stdout.splitlines() if l.startswith('LAUNCH') or l.startswith('{')]
     assert lines and lines[-1].startswith('{'), r.stdout[-2000:]
@@ -75,6 +76,22 @@ def test_skin_form_3_is_one_persistent_kernel_for_all_frames(mock, blend):
     assert count(k, 'feat_f16_kernel') == count(k, 'lbs_shape_rows_kernel') == (1 if blend == 5 else 0)
     fg = [g for kk, g in zip(k, grids) if 'lbs_fuseg_kernel' in kk][0]
     assert fg.startswith('grid=(148,1,1)') and 'block=608' in fg and 'smem=229120' in fg, fg
+
+
+def test_per_frame_shapes_keep_every_column_in_the_product(mock):
+    """frames_per_beta < 32: no shaped-template rows (a 128-frame tile could span more sequences than the kernel stages) - the fused
+    kernel runs on the K = 256 planes, four launches."""
+    info, k, _ = probe(mock, 3, 5, 1100, 1)
+    assert info['rc'] == 0 and info['used'] == [3, 5] and info['launches'] == len(k) == 4
+    assert count(k, 'lbs_shape_rows_kernel') == 0 and count(k, 'feat_f16_kernel') == 1 and count(k, 'lbs_fuseg_kernel') == 1
+
+
+def test_model_without_skinning_records_takes_the_two_kernel_form(mock):
+    """HbLbsModel.ft_rec absent (body_model.fuseg_records returns None for a mesh whose column tiles need more entries than a record
+    buffer holds): the fused kernel is not eligible and humor_lbs_fwd runs skin form 1 - and says so."""
+    info, k, _ = probe(mock, 3, 5, 1100, 60, 'norec')
+    assert info['rc'] == 0 and info['used'] == [1, 1]
+    assert count(k, 'lbs_fuseg_kernel') == 0 and count(k, 'lbs_skin_apply_kernel') == 3
 
 
 def test_short_batches_stay_on_the_ffma_path(mock):

@@ -232,14 +232,19 @@ class LbsModel:
         bs[:, :224] = bt * 1024.0
         bh = bs.to(torch.float16)
         self.t['blend16a_h'], self.t['blend16a_l'] = bh.contiguous(), (bs - bh.float()).to(torch.float16).contiguous()
-        s.blend16a_h, s.blend16a_l = self.t['blend16a_h'].data_ptr(), self.t['blend16a_l'].data_ptr()
+        # fp16's range is a property of the asset (SMPL+H in metres: |x * 2^10| < 1300): planes that would overflow are withheld and
+        # humor_lbs_fwd then runs the fused kernel on the tf32 planes (blend form 1) instead
+        fits16 = bool(bs.abs().max() < 6.0e4)
+        if fits16:
+            s.blend16a_h, s.blend16a_l = self.t['blend16a_h'].data_ptr(), self.t['blend16a_l'].data_ptr()
         # ... and the pose columns alone (features 16..204 -> 189 columns padded to 192) for calls with one shape per >= 32 frames:
         # template + shape blend are then added per SEQUENCE by the kernel's epilogue, K drops from 256 to 192
         bp = torch.zeros(packed['v3_ld'], 192, device=self.device)
         bp[:, :189] = self.t['blend_t'][:, 16:205] * 1024.0
         ph = bp.to(torch.float16)
         self.t['blend16p_h'], self.t['blend16p_l'] = ph.contiguous(), (bp - ph.float()).to(torch.float16).contiguous()
-        s.blend16p_h, s.blend16p_l = self.t['blend16p_h'].data_ptr(), self.t['blend16p_l'].data_ptr()
+        if fits16:
+            s.blend16p_h, s.blend16p_l = self.t['blend16p_h'].data_ptr(), self.t['blend16p_l'].data_ptr()
         self.ws_slot = 0
         s.max_depth = packed['max_depth']
         s.depth, s.child_start, s.child_list = (self.t[k].data_ptr() for k in ('depth', 'child_start', 'child_list'))

@@ -97,3 +97,23 @@ def test_model_without_skinning_records_takes_the_two_kernel_form(mock):
 def test_short_batches_stay_on_the_ffma_path(mock):
     info, k, _ = probe(mock, 3, 5, 64)                         # < 128 frames: no tensor-core path, forms irrelevant
     assert info['rc'] == 0 and count(k, 'lbs_skin_fwd_kernel') >= 1 and count(k, 'lbs_fuseg_kernel') == 0
+
+
+def test_asset_outside_fp16_range_withholds_the_fp16_planes():
+    """body_model.LbsModel._build: blend planes scaled by 2^10 must fit fp16; an asset in other units (a template in millimetres) gets no
+    fp16 planes - the C-ABI then runs the fused kernel on the tf32 planes (blend form 1) - while SMPL+H in metres gets them."""
+    import numpy as np
+    import torch
+    from humor_b200 import synth
+    from humor_b200 import body_model as BM
+
+    class Probe(BM.LbsModel):
+        def __init__(self, packed):            # host memory: only the tables / planes / struct are under test
+            self._build(packed, 'cpu')
+    asset = synth.make_smplh_asset()
+    ok = Probe(BM.pack_smplh(asset, 16)).struct
+    assert ok.blend16a_h and ok.blend16a_l and ok.blend16p_h and ok.blend16p_l and (ok.flags & 1)
+    big = dict(asset)
+    big['v_template'] = np.asarray(asset['v_template']) * 1000.0
+    far = Probe(BM.pack_smplh(big, 16)).struct
+    assert not far.blend16a_h and not far.blend16p_h and far.blend_t_hi and far.ft_rec

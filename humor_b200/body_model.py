@@ -214,7 +214,7 @@ class LbsModel:
         bt = torch.zeros(packed['v3_ld'], 224, device=self.device)
         bt[:, :KF] = self.t['blend_t']
         # column 205 (a zero padding column of blend_t; the pose kernels write feature 205 = 1 into the operand planes) carries
-        # v_template: the tensor-core products return v_posed itself and no epilogue adds the template (HB_PLANES_TEMPLATE)
+        # v_template: the tensor-core products return v_posed itself and no epilogue adds the template (HB_LBS_PLANES_TEMPLATE)
         bt[:self.t['v_template'].numel(), 205] = self.t['v_template']
         s.flags = 1 | (2 if packed.get('w_rows_sum_to_one') else 0)       # HB_LBS_PLANES_TEMPLATE | HB_LBS_WEIGHTS_SUM_1
         hi = _tf32_rn(bt)
